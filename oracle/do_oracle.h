@@ -1,0 +1,76 @@
+/* do_oracle.h — CPU restatement of PCG's pairwise direct-optimization (DO) hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under pcg_b200/ may include, link or call this.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs use it, and only as the checker / the timed CPU arm.
+ *
+ * Parity status:
+ *   C-linear dialect  : PINNED  — checked against the reference's golden file
+ *                       test/data-sets/golden-tests/chel-golden-test/chel_xml.golden
+ *                       (tests/golden/chel_*.json) and fuzzed against the compiled,
+ *                       unmodified reference (oracle/_ref/libpcgdo_ref.so).
+ *   C-affine dialect  : parity unpinned (reference has no golden vector; checked only
+ *                       against oracle/_ref, whose affine code has undefined behaviour).
+ *
+ * All reference citations are relative to /root/reference/.
+ *   EXT = lib/core/ffi/external-direct-optimization
+ *   DO  = lib/core/analysis/src/Analysis/Parsimony/Dynamic/DirectOptimization
+ *   DYN = lib/core/data-structures/src/Bio/Character/Encodable/Dynamic
+ */
+#ifndef PCG_DO_ORACLE_H
+#define PCG_DO_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Dense 2^a x 2^a cost / median tables (EXT/c_code_alloc_setup.c:110-205). */
+typedef struct oracle_tcm {
+    int       a;        /* alphabet size including the gap symbol          */
+    uint32_t  dim;      /* 1 << a                                          */
+    uint32_t  gap;      /* 1 << (a-1)                                      */
+    uint32_t  gap_open; /* 0 = linear                                      */
+    uint32_t *cost;     /* cost  [(e1 << a) + e2]                          */
+    uint32_t *median;   /* median[(e1 << a) + e2]                          */
+} oracle_tcm_t;
+
+oracle_tcm_t *oracle_tcm_new(const uint32_t *sigma /* a*a row-major */, int a, uint32_t gap_open);
+void          oracle_tcm_free(oracle_tcm_t *t);
+
+/* Band geometry of align2d (EXT/c_alignment_interface.c:101-109, EXT/alignCharacters.c:1163-1374).
+ * lg / sh INCLUDE the prepended gap.  mode: 0 full, 2 = case 2, 3 = case 3 subset 3.
+ * lo/hi (each lg entries) receive the inclusive column interval of every row;
+ * right_ukk[i] = 1 when row i's last cell has no DELETE option. Returns #cells filled. */
+uint64_t oracle_band_rows(size_t lg, size_t sh, int *mode, int32_t *lo, int32_t *hi, uint8_t *right_ukk);
+
+/* Raw align2d (EXT/c_alignment_interface.c:16-177) with flags (0,1,0).
+ * in1 / in2: element strings WITHOUT the leading gap.  Outputs (natural order, length *out_len):
+ *   out_gapped : gapped medians
+ *   out_slot1  : what the reference leaves in inputChar1's buffer
+ *   out_slot2  : what the reference leaves in inputChar2's buffer
+ *     (the slot of the LONGER input receives the aligned SHORTER string, 0 = gap)
+ * cells (optional) receives the number of DP cells the reference algorithm fills. */
+int64_t oracle_align2d(const oracle_tcm_t *t,
+                       const uint32_t *in1, size_t n1,
+                       const uint32_t *in2, size_t n2,
+                       uint32_t *out_gapped, uint32_t *out_slot1, uint32_t *out_slot2,
+                       size_t *out_len, uint64_t *cells);
+
+/* Haskell wrapper common to every dialect:
+ * DO/Pairwise/FFI.hsc:222-260 (algn2d), DO/Pairwise/Internal.hs:307-381,
+ * DYN/Internal.hs:135-241 (deleteGaps / insertGaps), DYN/Element.hs:127-153.
+ * A dynamic character is three parallel arrays (median,left,right) + a missing flag.
+ * Output arrays need capacity n1+n2. Returns the cost. */
+int64_t oracle_foreign_pairwise_do(const oracle_tcm_t *t,
+                                   const uint32_t *m1, const uint32_t *l1, const uint32_t *r1, size_t n1, int missing1,
+                                   const uint32_t *m2, const uint32_t *l2, const uint32_t *r2, size_t n2, int missing2,
+                                   uint32_t *om, uint32_t *ol, uint32_t *orr, size_t *on, int *omissing,
+                                   uint64_t *cells);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,198 @@
+"""ctypes loaders for the CPU oracle (TEST INFRASTRUCTURE ONLY — never imported by pcg_b200).
+
+Two checkers live here:
+
+* ``Oracle``      — ``oracle/liboracle_do.so``, our plain-C restatement (``do_oracle.c``).
+* ``Reference``   — ``oracle/_ref/libpcgdo_ref.so``, the UNMODIFIED reference C aligner compiled
+                    from ``/root/reference/lib/core/ffi/external-direct-optimization`` by
+                    ``oracle/Makefile`` (target ``ref``).  Driven exactly like the Haskell binding
+                    does (``DO/Pairwise/FFI.hsc:272-290, 474-515``): malloc'ed ``alignIO_t`` buffers
+                    of capacity ``len1+len2+2`` with the payload right-aligned.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "liboracle_do.so")
+REF_SO = os.path.join(_HERE, "_ref", "libpcgdo_ref.so")
+REF_MEMO_SO = os.path.join(_HERE, "_ref", "libtcmmemo_ref.so")
+
+_u32p = C.POINTER(C.c_uint32)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the restatement (always) and, if the reference tree is present, ``_ref``."""
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    if ref and os.path.isdir("/root/reference") and not os.path.exists(REF_SO):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def _as_u32(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint32))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_u32p)
+
+
+class Oracle:
+    """The C restatement (``do_oracle.c``)."""
+
+    def __init__(self, sigma, gap_open: int = 0):
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        L.oracle_tcm_new.restype = C.c_void_p
+        L.oracle_tcm_new.argtypes = [_u32p, C.c_int, C.c_uint32]
+        L.oracle_tcm_free.argtypes = [C.c_void_p]
+        L.oracle_align2d.restype = C.c_int64
+        L.oracle_align2d.argtypes = [C.c_void_p, _u32p, C.c_size_t, _u32p, C.c_size_t,
+                                     _u32p, _u32p, _u32p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+        L.oracle_foreign_pairwise_do.restype = C.c_int64
+        L.oracle_foreign_pairwise_do.argtypes = (
+            [C.c_void_p] + [_u32p, _u32p, _u32p, C.c_size_t, C.c_int] * 2
+            + [_u32p, _u32p, _u32p, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_uint64)])
+        L.oracle_band_rows.restype = C.c_uint64
+        L.oracle_band_rows.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]
+        sigma = _as_u32(sigma)
+        self.a = int(sigma.shape[0])
+        assert sigma.shape == (self.a, self.a)
+        self.gap = 1 << (self.a - 1)
+        self.sigma = sigma
+        self.t = L.oracle_tcm_new(_ptr(sigma), self.a, gap_open)
+
+        class _T(C.Structure):
+            _fields_ = [("a", C.c_int), ("dim", C.c_uint32), ("gap", C.c_uint32), ("gap_open", C.c_uint32),
+                        ("cost", _u32p), ("median", _u32p)]
+        tt = C.cast(self.t, C.POINTER(_T)).contents
+        dim = 1 << self.a
+        self.cost = np.ctypeslib.as_array(tt.cost, shape=(dim, dim)).copy()
+        self.median = np.ctypeslib.as_array(tt.median, shape=(dim, dim)).copy()
+
+    def __del__(self):
+        try:
+            self.lib.oracle_tcm_free(self.t)
+        except Exception:
+            pass
+
+    def band_cells(self, lg: int, sh: int):
+        """(#cells, mode) for strings of lg/sh elements INCLUDING the leading gap."""
+        mode = C.c_int(0)
+        n = self.lib.oracle_band_rows(lg, sh, C.byref(mode), None, None, None)
+        return int(n), int(mode.value)
+
+    def align2d(self, in1, in2):
+        """Raw ``align2d(...,0,1,0)``. Returns (cost, gapped, slot1, slot2, cells)."""
+        a1, a2 = _as_u32(in1), _as_u32(in2)
+        cap = len(a1) + len(a2) + 2
+        g, s1, s2 = (np.zeros(cap, np.uint32) for _ in range(3))
+        n = C.c_size_t(0)
+        cells = C.c_uint64(0)
+        cost = self.lib.oracle_align2d(self.t, _ptr(a1), len(a1), _ptr(a2), len(a2),
+                                       _ptr(g), _ptr(s1), _ptr(s2), C.byref(n), C.byref(cells))
+        k = n.value
+        return int(cost), g[:k].copy(), s1[:k].copy(), s2[:k].copy(), int(cells.value)
+
+    def pairwise_do(self, c1, c2):
+        """Haskell-level ``foreignPairwiseDO``. A character is ``None`` (Missing) or an (n,3) array of
+        (median,left,right). Returns (cost, character-or-None, cells)."""
+        def split(c):
+            if c is None:
+                z = np.zeros(1, np.uint32)
+                return z, z, z, 0, 1
+            c = _as_u32(c).reshape(-1, 3)
+            return (np.ascontiguousarray(c[:, 0]), np.ascontiguousarray(c[:, 1]),
+                    np.ascontiguousarray(c[:, 2]), len(c), 0)
+        m1, l1, r1, n1, x1 = split(c1)
+        m2, l2, r2, n2, x2 = split(c2)
+        cap = n1 + n2 + 2
+        om, ol, orr = (np.zeros(cap, np.uint32) for _ in range(3))
+        on = C.c_size_t(0)
+        omiss = C.c_int(0)
+        cells = C.c_uint64(0)
+        cost = self.lib.oracle_foreign_pairwise_do(
+            self.t, _ptr(m1), _ptr(l1), _ptr(r1), n1, x1, _ptr(m2), _ptr(l2), _ptr(r2), n2, x2,
+            _ptr(om), _ptr(ol), _ptr(orr), C.byref(on), C.byref(omiss), C.byref(cells))
+        if omiss.value:
+            return int(cost), None, int(cells.value)
+        k = on.value
+        return int(cost), np.stack([om[:k], ol[:k], orr[:k]], axis=1), int(cells.value)
+
+
+class _AlignIO(C.Structure):
+    _fields_ = [("character", _u32p), ("length", C.c_size_t), ("capacity", C.c_size_t)]
+
+
+class Reference:
+    """The compiled, unmodified reference aligner (``oracle/_ref/libpcgdo_ref.so``)."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def __init__(self, sigma, gap_open: int = 0):
+        self.lib = C.CDLL(REF_SO)
+        self.libc = C.CDLL(None)
+        self.libc.malloc.restype = C.c_void_p
+        self.libc.malloc.argtypes = [C.c_size_t]
+        self.libc.free.argtypes = [C.c_void_p]
+        sigma = _as_u32(sigma)
+        self.a = int(sigma.shape[0])
+        self.gap = 1 << (self.a - 1)
+        self.cm = C.create_string_buffer(256)       # cost_matrices_2d_t (EXT/costMatrix.h:35-93) fits
+        self.lib.setUp2dCostMtx.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_uint]
+        self.lib.setUp2dCostMtx(self.cm, _ptr(sigma), self.a, gap_open)
+        self.lib.align2d.restype = C.c_int
+        self.lib.align2d.argtypes = [C.POINTER(_AlignIO)] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.lib.align2dAffine.restype = C.c_int
+        self.lib.align2dAffine.argtypes = [C.POINTER(_AlignIO)] * 4 + [C.c_void_p, C.c_int]
+
+    def tables(self):
+        """(cost, median) dense tables as the reference built them."""
+        class _CM(C.Structure):
+            _fields_ = [("alphSize", C.c_size_t), ("costMatrixDimension", C.c_size_t), ("gap_char", C.c_uint),
+                        ("cost_model_type", C.c_int), ("include_ambiguities", C.c_int),
+                        ("gap_open_cost", C.c_uint), ("is_metric", C.c_int), ("num_elements", C.c_size_t),
+                        ("cost", _u32p), ("median", _u32p), ("worst", _u32p),
+                        ("prepend_cost", _u32p), ("tail_cost", _u32p)]
+        cm = C.cast(self.cm, C.POINTER(_CM)).contents
+        dim = 1 << self.a
+        return (np.ctypeslib.as_array(cm.cost, shape=(dim, dim)).copy(),
+                np.ctypeslib.as_array(cm.median, shape=(dim, dim)).copy())
+
+    def _aio(self, vals, cap):
+        """allocInitAlign_io (FFI.hsc:474-481): malloc'ed buffer, payload in the LAST len slots."""
+        n = len(vals)
+        buf = self.libc.malloc(cap * 4)
+        arr = (C.c_uint32 * cap).from_address(buf)
+        C.memset(buf, 0, cap * 4)
+        for i, v in enumerate(vals):
+            arr[cap - n + i] = int(v)
+        return _AlignIO(C.cast(buf, _u32p), n, cap)
+
+    def _take(self, aio):
+        off = aio.capacity - aio.length
+        out = np.array([aio.character[off + i] for i in range(aio.length)], dtype=np.uint32)
+        self.libc.free(C.cast(aio.character, C.c_void_p))
+        return out
+
+    def align2d(self, in1, in2, affine: bool = False):
+        cap = len(in1) + len(in2) + 2
+        a1, a2 = self._aio(in1, cap), self._aio(in2, cap)
+        g, u = self._aio([], cap), self._aio([], cap)
+        if affine:
+            cost = self.lib.align2dAffine(C.byref(a1), C.byref(a2), C.byref(g), C.byref(u), self.cm, 1)
+        else:
+            cost = self.lib.align2d(C.byref(a1), C.byref(a2), C.byref(g), C.byref(u), self.cm, 0, 1, 0)
+        s1, s2, gg = self._take(a1), self._take(a2), self._take(g)
+        self.libc.free(C.cast(u.character, C.c_void_p))
+        return int(cost), gg, s1, s2
