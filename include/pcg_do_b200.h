@@ -1,0 +1,140 @@
+/* pcg_do_b200.h — C ABI of the B200-native direct-optimization (DO) backend.
+ *
+ * Drop-in boundary for PCG's pairwise DO path: plain C types only (no torch, no CUDA types in
+ * the signatures).  Two groups of entry points:
+ *
+ *  (1) REFERENCE-COMPATIBLE symbols — same name, argument order, struct layout and ownership
+ *      rules as the C objects PCG's Haskell code binds today, so the existing
+ *      `foreign import ccall` declarations keep working against this library:
+ *        setUp2dCostMtx  <- EXT/c_code_alloc_setup.h / .c:110-205   (bound at Data/TCM/Dense/FFI.hsc:319-334)
+ *        align2d         <- EXT/c_alignment_interface.h:29-38, .c:16-177 (bound at DO/Pairwise/FFI.hsc:122-132)
+ *      (EXT = /root/reference/lib/core/ffi/external-direct-optimization,
+ *       DO  = /root/reference/lib/core/analysis/src/Analysis/Parsimony/Dynamic/DirectOptimization)
+ *      They run a batch of one pair through the GPU.  Correct, never fast: the FFI call, two
+ *      copies and a launch per pair dominate.
+ *
+ *  (2) BATCHED entry points (`pcgdo_*`) — what a `foreignPairwiseDOBatch`-style binding and the
+ *      post-order level scheduler call: many pairs per launch, data either in host buffers
+ *      (copies inside the call) or already resident in HBM.
+ *
+ * There is NO CPU fallback: every entry point fails loudly (non-zero return / abort for the
+ * reference-compatible `int cost` signatures) when no CUDA device is usable.
+ */
+#ifndef PCG_DO_B200_H
+#define PCG_DO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- reference-compatible types */
+
+typedef unsigned int elem_t;                       /* EXT/dyn_character.h:30 */
+
+/* EXT/c_alignment_interface.h:14-18 — payload lives in the LAST `length` slots of `character`. */
+typedef struct alignIO_t {
+    elem_t *character;
+    size_t  length;
+    size_t  capacity;
+} alignIO_t;
+
+/* EXT/costMatrix.h:35-93 — field order and types must not change (hsc #peek/#poke at
+ * Data/TCM/Dense/FFI.hsc:170-233 read alphSize, cost_model_type, cost, median directly). */
+typedef struct cost_matrices_2d_t {
+    size_t        alphSize;
+    size_t        costMatrixDimension;
+    elem_t        gap_char;
+    int           cost_model_type;
+    int           include_ambiguities;
+    unsigned int  gap_open_cost;
+    int           is_metric;
+    size_t        num_elements;
+    unsigned int *cost;
+    elem_t       *median;
+    unsigned int *worst;
+    unsigned int *prepend_cost;
+    unsigned int *tail_cost;
+} cost_matrices_2d_t;
+
+/* Builds the dense 2^a x 2^a cost / median tables on the host (same loops and the same
+ * sigma[pos*a + nucleotide] indexing as the reference) into caller-provided storage. */
+void setUp2dCostMtx(cost_matrices_2d_t *retMtx, unsigned int *tcm, size_t alphSize, unsigned int gap_open);
+
+/* Pairwise DO of one pair on the GPU.  Same contract as the reference's align2d for the flag
+ * combination PCG uses (getUngapped=0, getGapped=1, getUnion=0): on return
+ *   inputChar1_aio / inputChar2_aio hold the two aligned strings (the slot of the LONGER input
+ *   receives the aligned SHORTER string, gaps as 0), gappedOutput_aio the gapped medians,
+ *   all right-aligned with `length` updated; the return value is the alignment cost.
+ * getUngapped / getUnion other than 0 abort (PCG never passes them). */
+int align2d(alignIO_t *inputChar1_aio, alignIO_t *inputChar2_aio,
+            alignIO_t *gappedOutput_aio, alignIO_t *ungappedOutput_aio,
+            cost_matrices_2d_t *costMtx2d, int getUngapped, int getGapped, int getUnion);
+
+/* ---------------------------------------------------------------- batched API */
+
+typedef struct pcgdo_ctx pcgdo_ctx;     /* one per (process, GPU): streams, scratch, work counters */
+typedef struct pcgdo_tcm pcgdo_tcm;     /* device copy of one dense TCM                            */
+
+enum {
+    PCGDO_OK = 0,
+    PCGDO_ERR_CUDA = 1,          /* no device / CUDA call failed (message in pcgdo_last_error) */
+    PCGDO_ERR_ARG = 2,
+    PCGDO_ERR_UNSUPPORTED = 3,   /* alphabet > 8, TCM cost too large for the 16-bit device table, ... */
+    PCGDO_ERR_OVERFLOW = 4       /* a pair needs more scratch than the configured slot size   */
+};
+
+int         pcgdo_create(pcgdo_ctx **out, int device);
+void        pcgdo_destroy(pcgdo_ctx *ctx);
+const char *pcgdo_last_error(const pcgdo_ctx *ctx);
+
+/* Tunables (call before the first batch; 0 keeps the default).
+ *   pairs_per_warp : pairs a warp fills back-to-back before tracing them lane-parallel (1..32)
+ *   warps_per_cta  : 1..32
+ *   max_len        : longest string (elements, without the leading gap) the fast path must hold
+ *                    in shared memory; longer pairs take the general-geometry kernel            */
+int pcgdo_configure(pcgdo_ctx *ctx, int pairs_per_warp, int warps_per_cta, int max_len);
+
+/* sigma: a*a row-major symbol-change costs, gap is symbol a-1.  a <= 8. */
+int  pcgdo_tcm_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, unsigned int gap_open, pcgdo_tcm **out);
+void pcgdo_tcm_destroy(pcgdo_ctx *ctx, pcgdo_tcm *tcm);
+
+/* One batch of raw align2d problems.  Elements are one byte each (a <= 8).
+ * Pair k: first string = elems[off1[k] .. off1[k]+len1[k]), second likewise (no leading gap).
+ * Outputs for pair k start at byte out_off[k] (must be a multiple of 4, with room for
+ * round_up(len1[k]+len2[k], 4) bytes) of each of out_gapped / out_slot1 / out_slot2
+ * (same meaning as align2d's gappedOutput / inputChar1 / inputChar2 after the call);
+ * out_len[k] = alignment length, cost[k] = alignment cost, cells[k] (may be NULL) = DP cells of
+ * the reference algorithm's band for that pair.  out_slot1/out_slot2/out_gapped may be NULL
+ * (cost-only).  All pointers are DEVICE pointers for *_device, HOST pointers for *_host. */
+typedef struct pcgdo_batch {
+    size_t          n_pairs;
+    const uint8_t  *elems;
+    size_t          elems_bytes;     /* host variant: bytes to copy in                      */
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    const uint64_t *out_off;
+    size_t          out_bytes;       /* host variant: bytes to copy back per output array   */
+    uint8_t        *out_gapped, *out_slot1, *out_slot2;
+    uint32_t       *out_len;
+    int32_t        *cost;
+    uint64_t       *cells;
+} pcgdo_batch;
+
+/* Enqueue on `cuda_stream` (a cudaStream_t passed as void*, NULL = the context's stream);
+ * asynchronous unless a pair overflows the fast path's scratch. */
+int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream);
+
+/* Host buffers in, host buffers out: H2D copies, kernels and D2H copies inside the call. */
+int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b);
+
+/* Timing of the kernels of the most recent *_device / *_host call on this context, measured with
+ * CUDA events on the launching stream (ms); also the number of kernel launches it made. */
+int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCG_DO_B200_H */

@@ -1,0 +1,158 @@
+"""ctypes binding of the C-ABI CUDA library (include/pcg_do_b200.h).
+
+There is no CPU fallback: importing works anywhere (so the symbol/ABI tests can run without a
+GPU), but creating a context raises unless a CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_i32p = C.POINTER(C.c_int32)
+
+# every symbol include/pcg_do_b200.h declares
+EXPORTED_SYMBOLS = [
+    "setUp2dCostMtx", "align2d",
+    "pcgdo_create", "pcgdo_destroy", "pcgdo_last_error", "pcgdo_configure",
+    "pcgdo_tcm_create", "pcgdo_tcm_destroy",
+    "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
+]
+
+
+class AlignIO(C.Structure):
+    """alignIO_t (reference: c_alignment_interface.h:14-18)."""
+    _fields_ = [("character", _u32p), ("length", C.c_size_t), ("capacity", C.c_size_t)]
+
+
+class CostMatrices2D(C.Structure):
+    """cost_matrices_2d_t (reference: costMatrix.h:35-93)."""
+    _fields_ = [("alphSize", C.c_size_t), ("costMatrixDimension", C.c_size_t), ("gap_char", C.c_uint),
+                ("cost_model_type", C.c_int), ("include_ambiguities", C.c_int), ("gap_open_cost", C.c_uint),
+                ("is_metric", C.c_int), ("num_elements", C.c_size_t), ("cost", _u32p), ("median", _u32p),
+                ("worst", _u32p), ("prepend_cost", _u32p), ("tail_cost", _u32p)]
+
+
+class Batch(C.Structure):
+    """pcgdo_batch."""
+    _fields_ = [("n_pairs", C.c_size_t), ("elems", C.c_void_p), ("elems_bytes", C.c_size_t),
+                ("off1", C.c_void_p), ("off2", C.c_void_p), ("len1", C.c_void_p), ("len2", C.c_void_p),
+                ("out_off", C.c_void_p), ("out_bytes", C.c_size_t),
+                ("out_gapped", C.c_void_p), ("out_slot1", C.c_void_p), ("out_slot2", C.c_void_p),
+                ("out_len", C.c_void_p), ("cost", C.c_void_p), ("cells", C.c_void_p)]
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen the library (building it first if needed). Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise BackendError(f"{path} is missing: the CUDA extension has not been built")
+        _build.build()
+    L = C.CDLL(path)
+    L.pcgdo_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.pcgdo_destroy.argtypes = [C.c_void_p]
+    L.pcgdo_last_error.restype = C.c_char_p
+    L.pcgdo_last_error.argtypes = [C.c_void_p]
+    L.pcgdo_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.pcgdo_configure_ex.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+    L.pcgdo_tcm_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_uint, C.POINTER(C.c_void_p)]
+    L.pcgdo_tcm_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_align2d_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch), C.c_void_p]
+    L.pcgdo_align2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
+    L.pcgdo_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.setUp2dCostMtx.argtypes = [C.POINTER(CostMatrices2D), _u32p, C.c_size_t, C.c_uint]
+    L.setUp2dCostMtx.restype = None
+    L.align2d.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int, C.c_int, C.c_int]
+    L.align2d.restype = C.c_int
+    _lib = L
+    return L
+
+
+class Context:
+    """One GPU context (pcgdo_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.pcgdo_create(C.byref(h), device)
+        if rc != 0 or not h.value:
+            raise BackendError(f"pcgdo_create(device={device}) failed with code {rc}: "
+                               "a CUDA device is required (no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.pcgdo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise BackendError(f"{what} failed ({rc}): {self.lib.pcgdo_last_error(self.h).decode()}")
+
+    def configure(self, pairs_per_warp=0, warps_per_cta=0, max_len=0, max_b=0, arena_words=0):
+        self.check(self.lib.pcgdo_configure(self.h, pairs_per_warp, warps_per_cta, max_len), "pcgdo_configure")
+        self.check(self.lib.pcgdo_configure_ex(self.h, max_b, arena_words), "pcgdo_configure_ex")
+
+    def tcm(self, sigma, gap_open: int = 0) -> "Tcm":
+        return Tcm(self, sigma, gap_open)
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        self.check(self.lib.pcgdo_last_kernel_ms(self.h, C.byref(ms), C.byref(n)), "pcgdo_last_kernel_ms")
+        return float(ms.value), int(n.value)
+
+
+class Tcm:
+    def __init__(self, ctx: Context, sigma, gap_open: int = 0):
+        self.ctx = ctx
+        sigma = np.ascontiguousarray(np.asarray(sigma, dtype=np.uint32))
+        self.a = int(sigma.shape[0])
+        assert sigma.shape == (self.a, self.a)
+        self.gap = 1 << (self.a - 1)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.pcgdo_tcm_create(ctx.h, sigma.ctypes.data_as(_u32p), self.a, gap_open, C.byref(h)),
+                  "pcgdo_tcm_create")
+        self.h = h
+        # dense host tables from the library's own host code (setUp2dCostMtx), for the wrapper's
+        # "one string empty" case and for callers that want lookupPairwise
+        cm = CostMatrices2D()
+        ctx.lib.setUp2dCostMtx(C.byref(cm), sigma.ctypes.data_as(_u32p), self.a, gap_open)
+        dim = 1 << self.a
+        self.cost = np.ctypeslib.as_array(cm.cost, shape=(dim, dim)).copy()
+        self.median = np.ctypeslib.as_array(cm.median, shape=(dim, dim)).copy()
+        self.median_of_gap = self.median[:, self.gap].astype(np.uint8)
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        for f in ("cost", "median", "worst", "prepend_cost", "tail_cost"):
+            libc.free(C.cast(getattr(cm, f), C.c_void_p))
+
+    def __del__(self):
+        try:
+            if self.h.value and self.ctx.h.value:
+                self.ctx.lib.pcgdo_tcm_destroy(self.ctx.h, self.h)
+        except Exception:
+            pass

@@ -1,0 +1,470 @@
+// do_api.cu — C ABI of the DO backend (include/pcg_do_b200.h): context, TCM upload, batched
+// launches, and the reference-compatible single-pair shims.
+#include "do_device.cuh"
+#include "do_host.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace pcgdo {
+cudaError_t launch_linear(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+}
+using namespace pcgdo;
+
+struct pcgdo_tcm {
+    TcmDev dev{};
+    size_t a = 0;
+    unsigned int gap_open = 0;
+    void *d_sub4 = nullptr, *d_median = nullptr, *d_cgap = nullptr, *d_gapc = nullptr;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct pcgdo_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int last_launches = 0;
+    // tunables
+    int pairs_per_warp = 32;
+    int warps_per_cta = 16;
+    int max_len = 1024;
+    int max_b = 8;
+    size_t arena_words = 0;          // 0 = derive from max_len
+    // device scratch
+    DevBuf arena, counters, overflow;
+    // staging for the host-buffer entry point
+    DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
+    std::string err;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return PCGDO_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+static int ensure(pcgdo_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return PCGDO_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_create(pcgdo_ctx **out, int device)
+{
+    if (!out) return PCGDO_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fprintf(stderr, "pcgdo_create: no usable CUDA device (%s); this library has no CPU fallback\n",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return PCGDO_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) return PCGDO_ERR_ARG;
+    pcgdo_ctx *ctx = new pcgdo_ctx();
+    ctx->device = device;
+    auto fail = [&](const char *what, cudaError_t ee) {
+        fprintf(stderr, "pcgdo_create: %s: %s\n", what, cudaGetErrorString(ee));
+        delete ctx;
+        return PCGDO_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        fprintf(stderr, "pcgdo_create: device %d is sm_%d%d; this library is built for sm_100a only\n", device,
+                prop.major, prop.minor);
+        delete ctx;
+        return PCGDO_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("event", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("event", e);
+    *out = ctx;
+    return PCGDO_OK;
+}
+
+extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+                      &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
+                      &ctx->d_olen, &ctx->d_cost, &ctx->d_cells};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *pcgdo_last_error(const pcgdo_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pcgdo_configure(pcgdo_ctx *ctx, int pairs_per_warp, int warps_per_cta, int max_len)
+{
+    if (!ctx) return PCGDO_ERR_ARG;
+    if (pairs_per_warp) {
+        if (pairs_per_warp < 1 || pairs_per_warp > 32) return PCGDO_ERR_ARG;
+        ctx->pairs_per_warp = pairs_per_warp;
+    }
+    if (warps_per_cta) {
+        if (warps_per_cta < 1 || warps_per_cta > 16) return PCGDO_ERR_ARG;
+        ctx->warps_per_cta = warps_per_cta;
+    }
+    if (max_len) {
+        if (max_len < 1) return PCGDO_ERR_ARG;
+        ctx->max_len = max_len;
+    }
+    return PCGDO_OK;
+}
+
+// Optional finer control (not part of the reference-facing surface, used by tests / bench):
+// widest diagonals-per-lane variant the shared-memory window must accommodate, arena size.
+extern "C" int pcgdo_configure_ex(pcgdo_ctx *ctx, int max_b, size_t arena_words)
+{
+    if (!ctx) return PCGDO_ERR_ARG;
+    if (max_b) {
+        if (max_b != 2 && max_b != 4 && max_b != 8 && max_b != 16 && max_b != 32) return PCGDO_ERR_ARG;
+        ctx->max_b = max_b;
+    }
+    ctx->arena_words = arena_words;
+    return PCGDO_OK;
+}
+
+// --------------------------------------------------------------------------------------------- TCM
+
+static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, const unsigned int *cost,
+                           const unsigned int *median, pcgdo_tcm **out)
+{
+    if (a < 2 || a > 8) {
+        ctx->err = "alphabet size must be 2..8 for the dense-table path";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t dim = (size_t)1 << a;
+    const unsigned int gap = 1u << (a - 1);
+    auto C = [&](size_t x, size_t y) { return (long long)cost[(x << a) + y]; };
+    const bool repl = a <= 5;
+    const size_t rdim = repl ? 32 : dim;             // replicated layout always uses a 32 x 32 table
+    std::vector<int16_t> nat(rdim * rdim, (int16_t)kBigSub);
+    for (size_t l = 1; l < dim; ++l)
+        for (size_t s = 1; s < dim; ++s) {
+            const long long v = 4 * (C(l, s) - C(l, gap) - C(gap, s)) - 1;
+            if (v < -32000 || v >= kBigSub) {
+                ctx->err = "TCM costs too large for the 16-bit device table";
+                return PCGDO_ERR_UNSUPPORTED;
+            }
+            nat[l * rdim + s] = (int16_t)v;
+        }
+    std::vector<int16_t> tab;
+    if (repl) {
+        // 32 copies, copy k entirely in shared-memory bank k: entry e of copy k at byte
+        // (e >> 1) * 128 + k * 4 + (e & 1) * 2
+        tab.assign(32 * 1024, 0);
+        for (size_t k = 0; k < 32; ++k)
+            for (size_t e = 0; e < 1024; ++e) tab[((e >> 1) * 128 + k * 4 + (e & 1) * 2) / 2] = nat[e];
+    } else {
+        tab = nat;
+    }
+    std::vector<uint8_t> med(dim * dim, 0);
+    std::vector<uint32_t> cgap(dim, 0), gapc(dim, 0);
+    for (size_t i = 0; i < dim * dim; ++i) med[i] = (uint8_t)median[i];
+    for (size_t x = 1; x < dim; ++x) { cgap[x] = cost[(x << a) + gap]; gapc[x] = cost[((size_t)gap << a) + x]; }
+
+    pcgdo_tcm *t = new pcgdo_tcm();
+    t->a = a;
+    t->gap_open = gap_open;
+    auto up = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    CK(up(&t->d_sub4, tab.data(), tab.size() * 2));
+    CK(up(&t->d_median, med.data(), med.size()));
+    CK(up(&t->d_cgap, cgap.data(), cgap.size() * 4));
+    CK(up(&t->d_gapc, gapc.data(), gapc.size() * 4));
+    t->dev.a = (int)a;
+    t->dev.repl = repl ? 1 : 0;
+    t->dev.gap = gap;
+    t->dev.sub4_bytes = (uint32_t)(tab.size() * 2);
+    t->dev.sub4_gapgap = (int32_t)(4 * (C(gap, gap) - C(gap, gap) - C(gap, gap)) - 1);
+    t->dev.sub4 = (const int16_t *)t->d_sub4;
+    t->dev.median = (const uint8_t *)t->d_median;
+    t->dev.cgap = (const uint32_t *)t->d_cgap;
+    t->dev.gapc = (const uint32_t *)t->d_gapc;
+    *out = t;
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_tcm_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, unsigned int gap_open,
+                                pcgdo_tcm **out)
+{
+    if (!ctx || !sigma || !out) return PCGDO_ERR_ARG;
+    if (a < 2 || a > 8) {
+        ctx->err = "alphabet size must be 2..8 for the dense-table path";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    const size_t dim = (size_t)1 << a;
+    std::vector<unsigned int> cost(dim * dim, 0), median(dim * dim, 0);
+    build_dense_tables(sigma, a, cost.data(), median.data());
+    return tcm_from_tables(ctx, a, gap_open, cost.data(), median.data(), out);
+}
+
+extern "C" void pcgdo_tcm_destroy(pcgdo_ctx *ctx, pcgdo_tcm *t)
+{
+    if (!t) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(t->d_sub4);
+    cudaFree(t->d_median);
+    cudaFree(t->d_cgap);
+    cudaFree(t->d_gapc);
+    delete t;
+}
+
+// --------------------------------------------------------------------------------------------- batches
+
+static size_t smem_for(const pcgdo_ctx *ctx, const pcgdo_tcm *tcm, int warps, uint32_t seq_cap)
+{
+    const size_t dim = (size_t)1 << tcm->a;
+    return tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps * (384 + 2 * (size_t)seq_cap);
+}
+
+extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream)
+{
+    if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost) {
+        ctx->err = "bad batch description";
+        return PCGDO_ERR_ARG;
+    }
+    if ((b->out_gapped || b->out_slot1 || b->out_slot2) && !b->out_off) {
+        ctx->err = "out_off required when aligned strings are requested";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+
+    // shared-memory window per warp: both strings + paddings for the widest variant allowed
+    uint32_t seq_cap = (uint32_t)(2 * ctx->max_len + 80 * ctx->max_b + 96) & ~1u;
+    int warps = ctx->warps_per_cta;
+    while (warps > 1 && smem_for(ctx, tcm, warps, seq_cap) > 227 * 1024) --warps;
+    const size_t smem = smem_for(ctx, tcm, warps, seq_cap);
+    if (smem > 227 * 1024) {
+        ctx->err = "max_len too large for the shared-memory staging window";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    const int grid = ctx->sm_count;
+    size_t arena_words = ctx->arena_words;
+    if (!arena_words) {
+        // room for pairs_per_warp near-equal-length pairs of max_len
+        const size_t b_typ = (size_t)ctx->max_b;
+        arena_words = (size_t)ctx->pairs_per_warp * (((size_t)ctx->max_len + 17) / 16 * 32 * b_typ + ctx->max_len / 8 + 8);
+    }
+    arena_words = (arena_words + 3) & ~(size_t)3;
+    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
+    int rc;
+    if ((rc = ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->counters, 64))) return rc;
+    if ((rc = ensure(ctx, ctx->overflow, b->n_pairs * 4))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+
+    LinearParams p{};
+    p.tcm = tcm->dev;
+    p.b.n_pairs = (uint32_t)b->n_pairs;
+    p.b.elems = b->elems;
+    p.b.off1 = b->off1; p.b.off2 = b->off2;
+    p.b.len1 = b->len1; p.b.len2 = b->len2;
+    p.b.out_off = b->out_off;
+    p.b.out_gapped = b->out_gapped; p.b.out_slot1 = b->out_slot1; p.b.out_slot2 = b->out_slot2;
+    p.b.out_len = b->out_len;
+    p.b.cost = b->cost;
+    p.b.cells = b->cells;
+    p.arena = (uint32_t *)ctx->arena.p;
+    p.arena_words = (uint32_t)arena_words;
+    p.seq_cap = seq_cap;
+    p.pairs_per_warp = ctx->pairs_per_warp;
+    p.counter = (unsigned int *)ctx->counters.p;
+    p.overflow_count = p.counter + 1;
+    p.overflow_list = (uint32_t *)ctx->overflow.p;
+
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_linear(p, grid, warps * 32, smem, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    ctx->last_launches = 1;
+
+    // pairs the warp kernel could not hold (band wider than 1024 diagonals, strings longer than the
+    // staging window, scratch larger than the arena) are reported, not silently dropped
+    unsigned int h_over = 0;
+    CK(cudaMemcpyAsync(&h_over, p.overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_over) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "%u pair(s) exceed the fast path's limits (max_len=%d, max_b=%d); raise them with pcgdo_configure",
+                 h_over, ctx->max_len, ctx->max_b);
+        ctx->err = msg;
+        return PCGDO_ERR_OVERFLOW;
+    }
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches)
+{
+    if (!ctx) return PCGDO_ERR_ARG;
+    if (launches) *launches = ctx->last_launches;
+    if (ms) {
+        *ms = 0.f;
+        if (ctx->timed) {
+            CK(cudaEventSynchronize(ctx->ev1));
+            CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+        }
+    }
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b)
+{
+    if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = b->n_pairs;
+    const bool want_str = b->out_gapped || b->out_slot1 || b->out_slot2;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_elems, b->elems_bytes + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->d_off1, n * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_off2, n * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_len1, n * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_len2, n * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cost, n * 4))) return rc;
+    if (b->out_len && (rc = ensure(ctx, ctx->d_olen, n * 4))) return rc;
+    if (b->cells && (rc = ensure(ctx, ctx->d_cells, n * 8))) return rc;
+    if (want_str) {
+        if ((rc = ensure(ctx, ctx->d_out_off, n * 8))) return rc;
+        if (b->out_gapped && (rc = ensure(ctx, ctx->d_og, b->out_bytes + 16))) return rc;
+        if (b->out_slot1 && (rc = ensure(ctx, ctx->d_o1, b->out_bytes + 16))) return rc;
+        if (b->out_slot2 && (rc = ensure(ctx, ctx->d_o2, b->out_bytes + 16))) return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off1.p, b->off1, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off2.p, b->off2, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_len1.p, b->len1, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_len2.p, b->len2, n * 4, cudaMemcpyHostToDevice, st));
+    if (want_str) CK(cudaMemcpyAsync(ctx->d_out_off.p, b->out_off, n * 8, cudaMemcpyHostToDevice, st));
+
+    pcgdo_batch d = *b;
+    d.elems = (const uint8_t *)ctx->d_elems.p;
+    d.off1 = (const uint64_t *)ctx->d_off1.p;
+    d.off2 = (const uint64_t *)ctx->d_off2.p;
+    d.len1 = (const uint32_t *)ctx->d_len1.p;
+    d.len2 = (const uint32_t *)ctx->d_len2.p;
+    d.out_off = want_str ? (const uint64_t *)ctx->d_out_off.p : nullptr;
+    d.out_gapped = b->out_gapped ? (uint8_t *)ctx->d_og.p : nullptr;
+    d.out_slot1 = b->out_slot1 ? (uint8_t *)ctx->d_o1.p : nullptr;
+    d.out_slot2 = b->out_slot2 ? (uint8_t *)ctx->d_o2.p : nullptr;
+    d.out_len = b->out_len ? (uint32_t *)ctx->d_olen.p : nullptr;
+    d.cost = (int32_t *)ctx->d_cost.p;
+    d.cells = b->cells ? (uint64_t *)ctx->d_cells.p : nullptr;
+    rc = pcgdo_align2d_batch_device(ctx, tcm, &d, st);
+    if (rc) return rc;
+
+    CK(cudaMemcpyAsync(b->cost, d.cost, n * 4, cudaMemcpyDeviceToHost, st));
+    if (b->out_len) CK(cudaMemcpyAsync(b->out_len, d.out_len, n * 4, cudaMemcpyDeviceToHost, st));
+    if (b->cells) CK(cudaMemcpyAsync(b->cells, d.cells, n * 8, cudaMemcpyDeviceToHost, st));
+    if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped, d.out_gapped, b->out_bytes, cudaMemcpyDeviceToHost, st));
+    if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1, d.out_slot1, b->out_bytes, cudaMemcpyDeviceToHost, st));
+    if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2, d.out_slot2, b->out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PCGDO_OK;
+}
+
+// --------------------------------------------------------------------------------------------- shims
+
+namespace {
+std::mutex g_mu;
+pcgdo_ctx *g_ctx = nullptr;
+std::unordered_map<const void *, pcgdo_tcm *> g_tcms;   // keyed by the caller's cost-table pointer
+
+[[noreturn]] void die(const char *what, const char *detail)
+{
+    fprintf(stderr, "pcg_do_b200: %s: %s (no CPU fallback)\n", what, detail ? detail : "");
+    abort();
+}
+}  // namespace
+
+extern "C" int align2d(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignIO_t *ungapped,
+                       cost_matrices_2d_t *cm, int getUngapped, int getGapped, int getUnion)
+{
+    (void)ungapped;
+    if (getUngapped || getUnion) die("align2d", "only the (0,1,0) / (0,0,0) flag combinations PCG uses are implemented");
+    if (cm->cost_model_type != 0) die("align2d", "affine cost matrix passed to the linear entry point");
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx && pcgdo_create(&g_ctx, 0) != PCGDO_OK) die("align2d", "cannot create a GPU context");
+    pcgdo_ctx *ctx = g_ctx;
+    pcgdo_tcm *&t = g_tcms[cm->cost];
+    if (!t && tcm_from_tables(ctx, cm->alphSize, 0, cm->cost, cm->median, &t) != PCGDO_OK)
+        die("align2d", ctx->err.c_str());
+
+    const size_t n1 = in1->length, n2 = in2->length;
+    const size_t cap = (n1 + n2 + 3) & ~(size_t)3;
+    std::vector<uint8_t> elems(n1 + n2 + 1), og(cap + 4), o1(cap + 4), o2(cap + 4);
+    const elem_t *s1 = in1->character + (in1->capacity - n1), *s2 = in2->character + (in2->capacity - n2);
+    for (size_t i = 0; i < n1; ++i) elems[i] = (uint8_t)s1[i];
+    for (size_t i = 0; i < n2; ++i) elems[n1 + i] = (uint8_t)s2[i];
+    uint64_t off1 = 0, off2 = n1, out_off = 0;
+    uint32_t len1 = (uint32_t)n1, len2 = (uint32_t)n2, out_len = 0;
+    int32_t cost = 0;
+    pcgdo_batch b{};
+    b.n_pairs = 1;
+    b.elems = elems.data(); b.elems_bytes = elems.size();
+    b.off1 = &off1; b.off2 = &off2; b.len1 = &len1; b.len2 = &len2;
+    b.out_off = &out_off; b.out_bytes = cap;
+    b.cost = &cost;
+    if (getGapped) { b.out_gapped = og.data(); b.out_slot1 = o1.data(); b.out_slot2 = o2.data(); b.out_len = &out_len; }
+    const int saved_len = ctx->max_len, saved_b = ctx->max_b;
+    size_t need_len = n1 > n2 ? n1 : n2;
+    if ((int)need_len > ctx->max_len) ctx->max_len = (int)need_len;
+    ctx->max_b = 32;
+    int rc = pcgdo_align2d_batch_host(ctx, t, &b);
+    ctx->max_len = saved_len; ctx->max_b = saved_b;
+    if (rc != PCGDO_OK) die("align2d", ctx->err.c_str());
+
+    if (getGapped) {
+        auto put = [&](alignIO_t *io, const std::vector<uint8_t> &v) {
+            // same observable effect as dynCharToAlignIO (c_alignment_interface.c:544-585)
+            io->character = (elem_t *)realloc(io->character, io->capacity * sizeof(elem_t));
+            if (!io->character || out_len > io->capacity) die("align2d", "output buffer too small");
+            io->length = out_len;
+            elem_t *dst = io->character + (io->capacity - out_len);
+            for (uint32_t k = 0; k < out_len; ++k) dst[k] = v[k];
+        };
+        put(gapped, og);
+        put(in1, o1);
+        put(in2, o2);
+    }
+    return cost;
+}

@@ -1,0 +1,103 @@
+// do_device.cuh — shared device-side types for the DO kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pcgdo {
+
+constexpr uint32_t kInfW   = 0x80000001u;  // "infinite" cell in stored form (bit 31 = out of band / unreachable)
+constexpr uint32_t kBias4  = 1u << 30;     // 4 * BIAS; finite cells live in [0, 2^31)
+constexpr int      kBigSub = 1 << 14;      // 4*sub'-1 entry for the padding element 0
+
+// Device copy of one dense TCM.  Everything the kernels need, already in the layouts they read.
+struct TcmDev {
+    int            a;          // alphabet size (incl. gap), <= 8
+    int            repl;       // 1: sub4 is the 32-way bank-replicated 32x32 table (a <= 5), 0: plain [l << a | s]
+    uint32_t       gap;
+    uint32_t       sub4_bytes; // bytes of `sub4` to stage in shared memory
+    int32_t        sub4_gapgap;
+    const int16_t *sub4;       // 4*(cost[l][s] - cost[l][gap] - cost[gap][s]) - 1 ; row/col 0 = kBigSub
+    const uint8_t *median;     // [dim*dim]
+    const uint32_t *cgap;      // [dim] cost[x][gap]   (indel of consuming x from the longer string)
+    const uint32_t *gapc;      // [dim] cost[gap][y]
+};
+
+struct BatchDev {
+    uint32_t        n_pairs;
+    const uint8_t  *elems;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    const uint64_t *out_off;
+    uint8_t        *out_gapped, *out_slot1, *out_slot2;
+    uint32_t       *out_len;
+    int32_t        *cost;
+    uint64_t       *cells;
+};
+
+struct LinearParams {
+    TcmDev    tcm;
+    BatchDev  b;
+    uint32_t *arena;        // [n_warps_total][arena_words]: direction words + op streams of the
+    uint32_t  arena_words;  //   pairs a warp has filled but not yet traced
+    uint32_t  seq_cap;      // u16 elements of sequence staging per warp
+    int       pairs_per_warp;
+    unsigned int *counter;  // work counter (pairs handed out)
+    unsigned int *overflow_count;
+    uint32_t     *overflow_list;   // pair indices the fast path could not hold
+};
+
+// Geometry of one pair, identical on host and device (plain IEEE double multiplies only).
+// lg / sh include the leading gap.  Mirrors the band selection of the reference
+// (EXT/c_alignment_interface.c:101-109, EXT/alignCharacters.c:1163-1374) as ONE diagonal range
+// d = j - i in [dlo, dhi]: outside cells are "infinite", which reproduces the reference's
+// edge cells (left-most band cell without INSERT, right-most without DELETE) exactly.
+struct Geom {
+    int lg, sh;
+    int dlo, dhi;
+    int pad;        // 1 if an extra (masked) diagonal was added so that q0 is even
+    int q0;         // diagonal index of d = 0
+    int wb;         // diagonals incl. pad
+    int T;          // iterations (two anti-diagonals each)
+    int mode;       // 0 full matrix, 2 / 3 = the reference's banded cases
+};
+
+__host__ __device__ inline Geom make_geom(int lg, int sh)
+{
+    Geom g;
+    g.lg = lg; g.sh = sh;
+    const int diff = lg - sh;
+    const int lim = (int)(.1 * (double)lg);
+    const int delta = diff < lim ? lim / 2 : 2;
+    int W = 50 + delta, H = diff + 50 + delta;
+    if (W > sh) W = sh;
+    if (H > lg) H = lg;
+    int mode;
+    if ((double)lg >= 1.5 * (double)sh) mode = 0;
+    else if (2 * H < lg)                 mode = 2;
+    else if (8 >= lg - H)                mode = 0;
+    else                                 mode = 3;
+    if (mode == 0)      { g.dlo = -(lg - 1); g.dhi = sh - 1; }
+    else if (mode == 2) { g.dlo = -(H - 1);  g.dhi = W - 1; }
+    else                { g.dlo = -H;        g.dhi = W - 1; }
+    g.pad = (-g.dlo) & 1;
+    g.q0 = -g.dlo + g.pad;
+    g.wb = g.dhi - g.dlo + 1 + g.pad;
+    const int q_last = (sh - 1) - (lg - 1) + g.q0;
+    g.T = ((lg - 1) + (sh - 1) - (q_last & 1)) / 2 + 1;
+    g.mode = mode;
+    return g;
+}
+
+// DP cells of the reference's band in rows i0, i0+step, ... (sum over lanes / the whole range = total).
+__host__ __device__ inline unsigned long long band_cells(const Geom &g, int i0, int step)
+{
+    unsigned long long c = 0;
+    for (int i = i0; i < g.lg; i += step) {
+        int lo = i + g.dlo; if (lo < 0) lo = 0;
+        int hi = i + g.dhi; if (hi > g.sh - 1) hi = g.sh - 1;
+        if (hi >= lo) c += (unsigned long long)(hi - lo + 1);
+    }
+    return c;
+}
+
+}  // namespace pcgdo

@@ -1,0 +1,456 @@
+// do_linear.cu — linear-gap pairwise direct optimization ("C-linear" dialect) for sm_100a.
+//
+// Replaces, bit for bit, the reference's align2d pipeline
+//   EXT/c_alignment_interface.c:16-177  (long/short choice, band parameter)
+//   EXT/alignCharacters.c:388-658, 675-1374 (banded row fill), :4404-4507 (traceback),
+//   :4569-4594 (gapped median)            [EXT = lib/core/ffi/external-direct-optimization]
+// with one persistent kernel.  One WARP owns one pair at a time:
+//
+//   fill   lanes statically own B consecutive diagonals (q = j - i + q0) of the reference's band;
+//          the wavefront advances two anti-diagonals per iteration (even q, then odd q), each cell
+//          updated in place in registers, neighbours across lanes via one __shfl per half step.
+//          Cell values are stored as 4*(v - C(i) - G(j) + BIAS) | priority-code, so that
+//            up   needs no add, left only the +1 priority bump, diag one table add,
+//          and a single unsigned 3-way min yields both the cost and the reference's traceback
+//          choice (ALIGN > DELETE > INSERT).  The 2-bit choice of every cell is funnel-shifted into
+//          a per-diagonal word and flushed to HBM every 16 iterations as B consecutive words per
+//          lane (coalesced 128-bit stores): word[(t >> 4) * Wq + q].
+//   trace  after a warp has filled up to 32 pairs it walks all of them at once, one lane per pair,
+//          reading direction words with 16 consecutive ALIGN steps per word, and writes a packed
+//          2-bit op stream.
+//   emit   warp-cooperative per pair: prefix sums over the op stream give the element indices, the
+//          median comes from the dense table, and the three aligned strings leave as coalesced
+//          32-bit stores.
+//
+// No tensor cores: the recurrence is an integer min-plus DP.
+#include "do_device.cuh"
+
+namespace pcgdo {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ld_u16(const char *p) { return *reinterpret_cast<const uint16_t *>(p); }
+__device__ __forceinline__ int      ld_s16(const char *p) { return *reinterpret_cast<const int16_t *>(p); }
+
+// Smallest supported diagonals-per-lane for a band of `wb` diagonals (0 = does not fit a warp).
+__host__ __device__ inline int choose_b(int wb)
+{
+    if (wb <= 64)   return 2;
+    if (wb <= 128)  return 4;
+    if (wb <= 256)  return 8;
+    if (wb <= 512)  return 16;
+    if (wb <= 1024) return 32;
+    return 0;
+}
+
+// Staging layout of one pair in the warp's shared-memory window (u16 entries, already in
+// "table address" form): L region then S region, each with zero padding on both sides so that
+// every lane's sliding window may run off the ends of the strings.
+struct SeqLayout { int offL, sizeL, offS, sizeS; };
+
+__host__ __device__ inline SeqLayout seq_layout(const Geom &g, int B)
+{
+    const int H = B / 2;
+    const int tpad = (g.T + 15) & ~15;
+    SeqLayout s;
+    s.offL = 32 * H;
+    int needL = tpad + g.q0 / 2 + 2;
+    s.sizeL = s.offL + (needL > g.lg ? needL : g.lg) + 2;
+    s.offS = g.q0 / 2;
+    int needS = tpad - g.q0 / 2 + 32 * H + 2;
+    if (needS < g.sh) needS = g.sh;
+    s.sizeS = s.offS + needS + 2;
+    s.sizeL = (s.sizeL + 1) & ~1;
+    s.sizeS = (s.sizeS + 1) & ~1;
+    return s;
+}
+
+__host__ __device__ inline uint32_t dir_words(const Geom &g, int B) { return (uint32_t)((g.T + 15) / 16) * 32u * (uint32_t)B; }
+__host__ __device__ inline uint32_t ops_words(const Geom &g) { return (uint32_t)(g.lg + g.sh) / 16u + 2u; }
+
+// ---------------------------------------------------------------------------------------------
+// fill
+// ---------------------------------------------------------------------------------------------
+template <int B, int LS, bool TAIL>
+__device__ __forceinline__ void run_chunk(uint32_t (&w)[B], const uint32_t (&penc)[B], uint32_t (&dw)[B],
+                                          uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2],
+                                          const char *tab, uint32_t tab_lane, const char *&lptr, const char *&sptr,
+                                          int lane, int n_iter)
+{
+    constexpr int H = B / 2;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (TAIL && r >= n_iter) break;
+        const int tt = r % H;
+        // ---- even diagonals: anti-diagonal s = 2t
+        uint32_t wl = __shfl_up_sync(kFull, w[B - 1], 1);
+        if (lane == 0) wl = kInfW;
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            const int m = 2 * u;
+            const uint32_t left = (u == 0) ? wl : w[m > 0 ? m - 1 : 0];
+            const uint32_t up = w[m + 1];
+            const int sub = ld_s16(tab + lw[(tt - u + H) % H] * LS + sw[(tt + u) % H]);
+            const uint32_t t1 = __viaddmin_u32(w[m], (uint32_t)sub, up);
+            const uint32_t mn = __viaddmin_u32(left, 1u, t1);
+            dw[m] = __funnelshift_r(dw[m], mn, 2);
+            w[m] = (mn & ~3u) | penc[m];
+        }
+        sw[tt] = ld_u16(sptr + 2 * r) + tab_lane;
+        // ---- odd diagonals: anti-diagonal s = 2t + 1
+        uint32_t wr = __shfl_down_sync(kFull, w[0], 1);
+        if (lane == 31) wr = kInfW;
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            const int m = 2 * u + 1;
+            const uint32_t left = w[m - 1];
+            const uint32_t up = (u == H - 1) ? wr : w[m + 1 < B ? m + 1 : B - 1];
+            const int sub = ld_s16(tab + lw[(tt - u + H) % H] * LS + sw[(tt + u + 1) % H]);
+            const uint32_t t1 = __viaddmin_u32(w[m], (uint32_t)sub, up);
+            const uint32_t mn = __viaddmin_u32(left, 1u, t1);
+            dw[m] = __funnelshift_r(dw[m], mn, 2);
+            w[m] = (mn & ~3u) | penc[m];
+        }
+        lw[(tt + 1) % H] = ld_u16(lptr + 2 * r);
+    }
+    lptr += 32;
+    sptr += 32;
+}
+
+template <int B>
+__device__ __forceinline__ void store_words(uint32_t *dst, const uint32_t (&dw)[B])
+{
+    if constexpr (B >= 4) {
+#pragma unroll
+        for (int m = 0; m < B; m += 4)
+            *reinterpret_cast<uint4 *>(dst + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+    } else {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(dw[0], dw[1]);
+    }
+}
+
+// Lb / Sb point at the entries of index 0 (the leading gap) of the staged strings.
+template <int B, int LS>
+__device__ __noinline__ uint32_t fill_pair(const Geom g, const char *tab, uint32_t tab_lane,
+                                           const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg)
+{
+    constexpr int H = B / 2;
+    uint32_t w[B], penc[B], dw[B], lw[H], sw[H];
+    const int qb = lane * B;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int q = qb + m;
+        penc[m] = 1u | ((q < g.pad || q >= g.wb) ? 0x80000000u : 0u);
+        w[m] = (q == g.q0) ? (kBias4 - (uint32_t)sub4gg) : kInfW;
+        dw[m] = 0;
+    }
+    const int I0 = g.q0 / 2 - lane * H;      // row handled by this lane's first even diagonal at t = 0
+    const int J0 = -(g.q0 / 2) + lane * H;   // its column
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        lw[(H - u) % H] = ld_u16(Lb + 2 * (I0 - u));
+        sw[u] = ld_u16(Sb + 2 * (J0 + u)) + tab_lane;
+    }
+    const char *lptr = Lb + 2 * (I0 + 1);
+    const char *sptr = Sb + 2 * (J0 + H);
+    uint32_t *out = slot + qb;
+    const int nfull = g.T >> 4, rem = g.T & 15;
+    for (int c = 0; c < nfull; ++c) {
+        run_chunk<B, LS, false>(w, penc, dw, lw, sw, tab, tab_lane, lptr, sptr, lane, 16);
+        store_words<B>(out, dw);
+        out += 32 * B;
+    }
+    if (rem) {
+        run_chunk<B, LS, true>(w, penc, dw, lw, sw, tab, tab_lane, lptr, sptr, lane, rem);
+#pragma unroll
+        for (int m = 0; m < B; ++m) dw[m] >>= 2 * (16 - rem);
+        store_words<B>(out, dw);
+    }
+    const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
+    const int m_last = q_last % B;
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < B; ++m)
+        if (m == m_last) v = w[m];
+    return __shfl_sync(kFull, v, q_last / B);
+}
+
+// ---------------------------------------------------------------------------------------------
+// trace: one lane per pair
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t trace_lane(const uint32_t *dirw, uint32_t wq, int q0, int lg, int sh, uint32_t *ops)
+{
+    int i = lg - 1, j = sh - 1;
+    uint32_t n = 0, acc = 0, cur_idx = 0xffffffffu, cur_word = 0;
+    while (i > 0 || j > 0) {
+        const int q = j - i + q0;
+        const int t = (i + j - (q & 1)) >> 1;
+        const uint32_t idx = (uint32_t)(t >> 4) * wq + (uint32_t)q;
+        if (idx != cur_idx) { cur_word = __ldcg(dirw + idx); cur_idx = idx; }
+        const uint32_t code = (cur_word >> (2 * (t & 15))) & 3u;
+        acc |= code << (2 * (n & 15));
+        ++n;
+        if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
+        i -= (code != 2u);
+        j -= (code != 1u);
+    }
+    if (n & 15) ops[n >> 4] = acc;
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// emit: warp-cooperative, 128 alignment columns per pass
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_pair(const TcmDev &tcm, const uint8_t *pL, const uint8_t *pS,
+                                          const uint32_t *ops, uint32_t nal, bool first_long,
+                                          uint8_t *og, uint8_t *o1, uint8_t *o2, int lane)
+{
+    uint32_t base_i = 0, base_j = 0;
+    const uint32_t gap = tcm.gap;
+    for (uint32_t c0 = 0; c0 < nal; c0 += 128) {
+        const uint32_t c = c0 + 4u * lane;
+        uint32_t code[4];
+        uint32_t nl = 0, ns = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const uint32_t cc = c + x;
+            code[x] = 3u;
+            if (cc < nal) {
+                const uint32_t r = nal - 1u - cc;
+                code[x] = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
+            }
+            nl += (code[x] < 2u);
+            ns += (code[x] == 0u || code[x] == 2u);
+        }
+        const uint32_t packed = nl | (ns << 16);
+        uint32_t incl = packed;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t excl = incl - packed;
+        uint32_t il = base_i + (excl & 0xffffu), js = base_j + (excl >> 16);
+        uint32_t wg = 0, wx = 0, wy = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            uint32_t xx = 0, yy = 0, md = 0;
+            if (code[x] != 3u) {
+                if (code[x] < 2u) { yy = __ldg(pL + il); ++il; }                    // consume longer
+                if (code[x] == 0u || code[x] == 2u) { xx = __ldg(pS + js); ++js; }  // consume lesser
+                md = __ldg(tcm.median + (((xx ? xx : gap) << tcm.a) | (yy ? yy : gap)));
+            }
+            wg |= md << (8 * x);
+            wx |= xx << (8 * x);
+            wy |= yy << (8 * x);
+        }
+        if (c < nal) {
+            if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
+            if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wx : wy;
+            if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? wy : wx;
+        }
+        const uint32_t tot = __shfl_sync(kFull, incl, 31);
+        base_i += tot & 0xffffu;
+        base_j += tot >> 16;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-pair plan: which input is "long" (length, then first differing element), geometry
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool first_is_long(const uint8_t *p1, uint32_t n1, const uint8_t *p2, uint32_t n2, int lane)
+{
+    if (n1 != n2) return n1 > n2;
+    for (uint32_t base = 0; base < n1; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t a = 0, b = 0;
+        if (i < n1) { a = __ldg(p1 + i); b = __ldg(p2 + i); }
+        const unsigned diff = __ballot_sync(kFull, a != b);
+        if (diff) {
+            const int src = __ffs(diff) - 1;
+            const uint32_t aa = __shfl_sync(kFull, a, src), bb = __shfl_sync(kFull, b, src);
+            return aa > bb;
+        }
+    }
+    return true;
+}
+
+template <int LS>
+__device__ __forceinline__ uint32_t dispatch_fill(int B, const Geom &g, const char *tab, uint32_t tab_lane,
+                                                  const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg)
+{
+    switch (B) {
+        case 2:  return fill_pair<2, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
+        case 4:  return fill_pair<4, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
+        case 8:  return fill_pair<8, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
+        case 16: return fill_pair<16, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
+        default: return fill_pair<32, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
+    }
+}
+
+// Shared memory: [sub4 table | cgap[dim] | gapc[dim] | per-warp: flags[32], nal[32], off[32], seq window].
+extern __shared__ __align__(16) char smem[];
+
+__global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
+{
+    const TcmDev &tcm = p.tcm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int dim = 1 << tcm.a;
+
+    char *tab = smem;
+    uint32_t *s_cgap = reinterpret_cast<uint32_t *>(smem + tcm.sub4_bytes);
+    uint32_t *s_gapc = s_cgap + dim;
+    char *warp_base = reinterpret_cast<char *>(s_gapc + dim);
+    const uint32_t per_warp = 384u + 2u * p.seq_cap;
+    uint32_t *s_flags = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
+    uint32_t *s_nal = s_flags + 32;
+    uint32_t *s_off = s_flags + 64;
+    char *seq = reinterpret_cast<char *>(s_flags) + 384;
+
+    for (uint32_t i = threadIdx.x; i < tcm.sub4_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tab)[i] = __ldg(reinterpret_cast<const uint4 *>(tcm.sub4) + i);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_cgap[i] = tcm.cgap[i]; s_gapc[i] = tcm.gapc[i]; }
+    __syncthreads();
+
+    const uint32_t tab_lane = tcm.repl ? 4u * lane : 0u;
+    const int G = p.pairs_per_warp;
+    const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
+    uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
+    const BatchDev &b = p.b;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= b.n_pairs) break;
+        const int npw = (int)min((uint32_t)G, b.n_pairs - base);
+
+        const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
+        int pi = 0;
+        while (pi < npw) {
+            const int start = pi;
+            uint32_t cur = 0;
+            // -------------------------------------------------------------- fill, pair after pair,
+            // until the warp's scratch arena is full
+            for (; pi < npw; ++pi) {
+                const uint32_t k = base + pi;
+                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                const bool fl = first_is_long(p1, n1, p2, n2, lane);
+                const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
+                const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+                const int B = choose_b(g.wb);
+                bool ok = B != 0;
+                SeqLayout sl = {0, 0, 0, 0};
+                uint32_t need = 0;
+                if (ok) {
+                    sl = seq_layout(g, B);
+                    need = (dir_words(g, B) + ops_words(g) + 3u) & ~3u;
+                    ok = (uint32_t)(sl.sizeL + sl.sizeS) <= p.seq_cap && need <= p.arena_words;
+                }
+                if (!ok) {
+                    if (lane == 0) {
+                        s_flags[pi] = 0;
+                        p.overflow_list[atomicAdd(p.overflow_count, 1u)] = k;
+                    }
+                    continue;
+                }
+                if (cur + need > p.arena_words) break;     // trace + emit what we have, then go on
+                if (lane == 0) { s_flags[pi] = (fl ? 1u : 0u) | 2u; s_off[pi] = cur; }
+                uint32_t *slot = arena + cur;
+                cur += need;
+
+                // stage both strings in "table address" form; sum the indel costs folded out of the cells
+                uint16_t *Lr = reinterpret_cast<uint16_t *>(seq);
+                uint16_t *Sr = Lr + sl.sizeL;
+                uint32_t csum = 0;
+                const int lshift = tcm.repl ? 11 : tcm.a;
+                const uint32_t emask = (uint32_t)dim - 1u;
+                for (int idx = lane; idx < sl.sizeL; idx += 32) {
+                    const int i = idx - sl.offL;
+                    uint32_t e = 0;
+                    if (i == 0) e = tcm.gap;
+                    else if (i > 0 && i < g.lg) { e = __ldg(pL + i - 1) & emask; csum += s_cgap[e]; }
+                    Lr[idx] = (uint16_t)(e << lshift);
+                }
+                for (int idx = lane; idx < sl.sizeS; idx += 32) {
+                    const int j = idx - sl.offS;
+                    uint32_t e = 0;
+                    if (j == 0) e = tcm.gap;
+                    else if (j > 0 && j < g.sh) { e = __ldg(pS + j - 1) & emask; csum += s_gapc[e]; }
+                    Sr[idx] = (uint16_t)(tcm.repl ? (((e >> 1) << 7) | ((e & 1u) << 1)) : (e << 1));
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+                __syncwarp();
+
+                const char *Lb = reinterpret_cast<const char *>(Lr + sl.offL);
+                const char *Sb = reinterpret_cast<const char *>(Sr + sl.offS);
+                uint32_t fw;
+                if (tcm.repl) fw = dispatch_fill<1>(B, g, tab, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+                else          fw = dispatch_fill<2>(B, g, tab, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+                if (lane == 0) b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
+                if (b.cells) {
+                    unsigned long long c = band_cells(g, lane, 32);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+                    if (lane == 0) b.cells[k] = c;
+                }
+                __syncwarp();   // the staging window is reused by the next pair
+            }
+            __syncwarp();
+            if (!want_out) continue;
+
+            // -------------------------------------------------------------- trace: lane = pair
+            const int pj = start + lane;
+            if (pj < pi && (s_flags[pj] & 2u)) {
+                const uint32_t k = base + pj;
+                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                const bool fl = s_flags[pj] & 1u;
+                const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+                const int B = choose_b(g.wb);
+                uint32_t *slot = arena + s_off[pj];
+                const uint32_t n = trace_lane(slot, 32u * B, g.q0, g.lg, g.sh, slot + dir_words(g, B));
+                s_nal[pj] = n;
+                if (b.out_len) b.out_len[k] = n;
+            }
+            __syncwarp();
+
+            // -------------------------------------------------------------- emit: warp per pair
+            if (b.out_gapped || b.out_slot1 || b.out_slot2) {
+                for (int pe = start; pe < pi; ++pe) {
+                    const uint32_t fl_ok = s_flags[pe];
+                    if (!(fl_ok & 2u)) continue;
+                    const uint32_t k = base + pe;
+                    const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                    const bool fl = fl_ok & 1u;
+                    const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                    const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+                    const int B = choose_b(g.wb);
+                    const uint32_t *ops = arena + s_off[pe] + dir_words(g, B);
+                    const uint64_t oo = b.out_off[k];
+                    emit_pair(tcm, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                              b.out_gapped ? b.out_gapped + oo : nullptr,
+                              b.out_slot1 ? b.out_slot1 + oo : nullptr,
+                              b.out_slot2 ? b.out_slot2 + oo : nullptr, lane);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Host-side launcher (called from do_api.cu).
+cudaError_t launch_linear(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(do_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    do_linear_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace pcgdo

@@ -1,0 +1,54 @@
+"""Shared generators for the tests (TCMs of the reference's bench data, random strings)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tcm_matrix(name: str, a: int = 5) -> np.ndarray:
+    """Symbol-change matrices used by the reference's own tests / bench data (gap = last symbol)."""
+    idx = np.arange(a)
+    if name == "discrete":          # bench/strings/dna/dna-discrete.tcm
+        return (1 - np.eye(a, dtype=np.uint32)).astype(np.uint32)
+    if name == "l1":                # bench/strings/dna/dna-L1-norm.tcm
+        return np.abs(np.subtract.outer(idx, idx)).astype(np.uint32)
+    if name == "1:2":               # substitution 1, indel 2 (Pairwise/Test.hs metrics)
+        m = (1 - np.eye(a, dtype=np.uint32)).astype(np.uint32)
+        m[-1, :-1] = 2
+        m[:-1, -1] = 2
+        return m
+    if name == "2:1":
+        m = 2 * (1 - np.eye(a, dtype=np.uint32)).astype(np.uint32)
+        m[-1, :-1] = 1
+        m[:-1, -1] = 1
+        return m
+    if name == "weird":             # symmetric, non-metric, distinct entries
+        assert a == 5
+        return np.array([[0, 3, 1, 4, 2], [3, 0, 2, 1, 5], [1, 2, 0, 6, 2], [4, 1, 6, 0, 3], [2, 5, 2, 3, 0]],
+                        np.uint32)
+    raise KeyError(name)
+
+
+def random_string(rng, n, a=5, amb=0.15):
+    """Elements over an a-symbol alphabet: mostly single non-gap symbols, `amb` fraction arbitrary
+    non-empty ambiguity sets (may contain the gap bit), like the reference's generators."""
+    x = (1 << rng.integers(0, a - 1, size=n)).astype(np.uint32)
+    m = rng.random(n) < amb
+    return np.where(m, rng.integers(1, 1 << a, size=n), x).astype(np.uint8)
+
+
+def random_pair(rng, max_len=400, a=5, amb=0.15):
+    n1 = int(rng.integers(1, max_len))
+    if rng.random() < 0.6:
+        n2 = max(1, n1 + int(rng.integers(-30, 30)))
+    else:
+        n2 = int(rng.integers(1, max_len))
+    s1 = random_string(rng, n1, a, amb)
+    if rng.random() < 0.5 and n2 <= n1:
+        s2 = s1[:n2].copy()
+        mut = rng.random(n2) < 0.1
+        s2 = np.where(mut, random_string(rng, n2, a, amb), s2).astype(np.uint8)
+    else:
+        s2 = random_string(rng, n2, a, amb)
+    return s1, s2

@@ -1,0 +1,188 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, bit-exact."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import random_pair, random_string, tcm_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_batch(o, ctx, tcm, pairs, want_cells=True):
+    import pcg_b200 as P
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    r = P.align2d_batch(ctx, tcm, pp, want_cells=want_cells)
+    for k, (s1, s2) in enumerate(pairs):
+        oc = o.align2d(s1, s2)
+        gc = r.pair(pp, k)
+        assert gc[0] == oc[0], (k, len(s1), len(s2), gc[0], oc[0])
+        for x, y in zip(gc[1:], oc[1:4]):
+            assert np.array_equal(x, y), (k, len(s1), len(s2))
+        if want_cells:
+            assert int(r.cells[k]) == oc[4], (k, len(s1), len(s2))
+    return r
+
+
+@pytest.mark.parametrize("name", ["discrete", "l1", "1:2", "2:1", "weird"])
+def test_fuzz_against_oracle(oracle_mod, gpu_ctx, name):
+    sig = tcm_matrix(name)
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(max_len=640, max_b=32)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(101)
+    pairs = [random_pair(rng, 600) for _ in range(300)]
+    _check_batch(o, gpu_ctx, tcm, pairs)
+
+
+def test_edge_shapes(oracle_mod, gpu_ctx):
+    sig = tcm_matrix("discrete")
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(max_len=640, max_b=32)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(7)
+    pairs = []
+    for n1, n2 in [(1, 1), (1, 2), (2, 1), (1, 300), (300, 1), (5, 5), (16, 17), (31, 33), (64, 64), (65, 63),
+                   (99, 100), (128, 127), (200, 133), (200, 134), (150, 100), (151, 100), (500, 499),
+                   (512, 512), (600, 401), (600, 399), (57, 58), (59, 52), (61, 61)]:
+        pairs.append((random_string(rng, n1), random_string(rng, n2)))
+    s = random_string(rng, 257)
+    pairs.append((s, s.copy()))                       # identical inputs
+    t = s.copy(); t[200] ^= 3
+    pairs.append((s, t)); pairs.append((t, s))         # equal length, lexicographic tie-break
+    g = np.full(40, 16, np.uint8)
+    pairs.append((g, random_string(rng, 44)))          # all-gap elements as input symbols
+    pairs.append((np.full(90, 31, np.uint8), np.full(70, 31, np.uint8)))   # fully ambiguous
+    _check_batch(o, gpu_ctx, tcm, pairs)
+
+
+@pytest.mark.parametrize("a,name", [(3, "discrete"), (4, "l1"), (6, "discrete"), (7, "l1"), (8, "discrete")])
+def test_other_alphabets(oracle_mod, gpu_ctx, a, name):
+    sig = tcm_matrix(name, a)
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(max_len=320, max_b=32)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(a)
+    pairs = []
+    for _ in range(60):
+        s1, s2 = random_pair(rng, 300, a=a)
+        pairs.append((s1, s2))
+    _check_batch(o, gpu_ctx, tcm, pairs)
+
+
+def test_arena_recycling_and_small_batches(oracle_mod, gpu_ctx):
+    """Tiny arena: warps must trace/emit and restart several times within one hand-out of pairs."""
+    sig = tcm_matrix("l1")
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=4, max_len=320, max_b=32, arena_words=40000)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(9)
+    pairs = [random_pair(rng, 300) for _ in range(200)]
+    _check_batch(o, gpu_ctx, tcm, pairs)
+    gpu_ctx.configure(pairs_per_warp=3, warps_per_cta=16, max_len=320, max_b=32, arena_words=0)
+    _check_batch(o, gpu_ctx, tcm, pairs[:50])
+    gpu_ctx.configure(pairs_per_warp=32)
+
+
+def test_golden_nodes_through_gpu(oracle_mod, gpu_ctx):
+    """The reference's chel golden test, post-order nodes, through foreignPairwiseDO on the GPU."""
+    import pcg_b200 as P
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chel_golden.json")))
+    gpu_ctx.configure(max_len=640, max_b=32)
+    tcm = gpu_ctx.tcm(tcm_matrix("discrete"))
+    nodes = g["nodes"]
+    ids = [n["id"] for n in nodes if len(n["children"]) == 2 and n["id"] not in g["rerooted_nodes"]]
+    c1 = [np.array(nodes[sorted(nodes[i]["children"])[0]]["context"], np.uint8) for i in ids]
+    c2 = [np.array(nodes[sorted(nodes[i]["children"])[1]]["context"], np.uint8) for i in ids]
+    got = P.foreign_pairwise_do_batch(gpu_ctx, tcm, c1, c2)
+    assert len(ids) == 14
+    for i, (cost, ctx) in zip(ids, got):
+        assert cost == nodes[i]["local_cost"], i
+        assert ctx.tolist() == nodes[i]["context"], i
+
+
+def test_reference_compatible_align2d_symbol(oracle_mod, gpu_ctx):
+    """Call `align2d` exactly as DO/Pairwise/FFI.hsc does: malloc'ed alignIO_t, payload right-aligned."""
+    import pcg_b200.backend as be
+    lib = be.load()
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    sig = tcm_matrix("discrete")
+    o = oracle_mod.Oracle(sig)
+    cm = be.CostMatrices2D()
+    lib.setUp2dCostMtx(C.byref(cm), sig.ctypes.data_as(C.POINTER(C.c_uint32)), 5, 0)
+
+    def aio(vals, cap):
+        buf = libc.malloc(cap * 4)
+        C.memset(buf, 0, cap * 4)
+        arr = (C.c_uint32 * cap).from_address(buf)
+        for i, v in enumerate(vals):
+            arr[cap - len(vals) + i] = int(v)
+        return be.AlignIO(C.cast(buf, C.POINTER(C.c_uint32)), len(vals), cap)
+
+    def take(io):
+        off = io.capacity - io.length
+        out = [io.character[off + i] for i in range(io.length)]
+        libc.free(C.cast(io.character, C.c_void_p))
+        return out
+
+    rng = np.random.default_rng(23)
+    for _ in range(6):
+        s1, s2 = random_pair(rng, 200)
+        cap = len(s1) + len(s2) + 2
+        a1, a2, g, u = aio(s1, cap), aio(s2, cap), aio([], cap), aio([], cap)
+        cost = lib.align2d(C.byref(a1), C.byref(a2), C.byref(g), C.byref(u), C.byref(cm), 0, 1, 0)
+        oc = o.align2d(s1, s2)
+        assert cost == oc[0]
+        assert take(g) == oc[1].tolist() and take(a1) == oc[2].tolist() and take(a2) == oc[3].tolist()
+        libc.free(C.cast(u.character, C.c_void_p))
+
+
+def test_config2_shape_properties_and_sample(oracle_mod, gpu_ctx):
+    """BASELINE config 2 shape (1 kb uniform DNA pairs, L1 TCM, C band) at a size the oracle cannot
+    sweep: size-independent properties on every pair + the oracle on a sample."""
+    import pcg_b200 as P
+    sig = tcm_matrix("l1")
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=16, max_len=1024, max_b=8, arena_words=0)
+    tcm = gpu_ctx.tcm(sig)
+    n, L = 8192, 1000
+    rng = np.random.Generator(np.random.PCG64(20260101))
+    strings = (1 << rng.integers(0, 4, size=(2 * n, L))).astype(np.uint8)
+    pp = P.PackedPairs.uniform(strings)
+    r = P.align2d_batch(gpu_ctx, tcm, pp, want_cells=True)
+    cost_tab = o.cost
+    gap = o.gap
+    assert (r.cells == r.cells[0]).all() and int(r.cells[0]) == o.band_cells(L + 1, L + 1)[0]
+    for k in range(0, n, 37):
+        c, g, s1, s2 = r.pair(pp, k)
+        a, b = strings[2 * k], strings[2 * k + 1]
+        # each slot holds one input with gaps (0) inserted ...
+        first_long = a.tolist() >= b.tolist()         # equal lengths: lexicographic (c_alignment_interface.c:59-70)
+        x, y = (s1, s2) if first_long else (s2, s1)          # x = aligned lesser, y = aligned longer
+        lesser, longer = (b, a) if first_long else (a, b)
+        assert np.array_equal(x[x != 0], lesser) and np.array_equal(y[y != 0], longer)
+        assert not ((x == 0) & (y == 0)).any()
+        # ... the reported cost is the sum of the column costs, the median the table's
+        xe = np.where(x == 0, gap, x).astype(np.int64)
+        ye = np.where(y == 0, gap, y).astype(np.int64)
+        assert int(cost_tab[ye, xe].sum()) == c
+        assert np.array_equal(o.median[xe, ye].astype(np.uint8), g)
+    for k in range(0, n, 257):
+        oc = o.align2d(strings[2 * k], strings[2 * k + 1])
+        gc = r.pair(pp, k)
+        assert gc[0] == oc[0]
+        for x, y in zip(gc[1:], oc[1:4]):
+            assert np.array_equal(x, y)
+    # commutativity: swapping the inputs swaps the slots, nothing else
+    sw = strings.reshape(n, 2, L)[:, ::-1, :].reshape(2 * n, L)
+    pp2 = P.PackedPairs.uniform(np.ascontiguousarray(sw[:512]))
+    r2 = P.align2d_batch(gpu_ctx, tcm, pp2)
+    for k in range(256):
+        c, g, s1, s2 = r.pair(pp, k)
+        c2, g2, t1, t2 = r2.pair(pp2, k)
+        assert c == c2 and np.array_equal(g, g2) and np.array_equal(s1, t2) and np.array_equal(s2, t1)

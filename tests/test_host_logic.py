@@ -1,0 +1,82 @@
+"""CPU: the numpy gap bookkeeping of pcg_b200.pairwise (deleteGaps / measure / insertGaps / swap)
+against the oracle's restatement of the Haskell wrapper. The aligner is injected (the oracle's align2d)
+so only the host logic is under test here — the product path has no such hook enabled."""
+import json
+import os
+
+import numpy as np
+
+from tests.helpers import random_string, tcm_matrix
+from pcg_b200 import pairwise as pw
+
+
+class _FakeTcm:
+    def __init__(self, o):
+        self.gap = o.gap
+        self.a = o.a
+        self.median_of_gap = o.median[:, o.gap].astype(np.uint8)
+
+
+def _oracle_align(o):
+    def run(ctx, tcm, pp):
+        n = pp.n
+        cost = np.zeros(n, np.int32)
+        out_len = np.zeros(n, np.uint32)
+        g, s1, s2 = (np.zeros(pp.out_bytes, np.uint8) for _ in range(3))
+        for k in range(n):
+            a = pp.elems[int(pp.off1[k]):int(pp.off1[k]) + int(pp.len1[k])]
+            b = pp.elems[int(pp.off2[k]):int(pp.off2[k]) + int(pp.len2[k])]
+            c, gg, x1, x2, _ = o.align2d(a, b)
+            oo = int(pp.out_off[k])
+            cost[k], out_len[k] = c, len(gg)
+            g[oo:oo + len(gg)], s1[oo:oo + len(gg)], s2[oo:oo + len(gg)] = gg, x1, x2
+        return pw.BatchResult(cost, out_len, g, s1, s2, None)
+    return run
+
+
+def _random_context(rng, n, gap):
+    """A context as it comes out of a previous DO: aligned / inserted / deleted / gap triples."""
+    m = random_string(rng, n)
+    kind = rng.integers(0, 4, size=n)
+    c = np.stack([m, m, m], 1)
+    c[kind == 1, 2] = 0
+    c[kind == 2, 1] = 0
+    g = kind == 3
+    c[g] = [gap, 0, 0]
+    g2 = rng.random(n) < 0.1
+    c[g2, 0] = gap
+    return c.astype(np.uint8)
+
+
+def test_wrapper_host_logic_matches_oracle(oracle_mod):
+    o = oracle_mod.Oracle(tcm_matrix("discrete"))
+    rng = np.random.default_rng(17)
+    c1s, c2s = [], []
+    for _ in range(120):
+        c1s.append(_random_context(rng, int(rng.integers(1, 120)), o.gap))
+        c2s.append(_random_context(rng, int(rng.integers(1, 120)), o.gap))
+    # degenerate shapes: all gaps, equal inputs, one empty after ungapping, missing
+    allgap = np.array([[o.gap, 0, 0]] * 4, np.uint8)
+    c1s += [allgap, allgap, c1s[0], None, None, c1s[1]]
+    c2s += [allgap, c2s[0], c1s[0].copy(), c2s[1], None, None]
+    got = pw.foreign_pairwise_do_batch(None, _FakeTcm(o), c1s, c2s, _align=_oracle_align(o))
+    for k, (c1, c2) in enumerate(zip(c1s, c2s)):
+        cost, ctx, _ = o.pairwise_do(c1, c2)
+        assert got[k][0] == cost, k
+        if ctx is None:
+            assert got[k][1] is None, k
+        else:
+            assert np.array_equal(got[k][1], ctx), k
+
+
+def test_wrapper_on_golden_nodes(oracle_mod):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chel_golden.json")))
+    o = oracle_mod.Oracle(tcm_matrix("discrete"))
+    nodes = g["nodes"]
+    ids = [n["id"] for n in nodes if len(n["children"]) == 2 and n["id"] not in g["rerooted_nodes"]]
+    c1 = [np.array(nodes[sorted(nodes[i]["children"])[0]]["context"], np.uint8) for i in ids]
+    c2 = [np.array(nodes[sorted(nodes[i]["children"])[1]]["context"], np.uint8) for i in ids]
+    got = pw.foreign_pairwise_do_batch(None, _FakeTcm(o), c1, c2, _align=_oracle_align(o))
+    for i, (cost, ctx) in zip(ids, got):
+        assert cost == nodes[i]["local_cost"]
+        assert ctx.tolist() == nodes[i]["context"]

@@ -1,0 +1,93 @@
+"""CPU: the oracle (oracle/do_oracle.c) against the reference's golden file, the compiled reference
+(oracle/_ref, when built) and the numpy model of the device formulation."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import random_pair, tcm_matrix
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "chel_golden.json")
+
+
+def _golden():
+    return json.load(open(GOLDEN))
+
+
+def test_oracle_reproduces_chel_golden(oracle_mod):
+    """chel_xml.golden pins local cost and every (median,left,right) triple of 16 internal nodes; 14 are
+    post-order results, nodes 0 and 30 are rewritten by the re-rooting pass (out of scope)."""
+    g = _golden()
+    o = oracle_mod.Oracle(tcm_matrix("discrete"))
+    nodes = g["nodes"]
+    checked = 0
+    for n in nodes:
+        if len(n["children"]) != 2 or n["id"] in g["rerooted_nodes"]:
+            continue
+        l, r = sorted(n["children"])
+        cost, ctx, _ = o.pairwise_do(np.array(nodes[l]["context"]), np.array(nodes[r]["context"]))
+        assert cost == n["local_cost"], n["id"]
+        assert ctx.tolist() == n["context"], n["id"]
+        assert n["total_cost"] == cost + nodes[l]["total_cost"] + nodes[r]["total_cost"]
+        checked += 1
+    assert checked == 14
+
+
+def test_oracle_survey_sanity_example(oracle_mod):
+    # ACGTACGTTT vs ACTACGGT, discrete -> cost 3, median [1,2,20,8,1,2,4,24,12,8]
+    enc = {"A": 1, "C": 2, "G": 4, "T": 8}
+    o = oracle_mod.Oracle(tcm_matrix("discrete"))
+    cost, g, s1, s2, _ = o.align2d([enc[c] for c in "ACGTACGTTT"], [enc[c] for c in "ACTACGGT"])
+    assert cost == 3
+    assert g.tolist() == [1, 2, 20, 8, 1, 2, 4, 24, 12, 8]
+
+
+@pytest.mark.parametrize("name", ["discrete", "l1", "1:2", "2:1", "weird"])
+def test_oracle_matches_compiled_reference(oracle_mod, name):
+    if not oracle_mod.Reference.available():
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    sig = tcm_matrix(name)
+    o, r = oracle_mod.Oracle(sig), oracle_mod.Reference(sig)
+    c, m = r.tables()
+    assert np.array_equal(c, o.cost) and np.array_equal(m, o.median)
+    rng = np.random.default_rng(11)
+    modes = set()
+    for _ in range(150):
+        s1, s2 = random_pair(rng, 400)
+        rc, oc = r.align2d(s1, s2), o.align2d(s1, s2)
+        assert rc[0] == oc[0]
+        for x, y in zip(rc[1:], oc[1:4]):
+            assert np.array_equal(x, y)
+        modes.add(o.band_cells(max(len(s1), len(s2)) + 1, min(len(s1), len(s2)) + 1)[1])
+    assert modes == {0, 2, 3}
+
+
+def test_oracle_commutes_up_to_swap_context(oracle_mod):
+    """The reference's own property test (Pairwise/Test.hs:222-226)."""
+    o = oracle_mod.Oracle(tcm_matrix("l1"))
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        s1, s2 = random_pair(rng, 200)
+        c1 = np.stack([s1, s1, s1], 1)
+        c2 = np.stack([s2, s2, s2], 1)
+        a = o.pairwise_do(c1, c2)
+        b = o.pairwise_do(c2, c1)
+        assert a[0] == b[0]
+        assert np.array_equal(a[1], b[1][:, [0, 2, 1]])
+        n = len(a[1])
+        assert max(len(s1), len(s2)) <= n <= len(s1) + len(s2)     # Test.hs:228-242
+
+
+@pytest.mark.parametrize("name", ["discrete", "l1", "weird"])
+def test_device_formulation_model_matches_oracle(oracle_mod, name):
+    from tests.model import diag_model as M
+    o = oracle_mod.Oracle(tcm_matrix(name))
+    rng = np.random.default_rng(3)
+    for _ in range(25):
+        s1, s2 = random_pair(rng, 220)
+        oc = o.align2d(s1, s2)
+        mc = M.align2d(o.cost, o.median, 5, s1, s2, lanes_b=int(rng.choice([2, 4, 8])))
+        assert oc[0] == mc[0]
+        for x, y in zip(oc[1:4], mc[1:4]):
+            assert np.array_equal(x, y)
