@@ -1,0 +1,117 @@
+/* cpu_bench.c — times the CPU implementations of the path on host cores (TEST / BENCH INFRASTRUCTURE).
+ *
+ * kind "reference": dlopen()s oracle/_ref/libpcgdo_ref.so — the UNMODIFIED reference aligner — and calls
+ *   its align2d exactly as the Haskell binding does (DO/Pairwise/FFI.hsc:272-290, 474-515): four malloc'ed
+ *   alignIO_t buffers of capacity len1+len2+2 per call, payload right-aligned, freed after the call.
+ * kind "port": the restatement in do_oracle.c.
+ * Pairs are split over `threads` pthreads (the entry points are re-entrant: call-local allocations and
+ * a read-only cost matrix).  Only bench.py's cpu_baseline / --impl reference legs and tests call this.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "do_oracle.h"
+
+typedef struct { unsigned int *character; size_t length; size_t capacity; } aio_t;
+typedef int (*align2d_fn)(aio_t *, aio_t *, aio_t *, aio_t *, void *, int, int, int);
+typedef void (*setup_fn)(void *, unsigned int *, size_t, unsigned int);
+
+typedef struct {
+    int tid, threads;
+    size_t n;
+    const uint8_t *elems;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    int32_t *cost;
+    uint64_t *cells;
+    align2d_fn ref_align;
+    void *ref_cm;
+    const oracle_tcm_t *port;
+} job_t;
+
+static void fill_aio(aio_t *io, const uint8_t *src, size_t n, size_t cap)
+{
+    io->character = calloc(cap, sizeof(unsigned int));
+    io->length = n;
+    io->capacity = cap;
+    for (size_t i = 0; i < n; i++) io->character[cap - n + i] = src[i];
+}
+
+static void *worker(void *arg)
+{
+    job_t *j = arg;
+    for (size_t k = j->tid; k < j->n; k += j->threads) {
+        const uint8_t *s1 = j->elems + j->off1[k], *s2 = j->elems + j->off2[k];
+        const size_t n1 = j->len1[k], n2 = j->len2[k];
+        if (j->ref_align) {
+            const size_t cap = n1 + n2 + 2;
+            aio_t a, b, g, u;
+            fill_aio(&a, s1, n1, cap);
+            fill_aio(&b, s2, n2, cap);
+            fill_aio(&g, NULL, 0, cap);
+            fill_aio(&u, NULL, 0, cap);
+            j->cost[k] = j->ref_align(&a, &b, &g, &u, j->ref_cm, 0, 1, 0);
+            free(a.character); free(b.character); free(g.character); free(u.character);
+            if (j->cells) {
+                size_t lg = (n1 > n2 ? n1 : n2) + 1, sh = (n1 > n2 ? n2 : n1) + 1;
+                j->cells[k] = oracle_band_rows(lg, sh, NULL, NULL, NULL, NULL);
+            }
+        } else {
+            uint32_t *buf = malloc(sizeof(uint32_t) * (5 * (n1 + n2) + 8));
+            uint32_t *x1 = buf, *x2 = buf + n1, *og = x2 + n2, *o1 = og + n1 + n2 + 2, *o2 = o1 + n1 + n2 + 2;
+            for (size_t i = 0; i < n1; i++) x1[i] = s1[i];
+            for (size_t i = 0; i < n2; i++) x2[i] = s2[i];
+            size_t nal = 0;
+            uint64_t c = 0;
+            j->cost[k] = (int32_t)oracle_align2d(j->port, x1, n1, x2, n2, og, o1, o2, &nal, &c);
+            if (j->cells) j->cells[k] = c;
+            free(buf);
+        }
+    }
+    return NULL;
+}
+
+/* Returns 0 on success; *seconds = wall time of the alignment loop only (input already in memory). */
+int cpu_bench_align2d(const char *ref_so, const uint32_t *sigma, int a,
+                      const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
+                      const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                      int32_t *cost, uint64_t *cells, double *seconds)
+{
+    align2d_fn ref_align = NULL;
+    void *cm = NULL;
+    oracle_tcm_t *port = NULL;
+    if (ref_so) {
+        void *h = dlopen(ref_so, RTLD_NOW | RTLD_LOCAL);
+        if (!h) return 1;
+        ref_align = (align2d_fn)dlsym(h, "align2d");
+        setup_fn setup = (setup_fn)dlsym(h, "setUp2dCostMtx");
+        if (!ref_align || !setup) return 2;
+        cm = calloc(1, 256);
+        uint32_t *sg = malloc(sizeof(uint32_t) * a * a);
+        memcpy(sg, sigma, sizeof(uint32_t) * a * a);
+        setup(cm, sg, (size_t)a, 0);
+        free(sg);
+    } else {
+        port = oracle_tcm_new(sigma, a, 0);
+    }
+    if (threads < 1) threads = 1;
+    pthread_t *th = malloc(sizeof(pthread_t) * threads);
+    job_t *jobs = malloc(sizeof(job_t) * threads);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (job_t){ t, threads, n, elems, off1, off2, len1, len2, cost, cells, ref_align, cm, port };
+        pthread_create(&th[t], NULL, worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    free(th); free(jobs);
+    if (port) oracle_tcm_free(port);
+    return 0;
+}

@@ -77,6 +77,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_align2d_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch), C.c_void_p]
     L.pcgdo_align2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
     L.pcgdo_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.pcgdo_int32_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.setUp2dCostMtx.argtypes = [C.POINTER(CostMatrices2D), _u32p, C.c_size_t, C.c_uint]
     L.setUp2dCostMtx.restype = None
     L.align2d.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int, C.c_int, C.c_int]
@@ -119,6 +120,12 @@ class Context:
 
     def tcm(self, sigma, gap_open: int = 0) -> "Tcm":
         return Tcm(self, sigma, gap_open)
+
+    def int32_peak(self, mode: int = 0) -> float:
+        """Measured integer lane-ops/s of this GPU (roofline denominator for the DP fill)."""
+        v = C.c_double(0)
+        self.check(self.lib.pcgdo_int32_peak(self.h, mode, C.byref(v), None), "pcgdo_int32_peak")
+        return float(v.value)
 
     def last_kernel_ms(self):
         ms, n = C.c_float(0), C.c_int(0)

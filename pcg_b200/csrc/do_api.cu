@@ -14,6 +14,9 @@
 namespace pcgdo {
 cudaError_t launch_linear(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 }
+namespace pcgdo {
+double launch_int_peak(int mode, int grid, int iters, uint32_t *scratch, cudaStream_t st);
+}
 using namespace pcgdo;
 
 struct pcgdo_tcm {
@@ -343,6 +346,32 @@ extern "C" int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches)
             CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
         }
     }
+    return PCGDO_OK;
+}
+
+// Measured INT32 throughput of this GPU (integer lane-operations per second), the roofline
+// denominator bench.py reports the fill kernel against.  mode 0: add/min/logic only, 1: + multiply-add.
+extern "C" int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, float *ms_out)
+{
+    if (!ctx || !ops_per_s) return PCGDO_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->counters, 64))) return rc;
+    const int grid = ctx->sm_count * 8;
+    double best = 0;
+    float best_ms = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        const double ops = launch_int_peak(mode, grid, 2048, (uint32_t *)ctx->counters.p + 8, ctx->stream);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ops / (ms * 1e-3) > best) { best = ops / (ms * 1e-3); best_ms = ms; }
+    }
+    *ops_per_s = best;
+    if (ms_out) *ms_out = best_ms;
     return PCGDO_OK;
 }
 
