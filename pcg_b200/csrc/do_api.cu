@@ -12,7 +12,8 @@
 #include <vector>
 
 namespace pcgdo {
-cudaError_t launch_linear(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+uint32_t seq_cap_for(int max_len, int B);
 }
 namespace pcgdo {
 double launch_int_peak(int mode, int grid, int iters, uint32_t *scratch, cudaStream_t st);
@@ -40,12 +41,12 @@ struct pcgdo_ctx {
     int last_launches = 0;
     // tunables
     int pairs_per_warp = 32;
-    int warps_per_cta = 16;
+    int warps_per_cta = 32;
     int max_len = 1024;
     int max_b = 8;
     size_t arena_words = 0;          // 0 = derive from max_len
     // device scratch
-    DevBuf arena, counters, overflow;
+    DevBuf arena, counters, overflow, big;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
     std::string err;
@@ -112,7 +113,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
                       &ctx->d_olen, &ctx->d_cost, &ctx->d_cells};
     for (DevBuf *b : bufs)
@@ -133,7 +134,7 @@ extern "C" int pcgdo_configure(pcgdo_ctx *ctx, int pairs_per_warp, int warps_per
         ctx->pairs_per_warp = pairs_per_warp;
     }
     if (warps_per_cta) {
-        if (warps_per_cta < 1 || warps_per_cta > 16) return PCGDO_ERR_ARG;
+        if (warps_per_cta < 1 || warps_per_cta > 32) return PCGDO_ERR_ARG;
         ctx->warps_per_cta = warps_per_cta;
     }
     if (max_len) {
@@ -248,10 +249,10 @@ extern "C" void pcgdo_tcm_destroy(pcgdo_ctx *ctx, pcgdo_tcm *t)
 
 // --------------------------------------------------------------------------------------------- batches
 
-static size_t smem_for(const pcgdo_ctx *ctx, const pcgdo_tcm *tcm, int warps, uint32_t seq_cap)
+static size_t smem_for(const pcgdo_tcm *tcm, int warps, uint32_t seq_cap)
 {
     const size_t dim = (size_t)1 << tcm->a;
-    return tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps * (384 + 2 * (size_t)seq_cap);
+    return tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps * (384 + (size_t)seq_cap);
 }
 
 extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream)
@@ -271,28 +272,31 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
 
-    // shared-memory window per warp: both strings + paddings for the widest variant allowed
-    uint32_t seq_cap = (uint32_t)(2 * ctx->max_len + 80 * ctx->max_b + 96) & ~1u;
-    int warps = ctx->warps_per_cta;
-    while (warps > 1 && smem_for(ctx, tcm, warps, seq_cap) > 227 * 1024) --warps;
-    const size_t smem = smem_for(ctx, tcm, warps, seq_cap);
-    if (smem > 227 * 1024) {
+    // shared-memory window per warp: both strings + paddings for the widest variant of each kernel
+    const uint32_t cap_n = seq_cap_for(ctx->max_len, ctx->max_b < 8 ? ctx->max_b : 8);
+    const uint32_t cap_w = seq_cap_for(ctx->max_len, 32);
+    int warps_n = ctx->warps_per_cta, warps_w = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    while (warps_n > 1 && smem_for(tcm, warps_n, cap_n) > 227 * 1024) --warps_n;
+    while (warps_w > 1 && smem_for(tcm, warps_w, cap_w) > 227 * 1024) --warps_w;
+    if (smem_for(tcm, warps_n, cap_n) > 227 * 1024) {
         ctx->err = "max_len too large for the shared-memory staging window";
         return PCGDO_ERR_UNSUPPORTED;
     }
+    const bool wide_ok = ctx->max_b > 8 && smem_for(tcm, warps_w, cap_w) <= 227 * 1024;
     const int grid = ctx->sm_count;
+    const int warps_max = warps_n > warps_w ? warps_n : warps_w;
     size_t arena_words = ctx->arena_words;
     if (!arena_words) {
-        // room for pairs_per_warp near-equal-length pairs of max_len
-        const size_t b_typ = (size_t)ctx->max_b;
-        arena_words = (size_t)ctx->pairs_per_warp * (((size_t)ctx->max_len + 17) / 16 * 32 * b_typ + ctx->max_len / 8 + 8);
+        // room for pairs_per_warp near-equal-length pairs of max_len in the narrow kernel
+        arena_words = (size_t)ctx->pairs_per_warp * (((size_t)ctx->max_len + 17) / 16 * 32 * 8 + ctx->max_len / 8 + 8);
     }
     arena_words = (arena_words + 3) & ~(size_t)3;
     if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
     int rc;
-    if ((rc = ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->arena, (size_t)grid * warps_max * arena_words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->counters, 64))) return rc;
     if ((rc = ensure(ctx, ctx->overflow, b->n_pairs * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->big, b->n_pairs * 4))) return rc;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
 
     LinearParams p{};
@@ -308,23 +312,35 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     p.b.cells = b->cells;
     p.arena = (uint32_t *)ctx->arena.p;
     p.arena_words = (uint32_t)arena_words;
-    p.seq_cap = seq_cap;
     p.pairs_per_warp = ctx->pairs_per_warp;
     p.counter = (unsigned int *)ctx->counters.p;
     p.overflow_count = p.counter + 1;
+    p.big_count = p.counter + 3;
     p.overflow_list = (uint32_t *)ctx->overflow.p;
+    p.big_list = (uint32_t *)ctx->big.p;
+    p.k_four = 4u;
+    p.k_minus1 = 0xffffffffu;
+    p.l_stride = tcm->dev.repl ? 2048u : (2u << tcm->a);
 
     CK(cudaEventRecord(ctx->ev0, st));
-    CK(launch_linear(p, grid, warps * 32, smem, st));
+    p.seq_cap = cap_n;
+    CK(launch_linear(p, false, grid, warps_n * 32, smem_for(tcm, warps_n, cap_n), st));
+    ctx->last_launches = 1;
+    if (wide_ok) {
+        // consumes the queue the narrow kernel built on the device; exits at once when it is empty
+        p.seq_cap = cap_w;
+        CK(launch_linear(p, true, grid, warps_w * 32, smem_for(tcm, warps_w, cap_w), st));
+        ctx->last_launches = 2;
+    }
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
-    ctx->last_launches = 1;
 
     // pairs the warp kernel could not hold (band wider than 1024 diagonals, strings longer than the
     // staging window, scratch larger than the arena) are reported, not silently dropped
-    unsigned int h_over = 0;
-    CK(cudaMemcpyAsync(&h_over, p.overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    unsigned int h_cnt[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_cnt, p.counter, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const unsigned int h_over = h_cnt[1] + (wide_ok ? 0u : h_cnt[3]);
     if (h_over) {
         char msg[160];
         snprintf(msg, sizeof msg, "%u pair(s) exceed the fast path's limits (max_len=%d, max_b=%d); raise them with pcgdo_configure",

@@ -41,9 +41,14 @@ struct LinearParams {
     uint32_t  arena_words;  //   pairs a warp has filled but not yet traced
     uint32_t  seq_cap;      // u16 elements of sequence staging per warp
     int       pairs_per_warp;
-    unsigned int *counter;  // work counter (pairs handed out)
+    unsigned int *counter;  // work counter (pairs handed out); counter[2] = hand-out counter of the wide kernel
     unsigned int *overflow_count;
     uint32_t     *overflow_list;   // pair indices the fast path could not hold
+    unsigned int *big_count;       // pairs whose band needs more than 8 diagonals per lane:
+    uint32_t     *big_list;        //   queued by the narrow kernel, consumed by the wide one
+    // run-time "constants" (1, 4, -1, table row stride) kept opaque to ptxas so that the table-address add
+    // and the direction accumulation are emitted as IMAD (FMA pipe) instead of IADD3/LEA/SHF (ALU pipe)
+    uint32_t  k_four, k_minus1, l_stride;
 };
 
 // Geometry of one pair, identical on host and device (plain IEEE double multiplies only).
@@ -54,9 +59,9 @@ struct LinearParams {
 struct Geom {
     int lg, sh;
     int dlo, dhi;
-    int pad;        // 1 if an extra (masked) diagonal was added so that q0 is even
+    int pad;        // 1 or 2 masked diagonals in front of the band: q = 0 is always masked, q0 is even
     int q0;         // diagonal index of d = 0
-    int wb;         // diagonals incl. pad
+    int wb;         // diagonals incl. pad; the kernel also keeps q = 32*B - 1 masked, so it needs wb + 1 <= 32*B
     int T;          // iterations (two anti-diagonals each)
     int mode;       // 0 full matrix, 2 / 3 = the reference's banded cases
 };
@@ -79,7 +84,7 @@ __host__ __device__ inline Geom make_geom(int lg, int sh)
     if (mode == 0)      { g.dlo = -(lg - 1); g.dhi = sh - 1; }
     else if (mode == 2) { g.dlo = -(H - 1);  g.dhi = W - 1; }
     else                { g.dlo = -H;        g.dhi = W - 1; }
-    g.pad = (-g.dlo) & 1;
+    g.pad = 1 + ((1 - g.dlo) & 1);
     g.q0 = -g.dlo + g.pad;
     g.wb = g.dhi - g.dlo + 1 + g.pad;
     const int q_last = (sh - 1) - (lg - 1) + g.q0;

@@ -12,9 +12,10 @@
 //          Cell values are stored as 4*(v - C(i) - G(j) + BIAS) | priority-code, so that
 //            up   needs no add, left only the +1 priority bump, diag one table add,
 //          and a single unsigned 3-way min yields both the cost and the reference's traceback
-//          choice (ALIGN > DELETE > INSERT).  The 2-bit choice of every cell is funnel-shifted into
-//          a per-diagonal word and flushed to HBM every 16 iterations as B consecutive words per
-//          lane (coalesced 128-bit stores): word[(t >> 4) * Wq + q].
+//          choice (ALIGN > DELETE > INSERT).  The 2-bit choices accumulate per diagonal as
+//          D = 4*D + mn - w (two IMADs: the FMA pipe is otherwise idle while the ALU pipe is the
+//          bottleneck) and are flushed to HBM every 16 iterations as B consecutive words per lane
+//          (coalesced 128-bit stores): word[(t >> 4) * Wq + q], cell t at bits 2*(15 - (t & 15)).
 //   trace  after a warp has filled up to 32 pairs it walks all of them at once, one lane per pair,
 //          reading direction words with 16 consecutive ALIGN steps per word, and writes a packed
 //          2-bit op stream.
@@ -30,22 +31,40 @@ namespace pcgdo {
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t ld_u16(const char *p) { return *reinterpret_cast<const uint16_t *>(p); }
-__device__ __forceinline__ int      ld_s16(const char *p) { return *reinterpret_cast<const int16_t *>(p); }
+__device__ __forceinline__ uint32_t ld_u8(const char *p) { return *reinterpret_cast<const uint8_t *>(p); }
+// a*b + c on the FMA pipe; b is a run-time value so ptxas cannot strength-reduce it onto the ALU pipe
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// the TCM table is written once before the block-wide barrier and never again: a plain (non-volatile) load
+__device__ __forceinline__ uint32_t lds_s16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+struct FillConst { uint32_t k4, km1, lstride; };
 
 // Smallest supported diagonals-per-lane for a band of `wb` diagonals (0 = does not fit a warp).
 __host__ __device__ inline int choose_b(int wb)
 {
-    if (wb <= 64)   return 2;
-    if (wb <= 128)  return 4;
-    if (wb <= 256)  return 8;
-    if (wb <= 512)  return 16;
-    if (wb <= 1024) return 32;
+    // + 1: the last diagonal of the warp (q = 32*B - 1) stays masked, like q = 0, so that the
+    // block-edge shuffles need no special case in lanes 0 and 31
+    if (wb + 1 <= 64)   return 2;
+    if (wb + 1 <= 128)  return 4;
+    if (wb + 1 <= 256)  return 8;
+    if (wb + 1 <= 512)  return 16;
+    if (wb + 1 <= 1024) return 32;
     return 0;
 }
 
-// Staging layout of one pair in the warp's shared-memory window (u16 entries, already in
-// "table address" form): L region then S region, each with zero padding on both sides so that
-// every lane's sliding window may run off the ends of the strings.
+// Staging layout of one pair in the warp's shared-memory window: the shorter string S as u16 entries
+// already in "table address" form, then the longer string L as raw bytes (its table row offset is one
+// IMAD away), each with zero padding on both sides so that every lane's sliding window may run off the
+// ends of the strings.  Sizes are in elements.
 struct SeqLayout { int offL, sizeL, offS, sizeS; };
 
 __host__ __device__ inline SeqLayout seq_layout(const Geom &g, int B)
@@ -60,10 +79,11 @@ __host__ __device__ inline SeqLayout seq_layout(const Geom &g, int B)
     int needS = tpad - g.q0 / 2 + 32 * H + 2;
     if (needS < g.sh) needS = g.sh;
     s.sizeS = s.offS + needS + 2;
-    s.sizeL = (s.sizeL + 1) & ~1;
+    s.sizeL = (s.sizeL + 3) & ~3;
     s.sizeS = (s.sizeS + 1) & ~1;
     return s;
 }
+__host__ __device__ inline uint32_t seq_bytes(const SeqLayout &s) { return 2u * (uint32_t)s.sizeS + (uint32_t)s.sizeL; }
 
 __host__ __device__ inline uint32_t dir_words(const Geom &g, int B) { return (uint32_t)((g.T + 15) / 16) * 32u * (uint32_t)B; }
 __host__ __device__ inline uint32_t ops_words(const Geom &g) { return (uint32_t)(g.lg + g.sh) / 16u + 2u; }
@@ -71,67 +91,74 @@ __host__ __device__ inline uint32_t ops_words(const Geom &g) { return (uint32_t)
 // ---------------------------------------------------------------------------------------------
 // fill
 // ---------------------------------------------------------------------------------------------
-template <int B, int LS, bool TAIL>
+template <int B, bool TAIL>
 __device__ __forceinline__ void run_chunk(uint32_t (&w)[B], const uint32_t (&penc)[B], uint32_t (&dw)[B],
-                                          uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2],
-                                          const char *tab, uint32_t tab_lane, const char *&lptr, const char *&sptr,
-                                          int lane, int n_iter)
+                                          uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], const FillConst fc,
+                                          uint32_t tab_lane, const char *&lptr, const char *&sptr, int n_iter)
 {
     constexpr int H = B / 2;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
-        // ---- even diagonals: anti-diagonal s = 2t
-        uint32_t wl = __shfl_up_sync(kFull, w[B - 1], 1);
-        if (lane == 0) wl = kInfW;
+        // ---- even diagonals: anti-diagonal s = 2t.  Lane 0 receives its own value here: it only feeds the
+        // always-masked diagonal q = 0.
+        const uint32_t wl = __shfl_up_sync(kFull, w[B - 1], 1);
 #pragma unroll
         for (int u = 0; u < H; ++u) {
             const int m = 2 * u;
             const uint32_t left = (u == 0) ? wl : w[m > 0 ? m - 1 : 0];
             const uint32_t up = w[m + 1];
-            const int sub = ld_s16(tab + lw[(tt - u + H) % H] * LS + sw[(tt + u) % H]);
-            const uint32_t t1 = __viaddmin_u32(w[m], (uint32_t)sub, up);
+            const uint32_t sub = lds_s16(imad(lw[(tt - u + H) % H], fc.lstride, sw[(tt + u) % H]));
+            const uint32_t t1 = __viaddmin_u32(w[m], sub, up);
             const uint32_t mn = __viaddmin_u32(left, 1u, t1);
-            dw[m] = __funnelshift_r(dw[m], mn, 2);
-            w[m] = (mn & ~3u) | penc[m];
+            const uint32_t wn = (mn & ~3u) | penc[m];
+            dw[m] = imad(wn, fc.km1, imad(dw[m], fc.k4, mn));
+            w[m] = wn;
         }
         sw[tt] = ld_u16(sptr + 2 * r) + tab_lane;
-        // ---- odd diagonals: anti-diagonal s = 2t + 1
-        uint32_t wr = __shfl_down_sync(kFull, w[0], 1);
-        if (lane == 31) wr = kInfW;
+        // ---- odd diagonals: anti-diagonal s = 2t + 1 (lane 31's own value only feeds masked q = 32B-1)
+        const uint32_t wr = __shfl_down_sync(kFull, w[0], 1);
 #pragma unroll
         for (int u = 0; u < H; ++u) {
             const int m = 2 * u + 1;
             const uint32_t left = w[m - 1];
             const uint32_t up = (u == H - 1) ? wr : w[m + 1 < B ? m + 1 : B - 1];
-            const int sub = ld_s16(tab + lw[(tt - u + H) % H] * LS + sw[(tt + u + 1) % H]);
-            const uint32_t t1 = __viaddmin_u32(w[m], (uint32_t)sub, up);
+            const uint32_t sub = lds_s16(imad(lw[(tt - u + H) % H], fc.lstride, sw[(tt + u + 1) % H]));
+            const uint32_t t1 = __viaddmin_u32(w[m], sub, up);
             const uint32_t mn = __viaddmin_u32(left, 1u, t1);
-            dw[m] = __funnelshift_r(dw[m], mn, 2);
-            w[m] = (mn & ~3u) | penc[m];
+            const uint32_t wn = (mn & ~3u) | penc[m];
+            dw[m] = imad(wn, fc.km1, imad(dw[m], fc.k4, mn));
+            w[m] = wn;
         }
-        lw[(tt + 1) % H] = ld_u16(lptr + 2 * r);
+        lw[(tt + 1) % H] = ld_u8(lptr + r);
     }
-    lptr += 32;
+    lptr += 16;
     sptr += 32;
 }
 
+// dw holds sum_k (code_k - 1) * 4^(n-1-k) over the n cells of the chunk: add the ones back, left-align
 template <int B>
-__device__ __forceinline__ void store_words(uint32_t *dst, const uint32_t (&dw)[B])
+__device__ __forceinline__ void store_words(uint32_t *dst, const uint32_t (&dw)[B], int n)
 {
+    const int sh = 2 * (16 - n);
+    const uint32_t ones = 0x55555555u >> sh;
+    uint32_t o[B];
+#pragma unroll
+    for (int m = 0; m < B; ++m) o[m] = (dw[m] + ones) << sh;
     if constexpr (B >= 4) {
 #pragma unroll
         for (int m = 0; m < B; m += 4)
-            *reinterpret_cast<uint4 *>(dst + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+            *reinterpret_cast<uint4 *>(dst + m) = make_uint4(o[m], o[m + 1], o[m + 2], o[m + 3]);
     } else {
-        *reinterpret_cast<uint2 *>(dst) = make_uint2(dw[0], dw[1]);
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(o[0], o[1]);
     }
 }
 
-// Lb / Sb point at the entries of index 0 (the leading gap) of the staged strings.
-template <int B, int LS>
-__device__ __noinline__ uint32_t fill_pair(const Geom g, const char *tab, uint32_t tab_lane,
+// Lb / Sb point at the entries of index 0 (the leading gap) of the staged strings; tab_lane is the
+// shared-window address of this lane's copy of the TCM table.
+template <int B>
+__device__ __noinline__ uint32_t fill_pair(const Geom g, const FillConst fc, uint32_t tab_lane,
                                            const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg)
 {
     constexpr int H = B / 2;
@@ -141,6 +168,7 @@ __device__ __noinline__ uint32_t fill_pair(const Geom g, const char *tab, uint32
     for (int m = 0; m < B; ++m) {
         const int q = qb + m;
         penc[m] = 1u | ((q < g.pad || q >= g.wb) ? 0x80000000u : 0u);
+        asm volatile("" : "+r"(penc[m]));        // keep it in a register: ptxas otherwise re-derives it per cell
         w[m] = (q == g.q0) ? (kBias4 - (uint32_t)sub4gg) : kInfW;
         dw[m] = 0;
     }
@@ -148,23 +176,23 @@ __device__ __noinline__ uint32_t fill_pair(const Geom g, const char *tab, uint32
     const int J0 = -(g.q0 / 2) + lane * H;   // its column
 #pragma unroll
     for (int u = 0; u < H; ++u) {
-        lw[(H - u) % H] = ld_u16(Lb + 2 * (I0 - u));
+        lw[(H - u) % H] = ld_u8(Lb + (I0 - u));
         sw[u] = ld_u16(Sb + 2 * (J0 + u)) + tab_lane;
     }
-    const char *lptr = Lb + 2 * (I0 + 1);
+    const char *lptr = Lb + (I0 + 1);
     const char *sptr = Sb + 2 * (J0 + H);
     uint32_t *out = slot + qb;
     const int nfull = g.T >> 4, rem = g.T & 15;
     for (int c = 0; c < nfull; ++c) {
-        run_chunk<B, LS, false>(w, penc, dw, lw, sw, tab, tab_lane, lptr, sptr, lane, 16);
-        store_words<B>(out, dw);
+        run_chunk<B, false>(w, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, 16);
+        store_words<B>(out, dw, 16);
         out += 32 * B;
     }
     if (rem) {
-        run_chunk<B, LS, true>(w, penc, dw, lw, sw, tab, tab_lane, lptr, sptr, lane, rem);
 #pragma unroll
-        for (int m = 0; m < B; ++m) dw[m] >>= 2 * (16 - rem);
-        store_words<B>(out, dw);
+        for (int m = 0; m < B; ++m) dw[m] = 0;
+        run_chunk<B, true>(w, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, rem);
+        store_words<B>(out, dw, rem);
     }
     const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
     const int m_last = q_last % B;
@@ -187,7 +215,7 @@ __device__ __forceinline__ uint32_t trace_lane(const uint32_t *dirw, uint32_t wq
         const int t = (i + j - (q & 1)) >> 1;
         const uint32_t idx = (uint32_t)(t >> 4) * wq + (uint32_t)q;
         if (idx != cur_idx) { cur_word = __ldcg(dirw + idx); cur_idx = idx; }
-        const uint32_t code = (cur_word >> (2 * (t & 15))) & 3u;
+        const uint32_t code = (cur_word >> (2 * (15 - (t & 15)))) & 3u;
         acc |= code << (2 * (n & 15));
         ++n;
         if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
@@ -275,33 +303,43 @@ __device__ __forceinline__ bool first_is_long(const uint8_t *p1, uint32_t n1, co
     return true;
 }
 
-template <int LS>
-__device__ __forceinline__ uint32_t dispatch_fill(int B, const Geom &g, const char *tab, uint32_t tab_lane,
+template <int BMAX>
+__device__ __forceinline__ uint32_t dispatch_fill(int B, const Geom &g, const FillConst fc, uint32_t tab_lane,
                                                   const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg)
 {
-    switch (B) {
-        case 2:  return fill_pair<2, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
-        case 4:  return fill_pair<4, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
-        case 8:  return fill_pair<8, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
-        case 16: return fill_pair<16, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
-        default: return fill_pair<32, LS>(g, tab, tab_lane, Lb, Sb, slot, lane, sub4gg);
+    if constexpr (BMAX <= 8) {
+        switch (B) {
+            case 2:  return fill_pair<2>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg);
+            case 4:  return fill_pair<4>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg);
+            default: return fill_pair<8>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg);
+        }
+    } else {
+        if (B == 16) return fill_pair<16>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg);
+        return fill_pair<32>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg);
     }
 }
 
 // Shared memory: [sub4 table | cgap[dim] | gapc[dim] | per-warp: flags[32], nal[32], off[32], seq window].
 extern __shared__ __align__(16) char smem[];
 
-__global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
+// BMAX = 8 : the narrow kernel (64 registers, up to 32 warps per SM).  Takes pairs straight from the batch;
+//            pairs whose band needs 16 or 32 diagonals per lane are queued on big_list.
+// BMAX = 32: the wide kernel (128 registers, 16 warps per SM).  Takes its pairs from big_list.
+template <int BMAX>
+__global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(const LinearParams p)
 {
     const TcmDev &tcm = p.tcm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int dim = 1 << tcm.a;
+    const BatchDev &b = p.b;
+    const uint32_t n_work = BMAX <= 8 ? b.n_pairs : *p.big_count;
+    if (n_work == 0) return;
 
     char *tab = smem;
     uint32_t *s_cgap = reinterpret_cast<uint32_t *>(smem + tcm.sub4_bytes);
     uint32_t *s_gapc = s_cgap + dim;
     char *warp_base = reinterpret_cast<char *>(s_gapc + dim);
-    const uint32_t per_warp = 384u + 2u * p.seq_cap;
+    const uint32_t per_warp = 384u + p.seq_cap;
     uint32_t *s_flags = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
     uint32_t *s_nal = s_flags + 32;
     uint32_t *s_off = s_flags + 64;
@@ -312,20 +350,22 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
     for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_cgap[i] = tcm.cgap[i]; s_gapc[i] = tcm.gapc[i]; }
     __syncthreads();
 
-    const uint32_t tab_lane = tcm.repl ? 4u * lane : 0u;
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(tab) + (tcm.repl ? 4u * lane : 0u);
+    const FillConst fc = {p.k_four, p.k_minus1, p.l_stride};
     const int G = p.pairs_per_warp;
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
-    const BatchDev &b = p.b;
+    unsigned int *counter = BMAX <= 8 ? p.counter : p.counter + 2;
+    const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
 
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
+        if (lane == 0) base = atomicAdd(counter, (unsigned)G);
         base = __shfl_sync(kFull, base, 0);
-        if (base >= b.n_pairs) break;
-        const int npw = (int)min((uint32_t)G, b.n_pairs - base);
+        if (base >= n_work) break;
+        const int npw = (int)min((uint32_t)G, n_work - base);
+        auto pair_of = [&](int pi) -> uint32_t { return BMAX <= 8 ? base + pi : p.big_list[base + pi]; };
 
-        const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
         int pi = 0;
         while (pi < npw) {
             const int start = pi;
@@ -333,26 +373,27 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
             // -------------------------------------------------------------- fill, pair after pair,
             // until the warp's scratch arena is full
             for (; pi < npw; ++pi) {
-                const uint32_t k = base + pi;
+                const uint32_t k = pair_of(pi);
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                 const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
                 const bool fl = first_is_long(p1, n1, p2, n2, lane);
                 const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
                 const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                 const int B = choose_b(g.wb);
+                if (BMAX <= 8 && B > 8) {                   // hand over to the wide kernel
+                    if (lane == 0) { s_flags[pi] = 0; p.big_list[atomicAdd(p.big_count, 1u)] = k; }
+                    continue;
+                }
                 bool ok = B != 0;
                 SeqLayout sl = {0, 0, 0, 0};
                 uint32_t need = 0;
                 if (ok) {
                     sl = seq_layout(g, B);
                     need = (dir_words(g, B) + ops_words(g) + 3u) & ~3u;
-                    ok = (uint32_t)(sl.sizeL + sl.sizeS) <= p.seq_cap && need <= p.arena_words;
+                    ok = seq_bytes(sl) <= p.seq_cap && need <= p.arena_words;
                 }
                 if (!ok) {
-                    if (lane == 0) {
-                        s_flags[pi] = 0;
-                        p.overflow_list[atomicAdd(p.overflow_count, 1u)] = k;
-                    }
+                    if (lane == 0) { s_flags[pi] = 0; p.overflow_list[atomicAdd(p.overflow_count, 1u)] = k; }
                     continue;
                 }
                 if (cur + need > p.arena_words) break;     // trace + emit what we have, then go on
@@ -360,18 +401,17 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
                 uint32_t *slot = arena + cur;
                 cur += need;
 
-                // stage both strings in "table address" form; sum the indel costs folded out of the cells
-                uint16_t *Lr = reinterpret_cast<uint16_t *>(seq);
-                uint16_t *Sr = Lr + sl.sizeL;
+                // stage both strings; sum the indel costs that are folded out of the cell values
+                uint16_t *Sr = reinterpret_cast<uint16_t *>(seq);
+                uint8_t *Lr = reinterpret_cast<uint8_t *>(Sr + sl.sizeS);
                 uint32_t csum = 0;
-                const int lshift = tcm.repl ? 11 : tcm.a;
                 const uint32_t emask = (uint32_t)dim - 1u;
                 for (int idx = lane; idx < sl.sizeL; idx += 32) {
                     const int i = idx - sl.offL;
                     uint32_t e = 0;
                     if (i == 0) e = tcm.gap;
                     else if (i > 0 && i < g.lg) { e = __ldg(pL + i - 1) & emask; csum += s_cgap[e]; }
-                    Lr[idx] = (uint16_t)(e << lshift);
+                    Lr[idx] = (uint8_t)e;
                 }
                 for (int idx = lane; idx < sl.sizeS; idx += 32) {
                     const int j = idx - sl.offS;
@@ -386,9 +426,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
 
                 const char *Lb = reinterpret_cast<const char *>(Lr + sl.offL);
                 const char *Sb = reinterpret_cast<const char *>(Sr + sl.offS);
-                uint32_t fw;
-                if (tcm.repl) fw = dispatch_fill<1>(B, g, tab, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
-                else          fw = dispatch_fill<2>(B, g, tab, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+                const uint32_t fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
                 if (lane == 0) b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
                 if (b.cells) {
                     unsigned long long c = band_cells(g, lane, 32);
@@ -404,7 +442,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
             // -------------------------------------------------------------- trace: lane = pair
             const int pj = start + lane;
             if (pj < pi && (s_flags[pj] & 2u)) {
-                const uint32_t k = base + pj;
+                const uint32_t k = pair_of(pj);
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                 const bool fl = s_flags[pj] & 1u;
                 const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
@@ -421,7 +459,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
                 for (int pe = start; pe < pi; ++pe) {
                     const uint32_t fl_ok = s_flags[pe];
                     if (!(fl_ok & 2u)) continue;
-                    const uint32_t k = base + pe;
+                    const uint32_t k = pair_of(pe);
                     const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                     const bool fl = fl_ok & 1u;
                     const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
@@ -440,17 +478,31 @@ __global__ void __launch_bounds__(512, 1) do_linear_kernel(const LinearParams p)
     }
 }
 
-// Host-side launcher (called from do_api.cu).
-cudaError_t launch_linear(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+// Host-side launchers (called from do_api.cu).
+cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(do_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(do_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(do_linear_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    do_linear_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    if (wide) do_linear_kernel<32><<<grid, block, smem_bytes, stream>>>(p);
+    else      do_linear_kernel<8><<<grid, block, smem_bytes, stream>>>(p);
     return cudaGetLastError();
+}
+
+// worst-case staging bytes for strings of up to max_len elements with B diagonals per lane
+uint32_t seq_cap_for(int max_len, int B)
+{
+    const int H = B / 2;
+    const int tpad = (max_len + 1 + 15) & ~15;
+    const int q0h = 16 * B + 1;                       // q0 / 2 <= wb / 2 <= 16 B
+    const int sizeL = 32 * H + tpad + q0h + 8;
+    const int sizeS = q0h + tpad + 32 * H + 8;
+    return (uint32_t)((2 * sizeS + sizeL + 15) & ~15);
 }
 
 }  // namespace pcgdo

@@ -10,7 +10,8 @@ traceback addressing) can be checked against the oracle on a CPU:
     folded out so `up` needs no add and `left` only the +1 priority bump);
     candidates: diag = w[q] + (4*sub' - 1)  (code 0 = ALIGN), up = w[q+1] (code 1 = DELETE),
     left = w[q-1] + 1 (code 2 = INSERT); stored back as (min & ~3) | 1 | pen;
-  * direction words: word[(t >> 4) * Wq + q] gets code << 2*(t & 15).
+  * direction words: word[(t >> 4) * Wq + q] gets code << 2*(15 - (t & 15)); diagonals q = 0 and
+    q = Wq - 1 are always masked so the block-edge shuffles of lanes 0 / 31 need no special case.
 """
 import numpy as np
 
@@ -40,10 +41,11 @@ def fill(cost, a, lng, shr, lanes_b=None):
     lg, sh = len(lng), len(shr)
     gap = 1 << (a - 1)
     dlo, dhi = band_diagonals(lg, sh)
-    pad = (-dlo) & 1
+    pad = 1 + ((1 - dlo) & 1)                 # q = 0 always masked, q0 even
     q0 = -dlo + pad
     wb = dhi - dlo + 1 + pad
-    wq = wb if lanes_b is None else -(-wb // lanes_b) * lanes_b
+    b = lanes_b or 2
+    wq = -(-(wb + 1) // (32 * b)) * 32 * b    # the last diagonal of the warp stays masked too
     cost = cost.astype(np.int64)
     cg = cost[:, gap]                 # c(x) = cost[x][gap]
     gc = cost[gap, :]                 # g(y) = cost[gap][y]
@@ -81,7 +83,7 @@ def fill(cost, a, lng, shr, lanes_b=None):
             lf = w[q] + 1
             mn = np.minimum(np.minimum(dg, up), lf)
             assert (mn >= 0).all() and (mn < (1 << 32)).all()
-            words[t >> 4, q] |= ((mn & 3) << (2 * (t & 15))).astype(np.uint32)
+            words[t >> 4, q] |= ((mn & 3) << (2 * (15 - (t & 15)))).astype(np.uint32)
             w[1 + q] = (mn & ~3) | 1 | pen[q]
         if t == T - 1:
             final = int(w[1 + q_last])
@@ -97,7 +99,7 @@ def trace(words, geom, lg, sh):
     while i > 0 or j > 0:
         q = j - i + q0
         t = (i + j - (q & 1)) >> 1
-        code = (int(words[t >> 4, q]) >> (2 * (t & 15))) & 3
+        code = (int(words[t >> 4, q]) >> (2 * (15 - (t & 15)))) & 3
         ops.append(code)
         if code == 0:
             i -= 1; j -= 1
