@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
+    ap.add_argument("--warps", type=int, default=32, help="warps per CTA of the narrow kernel")
+    ap.add_argument("--ppw", type=int, default=8, help="pairs a warp fills before tracing them")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -193,7 +195,7 @@ def main():
 
     n = args.pairs
     ctx = P.Context(local_rank)
-    ctx.configure(pairs_per_warp=32, warps_per_cta=16, max_len=1024, max_b=8)
+    ctx.configure(pairs_per_warp=args.ppw, warps_per_cta=args.warps, max_len=1024, max_b=8)
     tcm = ctx.tcm(l1_tcm())
     strings = make_strings(n, rank)
     pp = P.PackedPairs.uniform(strings)
@@ -312,7 +314,7 @@ def main():
             pass
     roofline = {"bound": "int32-issue", "achieved": achieved_tops, "peak": int_peak, "unit": "Tinstr/s",
                 "frac": achieved_tops / int_peak if int_peak else None, "traffic": traffic,
-                "peak_source": "measured live (pcgdo_int32_peak: independent VIMNMX/IMAD chains on all SMs)",
+                "peak_source": "measured live (pcgdo_int32_peak: independent VIADDMNMX+IMAD chains on all SMs)",
                 "alg_ops_per_cell": ALG_OPS_PER_CELL, "kernel_ms": k_ms,
                 "hbm": {"alg_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

@@ -14,6 +14,9 @@
 namespace pcgdo {
 cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 uint32_t seq_cap_for(int max_len, int B);
+uint64_t general_words_for(uint32_t n1, uint32_t n2);
+cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_t *list, const uint64_t *scratch_off,
+                           uint32_t *scratch, cudaStream_t stream);
 }
 namespace pcgdo {
 double launch_int_peak(int mode, int grid, int iters, uint32_t *scratch, cudaStream_t st);
@@ -24,7 +27,7 @@ struct pcgdo_tcm {
     TcmDev dev{};
     size_t a = 0;
     unsigned int gap_open = 0;
-    void *d_sub4 = nullptr, *d_median = nullptr, *d_cgap = nullptr, *d_gapc = nullptr;
+    void *d_sub4 = nullptr, *d_sub4_nat = nullptr, *d_median = nullptr, *d_cgap = nullptr, *d_gapc = nullptr;
 };
 
 struct DevBuf {
@@ -46,7 +49,7 @@ struct pcgdo_ctx {
     int max_b = 8;
     size_t arena_words = 0;          // 0 = derive from max_len
     // device scratch
-    DevBuf arena, counters, overflow, big;
+    DevBuf arena, counters, overflow, big, gen_scratch, gen_off;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
     std::string err;
@@ -113,7 +116,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
                       &ctx->d_olen, &ctx->d_cost, &ctx->d_cells};
     for (DevBuf *b : bufs)
@@ -206,6 +209,10 @@ static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, cons
         return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
     };
     CK(up(&t->d_sub4, tab.data(), tab.size() * 2));
+    std::vector<int16_t> nat2(dim * dim, (int16_t)kBigSub);     // plain [l << a | s] for the general kernel
+    for (size_t l = 1; l < dim; ++l)
+        for (size_t sx = 1; sx < dim; ++sx) nat2[(l << a) + sx] = nat[l * rdim + sx];
+    CK(up(&t->d_sub4_nat, nat2.data(), nat2.size() * 2));
     CK(up(&t->d_median, med.data(), med.size()));
     CK(up(&t->d_cgap, cgap.data(), cgap.size() * 4));
     CK(up(&t->d_gapc, gapc.data(), gapc.size() * 4));
@@ -215,6 +222,7 @@ static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, cons
     t->dev.sub4_bytes = (uint32_t)(tab.size() * 2);
     t->dev.sub4_gapgap = (int32_t)(4 * (C(gap, gap) - C(gap, gap) - C(gap, gap)) - 1);
     t->dev.sub4 = (const int16_t *)t->d_sub4;
+    t->dev.sub4_nat = (const int16_t *)t->d_sub4_nat;
     t->dev.median = (const uint8_t *)t->d_median;
     t->dev.cgap = (const uint32_t *)t->d_cgap;
     t->dev.gapc = (const uint32_t *)t->d_gapc;
@@ -241,6 +249,7 @@ extern "C" void pcgdo_tcm_destroy(pcgdo_ctx *ctx, pcgdo_tcm *t)
     if (!t) return;
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(t->d_sub4);
+    cudaFree(t->d_sub4_nat);
     cudaFree(t->d_median);
     cudaFree(t->d_cgap);
     cudaFree(t->d_gapc);
@@ -335,18 +344,63 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
 
-    // pairs the warp kernel could not hold (band wider than 1024 diagonals, strings longer than the
-    // staging window, scratch larger than the arena) are reported, not silently dropped
     unsigned int h_cnt[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(h_cnt, p.counter, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const unsigned int h_over = h_cnt[1] + (wide_ok ? 0u : h_cnt[3]);
-    if (h_over) {
-        char msg[160];
-        snprintf(msg, sizeof msg, "%u pair(s) exceed the fast path's limits (max_len=%d, max_b=%d); raise them with pcgdo_configure",
-                 h_over, ctx->max_len, ctx->max_b);
-        ctx->err = msg;
-        return PCGDO_ERR_OVERFLOW;
+    // pairs the warp kernels could not hold (band wider than 1023 diagonals, strings longer than the
+    // staging window, scratch larger than the arena; plus the wide queue when that kernel is disabled)
+    // go through the general-geometry kernel: one CTA per pair, scratch sized from their lengths
+    std::vector<uint32_t> todo;
+    if (h_cnt[1]) {
+        todo.resize(h_cnt[1]);
+        CK(cudaMemcpyAsync(todo.data(), p.overflow_list, (size_t)h_cnt[1] * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (!wide_ok && h_cnt[3]) {
+        const size_t o = todo.size();
+        todo.resize(o + h_cnt[3]);
+        CK(cudaMemcpyAsync(todo.data() + o, p.big_list, (size_t)h_cnt[3] * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (!todo.empty()) {
+        CK(cudaStreamSynchronize(st));
+        std::vector<uint32_t> l1(todo.size()), l2(todo.size());
+        if (todo.size() > 256) {
+            std::vector<uint32_t> a1(b->n_pairs), a2(b->n_pairs);
+            CK(cudaMemcpyAsync(a1.data(), b->len1, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(a2.data(), b->len2, b->n_pairs * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < todo.size(); ++i) { l1[i] = a1[todo[i]]; l2[i] = a2[todo[i]]; }
+        } else {
+            for (size_t i = 0; i < todo.size(); ++i) {
+                CK(cudaMemcpyAsync(&l1[i], b->len1 + todo[i], 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&l2[i], b->len2 + todo[i], 4, cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaStreamSynchronize(st));
+        }
+        // bounded scratch: run the list in slices of at most ~8 GB
+        size_t i0 = 0;
+        while (i0 < todo.size()) {
+            std::vector<uint64_t> off;
+            uint64_t words = 0;
+            size_t i1 = i0;
+            while (i1 < todo.size()) {
+                const uint64_t w = general_words_for(l1[i1], l2[i1]);
+                if (i1 > i0 && (words + w) * 4 > ((uint64_t)8 << 30)) break;
+                off.push_back(words);
+                words += w;
+                ++i1;
+            }
+            if ((rc = ensure(ctx, ctx->gen_scratch, words * 4))) return rc;
+            if ((rc = ensure(ctx, ctx->gen_off, off.size() * 8 + (i1 - i0) * 4))) return rc;
+            uint64_t *d_off = (uint64_t *)ctx->gen_off.p;
+            uint32_t *d_list = (uint32_t *)(d_off + off.size());
+            CK(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_list, todo.data() + i0, (i1 - i0) * 4, cudaMemcpyHostToDevice, st));
+            CK(launch_general(p, (uint32_t)(i1 - i0), d_list, d_off, (uint32_t *)ctx->gen_scratch.p, st));
+            ctx->last_launches += 1;
+            CK(cudaStreamSynchronize(st));
+            i0 = i1;
+        }
+        CK(cudaEventRecord(ctx->ev1, st));
     }
     return PCGDO_OK;
 }

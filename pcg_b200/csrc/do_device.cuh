@@ -17,6 +17,7 @@ struct TcmDev {
     uint32_t       sub4_bytes; // bytes of `sub4` to stage in shared memory
     int32_t        sub4_gapgap;
     const int16_t *sub4;       // 4*(cost[l][s] - cost[l][gap] - cost[gap][s]) - 1 ; row/col 0 = kBigSub
+    const int16_t *sub4_nat;   // the same table in plain [l << a | s] layout (general-geometry kernel)
     const uint8_t *median;     // [dim*dim]
     const uint32_t *cgap;      // [dim] cost[x][gap]   (indel of consuming x from the longer string)
     const uint32_t *gapc;      // [dim] cost[gap][y]

@@ -478,6 +478,113 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// General-geometry kernel: one CTA per pair, any band width / string length.  Same recurrence, same
+// direction-word layout (so trace_lane / emit_pair are shared), but the diagonal values live in global
+// memory and each anti-diagonal is swept by the whole CTA with a barrier in between.  Used only for the
+// pairs the warp kernels cannot hold (band wider than 1023 diagonals, strings beyond the shared-memory
+// window): correct for every input, not tuned.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t general_wq(const Geom &g) { return (uint32_t)(g.wb + 1 + 3) & ~3u; }
+__host__ __device__ inline uint64_t general_words(const Geom &g)
+{
+    const uint64_t wq = general_wq(g);
+    return (wq + 8) + (uint64_t)((g.T + 15) / 16) * wq + ops_words(g) + 8;
+}
+
+__global__ void __launch_bounds__(256) do_general_kernel(const LinearParams p, const uint32_t *list,
+                                                         const uint64_t *scratch_off, uint32_t *scratch)
+{
+    const TcmDev &tcm = p.tcm;
+    const BatchDev &b = p.b;
+    const uint32_t k = list[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_fl;
+    __shared__ uint32_t s_red[8];
+    __shared__ uint32_t s_n;
+    const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+    const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+    if (warp == 0) {
+        const bool f = first_is_long(p1, n1, p2, n2, lane);
+        if (lane == 0) s_fl = f;
+    }
+    __syncthreads();
+    const bool fl = s_fl != 0;
+    const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
+    const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+    const uint32_t wq = general_wq(g);
+    uint32_t *w = scratch + scratch_off[blockIdx.x];          // w[1 + q], fences at 0 and wq + 1
+    uint32_t *dirw = w + wq + 8;
+    const uint32_t ndir = (uint32_t)((g.T + 15) / 16) * wq;
+    uint32_t *ops = dirw + ndir;
+    for (uint32_t i = threadIdx.x; i < wq + 8; i += blockDim.x) w[i] = kInfW;
+    for (uint32_t i = threadIdx.x; i < ndir; i += blockDim.x) dirw[i] = 0;
+    uint32_t csum = 0;
+    const uint32_t emask = (1u << tcm.a) - 1u;
+    for (int i = 1 + threadIdx.x; i < g.lg; i += blockDim.x) csum += tcm.cgap[pL[i - 1] & emask];
+    for (int j = 1 + threadIdx.x; j < g.sh; j += blockDim.x) csum += tcm.gapc[pS[j - 1] & emask];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+    if (lane == 0) s_red[warp] = csum;
+    __syncthreads();
+    csum = 0;
+    for (int x = 0; x < (int)(blockDim.x >> 5); ++x) csum += s_red[x];
+    if (threadIdx.x == 0) w[1 + g.q0] = kBias4 - (uint32_t)tcm.sub4_gapgap;
+    __syncthreads();
+
+    const int smax = (g.lg - 1) + (g.sh - 1);
+    for (int s = 0; s <= smax; ++s) {
+        const int i_lo = s - (g.sh - 1) > 0 ? s - (g.sh - 1) : 0;
+        const int i_hi = s < g.lg - 1 ? s : g.lg - 1;
+        for (int i = i_lo + (int)threadIdx.x; i <= i_hi; i += blockDim.x) {
+            const int j = s - i;
+            const int q = j - i + g.q0;
+            if (q < g.pad || q >= g.wb) continue;
+            const uint32_t l = i == 0 ? tcm.gap : (pL[i - 1] & emask);
+            const uint32_t sj = j == 0 ? tcm.gap : (pS[j - 1] & emask);
+            const uint32_t sub = (uint32_t)(int)tcm.sub4_nat[(l << tcm.a) | sj];
+            const uint32_t t1 = __viaddmin_u32(w[1 + q], sub, w[2 + q]);
+            const uint32_t mn = __viaddmin_u32(w[q], 1u, t1);
+            const int t = (s - (q & 1)) >> 1;
+            dirw[(uint32_t)(t >> 4) * wq + (uint32_t)q] |= (mn & 3u) << (2 * (15 - (t & 15)));
+            w[1 + q] = (mn & ~3u) | 1u;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
+        b.cost[k] = (int32_t)((w[1 + q_last] >> 2) - (kBias4 >> 2) + csum);
+        if (b.cells) b.cells[k] = band_cells(g, 0, 1);
+        const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
+        uint32_t n = 0;
+        if (want_out) {
+            n = trace_lane(dirw, wq, g.q0, g.lg, g.sh, ops);
+            if (b.out_len) b.out_len[k] = n;
+        }
+        s_n = n;
+        __threadfence_block();
+    }
+    __syncthreads();
+    if (warp == 0 && (b.out_gapped || b.out_slot1 || b.out_slot2)) {
+        const uint64_t oo = b.out_off[k];
+        emit_pair(tcm, pL, pS, ops, s_n, fl, b.out_gapped ? b.out_gapped + oo : nullptr,
+                  b.out_slot1 ? b.out_slot1 + oo : nullptr, b.out_slot2 ? b.out_slot2 + oo : nullptr, lane);
+    }
+}
+
+uint64_t general_words_for(uint32_t n1, uint32_t n2)
+{
+    const uint32_t lg = (n1 > n2 ? n1 : n2) + 1, sh = (n1 > n2 ? n2 : n1) + 1;
+    return (general_words(make_geom((int)lg, (int)sh)) + 3) & ~(uint64_t)3;
+}
+
+cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_t *list, const uint64_t *scratch_off,
+                           uint32_t *scratch, cudaStream_t stream)
+{
+    do_general_kernel<<<n_list, 256, 0, stream>>>(p, list, scratch_off, scratch);
+    return cudaGetLastError();
+}
+
 // Host-side launchers (called from do_api.cu).
 cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {

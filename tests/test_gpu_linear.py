@@ -186,3 +186,36 @@ def test_config2_shape_properties_and_sample(oracle_mod, gpu_ctx):
         c, g, s1, s2 = r.pair(pp, k)
         c2, g2, t1, t2 = r2.pair(pp2, k)
         assert c == c2 and np.array_equal(g, g2) and np.array_equal(s1, t2) and np.array_equal(s2, t1)
+
+
+def test_general_geometry_kernel(oracle_mod, gpu_ctx):
+    """Pairs the warp kernels cannot hold (forced by a tiny max_len / max_b, and genuinely wide ones)
+    take the one-CTA-per-pair kernel and must give the same bits."""
+    sig = tcm_matrix("l1")
+    o = oracle_mod.Oracle(sig)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(77)
+    pairs = [random_pair(rng, 400) for _ in range(40)]
+    pairs.append((random_string(rng, 2300), random_string(rng, 900)))     # full matrix, 3200 diagonals
+    pairs.append((random_string(rng, 1500), random_string(rng, 1400)))
+    pairs.append((random_string(rng, 700), random_string(rng, 1)))
+    gpu_ctx.configure(max_len=64, max_b=8)          # almost everything overflows the staging window
+    _check_batch(o, gpu_ctx, tcm, pairs)
+    gpu_ctx.configure(max_len=2400, max_b=8)        # wide kernel disabled: B > 8 pairs go to the general kernel
+    _check_batch(o, gpu_ctx, tcm, pairs)
+    gpu_ctx.configure(max_len=2400, max_b=32)       # everything that fits a warp stays on the warp kernels
+    _check_batch(o, gpu_ctx, tcm, pairs)
+
+
+def test_bench_strings_dna_all_pairs(oracle_mod, gpu_ctx):
+    """BASELINE config 1 shape: every unordered pair of 20 strings with lengths 8 ... 4608 (half of them
+    ambiguous), discrete TCM — synthetic stand-ins with the reference file's lengths."""
+    sig = tcm_matrix("discrete")
+    o = oracle_mod.Oracle(sig)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(20)
+    lens = [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 9, 18, 36, 72, 144, 288, 576, 1152, 2304, 4608]
+    strs = [random_string(rng, n, amb=0.0 if k < 10 else 0.5) for k, n in enumerate(lens)]
+    pairs = [(strs[i], strs[j]) for i in range(20) for j in range(i + 1, 20)]
+    gpu_ctx.configure(max_len=4700, max_b=32)
+    _check_batch(o, gpu_ctx, tcm, pairs, want_cells=True)
