@@ -130,6 +130,40 @@ int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo
 /* Host buffers in, host buffers out: H2D copies, kernels and D2H copies inside the call. */
 int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b);
 
+/* Finer tunables: widest diagonals-per-lane variant the warp kernels must accommodate (2,4,8,16,32; pairs
+ * needing more go to the general-geometry kernel) and the per-warp scratch arena in 32-bit words (0 = derive
+ * from max_len). */
+int pcgdo_configure_ex(pcgdo_ctx *ctx, int max_b, size_t arena_words);
+
+/* ---------------------------------------------------------------- post-order tree scoring
+ * Replaces the post-order sweep that calls the pairwise DO once per internal node and dynamic character
+ * (Bio/Graph/PhylogeneticDAG/Postorder.hs:98-158, DO/Internal.hs:109-140): all nodes of equal height
+ * across all candidate trees and characters are aligned in one launch; nodes keep their ungapped median
+ * strings resident in HBM.
+ *   n_taxa leaves have node ids 0 .. n_taxa-1 (shared by all trees), internal node x of a tree has id
+ *   n_taxa + x; children[(t*(n_taxa-1) + x)*2 + {0,1}] are the two child ids of internal node x of tree t.
+ *   node_cap = byte capacity of every node's median string. */
+typedef struct pcgdo_forest pcgdo_forest;
+int  pcgdo_forest_create(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
+                         const int32_t *children, pcgdo_forest **out);
+void pcgdo_forest_destroy(pcgdo_ctx *ctx, pcgdo_forest *forest);
+/* HOST buffers: character c of taxon v = elems[off[v*n_chars+c] .. +len[v*n_chars+c]) (no gap elements). */
+int  pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *forest, const uint8_t *elems, const uint64_t *off,
+                             const uint32_t *len);
+/* One sweep: every internal node's local cost, total cost (local + children, DO/Internal.hs:133-137) and
+ * ungapped median; per-tree cost = sum over this forest's characters of the root total. */
+int  pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *forest, void *cuda_stream);
+void *pcgdo_forest_tree_cost_ptr(pcgdo_forest *forest);              /* DEVICE int64[n_trees]          */
+int  pcgdo_forest_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *forest, int64_t *host_out);
+int  pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *forest, uint32_t tree, uint32_t character, uint32_t node,
+                           uint8_t *median_out, uint32_t *len_out, int32_t *local_cost, int64_t *total_cost);
+uint32_t pcgdo_forest_levels(const pcgdo_forest *forest);
+uint64_t pcgdo_forest_alignments(const pcgdo_forest *forest);
+
+/* Measured integer instruction-issue rate of this GPU in lane-instructions/s (roofline denominator of the
+ * DP fill; mode 0: ALU-pipe mix, 1: VIADDMNMX + IMAD, one per pipe). */
+int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, float *ms_out);
+
 /* Timing of the kernels of the most recent *_device / *_host call on this context, measured with
  * CUDA events on the launching stream (ms); also the number of kernel launches it made. */
 int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches);

@@ -23,6 +23,10 @@ EXPORTED_SYMBOLS = [
     "pcgdo_create", "pcgdo_destroy", "pcgdo_last_error", "pcgdo_configure",
     "pcgdo_tcm_create", "pcgdo_tcm_destroy",
     "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
+    "pcgdo_configure_ex", "pcgdo_int32_peak",
+    "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
+    "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
+    "pcgdo_forest_alignments",
 ]
 
 
@@ -78,6 +82,20 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_align2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
     L.pcgdo_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.pcgdo_int32_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.pcgdo_forest_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                      C.POINTER(C.c_void_p)]
+    L.pcgdo_forest_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_set_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_tree_cost_ptr.argtypes = [C.c_void_p]
+    L.pcgdo_forest_tree_cost_ptr.restype = C.c_void_p
+    L.pcgdo_forest_tree_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_get_node.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.pcgdo_forest_levels.argtypes = [C.c_void_p]
+    L.pcgdo_forest_levels.restype = C.c_uint32
+    L.pcgdo_forest_alignments.argtypes = [C.c_void_p]
+    L.pcgdo_forest_alignments.restype = C.c_uint64
     L.setUp2dCostMtx.argtypes = [C.POINTER(CostMatrices2D), _u32p, C.c_size_t, C.c_uint]
     L.setUp2dCostMtx.restype = None
     L.align2d.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int, C.c_int, C.c_int]
@@ -161,5 +179,72 @@ class Tcm:
         try:
             if self.h.value and self.ctx.h.value:
                 self.ctx.lib.pcgdo_tcm_destroy(self.ctx.h, self.h)
+        except Exception:
+            pass
+
+
+class Forest:
+    """Candidate trees x dynamic characters resident on one GPU (pcgdo_forest): post-order scoring.
+
+    ``children``: int32 array (n_trees, n_taxa-1, 2) of child node ids (leaves 0..n_taxa-1, internal node x
+    has id n_taxa + x).  ``leaves``: list over taxa of lists over characters of uint8 element strings."""
+
+    def __init__(self, ctx: Context, children, n_taxa: int, leaves, node_cap: int):
+        self.ctx = ctx
+        ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
+        assert ch.ndim == 3 and ch.shape[1] == n_taxa - 1 and ch.shape[2] == 2
+        self.n_trees, self.n_taxa = int(ch.shape[0]), int(n_taxa)
+        self.n_chars = len(leaves[0])
+        self.node_cap = (int(node_cap) + 3) & ~3
+        h = C.c_void_p()
+        ctx.check(ctx.lib.pcgdo_forest_create(ctx.h, self.n_trees, self.n_taxa, self.n_chars, self.node_cap,
+                                              ch.ctypes.data, C.byref(h)), "pcgdo_forest_create")
+        self.h = h
+        flat = [np.asarray(s, np.uint8) for taxon in leaves for s in taxon]
+        ln = np.array([len(s) for s in flat], np.uint32)
+        off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
+        elems = np.concatenate(flat) if flat else np.zeros(0, np.uint8)
+        elems = np.ascontiguousarray(elems)
+        ctx.check(ctx.lib.pcgdo_forest_set_leaves(ctx.h, self.h, elems.ctypes.data, off.ctypes.data, ln.ctypes.data),
+                  "pcgdo_forest_set_leaves")
+
+    def score(self, tcm: Tcm, stream: int = 0) -> np.ndarray:
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+                       "pcgdo_forest_score")
+        out = np.zeros(self.n_trees, np.int64)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_tree_costs(self.ctx.h, self.h, out.ctypes.data),
+                       "pcgdo_forest_tree_costs")
+        return out
+
+    def score_async(self, tcm: Tcm, stream: int = 0) -> int:
+        """Sweep only; returns the DEVICE pointer of the int64[n_trees] cost vector."""
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+                       "pcgdo_forest_score")
+        return int(self.ctx.lib.pcgdo_forest_tree_cost_ptr(self.h))
+
+    def node(self, tree: int, character: int, node: int):
+        buf = np.zeros(self.node_cap, np.uint8)
+        n, lc, tc = C.c_uint32(0), C.c_int32(0), C.c_int64(0)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_get_node(self.ctx.h, self.h, tree, character, node, buf.ctypes.data,
+                                                          C.byref(n), C.byref(lc), C.byref(tc)),
+                       "pcgdo_forest_get_node")
+        return buf[:n.value].copy(), int(lc.value), int(tc.value)
+
+    @property
+    def levels(self) -> int:
+        return int(self.ctx.lib.pcgdo_forest_levels(self.h))
+
+    @property
+    def alignments(self) -> int:
+        return int(self.ctx.lib.pcgdo_forest_alignments(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value and self.ctx.h.value:
+            self.ctx.lib.pcgdo_forest_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

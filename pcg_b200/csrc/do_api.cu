@@ -1,7 +1,6 @@
 // do_api.cu — C ABI of the DO backend (include/pcg_do_b200.h): context, TCM upload, batched
 // launches, and the reference-compatible single-pair shims.
-#include "do_device.cuh"
-#include "do_host.h"
+#include "do_ctx.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -23,48 +22,7 @@ double launch_int_peak(int mode, int grid, int iters, uint32_t *scratch, cudaStr
 }
 using namespace pcgdo;
 
-struct pcgdo_tcm {
-    TcmDev dev{};
-    size_t a = 0;
-    unsigned int gap_open = 0;
-    void *d_sub4 = nullptr, *d_sub4_nat = nullptr, *d_median = nullptr, *d_cgap = nullptr, *d_gapc = nullptr;
-};
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
-struct pcgdo_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-    int last_launches = 0;
-    // tunables
-    int pairs_per_warp = 32;
-    int warps_per_cta = 32;
-    int max_len = 1024;
-    int max_b = 8;
-    size_t arena_words = 0;          // 0 = derive from max_len
-    // device scratch
-    DevBuf arena, counters, overflow, big, gen_scratch, gen_off;
-    // staging for the host-buffer entry point
-    DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
-    std::string err;
-};
-
-#define CK(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e__ = (call);                                                             \
-        if (e__ != cudaSuccess) {                                                             \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
-            return PCGDO_ERR_CUDA;                                                            \
-        }                                                                                     \
-    } while (0)
-
-static int ensure(pcgdo_ctx *ctx, DevBuf &b, size_t bytes)
+int pcgdo_ensure(pcgdo_ctx *ctx, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return PCGDO_OK;
     if (b.p) CK(cudaFree(b.p));
@@ -264,23 +222,9 @@ static size_t smem_for(const pcgdo_tcm *tcm, int warps, uint32_t seq_cap)
     return tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps * (384 + (size_t)seq_cap);
 }
 
-extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream)
+int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &bd, cudaStream_t st,
+                         bool reset_overflow, LinearParams *out_p, bool *wide_ok_out)
 {
-    if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
-    ctx->timed = false;
-    ctx->last_launches = 0;
-    if (b->n_pairs == 0) return PCGDO_OK;
-    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost) {
-        ctx->err = "bad batch description";
-        return PCGDO_ERR_ARG;
-    }
-    if ((b->out_gapped || b->out_slot1 || b->out_slot2) && !b->out_off) {
-        ctx->err = "out_off required when aligned strings are requested";
-        return PCGDO_ERR_ARG;
-    }
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-
     // shared-memory window per warp: both strings + paddings for the widest variant of each kernel
     const uint32_t cap_n = seq_cap_for(ctx->max_len, ctx->max_b < 8 ? ctx->max_b : 8);
     const uint32_t cap_w = seq_cap_for(ctx->max_len, 32);
@@ -302,28 +246,20 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     arena_words = (arena_words + 3) & ~(size_t)3;
     if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
     int rc;
-    if ((rc = ensure(ctx, ctx->arena, (size_t)grid * warps_max * arena_words * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->counters, 64))) return rc;
-    if ((rc = ensure(ctx, ctx->overflow, b->n_pairs * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->big, b->n_pairs * 4))) return rc;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps_max * arena_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->overflow, (size_t)bd.n_pairs * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 16, st));
 
     LinearParams p{};
     p.tcm = tcm->dev;
-    p.b.n_pairs = (uint32_t)b->n_pairs;
-    p.b.elems = b->elems;
-    p.b.off1 = b->off1; p.b.off2 = b->off2;
-    p.b.len1 = b->len1; p.b.len2 = b->len2;
-    p.b.out_off = b->out_off;
-    p.b.out_gapped = b->out_gapped; p.b.out_slot1 = b->out_slot1; p.b.out_slot2 = b->out_slot2;
-    p.b.out_len = b->out_len;
-    p.b.cost = b->cost;
-    p.b.cells = b->cells;
+    p.b = bd;
     p.arena = (uint32_t *)ctx->arena.p;
     p.arena_words = (uint32_t)arena_words;
     p.pairs_per_warp = ctx->pairs_per_warp;
     p.counter = (unsigned int *)ctx->counters.p;
-    p.overflow_count = p.counter + 1;
+    p.overflow_count = p.counter + 8;
     p.big_count = p.counter + 3;
     p.overflow_list = (uint32_t *)ctx->overflow.p;
     p.big_list = (uint32_t *)ctx->big.p;
@@ -331,29 +267,66 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     p.k_minus1 = 0xffffffffu;
     p.l_stride = tcm->dev.repl ? 2048u : (2u << tcm->a);
 
-    CK(cudaEventRecord(ctx->ev0, st));
     p.seq_cap = cap_n;
     CK(launch_linear(p, false, grid, warps_n * 32, smem_for(tcm, warps_n, cap_n), st));
-    ctx->last_launches = 1;
+    ctx->last_launches += 1;
     if (wide_ok) {
         // consumes the queue the narrow kernel built on the device; exits at once when it is empty
         p.seq_cap = cap_w;
         CK(launch_linear(p, true, grid, warps_w * 32, smem_for(tcm, warps_w, cap_w), st));
-        ctx->last_launches = 2;
+        ctx->last_launches += 1;
     }
+
+    if (out_p) *out_p = p;
+    if (wide_ok_out) *wide_ok_out = wide_ok;
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream)
+{
+    if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost) {
+        ctx->err = "bad batch description";
+        return PCGDO_ERR_ARG;
+    }
+    if ((b->out_gapped || b->out_slot1 || b->out_slot2) && !b->out_off) {
+        ctx->err = "out_off required when aligned strings are requested";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+
+    BatchDev bd{};
+    bd.n_pairs = (uint32_t)b->n_pairs;
+    bd.elems = b->elems;
+    bd.off1 = b->off1; bd.off2 = b->off2;
+    bd.len1 = b->len1; bd.len2 = b->len2;
+    bd.out_off = b->out_off;
+    bd.out_gapped = b->out_gapped; bd.out_slot1 = b->out_slot1; bd.out_slot2 = b->out_slot2;
+    bd.out_len = b->out_len;
+    bd.cost = b->cost;
+    bd.cells = b->cells;
+    LinearParams p{};
+    bool wide_ok = false;
+    int rc;
+    CK(cudaEventRecord(ctx->ev0, st));
+    if ((rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, true, &p, &wide_ok))) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
 
-    unsigned int h_cnt[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(h_cnt, p.counter, 16, cudaMemcpyDeviceToHost, st));
+    unsigned int h_cnt[9] = {0};
+    CK(cudaMemcpyAsync(h_cnt, p.counter, 36, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     // pairs the warp kernels could not hold (band wider than 1023 diagonals, strings longer than the
     // staging window, scratch larger than the arena; plus the wide queue when that kernel is disabled)
     // go through the general-geometry kernel: one CTA per pair, scratch sized from their lengths
     std::vector<uint32_t> todo;
-    if (h_cnt[1]) {
-        todo.resize(h_cnt[1]);
-        CK(cudaMemcpyAsync(todo.data(), p.overflow_list, (size_t)h_cnt[1] * 4, cudaMemcpyDeviceToHost, st));
+    if (h_cnt[8]) {
+        todo.resize(h_cnt[8]);
+        CK(cudaMemcpyAsync(todo.data(), p.overflow_list, (size_t)h_cnt[8] * 4, cudaMemcpyDeviceToHost, st));
     }
     if (!wide_ok && h_cnt[3]) {
         const size_t o = todo.size();
@@ -389,8 +362,8 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
                 words += w;
                 ++i1;
             }
-            if ((rc = ensure(ctx, ctx->gen_scratch, words * 4))) return rc;
-            if ((rc = ensure(ctx, ctx->gen_off, off.size() * 8 + (i1 - i0) * 4))) return rc;
+            if ((rc = pcgdo_ensure(ctx, ctx->gen_scratch, words * 4))) return rc;
+            if ((rc = pcgdo_ensure(ctx, ctx->gen_off, off.size() * 8 + (i1 - i0) * 4))) return rc;
             uint64_t *d_off = (uint64_t *)ctx->gen_off.p;
             uint32_t *d_list = (uint32_t *)(d_off + off.size());
             CK(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
@@ -426,7 +399,7 @@ extern "C" int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, flo
     if (!ctx || !ops_per_s) return PCGDO_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     int rc;
-    if ((rc = ensure(ctx, ctx->counters, 64))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
     const int grid = ctx->sm_count * 8;
     double best = 0;
     float best_ms = 0;
@@ -453,19 +426,19 @@ extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, co
     const size_t n = b->n_pairs;
     const bool want_str = b->out_gapped || b->out_slot1 || b->out_slot2;
     int rc;
-    if ((rc = ensure(ctx, ctx->d_elems, b->elems_bytes + 16))) return rc;
-    if ((rc = ensure(ctx, ctx->d_off1, n * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->d_off2, n * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->d_len1, n * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_len2, n * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_cost, n * 4))) return rc;
-    if (b->out_len && (rc = ensure(ctx, ctx->d_olen, n * 4))) return rc;
-    if (b->cells && (rc = ensure(ctx, ctx->d_cells, n * 8))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_elems, b->elems_bytes + 16))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_off1, n * 8))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_off2, n * 8))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_len1, n * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_len2, n * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_cost, n * 4))) return rc;
+    if (b->out_len && (rc = pcgdo_ensure(ctx, ctx->d_olen, n * 4))) return rc;
+    if (b->cells && (rc = pcgdo_ensure(ctx, ctx->d_cells, n * 8))) return rc;
     if (want_str) {
-        if ((rc = ensure(ctx, ctx->d_out_off, n * 8))) return rc;
-        if (b->out_gapped && (rc = ensure(ctx, ctx->d_og, b->out_bytes + 16))) return rc;
-        if (b->out_slot1 && (rc = ensure(ctx, ctx->d_o1, b->out_bytes + 16))) return rc;
-        if (b->out_slot2 && (rc = ensure(ctx, ctx->d_o2, b->out_bytes + 16))) return rc;
+        if ((rc = pcgdo_ensure(ctx, ctx->d_out_off, n * 8))) return rc;
+        if (b->out_gapped && (rc = pcgdo_ensure(ctx, ctx->d_og, b->out_bytes + 16))) return rc;
+        if (b->out_slot1 && (rc = pcgdo_ensure(ctx, ctx->d_o1, b->out_bytes + 16))) return rc;
+        if (b->out_slot2 && (rc = pcgdo_ensure(ctx, ctx->d_o2, b->out_bytes + 16))) return rc;
     }
     cudaStream_t st = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));

@@ -1,0 +1,57 @@
+// do_ctx.h — internal: context / TCM objects shared by do_api.cu and do_forest.cu.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "do_device.cuh"
+#include "do_host.h"
+
+struct pcgdo_tcm {
+    pcgdo::TcmDev dev{};
+    size_t a = 0;
+    unsigned int gap_open = 0;
+    void *d_sub4 = nullptr, *d_sub4_nat = nullptr, *d_median = nullptr, *d_cgap = nullptr, *d_gapc = nullptr;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct pcgdo_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int last_launches = 0;
+    // tunables
+    int pairs_per_warp = 32;
+    int warps_per_cta = 32;
+    int max_len = 1024;
+    int max_b = 8;
+    size_t arena_words = 0;          // 0 = derive from max_len
+    // device scratch
+    DevBuf arena, counters, overflow, big, gen_scratch, gen_off;
+    // staging for the host-buffer entry point
+    DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
+    std::string err;
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return PCGDO_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+
+int pcgdo_ensure(pcgdo_ctx *ctx, DevBuf &b, size_t bytes);
+
+// Enqueue the narrow (+ wide) warp kernels for one batch on `st`.  Work counters are reset; the overflow
+// counter only when `reset_overflow` (the forest scheduler accumulates it over all levels and checks once).
+// *out_p receives the parameters used (for the caller's overflow handling).
+int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo::BatchDev &bd, cudaStream_t st,
+                         bool reset_overflow, pcgdo::LinearParams *out_p, bool *wide_ok_out);

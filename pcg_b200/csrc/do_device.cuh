@@ -33,6 +33,12 @@ struct BatchDev {
     uint32_t       *out_len;
     int32_t        *cost;
     uint64_t       *cells;
+    // post-order mode: the gapped median with its gap elements dropped (= the node's ungapped median
+    // string, what the parent's alignment consumes), at out_uoff[k], at most ucap bytes, length to out_ulen
+    uint8_t        *out_ungapped;
+    const uint64_t *out_uoff;
+    uint32_t       *out_ulen;
+    uint32_t        ucap;
 };
 
 struct LinearParams {

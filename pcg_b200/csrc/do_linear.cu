@@ -229,11 +229,12 @@ __device__ __forceinline__ uint32_t trace_lane(const uint32_t *dirw, uint32_t wq
 // ---------------------------------------------------------------------------------------------
 // emit: warp-cooperative, 128 alignment columns per pass
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_pair(const TcmDev &tcm, const uint8_t *pL, const uint8_t *pS,
-                                          const uint32_t *ops, uint32_t nal, bool first_long,
-                                          uint8_t *og, uint8_t *o1, uint8_t *o2, int lane)
+__device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *pL, const uint8_t *pS,
+                                              const uint32_t *ops, uint32_t nal, bool first_long,
+                                              uint8_t *og, uint8_t *o1, uint8_t *o2, int lane,
+                                              uint8_t *ou = nullptr, uint32_t ucap = 0)
 {
-    uint32_t base_i = 0, base_j = 0;
+    uint32_t base_i = 0, base_j = 0, base_u = 0;
     const uint32_t gap = tcm.gap;
     for (uint32_t c0 = 0; c0 < nal; c0 += 128) {
         const uint32_t c = c0 + 4u * lane;
@@ -259,7 +260,7 @@ __device__ __forceinline__ void emit_pair(const TcmDev &tcm, const uint8_t *pL, 
         }
         const uint32_t excl = incl - packed;
         uint32_t il = base_i + (excl & 0xffffu), js = base_j + (excl >> 16);
-        uint32_t wg = 0, wx = 0, wy = 0;
+        uint32_t wg = 0, wx = 0, wy = 0, nk = 0;
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             uint32_t xx = 0, yy = 0, md = 0;
@@ -267,10 +268,29 @@ __device__ __forceinline__ void emit_pair(const TcmDev &tcm, const uint8_t *pL, 
                 if (code[x] < 2u) { yy = __ldg(pL + il); ++il; }                    // consume longer
                 if (code[x] == 0u || code[x] == 2u) { xx = __ldg(pS + js); ++js; }  // consume lesser
                 md = __ldg(tcm.median + (((xx ? xx : gap) << tcm.a) | (yy ? yy : gap)));
+                nk += (md != gap);
             }
             wg |= md << (8 * x);
             wx |= xx << (8 * x);
             wy |= yy << (8 * x);
+        }
+        if (ou) {       // compact the non-gap medians: deleteGaps of the node's context, medians only
+            uint32_t inc = nk;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += o;
+            }
+            uint32_t pos = base_u + inc - nk;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const uint32_t md = (wg >> (8 * x)) & 0xffu;
+                if (code[x] != 3u && md != gap) {
+                    if (pos < ucap) ou[pos] = (uint8_t)md;
+                    ++pos;
+                }
+            }
+            base_u += __shfl_sync(kFull, inc, 31);
         }
         if (c < nal) {
             if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
@@ -281,6 +301,7 @@ __device__ __forceinline__ void emit_pair(const TcmDev &tcm, const uint8_t *pL, 
         base_i += tot & 0xffffu;
         base_j += tot >> 16;
     }
+    return base_u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
     unsigned int *counter = BMAX <= 8 ? p.counter : p.counter + 2;
-    const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
+    const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len || b.out_ungapped;
 
     for (;;) {
         uint32_t base = 0;
@@ -455,7 +476,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
             __syncwarp();
 
             // -------------------------------------------------------------- emit: warp per pair
-            if (b.out_gapped || b.out_slot1 || b.out_slot2) {
+            if (b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_ungapped) {
                 for (int pe = start; pe < pi; ++pe) {
                     const uint32_t fl_ok = s_flags[pe];
                     if (!(fl_ok & 2u)) continue;
@@ -466,11 +487,16 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                     const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                     const int B = choose_b(g.wb);
                     const uint32_t *ops = arena + s_off[pe] + dir_words(g, B);
-                    const uint64_t oo = b.out_off[k];
-                    emit_pair(tcm, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
-                              b.out_gapped ? b.out_gapped + oo : nullptr,
-                              b.out_slot1 ? b.out_slot1 + oo : nullptr,
-                              b.out_slot2 ? b.out_slot2 + oo : nullptr, lane);
+                    const uint64_t oo = b.out_off ? b.out_off[k] : 0;
+                    const uint32_t nu = emit_pair(tcm, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                                                  b.out_gapped ? b.out_gapped + oo : nullptr,
+                                                  b.out_slot1 ? b.out_slot1 + oo : nullptr,
+                                                  b.out_slot2 ? b.out_slot2 + oo : nullptr, lane,
+                                                  b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+                    if (b.out_ungapped && lane == 0) {
+                        b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
+                        if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);   // node string does not fit its slot
+                    }
                 }
             }
             __syncwarp();
@@ -555,7 +581,7 @@ __global__ void __launch_bounds__(256) do_general_kernel(const LinearParams p, c
         const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
         b.cost[k] = (int32_t)((w[1 + q_last] >> 2) - (kBias4 >> 2) + csum);
         if (b.cells) b.cells[k] = band_cells(g, 0, 1);
-        const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
+        const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len || b.out_ungapped;
         uint32_t n = 0;
         if (want_out) {
             n = trace_lane(dirw, wq, g.q0, g.lg, g.sh, ops);
@@ -565,10 +591,16 @@ __global__ void __launch_bounds__(256) do_general_kernel(const LinearParams p, c
         __threadfence_block();
     }
     __syncthreads();
-    if (warp == 0 && (b.out_gapped || b.out_slot1 || b.out_slot2)) {
-        const uint64_t oo = b.out_off[k];
-        emit_pair(tcm, pL, pS, ops, s_n, fl, b.out_gapped ? b.out_gapped + oo : nullptr,
-                  b.out_slot1 ? b.out_slot1 + oo : nullptr, b.out_slot2 ? b.out_slot2 + oo : nullptr, lane);
+    if (warp == 0 && (b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_ungapped)) {
+        const uint64_t oo = b.out_off ? b.out_off[k] : 0;
+        const uint32_t nu = emit_pair(tcm, pL, pS, ops, s_n, fl, b.out_gapped ? b.out_gapped + oo : nullptr,
+                                      b.out_slot1 ? b.out_slot1 + oo : nullptr,
+                                      b.out_slot2 ? b.out_slot2 + oo : nullptr, lane,
+                                      b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+        if (b.out_ungapped && lane == 0) {
+            b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
+            if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);
+        }
     }
 }
 

@@ -1,0 +1,122 @@
+"""GPU parity: the post-order level scheduler (pcgdo_forest_*) against the oracle's post-order and the
+reference's golden tree."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import random_string, tcm_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_postorder(o, children, n_taxa, leaves):
+    """leaves: per taxon element string. Returns {node: (context, local, total)} via the oracle's
+    restatement of foreignPairwiseDO (DO/Internal.hs:127-140 for the totals)."""
+    res = {v: (np.stack([leaves[v]] * 3, 1), 0, 0) for v in range(n_taxa)}
+    pending = {n_taxa + x: tuple(int(c) for c in children[x]) for x in range(n_taxa - 1)}
+    while pending:
+        for n in [n for n, (l, r) in pending.items() if l in res and r in res]:
+            l, r = pending.pop(n)
+            cost, ctx, _ = o.pairwise_do(res[l][0], res[r][0])
+            res[n] = (ctx, cost, cost + res[l][2] + res[r][2])
+    return res
+
+
+def test_forest_matches_oracle_postorder(oracle_mod, gpu_ctx):
+    import pcg_b200 as P
+    from pcg_b200.postorder import random_binary_trees
+    sig = tcm_matrix("discrete")
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=400, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(sig)
+    n_trees, n_taxa, n_chars = 5, 14, 3
+    rng = np.random.default_rng(31)
+    children = random_binary_trees(n_trees, n_taxa, seed=4)
+    leaves = [[random_string(rng, int(rng.integers(40, 90)), amb=0.05) for _ in range(n_chars)] for _ in range(n_taxa)]
+    for v in range(n_taxa):          # leaves are ungapped strings: no pure-gap elements
+        for c in range(n_chars):
+            leaves[v][c][leaves[v][c] == 16] = 1
+    f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=512)
+    costs = f.score(tcm)
+    assert f.alignments == n_trees * n_chars * (n_taxa - 1) and f.levels >= 4
+    for t in range(n_trees):
+        tree_cost = 0
+        for c in range(n_chars):
+            ref = _oracle_postorder(o, children[t], n_taxa, [leaves[v][c] for v in range(n_taxa)])
+            is_child = set(int(x) for x in children[t].reshape(-1))
+            for x in range(n_taxa - 1):
+                node = n_taxa + x
+                med, local, total = f.node(t, c, node)
+                ctx, rl, rt = ref[node]
+                assert local == rl and total == rt, (t, c, node)
+                assert np.array_equal(med, ctx[ctx[:, 0] != o.gap][:, 0]), (t, c, node)
+                if node not in is_child:
+                    tree_cost += rt
+        assert int(costs[t]) == tree_cost, t
+    f.close()
+
+
+def test_forest_on_reference_golden_tree(oracle_mod, gpu_ctx):
+    """chel golden test: the 14 post-order nodes the reference pins — local costs and (ungapped) medians
+    from the device scheduler, full contexts from the level-batched wrapper."""
+    import pcg_b200 as P
+    from pcg_b200.postorder import postorder_contexts
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "chel_golden.json")))
+    nodes = g["nodes"]
+    leaf_ids = [n["id"] for n in nodes if not n["children"]]
+    int_ids = [n["id"] for n in nodes if n["children"]]
+    n_taxa = len(leaf_ids)
+    assert n_taxa == 17 and len(int_ids) == 16
+    to_mine = {gid: k for k, gid in enumerate(leaf_ids)}
+    to_mine.update({gid: n_taxa + k for k, gid in enumerate(int_ids)})
+    children = np.zeros((1, n_taxa - 1, 2), np.int32)
+    for k, gid in enumerate(int_ids):
+        l, r = sorted(nodes[gid]["children"])            # lower node index = left (Postorder.hs:98-123)
+        children[0, k] = (to_mine[l], to_mine[r])
+    gap = 16
+    leaves = []
+    for gid in leaf_ids:
+        c = np.array(nodes[gid]["context"], np.uint8)
+        assert (c[:, 0] == c[:, 1]).all() and (c[:, 0] == c[:, 2]).all()
+        leaves.append([c[c[:, 0] != gap][:, 0].copy()])
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=400, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(tcm_matrix("discrete"))
+    f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=512)
+    f.score(tcm)
+    checked = 0
+    for gid in int_ids:
+        if gid in g["rerooted_nodes"]:
+            continue
+        med, local, total = f.node(0, 0, to_mine[gid])
+        want = np.array(nodes[gid]["context"], np.uint8)
+        assert local == nodes[gid]["local_cost"], gid
+        assert total == nodes[gid]["total_cost"], gid
+        assert np.array_equal(med, want[want[:, 0] != gap][:, 0]), gid
+        checked += 1
+    assert checked == 14
+    f.close()
+    # full contexts (with re-inserted gaps and left/right fields), level by level through foreignPairwiseDO;
+    # the golden leaves are fed as they are stored (gapped contexts)
+    leaf_ctx = [np.array(nodes[gid]["context"], np.uint8)[:, 0] for gid in leaf_ids]
+    ctxs, local, total = postorder_contexts(gpu_ctx, tcm, children[0], n_taxa, leaf_ctx)
+    for gid in int_ids:
+        if gid in g["rerooted_nodes"]:
+            continue
+        assert local[to_mine[gid]] == nodes[gid]["local_cost"]
+        assert ctxs[to_mine[gid]].tolist() == nodes[gid]["context"], gid
+
+
+def test_forest_reports_node_overflow(gpu_ctx):
+    import pcg_b200 as P
+    from pcg_b200.postorder import random_binary_trees
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=400, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(tcm_matrix("discrete"))
+    rng = np.random.default_rng(2)
+    n_taxa = 8
+    leaves = [[random_string(rng, 60, amb=0.0)] for _ in range(n_taxa)]
+    f = P.Forest(gpu_ctx, random_binary_trees(2, n_taxa, 1), n_taxa, leaves, node_cap=60)
+    with pytest.raises(P.BackendError):
+        f.score(tcm)      # medians of unrelated strings grow beyond 60 elements: must fail loudly
+    f.close()
