@@ -133,6 +133,116 @@ def cpu_arm(n_sample_hint, threads, kind_pref="reference", seconds_target=12.0):
             "cores": threads, "cost_checksum": int(cost.astype(np.int64).sum())}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# Config 5 (BASELINE.json configs[4]): post-order scoring of 1024 random 512-taxon binary trees x 64
+# dynamic DNA characters (length 256, discrete TCM, C-linear dialect).  One "evaluation" = the post-order
+# cost of one tree over all 64 characters (511 x 64 alignments).  Under torchrun the characters are
+# split across ranks (strong scaling) and the per-tree sums are all-reduced over NCCL.
+# ------------------------------------------------------------------------------------------------
+PO = {"n_trees": 1024, "n_taxa": 512, "n_chars": 64, "leaf_len": 256, "node_cap": 1024,
+      "tree_seed": 20260104, "leaf_seed": 20260105}
+
+
+def discrete_tcm(a=5):
+    return (1 - np.eye(a, dtype=np.uint32)).astype(np.uint32)      # bench/strings/dna/dna-discrete.tcm
+
+
+def po_inputs(n_trees, n_taxa, n_chars, leaf_len):
+    from pcg_b200.postorder import random_binary_trees
+    children = random_binary_trees(n_trees, n_taxa, PO["tree_seed"])
+    rng = np.random.Generator(np.random.PCG64(PO["leaf_seed"]))
+    x = rng.integers(0, 4, size=(n_taxa, n_chars, leaf_len), dtype=np.uint8)
+    return children, np.left_shift(np.uint8(1), x)
+
+
+def po_cpu_arm(children, leaves, threads, seconds_target=10.0, kind_pref="reference"):
+    """Reference align2d inside a CPU post-order loop, threads over (tree, character) columns, bounded sample."""
+    from oracle import pyoracle as po
+    kind = kind_pref if (kind_pref == "port" or os.path.exists(po.REF_SO)) else "port"
+    n_taxa, n_chars, L_ = leaves.shape
+    flat = np.ascontiguousarray(leaves.reshape(-1))
+    off = np.arange(n_taxa * n_chars, dtype=np.uint64) * np.uint64(L_)
+    ln = np.full(n_taxa * n_chars, L_, np.uint32)
+    sig = discrete_tcm()
+    sec, _, _ = po.cpu_bench_postorder(sig, children, n_taxa, n_chars, flat, off, ln, 0, threads, threads, kind)
+    n_cols = int(max(threads, min(children.shape[0] * n_chars, threads * seconds_target / max(sec, 1e-3))))
+    sec, cost, cells = po.cpu_bench_postorder(sig, children, n_taxa, n_chars, flat, off, ln, 0, n_cols, threads, kind)
+    return {"tree_evals_per_s": n_cols / n_chars / sec, "gcups": float(cells.sum()) / sec / 1e9, "seconds": sec,
+            "columns": n_cols, "kind": kind, "cores": threads, "col_cost": cost}
+
+
+def run_postorder(args, rank, world, local_rank, ctx, torch, dist, full=True):
+    """Returns the dict reported under "postorder" (rank 0) — value = whole-job tree evaluations / s."""
+    import pcg_b200 as P
+    n_trees, n_taxa, n_chars, leaf_len = (PO["n_trees"], PO["n_taxa"], PO["n_chars"], PO["leaf_len"])
+    if args.po_trees:
+        n_trees = args.po_trees
+    children, leaves = po_inputs(n_trees, n_taxa, n_chars, leaf_len)
+    assert n_chars % world == 0
+    cpr = n_chars // world
+    my = leaves[:, rank * cpr:(rank + 1) * cpr, :]
+    ctx.configure(pairs_per_warp=args.ppw, warps_per_cta=args.warps, max_len=PO["node_cap"], max_b=32)
+    tcm = ctx.tcm(discrete_tcm())
+    forest = P.Forest(ctx, children, n_taxa, [[my[v, c] for c in range(cpr)] for v in range(n_taxa)], PO["node_cap"])
+    dev = torch.device("cuda", local_rank)
+    costs = torch.zeros(n_trees, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        forest.score_into(tcm, costs.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(costs)          # the path's only collective: 8 KB of per-tree sums
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    barrier()
+    checksum = int(costs.sum().item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, args.po_steps)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    out = {"metric": "postorder tree cost evals/sec", "value": n_trees / (ms * 1e-3), "unit": "tree-evals/s",
+           "ms_per_sweep": ms, "scaling": "strong", "levels": forest.levels,
+           "alignments_per_sweep": n_trees * n_chars * (n_taxa - 1),
+           "config": {"workload": "config5: post-order of random binary trees x dynamic DNA characters, discrete TCM",
+                      "n_trees": n_trees, "n_taxa": n_taxa, "n_chars": n_chars, "leaf_len": leaf_len,
+                      "chars_per_gpu": cpr, "collective": "1 all_reduce(int64[n_trees]) per sweep" if world > 1 else "none"},
+           "cost_checksum": checksum, "gpu_launches_per_sweep": ctx.last_kernel_ms()[1]}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        info = po_cpu_arm(children, leaves, host_threads(), seconds_target=8.0)
+        # parity spot check of the same columns against the device totals
+        tr, ch = np.divmod(np.arange(info["columns"]), n_chars)
+        dev_tot = np.zeros(info["columns"], np.int64)
+        roots = {}
+        for k in range(min(info["columns"], 64)):
+            t, c = int(tr[k]), int(ch[k])
+            if t not in roots:
+                is_child = set(int(x) for x in children[t].reshape(-1))
+                roots[t] = [n_taxa + x for x in range(n_taxa - 1) if n_taxa + x not in is_child][0]
+            dev_tot[k] = forest.node(t, c, roots[t])[2]
+            assert dev_tot[k] == int(info["col_cost"][k]), (t, c)
+        out["cpu_baseline"] = {"value": info["tree_evals_per_s"], "unit": "tree-evals/s", "cores": info["cores"],
+                               "kind": info["kind"], "gcups": info["gcups"],
+                               "sample": f"first {info['columns']} (tree, character) columns, {info['seconds']:.1f} s on "
+                                         f"{info['cores']} host threads; root totals of the first 64 columns checked "
+                                         f"equal to the device's"}
+    forest.close()
+    return out
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -169,6 +279,10 @@ def main():
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
     ap.add_argument("--warps", type=int, default=32, help="warps per CTA of the narrow kernel")
     ap.add_argument("--ppw", type=int, default=8, help="pairs a warp fills before tracing them")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"])
+    ap.add_argument("--no-postorder", action="store_true", help="skip the config-5 post-order section")
+    ap.add_argument("--po-trees", type=int, default=0, help="override the number of candidate trees")
+    ap.add_argument("--po-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -195,6 +309,17 @@ def main():
 
     n = args.pairs
     ctx = P.Context(local_rank)
+    if args.workload == "config5":
+        po = run_postorder(args, rank, world, local_rank, ctx, torch, dist)
+        if rank == 0:
+            line = {"metric": po["metric"], "value": po["value"], "unit": po["unit"], "n_gpus": world,
+                    "steps": args.po_steps, "warmup": args.warmup, "ms_per_step": po["ms_per_sweep"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+                    "data": "synthetic", "config": po["config"], "postorder": po}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     ctx.configure(pairs_per_warp=args.ppw, warps_per_cta=args.warps, max_len=1024, max_b=8)
     tcm = ctx.tcm(l1_tcm())
     strings = make_strings(n, rank)
@@ -290,6 +415,16 @@ def main():
         except Exception as ex:   # pinned allocation can fail on small hosts: report, do not fake
             e2e = {"value": None, "unit": "GCUPS", "error": str(ex)[:200]}
 
+    # ---- second half of the metric: post-order tree scoring (config 5), same process, after the pair bench
+    postorder = None
+    if not args.no_postorder:
+        del d_elems, d_g, d_s1, d_s2
+        torch.cuda.empty_cache()
+        try:
+            postorder = run_postorder(args, rank, world, local_rank, ctx, torch, dist)
+        except Exception as ex:
+            postorder = {"value": None, "error": str(ex)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,7 +469,7 @@ def main():
                        "pairs_per_gpu": n, "len": L, "cells_per_pair": cpp, "full_equiv_gcups": value * L * L / cpp,
                        "l2": "inputs (2.1 GB) and direction scratch (>4 GB) exceed the 126 MB L2",
                        "seed": SEED},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "postorder": postorder,
             "cost_checksum": cost_checksum}
     print(json.dumps(line), flush=True)
     if world > 1:

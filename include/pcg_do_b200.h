@@ -155,6 +155,7 @@ int  pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *forest, const uint8_t
 int  pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *forest, void *cuda_stream);
 void *pcgdo_forest_tree_cost_ptr(pcgdo_forest *forest);              /* DEVICE int64[n_trees]          */
 int  pcgdo_forest_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *forest, int64_t *host_out);
+int  pcgdo_forest_copy_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *forest, void *dst_device, void *cuda_stream);
 int  pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *forest, uint32_t tree, uint32_t character, uint32_t node,
                            uint8_t *median_out, uint32_t *len_out, int32_t *local_cost, int64_t *total_cost);
 uint32_t pcgdo_forest_levels(const pcgdo_forest *forest);

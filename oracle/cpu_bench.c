@@ -115,3 +115,135 @@ int cpu_bench_align2d(const char *ref_so, const uint32_t *sigma, int a,
     if (port) oracle_tcm_free(port);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU post-order loop (BASELINE.md config 5 baseline): for every (tree, character) column, children before
+ * parents, node string = the gapped median of align2d(left, right) with its gap elements removed (what the
+ * Haskell wrapper's deleteGaps feeds to the next alignment), total = local + children.
+ * Columns are split over `threads` pthreads.  ref_so != NULL -> the unmodified reference align2d.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int tid, threads;
+    uint32_t n_trees, n_taxa, n_chars, col0, n_cols;   /* columns col0 .. col0+n_cols-1 of the tree x char grid */
+    const int32_t *children;
+    const uint8_t *leaf_elems;
+    const uint64_t *leaf_off;
+    const uint32_t *leaf_len;
+    int64_t *col_cost;         /* [n_cols] root total */
+    uint64_t *col_cells;       /* [n_cols] */
+    align2d_fn ref_align;
+    void *ref_cm;
+    const oracle_tcm_t *port;
+    uint32_t gap;
+} po_job_t;
+
+static void *po_worker(void *arg)
+{
+    po_job_t *j = arg;
+    const uint32_t ni = j->n_taxa - 1, nn = 2 * j->n_taxa - 1;
+    uint8_t **str = calloc(nn, sizeof(uint8_t *));
+    uint32_t *len = calloc(nn, sizeof(uint32_t));
+    int64_t *tot = calloc(nn, sizeof(int64_t));
+    int *done = calloc(nn, sizeof(int));
+    for (uint32_t col = j->tid; col < j->n_cols; col += j->threads) {
+        const uint32_t g = j->col0 + col, t = g / j->n_chars, c = g % j->n_chars;
+        const int32_t *ch = j->children + (size_t)t * ni * 2;
+        uint64_t cells = 0;
+        for (uint32_t v = 0; v < nn; v++) { done[v] = v < j->n_taxa; tot[v] = 0; }
+        for (uint32_t v = 0; v < j->n_taxa; v++) {
+            str[v] = (uint8_t *)j->leaf_elems + j->leaf_off[(size_t)v * j->n_chars + c];
+            len[v] = j->leaf_len[(size_t)v * j->n_chars + c];
+        }
+        uint32_t remaining = ni, root = 0;
+        while (remaining) {
+            for (uint32_t x = 0; x < ni; x++) {
+                const uint32_t node = j->n_taxa + x;
+                if (done[node] || !done[ch[2 * x]] || !done[ch[2 * x + 1]]) continue;
+                const uint32_t l = ch[2 * x], r = ch[2 * x + 1];
+                const size_t n1 = len[l], n2 = len[r], cap = n1 + n2 + 2;
+                uint8_t *out = malloc(cap);
+                uint32_t no = 0;
+                int64_t cost;
+                if (j->ref_align) {
+                    aio_t a, b, gg, u;
+                    fill_aio(&a, str[l], n1, cap);
+                    fill_aio(&b, str[r], n2, cap);
+                    fill_aio(&gg, NULL, 0, cap);
+                    fill_aio(&u, NULL, 0, cap);
+                    cost = j->ref_align(&a, &b, &gg, &u, j->ref_cm, 0, 1, 0);
+                    for (size_t k = 0; k < gg.length; k++) {
+                        unsigned int m = gg.character[gg.capacity - gg.length + k];
+                        if (m != j->gap) out[no++] = (uint8_t)m;
+                    }
+                    free(a.character); free(b.character); free(gg.character); free(u.character);
+                } else {
+                    uint32_t *buf = malloc(sizeof(uint32_t) * (5 * cap + 8));
+                    uint32_t *x1 = buf, *x2 = buf + n1, *og = x2 + n2, *o1 = og + cap, *o2 = o1 + cap;
+                    for (size_t i = 0; i < n1; i++) x1[i] = str[l][i];
+                    for (size_t i = 0; i < n2; i++) x2[i] = str[r][i];
+                    size_t nal = 0;
+                    uint64_t cc = 0;
+                    cost = oracle_align2d(j->port, x1, n1, x2, n2, og, o1, o2, &nal, &cc);
+                    for (size_t k = 0; k < nal; k++)
+                        if (og[k] != j->gap) out[no++] = (uint8_t)og[k];
+                    free(buf);
+                }
+                {
+                    size_t lg = (n1 > n2 ? n1 : n2) + 1, sh = (n1 > n2 ? n2 : n1) + 1;
+                    cells += oracle_band_rows(lg, sh, NULL, NULL, NULL, NULL);
+                }
+                str[node] = out;
+                len[node] = no;
+                tot[node] = cost + tot[l] + tot[r];
+                done[node] = 1;
+                root = node;
+                remaining--;
+            }
+        }
+        j->col_cost[col] = tot[root];        /* the last node completed is the root */
+        if (j->col_cells) j->col_cells[col] = cells;
+        for (uint32_t v = j->n_taxa; v < nn; v++) { free(str[v]); str[v] = NULL; }
+    }
+    free(str); free(len); free(tot); free(done);
+    return NULL;
+}
+
+int cpu_bench_postorder(const char *ref_so, const uint32_t *sigma, int a, uint32_t n_trees, uint32_t n_taxa,
+                        uint32_t n_chars, const int32_t *children, const uint8_t *leaf_elems,
+                        const uint64_t *leaf_off, const uint32_t *leaf_len, uint32_t col0, uint32_t n_cols,
+                        int threads, int64_t *col_cost, uint64_t *col_cells, double *seconds)
+{
+    align2d_fn ref_align = NULL;
+    void *cm = NULL;
+    oracle_tcm_t *port = NULL;
+    if (ref_so) {
+        void *h = dlopen(ref_so, RTLD_NOW | RTLD_LOCAL);
+        if (!h) return 1;
+        ref_align = (align2d_fn)dlsym(h, "align2d");
+        setup_fn setup = (setup_fn)dlsym(h, "setUp2dCostMtx");
+        if (!ref_align || !setup) return 2;
+        cm = calloc(1, 256);
+        uint32_t *sg = malloc(sizeof(uint32_t) * a * a);
+        memcpy(sg, sigma, sizeof(uint32_t) * a * a);
+        setup(cm, sg, (size_t)a, 0);
+        free(sg);
+    } else {
+        port = oracle_tcm_new(sigma, a, 0);
+    }
+    if (threads < 1) threads = 1;
+    pthread_t *th = malloc(sizeof(pthread_t) * threads);
+    po_job_t *jobs = malloc(sizeof(po_job_t) * threads);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (po_job_t){ t, threads, n_trees, n_taxa, n_chars, col0, n_cols, children, leaf_elems, leaf_off,
+                              leaf_len, col_cost, col_cells, ref_align, cm, port, 1u << (a - 1) };
+        pthread_create(&th[t], NULL, po_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    free(th); free(jobs);
+    if (port) oracle_tcm_free(port);
+    return 0;
+}

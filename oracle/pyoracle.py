@@ -222,3 +222,30 @@ def cpu_bench_align2d(sigma, pp, threads: int, kind: str = "reference", want_cel
     if rc:
         raise RuntimeError(f"cpu_bench_align2d failed: {rc}")
     return float(sec.value), cost, cells
+
+
+def cpu_bench_postorder(sigma, children, n_taxa, n_chars, leaf_elems, leaf_off, leaf_len, col0, n_cols,
+                        threads: int, kind: str = "reference"):
+    """CPU post-order over columns col0..col0+n_cols-1 of the (tree x character) grid.
+    Returns (seconds, col_cost[int64], col_cells[uint64])."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.cpu_bench_postorder.restype = C.c_int
+    lib.cpu_bench_postorder.argtypes = [C.c_char_p, _u32p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    sigma = _as_u32(sigma)
+    ch = np.ascontiguousarray(np.asarray(children, np.int32))
+    cost = np.zeros(n_cols, np.int64)
+    cells = np.zeros(n_cols, np.uint64)
+    sec = C.c_double(0)
+    so = REF_SO.encode() if kind == "reference" else None
+    if kind == "reference" and not os.path.exists(REF_SO):
+        raise FileNotFoundError(REF_SO)
+    rc = lib.cpu_bench_postorder(so, _ptr(sigma), int(sigma.shape[0]), ch.shape[0], n_taxa, n_chars, ch.ctypes.data,
+                                 leaf_elems.ctypes.data, leaf_off.ctypes.data, leaf_len.ctypes.data, col0, n_cols,
+                                 threads, cost.ctypes.data, cells.ctypes.data, C.byref(sec))
+    if rc:
+        raise RuntimeError(f"cpu_bench_postorder failed: {rc}")
+    return float(sec.value), cost, cells

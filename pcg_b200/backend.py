@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
     "pcgdo_configure_ex", "pcgdo_int32_peak",
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
-    "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
+    "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
 ]
 
@@ -90,6 +90,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_forest_tree_cost_ptr.argtypes = [C.c_void_p]
     L.pcgdo_forest_tree_cost_ptr.restype = C.c_void_p
     L.pcgdo_forest_tree_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_copy_tree_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pcgdo_forest_get_node.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                         C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.pcgdo_forest_levels.argtypes = [C.c_void_p]
@@ -221,6 +222,13 @@ class Forest:
         self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
                        "pcgdo_forest_score")
         return int(self.ctx.lib.pcgdo_forest_tree_cost_ptr(self.h))
+
+    def score_into(self, tcm: Tcm, dst_device_ptr: int, stream: int = 0) -> None:
+        """Sweep on `stream`, then copy the int64[n_trees] costs into device memory at dst_device_ptr."""
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+                       "pcgdo_forest_score")
+        self.ctx.check(self.ctx.lib.pcgdo_forest_copy_tree_costs(self.ctx.h, self.h, C.c_void_p(dst_device_ptr),
+                                                                 C.c_void_p(stream)), "pcgdo_forest_copy_tree_costs")
 
     def node(self, tree: int, character: int, node: int):
         buf = np.zeros(self.node_cap, np.uint8)

@@ -301,6 +301,16 @@ extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_fo
 
 extern "C" void *pcgdo_forest_tree_cost_ptr(pcgdo_forest *F) { return F ? F->tree_cost.p : nullptr; }
 
+// Device-to-device copy of the int64[n_trees] cost vector (e.g. into a tensor that is then all-reduced over NCCL).
+extern "C" int pcgdo_forest_copy_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *F, void *dst_device, void *cuda_stream)
+{
+    if (!ctx || !F || !dst_device) return PCGDO_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaMemcpyAsync(dst_device, F->tree_cost.p, (size_t)F->n_trees * 8, cudaMemcpyDeviceToDevice, st));
+    return PCGDO_OK;
+}
+
 extern "C" int pcgdo_forest_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *F, int64_t *host_out)
 {
     if (!ctx || !F || !host_out) return PCGDO_ERR_ARG;
