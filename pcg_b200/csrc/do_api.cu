@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cstdint>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -441,7 +443,7 @@ extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, co
         if (b->out_slot2 && (rc = pcgdo_ensure(ctx, ctx->d_o2, b->out_bytes + 16))) return rc;
     }
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));
+    // descriptors first (40 bytes per pair)
     CK(cudaMemcpyAsync(ctx->d_off1.p, b->off1, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_off2.p, b->off2, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_len1.p, b->len1, n * 4, cudaMemcpyHostToDevice, st));
@@ -461,6 +463,96 @@ extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, co
     d.out_len = b->out_len ? (uint32_t *)ctx->d_olen.p : nullptr;
     d.cost = (int32_t *)ctx->d_cost.p;
     d.cells = b->cells ? (uint64_t *)ctx->d_cells.p : nullptr;
+    // ---- pipelined path: the batch is cut into chunks whose strings and outputs are contiguous ranges of
+    // the host buffers; chunk c+1 is copied in and chunk c-1 copied out while chunk c is aligned
+    // (three streams, PCIe is full duplex).  Needs monotone layouts, which the packers produce; anything
+    // else, and any pair that overflows the warp kernels, takes the plain path below.
+    const size_t chunk = ctx->host_chunk_pairs ? ctx->host_chunk_pairs : 65536;
+    bool pipelined = n > chunk && ctx->max_b > 8;      // (wide kernel on: no per-chunk queue left behind)
+    std::vector<size_t> e_lo, e_hi, o_lo, o_hi;
+    if (pipelined) {
+        size_t prev_e = 0, prev_o = 0;
+        for (size_t c0 = 0; c0 < n && pipelined; c0 += chunk) {
+            const size_t c1 = std::min(n, c0 + chunk);
+            size_t lo = SIZE_MAX, hi = 0, olo = SIZE_MAX, ohi = 0;
+            for (size_t k = c0; k < c1; ++k) {
+                const size_t a1 = b->off1[k], a2 = b->off2[k];
+                lo = std::min(lo, std::min(a1, a2));
+                hi = std::max(hi, std::max(a1 + b->len1[k], a2 + b->len2[k]));
+                if (want_str) {
+                    const size_t o = b->out_off[k];
+                    olo = std::min(olo, o);
+                    ohi = std::max(ohi, o + (((size_t)b->len1[k] + b->len2[k] + 3) & ~(size_t)3));
+                }
+            }
+            if (lo < prev_e || hi > b->elems_bytes || (want_str && (olo < prev_o || ohi > b->out_bytes))) pipelined = false;
+            prev_e = hi; prev_o = want_str ? ohi : 0;
+            e_lo.push_back(lo); e_hi.push_back(hi); o_lo.push_back(olo); o_hi.push_back(ohi);
+        }
+    }
+    if (pipelined) {
+        if (!ctx->s_h2d) {
+            CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        }
+        const size_t nch = e_lo.size();
+        std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
+        for (size_t c = 0; c < nch; ++c) {
+            CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        }
+        cudaEvent_t ev_desc;
+        CK(cudaEventCreateWithFlags(&ev_desc, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_desc, st));
+        CK(cudaStreamWaitEvent(ctx->s_h2d, ev_desc, 0));
+        ctx->last_launches = 0;
+        CK(cudaEventRecord(ctx->ev0, st));
+        LinearParams p{};
+        bool wide_ok = false;
+        for (size_t c = 0; c < nch; ++c) {
+            const size_t c0 = c * chunk, c1 = std::min(n, c0 + chunk);
+            CK(cudaMemcpyAsync((uint8_t *)ctx->d_elems.p + e_lo[c], b->elems + e_lo[c], e_hi[c] - e_lo[c],
+                               cudaMemcpyHostToDevice, ctx->s_h2d));
+            CK(cudaEventRecord(ev_in[c], ctx->s_h2d));
+            CK(cudaStreamWaitEvent(st, ev_in[c], 0));
+            BatchDev bd{};
+            bd.n_pairs = (uint32_t)(c1 - c0);
+            bd.elems = d.elems;
+            bd.off1 = d.off1 + c0; bd.off2 = d.off2 + c0;
+            bd.len1 = d.len1 + c0; bd.len2 = d.len2 + c0;
+            bd.out_off = d.out_off ? d.out_off + c0 : nullptr;
+            bd.out_gapped = d.out_gapped; bd.out_slot1 = d.out_slot1; bd.out_slot2 = d.out_slot2;
+            bd.out_len = d.out_len ? d.out_len + c0 : nullptr;
+            bd.cost = d.cost + c0;
+            bd.cells = d.cells ? d.cells + c0 : nullptr;
+            if ((rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, c == 0, &p, &wide_ok))) return rc;
+            CK(cudaEventRecord(ev_done[c], st));
+            CK(cudaStreamWaitEvent(ctx->s_d2h, ev_done[c], 0));
+            cudaStream_t so = ctx->s_d2h;
+            CK(cudaMemcpyAsync(b->cost + c0, d.cost + c0, (c1 - c0) * 4, cudaMemcpyDeviceToHost, so));
+            if (b->out_len) CK(cudaMemcpyAsync(b->out_len + c0, d.out_len + c0, (c1 - c0) * 4, cudaMemcpyDeviceToHost, so));
+            if (b->cells) CK(cudaMemcpyAsync(b->cells + c0, d.cells + c0, (c1 - c0) * 8, cudaMemcpyDeviceToHost, so));
+            const size_t ob = want_str ? o_hi[c] - o_lo[c] : 0;
+            if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped + o_lo[c], d.out_gapped + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+            if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1 + o_lo[c], d.out_slot1 + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+            if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2 + o_lo[c], d.out_slot2 + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+        }
+        CK(cudaEventRecord(ctx->ev1, st));
+        ctx->timed = true;
+        unsigned int h_cnt[10] = {0};
+        CK(cudaMemcpyAsync(h_cnt, p.counter, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(ctx->s_d2h));
+        for (size_t c = 0; c < nch; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+        cudaEventDestroy(ev_desc);
+        // the overflow counter accumulates over the chunks; with the wide kernel enabled every pair that
+        // fits a warp has been handled in its own chunk
+        if (h_cnt[8] == 0 && wide_ok) return PCGDO_OK;
+        // fall through: some pairs need the general-geometry kernel — redo the batch on the plain path
+    } else {
+        CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));
+    }
+
     rc = pcgdo_align2d_batch_device(ctx, tcm, &d, st);
     if (rc) return rc;
 

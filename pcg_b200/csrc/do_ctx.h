@@ -21,7 +21,8 @@ struct DevBuf {
 struct pcgdo_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    size_t host_chunk_pairs = 0;     // pairs per pipelined chunk of the host entry point (0 = 65536)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int last_launches = 0;

@@ -219,3 +219,35 @@ def test_bench_strings_dna_all_pairs(oracle_mod, gpu_ctx):
     pairs = [(strs[i], strs[j]) for i in range(20) for j in range(i + 1, 20)]
     gpu_ctx.configure(max_len=4700, max_b=32)
     _check_batch(o, gpu_ctx, tcm, pairs, want_cells=True)
+
+
+def test_pipelined_host_entry_point(oracle_mod, gpu_ctx):
+    """More pairs than one host chunk: copies of chunk c+1 / c-1 overlap the alignment of chunk c; results
+    must equal the single-shot path, including when a chunk contains pairs for the wide / general kernels."""
+    import pcg_b200 as P
+    sig = tcm_matrix("l1")
+    o = oracle_mod.Oracle(sig)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(5)
+    pairs = [random_pair(rng, 120) for _ in range(70000)]
+    pairs[100] = (random_string(rng, 700), random_string(rng, 400))       # wide kernel (B = 16/32)
+    pairs[69000] = (random_string(rng, 500), random_string(rng, 30))
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=720, max_b=32, arena_words=0)
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    r = P.align2d_batch(gpu_ctx, tcm, pp)
+    for k in list(range(0, 70000, 997)) + [100, 69000, 65535, 65536, 69999]:
+        oc = o.align2d(*pairs[k])
+        gc = r.pair(pp, k)
+        assert gc[0] == oc[0], k
+        for x, y in zip(gc[1:], oc[1:4]):
+            assert np.array_equal(x, y), k
+    # a pair only the general kernel can hold forces the plain path for the whole batch
+    pairs[5] = (random_string(rng, 2000), random_string(rng, 600))
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    r = P.align2d_batch(gpu_ctx, tcm, pp)
+    for k in [5, 100, 6, 69999]:
+        oc = o.align2d(*pairs[k])
+        gc = r.pair(pp, k)
+        assert gc[0] == oc[0], k
+        for x, y in zip(gc[1:], oc[1:4]):
+            assert np.array_equal(x, y), k
