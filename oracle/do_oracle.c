@@ -338,3 +338,159 @@ int64_t oracle_foreign_pairwise_do(const oracle_tcm_t *t,
     free(buf);
     return cost;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * C-affine dialect (see do_oracle.h).  Rows i = 1..S follow the SHORTER string, columns j = 1..L the
+ * longer one; four cost planes (close-block-diagonal CB, extend-block-diagonal EB, extend-vertical EV,
+ * extend-horizontal EH) kept as two rolling rows each, exactly like the reference, so that cells outside
+ * the band carry whatever the reference would read there.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    A2A = 1, A2V = 2, A2H = 4, A2D = 8, BEG_B = 16, END_B = 32, BEG_V = 64, END_V = 128, BEG_H = 256,
+    END_H = 512, DO_A = 1024, DO_V = 2048, DO_H = 4096, DO_D = 8192          /* alignCharacters.c:76-89 */
+};
+#define AFF_INF 100000u                                                       /* alignCharacters.h:70 */
+
+static uint32_t aff_sub(const oracle_tcm_t *t, int variant, uint32_t x, uint32_t y)
+{
+    if (variant) return t->cost[((size_t)x << t->a) + y];
+    /* as compiled for x86-64: the 32-bit shift count (costMatrixDimension = 2^a) is taken mod 32 */
+    return t->cost[((size_t)x << (t->dim & 31u)) + y];
+}
+
+int64_t oracle_align2d_affine(const oracle_tcm_t *t, int variant,
+                              const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                              uint32_t *out_gapped, uint32_t *out_slot1, uint32_t *out_slot2,
+                              size_t *out_len, uint64_t *cells_out)
+{
+    const int first_long = n1 >= n2;                                      /* c_alignment_interface.c:212 */
+    const size_t L = first_long ? n1 : n2, S = first_long ? n2 : n1;
+    const uint32_t g = t->gap, GO = t->gap_open, amb = g - 1;
+    uint32_t *lng = malloc(sizeof(uint32_t) * (L + 1)), *shr = malloc(sizeof(uint32_t) * (S + 1));
+    lng[0] = shr[0] = g;
+    memcpy(lng + 1, first_long ? in1 : in2, sizeof(uint32_t) * L);
+    memcpy(shr + 1, first_long ? in2 : in1, sizeof(uint32_t) * S);
+
+    const size_t W = L + 1;
+    uint32_t *buf = calloc(8 * W + 3 * W, sizeof(uint32_t));
+    uint32_t *CB[2] = { buf, buf + W }, *EB[2] = { buf + 2 * W, buf + 3 * W };
+    uint32_t *EV[2] = { buf + 4 * W, buf + 5 * W }, *EH[2] = { buf + 6 * W, buf + 7 * W };
+    uint32_t *gr = buf + 8 * W, *go = buf + 9 * W, *he = buf + 10 * W;
+    uint16_t *dir = calloc((S + 1) * W, sizeof(uint16_t));
+    uint32_t fc_last = 0;
+    uint64_t cells = 0;
+
+    /* row 0 (alignCharacters.c:3152-3173) */
+    CB[0][0] = 0; EB[0][0] = 0; EH[0][0] = GO; EV[0][0] = GO; dir[0] = 0xFFFF;
+    for (size_t j = 1; j <= L; j++) {
+        gr[j] = C(t, g, lng[j]);
+        const uint32_t r = EH[0][j - 1] + gr[j];
+        EH[0][j] = r; CB[0][j] = r; EB[0][j] = AFF_INF; EV[0][j] = AFF_INF;
+        dir[j] = DO_H | END_H;
+        if (j == L) fc_last = r;
+    }
+    /* per-column gap-open / horizontal-extension costs (:3585-3595) */
+    for (size_t j = 1; j <= L; j++) {
+        go[j] = (!(g & lng[j - 1]) && (g & lng[j])) ? 0 : GO;
+        he[j] = ((lng[j - 1] & g) && !(lng[j] & g)) ? go[j] + gr[j] : gr[j];
+    }
+    if (L >= 1) he[1] = gr[1];
+
+    size_t start = 1, end = (L - S) + 8;
+    if (end < 40) end = 40;
+    if (end > L) end = L;
+    for (size_t i = 1; i <= S; i++) {
+        uint32_t *cb = CB[i & 1], *eb = EB[i & 1], *ev = EV[i & 1], *eh = EH[i & 1];
+        const uint32_t *pcb = CB[(i - 1) & 1], *peb = EB[(i - 1) & 1], *pev = EV[(i - 1) & 1], *peh = EH[(i - 1) & 1];
+        uint16_t *d = dir + i * W;
+        if (i > 40) start++;
+        const uint32_t si = shr[i], sp = shr[i - 1], sng = si & amb;
+        const uint32_t ge = C(t, si, g);
+        const uint32_t so = (!(g & sp) && (g & si)) ? 0 : GO;
+        const uint32_t ve = (i > 1 && (sp & g) && !(si & g)) ? so + ge : ge;
+        /* border cell: vertical extension only (:3614-3634) */
+        const uint32_t r = pev[start - 1] + ve;
+        eh[start - 1] = AFF_INF; eb[start - 1] = AFF_INF; ev[start - 1] = r; cb[start - 1] = AFF_INF;
+        d[start - 1] = DO_V | END_V;
+        if (start - 1 == L) fc_last = r;
+        for (size_t j = start; j <= end; j++) {
+            const uint32_t lj = lng[j], lng_ = lj & amb;
+            uint16_t m = 0;
+            /* FILL_EXTEND_HORIZONTAL (:2527-2560): signed compare, strict */
+            int ext = (int)(eh[j - 1] + he[j]), opn = (int)(cb[j - 1] + go[j] + gr[j]);
+            if (ext < opn) { m |= BEG_H; eh[j] = (uint32_t)ext; } else { m |= END_H; eh[j] = (uint32_t)opn; }
+            /* FILL_EXTEND_VERTICAL (:2588-2617) */
+            ext = (int)(pev[j] + ve); opn = (int)(pcb[j] + so + ge);
+            if (ext < opn) { m |= BEG_V; ev[j] = (uint32_t)ext; } else { m |= END_V; ev[j] = (uint32_t)opn; }
+            /* FILL_EXTEND_BLOCK_DIAGONAL (:2660-2710): both options add the same `diag` */
+            const uint32_t dg0 = ((g & si) && (g & lj)) ? 0 : AFF_INF;
+            ext = (int)(peb[j - 1] + dg0); opn = (int)(pcb[j - 1] + dg0);
+            if (ext < opn) { m |= BEG_B; eb[j] = (uint32_t)ext; } else { m |= END_B; eb[j] = (uint32_t)opn; }
+            /* FILL_CLOSE_BLOCK_DIAGONAL (:2770-2848): unsigned compares */
+            const uint32_t dg = aff_sub(t, variant, sng, lng_);
+            const uint32_t xgo = go[j] < so ? so : go[j];
+            const uint32_t fv = (si == sng) ? pev[j - 1] + dg : pev[j - 1] + dg + go[j];
+            const uint32_t fh = (lj == lng_) ? peh[j - 1] + dg : peh[j - 1] + dg + so;
+            const uint32_t fd = peb[j - 1] + dg + xgo;
+            uint32_t c = pcb[j - 1] + dg;
+            uint16_t mk = A2A;
+            if (c >= fv) { if (c > fv) { c = fv; mk = A2V; } else mk |= A2V; }
+            if (c >= fh) { if (c > fh) { c = fh; mk = A2H; } else mk |= A2H; }
+            if (c >= fd) { if (c > fd) { c = fd; mk = A2D; } else mk |= A2D; }
+            cb[j] = c;
+            m |= mk;
+            /* ASSIGN_MINIMUM (:3218-3256) */
+            uint32_t f = eh[j];
+            mk = DO_H;
+            if (f >= ev[j]) { if (f > ev[j]) { f = ev[j]; mk = DO_V; } else mk |= DO_V; }
+            if (f >= eb[j]) { if (f > eb[j]) { f = eb[j]; mk = DO_D; } else mk |= DO_D; }
+            if (f >= cb[j]) { if (f > cb[j]) { f = cb[j]; mk = DO_A; } else mk |= DO_A; }
+            m |= mk;
+            d[j] = m;
+            if (j == L) fc_last = f;
+            cells++;
+        }
+        if (end < L) {
+            end++;
+            d[end] = DO_H | END_H;
+            ev[end] = AFF_INF; cb[end] = AFF_INF; eh[end] = AFF_INF; eb[end] = AFF_INF;
+        }
+    }
+    if (cells_out) *cells_out = cells;
+    const int64_t cost = (int64_t)fc_last;
+
+    /* traceback state machine (:2850-3010) */
+    enum { M_TODO, M_V, M_H, M_D, M_A } mode = M_TODO;
+    size_t si_ = S, li_ = L, n = 0, cap = S + L + 2;
+    uint32_t *rm = malloc(sizeof(uint32_t) * cap), *rs = malloc(sizeof(uint32_t) * cap), *rl = malloc(sizeof(uint32_t) * cap);
+    while (si_ != 0 && li_ != 0) {
+        const uint16_t fl = dir[si_ * W + li_];
+        const uint32_t se = shr[si_], le = lng[li_];
+        if (mode == M_TODO) {
+            if (fl & DO_H) mode = M_H; else if (fl & DO_A) mode = M_A; else if (fl & DO_V) mode = M_V; else mode = M_D;
+        } else if (mode == M_V) {
+            if (fl & END_V) mode = M_TODO;
+            rm[n] = !(se & g) ? (se | g) : g; rs[n] = se; rl[n] = g; n++; si_--;
+        } else if (mode == M_H) {
+            if (fl & END_H) mode = M_TODO;
+            rm[n] = !(le & g) ? (le | g) : g; rs[n] = g; rl[n] = le; n++; li_--;
+        } else if (mode == M_D) {
+            if (fl & END_B) mode = M_TODO;
+            rm[n] = g; rs[n] = se; rl[n] = le; n++; si_--; li_--;
+        } else {
+            if (fl & A2H) mode = M_H; else if (fl & A2D) mode = M_D; else if (fl & A2V) mode = M_V;
+            rm[n] = t->median[((size_t)(se & amb) << t->a) + (le & amb)]; rs[n] = se; rl[n] = le; n++; si_--; li_--;
+        }
+    }
+    while (si_ != 0) { const uint32_t se = shr[si_]; rm[n] = !(se & g) ? (se | g) : g; rs[n] = se; rl[n] = g; n++; si_--; }
+    while (li_ != 0) { const uint32_t le = lng[li_]; rm[n] = !(le & g) ? (le | g) : g; rs[n] = g; rl[n] = le; n++; li_--; }
+    for (size_t k = 0; k < n; k++) {
+        out_gapped[k] = rm[n - 1 - k];
+        const uint32_t as = rs[n - 1 - k], al = rl[n - 1 - k];
+        out_slot1[k] = first_long ? al : as;            /* natural order: each slot keeps its own string */
+        out_slot2[k] = first_long ? as : al;
+    }
+    *out_len = n;
+    free(rm); free(rs); free(rl); free(dir); free(buf); free(lng); free(shr);
+    return cost;
+}

@@ -70,6 +70,21 @@ int64_t oracle_foreign_pairwise_do(const oracle_tcm_t *t,
                                    uint32_t *om, uint32_t *ol, uint32_t *orr, size_t *on, int *omissing,
                                    uint64_t *cells);
 
+
+/* C-affine dialect: raw align2dAffine (EXT/c_alignment_interface.c:180-348, EXT/alignCharacters.c:2470-3010,
+ * 3124-3256, 3483-3727) with getMedians = 1.  PARITY UNPINNED: the reference has no golden vector for it and its
+ * substitution lookup has undefined behaviour (`no_gap << costMatrixDimension`, alignCharacters.c:3636).
+ *   variant 0 = "as coded" on x86-64 (shift count taken mod 32: the lookup reads cost_flat[x' + y']),
+ *   variant 1 = "patched"  (`<< alphSize`, the evidently intended cost[x'][y']).
+ * Outputs in natural order, length *out_len: out_gapped = what lands in gappedOutput_aio (the full-length median,
+ * the two median buffers are crossed at c_alignment_interface.c:314-325), out_slot1 / out_slot2 = inputChar1 /
+ * inputChar2 after the call (natural order: each slot keeps ITS OWN string, gaps as gap_char).
+ * cells = DP cells inside the reference's band. */
+int64_t oracle_align2d_affine(const oracle_tcm_t *t, int variant,
+                              const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                              uint32_t *out_gapped, uint32_t *out_slot1, uint32_t *out_slot2,
+                              size_t *out_len, uint64_t *cells);
+
 #ifdef __cplusplus
 }
 #endif

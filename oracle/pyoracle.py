@@ -23,6 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "liboracle_do.so")
 REF_SO = os.path.join(_HERE, "_ref", "libpcgdo_ref.so")
 REF_MEMO_SO = os.path.join(_HERE, "_ref", "libtcmmemo_ref.so")
+REF_PATCHED_SO = os.path.join(_HERE, "_ref", "libpcgdo_ref_patched.so")
 
 _u32p = C.POINTER(C.c_uint32)
 
@@ -30,7 +31,7 @@ _u32p = C.POINTER(C.c_uint32)
 def build(ref: bool = True) -> None:
     """Compile the restatement (always) and, if the reference tree is present, ``_ref``."""
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
-    if ref and os.path.isdir("/root/reference") and not os.path.exists(REF_SO):
+    if ref and os.path.isdir("/root/reference") and not (os.path.exists(REF_SO) and os.path.exists(REF_PATCHED_SO)):
         subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
 
 
@@ -102,6 +103,23 @@ class Oracle:
         k = n.value
         return int(cost), g[:k].copy(), s1[:k].copy(), s2[:k].copy(), int(cells.value)
 
+    def align2d_affine(self, in1, in2, variant: int = 0):
+        """Raw ``align2dAffine(..., getMedians=1)``; variant 0 = as coded (x86), 1 = patched shift.
+        Returns (cost, gapped, slot1, slot2, cells)."""
+        L = self.lib
+        L.oracle_align2d_affine.restype = C.c_int64
+        L.oracle_align2d_affine.argtypes = [C.c_void_p, C.c_int, _u32p, C.c_size_t, _u32p, C.c_size_t,
+                                            _u32p, _u32p, _u32p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+        a1, a2 = _as_u32(in1), _as_u32(in2)
+        cap = len(a1) + len(a2) + 2
+        g, s1, s2 = (np.zeros(cap, np.uint32) for _ in range(3))
+        n = C.c_size_t(0)
+        cells = C.c_uint64(0)
+        cost = L.oracle_align2d_affine(self.t, variant, _ptr(a1), len(a1), _ptr(a2), len(a2),
+                                       _ptr(g), _ptr(s1), _ptr(s2), C.byref(n), C.byref(cells))
+        k = n.value
+        return int(cost), g[:k].copy(), s1[:k].copy(), s2[:k].copy(), int(cells.value)
+
     def pairwise_do(self, c1, c2):
         """Haskell-level ``foreignPairwiseDO``. A character is ``None`` (Missing) or an (n,3) array of
         (median,left,right). Returns (cost, character-or-None, cells)."""
@@ -139,8 +157,8 @@ class Reference:
     def available() -> bool:
         return os.path.exists(REF_SO)
 
-    def __init__(self, sigma, gap_open: int = 0):
-        self.lib = C.CDLL(REF_SO)
+    def __init__(self, sigma, gap_open: int = 0, patched: bool = False):
+        self.lib = C.CDLL(REF_PATCHED_SO if patched else REF_SO)
         self.libc = C.CDLL(None)
         self.libc.malloc.restype = C.c_void_p
         self.libc.malloc.argtypes = [C.c_size_t]
