@@ -130,6 +130,18 @@ int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo
 /* Host buffers in, host buffers out: H2D copies, kernels and D2H copies inside the call. */
 int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b);
 
+/* ---------------------------------------------------------------- affine gap costs
+ * align2dAffine (EXT/c_alignment_interface.c:180-348) per pair: out_gapped = what the reference leaves in
+ * gappedOutput_aio (the full-length median), out_slot1 / out_slot2 = inputChar1 / inputChar2 after the call
+ * (each slot keeps its own string, gaps as gap_char).  The reference's substitution lookup is undefined
+ * behaviour (alignCharacters.c:3636 shifts by 2^a); `variant` 0 reproduces the reference as compiled for x86-64
+ * (shift count mod 32), 1 the evidently intended `<< alphSize`.  PCG itself never enables affine costs
+ * (gap-open is hard-wired to 0, Bio/Metadata/Dynamic/Internal.hs:346); upstream has no golden vector for it. */
+int pcgdo_tcm_create_affine(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, unsigned int gap_open, int variant,
+                            pcgdo_tcm **out);
+int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream);
+int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b);
+
 /* Finer tunables: widest diagonals-per-lane variant the warp kernels must accommodate (2,4,8,16,32; pairs
  * needing more go to the general-geometry kernel) and the per-warp scratch arena in 32-bit words (0 = derive
  * from max_len). */

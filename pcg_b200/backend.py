@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_tcm_create", "pcgdo_tcm_destroy",
     "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
     "pcgdo_configure_ex", "pcgdo_int32_peak",
+    "pcgdo_tcm_create_affine", "pcgdo_align2d_affine_batch_device", "pcgdo_align2d_affine_batch_host",
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
@@ -78,6 +79,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_configure_ex.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     L.pcgdo_tcm_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_uint, C.POINTER(C.c_void_p)]
     L.pcgdo_tcm_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_tcm_create_affine.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]
+    L.pcgdo_align2d_affine_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch), C.c_void_p]
+    L.pcgdo_align2d_affine_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
     L.pcgdo_align2d_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch), C.c_void_p]
     L.pcgdo_align2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
     L.pcgdo_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -137,8 +141,8 @@ class Context:
         self.check(self.lib.pcgdo_configure(self.h, pairs_per_warp, warps_per_cta, max_len), "pcgdo_configure")
         self.check(self.lib.pcgdo_configure_ex(self.h, max_b, arena_words), "pcgdo_configure_ex")
 
-    def tcm(self, sigma, gap_open: int = 0) -> "Tcm":
-        return Tcm(self, sigma, gap_open)
+    def tcm(self, sigma, gap_open: int = 0, affine_variant: int = 0) -> "Tcm":
+        return Tcm(self, sigma, gap_open, affine_variant)
 
     def int32_peak(self, mode: int = 0) -> float:
         """Measured integer lane-ops/s of this GPU (roofline denominator for the DP fill)."""
@@ -153,15 +157,20 @@ class Context:
 
 
 class Tcm:
-    def __init__(self, ctx: Context, sigma, gap_open: int = 0):
+    def __init__(self, ctx: Context, sigma, gap_open: int = 0, affine_variant: int = 0):
         self.ctx = ctx
+        self.gap_open = gap_open
         sigma = np.ascontiguousarray(np.asarray(sigma, dtype=np.uint32))
         self.a = int(sigma.shape[0])
         assert sigma.shape == (self.a, self.a)
         self.gap = 1 << (self.a - 1)
         h = C.c_void_p()
-        ctx.check(ctx.lib.pcgdo_tcm_create(ctx.h, sigma.ctypes.data_as(_u32p), self.a, gap_open, C.byref(h)),
-                  "pcgdo_tcm_create")
+        if gap_open:
+            ctx.check(ctx.lib.pcgdo_tcm_create_affine(ctx.h, sigma.ctypes.data_as(_u32p), self.a, gap_open,
+                                                      affine_variant, C.byref(h)), "pcgdo_tcm_create_affine")
+        else:
+            ctx.check(ctx.lib.pcgdo_tcm_create(ctx.h, sigma.ctypes.data_as(_u32p), self.a, gap_open, C.byref(h)),
+                      "pcgdo_tcm_create")
         self.h = h
         # dense host tables from the library's own host code (setUp2dCostMtx), for the wrapper's
         # "one string empty" case and for callers that want lookupPairwise

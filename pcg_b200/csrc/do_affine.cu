@@ -1,0 +1,486 @@
+// do_affine.cu — affine-gap pairwise direct optimization ("C-affine" dialect) for sm_100a.
+//
+// Replaces align2dAffine (EXT/c_alignment_interface.c:180-348): plane initialisation
+// (EXT/alignCharacters.c:3124-3215), the banded 4-plane fill (:3483-3727 with FILL_EXTEND_HORIZONTAL /
+// _VERTICAL / _BLOCK_DIAGONAL, FILL_CLOSE_BLOCK_DIAGONAL :2523-2848 and ASSIGN_MINIMUM :3218-3256) and the
+// traceback state machine with its median rules (:2850-3010).  PARITY UNPINNED upstream (no golden vector;
+// the substitution lookup at :3636 is undefined behaviour): the device table `aff_sub` is built on the host
+// for either reading of that expression ("as coded on x86-64" or "patched"), the kernel is the same.
+//
+// Geometry.  Rows i = 1..S follow the SHORTER string, columns j = 1..L the longer one.  The reference's band
+// (start_pos advancing after row 40, end_pos = max(40, L-S+8) growing by one per row) is the diagonal range
+// d = j - i in [-40, E0] where d = -40 and column 0 hold its vertical-only border cells and d = E0 its
+// all-infinite right border.  One warp owns one pair; lane k owns B consecutive diagonals and keeps the four
+// plane values of each diagonal's latest cell in registers.  A ROW is processed per step (the warp is uniform
+// in i, so every per-row quantity of the reference is a broadcast load): CB / EV / EB of row i depend on row
+// i-1 only and are computed for all cells at once; EH, the only plane with an in-row dependency
+// (EH[j] = min(EH[j-1] + he[j], CB[j-1] + go[j] + gr[j])), is a min-plus prefix scan over the row
+// (lane-local composition + 5 shuffle steps).  Each cell's traceback information (which plane wins, with the
+// reference's priority horizontal > align > vertical > diagonal; the next mode out of an align step,
+// horizontal > diagonal > vertical > stay; the three END flags) is one byte; four rows make a word per
+// diagonal, stored as B consecutive words per lane.  Trace runs one lane per pair after a warp has filled
+// its hand-out of pairs; emit is warp-cooperative with coalesced stores.
+#include "do_device.cuh"
+
+namespace pcgdo {
+
+constexpr unsigned kFullA = 0xffffffffu;
+constexpr uint32_t kAInf = 1u << 28;          // "very large": finite values stay far below it (checked on the host)
+constexpr uint32_t kACap = 2u << 28;          // clamp for sums of "very large" values
+constexpr int kDB = -40;                      // left border diagonal (alignCharacters.c:3500 start_v = 40)
+
+struct AffGeom { int S, L, E0, wq_need; };
+
+__host__ __device__ inline AffGeom make_aff_geom(int S, int L)
+{
+    AffGeom g;
+    g.S = S; g.L = L;
+    int e = (L - S) + 8;
+    if (e < 40) e = 40;
+    if (e > L) e = L;
+    g.E0 = e;
+    g.wq_need = e - kDB + 1;                  // diagonals -40 .. E0
+    return g;
+}
+__host__ __device__ inline int aff_choose_b(int wq_need)
+{
+    if (wq_need <= 128) return 4;
+    if (wq_need <= 256) return 8;
+    if (wq_need <= 512) return 16;
+    if (wq_need <= 1024) return 32;
+    return 0;
+}
+// per-pair scratch (32-bit words): direction words | op stream | column params (2 words each) | row params
+__host__ __device__ inline uint32_t aff_dir_words(const AffGeom &g, int B) { return (uint32_t)(g.S / 4 + 1) * 32u * (uint32_t)B; }
+__host__ __device__ inline uint32_t aff_ops_words(const AffGeom &g) { return ((uint32_t)(g.S + g.L) / 16u + 4u) & ~1u; }
+__host__ __device__ inline uint32_t aff_col_entries(const AffGeom &g, int B) { return (uint32_t)(g.L + 32 * B + 96); }
+__host__ __device__ inline uint32_t aff_need_words(const AffGeom &g, int B)
+{
+    return (aff_dir_words(g, B) + aff_ops_words(g) + 2u * aff_col_entries(g, B) + 2u * (uint32_t)(g.S + 8) +
+            (uint32_t)(g.L + 8) + 7u) & ~3u;
+}
+constexpr int kColPad = 48;                   // column-parameter entries in front of j = 0 (j runs down to 1 - 40 - ...)
+
+struct AffParams {
+    TcmDev    tcm;
+    BatchDev  b;
+    const uint16_t *aff_sub;   // [s' << (a-1) | l'] substitution costs between gap-stripped elements
+    uint32_t  gap_open;
+    uint32_t *arena;
+    uint32_t  arena_words;
+    int       pairs_per_warp;
+    unsigned int *counter;
+    unsigned int *overflow_count;
+};
+
+// column entry: .x = gr (cost[gap][l_j]); .y = l'_j | lgap << 8 | go_is_open << 9 | he_has_open << 10
+// row entry   : .x = ve;                  .y = ge | so_is_open << 16 | sgap << 17 | s'_i << 24
+
+template <int B, bool EARLY>
+__device__ __forceinline__ void aff_row(uint32_t (&CB)[B], uint32_t (&EB)[B], uint32_t (&EV)[B], uint32_t (&EH)[B],
+                                        const uint32_t (&penup)[B], uint32_t (&fl)[B], const uint2 *colpar, uint2 rp,
+                                        uint32_t GO, const uint16_t *sub, int sub_shift, int i, int d0, int lane)
+{
+    const uint32_t ve = rp.x, ge = rp.y & 0xffffu, so = ((rp.y >> 16) & 1u) ? GO : 0u, sgap = (rp.y >> 17) & 1u;
+    const uint16_t *subrow = sub + ((rp.y >> 24) << sub_shift);
+    // up neighbours: diagonal q+1 of the previous row; the block edge comes from the next lane
+    const uint32_t nEV = __shfl_down_sync(kFullA, EV[0], 1), nCB = __shfl_down_sync(kFullA, CB[0], 1);
+    uint32_t cbn[B], evn[B], ebn[B], ha[B], hb[B];
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int j = i + d0 + m;
+        const uint2 cp = colpar[j];
+        const uint32_t gr = cp.x, lq = cp.y & 0xffu, lgap = (cp.y >> 8) & 1u;
+        const uint32_t go = ((cp.y >> 9) & 1u) ? GO : 0u, he = gr + (((cp.y >> 10) & 1u) ? go : 0u);
+        uint32_t uEV = (m == B - 1) ? nEV : EV[m + 1 < B ? m + 1 : m];
+        uint32_t uCB = (m == B - 1) ? nCB : CB[m + 1 < B ? m + 1 : m];
+        const uint32_t pen = (EARLY && i == 1) ? 0u : penup[m];   // row 1 still sees the real row-0 cell there
+        uEV |= pen;
+        uCB |= pen;
+        // extend vertical (FILL_EXTEND_VERTICAL)
+        const uint32_t vx = uEV + ve, vo = uCB + so + ge;
+        uint32_t ev = min(vx, vo);
+        uint32_t endv = !(vx < vo);
+        // extend block diagonal (FILL_EXTEND_BLOCK_DIAGONAL): both options add the same term
+        uint32_t eb = (sgap & lgap) ? min(EB[m], CB[m]) : kAInf;
+        const uint32_t endb = !(EB[m] < CB[m]);
+        // close block diagonal (FILL_CLOSE_BLOCK_DIAGONAL)
+        const uint32_t dg = subrow[lq];
+        const uint32_t ca = CB[m] + dg;
+        const uint32_t fv = EV[m] + dg + (sgap ? go : 0u);
+        const uint32_t fh = EH[m] + dg + (lgap ? so : 0u);
+        const uint32_t fd = EB[m] + dg + max(go, so);
+        uint32_t cb = min(min(ca, fv), min(fh, fd));
+        uint32_t an = 3u;                       // next mode out of an align step: H > D > V > stay
+        an = (fv == cb) ? 2u : an;
+        an = (fd == cb) ? 1u : an;
+        an = (fh == cb) ? 0u : an;
+        const bool border = EARLY ? (j == 0) : (m == 0 && lane == 0);   // vertical extension only (:3624-3634)
+        const bool outside = EARLY && j < 0;
+        if (border) { ev = vx; cb = kAInf; eb = kAInf; endv = 1u; }
+        if (outside) { ev = kAInf; cb = kAInf; eb = kAInf; }
+        cbn[m] = min(cb, kACap); evn[m] = min(ev, kACap); ebn[m] = eb;
+        fl[m] = (an << 2) | (endv << 4) | (endb << 6);
+        // horizontal extension as the min-plus map x -> min(x + a, b); b gets CB[j-1] of THIS row below
+        ha[m] = (border || outside) ? 0u : he;
+        hb[m] = go + gr;
+    }
+    const uint32_t lCB = __shfl_up_sync(kFullA, cbn[B - 1], 1);
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int j = i + d0 + m;
+        const uint32_t left = (m == 0) ? (lane == 0 ? kAInf : lCB) : cbn[m > 0 ? m - 1 : 0];
+        const bool dead = EARLY ? (j <= 0) : (m == 0 && lane == 0);
+        hb[m] = dead ? kACap : min(left + hb[m], kACap);
+    }
+    uint32_t A = 0, Bv = kACap;                 // composition of this lane's maps, then exclusive scan over lanes
+#pragma unroll
+    for (int m = 0; m < B; ++m) { Bv = min(Bv + ha[m], hb[m]); A += ha[m]; }
+    A = min(A, kAInf);
+    Bv = min(Bv, kACap);
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const uint32_t A2 = __shfl_up_sync(kFullA, A, dlt), B2 = __shfl_up_sync(kFullA, Bv, dlt);
+        if (lane >= dlt) { Bv = min(min(B2 + A, Bv), kACap); A = min(A2 + A, kAInf); }
+    }
+    uint32_t x = __shfl_up_sync(kFullA, Bv, 1);   // EH just left of this lane's first cell
+    if (lane == 0) x = kACap;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const uint32_t hx = x + ha[m], ho = hb[m];
+        uint32_t eh = min(min(hx, ho), kACap);
+        const uint32_t endh = !(hx < ho);
+        x = eh;
+        // ASSIGN_MINIMUM: which plane ends here, priority horizontal > align > vertical > diagonal
+        const uint32_t fc = min(min(eh, evn[m]), min(ebn[m], cbn[m]));
+        uint32_t td = 3u;
+        td = (evn[m] == fc) ? 2u : td;
+        td = (cbn[m] == fc) ? 1u : td;
+        td = (eh == fc) ? 0u : td;
+        fl[m] |= td | (endh << 5);
+        CB[m] = cbn[m]; EV[m] = evn[m]; EB[m] = ebn[m]; EH[m] = eh;
+    }
+}
+
+template <int B>
+__device__ __forceinline__ void aff_store(uint32_t *dst, const uint32_t (&dw)[B])
+{
+#pragma unroll
+    for (int m = 0; m < B; m += 4) *reinterpret_cast<uint4 *>(dst + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+}
+
+// Fills one pair; returns FC at (S, L).  colpar points at the entry of column j = 0.
+template <int B>
+__device__ __noinline__ uint32_t aff_fill(const AffGeom g, uint32_t GO, const uint16_t *sub, int sub_shift,
+                                          const uint2 *colpar, const uint2 *rowpar, const uint32_t *row0,
+                                          uint32_t *dirw, int lane)
+{
+    uint32_t CB[B], EB[B], EV[B], EH[B], penup[B], fl[B], dw[B];
+    const int d0 = kDB + lane * B;
+    const int qE = g.E0 - kDB;                   // diagonal index of the right border
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int q = lane * B + m, d = kDB + q;
+        penup[m] = (q + 1 >= qE) ? kAInf : 0u;   // the cell above the last in-band diagonal is "very large"
+        // row 0 (:3152-3173): cell (0, d)
+        CB[m] = EB[m] = EV[m] = EH[m] = kAInf;
+        if (d == 0) { CB[m] = 0; EB[m] = 0; EV[m] = GO; EH[m] = GO; }
+        else if (d > 0 && d <= g.L) { CB[m] = row0[d]; EH[m] = row0[d]; }
+        dw[m] = 0;
+    }
+    uint32_t fc_last = 0;
+    const int q_last = (g.L - g.S) - kDB, lane_last = q_last / B, m_last = q_last % B;
+    int i = 1;
+    const int early_end = g.S < 40 ? g.S : 40;
+    for (; i <= early_end; ++i) {
+        aff_row<B, true>(CB, EB, EV, EH, penup, fl, colpar, rowpar[i], GO, sub, sub_shift, i, d0, lane);
+#pragma unroll
+        for (int m = 0; m < B; ++m) dw[m] |= fl[m] << (8 * (i & 3));
+        if ((i & 3) == 3) {
+            aff_store<B>(dirw + (size_t)(i >> 2) * 32 * B + lane * B, dw);
+#pragma unroll
+            for (int m = 0; m < B; ++m) dw[m] = 0;
+        }
+    }
+    for (; i <= g.S; ++i) {
+        aff_row<B, false>(CB, EB, EV, EH, penup, fl, colpar, rowpar[i], GO, sub, sub_shift, i, d0, lane);
+#pragma unroll
+        for (int m = 0; m < B; ++m) dw[m] |= fl[m] << (8 * (i & 3));
+        if ((i & 3) == 3) {
+            aff_store<B>(dirw + (size_t)(i >> 2) * 32 * B + lane * B, dw);
+#pragma unroll
+            for (int m = 0; m < B; ++m) dw[m] = 0;
+        }
+    }
+    if ((g.S & 3) != 3) aff_store<B>(dirw + (size_t)(g.S >> 2) * 32 * B + lane * B, dw);
+    // FC of the last cell = min over the four planes there
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < B; ++m)
+        if (m == m_last) v = min(min(EH[m], EV[m]), min(EB[m], CB[m]));
+    fc_last = __shfl_sync(kFullA, v, lane_last);
+    return fc_last;
+}
+
+// One lane per pair.  Op codes: 0 vertical (consume shorter), 1 horizontal (consume longer), 2 block diagonal,
+// 3 align.  Written in traceback order (last column first), 2 bits each.
+__device__ __forceinline__ uint32_t aff_trace(const uint32_t *dirw, uint32_t wq, int S, int L, uint32_t *ops)
+{
+    int si = S, li = L;
+    uint32_t n = 0, acc = 0;
+    int mode = 0;                                  // 0 todo, 1 vertical, 2 horizontal, 3 diagonal, 4 align
+    auto put = [&](uint32_t code) {
+        acc |= code << (2 * (n & 15));
+        ++n;
+        if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
+    };
+    while (si != 0 && li != 0) {
+        const int q = li - si - kDB;
+        const uint32_t f = (__ldcg(dirw + (size_t)(si >> 2) * wq + q) >> (8 * (si & 3))) & 0xffu;
+        if (mode == 0) {
+            const uint32_t td = f & 3u;            // 0 H, 1 A, 2 V, 3 D
+            mode = td == 0 ? 2 : td == 1 ? 4 : td == 2 ? 1 : 3;
+        } else if (mode == 1) {
+            if (f & 16u) mode = 0;
+            put(0); --si;
+        } else if (mode == 2) {
+            if (f & 32u) mode = 0;
+            put(1); --li;
+        } else if (mode == 3) {
+            if (f & 64u) mode = 0;
+            put(2); --si; --li;
+        } else {
+            const uint32_t an = (f >> 2) & 3u;     // 0 H, 1 D, 2 V, 3 stay
+            mode = an == 0 ? 2 : an == 1 ? 3 : an == 2 ? 1 : 4;
+            put(3); --si; --li;
+        }
+    }
+    while (si != 0) { put(0); --si; }
+    while (li != 0) { put(1); --li; }
+    if (n & 15) ops[n >> 4] = acc;
+    return n;
+}
+
+__device__ __forceinline__ void aff_emit(const TcmDev &tcm, const uint8_t *pL, const uint8_t *pS, const uint32_t *ops,
+                                         uint32_t nal, bool first_long, uint8_t *og, uint8_t *o1, uint8_t *o2, int lane)
+{
+    uint32_t base_l = 0, base_s = 0;
+    const uint32_t g = tcm.gap, amb = g - 1u;
+    for (uint32_t c0 = 0; c0 < nal; c0 += 128) {
+        const uint32_t c = c0 + 4u * lane;
+        uint32_t code[4], nl = 0, ns = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const uint32_t cc = c + x;
+            code[x] = 4u;
+            if (cc < nal) {
+                const uint32_t r = nal - 1u - cc;
+                code[x] = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
+            }
+            nl += (code[x] == 1u || code[x] == 2u || code[x] == 3u);
+            ns += (code[x] == 0u || code[x] == 2u || code[x] == 3u);
+        }
+        const uint32_t packed = nl | (ns << 16);
+        uint32_t incl = packed;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFullA, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t excl = incl - packed;
+        uint32_t il = base_l + (excl & 0xffffu), is = base_s + (excl >> 16);
+        uint32_t wg = 0, ws = 0, wl = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            uint32_t se = g, le = g, md = 0;
+            if (code[x] != 4u) {
+                if (code[x] != 0u) { le = __ldg(pL + il); ++il; }
+                if (code[x] != 1u) { se = __ldg(pS + is); ++is; }
+                if (code[x] == 0u)      md = (se & g) ? g : (se | g);          // vertical   (:2904-2916)
+                else if (code[x] == 1u) md = (le & g) ? g : (le | g);          // horizontal (:2917-2931)
+                else if (code[x] == 2u) md = g;                                // block diagonal
+                else md = __ldg(tcm.median + (((se & amb) << tcm.a) | (le & amb)));
+            } else { se = 0; le = 0; }
+            wg |= md << (8 * x);
+            ws |= se << (8 * x);
+            wl |= le << (8 * x);
+        }
+        if (c < nal) {
+            if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
+            if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wl : ws;   // slots keep their own string
+            if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? ws : wl;
+        }
+        const uint32_t tot = __shfl_sync(kFullA, incl, 31);
+        base_l += tot & 0xffffu;
+        base_s += tot >> 16;
+    }
+}
+
+extern __shared__ __align__(16) char aff_smem[];
+
+__global__ void __launch_bounds__(512, 1) do_affine_kernel(const AffParams p)
+{
+    const TcmDev &tcm = p.tcm;
+    const BatchDev &b = p.b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int hdim = 1 << (tcm.a - 1);
+    // shared: substitution table between gap-stripped elements, then per-warp bookkeeping
+    uint16_t *s_sub = reinterpret_cast<uint16_t *>(aff_smem);
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(aff_smem + (size_t)hdim * hdim * 2) + warp * 96;
+    uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64;
+    for (int x = threadIdx.x; x < hdim * hdim; x += blockDim.x) s_sub[x] = p.aff_sub[x];
+    __syncthreads();
+
+    const uint32_t GO = p.gap_open, g = tcm.gap;
+    const int G = p.pairs_per_warp;
+    uint32_t *arena = p.arena + ((size_t)blockIdx.x * nwarps + warp) * (size_t)p.arena_words;
+    const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
+        base = __shfl_sync(kFullA, base, 0);
+        if (base >= b.n_pairs) break;
+        const int npw = (int)min((uint32_t)G, b.n_pairs - base);
+        int pi = 0;
+        while (pi < npw) {
+            const int start = pi;
+            uint32_t cur = 0;
+            for (; pi < npw; ++pi) {
+                const uint32_t k = base + pi;
+                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                const bool fl = n1 >= n2;                                    // c_alignment_interface.c:212
+                const uint8_t *pL = b.elems + (fl ? b.off1[k] : b.off2[k]), *pS = b.elems + (fl ? b.off2[k] : b.off1[k]);
+                const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
+                const int B = aff_choose_b(ag.wq_need);
+                const uint32_t need = B ? aff_need_words(ag, B) : 0u;
+                if (!B || need > p.arena_words) {
+                    if (lane == 0) { s_flags[pi] = 0; atomicAdd(p.overflow_count, 1u); }
+                    continue;
+                }
+                if (cur + need > p.arena_words) break;
+                if (lane == 0) { s_flags[pi] = (fl ? 1u : 0u) | 2u; s_off[pi] = cur; }
+                uint32_t *slot = arena + cur;
+                cur += need;
+                uint32_t *dirw = slot;
+                uint32_t *ops = dirw + aff_dir_words(ag, B);
+                uint2 *colbase = reinterpret_cast<uint2 *>(ops + aff_ops_words(ag));
+                uint2 *colpar = colbase + kColPad;                            // entry of column j = 0
+                uint2 *rowpar = colbase + aff_col_entries(ag, B);
+                uint32_t *row0 = reinterpret_cast<uint32_t *>(rowpar + ag.S + 8);   // L + 1 words: EH = CB of row 0
+                // ---- per-column parameters (:3585-3595) and row 0 prefix; per-row parameters (:3614-3625)
+                const int ncol = (int)aff_col_entries(ag, B);
+                uint32_t carry = GO;
+                for (int base_j = -kColPad; base_j < ncol - kColPad; base_j += 32) {
+                    const int j = base_j + lane;
+                    uint32_t gr = 0, y = 0;
+                    if (j >= 0 && j <= ag.L) {
+                        const uint32_t lj = j == 0 ? g : __ldg(pL + j - 1);
+                        const uint32_t lp = j <= 1 ? g : __ldg(pL + j - 2);       // l_{j-1}; l_0 = gap
+                        if (j >= 1) {
+                            gr = tcm.gapc[lj];
+                            const uint32_t go_open = !(!(g & lp) && (g & lj));
+                            uint32_t he_open = ((lp & g) && !(lj & g)) ? go_open : 0u;
+                            if (j == 1) he_open = 0u;                             // he[1] = gr[1]
+                            y = (lj & (g - 1u)) | (((lj & g) ? 1u : 0u) << 8) | (go_open << 9) | (he_open << 10);
+                        }
+                    }
+                    if (j < ncol - kColPad) colpar[j] = make_uint2(gr, y);
+                    // inclusive prefix of gr over the warp for row 0
+                    uint32_t s = gr;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(kFullA, s, d);
+                        if (lane >= d) s += o;
+                    }
+                    if (j >= 1 && j <= ag.L) row0[j] = carry + s;
+                    carry += __shfl_sync(kFullA, s, 31);
+                }
+                for (int i = 1 + lane; i <= ag.S; i += 32) {
+                    const uint32_t si = __ldg(pS + i - 1), sp = i == 1 ? g : __ldg(pS + i - 2);
+                    const uint32_t ge = tcm.cgap[si];
+                    const uint32_t so_open = !(!(g & sp) && (g & si));
+                    const uint32_t so = so_open ? GO : 0u;
+                    const uint32_t ve = (i > 1 && (sp & g) && !(si & g)) ? so + ge : ge;
+                    rowpar[i] = make_uint2(ve, ge | (so_open << 16) | (((si & g) ? 1u : 0u) << 17) | ((si & (g - 1u)) << 24));
+                }
+                __syncwarp();
+                uint32_t fc = 0;
+                const uint32_t *r0p = row0;
+                if (ag.S > 0) {
+                    switch (B) {
+                        case 4:  fc = aff_fill<4>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
+                        case 8:  fc = aff_fill<8>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
+                        case 16: fc = aff_fill<16>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
+                        default: fc = aff_fill<32>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
+                    }
+                } else {
+                    fc = ag.L > 0 ? r0p[ag.L] : 0u;
+                }
+                if (lane == 0) b.cost[k] = (int32_t)fc;
+                if (b.cells && lane == 0) {
+                    unsigned long long c = 0;
+                    for (int i = 1; i <= ag.S; ++i) {
+                        int lo = i > 40 ? i - 39 : 1, hi = ag.E0 + i - 1;
+                        if (hi > ag.L) hi = ag.L;
+                        if (hi >= lo) c += (unsigned long long)(hi - lo + 1);
+                    }
+                    b.cells[k] = c;
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            if (!want_out) continue;
+            const int pj = start + lane;
+            if (pj < pi && (s_flags[pj] & 2u)) {
+                const uint32_t k = base + pj;
+                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                const bool fl = s_flags[pj] & 1u;
+                const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
+                const int B = aff_choose_b(ag.wq_need);
+                uint32_t *slot = arena + s_off[pj];
+                const uint32_t n = aff_trace(slot, 32u * B, ag.S, ag.L, slot + aff_dir_words(ag, B));
+                s_nal[pj] = n;
+                if (b.out_len) b.out_len[k] = n;
+            }
+            __syncwarp();
+            if (b.out_gapped || b.out_slot1 || b.out_slot2) {
+                for (int pe = start; pe < pi; ++pe) {
+                    if (!(s_flags[pe] & 2u)) continue;
+                    const uint32_t k = base + pe;
+                    const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                    const bool fl = s_flags[pe] & 1u;
+                    const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
+                    const int B = aff_choose_b(ag.wq_need);
+                    const uint32_t *ops = arena + s_off[pe] + aff_dir_words(ag, B);
+                    const uint64_t oo = b.out_off[k];
+                    aff_emit(tcm, b.elems + (fl ? b.off1[k] : b.off2[k]), b.elems + (fl ? b.off2[k] : b.off1[k]), ops,
+                             s_nal[pe], fl, b.out_gapped ? b.out_gapped + oo : nullptr,
+                             b.out_slot1 ? b.out_slot1 + oo : nullptr, b.out_slot2 ? b.out_slot2 + oo : nullptr, lane);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+uint32_t aff_words_for(uint32_t n1, uint32_t n2)
+{
+    const AffGeom g = make_aff_geom((int)(n1 < n2 ? n1 : n2), (int)(n1 < n2 ? n2 : n1));
+    const int B = aff_choose_b(g.wq_need);
+    return B ? aff_need_words(g, B) : 0u;
+}
+
+cudaError_t launch_affine(const AffParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(do_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    do_affine_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace pcgdo

@@ -20,6 +20,21 @@ cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_
                            uint32_t *scratch, cudaStream_t stream);
 }
 namespace pcgdo {
+struct AffParams {
+    TcmDev    tcm;
+    BatchDev  b;
+    const uint16_t *aff_sub;
+    uint32_t  gap_open;
+    uint32_t *arena;
+    uint32_t  arena_words;
+    int       pairs_per_warp;
+    unsigned int *counter;
+    unsigned int *overflow_count;
+};
+uint32_t aff_words_for(uint32_t n1, uint32_t n2);
+cudaError_t launch_affine(const AffParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+}
+namespace pcgdo {
 double launch_int_peak(int mode, int grid, int iters, uint32_t *scratch, cudaStream_t st);
 }
 using namespace pcgdo;
@@ -123,7 +138,7 @@ extern "C" int pcgdo_configure_ex(pcgdo_ctx *ctx, int max_b, size_t arena_words)
 // --------------------------------------------------------------------------------------------- TCM
 
 static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, const unsigned int *cost,
-                           const unsigned int *median, pcgdo_tcm **out)
+                           const unsigned int *median, pcgdo_tcm **out, int affine_variant = 0)
 {
     if (a < 2 || a > 8) {
         ctx->err = "alphabet size must be 2..8 for the dense-table path";
@@ -176,6 +191,25 @@ static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, cons
     CK(up(&t->d_median, med.data(), med.size()));
     CK(up(&t->d_cgap, cgap.data(), cgap.size() * 4));
     CK(up(&t->d_gapc, gapc.data(), gapc.size() * 4));
+    if (gap_open) {
+        // substitution costs between gap-stripped elements x' = x & (gap-1) (alignCharacters.c:3636, 2770).
+        // variant 0: as compiled for x86-64 — the shift count costMatrixDimension = 2^a is taken mod 32, the
+        // lookup reads cost_flat[(x' << (2^a & 31)) + y']; variant 1: the patched `<< alphSize`, cost[x'][y'].
+        const size_t h = dim / 2;
+        std::vector<uint16_t> as(h * h, 0);
+        for (size_t x = 0; x < h; ++x)
+            for (size_t y = 0; y < h; ++y) {
+                const size_t idx = affine_variant ? ((x << a) + y) : ((x << (dim & 31)) + y);
+                const unsigned long long v = idx < dim * dim ? cost[idx] : 0ull;
+                if (v > 60000ull) {
+                    ctx->err = "TCM costs too large for the 16-bit affine table";
+                    return PCGDO_ERR_UNSUPPORTED;
+                }
+                as[x * h + y] = (uint16_t)v;
+            }
+        CK(up(&t->d_aff_sub, as.data(), as.size() * 2));
+        t->affine_variant = affine_variant;
+    }
     t->dev.a = (int)a;
     t->dev.repl = repl ? 1 : 0;
     t->dev.gap = gap;
@@ -204,11 +238,31 @@ extern "C" int pcgdo_tcm_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_
     return tcm_from_tables(ctx, a, gap_open, cost.data(), median.data(), out);
 }
 
+// Affine TCM: gap_open > 0; variant 0 = the reference as compiled for x86-64, 1 = with its shift patched.
+extern "C" int pcgdo_tcm_create_affine(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, unsigned int gap_open,
+                                       int variant, pcgdo_tcm **out)
+{
+    if (!ctx || !sigma || !out || gap_open == 0) return PCGDO_ERR_ARG;
+    if (a < 2 || a > 8) {
+        ctx->err = "alphabet size must be 2..8 for the dense-table path";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    if (variant == 0 && a < 5) {
+        ctx->err = "as-coded affine lookup reads out of bounds for alphabets < 5 (shift by 2^a); use variant 1";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    const size_t dim = (size_t)1 << a;
+    std::vector<unsigned int> cost(dim * dim, 0), median(dim * dim, 0);
+    build_dense_tables(sigma, a, cost.data(), median.data());
+    return tcm_from_tables(ctx, a, gap_open, cost.data(), median.data(), out, variant);
+}
+
 extern "C" void pcgdo_tcm_destroy(pcgdo_ctx *ctx, pcgdo_tcm *t)
 {
     if (!t) return;
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(t->d_sub4);
+    cudaFree(t->d_aff_sub);
     cudaFree(t->d_sub4_nat);
     cudaFree(t->d_median);
     cudaFree(t->d_cgap);
@@ -380,6 +434,84 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     return PCGDO_OK;
 }
 
+// --------------------------------------------------------------------------------------------- affine
+
+extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b,
+                                                 void *cuda_stream)
+{
+    if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    if (!tcm->d_aff_sub) {
+        ctx->err = "not an affine TCM (create it with pcgdo_tcm_create_affine)";
+        return PCGDO_ERR_ARG;
+    }
+    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost) {
+        ctx->err = "bad batch description";
+        return PCGDO_ERR_ARG;
+    }
+    if ((b->out_gapped || b->out_slot1 || b->out_slot2) && !b->out_off) {
+        ctx->err = "out_off required when aligned strings are requested";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const size_t hdim = (size_t)1 << (tcm->a - 1);
+    const int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    const size_t smem = hdim * hdim * 2 + (size_t)warps * 96 * 4;
+    if (smem > 227 * 1024) {
+        ctx->err = "alphabet too large for the affine kernel's shared-memory table";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    size_t arena_words = ctx->arena_words;
+    if (!arena_words) {
+        const size_t per = aff_words_for((uint32_t)ctx->max_len, (uint32_t)(ctx->max_len - ctx->max_len / 20));
+        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 1024);
+    }
+    arena_words = (arena_words + 3) & ~(size_t)3;
+    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
+    const int grid = ctx->sm_count;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    AffParams p{};
+    p.tcm = tcm->dev;
+    p.b.n_pairs = (uint32_t)b->n_pairs;
+    p.b.elems = b->elems;
+    p.b.off1 = b->off1; p.b.off2 = b->off2;
+    p.b.len1 = b->len1; p.b.len2 = b->len2;
+    p.b.out_off = b->out_off;
+    p.b.out_gapped = b->out_gapped; p.b.out_slot1 = b->out_slot1; p.b.out_slot2 = b->out_slot2;
+    p.b.out_len = b->out_len;
+    p.b.cost = b->cost;
+    p.b.cells = b->cells;
+    p.aff_sub = (const uint16_t *)tcm->d_aff_sub;
+    p.gap_open = tcm->gap_open;
+    p.arena = (uint32_t *)ctx->arena.p;
+    p.arena_words = (uint32_t)arena_words;
+    p.pairs_per_warp = ctx->pairs_per_warp;
+    p.counter = (unsigned int *)ctx->counters.p;
+    p.overflow_count = p.counter + 8;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_affine(p, grid, warps * 32, smem, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    ctx->last_launches = 1;
+    unsigned int h_over = 0;
+    CK(cudaMemcpyAsync(&h_over, p.overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_over) {
+        char msg[200];
+        snprintf(msg, sizeof msg, "%u affine pair(s) exceed the kernel's limits (band wider than 1024 diagonals or "
+                                  "scratch larger than the arena: raise max_len / arena_words)", h_over);
+        ctx->err = msg;
+        return PCGDO_ERR_OVERFLOW;
+    }
+    return PCGDO_OK;
+}
+
 extern "C" int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches)
 {
     if (!ctx) return PCGDO_ERR_ARG;
@@ -420,7 +552,20 @@ extern "C" int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, flo
     return PCGDO_OK;
 }
 
+static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, bool affine);
+
 extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b)
+{
+    return batch_host_impl(ctx, tcm, b, false);
+}
+
+// align2dAffine semantics per pair (see do_affine.cu); host buffers in, host buffers out.
+extern "C" int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b)
+{
+    return batch_host_impl(ctx, tcm, b, true);
+}
+
+static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, bool affine)
 {
     if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
     if (b->n_pairs == 0) return PCGDO_OK;
@@ -468,7 +613,7 @@ extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, co
     // (three streams, PCIe is full duplex).  Needs monotone layouts, which the packers produce; anything
     // else, and any pair that overflows the warp kernels, takes the plain path below.
     const size_t chunk = ctx->host_chunk_pairs ? ctx->host_chunk_pairs : 65536;
-    bool pipelined = n > chunk && ctx->max_b > 8;      // (wide kernel on: no per-chunk queue left behind)
+    bool pipelined = !affine && n > chunk && ctx->max_b > 8;      // (wide kernel on: no per-chunk queue left behind)
     std::vector<size_t> e_lo, e_hi, o_lo, o_hi;
     if (pipelined) {
         size_t prev_e = 0, prev_o = 0;
@@ -553,7 +698,7 @@ extern "C" int pcgdo_align2d_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, co
         CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));
     }
 
-    rc = pcgdo_align2d_batch_device(ctx, tcm, &d, st);
+    rc = affine ? pcgdo_align2d_affine_batch_device(ctx, tcm, &d, st) : pcgdo_align2d_batch_device(ctx, tcm, &d, st);
     if (rc) return rc;
 
     CK(cudaMemcpyAsync(b->cost, d.cost, n * 4, cudaMemcpyDeviceToHost, st));

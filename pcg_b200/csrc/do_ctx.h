@@ -10,6 +10,8 @@ struct pcgdo_tcm {
     pcgdo::TcmDev dev{};
     size_t a = 0;
     unsigned int gap_open = 0;
+    void *d_aff_sub = nullptr;       // affine only: u16 [s' << (a-1) | l']
+    int affine_variant = 0;
     void *d_sub4 = nullptr, *d_sub4_nat = nullptr, *d_median = nullptr, *d_cgap = nullptr, *d_gapc = nullptr;
 };
 

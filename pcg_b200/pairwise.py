@@ -102,7 +102,10 @@ def align2d_batch(ctx: Context, tcm: Tcm, pp: PackedPairs, want_strings: bool = 
     cells = np.zeros(n, np.uint64) if want_cells else None
     b = Batch(n, _p(pp.elems), pp.elems.nbytes, _p(pp.off1), _p(pp.off2), _p(pp.len1), _p(pp.len2),
               _p(pp.out_off), pp.out_bytes, _p(g), _p(s1), _p(s2), _p(out_len), _p(cost), _p(cells))
-    ctx.check(ctx.lib.pcgdo_align2d_batch_host(ctx.h, tcm.h, C.byref(b)), "pcgdo_align2d_batch_host")
+    if getattr(tcm, "gap_open", 0):       # getAlignmentStrategy (FFI.hsc:287-290): affine iff cost_model_type says so
+        ctx.check(ctx.lib.pcgdo_align2d_affine_batch_host(ctx.h, tcm.h, C.byref(b)), "pcgdo_align2d_affine_batch_host")
+    else:
+        ctx.check(ctx.lib.pcgdo_align2d_batch_host(ctx.h, tcm.h, C.byref(b)), "pcgdo_align2d_batch_host")
     return BatchResult(cost, out_len, g, s1, s2, cells)
 
 

@@ -91,3 +91,22 @@ def test_device_formulation_model_matches_oracle(oracle_mod, name):
         assert oc[0] == mc[0]
         for x, y in zip(oc[1:4], mc[1:4]):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("variant,patched", [(0, False), (1, True)])
+@pytest.mark.parametrize("name,go", [("discrete", 1), ("l1", 3), ("weird", 2)])
+def test_affine_oracle_matches_compiled_reference(oracle_mod, variant, patched, name, go):
+    """C-affine restatement vs the compiled reference: as coded (variant 0) and with the undefined shift at
+    alignCharacters.c:3636 patched to `<< alphSize` (variant 1, built by oracle/Makefile through sed)."""
+    import os
+    if not oracle_mod.Reference.available() or (patched and not os.path.exists(oracle_mod.REF_PATCHED_SO)):
+        pytest.skip("oracle/_ref not built")
+    sig = tcm_matrix(name)
+    o, r = oracle_mod.Oracle(sig, go), oracle_mod.Reference(sig, go, patched=patched)
+    rng = np.random.default_rng(40 + go)
+    for _ in range(120):
+        s1, s2 = random_pair(rng, 250, amb=0.2)
+        rc, oc = r.align2d(s1, s2, affine=True), o.align2d_affine(s1, s2, variant)
+        assert rc[0] == oc[0]
+        for x, y in zip(rc[1:], oc[1:4]):
+            assert np.array_equal(x, y)
