@@ -243,6 +243,123 @@ def run_postorder(args, rank, world, local_rank, ctx, torch, dist, full=True):
     forest.close()
     return out
 
+
+# ------------------------------------------------------------------------------------------------
+# Config 3 (BASELINE.json configs[2]): affine-gap DO on 100 000 pairs of ~5 kb strings with IUPAC ambiguity
+# codes (lengths U[4750, 5250], 10 % of the elements a uniform non-empty subset of {A,C,G,T}), discrete TCM,
+# gap-open 3, C-affine dialect.  The reference's affine substitution lookup is undefined behaviour
+# (alignCharacters.c:3636); the bench runs the PATCHED reading (`<< alphSize`) on both arms — the CPU arm is
+# oracle/_ref/libpcgdo_ref_patched.so, the same sources with that one expression corrected.
+# ------------------------------------------------------------------------------------------------
+def config3_pairs(n_pairs, rank=0):
+    from pcg_b200.pairwise import PackedPairs
+    rng = np.random.Generator(np.random.PCG64(20260102 + rank))
+    lens = rng.integers(4750, 5251, size=2 * n_pairs).astype(np.uint32)
+    total = int(lens.astype(np.int64).sum())
+    base = np.left_shift(np.uint8(1), rng.integers(0, 4, size=total, dtype=np.uint8))
+    amb = rng.integers(0, 10, size=total, dtype=np.uint8) == 0
+    vals = rng.integers(1, 16, size=total, dtype=np.uint8)
+    elems = np.where(amb, vals, base).astype(np.uint8)
+    del base, amb, vals
+    starts = np.concatenate([[0], np.cumsum(lens.astype(np.uint64))]).astype(np.uint64)
+    off1, off2 = starts[0:-1:2].copy(), starts[1:-1:2].copy()
+    len1, len2 = lens[0::2].copy(), lens[1::2].copy()
+    cap = (len1.astype(np.int64) + len2.astype(np.int64) + 3) & ~3
+    ostarts = np.concatenate([[0], np.cumsum(cap)]).astype(np.uint64)
+    elems = np.concatenate([elems, np.zeros(16, np.uint8)])
+    return PackedPairs(n_pairs, elems, off1, off2, len1, len2, ostarts[:-1].copy(), int(ostarts[-1]) + 16)
+
+
+def run_config3(args, rank, world, local_rank, ctx, torch, dist):
+    import ctypes as C
+    from pcg_b200.backend import Batch
+    n = args.pairs if args.pairs != (1 << 20) else 100000
+    GO, VARIANT = 3, 1
+    pp = config3_pairs(n, rank)
+    ctx.configure(pairs_per_warp=min(args.ppw, 8), warps_per_cta=16, max_len=5250, max_b=32)
+    tcm = ctx.tcm(discrete_tcm(), gap_open=GO, affine_variant=VARIANT)
+    dev = torch.device("cuda", local_rank)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    d_elems = t(pp.elems)
+    d_off1, d_off2 = t(pp.off1.view(np.int64)), t(pp.off2.view(np.int64))
+    d_len1, d_len2 = t(pp.len1.view(np.int32)), t(pp.len2.view(np.int32))
+    d_out_off = t(pp.out_off.view(np.int64))
+    d_g = torch.empty(pp.out_bytes, dtype=torch.uint8, device=dev)
+    d_s1, d_s2 = torch.empty_like(d_g), torch.empty_like(d_g)
+    d_olen = torch.empty(n, dtype=torch.int32, device=dev)
+    d_cost = torch.empty(n, dtype=torch.int32, device=dev)
+    d_cells = torch.empty(n, dtype=torch.int64, device=dev)
+    b = Batch(n, d_elems.data_ptr(), pp.elems.nbytes, d_off1.data_ptr(), d_off2.data_ptr(), d_len1.data_ptr(),
+              d_len2.data_ptr(), d_out_off.data_ptr(), pp.out_bytes, d_g.data_ptr(), d_s1.data_ptr(),
+              d_s2.data_ptr(), d_olen.data_ptr(), d_cost.data_ptr(), d_cells.data_ptr())
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ctx.check(ctx.lib.pcgdo_align2d_affine_batch_device(ctx.h, tcm.h, C.byref(b), C.c_void_p(stream.cuda_stream)),
+                  "pcgdo_align2d_affine_batch_device")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    total_cells = float(d_cells.sum().item())
+    checksum = int(d_cost.to(torch.int64).sum().item())
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        kms.append(ctx.last_kernel_ms()[0])
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms, total_cells], device=dev, dtype=torch.float64)
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, total_cells = float(mx[0].item()), float(sm[1].item())
+    value = total_cells / (ms * 1e-3) / 1e9
+    if rank != 0:
+        return None
+    k_ms = float(np.mean(kms))
+    int_peak = max(ctx.int32_peak(0), ctx.int32_peak(1)) / 1e12
+    ach = total_cells / max(world, 1) * 24 / (k_ms * 1e-3) / 1e12      # 24 integer ops per affine cell
+    cpu = None
+    if not args.no_cpu and world == 1:
+        from oracle import pyoracle as po
+        import types
+        threads = host_threads()
+        ns = max(threads, min(n, 4 * threads))
+        sub = types.SimpleNamespace(n=ns, elems=pp.elems, off1=pp.off1[:ns].copy(), off2=pp.off2[:ns].copy(),
+                                    len1=pp.len1[:ns].copy(), len2=pp.len2[:ns].copy())
+        kind = "reference" if os.path.exists(po.REF_PATCHED_SO) else "port"
+        sec, cost, _ = po.cpu_bench_align2d(discrete_tcm(), sub, threads, kind, want_cells=False, gap_open=GO,
+                                            affine_variant=VARIANT)
+        cells_s = float(d_cells[:ns].sum().item())
+        assert np.array_equal(cost, d_cost[:ns].cpu().numpy()), "device costs differ from the CPU arm on the sample"
+        cpu = {"value": cells_s / sec / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
+               "sample": f"first {ns} pairs, {sec:.1f} s on {threads} host threads "
+                         f"(align2dAffine of the one-expression-patched reference build); costs equal to the device's"}
+    return {"metric": "2D DO alignment GCUPS (affine)", "value": value, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "config3: affine-gap DO, ~5 kb IUPAC-ambiguous DNA pairs, discrete TCM, gap-open 3, "
+                                   "C-affine dialect (patched substitution lookup)",
+                       "pairs_per_gpu": n, "len": "U[4750,5250]", "cells_per_pair_avg": total_cells / world / n,
+                       "l2": "inputs (1 GB) and direction scratch exceed the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "roofline": {"bound": "int32-issue", "achieved": ach, "peak": int_peak, "unit": "Tinstr/s",
+                         "frac": ach / int_peak if int_peak else None, "alg_ops_per_cell": 24, "kernel_ms": k_ms,
+                         "traffic": None},
+            "cpu_baseline": cpu, "cost_checksum": checksum}
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -279,7 +396,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
     ap.add_argument("--warps", type=int, default=32, help="warps per CTA of the narrow kernel")
     ap.add_argument("--ppw", type=int, default=8, help="pairs a warp fills before tracing them")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config5"])
     ap.add_argument("--no-postorder", action="store_true", help="skip the config-5 post-order section")
     ap.add_argument("--po-trees", type=int, default=0, help="override the number of candidate trees")
     ap.add_argument("--po-steps", type=int, default=2)
@@ -309,6 +426,13 @@ def main():
 
     n = args.pairs
     ctx = P.Context(local_rank)
+    if args.workload == "config3":
+        line = run_config3(args, rank, world, local_rank, ctx, torch, dist)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "config5":
         po = run_postorder(args, rank, world, local_rank, ctx, torch, dist)
         if rank == 0:

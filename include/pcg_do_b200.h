@@ -73,6 +73,13 @@ int align2d(alignIO_t *inputChar1_aio, alignIO_t *inputChar2_aio,
             alignIO_t *gappedOutput_aio, alignIO_t *ungappedOutput_aio,
             cost_matrices_2d_t *costMtx2d, int getUngapped, int getGapped, int getUnion);
 
+/* Affine twin of align2d (EXT/c_alignment_interface.h:45-52).  inputChar1/2 come back holding their own strings
+ * with gaps as gap_char, gappedOutput the full-length median; ungappedOutput is returned empty (PCG's binding
+ * never reads it).  See pcgdo_tcm_create_affine below for the `variant` question (env PCGDO_AFFINE_VARIANT). */
+int align2dAffine(alignIO_t *inputChar1_aio, alignIO_t *inputChar2_aio,
+                  alignIO_t *gappedOutput_aio, alignIO_t *ungappedOutput_aio,
+                  cost_matrices_2d_t *costMtx2d_affine, int getMedians);
+
 /* ---------------------------------------------------------------- batched API */
 
 typedef struct pcgdo_ctx pcgdo_ctx;     /* one per (process, GPU): streams, scratch, work counters */

@@ -19,6 +19,7 @@
 
 typedef struct { unsigned int *character; size_t length; size_t capacity; } aio_t;
 typedef int (*align2d_fn)(aio_t *, aio_t *, aio_t *, aio_t *, void *, int, int, int);
+typedef int (*align2daff_fn)(aio_t *, aio_t *, aio_t *, aio_t *, void *, int);
 typedef void (*setup_fn)(void *, unsigned int *, size_t, unsigned int);
 
 typedef struct {
@@ -32,6 +33,8 @@ typedef struct {
     align2d_fn ref_align;
     void *ref_cm;
     const oracle_tcm_t *port;
+    align2daff_fn ref_affine;      /* non-NULL: affine dialect through the reference */
+    int affine_variant;            /* port, affine: 0 as coded, 1 patched; -1 = linear */
 } job_t;
 
 static void fill_aio(aio_t *io, const uint8_t *src, size_t n, size_t cap)
@@ -55,9 +58,10 @@ static void *worker(void *arg)
             fill_aio(&b, s2, n2, cap);
             fill_aio(&g, NULL, 0, cap);
             fill_aio(&u, NULL, 0, cap);
-            j->cost[k] = j->ref_align(&a, &b, &g, &u, j->ref_cm, 0, 1, 0);
+            j->cost[k] = j->ref_affine ? j->ref_affine(&a, &b, &g, &u, j->ref_cm, 1)
+                                       : j->ref_align(&a, &b, &g, &u, j->ref_cm, 0, 1, 0);
             free(a.character); free(b.character); free(g.character); free(u.character);
-            if (j->cells) {
+            if (j->cells && !j->ref_affine) {
                 size_t lg = (n1 > n2 ? n1 : n2) + 1, sh = (n1 > n2 ? n2 : n1) + 1;
                 j->cells[k] = oracle_band_rows(lg, sh, NULL, NULL, NULL, NULL);
             }
@@ -68,7 +72,10 @@ static void *worker(void *arg)
             for (size_t i = 0; i < n2; i++) x2[i] = s2[i];
             size_t nal = 0;
             uint64_t c = 0;
-            j->cost[k] = (int32_t)oracle_align2d(j->port, x1, n1, x2, n2, og, o1, o2, &nal, &c);
+            if (j->affine_variant >= 0)
+                j->cost[k] = (int32_t)oracle_align2d_affine(j->port, j->affine_variant, x1, n1, x2, n2, og, o1, o2, &nal, &c);
+            else
+                j->cost[k] = (int32_t)oracle_align2d(j->port, x1, n1, x2, n2, og, o1, o2, &nal, &c);
             if (j->cells) j->cells[k] = c;
             free(buf);
         }
@@ -77,35 +84,52 @@ static void *worker(void *arg)
 }
 
 /* Returns 0 on success; *seconds = wall time of the alignment loop only (input already in memory). */
+int cpu_bench_align2d_ex(const char *ref_so, const uint32_t *sigma, int a, uint32_t gap_open, int affine_variant,
+                         const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
+                         const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                         int32_t *cost, uint64_t *cells, double *seconds);
+
 int cpu_bench_align2d(const char *ref_so, const uint32_t *sigma, int a,
                       const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
                       const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
                       int32_t *cost, uint64_t *cells, double *seconds)
 {
+    return cpu_bench_align2d_ex(ref_so, sigma, a, 0, -1, elems, off1, len1, off2, len2, n, threads, cost, cells, seconds);
+}
+
+/* gap_open > 0: the affine dialect (reference align2dAffine, or the port with affine_variant 0 / 1). */
+int cpu_bench_align2d_ex(const char *ref_so, const uint32_t *sigma, int a, uint32_t gap_open, int affine_variant,
+                         const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
+                         const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                         int32_t *cost, uint64_t *cells, double *seconds)
+{
     align2d_fn ref_align = NULL;
+    align2daff_fn ref_affine = NULL;
     void *cm = NULL;
     oracle_tcm_t *port = NULL;
     if (ref_so) {
         void *h = dlopen(ref_so, RTLD_NOW | RTLD_LOCAL);
         if (!h) return 1;
         ref_align = (align2d_fn)dlsym(h, "align2d");
+        if (gap_open) ref_affine = (align2daff_fn)dlsym(h, "align2dAffine");
         setup_fn setup = (setup_fn)dlsym(h, "setUp2dCostMtx");
-        if (!ref_align || !setup) return 2;
+        if (!ref_align || !setup || (gap_open && !ref_affine)) return 2;
         cm = calloc(1, 256);
         uint32_t *sg = malloc(sizeof(uint32_t) * a * a);
         memcpy(sg, sigma, sizeof(uint32_t) * a * a);
-        setup(cm, sg, (size_t)a, 0);
+        setup(cm, sg, (size_t)a, gap_open);
         free(sg);
     } else {
-        port = oracle_tcm_new(sigma, a, 0);
+        port = oracle_tcm_new(sigma, a, gap_open);
     }
+    if (!gap_open) affine_variant = -1;
     if (threads < 1) threads = 1;
     pthread_t *th = malloc(sizeof(pthread_t) * threads);
     job_t *jobs = malloc(sizeof(job_t) * threads);
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
-        jobs[t] = (job_t){ t, threads, n, elems, off1, off2, len1, len2, cost, cells, ref_align, cm, port };
+        jobs[t] = (job_t){ t, threads, n, elems, off1, off2, len1, len2, cost, cells, ref_align, cm, port, ref_affine, affine_variant };
         pthread_create(&th[t], NULL, worker, &jobs[t]);
     }
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);

@@ -216,27 +216,30 @@ class Reference:
         return int(cost), gg, s1, s2
 
 
-def cpu_bench_align2d(sigma, pp, threads: int, kind: str = "reference", want_cells: bool = True):
+def cpu_bench_align2d(sigma, pp, threads: int, kind: str = "reference", want_cells: bool = True,
+                      gap_open: int = 0, affine_variant: int = 0):
     """Time the CPU path on `threads` host threads over the packed pairs `pp` (a pcg_b200 PackedPairs-like
     object: elems/off1/len1/off2/len2/n).  kind: "reference" (oracle/_ref) or "port" (do_oracle.c).
     Returns (seconds, cost[int32], cells[uint64])."""
     if not os.path.exists(ORACLE_SO):
         build(ref=False)
     lib = C.CDLL(ORACLE_SO)
-    lib.cpu_bench_align2d.restype = C.c_int
-    lib.cpu_bench_align2d.argtypes = [C.c_char_p, _u32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
-                                      C.POINTER(C.c_double)]
+    lib.cpu_bench_align2d_ex.restype = C.c_int
+    lib.cpu_bench_align2d_ex.argtypes = [C.c_char_p, _u32p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.POINTER(C.c_double)]
     sigma = _as_u32(sigma)
     cost = np.zeros(pp.n, np.int32)
     cells = np.zeros(pp.n, np.uint64)
     sec = C.c_double(0)
-    so = REF_SO.encode() if kind == "reference" else None
-    if kind == "reference" and not os.path.exists(REF_SO):
-        raise FileNotFoundError(REF_SO)
-    rc = lib.cpu_bench_align2d(so, _ptr(sigma), int(sigma.shape[0]), pp.elems.ctypes.data, pp.off1.ctypes.data,
-                               pp.len1.ctypes.data, pp.off2.ctypes.data, pp.len2.ctypes.data, pp.n, threads,
-                               cost.ctypes.data, cells.ctypes.data if want_cells else None, C.byref(sec))
+    ref_path = REF_PATCHED_SO if (gap_open and affine_variant == 1) else REF_SO
+    so = ref_path.encode() if kind == "reference" else None
+    if kind == "reference" and not os.path.exists(ref_path):
+        raise FileNotFoundError(ref_path)
+    rc = lib.cpu_bench_align2d_ex(so, _ptr(sigma), int(sigma.shape[0]), gap_open, affine_variant, pp.elems.ctypes.data,
+                                  pp.off1.ctypes.data, pp.len1.ctypes.data, pp.off2.ctypes.data, pp.len2.ctypes.data,
+                                  pp.n, threads, cost.ctypes.data, cells.ctypes.data if want_cells else None,
+                                  C.byref(sec))
     if rc:
         raise RuntimeError(f"cpu_bench_align2d failed: {rc}")
     return float(sec.value), cost, cells

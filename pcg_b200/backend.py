@@ -19,7 +19,7 @@ _i32p = C.POINTER(C.c_int32)
 
 # every symbol include/pcg_do_b200.h declares
 EXPORTED_SYMBOLS = [
-    "setUp2dCostMtx", "align2d",
+    "setUp2dCostMtx", "align2d", "align2dAffine",
     "pcgdo_create", "pcgdo_destroy", "pcgdo_last_error", "pcgdo_configure",
     "pcgdo_tcm_create", "pcgdo_tcm_destroy",
     "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
@@ -105,6 +105,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.setUp2dCostMtx.restype = None
     L.align2d.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int, C.c_int, C.c_int]
     L.align2d.restype = C.c_int
+    L.align2dAffine.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int]
+    L.align2dAffine.restype = C.c_int
     _lib = L
     return L
 

@@ -777,3 +777,57 @@ extern "C" int align2d(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignI
     }
     return cost;
 }
+
+// Reference-compatible affine entry point (EXT/c_alignment_interface.h:45-52; bound at DO/Pairwise/FFI.hsc:135-143).
+// On return inputChar1/2 hold their own strings with gaps as gap_char, gappedOutput the full-length median
+// (what the reference leaves there), ungappedOutput is left empty (the Haskell side never reads it, FFI.hsc:328-330).
+// The environment variable PCGDO_AFFINE_VARIANT=1 selects the patched substitution lookup (see header).
+extern "C" int align2dAffine(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignIO_t *ungapped,
+                             cost_matrices_2d_t *cm, int getMedians)
+{
+    if (cm->cost_model_type == 0 || cm->gap_open_cost == 0) die("align2dAffine", "linear cost matrix passed to the affine entry point");
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx && pcgdo_create(&g_ctx, 0) != PCGDO_OK) die("align2dAffine", "cannot create a GPU context");
+    pcgdo_ctx *ctx = g_ctx;
+    const char *ev = getenv("PCGDO_AFFINE_VARIANT");
+    const int variant = (ev && ev[0] == '1') ? 1 : 0;
+    pcgdo_tcm *&t = g_tcms[(const char *)cm->cost + 1 + variant];      // distinct keys from the linear cache
+    if (!t && tcm_from_tables(ctx, cm->alphSize, cm->gap_open_cost, cm->cost, cm->median, &t, variant) != PCGDO_OK)
+        die("align2dAffine", ctx->err.c_str());
+    const size_t n1 = in1->length, n2 = in2->length;
+    const size_t cap = (n1 + n2 + 3) & ~(size_t)3;
+    std::vector<uint8_t> elems(n1 + n2 + 1), og(cap + 4), o1(cap + 4), o2(cap + 4);
+    const elem_t *s1 = in1->character + (in1->capacity - n1), *s2 = in2->character + (in2->capacity - n2);
+    for (size_t i = 0; i < n1; ++i) elems[i] = (uint8_t)s1[i];
+    for (size_t i = 0; i < n2; ++i) elems[n1 + i] = (uint8_t)s2[i];
+    uint64_t off1 = 0, off2 = n1, out_off = 0;
+    uint32_t len1 = (uint32_t)n1, len2 = (uint32_t)n2, out_len = 0;
+    int32_t cost = 0;
+    pcgdo_batch b{};
+    b.n_pairs = 1;
+    b.elems = elems.data(); b.elems_bytes = elems.size();
+    b.off1 = &off1; b.off2 = &off2; b.len1 = &len1; b.len2 = &len2;
+    b.out_off = &out_off; b.out_bytes = cap;
+    b.cost = &cost;
+    if (getMedians) { b.out_gapped = og.data(); b.out_slot1 = o1.data(); b.out_slot2 = o2.data(); b.out_len = &out_len; }
+    const int saved_len = ctx->max_len;
+    const size_t need_len = n1 > n2 ? n1 : n2;
+    if ((int)need_len > ctx->max_len) ctx->max_len = (int)need_len;
+    const int rc = pcgdo_align2d_affine_batch_host(ctx, t, &b);
+    ctx->max_len = saved_len;
+    if (rc != PCGDO_OK) die("align2dAffine", ctx->err.c_str());
+    if (getMedians) {
+        auto put = [&](alignIO_t *io, const std::vector<uint8_t> &v, uint32_t n) {
+            io->character = (elem_t *)realloc(io->character, io->capacity * sizeof(elem_t));
+            if (!io->character || n > io->capacity) die("align2dAffine", "output buffer too small");
+            io->length = n;
+            elem_t *dst = io->character + (io->capacity - n);
+            for (uint32_t k = 0; k < n; ++k) dst[k] = v[k];
+        };
+        put(gapped, og, out_len);
+        put(in1, o1, out_len);
+        put(in2, o2, out_len);
+        if (ungapped) ungapped->length = 0;
+    }
+    return cost;
+}

@@ -56,3 +56,44 @@ def test_affine_oracle_matches_reference_builds(oracle_mod):
             assert rc[0] == oc[0]
             for x, y in zip(rc[1:], oc[1:4]):
                 assert np.array_equal(x, y)
+
+
+def test_reference_compatible_align2dAffine_symbol(oracle_mod, gpu_ctx):
+    """`align2dAffine` called the way FFI.hsc does, against the compiled reference's own answer (as coded)."""
+    import ctypes as C
+    import pcg_b200.backend as be
+    lib = be.load()
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    sig = tcm_matrix("l1")
+    o = oracle_mod.Oracle(sig, 3)
+    cm = be.CostMatrices2D()
+    lib.setUp2dCostMtx(C.byref(cm), sig.ctypes.data_as(C.POINTER(C.c_uint32)), 5, 3)
+    assert cm.cost_model_type == 3 and cm.gap_open_cost == 3
+
+    def aio(vals, cap):
+        buf = libc.malloc(cap * 4)
+        C.memset(buf, 0, cap * 4)
+        arr = (C.c_uint32 * cap).from_address(buf)
+        for i, v in enumerate(vals):
+            arr[cap - len(vals) + i] = int(v)
+        return be.AlignIO(C.cast(buf, C.POINTER(C.c_uint32)), len(vals), cap)
+
+    def take(io):
+        off = io.capacity - io.length
+        out = [io.character[off + i] for i in range(io.length)]
+        libc.free(C.cast(io.character, C.c_void_p))
+        return out
+
+    rng = np.random.default_rng(77)
+    for _ in range(5):
+        s1, s2 = random_pair(rng, 150, amb=0.2)
+        cap = len(s1) + len(s2) + 2
+        a1, a2, g, u = aio(s1, cap), aio(s2, cap), aio([], cap), aio([], cap)
+        cost = lib.align2dAffine(C.byref(a1), C.byref(a2), C.byref(g), C.byref(u), C.byref(cm), 1)
+        oc = o.align2d_affine(s1, s2, 0)
+        assert cost == oc[0]
+        assert take(g) == oc[1].tolist() and take(a1) == oc[2].tolist() and take(a2) == oc[3].tolist()
+        libc.free(C.cast(u.character, C.c_void_p))
