@@ -149,6 +149,34 @@ int pcgdo_tcm_create_affine(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a,
 int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, void *cuda_stream);
 int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b);
 
+/* ---------------------------------------------------------------- large alphabets (a > 8): Haskell dialects
+ * The reference dispatches alphabets of more than 8 symbols to its Haskell aligners over an overlap function
+ * (DO/Internal.hs:67-83).  Elements are 32-bit ambiguity sets here (a <= 24 on this path); the overlap is the
+ * DISCRETE METRIC's closed form (Data/MetricRepresentation.hs:116-128), computed per cell on the device.
+ *   dialect 0 = S1 full matrix   : naiveDO / naiveDOMemo / unboxedSwappingDO
+ *   dialect 1 = S1 Ukkonen ribbon: ukkonenDO
+ *   dialect 2 = S2 Ukkonen band  : unboxedUkkonenFullSpaceDO  (PCG's production path for a > 8)
+ * Inputs are median strings (what `measureAndUngapCharacters` leaves); outputs per pair: median, aligned first
+ * input, aligned second input (0 = gap), at element offset out_off[k] (room for len1+len2 elements).
+ * Upstream has neither golden vectors nor (here) an executable for these paths: parity is against the restatement
+ * in oracle/do_oracle.c only.  Explicit (non-discrete) matrices and the L1 metric for a > 8 are not built yet. */
+typedef struct pcgdo_batch32 {
+    size_t          n_pairs;
+    const uint32_t *elems;
+    size_t          elems_count;     /* host variant: elements to copy in              */
+    const uint64_t *off1, *off2;     /* element offsets                                */
+    const uint32_t *len1, *len2;
+    const uint64_t *out_off;
+    size_t          out_count;       /* host variant: elements to copy back per array  */
+    uint32_t       *out_med, *out_a1, *out_a2;
+    uint32_t       *out_len;
+    int32_t        *cost;
+    uint64_t       *cells;           /* may be NULL: cells of the final band           */
+    int32_t        *final_offset;    /* may be NULL: Ukkonen offset reached (-1 = full matrix) */
+} pcgdo_batch32;
+int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b, void *cuda_stream);
+int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b);
+
 /* Finer tunables: widest diagonals-per-lane variant the warp kernels must accommodate (2,4,8,16,32; pairs
  * needing more go to the general-geometry kernel) and the per-warp scratch arena in 32-bit words (0 = derive
  * from max_len). */

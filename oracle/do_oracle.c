@@ -494,3 +494,164 @@ int64_t oracle_align2d_affine(const oracle_tcm_t *t, int variant,
     free(rm); free(rs); free(rl); free(dir); free(buf); free(lng); free(shr);
     return cost;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Haskell dialects S1 / S2 over an arbitrary overlap function (alphabets up to 32 symbols here).
+ * PARITY UNPINNED: no GHC in this environment, no golden vector upstream for these paths; restated from
+ *   DO/Pairwise/Internal.hs:389-424 (needlemanWunschDefinition, S1 cell), NeedlemanWunsch.hs:97-143,
+ *   UnboxedSwapping.hs:58-124 (S1 full), Ukkonen/Internal.hs:79-202 + Ukkonen/Ribbon.hs:100-155 (S1 ribbon),
+ *   UnboxedUkkonenFullSpace.hs:59-276, 641-815 (S2 band: getMinimalResult relabels Diag -> Left when the
+ *   median is the gap), UnboxedUkkonenSwapping.hs:436-459 (ukkonenConstants),
+ *   Bio/Metadata/Overlap.hs:56-86 (overlap), Data/MetricRepresentation.hs:116-128 (discrete metric).
+ * The Ukkonen variants are filled FROM SCRATCH at every offset of the reference's doubling schedule (the
+ * reference expands its band incrementally, UnboxedUkkonenFullSpace.hs:344-638; equal results assumed).
+ * Rows i = 0..m follow the lesser string, columns j = 0..n the longer one, exactly as in the Haskell.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int kind;                /* 0 discrete metric, 1 explicit symbol-change matrix */
+    int a;
+    const uint32_t *sigma;   /* a*a, indexed [median symbol][input symbol] (Overlap.hs:75-86) */
+} hs_metric_t;
+
+static void hs_overlap(const hs_metric_t *mt, uint32_t x, uint32_t y, uint32_t *med, uint64_t *cost)
+{
+    if (mt->kind == 0) {                                     /* discreteMetricPairwiseLogic */
+        if (x & y) { *med = x & y; *cost = 0; } else { *med = x | y; *cost = 1; }
+        return;
+    }
+    uint64_t best = UINT64_MAX;
+    uint32_t bits = 0;
+    for (int s = mt->a - 1; s >= 0; s--) {                   /* overlap: every symbol attaining the minimum */
+        uint64_t dx = UINT64_MAX, dy = UINT64_MAX;
+        for (int j = 0; j < mt->a; j++) {
+            if (x & (1u << j)) { uint64_t v = mt->sigma[s * mt->a + j]; if (v < dx) dx = v; }
+            if (y & (1u << j)) { uint64_t v = mt->sigma[s * mt->a + j]; if (v < dy) dy = v; }
+        }
+        const uint64_t c = dx + dy;
+        if (c == best) bits |= 1u << s;
+        else if (c < best) { best = c; bits = 1u << s; }
+    }
+    *med = bits; *cost = best;
+}
+
+#define HS_INF (UINT64_MAX / 4)
+enum { HS_DIAG = 0, HS_LEFT = 1, HS_UP = 2 };
+
+/* one banded fill: cells with j - i outside [-off, (n-m) + off] are infinite. s2 != 0: getMinimalResult. */
+static uint64_t hs_fill(const hs_metric_t *mt, int s2, const uint32_t *les, size_t m, const uint32_t *lon, size_t n,
+                        long off, uint8_t *dir, uint64_t *cells)
+{
+    const uint32_t gap = 1u << (mt->a - 1);
+    const size_t W = n + 1;
+    uint64_t *prev = malloc(sizeof(uint64_t) * W), *cur = malloc(sizeof(uint64_t) * W), cnt = 0;
+    for (size_t i = 0; i <= m; i++) {
+        for (size_t j = 0; j <= n; j++) {
+            const long x = (long)j - (long)i;
+            if (x < -off || x > (long)(n - m) + off) { cur[j] = HS_INF; continue; }
+            cnt++;
+            if (i == 0 && j == 0) { cur[0] = 0; dir[0] = HS_DIAG; continue; }
+            uint32_t md; uint64_t c;
+            uint64_t best = HS_INF; uint8_t bd = HS_DIAG; int relabel = 0;
+            if (i > 0 && j > 0 && prev[j - 1] < HS_INF) {
+                hs_overlap(mt, lon[j - 1], les[i - 1], &md, &c);
+                best = prev[j - 1] + c; bd = HS_DIAG; relabel = s2 && md == gap;
+            }
+            if (j > 0 && cur[j - 1] < HS_INF) {
+                hs_overlap(mt, lon[j - 1], gap, &md, &c);
+                if (cur[j - 1] + c < best) { best = cur[j - 1] + c; bd = HS_LEFT; relabel = 0; }
+            }
+            if (i > 0 && prev[j] < HS_INF) {
+                hs_overlap(mt, gap, les[i - 1], &md, &c);
+                if (prev[j] + c < best) { best = prev[j] + c; bd = HS_UP; relabel = 0; }
+            }
+            cur[j] = best;
+            dir[i * W + j] = relabel ? HS_LEFT : bd;
+        }
+        uint64_t *t = prev; prev = cur; cur = t;
+    }
+    const uint64_t res = prev[n];
+    free(prev); free(cur);
+    if (cells) *cells += cnt;
+    return res;
+}
+
+/* dialect: 0 S1 full (naiveDO / naiveDOMemo / unboxedSwappingDO), 1 S1 Ukkonen (ukkonenDO),
+ *          2 S2 Ukkonen (unboxedUkkonenFullSpaceDO).  in1 / in2: median strings (no gap-only elements).
+ * Outputs (length *out_len): median, aligned first input, aligned second input (0 = gap). */
+int64_t oracle_haskell_do(int dialect, int metric_kind, const uint32_t *sigma, int a,
+                          const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                          uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                          uint64_t *cells, int *final_offset)
+{
+    const hs_metric_t mt = { metric_kind, a, sigma };
+    const uint32_t gap = 1u << (a - 1);
+    /* measureCharacters on median strings: shorter first, then lexicographic; equal -> not swapped */
+    int swapped = 0;
+    if (n1 != n2) swapped = n1 > n2;
+    else for (size_t i = 0; i < n1; i++) if (in1[i] != in2[i]) { swapped = in1[i] > in2[i]; break; }
+    const uint32_t *les = swapped ? in2 : in1, *lon = swapped ? in1 : in2;
+    const size_t m = swapped ? n2 : n1, n = swapped ? n1 : n2;
+    if (cells) *cells = 0;
+    if (final_offset) *final_offset = -1;
+    uint8_t *dir = calloc((m + 1) * (n + 1), 1);
+
+    /* Delta = cheapest indel of a single non-gap symbol; G = elements containing the gap bit */
+    uint64_t delta = UINT64_MAX, G = 0;
+    for (int s = 0; s < a - 1; s++) {
+        uint32_t md; uint64_t c1, c2;
+        hs_overlap(&mt, 1u << s, gap, &md, &c1);
+        hs_overlap(&mt, gap, 1u << s, &md, &c2);
+        const uint64_t c = c1 < c2 ? c1 : c2;
+        if (c < delta) delta = c;
+    }
+    for (size_t i = 0; i < m; i++) G += (les[i] & gap) != 0;
+    for (size_t j = 0; j < n; j++) G += (lon[j] & gap) != 0;
+    const uint64_t qd = n - m + 1;
+    int no_gain = m <= 4 || 2 * n >= 3 * m || delta == 0;
+    if (dialect == 2) no_gain = no_gain || G >= n;
+
+    uint64_t cost;
+    if (dialect == 0 || no_gain) {
+        cost = hs_fill(&mt, 0, les, m, lon, n, (long)(m + n + 2), dir, cells);   /* full matrix, S1 cell */
+    } else if (dialect == 1) {                                  /* Ukkonen/Internal.hs:130-202 */
+        uint64_t off = 2;
+        for (;;) {
+            const long a_off = (long)(off < m ? off : m);       /* Ribbon.hs: a = min alpha (w - d) */
+            cost = hs_fill(&mt, 0, les, m, lon, n, a_off, dir, cells);
+            const int64_t cv = (int64_t)delta * ((int64_t)qd + (int64_t)off - (int64_t)G);
+            const uint64_t thr = cv > 0 ? (uint64_t)cv : 0;
+            if (final_offset) *final_offset = (int)off;
+            if (thr <= cost) off *= 2; else break;
+        }
+    } else {                                                    /* UnboxedUkkonenFullSpace.hs:159-207 */
+        uint64_t off = 2 + G;
+        for (;;) {
+            const long a_off = (long)(off < m ? off : m);       /* ukkonenConstants: min o (cols - qd) */
+            cost = hs_fill(&mt, 1, les, m, lon, n, a_off, dir, cells);
+            if (final_offset) *final_offset = (int)off;
+            if (qd + off > n) break;
+            const uint64_t thr = (qd + off <= G) ? 0 : delta * (qd + off - G);
+            if (thr <= cost) off *= 2; else break;
+        }
+    }
+    /* traceback (Pairwise/Internal.hs:531-581) */
+    size_t i = m, j = n, k = 0, cap = m + n + 1;
+    uint32_t *rm = malloc(sizeof(uint32_t) * cap), *rx = malloc(sizeof(uint32_t) * cap), *ry = malloc(sizeof(uint32_t) * cap);
+    while (i > 0 || j > 0) {
+        const uint8_t d = dir[i * (n + 1) + j];
+        uint32_t md; uint64_t c;
+        if (d == HS_LEFT)    { hs_overlap(&mt, gap, lon[j - 1], &md, &c); rm[k] = md; rx[k] = 0; ry[k] = lon[j - 1]; j--; }
+        else if (d == HS_UP) { hs_overlap(&mt, les[i - 1], gap, &md, &c); rm[k] = md; rx[k] = les[i - 1]; ry[k] = 0; i--; }
+        else                 { hs_overlap(&mt, les[i - 1], lon[j - 1], &md, &c); rm[k] = md; rx[k] = les[i - 1]; ry[k] = lon[j - 1]; i--; j--; }
+        k++;
+    }
+    for (size_t t = 0; t < k; t++) {
+        out_med[t] = rm[k - 1 - t];
+        const uint32_t x = rx[k - 1 - t], y = ry[k - 1 - t];     /* x from the lesser, y from the longer */
+        out_a1[t] = swapped ? y : x;
+        out_a2[t] = swapped ? x : y;
+    }
+    *out_len = k;
+    free(rm); free(rx); free(ry); free(dir);
+    return (int64_t)cost;
+}

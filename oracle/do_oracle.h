@@ -85,6 +85,15 @@ int64_t oracle_align2d_affine(const oracle_tcm_t *t, int variant,
                               uint32_t *out_gapped, uint32_t *out_slot1, uint32_t *out_slot2,
                               size_t *out_len, uint64_t *cells);
 
+/* Haskell dialects (PARITY UNPINNED, see do_oracle.c): dialect 0 = S1 full matrix (naiveDO, naiveDOMemo,
+ * unboxedSwappingDO), 1 = S1 Ukkonen ribbon (ukkonenDO), 2 = S2 Ukkonen band (unboxedUkkonenFullSpaceDO, the
+ * production path for alphabets > 8).  metric_kind 0 = discrete metric, 1 = explicit sigma[a*a] through overlap.
+ * in1 / in2 are median strings; outputs: median, aligned in1, aligned in2 (0 = gap). */
+int64_t oracle_haskell_do(int dialect, int metric_kind, const uint32_t *sigma, int a,
+                          const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                          uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                          uint64_t *cells, int *final_offset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,29 @@ class Oracle:
         return int(cost), np.stack([om[:k], ol[:k], orr[:k]], axis=1), int(cells.value)
 
 
+def haskell_do(dialect: int, a: int, in1, in2, sigma=None):
+    """S1 / S2 Haskell dialects on median strings (see do_oracle.c). sigma=None -> discrete metric.
+    Returns (cost, median, aligned1, aligned2, cells, final_offset)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.oracle_haskell_do.restype = C.c_int64
+    lib.oracle_haskell_do.argtypes = [C.c_int, C.c_int, _u32p, C.c_int, _u32p, C.c_size_t, _u32p, C.c_size_t,
+                                      _u32p, _u32p, _u32p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_int)]
+    a1, a2 = _as_u32(in1), _as_u32(in2)
+    sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
+    cap = len(a1) + len(a2) + 2
+    m, x, y = (np.zeros(cap, np.uint32) for _ in range(3))
+    n = C.c_size_t(0)
+    cells = C.c_uint64(0)
+    off = C.c_int(0)
+    cost = lib.oracle_haskell_do(dialect, 0 if sigma is None else 1, _ptr(sg), a, _ptr(a1), len(a1), _ptr(a2), len(a2),
+                                 _ptr(m), _ptr(x), _ptr(y), C.byref(n), C.byref(cells), C.byref(off))
+    k = n.value
+    return int(cost), m[:k].copy(), x[:k].copy(), y[:k].copy(), int(cells.value), int(off.value)
+
+
 class _AlignIO(C.Structure):
     _fields_ = [("character", _u32p), ("length", C.c_size_t), ("capacity", C.c_size_t)]
 

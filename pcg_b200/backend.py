@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_tcm_create", "pcgdo_tcm_destroy",
     "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
     "pcgdo_configure_ex", "pcgdo_int32_peak",
+    "pcgdo_metric_batch_device", "pcgdo_metric_batch_host",
     "pcgdo_tcm_create_affine", "pcgdo_align2d_affine_batch_device", "pcgdo_align2d_affine_batch_host",
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
@@ -51,6 +52,15 @@ class Batch(C.Structure):
                 ("out_off", C.c_void_p), ("out_bytes", C.c_size_t),
                 ("out_gapped", C.c_void_p), ("out_slot1", C.c_void_p), ("out_slot2", C.c_void_p),
                 ("out_len", C.c_void_p), ("cost", C.c_void_p), ("cells", C.c_void_p)]
+
+
+class Batch32(C.Structure):
+    """pcgdo_batch32."""
+    _fields_ = [("n_pairs", C.c_size_t), ("elems", C.c_void_p), ("elems_count", C.c_size_t),
+                ("off1", C.c_void_p), ("off2", C.c_void_p), ("len1", C.c_void_p), ("len2", C.c_void_p),
+                ("out_off", C.c_void_p), ("out_count", C.c_size_t),
+                ("out_med", C.c_void_p), ("out_a1", C.c_void_p), ("out_a2", C.c_void_p),
+                ("out_len", C.c_void_p), ("cost", C.c_void_p), ("cells", C.c_void_p), ("final_offset", C.c_void_p)]
 
 
 class BackendError(RuntimeError):
@@ -86,6 +96,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_align2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
     L.pcgdo_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.pcgdo_int32_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.pcgdo_metric_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Batch32), C.c_void_p]
+    L.pcgdo_metric_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Batch32)]
     L.pcgdo_forest_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                       C.POINTER(C.c_void_p)]
     L.pcgdo_forest_destroy.argtypes = [C.c_void_p, C.c_void_p]

@@ -35,6 +35,35 @@ uint32_t aff_words_for(uint32_t n1, uint32_t n2);
 cudaError_t launch_affine(const AffParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 }
 namespace pcgdo {
+struct MetricBatchDev {
+    uint32_t        n_pairs;
+    const uint32_t *elems;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    const uint64_t *out_off;
+    uint32_t       *out_med, *out_a1, *out_a2;
+    uint32_t       *out_len;
+    int32_t        *cost;
+    uint64_t       *cells;
+    int32_t        *final_offset;
+};
+struct MetricParams {
+    MetricBatchDev b;
+    int       a;
+    int       dialect;
+    uint32_t *arena;
+    uint32_t  arena_words;
+    uint32_t  seq_cap;
+    int       pairs_per_warp;
+    unsigned int *counter;
+    unsigned int *overflow_count;
+    uint32_t  k_four, k_minus1;
+};
+uint32_t metric_seq_cap(int max_len);
+uint32_t metric_words_for(uint32_t n1, uint32_t n2);
+cudaError_t launch_metric(const MetricParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+}
+namespace pcgdo {
 double launch_int_peak(int mode, int grid, int iters, uint32_t *scratch, cudaStream_t st);
 }
 using namespace pcgdo;
@@ -509,6 +538,134 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
         ctx->err = msg;
         return PCGDO_ERR_OVERFLOW;
     }
+    return PCGDO_OK;
+}
+
+// --------------------------------------------------------------------------------------------- large alphabets
+
+extern "C" int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b,
+                                         void *cuda_stream)
+{
+    if (!ctx || !b) return PCGDO_ERR_ARG;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    if (alphabet < 2 || alphabet > 24 || dialect < 0 || dialect > 2) {
+        ctx->err = "metric path: alphabet must be 2..24, dialect 0..2";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost ||
+        ((b->out_med || b->out_a1 || b->out_a2) && !b->out_off)) {
+        ctx->err = "bad batch description";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const uint32_t seq_cap = metric_seq_cap(ctx->max_len);
+    int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    while (warps > 1 && (size_t)warps * (512 + seq_cap) > 227 * 1024) --warps;
+    const size_t smem = (size_t)warps * (512 + seq_cap);
+    if (smem > 227 * 1024) {
+        ctx->err = "max_len too large for the metric kernel's staging window";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    size_t arena_words = ctx->arena_words;
+    if (!arena_words) {
+        const size_t per = metric_words_for((uint32_t)ctx->max_len, (uint32_t)ctx->max_len);
+        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 4096);
+    }
+    arena_words = (arena_words + 3) & ~(size_t)3;
+    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
+    const int grid = ctx->sm_count;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    MetricParams p{};
+    p.b.n_pairs = (uint32_t)b->n_pairs;
+    p.b.elems = b->elems;
+    p.b.off1 = b->off1; p.b.off2 = b->off2; p.b.len1 = b->len1; p.b.len2 = b->len2;
+    p.b.out_off = b->out_off;
+    p.b.out_med = b->out_med; p.b.out_a1 = b->out_a1; p.b.out_a2 = b->out_a2;
+    p.b.out_len = b->out_len;
+    p.b.cost = b->cost;
+    p.b.cells = b->cells;
+    p.b.final_offset = b->final_offset;
+    p.a = alphabet;
+    p.dialect = dialect;
+    p.arena = (uint32_t *)ctx->arena.p;
+    p.arena_words = (uint32_t)arena_words;
+    p.seq_cap = seq_cap;
+    p.pairs_per_warp = ctx->pairs_per_warp;
+    p.counter = (unsigned int *)ctx->counters.p;
+    p.overflow_count = p.counter + 8;
+    p.k_four = 4u;
+    p.k_minus1 = 0xffffffffu;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_metric(p, grid, warps * 32, smem, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    ctx->last_launches = 1;
+    unsigned int h_over = 0;
+    CK(cudaMemcpyAsync(&h_over, p.overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_over) {
+        char msg[200];
+        snprintf(msg, sizeof msg, "%u pair(s) exceed the metric kernel's limits (band wider than 1023 diagonals, strings "
+                                  "longer than max_len=%d, or scratch beyond the arena)", h_over, ctx->max_len);
+        ctx->err = msg;
+        return PCGDO_ERR_OVERFLOW;
+    }
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b)
+{
+    if (!ctx || !b) return PCGDO_ERR_ARG;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = b->n_pairs;
+    const bool want = b->out_med || b->out_a1 || b->out_a2;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_elems, b->elems_count * 4 + 16))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_off1, n * 8)) || (rc = pcgdo_ensure(ctx, ctx->d_off2, n * 8)) ||
+        (rc = pcgdo_ensure(ctx, ctx->d_len1, n * 4)) || (rc = pcgdo_ensure(ctx, ctx->d_len2, n * 4)) ||
+        (rc = pcgdo_ensure(ctx, ctx->d_cost, n * 4)) || (rc = pcgdo_ensure(ctx, ctx->d_olen, n * 8)) ||
+        (rc = pcgdo_ensure(ctx, ctx->d_cells, n * 8)))
+        return rc;
+    if (want) {
+        if ((rc = pcgdo_ensure(ctx, ctx->d_out_off, n * 8)) || (rc = pcgdo_ensure(ctx, ctx->d_og, b->out_count * 4 + 16)) ||
+            (rc = pcgdo_ensure(ctx, ctx->d_o1, b->out_count * 4 + 16)) || (rc = pcgdo_ensure(ctx, ctx->d_o2, b->out_count * 4 + 16)))
+            return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_count * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off1.p, b->off1, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off2.p, b->off2, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_len1.p, b->len1, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_len2.p, b->len2, n * 4, cudaMemcpyHostToDevice, st));
+    if (want) CK(cudaMemcpyAsync(ctx->d_out_off.p, b->out_off, n * 8, cudaMemcpyHostToDevice, st));
+    pcgdo_batch32 d = *b;
+    d.elems = (const uint32_t *)ctx->d_elems.p;
+    d.off1 = (const uint64_t *)ctx->d_off1.p; d.off2 = (const uint64_t *)ctx->d_off2.p;
+    d.len1 = (const uint32_t *)ctx->d_len1.p; d.len2 = (const uint32_t *)ctx->d_len2.p;
+    d.out_off = want ? (const uint64_t *)ctx->d_out_off.p : nullptr;
+    d.out_med = b->out_med ? (uint32_t *)ctx->d_og.p : nullptr;
+    d.out_a1 = b->out_a1 ? (uint32_t *)ctx->d_o1.p : nullptr;
+    d.out_a2 = b->out_a2 ? (uint32_t *)ctx->d_o2.p : nullptr;
+    d.out_len = b->out_len ? (uint32_t *)ctx->d_olen.p : nullptr;
+    d.cost = (int32_t *)ctx->d_cost.p;
+    d.cells = b->cells ? (uint64_t *)ctx->d_cells.p : nullptr;
+    d.final_offset = b->final_offset ? (int32_t *)((uint32_t *)ctx->d_olen.p + n) : nullptr;
+    if ((rc = pcgdo_metric_batch_device(ctx, alphabet, dialect, &d, st))) return rc;
+    CK(cudaMemcpyAsync(b->cost, d.cost, n * 4, cudaMemcpyDeviceToHost, st));
+    if (b->out_len) CK(cudaMemcpyAsync(b->out_len, d.out_len, n * 4, cudaMemcpyDeviceToHost, st));
+    if (b->final_offset) CK(cudaMemcpyAsync(b->final_offset, d.final_offset, n * 4, cudaMemcpyDeviceToHost, st));
+    if (b->cells) CK(cudaMemcpyAsync(b->cells, d.cells, n * 8, cudaMemcpyDeviceToHost, st));
+    if (b->out_med) CK(cudaMemcpyAsync(b->out_med, d.out_med, b->out_count * 4, cudaMemcpyDeviceToHost, st));
+    if (b->out_a1) CK(cudaMemcpyAsync(b->out_a1, d.out_a1, b->out_count * 4, cudaMemcpyDeviceToHost, st));
+    if (b->out_a2) CK(cudaMemcpyAsync(b->out_a2, d.out_a2, b->out_count * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return PCGDO_OK;
 }
 

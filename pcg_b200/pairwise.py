@@ -21,7 +21,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .backend import Batch, Context, Tcm
+from .backend import Batch, Batch32, Context, Tcm
 
 
 def _rup4(x):
@@ -222,3 +222,53 @@ def foreign_pairwise_do_batch(ctx: Context, tcm: Tcm, chars1: Sequence[Optional[
 
 def foreign_pairwise_do(ctx: Context, tcm: Tcm, c1, c2, median_of_gap=None):
     return foreign_pairwise_do_batch(ctx, tcm, [c1], [c2], median_of_gap)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# Large alphabets: the Haskell dialects over the discrete metric (reference dispatch: DO/Internal.hs:67-83)
+# ------------------------------------------------------------------------------------------------
+S1_FULL, S1_UKKONEN, S2_UKKONEN = 0, 1, 2      # naiveDO / ukkonenDO / unboxedUkkonenFullSpaceDO
+
+
+@dataclass
+class MetricResult:
+    cost: np.ndarray
+    out_len: np.ndarray
+    median: np.ndarray          # uint32 flat, indexed by out_off
+    a1: np.ndarray
+    a2: np.ndarray
+    cells: np.ndarray
+    final_offset: np.ndarray
+    out_off: np.ndarray
+
+    def pair(self, k: int):
+        o, n = int(self.out_off[k]), int(self.out_len[k])
+        return int(self.cost[k]), self.median[o:o + n], self.a1[o:o + n], self.a2[o:o + n]
+
+
+def metric_do_batch(ctx: Context, alphabet: int, dialect: int, first: Sequence[np.ndarray],
+                    second: Sequence[np.ndarray]) -> MetricResult:
+    """``naiveDO`` / ``ukkonenDO`` / ``unboxedUkkonenFullSpaceDO`` with the discrete metric on median strings
+    (uint32 ambiguity sets), one launch for the whole batch."""
+    n = len(first)
+    len1 = np.fromiter((len(x) for x in first), dtype=np.uint32, count=n)
+    len2 = np.fromiter((len(x) for x in second), dtype=np.uint32, count=n)
+    tot = len1.astype(np.uint64) + len2.astype(np.uint64)
+    starts = np.concatenate([[0], np.cumsum(tot)]).astype(np.uint64)
+    off1 = starts[:-1].copy()
+    off2 = off1 + len1
+    elems = np.zeros(int(starts[-1]) + 4, np.uint32)
+    for k in range(n):
+        elems[int(off1[k]):int(off1[k]) + int(len1[k])] = first[k]
+        elems[int(off2[k]):int(off2[k]) + int(len2[k])] = second[k]
+    out_off = off1.copy()
+    cnt = int(starts[-1]) + 4
+    med, a1, a2 = (np.zeros(cnt, np.uint32) for _ in range(3))
+    cost = np.zeros(n, np.int32)
+    out_len = np.zeros(n, np.uint32)
+    cells = np.zeros(n, np.uint64)
+    fo = np.zeros(n, np.int32)
+    b = Batch32(n, _p(elems), elems.size, _p(off1), _p(off2), _p(len1), _p(len2), _p(out_off), cnt,
+                _p(med), _p(a1), _p(a2), _p(out_len), _p(cost), _p(cells), _p(fo))
+    ctx.check(ctx.lib.pcgdo_metric_batch_host(ctx.h, alphabet, dialect, C.byref(b)), "pcgdo_metric_batch_host")
+    return MetricResult(cost, out_len, med, a1, a2, cells, fo, out_off)
