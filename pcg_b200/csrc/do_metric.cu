@@ -7,8 +7,8 @@
 //   S2 Ukkonen       unboxedUkkonenFullSpaceDO (production, a>8) DO/Pairwise/UnboxedUkkonenFullSpace.hs:59-276, 641-815
 // with the discrete metric's closed-form overlap (lib/core/tcm/src/Data/MetricRepresentation.hs:116-128)
 // computed per cell in registers — no tcm-memo hash lookups (lib/tcm-memo), no per-cell FFI.
-// PARITY UNPINNED upstream for these paths (no executable Haskell here, no golden vector): the checker is
-// oracle/do_oracle.c::oracle_haskell_do.  The Ukkonen variants re-fill the band from scratch at each offset
+// PARITY UNPINNED upstream for these paths (no executable Haskell here, no golden vector): the checker is the
+// CPU restatement kept with the tests.  The Ukkonen variants re-fill the band from scratch at each offset
 // of the reference's doubling schedule (the reference expands incrementally; same cells, same rules).
 //
 // Same machinery as do_linear.cu: one warp per pair, lanes own B consecutive diagonals of the band, two
