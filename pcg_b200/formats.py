@@ -1,0 +1,130 @@
+"""Input formats either side of the DO path: FASTA / FASTC sequence files, TCM text files, IUPAC codes.
+
+Reference (lib = /root/reference/lib):
+* FASTA  — lib/file-parsers/src/File/Format/Fasta/Parser.hs: ``>`` + taxon name line, then sequence lines;
+           one character per symbol, whitespace ignored.
+* FASTC  — lib/file-parsers/src/File/Format/Fastc/Parser.hs: same header; symbols are whitespace-separated
+           tokens, ``[a b c]`` is an ambiguity group.
+* TCM    — lib/file-parsers/src/File/Format/TransitionCostMatrix/Parser.hs: first line = the alphabet symbols
+           (gap is implicit and LAST), then an (n+1) x (n+1) matrix, row/column n = gap.
+* IUPAC  — lib/alphabet/src/Data/Alphabet/IUPAC.hs:62-124 (DNA: lower case = the upper-case set plus gap,
+           ``?`` = everything including gap; amino acids: B = DN, Z = EQ, X = all 20, ``?`` = all + gap).
+
+Elements are encoded as the DO path wants them: bit i = symbol i of the alphabet, gap = highest bit
+(``1 << (a - 1)``, DYN/Internal.hs:253-257).  Pure host-side text handling: no alignment work happens here.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+DNA = ["A", "C", "G", "T"]
+AMINO = list("ACDEFGHIKLMNPQRSTVWY")
+
+_DNA_IUPAC = {"A": "A", "C": "C", "G": "G", "T": "T", "R": "AG", "Y": "CT", "S": "CG", "W": "AT", "K": "GT",
+              "M": "AC", "B": "CGT", "D": "AGT", "H": "ACT", "V": "ACG", "N": "ACGT"}
+_AMINO_IUPAC = {**{c: c for c in AMINO}, "B": "DN", "Z": "EQ", "X": "".join(AMINO)}
+
+
+def iupac_dna_codes() -> Dict[str, int]:
+    """char -> 5-bit element (A=1, C=2, G=4, T=8, gap=16)."""
+    bit = {s: 1 << i for i, s in enumerate(DNA)}
+    gap = 1 << len(DNA)
+    out = {}
+    for ch, syms in _DNA_IUPAC.items():
+        v = sum(bit[s] for s in syms)
+        out[ch] = v
+        if ch not in "N":
+            out[ch.lower()] = v | gap
+    out["-"] = gap
+    out["?"] = (gap << 1) - 1
+    return out
+
+
+def iupac_amino_codes() -> Dict[str, int]:
+    bit = {s: 1 << i for i, s in enumerate(AMINO)}
+    gap = 1 << len(AMINO)
+    out = {ch: sum(bit[s] for s in syms) for ch, syms in _AMINO_IUPAC.items()}
+    out["-"] = gap
+    out["?"] = (gap << 1) - 1
+    return out
+
+
+def read_fasta(text: str) -> List[Tuple[str, str]]:
+    """[(taxon name, sequence characters with whitespace removed)]."""
+    out: List[Tuple[str, str]] = []
+    name, buf = None, []
+    for line in text.splitlines():
+        line = line.strip()
+        if not line:
+            continue
+        if line.startswith(">"):
+            if name is not None:
+                out.append((name, "".join(buf)))
+            name, buf = line[1:].strip(), []
+        else:
+            buf.append("".join(line.split()))
+    if name is not None:
+        out.append((name, "".join(buf)))
+    return out
+
+
+def encode_fasta(seq: str, codes: Dict[str, int], dtype=np.uint8) -> np.ndarray:
+    return np.fromiter((codes[c] for c in seq), dtype=dtype, count=len(seq))
+
+
+def read_fastc(text: str) -> List[Tuple[str, List[List[str]]]]:
+    """[(taxon name, [ambiguity group = list of symbols])]."""
+    out: List[Tuple[str, List[List[str]]]] = []
+    name, toks = None, []
+
+    def flush():
+        if name is None:
+            return
+        groups, cur = [], None
+        for t in toks:
+            while t:
+                if t[0] == "[":
+                    cur, t = [], t[1:]
+                elif t[-1] == "]" and cur is not None:
+                    if t[:-1]:
+                        cur.append(t[:-1])
+                    groups.append(cur)
+                    cur, t = None, ""
+                else:
+                    (cur if cur is not None else groups).append(t if cur is not None else [t])
+                    t = ""
+        out.append((name, groups))
+
+    for line in text.splitlines():
+        line = line.strip()
+        if not line:
+            continue
+        if line.startswith(">"):
+            flush()
+            name, toks = line[1:].strip(), []
+        else:
+            toks.extend(line.split())
+    flush()
+    return out
+
+
+def encode_fastc(groups: Sequence[Sequence[str]], alphabet: Sequence[str], dtype=np.uint32) -> np.ndarray:
+    """alphabet WITHOUT the gap; '-' encodes as the gap bit, '?' as everything."""
+    bit = {s: 1 << i for i, s in enumerate(alphabet)}
+    gap = 1 << len(alphabet)
+    bit["-"] = gap
+    full = (gap << 1) - 1
+    return np.fromiter((full if g == ["?"] else sum(bit[s] for s in g) for g in groups), dtype=dtype, count=len(groups))
+
+
+def read_tcm(text: str) -> Tuple[List[str], np.ndarray]:
+    """(alphabet without gap, (n+1) x (n+1) uint32 matrix with the gap as last row / column)."""
+    lines = [ln.split() for ln in text.splitlines() if ln.strip()]
+    alphabet = lines[0]
+    n = len(alphabet) + 1
+    rows = lines[1:1 + n]
+    if len(rows) != n or any(len(r) != n for r in rows):
+        raise ValueError(f"TCM: expected a {n} x {n} matrix after the alphabet line")
+    return alphabet, np.array([[int(float(x)) for x in r] for r in rows], dtype=np.uint32)

@@ -52,3 +52,23 @@ def random_pair(rng, max_len=400, a=5, amb=0.15):
     else:
         s2 = random_string(rng, n2, a, amb)
     return s1, s2
+
+
+def bench_strings_golden():
+    """tests/golden/bench_strings_dna.json (made by make_bench_strings_golden.py from the reference's
+    bench/strings/dna inputs and the compiled reference aligner).  Returns (encoded ungapped strings,
+    {tcm file: (sigma, records [i, j, cost, out_len, crc_gapped, crc_slot1, crc_slot2])})."""
+    import json
+    from pcg_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_strings_dna.json")))
+    codes = formats.iupac_dna_codes()
+    enc = []
+    for s in g["text"]:
+        e = formats.encode_fasta(s, codes)
+        enc.append(e[e != 16])
+    return enc, {k: (np.array(g["tcms"][k], np.uint32), g["pairs"][k]) for k in g["pairs"]}
+
+
+def crc_u8(a):
+    import zlib
+    return zlib.crc32(np.asarray(a, np.uint8).tobytes())

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.helpers import random_pair, random_string, tcm_matrix
+from tests.helpers import bench_strings_golden, crc_u8, random_pair, random_string, tcm_matrix
 
 pytestmark = pytest.mark.gpu
 
@@ -251,3 +251,23 @@ def test_pipelined_host_entry_point(oracle_mod, gpu_ctx):
         assert gc[0] == oc[0], k
         for x, y in zip(gc[1:], oc[1:4]):
             assert np.array_equal(x, y), k
+
+
+@pytest.mark.parametrize("tcm_file", ["dna-discrete.tcm", "dna-L1-norm.tcm", "dna-pref-gap.tcm", "dna-pref-sub.tcm"])
+def test_bench_strings_golden_through_gpu(gpu_ctx, tcm_file):
+    """BASELINE config 1 on the device against the committed outputs of the compiled reference (no oracle
+    in the loop): 190 pairs, lengths 8 ... 4608, IUPAC ambiguity, all four DNA TCM files."""
+    import pcg_b200 as P
+    enc, per_tcm = bench_strings_golden()
+    sigma, recs = per_tcm[tcm_file]
+    tcm = gpu_ctx.tcm(sigma)
+    gpu_ctx.configure(max_len=4700, max_b=32)
+    firsts, seconds = [], []
+    for i, j, *_ in recs:
+        a, b = (enc[i], enc[j]) if len(enc[i]) >= len(enc[j]) else (enc[j], enc[i])
+        firsts.append(a); seconds.append(b)
+    pp = P.PackedPairs.from_lists(firsts, seconds)
+    r = P.align2d_batch(gpu_ctx, tcm, pp)
+    for k, (i, j, cost, n, cg, c1, c2) in enumerate(recs):
+        gc = r.pair(pp, k)
+        assert (gc[0], len(gc[1]), crc_u8(gc[1]), crc_u8(gc[2]), crc_u8(gc[3])) == (cost, n, cg, c1, c2), (i, j)

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.helpers import random_pair, tcm_matrix
+from tests.helpers import bench_strings_golden, crc_u8, random_pair, tcm_matrix
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "chel_golden.json")
 
@@ -110,3 +110,17 @@ def test_affine_oracle_matches_compiled_reference(oracle_mod, variant, patched, 
         assert rc[0] == oc[0]
         for x, y in zip(rc[1:], oc[1:4]):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("tcm_file", ["dna-discrete.tcm", "dna-L1-norm.tcm", "dna-pref-gap.tcm", "dna-pref-sub.tcm"])
+def test_oracle_reproduces_bench_strings_golden(oracle_mod, tcm_file):
+    """BASELINE config 1: all 190 pairs of the reference's bench/strings/dna strings; cost and the three
+    output strings as the compiled reference produced them (fixture made by make_bench_strings_golden.py)."""
+    enc, per_tcm = bench_strings_golden()
+    sigma, recs = per_tcm[tcm_file]
+    o = oracle_mod.Oracle(sigma)
+    assert len(recs) == 190
+    for i, j, cost, n, cg, c1, c2 in recs:
+        a, b = (enc[i], enc[j]) if len(enc[i]) >= len(enc[j]) else (enc[j], enc[i])
+        oc = o.align2d(a, b)
+        assert (oc[0], len(oc[1]), crc_u8(oc[1]), crc_u8(oc[2]), crc_u8(oc[3])) == (cost, n, cg, c1, c2), (i, j)
