@@ -159,7 +159,8 @@ int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const 
  * Inputs are median strings (what `measureAndUngapCharacters` leaves); outputs per pair: median, aligned first
  * input, aligned second input (0 = gap), at element offset out_off[k] (room for len1+len2 elements).
  * Upstream has neither golden vectors nor (here) an executable for these paths: parity is against the restatement
- * in oracle/do_oracle.c only.  Explicit (non-discrete) matrices and the L1 metric for a > 8 are not built yet. */
+ * in oracle/do_oracle.c only.  Explicit matrices: pcgdo_explicit_batch_* below.  The additive (L1) metric for
+ * a > 8 is not built (its reference semantics hinge on the un-vendored bv-little bit order). */
 typedef struct pcgdo_batch32 {
     size_t          n_pairs;
     const uint32_t *elems;
@@ -176,6 +177,34 @@ typedef struct pcgdo_batch32 {
 } pcgdo_batch32;
 int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b, void *cuda_stream);
 int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b);
+
+/* ---------------------------------------------------------------- explicit matrices for a > 8: tcm-memo replacement
+ * For alphabets the dense table cannot hold and a symbol-change matrix that is neither the discrete metric nor
+ * additive, the reference answers every per-cell overlap through lib/tcm-memo (a C++ hash map memoizing the Sankoff
+ * median/cost of a pair of ambiguity sets, lib/tcm-memo/ffi/memoized-tcm/costMatrix_2d.cpp:131-267).  Here the
+ * overlap is a device function and the memo a per-pair dense table in shared memory / HBM (do_explicit.cu).
+ * sigma: a*a row-major, sigma[s*a + j] = cost between MEDIAN symbol s and INPUT symbol j, gap = symbol a-1; a <= 32. */
+typedef struct pcgdo_memo pcgdo_memo;
+int  pcgdo_memo_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, pcgdo_memo **out);
+void pcgdo_memo_destroy(pcgdo_ctx *ctx, pcgdo_memo *memo);
+/* n independent overlap lookups: median[k], cost[k] = Sankoff median / cost of the sets e1[k], e2[k]. */
+int  pcgdo_overlap2d_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, size_t n, const uint32_t *e1, const uint32_t *e2,
+                                  uint32_t *median, uint32_t *cost, void *cuda_stream);
+int  pcgdo_overlap2d_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, size_t n, const uint32_t *e1, const uint32_t *e2,
+                                uint32_t *median, uint32_t *cost);
+/* The three Haskell dialects of pcgdo_metric_batch_* over the explicit matrix (same batch layout and outputs). */
+int  pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b, void *cuda_stream);
+int  pcgdo_explicit_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b);
+
+/* Reference-compatible tcm-memo symbols (lib/tcm-memo/ffi/memoized-tcm/costMatrixWrapper.h:12-31,
+ * dynamicCharacterOperations.h; bound at lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:49-69): one lookup per call
+ * through the GPU, alphabets <= 32.  getCostAndMedian2D frees and re-allocates retElem->element like the
+ * reference (costMatrix_2d.cpp:156-166).  The 3D lookup is not on this path (3D DO is disabled upstream). */
+typedef struct dcElement_t { size_t alphSize; uint64_t *element; } dcElement_t;
+typedef void *costMatrix_p;
+costMatrix_p matrixInit(size_t alphSize, unsigned int *tcm);
+void         matrixDestroy(costMatrix_p untyped_ptr);
+unsigned int getCostAndMedian2D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *retElem, costMatrix_p tcm);
 
 /* Finer tunables: widest diagonals-per-lane variant the warp kernels must accommodate (2,4,8,16,32; pairs
  * needing more go to the general-geometry kernel) and the per-warp scratch arena in 32-bit words (0 = derive

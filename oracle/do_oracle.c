@@ -534,6 +534,17 @@ static void hs_overlap(const hs_metric_t *mt, uint32_t x, uint32_t y, uint32_t *
     *med = bits; *cost = best;
 }
 
+/* exported: one overlap lookup (metric_kind as oracle_haskell_do); the explicit branch restates
+ * CostMatrix_2d::computeCostMedian / findDistance (lib/tcm-memo/ffi/memoized-tcm/costMatrix_2d.cpp:175-267) and is
+ * PINNED against the compiled reference tcm-memo (tests/golden/tcm_memo_golden.json, tests/test_oracle.py). */
+uint64_t oracle_overlap(int metric_kind, const uint32_t *sigma, int a, uint32_t x, uint32_t y, uint32_t *med)
+{
+    const hs_metric_t mt = { metric_kind, a, sigma };
+    uint64_t c;
+    hs_overlap(&mt, x, y, med, &c);
+    return c;
+}
+
 #define HS_INF (UINT64_MAX / 4)
 enum { HS_DIAG = 0, HS_LEFT = 1, HS_UP = 2 };
 

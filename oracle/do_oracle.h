@@ -94,6 +94,10 @@ int64_t oracle_haskell_do(int dialect, int metric_kind, const uint32_t *sigma, i
                           uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
                           uint64_t *cells, int *final_offset);
 
+/* One overlap lookup: Sankoff median / cost of two ambiguity sets (metric_kind 0 discrete, 1 explicit sigma[a*a],
+ * sigma[s*a + j] = median symbol s vs input symbol j).  Explicit branch pinned against the compiled tcm-memo. */
+uint64_t oracle_overlap(int metric_kind, const uint32_t *sigma, int a, uint32_t x, uint32_t y, uint32_t *med);
+
 #ifdef __cplusplus
 }
 #endif

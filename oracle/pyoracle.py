@@ -169,6 +169,59 @@ def haskell_do(dialect: int, a: int, in1, in2, sigma=None):
     return int(cost), m[:k].copy(), x[:k].copy(), y[:k].copy(), int(cells.value), int(off.value)
 
 
+def overlap(a: int, x: int, y: int, sigma=None):
+    """(median, cost) of one overlap lookup by the restatement (sigma=None -> discrete metric)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.oracle_overlap.restype = C.c_uint64
+    lib.oracle_overlap.argtypes = [C.c_int, _u32p, C.c_int, C.c_uint32, C.c_uint32, _u32p]
+    sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
+    med = C.c_uint32(0)
+    cost = lib.oracle_overlap(0 if sigma is None else 1, _ptr(sg), a, x, y, C.byref(med))
+    return int(med.value), int(cost)
+
+
+class _DcElement(C.Structure):
+    _fields_ = [("alphSize", C.c_size_t), ("element", C.POINTER(C.c_uint64))]
+
+
+class ReferenceMemo:
+    """The compiled, unmodified reference tcm-memo (``oracle/_ref/libtcmmemo_ref.so``), driven like
+    ``getMedianAndCost2D`` (lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:97-112): malloc'ed dcElement_t buffers."""
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_MEMO_SO)
+
+    def __init__(self, sigma):
+        self.lib = C.CDLL(REF_MEMO_SO)
+        self.libc = C.CDLL(None)
+        self.libc.calloc.restype = C.c_void_p
+        self.libc.calloc.argtypes = [C.c_size_t, C.c_size_t]
+        self.libc.free.argtypes = [C.c_void_p]
+        self.sigma = _as_u32(sigma).copy()
+        self.a = int(self.sigma.shape[0])
+        self.lib.matrixInit.restype = C.c_void_p
+        self.lib.matrixInit.argtypes = [C.c_size_t, _u32p]
+        self.lib.getCostAndMedian2D.restype = C.c_uint
+        self.lib.getCostAndMedian2D.argtypes = [C.POINTER(_DcElement)] * 3 + [C.c_void_p]
+        self.m = self.lib.matrixInit(self.a, _ptr(self.sigma))
+
+    def _elem(self, v):
+        buf = self.libc.calloc(1, 8)
+        C.cast(buf, C.POINTER(C.c_uint64))[0] = int(v)
+        return _DcElement(self.a, C.cast(buf, C.POINTER(C.c_uint64)))
+
+    def overlap(self, x: int, y: int):
+        e1, e2, r = self._elem(x), self._elem(y), self._elem(0)
+        cost = self.lib.getCostAndMedian2D(C.byref(e1), C.byref(e2), C.byref(r), self.m)
+        med = int(r.element[0])
+        for e in (e1, e2, r):
+            self.libc.free(C.cast(e.element, C.c_void_p))
+        return med, int(cost)
+
+
 class _AlignIO(C.Structure):
     _fields_ = [("character", _u32p), ("length", C.c_size_t), ("capacity", C.c_size_t)]
 

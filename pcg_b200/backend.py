@@ -29,6 +29,9 @@ EXPORTED_SYMBOLS = [
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
+    "pcgdo_memo_create", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
+    "pcgdo_explicit_batch_device", "pcgdo_explicit_batch_host",
+    "matrixInit", "matrixDestroy", "getCostAndMedian2D",
 ]
 
 
@@ -61,6 +64,11 @@ class Batch32(C.Structure):
                 ("out_off", C.c_void_p), ("out_count", C.c_size_t),
                 ("out_med", C.c_void_p), ("out_a1", C.c_void_p), ("out_a2", C.c_void_p),
                 ("out_len", C.c_void_p), ("cost", C.c_void_p), ("cells", C.c_void_p), ("final_offset", C.c_void_p)]
+
+
+class DcElement(C.Structure):
+    """dcElement_t (reference: lib/tcm-memo/ffi/memoized-tcm/dynamicCharacterOperations.h)."""
+    _fields_ = [("alphSize", C.c_size_t), ("element", _u64p)]
 
 
 class BackendError(RuntimeError):
@@ -113,6 +121,18 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_forest_levels.restype = C.c_uint32
     L.pcgdo_forest_alignments.argtypes = [C.c_void_p]
     L.pcgdo_forest_alignments.restype = C.c_uint64
+    L.pcgdo_memo_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.pcgdo_memo_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_overlap2d_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 5
+    L.pcgdo_overlap2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
+    L.pcgdo_explicit_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Batch32), C.c_void_p]
+    L.pcgdo_explicit_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Batch32)]
+    L.matrixInit.argtypes = [C.c_size_t, _u32p]
+    L.matrixInit.restype = C.c_void_p
+    L.matrixDestroy.argtypes = [C.c_void_p]
+    L.matrixDestroy.restype = None
+    L.getCostAndMedian2D.argtypes = [C.POINTER(DcElement)] * 3 + [C.c_void_p]
+    L.getCostAndMedian2D.restype = C.c_uint
     L.setUp2dCostMtx.argtypes = [C.POINTER(CostMatrices2D), _u32p, C.c_size_t, C.c_uint]
     L.setUp2dCostMtx.restype = None
     L.align2d.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int, C.c_int, C.c_int]
@@ -157,6 +177,9 @@ class Context:
 
     def tcm(self, sigma, gap_open: int = 0, affine_variant: int = 0) -> "Tcm":
         return Tcm(self, sigma, gap_open, affine_variant)
+
+    def memo(self, sigma) -> "Memo":
+        return Memo(self, sigma)
 
     def int32_peak(self, mode: int = 0) -> float:
         """Measured integer lane-ops/s of this GPU (roofline denominator for the DP fill)."""
@@ -203,6 +226,39 @@ class Tcm:
         try:
             if self.h.value and self.ctx.h.value:
                 self.ctx.lib.pcgdo_tcm_destroy(self.ctx.h, self.h)
+        except Exception:
+            pass
+
+
+class Memo:
+    """Explicit symbol-change matrix for alphabets the dense table cannot hold (pcgdo_memo): the device-side
+    replacement of the reference's memoized TCM (lib/tcm-memo).  sigma[s, j]: median symbol s, input symbol j."""
+
+    def __init__(self, ctx: Context, sigma):
+        self.ctx = ctx
+        sigma = np.ascontiguousarray(np.asarray(sigma, dtype=np.uint32))
+        self.a = int(sigma.shape[0])
+        assert sigma.shape == (self.a, self.a)
+        self.gap = 1 << (self.a - 1)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.pcgdo_memo_create(ctx.h, sigma.ctypes.data_as(_u32p), self.a, C.byref(h)), "pcgdo_memo_create")
+        self.h = h
+
+    def overlap(self, e1, e2):
+        """``getMedianAndCost2D`` over arrays of ambiguity sets: (median[uint32], cost[uint32])."""
+        e1 = np.ascontiguousarray(np.asarray(e1, np.uint32))
+        e2 = np.ascontiguousarray(np.asarray(e2, np.uint32))
+        assert e1.shape == e2.shape
+        med, cost = np.zeros(e1.size, np.uint32), np.zeros(e1.size, np.uint32)
+        self.ctx.check(self.ctx.lib.pcgdo_overlap2d_batch_host(self.ctx.h, self.h, e1.size, e1.ctypes.data, e2.ctypes.data,
+                                                               med.ctypes.data, cost.ctypes.data),
+                       "pcgdo_overlap2d_batch_host")
+        return med.reshape(e1.shape), cost.reshape(e1.shape)
+
+    def __del__(self):
+        try:
+            if self.h.value and self.ctx.h.value:
+                self.ctx.lib.pcgdo_memo_destroy(self.ctx.h, self.h)
         except Exception:
             pass
 

@@ -34,31 +34,9 @@ struct AffParams {
 uint32_t aff_words_for(uint32_t n1, uint32_t n2);
 cudaError_t launch_affine(const AffParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 }
+#include "do_metric.cuh"
+#include "do_explicit.h"
 namespace pcgdo {
-struct MetricBatchDev {
-    uint32_t        n_pairs;
-    const uint32_t *elems;
-    const uint64_t *off1, *off2;
-    const uint32_t *len1, *len2;
-    const uint64_t *out_off;
-    uint32_t       *out_med, *out_a1, *out_a2;
-    uint32_t       *out_len;
-    int32_t        *cost;
-    uint64_t       *cells;
-    int32_t        *final_offset;
-};
-struct MetricParams {
-    MetricBatchDev b;
-    int       a;
-    int       dialect;
-    uint32_t *arena;
-    uint32_t  arena_words;
-    uint32_t  seq_cap;
-    int       pairs_per_warp;
-    unsigned int *counter;
-    unsigned int *overflow_count;
-    uint32_t  k_four, k_minus1;
-};
 uint32_t metric_seq_cap(int max_len);
 uint32_t metric_words_for(uint32_t n1, uint32_t n2);
 cudaError_t launch_metric(const MetricParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
@@ -120,7 +98,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
                       &ctx->d_olen, &ctx->d_cost, &ctx->d_cells};
     for (DevBuf *b : bufs)
@@ -619,7 +597,8 @@ extern "C" int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int diale
     return PCGDO_OK;
 }
 
-extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b)
+template <class DeviceCall>
+static int batch32_host_impl(pcgdo_ctx *ctx, const pcgdo_batch32 *b, DeviceCall device_call)
 {
     if (!ctx || !b) return PCGDO_ERR_ARG;
     if (b->n_pairs == 0) return PCGDO_OK;
@@ -657,7 +636,7 @@ extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect
     d.cost = (int32_t *)ctx->d_cost.p;
     d.cells = b->cells ? (uint64_t *)ctx->d_cells.p : nullptr;
     d.final_offset = b->final_offset ? (int32_t *)((uint32_t *)ctx->d_olen.p + n) : nullptr;
-    if ((rc = pcgdo_metric_batch_device(ctx, alphabet, dialect, &d, st))) return rc;
+    if ((rc = device_call(&d, st))) return rc;
     CK(cudaMemcpyAsync(b->cost, d.cost, n * 4, cudaMemcpyDeviceToHost, st));
     if (b->out_len) CK(cudaMemcpyAsync(b->out_len, d.out_len, n * 4, cudaMemcpyDeviceToHost, st));
     if (b->final_offset) CK(cudaMemcpyAsync(b->final_offset, d.final_offset, n * 4, cudaMemcpyDeviceToHost, st));
@@ -667,6 +646,220 @@ extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect
     if (b->out_a2) CK(cudaMemcpyAsync(b->out_a2, d.out_a2, b->out_count * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PCGDO_OK;
+}
+
+extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b)
+{
+    return batch32_host_impl(ctx, b, [&](const pcgdo_batch32 *d, cudaStream_t st) {
+        return pcgdo_metric_batch_device(ctx, alphabet, dialect, d, st);
+    });
+}
+
+// --------------------------------------------------------------------------------------------- explicit matrices
+// (a = 2..32): the tcm-memo replacement.  sigma[s*a + j]: s = median symbol, j = input symbol
+// (costMatrix_2d.cpp:252-267 reads tcm[fixedSymbolIndex * alphabetSize + ambiguitySymbolIndex]).
+
+struct pcgdo_memo {
+    size_t a = 0;
+    uint32_t delta = 0;
+    std::vector<uint32_t> sigma;
+    void *d_sigma = nullptr;
+};
+
+static void host_overlap(const uint32_t *sg, size_t a, uint64_t x, uint64_t y, uint64_t *med, uint32_t *cost)
+{
+    uint32_t best = 0xffffffffu;
+    uint64_t bits = 0;
+    for (size_t s = 0; s < a; ++s) {
+        uint32_t dx = 0xffffffffu, dy = 0xffffffffu;
+        for (size_t j = 0; j < a; ++j) {
+            if ((x >> j) & 1) dx = std::min(dx, sg[s * a + j]);
+            if ((y >> j) & 1) dy = std::min(dy, sg[s * a + j]);
+        }
+        const uint32_t c = dx + dy;
+        if (c < best) { best = c; bits = (uint64_t)1 << s; }
+        else if (c == best) bits |= (uint64_t)1 << s;
+    }
+    *med = bits; *cost = best;
+}
+
+extern "C" int pcgdo_memo_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, pcgdo_memo **out)
+{
+    if (!ctx || !sigma || !out) return PCGDO_ERR_ARG;
+    if (a < 2 || a > 32) {
+        ctx->err = "explicit-matrix path: alphabet size must be 2..32";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    for (size_t i = 0; i < a * a; ++i)
+        if (sigma[i] > 2000u) {
+            ctx->err = "explicit-matrix path: symbol-change costs above 2000 do not fit the 16-bit device table";
+            return PCGDO_ERR_UNSUPPORTED;
+        }
+    CK(cudaSetDevice(ctx->device));
+    pcgdo_memo *m = new pcgdo_memo();
+    m->a = a;
+    m->sigma.assign(sigma, sigma + a * a);
+    // Ukkonen coefficient: cheapest indel of a single non-gap symbol (UnboxedUkkonenSwapping.hs:436-459) —
+    // setup-time table work on a*a numbers, like setUp2dCostMtx
+    uint32_t delta = 0xffffffffu;
+    const uint64_t gap = (uint64_t)1 << (a - 1);
+    for (size_t s = 0; s + 1 < a; ++s) {
+        uint64_t md; uint32_t c1, c2;
+        host_overlap(m->sigma.data(), a, (uint64_t)1 << s, gap, &md, &c1);
+        host_overlap(m->sigma.data(), a, gap, (uint64_t)1 << s, &md, &c2);
+        delta = std::min(delta, std::min(c1, c2));
+    }
+    m->delta = delta;
+    cudaError_t e = cudaMalloc(&m->d_sigma, a * a * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_sigma, m->sigma.data(), a * a * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("pcgdo_memo_create: ") + cudaGetErrorString(e);
+        delete m;
+        return PCGDO_ERR_CUDA;
+    }
+    *out = m;
+    return PCGDO_OK;
+}
+
+extern "C" void pcgdo_memo_destroy(pcgdo_ctx *ctx, pcgdo_memo *m)
+{
+    if (!m) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(m->d_sigma);
+    delete m;
+}
+
+extern "C" int pcgdo_overlap2d_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, size_t n, const uint32_t *e1,
+                                            const uint32_t *e2, uint32_t *median, uint32_t *cost, void *cuda_stream)
+{
+    if (!ctx || !memo || (n && (!e1 || !e2))) return PCGDO_ERR_ARG;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (n == 0) return PCGDO_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_overlap2d((const uint32_t *)memo->d_sigma, (int)memo->a, n, e1, e2, median, cost, ctx->sm_count, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    ctx->last_launches = 1;
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_overlap2d_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, size_t n, const uint32_t *e1,
+                                          const uint32_t *e2, uint32_t *median, uint32_t *cost)
+{
+    if (!ctx || !memo || (n && (!e1 || !e2))) return PCGDO_ERR_ARG;
+    if (n == 0) return PCGDO_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_elems, n * 8)) || (rc = pcgdo_ensure(ctx, ctx->d_og, n * 8))) return rc;
+    cudaStream_t st = ctx->stream;
+    uint32_t *d1 = (uint32_t *)ctx->d_elems.p, *d2 = d1 + n, *dm = (uint32_t *)ctx->d_og.p, *dc = dm + n;
+    CK(cudaMemcpyAsync(d1, e1, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, e2, n * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = pcgdo_overlap2d_batch_device(ctx, memo, n, d1, d2, dm, dc, st))) return rc;
+    if (median) CK(cudaMemcpyAsync(median, dm, n * 4, cudaMemcpyDeviceToHost, st));
+    if (cost) CK(cudaMemcpyAsync(cost, dc, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b,
+                                           void *cuda_stream)
+{
+    if (!ctx || !memo || !b) return PCGDO_ERR_ARG;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (b->n_pairs == 0) return PCGDO_OK;
+    if (dialect < 0 || dialect > 2) {
+        ctx->err = "explicit-matrix path: dialect must be 0..2";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost ||
+        ((b->out_med || b->out_a1 || b->out_a2) && !b->out_off)) {
+        ctx->err = "bad batch description";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const int a = (int)memo->a;
+    const uint32_t seq_cap = metric_seq_cap(ctx->max_len);
+    const uint32_t tab_entries = 1024;                     // 2 KB of shared memory per warp for small tables
+    const size_t sg_bytes = ((size_t)a * a * 4 + 15) & ~(size_t)15;
+    const size_t per_warp = 512 + (size_t)seq_cap + 2 * (size_t)tab_entries;
+    int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    while (warps > 1 && sg_bytes + (size_t)warps * per_warp > 227 * 1024) --warps;
+    const size_t smem = sg_bytes + (size_t)warps * per_warp;
+    if (smem > 227 * 1024) {
+        ctx->err = "max_len too large for the explicit-matrix kernel's staging window";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    size_t arena_words = ctx->arena_words;
+    if (!arena_words) {
+        const size_t per = metric_words_for((uint32_t)ctx->max_len, (uint32_t)ctx->max_len);
+        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 4096);
+    }
+    arena_words = (arena_words + 3) & ~(size_t)3;
+    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
+    size_t ts_words = explicit_scratch_words(ctx->max_len, a, (size_t)1 << 20);
+    ts_words = (ts_words + 3) & ~(size_t)3;
+    const int grid = ctx->sm_count;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->tscratch, (size_t)grid * warps * ts_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    ExplicitParams p{};
+    p.b.n_pairs = (uint32_t)b->n_pairs;
+    p.b.elems = b->elems;
+    p.b.off1 = b->off1; p.b.off2 = b->off2; p.b.len1 = b->len1; p.b.len2 = b->len2;
+    p.b.out_off = b->out_off;
+    p.b.out_med = b->out_med; p.b.out_a1 = b->out_a1; p.b.out_a2 = b->out_a2;
+    p.b.out_len = b->out_len;
+    p.b.cost = b->cost;
+    p.b.cells = b->cells;
+    p.b.final_offset = b->final_offset;
+    p.a = a;
+    p.dialect = dialect;
+    p.sigma = (const uint32_t *)memo->d_sigma;
+    p.delta = memo->delta;
+    p.arena = (uint32_t *)ctx->arena.p;
+    p.arena_words = (uint32_t)arena_words;
+    p.tscratch = (uint32_t *)ctx->tscratch.p;
+    p.tscratch_words = (uint32_t)ts_words;
+    p.seq_cap = seq_cap;
+    p.smem_tab_entries = tab_entries;
+    p.pairs_per_warp = ctx->pairs_per_warp;
+    p.counter = (unsigned int *)ctx->counters.p;
+    p.overflow_count = p.counter + 8;
+    p.k_four = 4u;
+    p.k_minus1 = 0xffffffffu;
+    p.k_one = 1u;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_explicit(p, grid, warps * 32, smem, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    ctx->last_launches = 1;
+    unsigned int h_over[2] = {0, 0};
+    CK(cudaMemcpyAsync(h_over, p.overflow_count, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_over[0]) {
+        char msg[260];
+        snprintf(msg, sizeof msg, "%u pair(s) exceed the explicit-matrix kernel's limits (band wider than 1023 diagonals, "
+                                  "strings longer than max_len=%d, or scratch beyond the arena); %u of them because a "
+                                  "folded cost does not fit 16 bits", h_over[0], ctx->max_len, h_over[1]);
+        ctx->err = msg;
+        return PCGDO_ERR_OVERFLOW;
+    }
+    return PCGDO_OK;
+}
+
+extern "C" int pcgdo_explicit_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b)
+{
+    return batch32_host_impl(ctx, b, [&](const pcgdo_batch32 *d, cudaStream_t st) {
+        return pcgdo_explicit_batch_device(ctx, memo, dialect, d, st);
+    });
 }
 
 extern "C" int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches)
@@ -875,6 +1068,16 @@ std::mutex g_mu;
 pcgdo_ctx *g_ctx = nullptr;
 std::unordered_map<const void *, pcgdo_tcm *> g_tcms;   // keyed by the caller's cost-table pointer
 
+pcgdo_ctx *shim_ctx()
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx && pcgdo_create(&g_ctx, 0) != PCGDO_OK) {
+        fprintf(stderr, "pcg_do_b200: cannot create a GPU context (no CPU fallback)\n");
+        abort();
+    }
+    return g_ctx;
+}
+
 [[noreturn]] void die(const char *what, const char *detail)
 {
     fprintf(stderr, "pcg_do_b200: %s: %s (no CPU fallback)\n", what, detail ? detail : "");
@@ -988,3 +1191,37 @@ extern "C" int align2dAffine(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, 
     }
     return cost;
 }
+
+// Reference-compatible tcm-memo entry points (lib/tcm-memo/ffi/memoized-tcm/costMatrixWrapper.h:12-31, bound at
+// lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:49-69).  One lookup per call through the GPU: correct, never fast —
+// the batched kernels above are the product; these keep the existing binding linkable against this library.
+extern "C" costMatrix_p matrixInit(size_t alphSize, unsigned int *tcm)
+{
+    pcgdo_ctx *ctx = shim_ctx();
+    pcgdo_memo *m = nullptr;
+    if (pcgdo_memo_create(ctx, tcm, alphSize, &m) != PCGDO_OK) {
+        fprintf(stderr, "pcg_do_b200: matrixInit: %s (no CPU fallback)\n", ctx->err.c_str());
+        abort();
+    }
+    return (costMatrix_p)m;
+}
+
+extern "C" void matrixDestroy(costMatrix_p untyped_ptr) { pcgdo_memo_destroy(shim_ctx(), (pcgdo_memo *)untyped_ptr); }
+
+extern "C" unsigned int getCostAndMedian2D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *retElem, costMatrix_p tcm)
+{
+    pcgdo_ctx *ctx = shim_ctx();
+    const pcgdo_memo *m = (const pcgdo_memo *)tcm;
+    uint32_t e1 = (uint32_t)elem1->element[0], e2 = (uint32_t)elem2->element[0], med = 0, cost = 0;
+    std::lock_guard<std::mutex> lock(g_mu);          // one context, shared staging buffers
+    if (pcgdo_overlap2d_batch_host(ctx, m, 1, &e1, &e2, &med, &cost) != PCGDO_OK) {
+        fprintf(stderr, "pcg_do_b200: getCostAndMedian2D: %s (no CPU fallback)\n", ctx->err.c_str());
+        abort();
+    }
+    // callee frees and re-allocates the median buffer (costMatrix_2d.cpp:156-166)
+    if (retElem->element != NULL) free(retElem->element);
+    retElem->element = (uint64_t *)calloc((m->a + 63) / 64, sizeof(uint64_t));
+    retElem->element[0] = med;
+    return cost;
+}
+

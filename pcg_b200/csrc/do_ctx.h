@@ -35,7 +35,7 @@ struct pcgdo_ctx {
     int max_b = 8;
     size_t arena_words = 0;          // 0 = derive from max_len
     // device scratch
-    DevBuf arena, counters, overflow, big, gen_scratch, gen_off;
+    DevBuf arena, counters, overflow, big, gen_scratch, gen_off, tscratch;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
     std::string err;

@@ -1,0 +1,549 @@
+// do_explicit.cu — the Haskell DO dialects over an EXPLICIT symbol-change matrix (alphabets of 9..32 symbols),
+// sm_100a.  Replaces, for this path, the memoized Sankoff lookups of lib/tcm-memo:
+//   getMedianAndCost2D      lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:97-112        (one FFI call per DP cell)
+//   CostMatrix_2d::getSetCostMedian / computeCostMedian / findDistance
+//                           lib/tcm-memo/ffi/memoized-tcm/costMatrix_2d.cpp:131-267   (hash map keyed on the pair)
+//   overlap / overlap2      lib/core/data-structures/src/Bio/Metadata/Overlap.hs:56-86, 136-142
+// and runs the same three dialects as do_metric.cu (S1 full, S1 Ukkonen, S2 Ukkonen; file references there).
+//
+// Memoization becomes a PER-PAIR DENSE TABLE: the distinct ambiguity sets of the two strings are numbered
+// (warp-parallel open-addressing hash), the Sankoff cost/median of every (distinct longer, distinct lesser)
+// combination is computed once — from per-element profiles m_x[s] = min_{j in x} sigma[s][j] — and stored as
+// the same folded int16 value the dense-table kernel uses, 4*(cost(x,y) - cost(x,gap) - cost(gap,y)) - 1 (+1 when
+// S2 and the median is exactly the gap).  The table sits in shared memory when it is small (single-symbol
+// strings over 21 amino acids: 22 x 22 entries) and in the warp's global scratch otherwise.  The fill is then
+// the dense-table recurrence: one address IMAD, one load, two VIADDMNMX, one LOP3, two IMAD per cell.
+// PARITY UNPINNED for the dialect logic (see do_metric.cu); the overlap itself is pinned against the compiled
+// reference tcm-memo (tests/golden/tcm_memo_golden.json).
+#include "do_metric.cuh"
+#include "do_explicit.h"
+
+namespace pcgdo {
+
+// Sankoff median / cost of two ambiguity sets straight from sigma (shared memory), costMatrix_2d.cpp:175-267.
+__device__ __forceinline__ void ov_explicit(const uint32_t *sg, int a, uint32_t x, uint32_t y, uint32_t &med, uint32_t &cost)
+{
+    uint32_t best = 0xffffffffu, bits = 0;
+    for (int s = 0; s < a; ++s) {
+        const uint32_t *row = sg + s * a;
+        uint32_t dx = 0xffffffffu, dy = 0xffffffffu;
+        for (uint32_t t = x; t; t &= t - 1) dx = min(dx, row[__ffs(t) - 1]);
+        for (uint32_t t = y; t; t &= t - 1) dy = min(dy, row[__ffs(t) - 1]);
+        const uint32_t c = dx + dy;                      // unsigned wrap for empty sets, as the reference
+        if (c < best) { best = c; bits = 1u << s; }
+        else if (c == best) bits |= 1u << s;
+    }
+    med = bits; cost = best;
+}
+
+__global__ void overlap2d_kernel(const uint32_t *sigma, int a, size_t n, const uint32_t *e1, const uint32_t *e2,
+                                 uint32_t *med, uint32_t *cost)
+{
+    __shared__ uint32_t sg[32 * 32];
+    for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = sigma[i];
+    __syncthreads();
+    const uint32_t mask = a >= 32 ? 0xffffffffu : ((1u << a) - 1u);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        uint32_t m, c;
+        ov_explicit(sg, a, e1[k] & mask, e2[k] & mask, m, c);
+        if (med) med[k] = m;
+        if (cost) cost[k] = c;
+    }
+}
+
+cudaError_t launch_overlap2d(const uint32_t *sigma, int a, size_t n, const uint32_t *e1, const uint32_t *e2,
+                             uint32_t *med, uint32_t *cost, int sm_count, cudaStream_t st)
+{
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
+    if (blocks == 0) blocks = 1;
+    overlap2d_kernel<<<(unsigned)blocks, 256, 0, st>>>(sigma, a, n, e1, e2, med, cost);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ fill
+__device__ __forceinline__ uint32_t x_lds_s16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t x_ldg_s16(const char *base, uint32_t off)
+{
+    uint32_t v;
+    asm("ld.global.s16 %0, [%1];" : "=r"(v) : "l"(base + off));
+    return v;
+}
+
+template <int B, bool GLOBAL, bool TAIL>
+__device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)[B], uint32_t (&dw)[B],
+                                        uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t k4, uint32_t km1,
+                                        uint32_t k1, const char *gtab, const uint32_t *&lptr, const uint32_t *&sptr,
+                                        int n_iter)
+{
+    constexpr int H = B / 2;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (TAIL && r >= n_iter) break;
+        const int tt = r % H;
+        const uint32_t wl = __shfl_up_sync(kFullM, w[B - 1], 1);
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            const int m = 2 * u;
+            const uint32_t left = (u == 0) ? wl : w[m > 0 ? m - 1 : 0];
+            const uint32_t ad = m_imad(lw[(tt - u + H) % H], k1, sw[(tt + u) % H]);
+            const uint32_t sub = GLOBAL ? x_ldg_s16(gtab, ad) : x_lds_s16(ad);
+            const uint32_t t1 = __viaddmin_u32(w[m], sub, w[m + 1]);
+            const uint32_t mn = __viaddmin_u32(left, 1u, t1);
+            const uint32_t wn = (mn & ~3u) | penc[m];
+            dw[m] = m_imad(wn, km1, m_imad(dw[m], k4, mn));
+            w[m] = wn;
+        }
+        sw[tt] = sptr[r];
+        const uint32_t wr = __shfl_down_sync(kFullM, w[0], 1);
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            const int m = 2 * u + 1;
+            const uint32_t up = (u == H - 1) ? wr : w[m + 1 < B ? m + 1 : B - 1];
+            const uint32_t ad = m_imad(lw[(tt - u + H) % H], k1, sw[(tt + u + 1) % H]);
+            const uint32_t sub = GLOBAL ? x_ldg_s16(gtab, ad) : x_lds_s16(ad);
+            const uint32_t t1 = __viaddmin_u32(w[m], sub, up);
+            const uint32_t mn = __viaddmin_u32(w[m - 1], 1u, t1);
+            const uint32_t wn = (mn & ~3u) | penc[m];
+            dw[m] = m_imad(wn, km1, m_imad(dw[m], k4, mn));
+            w[m] = wn;
+        }
+        lw[(tt + 1) % H] = lptr[r];
+    }
+    lptr += 16;
+    sptr += 16;
+}
+
+// Lb / Sb: staged row-offset / column-offset words, entry 0 = the leading gap.
+template <int B, bool GLOBAL>
+__device__ __noinline__ uint32_t x_fill(const MGeom g, uint32_t k4, uint32_t km1, uint32_t k1, const char *gtab,
+                                        const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot, int lane)
+{
+    constexpr int H = B / 2;
+    uint32_t w[B], penc[B], dw[B], lw[H], sw[H];
+    const int qb = lane * B;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int q = qb + m;
+        penc[m] = 1u | ((q < g.pad || q >= g.wb) ? 0x80000000u : 0u);
+        asm volatile("" : "+r"(penc[m]));
+        w[m] = (q == g.q0) ? (kBias4 + 1u) : kInfW;       // table entry of (leading gap, leading gap) is -1
+        dw[m] = 0;
+    }
+    const int I0 = g.q0 / 2 - lane * H, J0 = -(g.q0 / 2) + lane * H;
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        lw[(H - u) % H] = Lb[I0 - u];
+        sw[u] = Sb[J0 + u];
+    }
+    const uint32_t *lptr = Lb + (I0 + 1), *sptr = Sb + (J0 + H);
+    uint32_t *out = slot + qb;
+    const int nfull = g.T >> 4, rem = g.T & 15;
+    for (int c = 0; c < nfull; ++c) {
+        x_chunk<B, GLOBAL, false>(w, penc, dw, lw, sw, k4, km1, k1, gtab, lptr, sptr, 16);
+        m_store<B>(out, dw, 16);
+        out += 32 * B;
+    }
+    if (rem) {
+#pragma unroll
+        for (int m = 0; m < B; ++m) dw[m] = 0;
+        x_chunk<B, GLOBAL, true>(w, penc, dw, lw, sw, k4, km1, k1, gtab, lptr, sptr, rem);
+        m_store<B>(out, dw, rem);
+    }
+    const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0, m_last = q_last % B;
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < B; ++m)
+        if (m == m_last) v = w[m];
+    return __shfl_sync(kFullM, v, q_last / B);
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ uint32_t x_dispatch(int B, const MGeom &g, uint32_t k4, uint32_t km1, uint32_t k1,
+                                               const char *gtab, const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot,
+                                               int lane)
+{
+    switch (B) {
+        case 2:  return x_fill<2, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
+        case 4:  return x_fill<4, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
+        case 8:  return x_fill<8, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
+        case 16: return x_fill<16, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
+        default: return x_fill<32, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
+    }
+}
+
+__device__ __forceinline__ void x_emit(const uint32_t *sg, int a, const uint32_t *pL, const uint32_t *pS, uint32_t gap,
+                                       uint32_t mask, const uint32_t *ops, uint32_t nal, bool swapped, uint32_t *om,
+                                       uint32_t *o1, uint32_t *o2, int lane)
+{
+    uint32_t base_i = 0, base_j = 0;
+    for (uint32_t c0 = 0; c0 < nal; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        uint32_t code = 3u;
+        if (c < nal) {
+            const uint32_t r = nal - 1u - c;
+            code = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
+        }
+        const unsigned bl = __ballot_sync(kFullM, code < 2u), bs = __ballot_sync(kFullM, code == 0u || code == 2u);
+        const unsigned lt = (1u << lane) - 1u;
+        const uint32_t il = base_i + __popc(bl & lt), js = base_j + __popc(bs & lt);
+        if (c < nal) {
+            const uint32_t y = code < 2u ? (__ldg(pL + il) & mask) : 0u;
+            const uint32_t x = (code == 0u || code == 2u) ? (__ldg(pS + js) & mask) : 0u;
+            uint32_t md, cc;
+            ov_explicit(sg, a, x ? x : gap, y ? y : gap, md, cc);
+            if (om) om[c] = md;
+            if (o1) o1[c] = swapped ? y : x;
+            if (o2) o2[c] = swapped ? x : y;
+        }
+        base_i += __popc(bl);
+        base_j += __popc(bs);
+    }
+}
+
+__host__ __device__ inline uint32_t x_hash_size(uint32_t n)
+{
+    uint32_t h = 32;
+    while (h < 2u * n + 2u) h <<= 1;
+    return h;
+}
+__device__ __forceinline__ uint32_t x_hash(uint32_t e) { return (e * 0x9E3779B1u) >> 7; }
+
+// number the distinct elements of one string: idx[i] = 2 + rank of str[i] among the occupied hash slots
+// (0 is the padding entry, 1 the leading gap); elements with no bit set map to the padding entry.
+__device__ __forceinline__ uint32_t x_number(const uint32_t *str, int len, uint32_t mask, uint32_t H, uint32_t *hk,
+                                             uint32_t *hv, uint32_t *el, uint32_t *idx, int lane)
+{
+    for (uint32_t i = lane; i < H; i += 32) hk[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t e = __ldg(str + i) & mask;
+        if (!e) continue;
+        uint32_t h = x_hash(e) & (H - 1);
+        for (;;) {
+            const uint32_t old = atomicCAS(hk + h, 0u, e);
+            if (old == 0u || old == e) break;
+            h = (h + 1) & (H - 1);
+        }
+    }
+    __syncwarp();
+    uint32_t D = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < H; base += 32) {
+        const uint32_t k = __ldcg(hk + base + lane);       // written by atomics: bypass L1
+        const unsigned bal = __ballot_sync(kFullM, k != 0u);
+        if (k) {
+            const uint32_t r = D + __popc(bal & lt);
+            hv[base + lane] = r + 2u;
+            el[r] = k;
+        }
+        D += __popc(bal);
+    }
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t e = __ldg(str + i) & mask;
+        uint32_t v = 0;
+        if (e) {
+            uint32_t h = x_hash(e) & (H - 1);
+            while (__ldcg(hk + h) != e) h = (h + 1) & (H - 1);
+            v = hv[h];
+        }
+        idx[i] = v;
+    }
+    __syncwarp();
+    return D;
+}
+
+extern __shared__ __align__(16) char x_smem[];
+
+__global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParams p)
+{
+    const MetricBatchDev &b = p.b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int a = p.a;
+    uint32_t *sg = reinterpret_cast<uint32_t *>(x_smem);                       // sigma[a*a]
+    const uint32_t sg_bytes = ((uint32_t)(a * a) * 4u + 15u) & ~15u;
+    const uint32_t per_warp = 512u + p.seq_cap + 2u * p.smem_tab_entries;
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(x_smem + sg_bytes + (size_t)warp * per_warp);
+    uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64, *s_geo = s_meta + 96;
+    uint32_t *seq = s_meta + 128;
+    int16_t *stab = reinterpret_cast<int16_t *>(reinterpret_cast<char *>(seq) + p.seq_cap);
+    for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = p.sigma[i];
+    __syncthreads();
+
+    const uint32_t gap = 1u << (a - 1);
+    const uint32_t mask = a >= 32 ? 0xffffffffu : ((1u << a) - 1u);
+    const int G = p.pairs_per_warp;
+    const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
+    uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
+    uint32_t *ts = p.tscratch + warp_global * (size_t)p.tscratch_words;
+    const bool want_out = b.out_med || b.out_a1 || b.out_a2 || b.out_len;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
+        base = __shfl_sync(kFullM, base, 0);
+        if (base >= b.n_pairs) break;
+        const int npw = (int)min((uint32_t)G, b.n_pairs - base);
+        int pi = 0;
+        while (pi < npw) {
+            const int start = pi;
+            uint32_t cur = 0;
+            for (; pi < npw; ++pi) {
+                const uint32_t k = base + pi;
+                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                bool swapped = n1 > n2;                     // measureCharacters on the median strings
+                if (n1 == n2) {
+                    for (uint32_t bs = 0; bs < n1; bs += 32) {
+                        const uint32_t i = bs + lane;
+                        uint32_t x = 0, y = 0;
+                        if (i < n1) { x = __ldg(p1 + i); y = __ldg(p2 + i); }
+                        const unsigned df = __ballot_sync(kFullM, x != y);
+                        if (df) {
+                            const int src = __ffs(df) - 1;
+                            swapped = __shfl_sync(kFullM, x, src) > __shfl_sync(kFullM, y, src);
+                            break;
+                        }
+                    }
+                }
+                const uint32_t *pL = swapped ? p1 : p2, *pS = swapped ? p2 : p1;
+                const int n = (int)(swapped ? n1 : n2), m = (int)(swapped ? n2 : n1);     // longer, lesser
+                const int lg = n + 1, sh = m + 1;
+                uint32_t gcnt = 0;
+                for (int i = lane; i < n; i += 32) gcnt += (__ldg(pL + i) & gap) != 0u;
+                for (int j = lane; j < m; j += 32) gcnt += (__ldg(pS + j) & gap) != 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) gcnt += __shfl_xor_sync(kFullM, gcnt, d);
+                const long long Gc = gcnt, qd = n - m + 1, delta = p.delta;
+                bool no_gain = m <= 4 || 2 * n >= 3 * m || delta == 0;
+                if (p.dialect == 2) no_gain = no_gain || Gc >= n;
+                const bool full = p.dialect == 0 || no_gain;
+                const bool s2 = p.dialect == 2 && !no_gain;
+                long long off = p.dialect == 2 ? 2 + Gc : 2;
+
+                // ---------------- number the distinct elements, build profiles, indel costs and the pair's table
+                const uint32_t HL = x_hash_size((uint32_t)n), HS = x_hash_size((uint32_t)m);
+                uint32_t *hkL = ts, *hvL = hkL + HL, *hkS = hvL + HL, *hvS = hkS + HS;
+                uint32_t *elL = hvS + HS, *elS = elL + n, *idxL = elS + m, *idxS = idxL + n;
+                uint32_t *cL = idxS + m, *gS = cL + (n + 2);
+                uint32_t *mxL = gS + (m + 2), *mxS = mxL + (size_t)n * a;
+                uint32_t *tail = mxS + (size_t)m * a;
+                bool ok = (size_t)(tail - ts) <= p.tscratch_words;
+                uint32_t DL = 0, DS = 0, Wt = 0, entries = 0;
+                bool gtable = false;
+                const char *gtab = nullptr;
+                uint32_t tab32 = 0;
+                if (ok) {
+                    DL = x_number(pL, n, mask, HL, hkL, hvL, elL, idxL, lane);
+                    DS = x_number(pS, m, mask, HS, hkS, hvS, elS, idxS, lane);
+                    Wt = DS + 2u;
+                    entries = (DL + 2u) * Wt;
+                    gtable = entries > p.smem_tab_entries;
+                    if (gtable) ok = (size_t)(tail - ts) + (entries + 1u) / 2u <= p.tscratch_words && Wt * 2u * (DL + 2u) < 0x7fffffffu;
+                }
+                uint32_t bad = 0;
+                if (ok) {
+                    for (uint32_t t = lane; t < DL * (uint32_t)a; t += 32) {
+                        const uint32_t d = t / a, s = t - d * a;
+                        uint32_t mn = 0xffffffffu;
+                        for (uint32_t x = elL[d]; x; x &= x - 1) mn = min(mn, sg[s * a + __ffs(x) - 1]);
+                        mxL[t] = mn;
+                    }
+                    for (uint32_t t = lane; t < DS * (uint32_t)a; t += 32) {
+                        const uint32_t d = t / a, s = t - d * a;
+                        uint32_t mn = 0xffffffffu;
+                        for (uint32_t x = elS[d]; x; x &= x - 1) mn = min(mn, sg[s * a + __ffs(x) - 1]);
+                        mxS[t] = mn;
+                    }
+                    __syncwarp();
+                    for (uint32_t d = lane; d < DL + 2u; d += 32) {
+                        uint32_t c = 0;
+                        if (d >= 2u) {
+                            c = 0xffffffffu;
+                            for (int s = 0; s < a; ++s) c = min(c, mxL[(d - 2u) * a + s] + sg[s * a + a - 1]);
+                        }
+                        cL[d] = c;
+                    }
+                    for (uint32_t d = lane; d < DS + 2u; d += 32) {
+                        uint32_t c = 0;
+                        if (d >= 2u) {
+                            c = 0xffffffffu;
+                            for (int s = 0; s < a; ++s) c = min(c, mxS[(d - 2u) * a + s] + sg[s * a + a - 1]);
+                        }
+                        gS[d] = c;
+                    }
+                    __syncwarp();
+                    int16_t *tab = gtable ? reinterpret_cast<int16_t *>(tail) : stab;
+                    for (uint32_t t = lane; t < entries; t += 32) {
+                        const uint32_t dl = t / Wt, ds = t - dl * Wt;
+                        int v;
+                        if (dl == 0u || ds == 0u) v = kBigSub;
+                        else if (dl == 1u || ds == 1u) v = -1;
+                        else {
+                            const uint32_t *ml = mxL + (size_t)(dl - 2u) * a, *ms = mxS + (size_t)(ds - 2u) * a;
+                            uint32_t best = 0xffffffffu, bits = 0;
+                            for (int s = 0; s < a; ++s) {
+                                const uint32_t c = ml[s] + ms[s];
+                                if (c < best) { best = c; bits = 1u << s; }
+                                else if (c == best) bits |= 1u << s;
+                            }
+                            const long long f = 4ll * ((long long)best - (long long)cL[dl] - (long long)gS[ds]) - 1ll +
+                                                ((s2 && bits == gap) ? 1ll : 0ll);
+                            if (f < -32000ll || f >= (long long)kBigSub) bad = 1;
+                            v = (int)f;
+                        }
+                        tab[t] = (int16_t)v;
+                    }
+                    bad = __any_sync(kFullM, bad != 0u) ? 1u : 0u;
+                    if (bad) ok = false;
+                    gtab = reinterpret_cast<const char *>(tail);
+                    tab32 = (uint32_t)__cvta_generic_to_shared(stab);
+                    __syncwarp();
+                }
+
+                const MGeom gfull = make_mgeom(lg, sh, -(lg - 1), sh - 1);
+                uint32_t fw = 0, csum = 0;
+                MGeom g = gfull;
+                int B = m_choose_b(gfull.wb);
+                uint32_t need = 0;
+                int final_off = -1;
+                while (ok) {
+                    if (!full) {
+                        const int a_off = (int)(off < m ? off : m);
+                        g = make_mgeom(lg, sh, -(n - m) - a_off, a_off);
+                        B = m_choose_b(g.wb);
+                        final_off = (int)(off > 0x7fffffff ? 0x7fffffff : off);
+                    }
+                    MSeq sl = {0, 0, 0, 0};
+                    ok = B != 0;
+                    if (ok) {
+                        sl = m_seq_layout(g, B);
+                        need = (m_dir_words(g, B) + m_ops_words(lg, sh) + 3u) & ~3u;
+                        ok = 4u * (uint32_t)(sl.sizeL + sl.sizeS) <= p.seq_cap && need <= p.arena_words;
+                    }
+                    if (!ok) break;
+                    if (cur + need > p.arena_words) break;
+                    // stage row offsets (bytes into the table) and column offsets (+ the table's shared address)
+                    uint32_t *Sr = seq, *Lr = seq + sl.sizeS;
+                    csum = 0;
+                    const uint32_t rowb = Wt * 2u, sbase = gtable ? 0u : tab32;
+                    for (int idx = lane; idx < sl.sizeL; idx += 32) {
+                        const int i = idx - sl.offL;
+                        uint32_t d = 0;
+                        if (i == 0) d = 1;
+                        else if (i > 0 && i < lg) { d = idxL[i - 1]; csum += cL[d]; }
+                        Lr[idx] = d * rowb;
+                    }
+                    for (int idx = lane; idx < sl.sizeS; idx += 32) {
+                        const int j = idx - sl.offS;
+                        uint32_t d = 0;
+                        if (j == 0) d = 1;
+                        else if (j > 0 && j < sh) { d = idxS[j - 1]; csum += gS[d]; }
+                        Sr[idx] = d * 2u + sbase;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFullM, csum, d);
+                    __syncwarp();
+                    uint32_t *slot = arena + cur;
+                    if (gtable) fw = x_dispatch<true>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
+                    else        fw = x_dispatch<false>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
+                    __syncwarp();
+                    if (full) break;
+                    const long long cost = (long long)((fw >> 2) - (kBias4 >> 2) + csum);
+                    if (p.dialect == 2) {
+                        if (qd + off > n) break;
+                        const long long thr = (qd + off <= Gc) ? 0 : delta * (qd + off - Gc);
+                        if (thr <= cost) off *= 2; else break;
+                    } else {
+                        long long thr = delta * (qd + off - Gc);
+                        if (thr < 0) thr = 0;
+                        if (thr <= cost) off *= 2; else break;
+                    }
+                }
+                if (!ok) {
+                    if (lane == 0) { s_flags[pi] = 0; atomicAdd(p.overflow_count, 1u); if (bad) atomicAdd(p.overflow_count + 1, 1u); }
+                    continue;
+                }
+                if (cur + need > p.arena_words) break;       // flush what we have, then redo this pair
+                if (lane == 0) {
+                    s_flags[pi] = (swapped ? 1u : 0u) | 2u;
+                    s_off[pi] = cur;
+                    s_geo[pi] = (uint32_t)(uint16_t)(int16_t)g.dlo | ((uint32_t)(uint16_t)(int16_t)g.dhi << 16);
+                    b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
+                    if (b.final_offset) b.final_offset[k] = final_off;
+                }
+                if (b.cells) {
+                    unsigned long long c = m_band_cells(g, lane, 32);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFullM, c, d);
+                    if (lane == 0) b.cells[k] = c;
+                }
+                cur += need;
+                __syncwarp();
+            }
+            __syncwarp();
+            if (!want_out) continue;
+            const int pj = start + lane;
+            if (pj < pi && (s_flags[pj] & 2u)) {
+                const uint32_t k = base + pj;
+                const bool swapped = s_flags[pj] & 1u;
+                const int n = (int)(swapped ? b.len1[k] : b.len2[k]), m = (int)(swapped ? b.len2[k] : b.len1[k]);
+                const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pj] & 0xffffu), (int)(int16_t)(s_geo[pj] >> 16));
+                const int B = m_choose_b(g.wb);
+                uint32_t *slot = arena + s_off[pj];
+                const uint32_t na = m_trace(slot, 32u * B, g.q0, g.lg, g.sh, slot + m_dir_words(g, B));
+                s_nal[pj] = na;
+                if (b.out_len) b.out_len[k] = na;
+            }
+            __syncwarp();
+            if (b.out_med || b.out_a1 || b.out_a2) {
+                for (int pe = start; pe < pi; ++pe) {
+                    if (!(s_flags[pe] & 2u)) continue;
+                    const uint32_t k = base + pe;
+                    const bool swapped = s_flags[pe] & 1u;
+                    const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                    const int n = (int)(swapped ? b.len1[k] : b.len2[k]), m = (int)(swapped ? b.len2[k] : b.len1[k]);
+                    const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pe] & 0xffffu), (int)(int16_t)(s_geo[pe] >> 16));
+                    const int B = m_choose_b(g.wb);
+                    const uint32_t *ops = arena + s_off[pe] + m_dir_words(g, B);
+                    const uint64_t oo = b.out_off[k];
+                    x_emit(sg, a, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe], swapped,
+                           b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
+                           b.out_a2 ? b.out_a2 + oo : nullptr, lane);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// per-warp global scratch (32-bit words) for strings of up to max_len elements over `a` symbols:
+// two hash tables, distinct elements, indices, indel costs, profiles, and the table itself (capped)
+size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries)
+{
+    const size_t n = (size_t)max_len;
+    const size_t H = x_hash_size((uint32_t)max_len);
+    size_t entries = (n + 2) * (n + 2);
+    if (entries > table_cap_entries) entries = table_cap_entries;
+    return 4 * H + 4 * n + 2 * (n + 2) + 2 * n * (size_t)a + (entries + 1) / 2 + 16;
+}
+
+cudaError_t launch_explicit(const ExplicitParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(do_explicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    do_explicit_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace pcgdo

@@ -1,0 +1,30 @@
+// do_explicit.h — internal: launch parameters of the explicit-matrix large-alphabet kernel (do_explicit.cu).
+#pragma once
+#include "do_metric.cuh"
+
+namespace pcgdo {
+
+struct ExplicitParams {
+    MetricBatchDev b;
+    int       a;              // alphabet size (incl. gap), <= 32
+    int       dialect;        // 0 S1 full, 1 S1 Ukkonen, 2 S2 Ukkonen
+    const uint32_t *sigma;    // device [a*a]: sigma[s*a + j], s = median symbol, j = input symbol
+    uint32_t  delta;          // cheapest indel of a single non-gap symbol (Ukkonen coefficient)
+    uint32_t *arena;          // per warp: direction words + op streams
+    uint32_t  arena_words;
+    uint32_t *tscratch;       // per warp: hash tables, distinct elements, profiles, the pair's table
+    uint32_t  tscratch_words;
+    uint32_t  seq_cap;        // bytes of staging per warp
+    uint32_t  smem_tab_entries;   // int16 entries of shared memory per warp for small tables
+    int       pairs_per_warp;
+    unsigned int *counter;
+    unsigned int *overflow_count;
+    uint32_t  k_four, k_minus1, k_one;
+};
+
+size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries);
+cudaError_t launch_explicit(const ExplicitParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_overlap2d(const uint32_t *sigma, int a, size_t n, const uint32_t *e1, const uint32_t *e2,
+                             uint32_t *med, uint32_t *cost, int sm_count, cudaStream_t st);
+
+}  // namespace pcgdo

@@ -246,10 +246,12 @@ class MetricResult:
         return int(self.cost[k]), self.median[o:o + n], self.a1[o:o + n], self.a2[o:o + n]
 
 
-def metric_do_batch(ctx: Context, alphabet: int, dialect: int, first: Sequence[np.ndarray],
+def metric_do_batch(ctx: Context, alphabet, dialect: int, first: Sequence[np.ndarray],
                     second: Sequence[np.ndarray]) -> MetricResult:
-    """``naiveDO`` / ``ukkonenDO`` / ``unboxedUkkonenFullSpaceDO`` with the discrete metric on median strings
-    (uint32 ambiguity sets), one launch for the whole batch."""
+    """``naiveDO`` / ``ukkonenDO`` / ``unboxedUkkonenFullSpaceDO`` on median strings (uint32 ambiguity sets), one
+    launch for the whole batch.  ``alphabet``: an int selects the discrete metric over that many symbols
+    (``discreteMetricPairwiseLogic``); a ``Memo`` selects its explicit matrix (the reference's memoized
+    ``getMedianAndCost2D`` path, ``extractPairwiseTransitionCostMatrix``, Bio/Metadata/Dynamic/Internal.hs:352-374)."""
     n = len(first)
     len1 = np.fromiter((len(x) for x in first), dtype=np.uint32, count=n)
     len2 = np.fromiter((len(x) for x in second), dtype=np.uint32, count=n)
@@ -270,5 +272,8 @@ def metric_do_batch(ctx: Context, alphabet: int, dialect: int, first: Sequence[n
     fo = np.zeros(n, np.int32)
     b = Batch32(n, _p(elems), elems.size, _p(off1), _p(off2), _p(len1), _p(len2), _p(out_off), cnt,
                 _p(med), _p(a1), _p(a2), _p(out_len), _p(cost), _p(cells), _p(fo))
-    ctx.check(ctx.lib.pcgdo_metric_batch_host(ctx.h, alphabet, dialect, C.byref(b)), "pcgdo_metric_batch_host")
+    if isinstance(alphabet, int):
+        ctx.check(ctx.lib.pcgdo_metric_batch_host(ctx.h, alphabet, dialect, C.byref(b)), "pcgdo_metric_batch_host")
+    else:
+        ctx.check(ctx.lib.pcgdo_explicit_batch_host(ctx.h, alphabet.h, dialect, C.byref(b)), "pcgdo_explicit_batch_host")
     return MetricResult(cost, out_len, med, a1, a2, cells, fo, out_off)

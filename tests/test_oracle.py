@@ -124,3 +124,31 @@ def test_oracle_reproduces_bench_strings_golden(oracle_mod, tcm_file):
         a, b = (enc[i], enc[j]) if len(enc[i]) >= len(enc[j]) else (enc[j], enc[i])
         oc = o.align2d(a, b)
         assert (oc[0], len(oc[1]), crc_u8(oc[1]), crc_u8(oc[2]), crc_u8(oc[3])) == (cost, n, cg, c1, c2), (i, j)
+
+
+def _memo_golden():
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tcm_memo_golden.json")))
+
+
+@pytest.mark.parametrize("name", ["bench/strings/protein/protein-pref-gap.tcm", "bench/strings/protein/protein-pref-sub.tcm",
+                                  "bench/strings/protein/protein-L1-norm.tcm", "bench/strings/dna/dna-pref-gap.tcm",
+                                  "random-asymmetric-12"])
+def test_oracle_overlap_reproduces_tcm_memo_golden(oracle_mod, name):
+    """The explicit-matrix overlap of the restatement against lookups answered by the compiled reference
+    tcm-memo (getCostAndMedian2D); fixture made by tests/golden/make_tcm_memo_golden.py."""
+    g = _memo_golden()[name]
+    sg = np.array(g["sigma"], np.uint32)
+    for x, y, med, cost in g["lookups"]:
+        assert oracle_mod.overlap(sg.shape[0], x, y, sg) == (med, cost), (x, y)
+
+
+def test_oracle_overlap_matches_live_tcm_memo(oracle_mod):
+    if not oracle_mod.ReferenceMemo.available():
+        pytest.skip("compiled reference tcm-memo not present")
+    rng = np.random.default_rng(77)
+    for a in (9, 21, 32):
+        sg = rng.integers(0, 12, size=(a, a)).astype(np.uint32)
+        ref = oracle_mod.ReferenceMemo(sg)
+        for _ in range(300):
+            x, y = int(rng.integers(1, 1 << a)), int(rng.integers(1, 1 << a))
+            assert oracle_mod.overlap(a, x, y, sg) == ref.overlap(x, y), (a, x, y)
