@@ -271,3 +271,104 @@ int cpu_bench_postorder(const char *ref_so, const uint32_t *sigma, int a, uint32
     if (port) oracle_tcm_free(port);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Large-alphabet dialects (BASELINE config 4 baseline).  The reference runs these in Haskell
+ * (unboxedUkkonenFullSpaceDO); no GHC here, so the timed code is the restatement in do_oracle.c ("port").
+ * memo_so != NULL: every per-cell overlap goes through the UNMODIFIED compiled reference tcm-memo
+ * (getCostAndMedian2D with freshly malloc'ed dcElement_t buffers per call, as
+ * lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:97-112 does) — one memo matrix per thread, because the reference's
+ * unordered_map is not thread-safe.  memo_so == NULL: metric_kind 0 (discrete closed form) or 1 (direct Sankoff).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { size_t alphSize; uint64_t *element; } dce_t;
+typedef void *(*minit_fn)(size_t, unsigned int *);
+typedef unsigned int (*mget_fn)(dce_t *, dce_t *, dce_t *, void *);
+
+typedef struct { mget_fn get; void *matrix; size_t a; uint64_t lookups; } memo_ctx_t;
+
+static uint64_t memo_lookup(void *vctx, uint32_t x, uint32_t y, uint32_t *med)
+{
+    memo_ctx_t *c = vctx;
+    dce_t e1 = { c->a, calloc(1, 8) }, e2 = { c->a, calloc(1, 8) }, r = { c->a, calloc(1, 8) };
+    e1.element[0] = x; e2.element[0] = y;
+    const unsigned int cost = c->get(&e1, &e2, &r, c->matrix);
+    *med = (uint32_t)r.element[0];
+    free(e1.element); free(e2.element); free(r.element);
+    c->lookups++;
+    return cost;
+}
+
+typedef struct {
+    int tid, threads, dialect, metric_kind, a;
+    const uint32_t *sigma;
+    size_t n;
+    const uint32_t *elems;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    int32_t *cost;
+    uint64_t *cells;
+    memo_ctx_t *memo;      /* per thread, or NULL */
+} hs_job_t;
+
+static void *hs_worker(void *arg)
+{
+    hs_job_t *j = arg;
+    for (size_t k = j->tid; k < j->n; k += j->threads) {
+        const uint32_t *s1 = j->elems + j->off1[k], *s2 = j->elems + j->off2[k];
+        const size_t n1 = j->len1[k], n2 = j->len2[k], cap = n1 + n2 + 2;
+        uint32_t *buf = malloc(sizeof(uint32_t) * 3 * cap);
+        size_t nal = 0;
+        uint64_t c = 0;
+        int off = 0;
+        if (j->memo)
+            j->cost[k] = (int32_t)oracle_haskell_do_lookup(j->dialect, memo_lookup, j->memo, j->a, s1, n1, s2, n2,
+                                                           buf, buf + cap, buf + 2 * cap, &nal, &c, &off);
+        else
+            j->cost[k] = (int32_t)oracle_haskell_do(j->dialect, j->metric_kind, j->sigma, j->a, s1, n1, s2, n2,
+                                                    buf, buf + cap, buf + 2 * cap, &nal, &c, &off);
+        if (j->cells) j->cells[k] = c;
+        free(buf);
+    }
+    return NULL;
+}
+
+int cpu_bench_haskell(const char *memo_so, int dialect, int metric_kind, const uint32_t *sigma, int a,
+                      const uint32_t *elems, const uint64_t *off1, const uint32_t *len1,
+                      const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                      int32_t *cost, uint64_t *cells, double *seconds, uint64_t *lookups)
+{
+    if (threads < 1) threads = 1;
+    memo_ctx_t *memos = NULL;
+    if (memo_so) {
+        void *h = dlopen(memo_so, RTLD_NOW | RTLD_LOCAL);
+        if (!h) return 1;
+        minit_fn init = (minit_fn)dlsym(h, "matrixInit");
+        mget_fn get = (mget_fn)dlsym(h, "getCostAndMedian2D");
+        if (!init || !get) return 2;
+        memos = calloc(threads, sizeof(memo_ctx_t));
+        for (int t = 0; t < threads; t++) {
+            unsigned int *sg = malloc(sizeof(unsigned int) * a * a);
+            memcpy(sg, sigma, sizeof(unsigned int) * a * a);
+            memos[t] = (memo_ctx_t){ get, init((size_t)a, sg), (size_t)a, 0 };
+            free(sg);
+        }
+    }
+    pthread_t *th = malloc(sizeof(pthread_t) * threads);
+    hs_job_t *jobs = malloc(sizeof(hs_job_t) * threads);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (hs_job_t){ t, threads, dialect, metric_kind, a, sigma, n, elems, off1, off2, len1, len2, cost, cells,
+                              memos ? &memos[t] : NULL };
+        pthread_create(&th[t], NULL, hs_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    if (lookups) {
+        *lookups = 0;
+        for (int t = 0; memos && t < threads; t++) *lookups += memos[t].lookups;
+    }
+    free(th); free(jobs); free(memos);     /* the memo matrices are leaked, like the reference does */
+    return 0;
+}

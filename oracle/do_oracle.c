@@ -508,9 +508,11 @@ int64_t oracle_align2d_affine(const oracle_tcm_t *t, int variant,
  * Rows i = 0..m follow the lesser string, columns j = 0..n the longer one, exactly as in the Haskell.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
-    int kind;                /* 0 discrete metric, 1 explicit symbol-change matrix */
+    int kind;                /* 0 discrete metric, 1 explicit symbol-change matrix, 2 external lookup (compiled tcm-memo) */
     int a;
     const uint32_t *sigma;   /* a*a, indexed [median symbol][input symbol] (Overlap.hs:75-86) */
+    oracle_lookup_fn lookup; /* kind 2 */
+    void *lookup_ctx;
 } hs_metric_t;
 
 static void hs_overlap(const hs_metric_t *mt, uint32_t x, uint32_t y, uint32_t *med, uint64_t *cost)
@@ -519,6 +521,7 @@ static void hs_overlap(const hs_metric_t *mt, uint32_t x, uint32_t y, uint32_t *
         if (x & y) { *med = x & y; *cost = 0; } else { *med = x | y; *cost = 1; }
         return;
     }
+    if (mt->kind == 2) { *cost = mt->lookup(mt->lookup_ctx, x, y, med); return; }
     uint64_t best = UINT64_MAX;
     uint32_t bits = 0;
     for (int s = mt->a - 1; s >= 0; s--) {                   /* overlap: every symbol attaining the minimum */
@@ -539,7 +542,7 @@ static void hs_overlap(const hs_metric_t *mt, uint32_t x, uint32_t y, uint32_t *
  * PINNED against the compiled reference tcm-memo (tests/golden/tcm_memo_golden.json, tests/test_oracle.py). */
 uint64_t oracle_overlap(int metric_kind, const uint32_t *sigma, int a, uint32_t x, uint32_t y, uint32_t *med)
 {
-    const hs_metric_t mt = { metric_kind, a, sigma };
+    const hs_metric_t mt = { metric_kind, a, sigma, NULL, NULL };
     uint64_t c;
     hs_overlap(&mt, x, y, med, &c);
     return c;
@@ -589,12 +592,35 @@ static uint64_t hs_fill(const hs_metric_t *mt, int s2, const uint32_t *les, size
 /* dialect: 0 S1 full (naiveDO / naiveDOMemo / unboxedSwappingDO), 1 S1 Ukkonen (ukkonenDO),
  *          2 S2 Ukkonen (unboxedUkkonenFullSpaceDO).  in1 / in2: median strings (no gap-only elements).
  * Outputs (length *out_len): median, aligned first input, aligned second input (0 = gap). */
+static int64_t hs_do(const hs_metric_t mt, int dialect, int a,
+                     const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                     uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                     uint64_t *cells, int *final_offset);
+
 int64_t oracle_haskell_do(int dialect, int metric_kind, const uint32_t *sigma, int a,
                           const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
                           uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
                           uint64_t *cells, int *final_offset)
 {
-    const hs_metric_t mt = { metric_kind, a, sigma };
+    const hs_metric_t mt = { metric_kind, a, sigma, NULL, NULL };
+    return hs_do(mt, dialect, a, in1, n1, in2, n2, out_med, out_a1, out_a2, out_len, cells, final_offset);
+}
+
+/* the same dialects with every overlap answered by an external lookup (bench: the compiled reference tcm-memo) */
+int64_t oracle_haskell_do_lookup(int dialect, oracle_lookup_fn lookup, void *lookup_ctx, int a,
+                                 const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                                 uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                                 uint64_t *cells, int *final_offset)
+{
+    const hs_metric_t mt = { 2, a, NULL, lookup, lookup_ctx };
+    return hs_do(mt, dialect, a, in1, n1, in2, n2, out_med, out_a1, out_a2, out_len, cells, final_offset);
+}
+
+static int64_t hs_do(const hs_metric_t mt, int dialect, int a,
+                     const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                     uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                     uint64_t *cells, int *final_offset)
+{
     const uint32_t gap = 1u << (a - 1);
     /* measureCharacters on median strings: shorter first, then lexicographic; equal -> not swapped */
     int swapped = 0;

@@ -94,6 +94,13 @@ int64_t oracle_haskell_do(int dialect, int metric_kind, const uint32_t *sigma, i
                           uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
                           uint64_t *cells, int *final_offset);
 
+/* the same with every overlap answered by `lookup` (returns the cost, writes the median) */
+typedef uint64_t (*oracle_lookup_fn)(void *ctx, uint32_t x, uint32_t y, uint32_t *med);
+int64_t oracle_haskell_do_lookup(int dialect, oracle_lookup_fn lookup, void *lookup_ctx, int a,
+                                 const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                                 uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                                 uint64_t *cells, int *final_offset);
+
 /* One overlap lookup: Sankoff median / cost of two ambiguity sets (metric_kind 0 discrete, 1 explicit sigma[a*a],
  * sigma[s*a + j] = median symbol s vs input symbol j).  Explicit branch pinned against the compiled tcm-memo. */
 uint64_t oracle_overlap(int metric_kind, const uint32_t *sigma, int a, uint32_t x, uint32_t y, uint32_t *med);

@@ -346,3 +346,34 @@ def cpu_bench_postorder(sigma, children, n_taxa, n_chars, leaf_elems, leaf_off, 
     if rc:
         raise RuntimeError(f"cpu_bench_postorder failed: {rc}")
     return float(sec.value), cost, cells
+
+
+def cpu_bench_haskell(dialect: int, a: int, elems, off1, len1, off2, len2, threads: int, sigma=None,
+                      through_reference_memo: bool = False):
+    """Time the restated Haskell dialect on `threads` host threads (elems: uint32 ambiguity sets).
+    sigma=None -> discrete metric; through_reference_memo -> every overlap answered by the compiled reference
+    tcm-memo.  Returns (seconds, cost[int32], cells[uint64], memo lookups)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.cpu_bench_haskell.restype = C.c_int
+    lib.cpu_bench_haskell.argtypes = [C.c_char_p, C.c_int, C.c_int, _u32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    n = len(len1)
+    sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
+    cost = np.zeros(n, np.int32)
+    cells = np.zeros(n, np.uint64)
+    sec = C.c_double(0)
+    lk = C.c_uint64(0)
+    so = None
+    if through_reference_memo:
+        if not os.path.exists(REF_MEMO_SO):
+            raise FileNotFoundError(REF_MEMO_SO)
+        so = REF_MEMO_SO.encode()
+    rc = lib.cpu_bench_haskell(so, dialect, 0 if sigma is None else 1, _ptr(sg), a, elems.ctypes.data, off1.ctypes.data,
+                               len1.ctypes.data, off2.ctypes.data, len2.ctypes.data, n, threads, cost.ctypes.data,
+                               cells.ctypes.data, C.byref(sec), C.byref(lk))
+    if rc:
+        raise RuntimeError(f"cpu_bench_haskell failed: {rc}")
+    return float(sec.value), cost, cells, int(lk.value)
