@@ -222,6 +222,21 @@ static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, cons
     t->dev.gap = gap;
     t->dev.sub4_bytes = (uint32_t)(tab.size() * 2);
     t->dev.sub4_gapgap = (int32_t)(4 * (C(gap, gap) - C(gap, gap) - C(gap, gap)) - 1);
+    {
+        // packed 16-bit fill: finite cell values are re-based every 32 iterations so that their maximum returns to
+        // kTop16 = 0x7000; in between a value falls at most 64 * s_minus and rises at most 64 * s_plus
+        long long lo = -1, hi = -1;                       // the leading-gap entries are -1
+        for (size_t l = 1; l < dim; ++l)
+            for (size_t sx = 1; sx < dim; ++sx) {
+                const long long v = nat[l * rdim + sx];
+                lo = std::min(lo, v); hi = std::max(hi, v);
+            }
+        const long long s_minus = 1 - lo, s_plus = std::max(0ll, hi) + 2;
+        const long long spread = 0x7000 - 64 * s_minus - 64;
+        t->dev.pack_ok = (0x7000 + 64 * s_plus < 0x7800 && spread >= 8192) ? 1 : 0;
+        t->dev.spread16 = t->dev.pack_ok ? (uint32_t)spread : 0u;
+        if (getenv("PCGDO_NO_PACK16")) t->dev.pack_ok = 0;
+    }
     t->dev.sub4 = (const int16_t *)t->d_sub4;
     t->dev.sub4_nat = (const int16_t *)t->d_sub4_nat;
     t->dev.median = (const uint8_t *)t->d_median;
@@ -329,6 +344,7 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     p.k_four = 4u;
     p.k_minus1 = 0xffffffffu;
     p.l_stride = tcm->dev.repl ? 2048u : (2u << tcm->a);
+    p.k_64k = 65536u;
 
     p.seq_cap = cap_n;
     CK(launch_linear(p, false, grid, warps_n * 32, smem_for(tcm, warps_n, cap_n), st));

@@ -21,6 +21,11 @@ struct TcmDev {
     const uint8_t *median;     // [dim*dim]
     const uint32_t *cgap;      // [dim] cost[x][gap]   (indel of consuming x from the longer string)
     const uint32_t *gapc;      // [dim] cost[gap][y]
+    // packed 16-bit fill (two diagonals per register, VIADDMNMX.U16x2): usable when every finite table entry lies
+    // in [-s_minus, s_plus] with the margins do_linear.cu's rebase16 needs; spread16 = largest max - min of the
+    // finite cell values of one anti-diagonal sweep that the 15-bit window can hold
+    int            pack_ok;
+    uint32_t       spread16;
 };
 
 struct BatchDev {
@@ -55,7 +60,7 @@ struct LinearParams {
     uint32_t     *big_list;        //   queued by the narrow kernel, consumed by the wide one
     // run-time "constants" (1, 4, -1, table row stride) kept opaque to ptxas so that the table-address add
     // and the direction accumulation are emitted as IMAD (FMA pipe) instead of IADD3/LEA/SHF (ALU pipe)
-    uint32_t  k_four, k_minus1, l_stride;
+    uint32_t  k_four, k_minus1, l_stride, k_64k;
 };
 
 // Geometry of one pair, identical on host and device (plain IEEE double multiplies only).

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t lds_s16(uint32_t saddr)
     asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-struct FillConst { uint32_t k4, km1, lstride; };
+struct FillConst { uint32_t k4, km1, lstride, k64k; };
 
 // Smallest supported diagonals-per-lane for a band of `wb` diagonals (0 = does not fit a warp).
 __host__ __device__ inline int choose_b(int wb)
@@ -203,6 +203,215 @@ __device__ __noinline__ uint32_t fill_pair(const Geom g, const FillConst fc, uin
     return __shfl_sync(kFull, v, q_last / B);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// packed fill: two diagonals per 32-bit register, VIADDMNMX.U16x2
+//
+// Register R[m] (m < H = B/2) holds diagonal m of the lane in its low half and diagonal m + H in its high half
+// (same parity, H even), each as a 16-bit cell value 4*(v - C(i) - G(j)) + base | code with bit 15 = unreachable.
+// One packed update = two cells: two table fetches merged by one IMAD, two VIADDMNMX.U16x2, one LOP3 to
+// re-normalise, one LOP3 + one IMAD to append both 2-bit choices to a packed direction word — 10 instructions
+// for 2 cells instead of 14.  Neighbours of a packed pair are the adjacent registers; only the lane edges need
+// a shuffle plus a funnel shift.  The 15-bit window follows the values: every 32 iterations the warp's finite
+// maximum is moved back to kTop16 (rebase16); if the finite spread of the sweep ever exceeds what the window
+// holds, the pair is redone by the 32-bit fill (never silently wrong).
+// Direction words: word[(t >> 3) * 32*H + lane*H + m], cell t of diagonal m (m + H) at bits 2*(7 - (t & 7))
+// of the low (high) half.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kTop16 = 0x7000u;
+constexpr uint32_t kOverflow16 = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+template <int H>
+__device__ __forceinline__ void store_words16(uint32_t *dst, const uint32_t (&dw)[H], int n)
+{
+    const int sh = 2 * (8 - n);           // left-align a partial group; the halves cannot collide (2n + sh = 16)
+    if constexpr (H >= 4) {
+#pragma unroll
+        for (int m = 0; m < H; m += 4)
+            *reinterpret_cast<uint4 *>(dst + m) = make_uint4(dw[m] << sh, dw[m + 1] << sh, dw[m + 2] << sh, dw[m + 3] << sh);
+    } else {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(dw[0] << sh, dw[1] << sh);
+    }
+}
+
+template <int B, bool TAIL>
+__device__ __forceinline__ void run_chunk16(uint32_t (&R)[B / 2], const uint32_t (&penc)[B / 2], uint32_t (&dw)[B / 2],
+                                            uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], const FillConst fc,
+                                            uint32_t tab_lane, const char *&lptr, const char *&sptr, int n_iter,
+                                            uint32_t *&out)
+{
+    constexpr int H = B / 2, Q = H / 2;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (TAIL && r >= n_iter) break;
+        const int tt = r % H;
+        // ---- even diagonals (registers with even m): anti-diagonal s = 2t
+        const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
+        const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);      // (own diag H-1) << 16 | (left lane's diag B-1)
+#pragma unroll
+        for (int m = 0; m < H; m += 2) {
+            const int u = m / 2;
+            const uint32_t left = (m == 0) ? left0 : R[m > 0 ? m - 1 : 0];
+            const uint32_t a_lo = imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u) % H]);
+            const uint32_t a_hi = imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q) % H]);
+            const uint32_t sub2 = imad(lds_u16(a_hi), fc.k64k, lds_u16(a_lo));
+            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
+            const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
+            R[m] = (mn & 0xfffcfffcu) | penc[m];
+            const uint32_t c2 = mn & 0x00030003u;
+            dw[m] = (r % 8 == 0) ? c2 : imad(dw[m], fc.k4, c2);
+        }
+        sw[tt] = ld_u16(sptr + 2 * r) + tab_lane;
+        // ---- odd diagonals: anti-diagonal s = 2t + 1
+        const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
+        const uint32_t upl = __funnelshift_r(R[0], next, 16);            // (right lane's diag 0) << 16 | (own diag H)
+#pragma unroll
+        for (int m = 1; m < H; m += 2) {
+            const int u = (m - 1) / 2;
+            const uint32_t up = (m == H - 1) ? upl : R[m + 1 < H ? m + 1 : H - 1];
+            const uint32_t a_lo = imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u + 1) % H]);
+            const uint32_t a_hi = imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q + 1) % H]);
+            const uint32_t sub2 = imad(lds_u16(a_hi), fc.k64k, lds_u16(a_lo));
+            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
+            const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
+            R[m] = (mn & 0xfffcfffcu) | penc[m];
+            const uint32_t c2 = mn & 0x00030003u;
+            dw[m] = (r % 8 == 0) ? c2 : imad(dw[m], fc.k4, c2);
+        }
+        lw[(tt + 1) % H] = ld_u8(lptr + r);
+        if (r % 8 == 7) {
+            store_words16<H>(out, dw, 8);
+            out += 32 * H;
+        } else if (TAIL && r == n_iter - 1) {
+            store_words16<H>(out, dw, (r % 8) + 1);
+            out += 32 * H;
+        }
+    }
+    lptr += 16;
+    sptr += 32;
+}
+
+// Move the warp's finite maximum back to kTop16.  Returns false when the finite spread no longer fits the window.
+template <int H>
+__device__ __forceinline__ bool rebase16(uint32_t (&R)[H], int &total_shift, uint32_t spread_limit)
+{
+    uint32_t mx = 0u, mnv = 0xffffffffu;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        mx = __vmaxu2(mx, R[m] ^ 0x80008000u);       // finite halves become >= 0x8000, unreachable ones < 0x8000
+        mnv = __vminu2(mnv, R[m]);
+    }
+    uint32_t hi = max(mx & 0xffffu, mx >> 16), lo = min(mnv & 0xffffu, mnv >> 16);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        hi = max(hi, __shfl_xor_sync(kFull, hi, d));
+        lo = min(lo, __shfl_xor_sync(kFull, lo, d));
+    }
+    if (hi < 0x8000u) return true;                   // no finite cell yet
+    const uint32_t maxf = hi & 0x7ffcu, minf = lo & 0xfffcu;
+    const int delta = (int)kTop16 - (int)maxf;
+    const uint32_t d2 = ((uint32_t)delta & 0xffffu) * 0x00010001u;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        const uint32_t unreach = ((R[m] >> 15) & 0x00010001u) * 0xffffu;
+        R[m] = __vadd2(R[m], d2 & ~unreach);
+    }
+    total_shift += delta;
+    return maxf - minf <= spread_limit;
+}
+
+// Returns the final cell's 4*(v - C - G) + kBias4 | code in the 32-bit convention of fill_pair, or kOverflow16.
+template <int B>
+__device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, uint32_t tab_lane, const char *Lb,
+                                             const char *Sb, uint32_t *slot, int lane, int sub4gg, uint32_t spread_limit)
+{
+    constexpr int H = B / 2;
+    uint32_t R[H], penc[H], dw[H], lw[H], sw[H];
+    const int qb = lane * B;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        uint32_t pe = 0, wv = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = qb + m + h * H;
+            const uint32_t p1 = 1u | ((q < g.pad || q >= g.wb) ? 0x8000u : 0u);
+            const uint32_t w1 = (q == g.q0) ? ((kTop16 - (uint32_t)sub4gg) & 0xffffu) : 0x8001u;
+            pe |= p1 << (16 * h);
+            wv |= w1 << (16 * h);
+        }
+        penc[m] = pe;
+        asm volatile("" : "+r"(penc[m]));
+        R[m] = wv;
+        dw[m] = 0;
+    }
+    const int I0 = g.q0 / 2 - lane * H;
+    const int J0 = -(g.q0 / 2) + lane * H;
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        lw[(H - u) % H] = ld_u8(Lb + (I0 - u));
+        sw[u] = ld_u16(Sb + 2 * (J0 + u)) + tab_lane;
+    }
+    const char *lptr = Lb + (I0 + 1);
+    const char *sptr = Sb + 2 * (J0 + H);
+    uint32_t *out = slot + lane * H;
+    const int nfull = g.T >> 4, rem = g.T & 15;
+    int total_shift = 0;
+    bool ok = true;
+    for (int c = 0; c < nfull; ++c) {
+        if (c && !(c & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        run_chunk16<B, false>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, 16, out);
+    }
+    if (rem) {
+        if (nfull && !(nfull & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        run_chunk16<B, true>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, rem, out);
+    }
+    // one last look at the window: everything since the previous check stayed inside it iff that check passed
+    ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+    if (!ok) return kOverflow16;
+    const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
+    const int m_last = q_last % B;
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        if (m == m_last) v = R[m] & 0xffffu;
+        if (m + H == m_last) v = R[m] >> 16;
+    }
+    v = __shfl_sync(kFull, v, q_last / B);
+    const int x4 = (int)(v & 0x7ffcu) - (int)kTop16 - total_shift;      // 4 * (v - C - G)
+    return (uint32_t)((int)kBias4 + x4) | 1u;
+}
+
+// one lane per pair, packed layout
+__device__ __forceinline__ uint32_t trace_lane16(const uint32_t *dirw, int B, int q0, int lg, int sh, uint32_t *ops)
+{
+    const int H = B >> 1;
+    int i = lg - 1, j = sh - 1;
+    uint32_t n = 0, acc = 0, cur_idx = 0xffffffffu, cur_word = 0;
+    while (i > 0 || j > 0) {
+        const int q = j - i + q0;
+        const int t = (i + j - (q & 1)) >> 1;
+        const int ln = q / B, mm = q - ln * B;
+        const int half = mm >= H ? 1 : 0, reg = mm - half * H;
+        const uint32_t idx = (uint32_t)(t >> 3) * (uint32_t)(32 * H) + (uint32_t)(ln * H + reg);
+        if (idx != cur_idx) { cur_word = __ldcg(dirw + idx); cur_idx = idx; }
+        const uint32_t code = (cur_word >> (16 * half + 2 * (7 - (t & 7)))) & 3u;
+        acc |= code << (2 * (n & 15));
+        ++n;
+        if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
+        i -= (code != 2u);
+        j -= (code != 1u);
+    }
+    if (n & 15) ops[n >> 4] = acc;
+    return n;
+}
+
 // ---------------------------------------------------------------------------------------------
 // trace: one lane per pair
 // ---------------------------------------------------------------------------------------------
@@ -340,6 +549,23 @@ __device__ __forceinline__ uint32_t dispatch_fill(int B, const Geom &g, const Fi
     }
 }
 
+template <int BMAX>
+__device__ __forceinline__ uint32_t dispatch_fill16(int B, const Geom &g, const FillConst fc, uint32_t tab_lane,
+                                                    const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg,
+                                                    uint32_t spread)
+{
+    if constexpr (BMAX <= 8) {
+        switch (B) {
+            case 4:  return fill_pair16<4>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg, spread);
+            case 8:  return fill_pair16<8>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg, spread);
+            default: return fill_pair16<16>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg, spread);
+        }
+    } else {
+        if (B == 16) return fill_pair16<16>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg, spread);
+        return fill_pair16<32>(g, fc, tab_lane, Lb, Sb, slot, lane, sub4gg, spread);
+    }
+}
+
 // Shared memory: [sub4 table | cgap[dim] | gapc[dim] | per-warp: flags[32], nal[32], off[32], seq window].
 extern __shared__ __align__(16) char smem[];
 
@@ -372,7 +598,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     __syncthreads();
 
     const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(tab) + (tcm.repl ? 4u * lane : 0u);
-    const FillConst fc = {p.k_four, p.k_minus1, p.l_stride};
+    const FillConst fc = {p.k_four, p.k_minus1, p.l_stride, p.k_64k};
     const int G = p.pairs_per_warp;
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
@@ -385,7 +611,9 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
         base = __shfl_sync(kFull, base, 0);
         if (base >= n_work) break;
         const int npw = (int)min((uint32_t)G, n_work - base);
-        auto pair_of = [&](int pi) -> uint32_t { return BMAX <= 8 ? base + pi : p.big_list[base + pi]; };
+        // wide kernel: queue entries carry bit 31 = "the packed fill overflowed its window, use the 32-bit fill"
+        auto entry_of = [&](int pi) -> uint32_t { return BMAX <= 8 ? base + pi : p.big_list[base + pi]; };
+        auto pair_of = [&](int pi) -> uint32_t { return entry_of(pi) & 0x7fffffffu; };
 
         int pi = 0;
         while (pi < npw) {
@@ -401,8 +629,10 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                 const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
                 const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                 const int B = choose_b(g.wb);
-                if (BMAX <= 8 && B > 8) {                   // hand over to the wide kernel
-                    if (lane == 0) { s_flags[pi] = 0; p.big_list[atomicAdd(p.big_count, 1u)] = k; }
+                // packed 16-bit fill: B = 4 .. 16 in the narrow kernel, B = 32 in the wide one
+                bool packed = tcm.pack_ok && B >= 4 && !(entry_of(pi) >> 31);
+                if (BMAX <= 8 && (packed ? (B > 16 || (B == 16 && seq_bytes(seq_layout(g, 16)) > p.seq_cap)) : B > 8)) {
+                    if (lane == 0) { s_flags[pi] = 0; p.big_list[atomicAdd(p.big_count, 1u)] = k; }   // -> wide kernel
                     continue;
                 }
                 bool ok = B != 0;
@@ -418,9 +648,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                     continue;
                 }
                 if (cur + need > p.arena_words) break;     // trace + emit what we have, then go on
-                if (lane == 0) { s_flags[pi] = (fl ? 1u : 0u) | 2u; s_off[pi] = cur; }
                 uint32_t *slot = arena + cur;
-                cur += need;
 
                 // stage both strings; sum the indel costs that are folded out of the cell values
                 uint16_t *Sr = reinterpret_cast<uint16_t *>(seq);
@@ -447,7 +675,23 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
 
                 const char *Lb = reinterpret_cast<const char *>(Lr + sl.offL);
                 const char *Sb = reinterpret_cast<const char *>(Sr + sl.offS);
-                const uint32_t fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+                uint32_t fw;
+                if (packed) {
+                    fw = dispatch_fill16<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap, tcm.spread16);
+                    if (fw == kOverflow16) {                // the sweep's finite spread left the 15-bit window
+                        packed = false;
+                        if (BMAX <= 8 && B > 8) {           // the 32-bit fill of this width lives in the wide kernel
+                            if (lane == 0) { s_flags[pi] = 0; p.big_list[atomicAdd(p.big_count, 1u)] = k | 0x80000000u; }
+                            __syncwarp();
+                            continue;
+                        }
+                        fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+                    }
+                } else {
+                    fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+                }
+                if (lane == 0) { s_flags[pi] = (fl ? 1u : 0u) | 2u | (packed ? 4u : 0u); s_off[pi] = cur; }
+                cur += need;
                 if (lane == 0) b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
                 if (b.cells) {
                     unsigned long long c = band_cells(g, lane, 32);
@@ -469,7 +713,8 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                 const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                 const int B = choose_b(g.wb);
                 uint32_t *slot = arena + s_off[pj];
-                const uint32_t n = trace_lane(slot, 32u * B, g.q0, g.lg, g.sh, slot + dir_words(g, B));
+                const uint32_t n = (s_flags[pj] & 4u) ? trace_lane16(slot, B, g.q0, g.lg, g.sh, slot + dir_words(g, B))
+                                                      : trace_lane(slot, 32u * B, g.q0, g.lg, g.sh, slot + dir_words(g, B));
                 s_nal[pj] = n;
                 if (b.out_len) b.out_len[k] = n;
             }
