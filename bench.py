@@ -570,7 +570,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
     ap.add_argument("--warps", type=int, default=32, help="warps per CTA of the narrow kernel")
-    ap.add_argument("--ppw", type=int, default=8, help="pairs a warp fills before tracing them")
+    ap.add_argument("--ppw", type=int, default=32, help="pairs a warp fills before tracing them")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--no-postorder", action="store_true", help="skip the config-5 post-order section")
     ap.add_argument("--po-trees", type=int, default=0, help="override the number of candidate trees")

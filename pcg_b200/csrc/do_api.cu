@@ -297,7 +297,7 @@ extern "C" void pcgdo_tcm_destroy(pcgdo_ctx *ctx, pcgdo_tcm *t)
 static size_t smem_for(const pcgdo_tcm *tcm, int warps, uint32_t seq_cap)
 {
     const size_t dim = (size_t)1 << tcm->a;
-    return tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps * (384 + (size_t)seq_cap);
+    return tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps * (512 + (size_t)seq_cap);
 }
 
 int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &bd, cudaStream_t st,
@@ -345,6 +345,7 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     p.k_minus1 = 0xffffffffu;
     p.l_stride = tcm->dev.repl ? 2048u : (2u << tcm->a);
     p.k_64k = 65536u;
+    p.grab = 2;
 
     p.seq_cap = cap_n;
     CK(launch_linear(p, false, grid, warps_n * 32, smem_for(tcm, warps_n, cap_n), st));

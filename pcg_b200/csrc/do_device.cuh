@@ -52,7 +52,8 @@ struct LinearParams {
     uint32_t *arena;        // [n_warps_total][arena_words]: direction words + op streams of the
     uint32_t  arena_words;  //   pairs a warp has filled but not yet traced
     uint32_t  seq_cap;      // u16 elements of sequence staging per warp
-    int       pairs_per_warp;
+    int       pairs_per_warp;   // pairs a warp fills before it traces them, one lane per pair (1..32)
+    uint32_t  grab;         // pairs taken from the work counter at a time
     unsigned int *counter;  // work counter (pairs handed out); counter[2] = hand-out counter of the wide kernel
     unsigned int *overflow_count;
     uint32_t     *overflow_list;   // pair indices the fast path could not hold

@@ -586,11 +586,12 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     uint32_t *s_cgap = reinterpret_cast<uint32_t *>(smem + tcm.sub4_bytes);
     uint32_t *s_gapc = s_cgap + dim;
     char *warp_base = reinterpret_cast<char *>(s_gapc + dim);
-    const uint32_t per_warp = 384u + p.seq_cap;
+    const uint32_t per_warp = 512u + p.seq_cap;
     uint32_t *s_flags = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
     uint32_t *s_nal = s_flags + 32;
     uint32_t *s_off = s_flags + 64;
-    char *seq = reinterpret_cast<char *>(s_flags) + 384;
+    uint32_t *s_pair = s_flags + 96;
+    char *seq = reinterpret_cast<char *>(s_flags) + 512;
 
     for (uint32_t i = threadIdx.x; i < tcm.sub4_bytes / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(tab)[i] = __ldg(reinterpret_cast<const uint4 *>(tcm.sub4) + i);
@@ -605,129 +606,140 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     unsigned int *counter = BMAX <= 8 ? p.counter : p.counter + 2;
     const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len || b.out_ungapped;
 
+    // Work is taken from the counter `grab` pairs at a time (fine-grained: the tail of a batch costs at most one
+    // grab per warp) and filled back to back; once `G` pairs are waiting in the arena — or the arena is full, or the
+    // batch is exhausted — the warp traces them all at once, one lane per pair, and emits them.
+    const uint32_t grab = p.grab ? p.grab : 1u;
+    uint32_t gpos = 0, gend = 0;
+    bool exhausted = false;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned)G);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= n_work) break;
-        const int npw = (int)min((uint32_t)G, n_work - base);
-        // wide kernel: queue entries carry bit 31 = "the packed fill overflowed its window, use the 32-bit fill"
-        auto entry_of = [&](int pi) -> uint32_t { return BMAX <= 8 ? base + pi : p.big_list[base + pi]; };
-        auto pair_of = [&](int pi) -> uint32_t { return entry_of(pi) & 0x7fffffffu; };
+        int cnt = 0;
+        uint32_t cur = 0;
+        // -------------------------------------------------------------- fill, pair after pair
+        for (;;) {
+            if (cnt == G) break;
+            if (gpos == gend) {
+                if (exhausted) break;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(counter, grab);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= n_work) { exhausted = true; break; }
+                gpos = base;
+                gend = min(base + grab, n_work);
+            }
+            // wide kernel: queue entries carry bit 31 = "the packed fill overflowed its window, use the 32-bit fill"
+            const uint32_t entry = BMAX <= 8 ? gpos : p.big_list[gpos];
+            const uint32_t k = entry & 0x7fffffffu;
+            const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+            const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+            const bool fl = first_is_long(p1, n1, p2, n2, lane);
+            const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
+            const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+            const int B = choose_b(g.wb);
+            // packed 16-bit fill: B = 4 .. 16 in the narrow kernel, B = 16 / 32 in the wide one
+            bool packed = tcm.pack_ok && B >= 4 && !(entry >> 31);
+            if (BMAX <= 8 && (packed ? (B > 16 || (B == 16 && seq_bytes(seq_layout(g, 16)) > p.seq_cap)) : B > 8)) {
+                if (lane == 0) p.big_list[atomicAdd(p.big_count, 1u)] = k;       // -> wide kernel
+                ++gpos;
+                continue;
+            }
+            bool ok = B != 0;
+            SeqLayout sl = {0, 0, 0, 0};
+            uint32_t need = 0;
+            if (ok) {
+                sl = seq_layout(g, B);
+                need = (dir_words(g, B) + ops_words(g) + 3u) & ~3u;
+                ok = seq_bytes(sl) <= p.seq_cap && need <= p.arena_words;
+            }
+            if (!ok) {
+                if (lane == 0) p.overflow_list[atomicAdd(p.overflow_count, 1u)] = k;
+                ++gpos;
+                continue;
+            }
+            if (cur + need > p.arena_words) break;         // trace + emit what we have, then come back to this pair
+            uint32_t *slot = arena + cur;
 
-        int pi = 0;
-        while (pi < npw) {
-            const int start = pi;
-            uint32_t cur = 0;
-            // -------------------------------------------------------------- fill, pair after pair,
-            // until the warp's scratch arena is full
-            for (; pi < npw; ++pi) {
-                const uint32_t k = pair_of(pi);
-                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
-                const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
-                const bool fl = first_is_long(p1, n1, p2, n2, lane);
-                const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
-                const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
-                const int B = choose_b(g.wb);
-                // packed 16-bit fill: B = 4 .. 16 in the narrow kernel, B = 32 in the wide one
-                bool packed = tcm.pack_ok && B >= 4 && !(entry_of(pi) >> 31);
-                if (BMAX <= 8 && (packed ? (B > 16 || (B == 16 && seq_bytes(seq_layout(g, 16)) > p.seq_cap)) : B > 8)) {
-                    if (lane == 0) { s_flags[pi] = 0; p.big_list[atomicAdd(p.big_count, 1u)] = k; }   // -> wide kernel
-                    continue;
-                }
-                bool ok = B != 0;
-                SeqLayout sl = {0, 0, 0, 0};
-                uint32_t need = 0;
-                if (ok) {
-                    sl = seq_layout(g, B);
-                    need = (dir_words(g, B) + ops_words(g) + 3u) & ~3u;
-                    ok = seq_bytes(sl) <= p.seq_cap && need <= p.arena_words;
-                }
-                if (!ok) {
-                    if (lane == 0) { s_flags[pi] = 0; p.overflow_list[atomicAdd(p.overflow_count, 1u)] = k; }
-                    continue;
-                }
-                if (cur + need > p.arena_words) break;     // trace + emit what we have, then go on
-                uint32_t *slot = arena + cur;
-
-                // stage both strings; sum the indel costs that are folded out of the cell values
-                uint16_t *Sr = reinterpret_cast<uint16_t *>(seq);
-                uint8_t *Lr = reinterpret_cast<uint8_t *>(Sr + sl.sizeS);
-                uint32_t csum = 0;
-                const uint32_t emask = (uint32_t)dim - 1u;
-                for (int idx = lane; idx < sl.sizeL; idx += 32) {
-                    const int i = idx - sl.offL;
-                    uint32_t e = 0;
-                    if (i == 0) e = tcm.gap;
-                    else if (i > 0 && i < g.lg) { e = __ldg(pL + i - 1) & emask; csum += s_cgap[e]; }
-                    Lr[idx] = (uint8_t)e;
-                }
-                for (int idx = lane; idx < sl.sizeS; idx += 32) {
-                    const int j = idx - sl.offS;
-                    uint32_t e = 0;
-                    if (j == 0) e = tcm.gap;
-                    else if (j > 0 && j < g.sh) { e = __ldg(pS + j - 1) & emask; csum += s_gapc[e]; }
-                    Sr[idx] = (uint16_t)(tcm.repl ? (((e >> 1) << 7) | ((e & 1u) << 1)) : (e << 1));
-                }
+            // stage both strings; sum the indel costs that are folded out of the cell values
+            uint16_t *Sr = reinterpret_cast<uint16_t *>(seq);
+            uint8_t *Lr = reinterpret_cast<uint8_t *>(Sr + sl.sizeS);
+            uint32_t csum = 0;
+            const uint32_t emask = (uint32_t)dim - 1u;
+            for (int idx = lane; idx < sl.sizeL; idx += 32) {
+                const int i = idx - sl.offL;
+                uint32_t e = 0;
+                if (i == 0) e = tcm.gap;
+                else if (i > 0 && i < g.lg) { e = __ldg(pL + i - 1) & emask; csum += s_cgap[e]; }
+                Lr[idx] = (uint8_t)e;
+            }
+            for (int idx = lane; idx < sl.sizeS; idx += 32) {
+                const int j = idx - sl.offS;
+                uint32_t e = 0;
+                if (j == 0) e = tcm.gap;
+                else if (j > 0 && j < g.sh) { e = __ldg(pS + j - 1) & emask; csum += s_gapc[e]; }
+                Sr[idx] = (uint16_t)(tcm.repl ? (((e >> 1) << 7) | ((e & 1u) << 1)) : (e << 1));
+            }
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
-                __syncwarp();
+            for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+            __syncwarp();
 
-                const char *Lb = reinterpret_cast<const char *>(Lr + sl.offL);
-                const char *Sb = reinterpret_cast<const char *>(Sr + sl.offS);
-                uint32_t fw;
-                if (packed) {
-                    fw = dispatch_fill16<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap, tcm.spread16);
-                    if (fw == kOverflow16) {                // the sweep's finite spread left the 15-bit window
-                        packed = false;
-                        if (BMAX <= 8 && B > 8) {           // the 32-bit fill of this width lives in the wide kernel
-                            if (lane == 0) { s_flags[pi] = 0; p.big_list[atomicAdd(p.big_count, 1u)] = k | 0x80000000u; }
-                            __syncwarp();
-                            continue;
-                        }
-                        fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
+            const char *Lb = reinterpret_cast<const char *>(Lr + sl.offL);
+            const char *Sb = reinterpret_cast<const char *>(Sr + sl.offS);
+            uint32_t fw;
+            if (packed) {
+                fw = dispatch_fill16<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap, tcm.spread16);
+                if (fw == kOverflow16) {                // the sweep's finite spread left the 15-bit window
+                    packed = false;
+                    if (BMAX <= 8 && B > 8) {           // the 32-bit fill of this width lives in the wide kernel
+                        if (lane == 0) p.big_list[atomicAdd(p.big_count, 1u)] = k | 0x80000000u;
+                        __syncwarp();
+                        ++gpos;
+                        continue;
                     }
-                } else {
                     fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
                 }
-                if (lane == 0) { s_flags[pi] = (fl ? 1u : 0u) | 2u | (packed ? 4u : 0u); s_off[pi] = cur; }
-                cur += need;
-                if (lane == 0) b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
-                if (b.cells) {
-                    unsigned long long c = band_cells(g, lane, 32);
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
-                    if (lane == 0) b.cells[k] = c;
-                }
-                __syncwarp();   // the staging window is reused by the next pair
+            } else {
+                fw = dispatch_fill<BMAX>(B, g, fc, tab_lane, Lb, Sb, slot, lane, tcm.sub4_gapgap);
             }
-            __syncwarp();
-            if (!want_out) continue;
-
+            if (lane == 0) {
+                s_flags[cnt] = (fl ? 1u : 0u) | (packed ? 4u : 0u);
+                s_off[cnt] = cur;
+                s_pair[cnt] = k;
+                b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
+            }
+            cur += need;
+            if (b.cells) {
+                unsigned long long c = band_cells(g, lane, 32);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+                if (lane == 0) b.cells[k] = c;
+            }
+            ++cnt;
+            ++gpos;
+            __syncwarp();   // the staging window is reused by the next pair
+        }
+        __syncwarp();
+        if (cnt && want_out) {
             // -------------------------------------------------------------- trace: lane = pair
-            const int pj = start + lane;
-            if (pj < pi && (s_flags[pj] & 2u)) {
-                const uint32_t k = pair_of(pj);
+            if (lane < cnt) {
+                const uint32_t k = s_pair[lane];
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
-                const bool fl = s_flags[pj] & 1u;
+                const bool fl = s_flags[lane] & 1u;
                 const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                 const int B = choose_b(g.wb);
-                uint32_t *slot = arena + s_off[pj];
-                const uint32_t n = (s_flags[pj] & 4u) ? trace_lane16(slot, B, g.q0, g.lg, g.sh, slot + dir_words(g, B))
-                                                      : trace_lane(slot, 32u * B, g.q0, g.lg, g.sh, slot + dir_words(g, B));
-                s_nal[pj] = n;
+                uint32_t *slot = arena + s_off[lane];
+                const uint32_t n = (s_flags[lane] & 4u) ? trace_lane16(slot, B, g.q0, g.lg, g.sh, slot + dir_words(g, B))
+                                                        : trace_lane(slot, 32u * B, g.q0, g.lg, g.sh, slot + dir_words(g, B));
+                s_nal[lane] = n;
                 if (b.out_len) b.out_len[k] = n;
             }
             __syncwarp();
 
             // -------------------------------------------------------------- emit: warp per pair
             if (b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_ungapped) {
-                for (int pe = start; pe < pi; ++pe) {
-                    const uint32_t fl_ok = s_flags[pe];
-                    if (!(fl_ok & 2u)) continue;
-                    const uint32_t k = pair_of(pe);
+                for (int pe = 0; pe < cnt; ++pe) {
+                    const uint32_t k = s_pair[pe];
                     const uint32_t n1 = b.len1[k], n2 = b.len2[k];
-                    const bool fl = fl_ok & 1u;
+                    const bool fl = s_flags[pe] & 1u;
                     const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
                     const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                     const int B = choose_b(g.wb);
@@ -746,6 +758,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
             }
             __syncwarp();
         }
+        if (exhausted && gpos == gend) break;
     }
 }
 
