@@ -538,10 +538,17 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
 
 // --------------------------------------------------------------------------------------------- large alphabets
 
+struct pcgdo_memo;
+static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const pcgdo_batch32 *b,
+                              void *cuda_stream);
+
 extern "C" int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b,
                                          void *cuda_stream)
 {
     if (!ctx || !b) return PCGDO_ERR_ARG;
+    // The per-pair table kernel (do_explicit.cu) with the closed-form discrete overlap; PCGDO_METRIC_REGISTERS=1
+    // selects the older kernel that evaluates the overlap per cell in registers (do_metric.cu, a <= 24).
+    if (!getenv("PCGDO_METRIC_REGISTERS")) return table_batch_device(ctx, nullptr, alphabet, dialect, b, cuda_stream);
     ctx->timed = false;
     ctx->last_launches = 0;
     if (b->n_pairs == 0) return PCGDO_OK;
@@ -782,10 +789,21 @@ extern "C" int pcgdo_overlap2d_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo
     return PCGDO_OK;
 }
 
+static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const pcgdo_batch32 *b,
+                              void *cuda_stream);
+
 extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b,
                                            void *cuda_stream)
 {
-    if (!ctx || !memo || !b) return PCGDO_ERR_ARG;
+    if (!memo) return PCGDO_ERR_ARG;
+    return table_batch_device(ctx, memo, (int)memo->a, dialect, b, cuda_stream);
+}
+
+// memo == NULL: the discrete metric over `alphabet` symbols through the same per-pair table machinery
+static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const pcgdo_batch32 *b,
+                              void *cuda_stream)
+{
+    if (!ctx || !b) return PCGDO_ERR_ARG;
     ctx->timed = false;
     ctx->last_launches = 0;
     if (b->n_pairs == 0) return PCGDO_OK;
@@ -800,7 +818,11 @@ extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *mem
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    const int a = (int)memo->a;
+    const int a = alphabet;
+    if (a < 2 || a > 32) {
+        ctx->err = "table path: alphabet size must be 2..32";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
     const uint32_t seq_cap = metric_seq_cap(ctx->max_len);
     const uint32_t tab_entries = 1024;                     // 2 KB of shared memory per warp for small tables
     const size_t sg_bytes = ((size_t)a * a * 4 + 15) & ~(size_t)15;
@@ -839,8 +861,11 @@ extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *mem
     p.b.final_offset = b->final_offset;
     p.a = a;
     p.dialect = dialect;
-    p.sigma = (const uint32_t *)memo->d_sigma;
-    p.delta = memo->delta;
+    p.kind = memo ? 2 : 0;
+    p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
+    p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
+    p.delta = memo ? memo->delta : 1u;
+    p.k_64k = 65536u;
     p.arena = (uint32_t *)ctx->arena.p;
     p.arena_words = (uint32_t)arena_words;
     p.tscratch = (uint32_t *)ctx->tscratch.p;

@@ -17,6 +17,7 @@
 // reference tcm-memo (tests/golden/tcm_memo_golden.json).
 #include "do_metric.cuh"
 #include "do_explicit.h"
+#include "do_pack16.cuh"
 
 namespace pcgdo {
 
@@ -177,7 +178,152 @@ __device__ __forceinline__ uint32_t x_dispatch(int B, const MGeom &g, uint32_t k
     }
 }
 
-__device__ __forceinline__ void x_emit(const uint32_t *sg, int a, const uint32_t *pL, const uint32_t *pS, uint32_t gap,
+// ------------------------------------------------------------------------------------------------ packed fill
+// Same scheme as do_linear.cu's fill_pair16: two diagonals per register, VIADDMNMX.U16x2, windowed re-basing.
+__device__ __forceinline__ uint32_t x_lds_u16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t x_ldg_u16(const char *base, uint32_t off)
+{
+    uint32_t v;
+    asm("ld.global.u16 %0, [%1];" : "=r"(v) : "l"(base + off));
+    return v;
+}
+
+template <int B, bool GLOBAL, bool TAIL>
+__device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (&penc)[B / 2], uint32_t (&dw)[B / 2],
+                                          uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t k4, uint32_t k1,
+                                          uint32_t k64k, const char *gtab, const uint32_t *&lptr, const uint32_t *&sptr,
+                                          int n_iter, uint32_t *&out)
+{
+    constexpr int H = B / 2, Q = H / 2;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        if (TAIL && r >= n_iter) break;
+        const int tt = r % H;
+        const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
+        const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);
+#pragma unroll
+        for (int m = 0; m < H; m += 2) {
+            const int u = m / 2;
+            const uint32_t left = (m == 0) ? left0 : R[m > 0 ? m - 1 : 0];
+            const uint32_t a_lo = m_imad(lw[(tt - u + 2 * H) % H], k1, sw[(tt + u) % H]);
+            const uint32_t a_hi = m_imad(lw[(tt - u - Q + 2 * H) % H], k1, sw[(tt + u + Q) % H]);
+            const uint32_t s_lo = GLOBAL ? x_ldg_u16(gtab, a_lo) : x_lds_u16(a_lo);
+            const uint32_t s_hi = GLOBAL ? x_ldg_u16(gtab, a_hi) : x_lds_u16(a_hi);
+            const uint32_t sub2 = m_imad(s_hi, k64k, s_lo);
+            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
+            const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
+            R[m] = (mn & 0xfffcfffcu) | penc[m];
+            const uint32_t c2 = mn & 0x00030003u;
+            dw[m] = (r % 8 == 0) ? c2 : m_imad(dw[m], k4, c2);
+        }
+        sw[tt] = sptr[r];
+        const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
+        const uint32_t upl = __funnelshift_r(R[0], next, 16);
+#pragma unroll
+        for (int m = 1; m < H; m += 2) {
+            const int u = (m - 1) / 2;
+            const uint32_t up = (m == H - 1) ? upl : R[m + 1 < H ? m + 1 : H - 1];
+            const uint32_t a_lo = m_imad(lw[(tt - u + 2 * H) % H], k1, sw[(tt + u + 1) % H]);
+            const uint32_t a_hi = m_imad(lw[(tt - u - Q + 2 * H) % H], k1, sw[(tt + u + Q + 1) % H]);
+            const uint32_t s_lo = GLOBAL ? x_ldg_u16(gtab, a_lo) : x_lds_u16(a_lo);
+            const uint32_t s_hi = GLOBAL ? x_ldg_u16(gtab, a_hi) : x_lds_u16(a_hi);
+            const uint32_t sub2 = m_imad(s_hi, k64k, s_lo);
+            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
+            const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
+            R[m] = (mn & 0xfffcfffcu) | penc[m];
+            const uint32_t c2 = mn & 0x00030003u;
+            dw[m] = (r % 8 == 0) ? c2 : m_imad(dw[m], k4, c2);
+        }
+        lw[(tt + 1) % H] = lptr[r];
+        if (r % 8 == 7) {
+            store_words16<H>(out, dw, 8);
+            out += 32 * H;
+        } else if (TAIL && r == n_iter - 1) {
+            store_words16<H>(out, dw, (r % 8) + 1);
+            out += 32 * H;
+        }
+    }
+    lptr += 16;
+    sptr += 16;
+}
+
+// returns the last cell in the 32-bit convention of x_fill, or kOverflow16
+template <int B, bool GLOBAL>
+__device__ __noinline__ uint32_t x_fill16(const MGeom g, uint32_t k4, uint32_t k1, uint32_t k64k, const char *gtab,
+                                          const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot, int lane,
+                                          uint32_t spread_limit)
+{
+    constexpr int H = B / 2;
+    uint32_t R[H], penc[H], dw[H], lw[H], sw[H];
+    const int qb = lane * B;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        uint32_t pe = 0, wv = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = qb + m + h * H;
+            const uint32_t p1 = 1u | ((q < g.pad || q >= g.wb) ? 0x8000u : 0u);
+            const uint32_t w1 = (q == g.q0) ? (kTop16 + 1u) : 0x8001u;
+            pe |= p1 << (16 * h);
+            wv |= w1 << (16 * h);
+        }
+        penc[m] = pe;
+        asm volatile("" : "+r"(penc[m]));
+        R[m] = wv;
+        dw[m] = 0;
+    }
+    const int I0 = g.q0 / 2 - lane * H, J0 = -(g.q0 / 2) + lane * H;
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        lw[(H - u) % H] = Lb[I0 - u];
+        sw[u] = Sb[J0 + u];
+    }
+    const uint32_t *lptr = Lb + (I0 + 1), *sptr = Sb + (J0 + H);
+    uint32_t *out = slot + lane * H;
+    const int nfull = g.T >> 4, rem = g.T & 15;
+    int total_shift = 0;
+    bool ok = true;
+    for (int c = 0; c < nfull; ++c) {
+        if (c && !(c & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, 16, out);
+    }
+    if (rem) {
+        if (nfull && !(nfull & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        x_chunk16<B, GLOBAL, true>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, rem, out);
+    }
+    ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+    if (!ok) return kOverflow16;
+    const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0, m_last = q_last % B;
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        if (m == m_last) v = R[m] & 0xffffu;
+        if (m + H == m_last) v = R[m] >> 16;
+    }
+    v = __shfl_sync(kFull, v, q_last / B);
+    const int x4 = (int)(v & 0x7ffcu) - (int)kTop16 - total_shift;
+    return (uint32_t)((int)kBias4 + x4) | 1u;
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ uint32_t x_dispatch16(int B, const MGeom &g, uint32_t k4, uint32_t k1, uint32_t k64k,
+                                                 const char *gtab, const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot,
+                                                 int lane, uint32_t spread)
+{
+    switch (B) {
+        case 4:  return x_fill16<4, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
+        case 8:  return x_fill16<8, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
+        case 16: return x_fill16<16, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
+        default: return x_fill16<32, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
+    }
+}
+
+__device__ __forceinline__ void x_emit(const uint32_t *sg, int a, int kind, const uint32_t *pL, const uint32_t *pS, uint32_t gap,
                                        uint32_t mask, const uint32_t *ops, uint32_t nal, bool swapped, uint32_t *om,
                                        uint32_t *o1, uint32_t *o2, int lane)
 {
@@ -196,7 +342,9 @@ __device__ __forceinline__ void x_emit(const uint32_t *sg, int a, const uint32_t
             const uint32_t y = code < 2u ? (__ldg(pL + il) & mask) : 0u;
             const uint32_t x = (code == 0u || code == 2u) ? (__ldg(pS + js) & mask) : 0u;
             uint32_t md, cc;
-            ov_explicit(sg, a, x ? x : gap, y ? y : gap, md, cc);
+            const uint32_t xx = x ? x : gap, yy = y ? y : gap;
+            if (kind == 0) md = (xx & yy) ? (xx & yy) : (xx | yy);       // discreteMetricPairwiseLogic
+            else ov_explicit(sg, a, xx, yy, md, cc);
             if (om) om[c] = md;
             if (o1) o1[c] = swapped ? y : x;
             if (o2) o2[c] = swapped ? x : y;
@@ -273,7 +421,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64, *s_geo = s_meta + 96;
     uint32_t *seq = s_meta + 128;
     int16_t *stab = reinterpret_cast<int16_t *>(reinterpret_cast<char *>(seq) + p.seq_cap);
-    for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = p.sigma[i];
+    if (p.kind != 0)
+        for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = p.sigma[i];
     __syncthreads();
 
     const uint32_t gap = 1u << (a - 1);
@@ -348,7 +497,29 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     if (gtable) ok = (size_t)(tail - ts) + (entries + 1u) / 2u <= p.tscratch_words && Wt * 2u * (DL + 2u) < 0x7fffffffu;
                 }
                 uint32_t bad = 0;
-                if (ok) {
+                int emin = -1, emax = -1;                   // range of the finite table entries (leading gap: -1)
+                if (ok && p.kind == 0) {
+                    // discrete metric (Data/MetricRepresentation.hs:116-128): cost(x, y) = x & y ? 0 : 1 — no profiles
+                    for (uint32_t d = lane; d < DL + 2u; d += 32) cL[d] = (d >= 2u && !(elL[d - 2u] & gap)) ? 1u : 0u;
+                    for (uint32_t d = lane; d < DS + 2u; d += 32) gS[d] = (d >= 2u && !(elS[d - 2u] & gap)) ? 1u : 0u;
+                    __syncwarp();
+                    int16_t *tab = gtable ? reinterpret_cast<int16_t *>(tail) : stab;
+                    for (uint32_t t = lane; t < entries; t += 32) {
+                        const uint32_t dl = t / Wt, ds = t - dl * Wt;
+                        int v;
+                        if (dl == 0u || ds == 0u) v = kBigSub;
+                        else if (dl == 1u || ds == 1u) v = -1;
+                        else {
+                            const uint32_t x = elL[dl - 2u], y = elS[ds - 2u], t2 = x & y;
+                            v = 4 * ((t2 ? 0 : 1) - (int)cL[dl] - (int)gS[ds]) - 1 + ((s2 && t2 == gap) ? 1 : 0);
+                            emin = min(emin, v); emax = max(emax, v);
+                        }
+                        tab[t] = (int16_t)v;
+                    }
+                    gtab = reinterpret_cast<const char *>(tail);
+                    tab32 = (uint32_t)__cvta_generic_to_shared(stab);
+                    __syncwarp();
+                } else if (ok) {
                     for (uint32_t t = lane; t < DL * (uint32_t)a; t += 32) {
                         const uint32_t d = t / a, s = t - d * a;
                         uint32_t mn = 0xffffffffu;
@@ -397,6 +568,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                                                 ((s2 && bits == gap) ? 1ll : 0ll);
                             if (f < -32000ll || f >= (long long)kBigSub) bad = 1;
                             v = (int)f;
+                            emin = min(emin, v); emax = max(emax, v);
                         }
                         tab[t] = (int16_t)v;
                     }
@@ -407,12 +579,22 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     __syncwarp();
                 }
 
+                // packed 16-bit fill when the entries leave room in the 15-bit window (see do_linear.cu: rebase16)
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    emin = min(emin, __shfl_xor_sync(kFullM, emin, d));
+                    emax = max(emax, __shfl_xor_sync(kFullM, emax, d));
+                }
+                const int s_minus = 1 - emin, s_plus = max(0, emax) + 2, spread16 = 0x7000 - 64 * s_minus - 64;
+                bool packed = p.pack16 && 0x7000 + 64 * s_plus < 0x7800 && spread16 >= 8192;
+
                 const MGeom gfull = make_mgeom(lg, sh, -(lg - 1), sh - 1);
                 uint32_t fw = 0, csum = 0;
                 MGeom g = gfull;
                 int B = m_choose_b(gfull.wb);
                 uint32_t need = 0;
                 int final_off = -1;
+                bool used16 = false;
                 while (ok) {
                     if (!full) {
                         const int a_off = (int)(off < m ? off : m);
@@ -451,8 +633,16 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFullM, csum, d);
                     __syncwarp();
                     uint32_t *slot = arena + cur;
-                    if (gtable) fw = x_dispatch<true>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
-                    else        fw = x_dispatch<false>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
+                    used16 = packed && B >= 4;
+                    if (used16) {
+                        if (gtable) fw = x_dispatch16<true>(B, g, p.k_four, p.k_one, p.k_64k, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, (uint32_t)spread16);
+                        else        fw = x_dispatch16<false>(B, g, p.k_four, p.k_one, p.k_64k, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, (uint32_t)spread16);
+                        if (fw == kOverflow16) { used16 = false; packed = false; }       // redo this and later fills in 32 bits
+                    }
+                    if (!used16) {
+                        if (gtable) fw = x_dispatch<true>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
+                        else        fw = x_dispatch<false>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
+                    }
                     __syncwarp();
                     if (full) break;
                     const long long cost = (long long)((fw >> 2) - (kBias4 >> 2) + csum);
@@ -472,7 +662,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 }
                 if (cur + need > p.arena_words) break;       // flush what we have, then redo this pair
                 if (lane == 0) {
-                    s_flags[pi] = (swapped ? 1u : 0u) | 2u;
+                    s_flags[pi] = (swapped ? 1u : 0u) | 2u | (used16 ? 4u : 0u);
                     s_off[pi] = cur;
                     s_geo[pi] = (uint32_t)(uint16_t)(int16_t)g.dlo | ((uint32_t)(uint16_t)(int16_t)g.dhi << 16);
                     b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
@@ -497,7 +687,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pj] & 0xffffu), (int)(int16_t)(s_geo[pj] >> 16));
                 const int B = m_choose_b(g.wb);
                 uint32_t *slot = arena + s_off[pj];
-                const uint32_t na = m_trace(slot, 32u * B, g.q0, g.lg, g.sh, slot + m_dir_words(g, B));
+                const uint32_t na = (s_flags[pj] & 4u) ? trace_lane16(slot, B, g.q0, g.lg, g.sh, slot + m_dir_words(g, B))
+                                                       : m_trace(slot, 32u * B, g.q0, g.lg, g.sh, slot + m_dir_words(g, B));
                 s_nal[pj] = na;
                 if (b.out_len) b.out_len[k] = na;
             }
@@ -513,7 +704,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     const int B = m_choose_b(g.wb);
                     const uint32_t *ops = arena + s_off[pe] + m_dir_words(g, B);
                     const uint64_t oo = b.out_off[k];
-                    x_emit(sg, a, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe], swapped,
+                    x_emit(sg, a, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe], swapped,
                            b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
                            b.out_a2 ? b.out_a2 + oo : nullptr, lane);
                 }

@@ -8,6 +8,8 @@ struct ExplicitParams {
     MetricBatchDev b;
     int       a;              // alphabet size (incl. gap), <= 32
     int       dialect;        // 0 S1 full, 1 S1 Ukkonen, 2 S2 Ukkonen
+    int       kind;           // 0 discrete metric (closed form, sigma unused), 2 explicit sigma
+    int       pack16;         // allow the packed 16-bit fill
     const uint32_t *sigma;    // device [a*a]: sigma[s*a + j], s = median symbol, j = input symbol
     uint32_t  delta;          // cheapest indel of a single non-gap symbol (Ukkonen coefficient)
     uint32_t *arena;          // per warp: direction words + op streams
@@ -19,7 +21,7 @@ struct ExplicitParams {
     int       pairs_per_warp;
     unsigned int *counter;
     unsigned int *overflow_count;
-    uint32_t  k_four, k_minus1, k_one;
+    uint32_t  k_four, k_minus1, k_one, k_64k;
 };
 
 size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries);

@@ -25,10 +25,10 @@
 //
 // No tensor cores: the recurrence is an integer min-plus DP.
 #include "do_device.cuh"
+#include "do_pack16.cuh"
 
 namespace pcgdo {
 
-constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t ld_u16(const char *p) { return *reinterpret_cast<const uint16_t *>(p); }
 __device__ __forceinline__ uint32_t ld_u8(const char *p) { return *reinterpret_cast<const uint8_t *>(p); }
@@ -218,27 +218,11 @@ __device__ __noinline__ uint32_t fill_pair(const Geom g, const FillConst fc, uin
 // Direction words: word[(t >> 3) * 32*H + lane*H + m], cell t of diagonal m (m + H) at bits 2*(7 - (t & 7))
 // of the low (high) half.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t kTop16 = 0x7000u;
-constexpr uint32_t kOverflow16 = 0xffffffffu;
-
 __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
 {
     uint32_t v;
     asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
-}
-
-template <int H>
-__device__ __forceinline__ void store_words16(uint32_t *dst, const uint32_t (&dw)[H], int n)
-{
-    const int sh = 2 * (8 - n);           // left-align a partial group; the halves cannot collide (2n + sh = 16)
-    if constexpr (H >= 4) {
-#pragma unroll
-        for (int m = 0; m < H; m += 4)
-            *reinterpret_cast<uint4 *>(dst + m) = make_uint4(dw[m] << sh, dw[m + 1] << sh, dw[m + 2] << sh, dw[m + 3] << sh);
-    } else {
-        *reinterpret_cast<uint2 *>(dst) = make_uint2(dw[0] << sh, dw[1] << sh);
-    }
 }
 
 template <int B, bool TAIL>
@@ -296,35 +280,6 @@ __device__ __forceinline__ void run_chunk16(uint32_t (&R)[B / 2], const uint32_t
     }
     lptr += 16;
     sptr += 32;
-}
-
-// Move the warp's finite maximum back to kTop16.  Returns false when the finite spread no longer fits the window.
-template <int H>
-__device__ __forceinline__ bool rebase16(uint32_t (&R)[H], int &total_shift, uint32_t spread_limit)
-{
-    uint32_t mx = 0u, mnv = 0xffffffffu;
-#pragma unroll
-    for (int m = 0; m < H; ++m) {
-        mx = __vmaxu2(mx, R[m] ^ 0x80008000u);       // finite halves become >= 0x8000, unreachable ones < 0x8000
-        mnv = __vminu2(mnv, R[m]);
-    }
-    uint32_t hi = max(mx & 0xffffu, mx >> 16), lo = min(mnv & 0xffffu, mnv >> 16);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        hi = max(hi, __shfl_xor_sync(kFull, hi, d));
-        lo = min(lo, __shfl_xor_sync(kFull, lo, d));
-    }
-    if (hi < 0x8000u) return true;                   // no finite cell yet
-    const uint32_t maxf = hi & 0x7ffcu, minf = lo & 0xfffcu;
-    const int delta = (int)kTop16 - (int)maxf;
-    const uint32_t d2 = ((uint32_t)delta & 0xffffu) * 0x00010001u;
-#pragma unroll
-    for (int m = 0; m < H; ++m) {
-        const uint32_t unreach = ((R[m] >> 15) & 0x00010001u) * 0xffffu;
-        R[m] = __vadd2(R[m], d2 & ~unreach);
-    }
-    total_shift += delta;
-    return maxf - minf <= spread_limit;
 }
 
 // Returns the final cell's 4*(v - C - G) + kBias4 | code in the 32-bit convention of fill_pair, or kOverflow16.
@@ -388,29 +343,6 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
     return (uint32_t)((int)kBias4 + x4) | 1u;
 }
 
-// one lane per pair, packed layout
-__device__ __forceinline__ uint32_t trace_lane16(const uint32_t *dirw, int B, int q0, int lg, int sh, uint32_t *ops)
-{
-    const int H = B >> 1;
-    int i = lg - 1, j = sh - 1;
-    uint32_t n = 0, acc = 0, cur_idx = 0xffffffffu, cur_word = 0;
-    while (i > 0 || j > 0) {
-        const int q = j - i + q0;
-        const int t = (i + j - (q & 1)) >> 1;
-        const int ln = q / B, mm = q - ln * B;
-        const int half = mm >= H ? 1 : 0, reg = mm - half * H;
-        const uint32_t idx = (uint32_t)(t >> 3) * (uint32_t)(32 * H) + (uint32_t)(ln * H + reg);
-        if (idx != cur_idx) { cur_word = __ldcg(dirw + idx); cur_idx = idx; }
-        const uint32_t code = (cur_word >> (16 * half + 2 * (7 - (t & 7)))) & 3u;
-        acc |= code << (2 * (n & 15));
-        ++n;
-        if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
-        i -= (code != 2u);
-        j -= (code != 1u);
-    }
-    if (n & 15) ops[n >> 4] = acc;
-    return n;
-}
 
 // ---------------------------------------------------------------------------------------------
 // trace: one lane per pair

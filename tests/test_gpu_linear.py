@@ -271,3 +271,29 @@ def test_bench_strings_golden_through_gpu(gpu_ctx, tcm_file):
     for k, (i, j, cost, n, cg, c1, c2) in enumerate(recs):
         gc = r.pair(pp, k)
         assert (gc[0], len(gc[1]), crc_u8(gc[1]), crc_u8(gc[2]), crc_u8(gc[3])) == (cost, n, cg, c1, c2), (i, j)
+
+
+def test_packed_fill_equals_32bit_fill(oracle_mod, gpu_ctx, monkeypatch):
+    """The packed 16-bit fill (default when the TCM leaves room in its window) against the 32-bit fill
+    (PCGDO_NO_PACK16=1 at TCM creation), and a TCM whose costs force the window to overflow -> fallback."""
+    import pcg_b200 as P
+    rng = np.random.default_rng(77)
+    pairs = [random_pair(rng, 700) for _ in range(300)]
+    pairs += [(random_string(rng, 1500), random_string(rng, 1450)), (random_string(rng, 3000, amb=0.0), random_string(rng, 2900, amb=0.0))]
+    gpu_ctx.configure(max_len=3100, max_b=32)
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    for name in ("l1", "weird"):
+        sig = tcm_matrix(name)
+        r16 = P.align2d_batch(gpu_ctx, gpu_ctx.tcm(sig), pp)
+        monkeypatch.setenv("PCGDO_NO_PACK16", "1")
+        r32 = P.align2d_batch(gpu_ctx, gpu_ctx.tcm(sig), pp)
+        monkeypatch.delenv("PCGDO_NO_PACK16")
+        assert np.array_equal(r16.cost, r32.cost), name
+        assert np.array_equal(r16.out_len, r32.out_len), name
+        assert np.array_equal(r16.gapped, r32.gapped) and np.array_equal(r16.slot1, r32.slot1), name
+    # large indel costs: 4 * 60 per step, the finite spread of long unrelated strings leaves the 15-bit window
+    sig = tcm_matrix("discrete") * 3
+    sig[-1, :-1] = 60
+    sig[:-1, -1] = 60
+    o = oracle_mod.Oracle(sig)
+    _check_batch(o, gpu_ctx, gpu_ctx.tcm(sig), pairs[:60] + pairs[-2:])

@@ -79,3 +79,24 @@ def test_metric_matches_dense_table_path_on_dna(oracle_mod, gpu_ctx):
     pp = P.PackedPairs.from_lists([p[0].astype(np.uint8) for p in pairs], [p[1].astype(np.uint8) for p in pairs])
     rl = P.align2d_batch(gpu_ctx, tcm, pp)
     assert np.array_equal(r.cost, rl.cost)
+
+
+def test_register_kernel_equals_table_kernel(gpu_ctx, monkeypatch):
+    """The discrete metric has two device implementations: the per-pair table kernel (default) and the older
+    kernel that evaluates the overlap per cell in registers (PCGDO_METRIC_REGISTERS=1).  Same results required;
+    PCGDO_NO_PACK16=1 additionally forces the table kernel's 32-bit fill."""
+    from pcg_b200.pairwise import metric_do_batch
+    rng = np.random.default_rng(321)
+    pairs = _pairs(rng, 21, 120, 240)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=300, max_b=32, arena_words=0)
+    f, s = [p[0] for p in pairs], [p[1] for p in pairs]
+    for dialect in (0, 1, 2):
+        ref = metric_do_batch(gpu_ctx, 21, dialect, f, s)
+        for env in ("PCGDO_METRIC_REGISTERS", "PCGDO_NO_PACK16"):
+            monkeypatch.setenv(env, "1")
+            r = metric_do_batch(gpu_ctx, 21, dialect, f, s)
+            monkeypatch.delenv(env)
+            assert np.array_equal(ref.cost, r.cost) and np.array_equal(ref.final_offset, r.final_offset), (dialect, env)
+            for k in range(len(pairs)):
+                for x, y in zip(ref.pair(k)[1:], r.pair(k)[1:]):
+                    assert np.array_equal(x, y), (dialect, env, k)
