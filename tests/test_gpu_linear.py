@@ -292,8 +292,11 @@ def test_packed_fill_equals_32bit_fill(oracle_mod, gpu_ctx, monkeypatch):
         assert np.array_equal(r16.out_len, r32.out_len), name
         assert np.array_equal(r16.gapped, r32.gapped) and np.array_equal(r16.slot1, r32.slot1), name
     # large indel costs: 4 * 60 per step, the finite spread of long unrelated strings leaves the 15-bit window
-    sig = tcm_matrix("discrete") * 3
-    sig[-1, :-1] = 60
-    sig[:-1, -1] = 60
-    o = oracle_mod.Oracle(sig)
-    _check_batch(o, gpu_ctx, gpu_ctx.tcm(sig), pairs[:60] + pairs[-2:])
+    # indel 60: statically outside the packed window; indel 20: inside it statically, but the sweep of long
+    # unrelated strings overflows it dynamically -> redone by the 32-bit fill
+    for indel in (60, 20):
+        sig = tcm_matrix("discrete") * 3
+        sig[-1, :-1] = indel
+        sig[:-1, -1] = indel
+        o = oracle_mod.Oracle(sig)
+        _check_batch(o, gpu_ctx, gpu_ctx.tcm(sig), pairs[:60] + pairs[-2:])
