@@ -235,6 +235,17 @@ int  pcgdo_forest_copy_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *forest, void *ds
 int  pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *forest, uint32_t tree, uint32_t character, uint32_t node,
                            uint8_t *median_out, uint32_t *len_out, int32_t *local_cost, int64_t *total_cost);
 uint32_t pcgdo_forest_levels(const pcgdo_forest *forest);
+/* Re-rooting of dynamic characters (Bio/Graph/PhylogeneticDAG/DynamicCharacterRerooting.hs:70-420, trees only): after
+ * the post-order, directed subtree data for every internal node (a pre-order sweep by depth) and one cost-only
+ * alignment per unrooted edge; per-tree cost = sum over characters of the minimum over the 2*n_taxa-3 edges (each
+ * dynamic character picks its own root edge).  enable_rerooting grows the node storage to 3 slots per internal
+ * node.  get_edges: (u, v) node ids of one tree's edges (edge 0 = the original root edge) and, for one character,
+ * the total / local cost of rooting on each. */
+int  pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *forest);
+int  pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *forest, void *cuda_stream);
+int  pcgdo_forest_get_edges(pcgdo_ctx *ctx, pcgdo_forest *forest, uint32_t tree, uint32_t character, int32_t *edge_uv,
+                            int64_t *edge_total, int32_t *edge_local);
+uint32_t pcgdo_forest_edges(const pcgdo_forest *forest);
 uint64_t pcgdo_forest_alignments(const pcgdo_forest *forest);
 
 /* Measured integer instruction-issue rate of this GPU in lane-instructions/s (roofline denominator of the

@@ -94,6 +94,12 @@ int64_t oracle_haskell_do(int dialect, int metric_kind, const uint32_t *sigma, i
                           uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
                           uint64_t *cells, int *final_offset);
 
+/* Re-rooting pass for one tree and one dynamic character (reroot_oracle.c; trees only).  2*n_taxa - 3 edges are
+ * reported, edge 0 = the original root edge; returns the minimum total over the edges. */
+int64_t oracle_reroot(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *children,
+                      const uint32_t *const *leaf, const size_t *leaf_len,
+                      int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells);
+
 /* the same with every overlap answered by `lookup` (returns the cost, writes the median) */
 typedef uint64_t (*oracle_lookup_fn)(void *ctx, uint32_t x, uint32_t y, uint32_t *med);
 int64_t oracle_haskell_do_lookup(int dialect, oracle_lookup_fn lookup, void *lookup_ctx, int a,

@@ -146,6 +146,26 @@ class Oracle:
         return int(cost), np.stack([om[:k], ol[:k], orr[:k]], axis=1), int(cells.value)
 
 
+def reroot(oracle: "Oracle", children, leaves):
+    """Re-rooting pass of one tree / one character (reroot_oracle.c).  children: (n_taxa-1, 2) int32, leaves: list of
+    element strings.  Returns (min cost, edges [(u, v)], edge_cost, edge_local)."""
+    lib = oracle.lib
+    lib.oracle_reroot.restype = C.c_int64
+    lib.oracle_reroot.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    ch = np.ascontiguousarray(np.asarray(children, np.int32))
+    n_taxa = ch.shape[0] + 1
+    arrs = [_as_u32(x) for x in leaves]
+    ptrs = (C.c_void_p * n_taxa)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_size_t * n_taxa)(*[len(a) for a in arrs])
+    ne = 2 * n_taxa - 3
+    eu, ev = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
+    ec, el = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
+    best = lib.oracle_reroot(oracle.t, n_taxa, ch.ctypes.data, ptrs, lens, eu.ctypes.data, ev.ctypes.data,
+                             ec.ctypes.data, el.ctypes.data, None)
+    return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el
+
+
 def haskell_do(dialect: int, a: int, in1, in2, sigma=None):
     """S1 / S2 Haskell dialects on median strings (see do_oracle.c). sigma=None -> discrete metric.
     Returns (cost, median, aligned1, aligned2, cells, final_offset)."""

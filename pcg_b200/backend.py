@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
+    "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges",
     "pcgdo_memo_create", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
     "pcgdo_explicit_batch_device", "pcgdo_explicit_batch_host",
     "matrixInit", "matrixDestroy", "getCostAndMedian2D",
@@ -121,6 +122,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_forest_levels.restype = C.c_uint32
     L.pcgdo_forest_alignments.argtypes = [C.c_void_p]
     L.pcgdo_forest_alignments.restype = C.c_uint64
+    L.pcgdo_forest_enable_rerooting.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_score_rerooted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_get_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_edges.argtypes = [C.c_void_p]
+    L.pcgdo_forest_edges.restype = C.c_uint32
     L.pcgdo_memo_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.POINTER(C.c_void_p)]
     L.pcgdo_memo_destroy.argtypes = [C.c_void_p, C.c_void_p]
     L.pcgdo_overlap2d_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 5
@@ -308,6 +314,32 @@ class Forest:
                        "pcgdo_forest_score")
         self.ctx.check(self.ctx.lib.pcgdo_forest_copy_tree_costs(self.ctx.h, self.h, C.c_void_p(dst_device_ptr),
                                                                  C.c_void_p(stream)), "pcgdo_forest_copy_tree_costs")
+
+    def enable_rerooting(self) -> None:
+        self.ctx.check(self.ctx.lib.pcgdo_forest_enable_rerooting(self.ctx.h, self.h), "pcgdo_forest_enable_rerooting")
+
+    def score_rerooted(self, tcm: Tcm, stream: int = 0) -> np.ndarray:
+        """Post-order + re-rooting: per-tree sum over characters of the cheapest root edge."""
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score_rerooted(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+                       "pcgdo_forest_score_rerooted")
+        out = np.zeros(self.n_trees, np.int64)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_tree_costs(self.ctx.h, self.h, out.ctypes.data),
+                       "pcgdo_forest_tree_costs")
+        return out
+
+    def score_rerooted_into(self, tcm: Tcm, dst_device_ptr: int, stream: int = 0) -> None:
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score_rerooted(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+                       "pcgdo_forest_score_rerooted")
+        self.ctx.check(self.ctx.lib.pcgdo_forest_copy_tree_costs(self.ctx.h, self.h, C.c_void_p(dst_device_ptr),
+                                                                 C.c_void_p(stream)), "pcgdo_forest_copy_tree_costs")
+
+    def edges(self, tree: int, character: int):
+        """((u, v) per unrooted edge, total cost of rooting there, local cost); edge 0 = the original root edge."""
+        ne = int(self.ctx.lib.pcgdo_forest_edges(self.h))
+        uv, tot, loc = np.zeros((ne, 2), np.int32), np.zeros(ne, np.int64), np.zeros(ne, np.int32)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_get_edges(self.ctx.h, self.h, tree, character, uv.ctypes.data,
+                                                           tot.ctypes.data, loc.ctypes.data), "pcgdo_forest_get_edges")
+        return uv, tot, loc
 
     def node(self, tree: int, character: int, node: int):
         buf = np.zeros(self.node_cap, np.uint8)

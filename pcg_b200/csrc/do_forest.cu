@@ -14,6 +14,15 @@
 // DO/Pairwise/Internal.hs:364-381), so that is what nodes keep resident in HBM: fixed-capacity byte slots,
 // leaves shared by all trees.  No host round trip between levels; one check of the overflow counters at
 // the end.  Multi-GPU: ranks own character blocks of the same trees and all-reduce the per-tree sums.
+//
+// Re-rooting (pcgdo_forest_enable_rerooting / pcgdo_forest_score_rerooted; trees only) replaces
+//   .../PhylogeneticDAG/DynamicCharacterRerooting.hs:70-420  (assignOptimalDynamicCharacterRootEdges):
+// after the post-order, a PRE-ORDER sweep by depth computes for every internal non-root node n with adjacent
+// nodes [c1, c2, p] (children in index order, unrooted parent = the sibling when the parent is the root) the two
+// directed data "n entered from c1" = DO(n->c2 , n->p) and "n entered from c2" = DO(n->p , n->c1) (:291-326; the
+// third, "entered from p", is the post-order datum), then ONE cost-only batch aligns, for every non-root edge
+// (q, child), "q entered from child" with the child's post-order datum (:176-199); per character the minimum over
+// the 2n-3 edges (the root edge keeps the post-order root) is the re-rooted cost (:345-420).
 #include "do_ctx.h"
 
 #include <algorithm>
@@ -21,10 +30,20 @@
 
 using namespace pcgdo;
 
-struct LevelItem { int32_t tree, x, left, right; };   // x = internal index (node id = n_taxa + x)
+// out = slot of the result within its (tree, character) column: x for the post-order datum of internal node x,
+// n_internal + 2x + s for "x entered from its s-th child (index order)", or an edge number for cost-only edge jobs;
+// left / right = node refs: < n_taxa a leaf, otherwise n_taxa + slot
+struct LevelItem { int32_t tree, out, left, right; };
 
 struct pcgdo_forest {
     uint32_t n_trees = 0, n_taxa = 0, n_chars = 0, cap = 0, n_internal = 0;
+    uint32_t stride = 0;                 // result slots per (tree, character) column: n_internal, or 3x with re-rooting
+    bool reroot = false;
+    uint32_t n_edges = 0;                // 2 * n_taxa - 3 unrooted edges per tree, edge 0 = the root edge
+    std::vector<int32_t> h_children, h_edges;                 // h_edges: (u, v) per tree and edge
+    std::vector<std::pair<size_t, size_t>> up_levels;         // pre-order levels (by depth) of directed-datum jobs
+    std::pair<size_t, size_t> edge_items{0, 0};
+    DevBuf edge_total, edge_local, char_min;                  // i64 / i32 [n_trees*n_chars*n_edges], i64 [n_trees*n_chars]
     size_t leaf_bytes = 0;
     DevBuf store;        // [leaf slots | internal-node slots], cap bytes each
     DevBuf leaf_len;     // u32 [n_taxa * n_chars]
@@ -43,7 +62,7 @@ struct pcgdo_forest {
 namespace {
 
 struct ForestDev {
-    uint32_t n_taxa, n_chars, n_internal, cap;
+    uint32_t n_taxa, n_chars, n_internal, cap;        // n_internal = result slots per column (stride)
     uint64_t leaf_bytes;
     const uint32_t *leaf_len;
     uint32_t *node_len;
@@ -70,7 +89,7 @@ __global__ void forest_prep_kernel(ForestDev f, const LevelItem *items, uint32_t
     const uint32_t c = (uint32_t)(k % f.n_chars);
     off1[k] = slot_of(f, it.tree, c, it.left);
     off2[k] = slot_of(f, it.tree, c, it.right);
-    uoff[k] = slot_of(f, it.tree, c, (int32_t)(f.n_taxa + it.x));
+    uoff[k] = slot_of(f, it.tree, c, (int32_t)(f.n_taxa + it.out));
     len1[k] = (uint32_t)it.left < f.n_taxa ? f.leaf_len[(uint64_t)it.left * f.n_chars + c]
                                            : f.node_len[nidx(f, it.tree, c, it.left - f.n_taxa)];
     len2[k] = (uint32_t)it.right < f.n_taxa ? f.leaf_len[(uint64_t)it.right * f.n_chars + c]
@@ -84,7 +103,7 @@ __global__ void forest_post_kernel(ForestDev f, const LevelItem *items, uint32_t
     if (k >= (uint64_t)n_items * f.n_chars) return;
     const LevelItem it = items[k / f.n_chars];
     const uint32_t c = (uint32_t)(k % f.n_chars);
-    const uint64_t me = nidx(f, it.tree, c, it.x);
+    const uint64_t me = nidx(f, it.tree, c, it.out);
     int64_t tot = cost[k];
     if ((uint32_t)it.left >= f.n_taxa) tot += f.node_total[nidx(f, it.tree, c, it.left - f.n_taxa)];
     if ((uint32_t)it.right >= f.n_taxa) tot += f.node_total[nidx(f, it.tree, c, it.right - f.n_taxa)];
@@ -103,10 +122,51 @@ __global__ void forest_reduce_kernel(ForestDev f, const int32_t *roots, uint32_t
     tree_cost[t] = s;
 }
 
+// cost-only edge jobs: total of rooting on that edge = local + both data's totals
+__global__ void forest_edge_post_kernel(ForestDev f, const LevelItem *items, uint32_t n_items, const int32_t *cost,
+                                        uint32_t n_edges, int64_t *edge_total, int32_t *edge_local)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (uint64_t)n_items * f.n_chars) return;
+    const LevelItem it = items[k / f.n_chars];
+    const uint32_t c = (uint32_t)(k % f.n_chars);
+    int64_t tot = cost[k];
+    if ((uint32_t)it.left >= f.n_taxa) tot += f.node_total[nidx(f, it.tree, c, it.left - f.n_taxa)];
+    if ((uint32_t)it.right >= f.n_taxa) tot += f.node_total[nidx(f, it.tree, c, it.right - f.n_taxa)];
+    const uint64_t e = ((uint64_t)it.tree * f.n_chars + c) * n_edges + (uint32_t)it.out;
+    edge_total[e] = tot;
+    edge_local[e] = cost[k];
+}
+
+// per (tree, character): the root edge keeps the post-order root; minimum over all edges
+__global__ void forest_edge_min_kernel(ForestDev f, const int32_t *roots, uint32_t n_trees, uint32_t n_edges,
+                                       int64_t *edge_total, int32_t *edge_local, int64_t *char_min)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (uint64_t)n_trees * f.n_chars) return;
+    const uint32_t t = (uint32_t)(k / f.n_chars), c = (uint32_t)(k % f.n_chars);
+    const uint64_t r = nidx(f, t, c, (uint32_t)roots[t]);
+    int64_t *et = edge_total + k * n_edges;
+    et[0] = f.node_total[r];
+    edge_local[k * n_edges] = f.node_local[r];
+    int64_t best = et[0];
+    for (uint32_t e = 1; e < n_edges; ++e) best = min(best, et[e]);
+    char_min[k] = best;
+}
+
+__global__ void forest_reduce_min_kernel(uint32_t n_chars, const int64_t *char_min, uint32_t n_trees, int64_t *tree_cost)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    int64_t s = 0;
+    for (uint32_t c = 0; c < n_chars; ++c) s += char_min[(uint64_t)t * n_chars + c];
+    tree_cost[t] = s;
+}
+
 ForestDev dev_view(const pcgdo_forest *F)
 {
     ForestDev f;
-    f.n_taxa = F->n_taxa; f.n_chars = F->n_chars; f.n_internal = F->n_internal; f.cap = F->cap;
+    f.n_taxa = F->n_taxa; f.n_chars = F->n_chars; f.n_internal = F->stride; f.cap = F->cap;
     f.leaf_bytes = F->leaf_bytes;
     f.leaf_len = (const uint32_t *)F->leaf_len.p;
     f.node_len = (uint32_t *)F->node_len.p;
@@ -126,6 +186,9 @@ extern "C" int pcgdo_forest_create(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_
     F->n_trees = n_trees; F->n_taxa = n_taxa; F->n_chars = n_chars;
     F->cap = (node_cap + 3u) & ~3u;
     F->n_internal = n_taxa - 1;
+    F->stride = F->n_internal;
+    F->n_edges = n_taxa >= 3 ? 2 * n_taxa - 3 : 1;
+    F->h_children.assign(children, children + (size_t)n_trees * (n_taxa - 1) * 2);
     const uint32_t ni = F->n_internal, n_nodes = 2 * n_taxa - 1;
     // heights per tree -> items grouped by height
     std::vector<std::vector<LevelItem>> by_h;
@@ -211,7 +274,8 @@ extern "C" void pcgdo_forest_destroy(pcgdo_ctx *ctx, pcgdo_forest *F)
     if (!F) return;
     if (ctx) cudaSetDevice(ctx->device);
     DevBuf *bufs[] = {&F->store, &F->leaf_len, &F->node_len, &F->node_local, &F->node_total, &F->items, &F->roots,
-                      &F->tree_cost, &F->boff1, &F->boff2, &F->buoff, &F->blen1, &F->blen2, &F->bcost, &F->bulen};
+                      &F->tree_cost, &F->boff1, &F->boff2, &F->buoff, &F->blen1, &F->blen2, &F->bcost, &F->bulen,
+                      &F->edge_total, &F->edge_local, &F->char_min};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete F;
@@ -238,21 +302,16 @@ extern "C" int pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *F, const ui
     return PCGDO_OK;
 }
 
-// One post-order sweep over all trees and this forest's characters.  tree_cost_out: DEVICE pointer to
-// n_trees int64 (may be NULL: read the forest's own buffer with pcgdo_forest_tree_cost_ptr).
-extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, void *cuda_stream)
+// Enqueue one batch of forest jobs: mode 0 = data (ungapped median of the result kept in its slot, totals
+// accumulated), mode 1 = cost-only edge jobs.
+static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, cudaStream_t st, size_t first_item,
+                            size_t count, int mode, bool &first, LinearParams &p)
 {
-    if (!ctx || !tcm || !F) return PCGDO_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const ForestDev f = dev_view(F);
-    ctx->last_launches = 0;
-    CK(cudaEventRecord(ctx->ev0, st));
-    bool first = true;
-    LinearParams p{};
-    for (const auto &lv : F->levels) {
-        const LevelItem *items = (const LevelItem *)F->items.p + lv.first;
-        const uint32_t n_items = (uint32_t)lv.second;
+    const size_t chunk = F->max_level_items ? F->max_level_items : count;
+    for (size_t c0 = 0; c0 < count; c0 += chunk) {
+        const LevelItem *items = (const LevelItem *)F->items.p + first_item + c0;
+        const uint32_t n_items = (uint32_t)std::min(chunk, count - c0);
         const uint64_t n_pairs = (uint64_t)n_items * F->n_chars;
         const uint32_t blocks = (uint32_t)((n_pairs + 255) / 256);
         forest_prep_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (uint64_t *)F->boff1.p, (uint64_t *)F->boff2.p,
@@ -265,24 +324,29 @@ extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_fo
         bd.off1 = (const uint64_t *)F->boff1.p; bd.off2 = (const uint64_t *)F->boff2.p;
         bd.len1 = (const uint32_t *)F->blen1.p; bd.len2 = (const uint32_t *)F->blen2.p;
         bd.cost = (int32_t *)F->bcost.p;
-        bd.out_ungapped = (uint8_t *)F->store.p;
-        bd.out_uoff = (const uint64_t *)F->buoff.p;
-        bd.out_ulen = (uint32_t *)F->bulen.p;
-        bd.ucap = F->cap;
+        if (mode == 0) {
+            bd.out_ungapped = (uint8_t *)F->store.p;
+            bd.out_uoff = (const uint64_t *)F->buoff.p;
+            bd.out_ulen = (uint32_t *)F->bulen.p;
+            bd.ucap = F->cap;
+        }
         int rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, first, &p, nullptr);
         if (rc) return rc;
         first = false;
-        forest_post_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p,
-                                                   (const uint32_t *)F->bulen.p);
+        if (mode == 0)
+            forest_post_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p,
+                                                       (const uint32_t *)F->bulen.p);
+        else
+            forest_edge_post_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p, F->n_edges,
+                                                            (int64_t *)F->edge_total.p, (int32_t *)F->edge_local.p);
         CK(cudaGetLastError());
         ctx->last_launches += 2;
     }
-    forest_reduce_kernel<<<(F->n_trees + 127) / 128, 128, 0, st>>>(f, (const int32_t *)F->roots.p, F->n_trees,
-                                                                  (int64_t *)F->tree_cost.p);
-    CK(cudaGetLastError());
-    ctx->last_launches += 1;
-    CK(cudaEventRecord(ctx->ev1, st));
-    ctx->timed = true;
+    return PCGDO_OK;
+}
+
+static int forest_check(pcgdo_ctx *ctx, pcgdo_forest *F, const LinearParams &p, cudaStream_t st)
+{
     // one look at the failure counters for the whole sweep: pairs beyond the warp kernels' limits, wide pairs
     // with the wide kernel disabled, node strings beyond their slot
     unsigned int h[10] = {0};
@@ -298,6 +362,196 @@ extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_fo
     }
     return PCGDO_OK;
 }
+
+// One post-order sweep over all trees and this forest's characters; per-tree cost = sum of the root totals.
+extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, void *cuda_stream)
+{
+    if (!ctx || !tcm || !F) return PCGDO_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const ForestDev f = dev_view(F);
+    ctx->last_launches = 0;
+    CK(cudaEventRecord(ctx->ev0, st));
+    bool first = true;
+    LinearParams p{};
+    int rc;
+    for (const auto &lv : F->levels)
+        if ((rc = forest_run_items(ctx, tcm, F, st, lv.first, lv.second, 0, first, p))) return rc;
+    forest_reduce_kernel<<<(F->n_trees + 127) / 128, 128, 0, st>>>(f, (const int32_t *)F->roots.p, F->n_trees,
+                                                                  (int64_t *)F->tree_cost.p);
+    CK(cudaGetLastError());
+    ctx->last_launches += 1;
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    return forest_check(ctx, F, p, st);
+}
+
+// Builds the pre-order (directed data) and edge job lists and grows the node storage to 3 result slots per
+// internal node.  Call once, before or after pcgdo_forest_set_leaves.
+extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F)
+{
+    if (!ctx || !F) return PCGDO_ERR_ARG;
+    if (F->reroot) return PCGDO_OK;
+    if (F->n_taxa < 3) {
+        ctx->err = "re-rooting needs at least 3 taxa";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n_taxa = F->n_taxa, ni = F->n_internal, n_nodes = 2 * n_taxa - 1;
+    std::vector<std::vector<LevelItem>> by_depth;
+    std::vector<LevelItem> edges;
+    F->h_edges.assign((size_t)F->n_trees * F->n_edges * 2, 0);
+    std::vector<int32_t> parent(n_nodes), side(n_nodes), depth(n_nodes), order;
+    for (uint32_t t = 0; t < F->n_trees; ++t) {
+        const int32_t *ch = F->h_children.data() + (size_t)t * ni * 2;
+        const int32_t root = (int32_t)(n_taxa + (uint32_t)F->h_roots[t]);
+        std::fill(parent.begin(), parent.end(), -1);
+        for (uint32_t x = 0; x < ni; ++x) {
+            // "s-th child in index order" (IM.keys of childRefs is ascending)
+            const int32_t c0 = std::min(ch[2 * x], ch[2 * x + 1]), c1 = std::max(ch[2 * x], ch[2 * x + 1]);
+            parent[c0] = (int32_t)(n_taxa + x); side[c0] = 0;
+            parent[c1] = (int32_t)(n_taxa + x); side[c1] = 1;
+        }
+        // depths, top-down
+        order.clear();
+        order.push_back(root);
+        depth[root] = 0;
+        for (size_t q = 0; q < order.size(); ++q) {
+            const int32_t v = order[q];
+            if ((uint32_t)v < n_taxa) continue;
+            for (int s = 0; s < 2; ++s) {
+                const int32_t c = ch[2 * (v - n_taxa) + s];
+                depth[c] = depth[v] + 1;
+                order.push_back(c);
+            }
+        }
+        auto up_ref = [&](int32_t q, int s) { return (int32_t)(n_taxa + ni + 2 * (uint32_t)(q - n_taxa) + (uint32_t)s); };
+        // the datum of n's unrooted parent entered from n
+        auto parent_side = [&](int32_t n) -> int32_t {
+            const int32_t q = parent[n];
+            if (q == root) {                                     // the sibling under the root, entered from n:
+                const int32_t x = q - (int32_t)n_taxa;           // equal to the sibling's post-order datum
+                return ch[2 * x] == n ? ch[2 * x + 1] : ch[2 * x];
+            }
+            return up_ref(q, side[n]);
+        };
+        int32_t *he = F->h_edges.data() + (size_t)t * F->n_edges * 2;
+        {
+            const int32_t x = root - (int32_t)n_taxa;
+            he[0] = std::min(ch[2 * x], ch[2 * x + 1]); he[1] = std::max(ch[2 * x], ch[2 * x + 1]);
+        }
+        uint32_t ne = 1;
+        for (const int32_t n : order) {
+            if ((uint32_t)n < n_taxa || n == root) continue;
+            const int32_t x = n - (int32_t)n_taxa;
+            const int32_t c1 = std::min(ch[2 * x], ch[2 * x + 1]), c2 = std::max(ch[2 * x], ch[2 * x + 1]);
+            const int32_t ps = parent_side(n);
+            const size_t d = (size_t)depth[n];
+            if (by_depth.size() <= d) by_depth.resize(d + 1);
+            // rotations (i, j, k) of [c1, c2, p]: entered from c1 = DO(c2-side, p-side); from c2 = DO(p-side, c1-side)
+            by_depth[d].push_back({(int32_t)t, (int32_t)(ni + 2 * (uint32_t)x + 0), c2, ps});
+            by_depth[d].push_back({(int32_t)t, (int32_t)(ni + 2 * (uint32_t)x + 1), ps, c1});
+            // the two edges below n: DO("n entered from the child", the child's post-order datum)
+            edges.push_back({(int32_t)t, (int32_t)ne, up_ref(n, 0), c1}); he[2 * ne] = n; he[2 * ne + 1] = c1; ++ne;
+            edges.push_back({(int32_t)t, (int32_t)ne, up_ref(n, 1), c2}); he[2 * ne] = n; he[2 * ne + 1] = c2; ++ne;
+        }
+        if (ne != F->n_edges) {
+            ctx->err = "re-rooting: internal error enumerating the unrooted edges";
+            return PCGDO_ERR_ARG;
+        }
+    }
+    // append the new job lists to the item array
+    const size_t n_post = F->levels.empty() ? 0 : F->levels.back().first + F->levels.back().second;
+    std::vector<LevelItem> all(n_post);
+    CK(cudaMemcpy(all.data(), F->items.p, n_post * sizeof(LevelItem), cudaMemcpyDeviceToHost));
+    for (auto &lv : by_depth) {
+        if (lv.empty()) continue;
+        F->up_levels.push_back({all.size(), lv.size()});
+        F->max_level_items = std::max(F->max_level_items, lv.size());
+        all.insert(all.end(), lv.begin(), lv.end());
+    }
+    F->edge_items = {all.size(), edges.size()};
+    all.insert(all.end(), edges.begin(), edges.end());
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, F->items, all.size() * sizeof(LevelItem)))) return rc;
+    CK(cudaMemcpy(F->items.p, all.data(), all.size() * sizeof(LevelItem), cudaMemcpyHostToDevice));
+    // 3 result slots per internal node; the leaf region (front of the store) is preserved
+    const uint32_t stride = 3 * ni;
+    const size_t n_slots = (size_t)F->n_trees * F->n_chars * stride;
+    DevBuf store;
+    if ((rc = pcgdo_ensure(ctx, store, F->leaf_bytes + n_slots * F->cap + 64))) return rc;
+    CK(cudaMemcpy(store.p, F->store.p, F->leaf_bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaFree(F->store.p));
+    F->store = store;
+    if ((rc = pcgdo_ensure(ctx, F->node_len, n_slots * 4)) || (rc = pcgdo_ensure(ctx, F->node_local, n_slots * 4)) ||
+        (rc = pcgdo_ensure(ctx, F->node_total, n_slots * 8)))
+        return rc;
+    const size_t n_cols = (size_t)F->n_trees * F->n_chars;
+    if ((rc = pcgdo_ensure(ctx, F->edge_total, n_cols * F->n_edges * 8)) ||
+        (rc = pcgdo_ensure(ctx, F->edge_local, n_cols * F->n_edges * 4)) || (rc = pcgdo_ensure(ctx, F->char_min, n_cols * 8)))
+        return rc;
+    const size_t mb = F->max_level_items * F->n_chars;
+    if ((rc = pcgdo_ensure(ctx, F->boff1, mb * 8)) || (rc = pcgdo_ensure(ctx, F->boff2, mb * 8)) ||
+        (rc = pcgdo_ensure(ctx, F->buoff, mb * 8)) || (rc = pcgdo_ensure(ctx, F->blen1, mb * 4)) ||
+        (rc = pcgdo_ensure(ctx, F->blen2, mb * 4)) || (rc = pcgdo_ensure(ctx, F->bcost, mb * 4)) ||
+        (rc = pcgdo_ensure(ctx, F->bulen, mb * 4)))
+        return rc;
+    F->stride = stride;
+    F->reroot = true;
+    return PCGDO_OK;
+}
+
+// Post-order, directed data (pre-order by depth), edge costs; per-tree cost = sum over characters of the minimum
+// over the tree's unrooted edges (every dynamic character picks its own best root edge).
+extern "C" int pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, void *cuda_stream)
+{
+    if (!ctx || !tcm || !F) return PCGDO_ERR_ARG;
+    if (!F->reroot) {
+        ctx->err = "call pcgdo_forest_enable_rerooting first";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const ForestDev f = dev_view(F);
+    ctx->last_launches = 0;
+    CK(cudaEventRecord(ctx->ev0, st));
+    bool first = true;
+    LinearParams p{};
+    int rc;
+    for (const auto &lv : F->levels)
+        if ((rc = forest_run_items(ctx, tcm, F, st, lv.first, lv.second, 0, first, p))) return rc;
+    for (const auto &lv : F->up_levels)
+        if ((rc = forest_run_items(ctx, tcm, F, st, lv.first, lv.second, 0, first, p))) return rc;
+    if ((rc = forest_run_items(ctx, tcm, F, st, F->edge_items.first, F->edge_items.second, 1, first, p))) return rc;
+    const uint64_t n_cols = (uint64_t)F->n_trees * F->n_chars;
+    forest_edge_min_kernel<<<(uint32_t)((n_cols + 127) / 128), 128, 0, st>>>(
+        f, (const int32_t *)F->roots.p, F->n_trees, F->n_edges, (int64_t *)F->edge_total.p, (int32_t *)F->edge_local.p,
+        (int64_t *)F->char_min.p);
+    CK(cudaGetLastError());
+    forest_reduce_min_kernel<<<(F->n_trees + 127) / 128, 128, 0, st>>>(F->n_chars, (const int64_t *)F->char_min.p,
+                                                                      F->n_trees, (int64_t *)F->tree_cost.p);
+    CK(cudaGetLastError());
+    ctx->last_launches += 2;
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    return forest_check(ctx, F, p, st);
+}
+
+// For parity tests / reporting: the 2*n_taxa-3 unrooted edges of one tree ((u, v) node ids; edge 0 = the root edge)
+// and, for one character, the total and local cost of rooting on each of them.  Any output may be NULL.
+extern "C" int pcgdo_forest_get_edges(pcgdo_ctx *ctx, pcgdo_forest *F, uint32_t tree, uint32_t c, int32_t *edge_uv,
+                                      int64_t *edge_total, int32_t *edge_local)
+{
+    if (!ctx || !F || !F->reroot || tree >= F->n_trees || c >= F->n_chars) return PCGDO_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (edge_uv) std::copy(F->h_edges.begin() + (size_t)tree * F->n_edges * 2,
+                           F->h_edges.begin() + (size_t)(tree + 1) * F->n_edges * 2, edge_uv);
+    const size_t base = ((size_t)tree * F->n_chars + c) * F->n_edges;
+    if (edge_total) CK(cudaMemcpy(edge_total, (int64_t *)F->edge_total.p + base, (size_t)F->n_edges * 8, cudaMemcpyDeviceToHost));
+    if (edge_local) CK(cudaMemcpy(edge_local, (int32_t *)F->edge_local.p + base, (size_t)F->n_edges * 4, cudaMemcpyDeviceToHost));
+    return PCGDO_OK;
+}
+extern "C" uint32_t pcgdo_forest_edges(const pcgdo_forest *F) { return F ? F->n_edges : 0; }
 
 extern "C" void *pcgdo_forest_tree_cost_ptr(pcgdo_forest *F) { return F ? F->tree_cost.p : nullptr; }
 
@@ -328,7 +582,7 @@ extern "C" int pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *F, uint32_t t
         return PCGDO_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const uint32_t x = node - F->n_taxa;
-    const size_t me = ((size_t)tree * F->n_chars + c) * F->n_internal + x;
+    const size_t me = ((size_t)tree * F->n_chars + c) * F->stride + x;
     uint32_t len = 0;
     CK(cudaMemcpy(&len, (uint32_t *)F->node_len.p + me, 4, cudaMemcpyDeviceToHost));
     if (len_out) *len_out = len;

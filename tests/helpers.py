@@ -72,3 +72,25 @@ def bench_strings_golden():
 def crc_u8(a):
     import zlib
     return zlib.crc32(np.asarray(a, np.uint8).tobytes())
+
+
+def chel_golden_tree():
+    """The reference's chel golden tree in the forest's numbering: (golden dict, children[1, 16, 2], per-taxon
+    ungapped leaf strings, golden-id -> node-id map)."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "chel_golden.json")))
+    nodes = g["nodes"]
+    leaf_ids = [n["id"] for n in nodes if not n["children"]]
+    int_ids = [n["id"] for n in nodes if n["children"]]
+    n_taxa = len(leaf_ids)
+    to_mine = {gid: k for k, gid in enumerate(leaf_ids)}
+    to_mine.update({gid: n_taxa + k for k, gid in enumerate(int_ids)})
+    children = np.zeros((1, n_taxa - 1, 2), np.int32)
+    for k, gid in enumerate(int_ids):
+        l, r = sorted(nodes[gid]["children"])
+        children[0, k] = (to_mine[l], to_mine[r])
+    leaves = []
+    for gid in leaf_ids:
+        c = np.array(nodes[gid]["context"], np.uint8)
+        leaves.append(c[c[:, 0] != 16][:, 0].copy())
+    return g, children, leaves, to_mine

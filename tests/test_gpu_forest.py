@@ -120,3 +120,63 @@ def test_forest_reports_node_overflow(gpu_ctx):
     with pytest.raises(P.BackendError):
         f.score(tcm)      # medians of unrelated strings grow beyond 60 elements: must fail loudly
     f.close()
+
+
+def test_forest_rerooting_matches_oracle(oracle_mod, gpu_ctx):
+    """Directed subtree data + edge costs on the device against the restatement of the re-rooting pass."""
+    import pcg_b200 as P
+    from pcg_b200.postorder import random_binary_trees
+    sig = tcm_matrix("discrete")
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=600, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(sig)
+    n_trees, n_taxa, n_chars = 6, 13, 2
+    rng = np.random.default_rng(77)
+    children = random_binary_trees(n_trees, n_taxa, seed=11)
+    base = [random_string(rng, 70, amb=0.0) for _ in range(n_chars)]
+    leaves = []
+    for v in range(n_taxa):          # related strings: mutated copies of a common ancestor, ragged lengths
+        row = []
+        for c in range(n_chars):
+            s = base[c].copy()
+            mut = rng.random(len(s)) < 0.25
+            s = np.where(mut, random_string(rng, len(s), amb=0.1), s).astype(np.uint8)
+            s = s[rng.random(len(s)) > 0.1]
+            s[s == 16] = 2
+            row.append(s)
+        leaves.append(row)
+    f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=768)
+    plain = f.score(tcm)
+    f.enable_rerooting()
+    again = f.score(tcm)             # the post-order alone still works on the grown storage
+    assert np.array_equal(plain, again)
+    costs = f.score_rerooted(tcm)
+    for t in range(n_trees):
+        want = 0
+        for c in range(n_chars):
+            best, edges, ec, el = oracle_mod.reroot(o, children[t], [leaves[v][c] for v in range(n_taxa)])
+            uv, tot, loc = f.edges(t, c)
+            got = {(int(a), int(b)): (int(x), int(y)) for (a, b), x, y in zip(uv, tot, loc)}
+            ref = {(int(a), int(b)): (int(x), int(y)) for (a, b), x, y in zip(edges, ec, el)}
+            assert {tuple(sorted(k)): v for k, v in got.items()} == {tuple(sorted(k)): v for k, v in ref.items()}, (t, c)
+            want += best
+        assert int(costs[t]) == want, t
+        assert int(costs[t]) <= int(plain[t])
+    f.close()
+
+
+def test_forest_rerooting_on_reference_golden_tree(gpu_ctx):
+    """chel golden test through the device: re-rooted total 336, local cost 49 on the single minimal edge."""
+    import pcg_b200 as P
+    from tests.helpers import chel_golden_tree
+    g, children, leaves, _ = chel_golden_tree()
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=400, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(tcm_matrix("discrete"))
+    f = P.Forest(gpu_ctx, children, 17, [[s] for s in leaves], node_cap=512)
+    f.enable_rerooting()
+    costs = f.score_rerooted(tcm)
+    assert int(costs[0]) == 336 == g["nodes"][0]["total_cost"]
+    uv, tot, loc = f.edges(0, 0)
+    k = int(np.argmin(tot))
+    assert (tot == 336).sum() == 1 and int(loc[k]) == 49 == g["nodes"][0]["local_cost"]
+    f.close()

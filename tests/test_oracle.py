@@ -152,3 +152,18 @@ def test_oracle_overlap_matches_live_tcm_memo(oracle_mod):
         for _ in range(300):
             x, y = int(rng.integers(1, 1 << a)), int(rng.integers(1, 1 << a))
             assert oracle_mod.overlap(a, x, y, sg) == ref.overlap(x, y), (a, x, y)
+
+
+def test_reroot_oracle_reproduces_chel_golden_total(oracle_mod):
+    """The reference's golden test pins the RE-ROOTED result of chel.tree: DAG total cost 336, and the root node
+    (rewritten to the minimal rooting edge) has local cost 49 (chel_xml.golden, node 0).  The post-order root of the
+    input tree costs more, so the pass is exercised."""
+    from tests.helpers import chel_golden_tree
+    g, children, leaves, _ = chel_golden_tree()
+    o = oracle_mod.Oracle(tcm_matrix("discrete"))
+    best, edges, ec, el = oracle_mod.reroot(o, children[0], leaves)
+    root = g["nodes"][0]
+    assert best == root["total_cost"] == 336
+    k = int(np.argmin(ec))
+    assert (ec == best).sum() == 1 and int(el[k]) == root["local_cost"] == 49
+    assert ec[0] > best and len(edges) == 2 * 17 - 3
