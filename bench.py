@@ -179,9 +179,10 @@ def run_postorder(args, rank, world, local_rank, ctx, torch, dist, full=True):
     if args.po_trees:
         n_trees = args.po_trees
     children, leaves = po_inputs(n_trees, n_taxa, n_chars, leaf_len)
-    assert n_chars % world == 0
-    cpr = n_chars // world
-    my = leaves[:, rank * cpr:(rank + 1) * cpr, :]
+    from pcg_b200.sharding import character_block
+    c_lo, c_hi = character_block(n_chars, rank, world)
+    cpr = c_hi - c_lo
+    my = leaves[:, c_lo:c_hi, :]
     ctx.configure(pairs_per_warp=args.ppw, warps_per_cta=args.warps, max_len=PO["node_cap"], max_b=32)
     tcm = ctx.tcm(discrete_tcm())
     forest = P.Forest(ctx, children, n_taxa, [[my[v, c] for c in range(cpr)] for v in range(n_taxa)], PO["node_cap"])
@@ -543,6 +544,63 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist):
                          "cells_per_pair_avg": rx["cells_rank"] / n, "cost_checksum": rx["checksum"],
                          "cpu_baseline": cpu_x}}
 
+# ------------------------------------------------------------------------------------------------
+# Config 1 (BASELINE.json configs[0], "bench-string-alignment-small"): the 190 unordered pairs of the 20 strings of
+# the reference's bench/strings/dna/dna-sequences.fasta (lengths 8 ... 4608, half of them IUPAC-ambiguous), discrete
+# TCM.  The strings travel as the committed fixture tests/golden/bench_strings_dna.json together with the costs the
+# compiled reference produced for them.  It is the reference's own CPU-runnable case: a parity line more than a
+# throughput line (190 pairs cannot fill a B200).
+# ------------------------------------------------------------------------------------------------
+def run_config1(args, ctx):
+    import pcg_b200 as P
+    from pcg_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_strings_dna.json")))
+    codes = formats.iupac_dna_codes()
+    enc = []
+    for sq in g["text"]:
+        e = formats.encode_fasta(sq, codes)
+        enc.append(e[e != 16])
+    tf = "dna-discrete.tcm"
+    sigma, recs = np.array(g["tcms"][tf], np.uint32), g["pairs"][tf]
+    firsts, seconds = [], []
+    for i, j, *_ in recs:
+        a, b = (enc[i], enc[j]) if len(enc[i]) >= len(enc[j]) else (enc[j], enc[i])
+        firsts.append(a); seconds.append(b)
+    pp = P.PackedPairs.from_lists(firsts, seconds)
+    ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=4700, max_b=32)
+    tcm = ctx.tcm(sigma)
+    for _ in range(max(args.warmup, 3)):
+        r = P.align2d_batch(ctx, tcm, pp, want_cells=True)
+    assert [int(x) for x in r.cost] == [rec[2] for rec in recs], "device costs differ from the reference's golden costs"
+    t0 = time.perf_counter()
+    kms = []
+    for _ in range(args.steps):
+        r = P.align2d_batch(ctx, tcm, pp, want_cells=True)
+        kms.append(ctx.last_kernel_ms()[0])
+    dt = (time.perf_counter() - t0) / args.steps
+    cells = float(r.cells.sum())
+    cpu = None
+    if not args.no_cpu:
+        from oracle import pyoracle as po
+        kind = "reference" if os.path.exists(po.REF_SO) else "port"
+        sec1, cost1, _ = po.cpu_bench_align2d(sigma, pp, 1, kind)
+        secn, _, _ = po.cpu_bench_align2d(sigma, pp, host_threads(), kind)
+        assert [int(x) for x in cost1] == [rec[2] for rec in recs]
+        cpu = {"value": cells / sec1 / 1e9, "unit": "GCUPS", "cores": 1, "kind": kind,
+               "us_per_pair": 1e6 * sec1 / len(recs), "all_threads_gcups": cells / secn / 1e9, "threads": host_threads(),
+               "sample": "all 190 pairs, one pass, single thread (and all host threads); costs equal to the golden's"}
+    return {"metric": "2D DO alignment GCUPS", "value": cells / (float(np.mean(kms)) * 1e-3) / 1e9, "unit": "GCUPS",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(kms)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "reference bench/strings/dna (committed fixture)",
+            "config": {"workload": "config1: 190 pairs of the reference's DNA bench strings (8 ... 4608 elements, IUPAC "
+                                   "ambiguity), discrete TCM, align2d", "pairs": len(recs), "cells": cells,
+                       "us_per_pair_kernel": 1e3 * float(np.mean(kms)) / len(recs)},
+            "e2e": {"value": cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3,
+                    "h2d_bytes_per_step": int(pp.elems.nbytes + 40 * pp.n), "d2h_bytes_per_step": int(3 * pp.out_bytes + 16 * pp.n)},
+            "gpu_launches": ctx.last_kernel_ms()[1] * args.steps, "cpu_baseline": cpu,
+            "cost_checksum": int(np.asarray(r.cost, np.int64).sum())}
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -579,7 +637,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=1 << 20, help="pairs per GPU per step")
     ap.add_argument("--warps", type=int, default=32, help="warps per CTA of the narrow kernel")
     ap.add_argument("--ppw", type=int, default=32, help="pairs a warp fills before tracing them")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--no-postorder", action="store_true", help="skip the config-5 post-order section")
     ap.add_argument("--po-trees", type=int, default=0, help="override the number of candidate trees")
     ap.add_argument("--po-steps", type=int, default=2)
@@ -611,6 +669,12 @@ def main():
 
     n = args.pairs
     ctx = P.Context(local_rank)
+    if args.workload == "config1":
+        if rank == 0:
+            print(json.dumps(run_config1(args, ctx)), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "config3":
         line = run_config3(args, rank, world, local_rank, ctx, torch, dist)
         if rank == 0:
