@@ -69,8 +69,11 @@ struct AffParams {
     uint32_t *arena;
     uint32_t  arena_words;
     int       pairs_per_warp;
-    unsigned int *counter;
+    unsigned int *counter;         // [0] narrow hand-out, [2] wide hand-out
     unsigned int *overflow_count;
+    int       wave;            // 1: wavefront fill (default), 0: the row-wise fill with its prefix scan
+    unsigned int *big_count;       // pairs whose band needs 16+ diagonals per lane (wavefront mode):
+    uint32_t     *big_list;        //   queued by the 512-thread kernel, consumed by the 256-thread one
 };
 
 // column entry: .x = gr (cost[gap][l_j]); .y = l'_j | lgap << 8 | go_is_open << 9 | he_has_open << 10
@@ -261,6 +264,244 @@ __device__ __forceinline__ uint32_t aff_trace(const uint32_t *dirw, uint32_t wq,
     return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wavefront fill (default).  Same cells, same per-cell rules as aff_row above, but swept along ANTI-DIAGONALS like
+// the linear kernel: lane k owns B consecutive diagonals q = d + 40, iteration t handles anti-diagonal s = 2t for
+// even q and s = 2t + 1 for odd q, the four plane values of each diagonal's latest cell stay in registers and
+// are updated in place.  The only in-row dependency of the reference (EH on the cell to its left) is then a
+// neighbour of the PREVIOUS half step, so no prefix scan is needed; the up / left neighbours at the lane edges
+// come from four shuffles per iteration.  All plane values are kept multiplied by 4 so that the two priority
+// decisions of a cell are single mins over candidates that carry their priority in the low two bits
+// (next mode out of an align step: horizontal 0 > diagonal 1 > vertical 2 > stay 3; plane that ends here:
+// horizontal 0 > align 1 > vertical 2 > diagonal 3).  Row / column parameters are decoded once per lane and
+// iteration into sliding register windows (a row or column is used by B cells of the lane).  The first
+// iterations, in which some diagonal of the warp is still above row 1 or left of column 1, run a predicated
+// variant (EARLY); row 0 lives in the registers' initial values.
+// Direction bytes: word[(t >> 2) * Wq + q], byte t & 3 — same flag layout as the row-wise fill.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kInf4 = 1u << 29;          // "very large" x 4
+constexpr uint32_t kCap4 = 1u << 30;          // clamp for sums of very large values
+
+// parameter entries (global scratch, 16 bytes each), decoded into the windows below
+//   row i   : .x = 4*ve, .y = 4*(so + ge), .z = 4*so, .w = table row offset (bytes) | sgap << 31
+//   column j: .x = 4*he, .y = 4*(go + gr), .z = 4*go, .w = table column offset (bytes) | lgap << 31
+template <int H>
+struct AffWin { uint32_t a[H], b[H], c[H], m[H], o[H]; };
+
+template <int H>
+__device__ __forceinline__ void aff_win_load(AffWin<H> &w, int slot, const uint4 v)
+{
+    w.a[slot] = v.x; w.b[slot] = v.y; w.c[slot] = v.z;
+    w.m[slot] = (uint32_t)((int32_t)v.w >> 31);
+    w.o[slot] = v.w & 0x7fffffffu;
+}
+
+__device__ __forceinline__ uint32_t aff_lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// One cell.  rs / cs: window slots of its row and column.  Returns the flag byte.
+template <int H, bool EARLY>
+__device__ __forceinline__ uint32_t aff_cell(uint32_t &CB, uint32_t &EB, uint32_t &EV, uint32_t &EH, uint32_t uEV,
+                                             uint32_t uCB, uint32_t lEH, uint32_t lCB, uint32_t penup,
+                                             const AffWin<H> &rw, int rs, const AffWin<H> &cw, int cs, uint32_t tab,
+                                             bool border, int i, int j)
+{
+    const uint32_t ve = rw.a[rs], voa = rw.b[rs], so = rw.c[rs], sgM = rw.m[rs];
+    const uint32_t he = cw.a[cs], hoa = cw.b[cs], go = cw.c[cs], lgM = cw.m[cs];
+    const uint32_t pen = (EARLY && i == 1) ? 0u : penup;      // row 1 still sees the real row-0 cell above the band
+    uEV |= pen;
+    uCB |= pen;
+    // extend vertical
+    const uint32_t vx = uEV + ve, vo = uCB + voa;
+    uint32_t ev = min(vx, vo);
+    uint32_t endv = !(vx < vo);
+    // extend block diagonal
+    const uint32_t gm = sgM & lgM;
+    uint32_t eb = (min(EB, CB) & gm) | (kInf4 & ~gm);
+    const uint32_t endb = !(EB < CB);
+    // close block diagonal: candidates carry the next mode in their low bits
+    const uint32_t dg = aff_lds32(tab + rw.o[rs] + cw.o[cs]);
+    const uint32_t fh = EH + dg + (lgM & so);
+    const uint32_t fd = EB + dg + ((go | so) | 1u);
+    const uint32_t fv = EV + dg + ((sgM & go) | 2u);
+    const uint32_t ca = CB + dg + 3u;
+    const uint32_t cbm = min(min(fh, fd), min(fv, ca));
+    const uint32_t an = cbm & 3u;
+    uint32_t cb = cbm & ~3u;
+    // extend horizontal: the left neighbour of this half step
+    const uint32_t hx = lEH + he, ho = lCB + hoa;
+    uint32_t eh = min(hx, ho);
+    const uint32_t endh = !(hx < ho);
+    if (border) { ev = vx; cb = kInf4; eb = kInf4; endv = 1u; eh = kCap4; }   // vertical extension only
+    if (EARLY && j < 0) { ev = kInf4; cb = kInf4; eb = kInf4; eh = kCap4; }
+    // no clamping: every candidate is ONE plane value plus a small term, so "very large" values only drift by
+    // 4 * (a few costs) per step — they never wrap and never come near a finite value (checked on the host)
+    // which plane ends here
+    const uint32_t fcm = min(min(eh, cb | 1u), min(ev | 2u, eb | 3u));
+    const uint32_t fl = (fcm & 3u) | (an << 2) | (endv << 4) | (endh << 5) | (endb << 6);
+    if (!EARLY || i >= 1) { CB = cb; EB = eb; EV = ev; EH = eh; }             // rows <= 0: keep the row-0 value
+    return fl;
+}
+
+template <int B, bool EARLY, bool TAIL>
+__device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)[B], uint32_t (&EV)[B], uint32_t (&EH)[B],
+                                               const uint32_t (&penup)[B], uint32_t (&dw)[B], AffWin<B / 2> &rw,
+                                               AffWin<B / 2> &cw, uint32_t tab, const uint4 *&rptr, const uint4 *&cptr,
+                                               int n_iter, int i_even0, int j_even0, int lane, uint32_t *&out)
+{
+    constexpr int H = B / 2, CH = H < 4 ? 4 : H;
+#pragma unroll
+    for (int r = 0; r < CH; ++r) {
+        if (TAIL && r >= n_iter) break;
+        const int tt = r % H;
+        // ---- even diagonals (anti-diagonal 2t): m = 2u handles row i_even0 + r - u, column j_even0 + r + u
+        const uint32_t lEH0 = __shfl_up_sync(kFullA, EH[B - 1], 1), lCB0 = __shfl_up_sync(kFullA, CB[B - 1], 1);
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            const int m = 2 * u;
+            const uint32_t lEH = (u == 0) ? (lane == 0 ? kCap4 : lEH0) : EH[m > 0 ? m - 1 : 0];
+            const uint32_t lCB = (u == 0) ? (lane == 0 ? kCap4 : lCB0) : CB[m > 0 ? m - 1 : 0];
+            const int i = i_even0 + r - u, j = j_even0 + r + u;
+            const bool border = (u == 0 && lane == 0) || (EARLY && j == 0);     // d = -40 and column 0
+            const uint32_t fl = aff_cell<H, EARLY>(CB[m], EB[m], EV[m], EH[m], EV[m + 1], CB[m + 1], lEH, lCB, penup[m],
+                                                   rw, (tt - u + 2 * H) % H, cw, (tt + u) % H, tab, border, i, j);
+            dw[m] = fl * (1u << (8 * (r & 3))) + dw[m];
+        }
+        aff_win_load<H>(cw, tt, __ldg(cptr + r));
+        // ---- odd diagonals (anti-diagonal 2t + 1): m = 2u + 1 handles row i_even0 + r - u, column j_even0 + r + u + 1
+        const uint32_t uEV0 = __shfl_down_sync(kFullA, EV[0], 1), uCB0 = __shfl_down_sync(kFullA, CB[0], 1);
+#pragma unroll
+        for (int u = 0; u < H; ++u) {
+            const int m = 2 * u + 1;
+            const uint32_t uEV = (u == H - 1) ? uEV0 : EV[m + 1 < B ? m + 1 : B - 1];
+            const uint32_t uCB = (u == H - 1) ? uCB0 : CB[m + 1 < B ? m + 1 : B - 1];
+            const int i = i_even0 + r - u, j = j_even0 + r + u + 1;
+            const bool border = EARLY ? (j == 0) : false;
+            const uint32_t fl = aff_cell<H, EARLY>(CB[m], EB[m], EV[m], EH[m], uEV, uCB, EH[m - 1], CB[m - 1], penup[m],
+                                                   rw, (tt - u + 2 * H) % H, cw, (tt + u + 1) % H, tab, border, i, j);
+            dw[m] = fl * (1u << (8 * (r & 3))) + dw[m];
+        }
+        aff_win_load<H>(rw, (tt + 1) % H, __ldg(rptr + r));
+        if ((r & 3) == 3 || (TAIL && r == n_iter - 1)) {
+#pragma unroll
+            for (int m = 0; m < B; m += 4) *reinterpret_cast<uint4 *>(out + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+#pragma unroll
+            for (int m = 0; m < B; ++m) dw[m] = 0;
+            out += 32 * B;
+        }
+    }
+    rptr += CH;
+    cptr += CH;
+}
+
+// rowp / colp point at the entries of row 0 / column 0 (padded on both sides).  Returns 4 * FC at (S, L).
+template <int B>
+__device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uint32_t tab, const uint4 *rowp,
+                                               const uint4 *colp, const uint32_t *row0, uint32_t *dirw, int lane)
+{
+    constexpr int H = B / 2, CH = H < 4 ? 4 : H;
+    uint32_t CB[B], EB[B], EV[B], EH[B], penup[B], dw[B];
+    AffWin<H> rw, cw;
+    const int qE = g.E0 - kDB;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int q = lane * B + m, d = kDB + q;
+        penup[m] = (q + 1 >= qE) ? kInf4 : 0u;
+        CB[m] = EB[m] = EV[m] = EH[m] = kInf4;
+        if (d == 0) { CB[m] = 0; EB[m] = 0; EV[m] = 4u * GO; EH[m] = 4u * GO; }
+        else if (d > 0 && d <= g.L) { CB[m] = 4u * row0[d]; EH[m] = 4u * row0[d]; }
+        dw[m] = 0;
+    }
+    // even diagonal m = 2u of this lane at iteration t: row t + 20 - q/2, column t - 20 + q/2 with q = lane*B + 2u
+    const int I0 = 20 - lane * H, J0 = -20 + lane * H;
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        aff_win_load<H>(rw, (H - u) % H, __ldg(rowp + (I0 - u)));
+        aff_win_load<H>(cw, u, __ldg(colp + (J0 + u)));
+    }
+    const uint4 *rptr = rowp + (I0 + 1), *cptr = colp + (J0 + H);
+    uint32_t *out = dirw + lane * B;
+    const int T = (g.S + g.L) / 2 + 1;
+    int T0 = qE / 2 - 17;                         // from here on every diagonal is at row >= 1 and column >= 1
+    if (T0 < 22) T0 = 22;
+    T0 = (T0 + CH - 1) / CH * CH;
+    int t = 0;
+    for (; t + CH <= T0 && t + CH <= T; t += CH)
+        aff_wave_chunk<B, true, false>(CB, EB, EV, EH, penup, dw, rw, cw, tab, rptr, cptr, CH, I0 + t, J0 + t, lane, out);
+    for (; t + CH <= T; t += CH)
+        aff_wave_chunk<B, false, false>(CB, EB, EV, EH, penup, dw, rw, cw, tab, rptr, cptr, CH, I0 + t, J0 + t, lane, out);
+    if (t < T)      // the last cell must stay in its register: stop exactly after iteration T - 1
+        aff_wave_chunk<B, true, true>(CB, EB, EV, EH, penup, dw, rw, cw, tab, rptr, cptr, T - t, I0 + t, J0 + t, lane, out);
+    const int q_last = (g.L - g.S) - kDB, lane_last = q_last / B, m_last = q_last % B;
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < B; ++m)
+        if (m == m_last) v = min(min(EH[m], EV[m]), min(EB[m], CB[m]));
+    return __shfl_sync(kFullA, v, lane_last);
+}
+
+// per-pair scratch of the wavefront fill (32-bit words): direction words | op stream | row params | column params | row 0
+__host__ __device__ inline int aff_wave_chunk_len(int B) { return B / 2 < 4 ? 4 : B / 2; }
+__host__ __device__ inline uint32_t aff_wave_iters(const AffGeom &g, int B)
+{
+    const int ch = aff_wave_chunk_len(B);
+    return (uint32_t)((((g.S + g.L) / 2 + 1) + ch - 1) / ch * ch);
+}
+__host__ __device__ inline uint32_t aff_wave_dir_words(const AffGeom &g, int B) { return (aff_wave_iters(g, B) / 4u + 1u) * 32u * (uint32_t)B; }
+constexpr int kWavePad = 16 * 32 + 64;        // parameter entries in front of index 0 (rows run down to 20 - 31*16)
+__host__ __device__ inline uint32_t aff_wave_par_entries(const AffGeom &g, int B)
+{
+    return (uint32_t)(kWavePad + aff_wave_iters(g, B) + 32 * B + 64);
+}
+__host__ __device__ inline uint32_t aff_wave_ops_words(const AffGeom &g) { return (aff_ops_words(g) + 3u) & ~3u; }   // keeps the uint4 arrays aligned
+__host__ __device__ inline uint32_t aff_wave_need_words(const AffGeom &g, int B)
+{
+    return (aff_wave_dir_words(g, B) + aff_wave_ops_words(g) + 8u * aff_wave_par_entries(g, B) + (uint32_t)(g.L + 8) + 7u) & ~3u;
+}
+
+// One lane per pair, wavefront layout.
+__device__ __forceinline__ uint32_t aff_trace_wave(const uint32_t *dirw, uint32_t wq, int S, int L, uint32_t *ops)
+{
+    int si = S, li = L;
+    uint32_t n = 0, acc = 0;
+    int mode = 0;
+    auto put = [&](uint32_t code) {
+        acc |= code << (2 * (n & 15));
+        ++n;
+        if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
+    };
+    while (si != 0 && li != 0) {
+        const int q = li - si - kDB;
+        const int t = (si + li - (q & 1)) >> 1;
+        const uint32_t f = (__ldcg(dirw + (size_t)(t >> 2) * wq + q) >> (8 * (t & 3))) & 0xffu;
+        if (mode == 0) {
+            const uint32_t td = f & 3u;
+            mode = td == 0 ? 2 : td == 1 ? 4 : td == 2 ? 1 : 3;
+        } else if (mode == 1) {
+            if (f & 16u) mode = 0;
+            put(0); --si;
+        } else if (mode == 2) {
+            if (f & 32u) mode = 0;
+            put(1); --li;
+        } else if (mode == 3) {
+            if (f & 64u) mode = 0;
+            put(2); --si; --li;
+        } else {
+            const uint32_t an = (f >> 2) & 3u;
+            mode = an == 0 ? 2 : an == 1 ? 3 : an == 2 ? 1 : 4;
+            put(3); --si; --li;
+        }
+    }
+    while (si != 0) { put(0); --si; }
+    while (li != 0) { put(1); --li; }
+    if (n & 15) ops[n >> 4] = acc;
+    return n;
+}
+
 __device__ __forceinline__ void aff_emit(const TcmDev &tcm, const uint8_t *pL, const uint8_t *pS, const uint32_t *ops,
                                          uint32_t nal, bool first_long, uint8_t *og, uint8_t *o1, uint8_t *o2, int lane)
 {
@@ -318,141 +559,250 @@ __device__ __forceinline__ void aff_emit(const TcmDev &tcm, const uint8_t *pL, c
 
 extern __shared__ __align__(16) char aff_smem[];
 
-__global__ void __launch_bounds__(512, 1) do_affine_kernel(const AffParams p)
+__device__ __forceinline__ unsigned long long aff_band_cells(const AffGeom &ag)
+{
+    unsigned long long c = 0;
+    for (int i = 1; i <= ag.S; ++i) {
+        int lo = i > 40 ? i - 39 : 1, hi = ag.E0 + i - 1;
+        if (hi > ag.L) hi = ag.L;
+        if (hi >= lo) c += (unsigned long long)(hi - lo + 1);
+    }
+    return c;
+}
+
+// Stage the parameters of one pair in its scratch slot and run the wavefront fill.  Returns FC at (S, L).
+template <bool WIDE>
+__device__ __forceinline__ uint32_t aff_pair_wave(const TcmDev &tcm, const AffGeom &ag, int B, uint32_t GO, uint32_t tab_lane,
+                                                  uint32_t ent_shift, const uint8_t *pL, const uint8_t *pS, uint32_t *slot,
+                                                  int lane)
+{
+    const uint32_t g = tcm.gap;
+    uint32_t *dirw = slot;
+    uint32_t *ops = dirw + aff_wave_dir_words(ag, B);
+    const uint32_t npar = aff_wave_par_entries(ag, B);
+    uint4 *rowbase = reinterpret_cast<uint4 *>(ops + aff_wave_ops_words(ag));
+    uint4 *colbase = rowbase + npar;
+    uint4 *rowp = rowbase + kWavePad, *colp = colbase + kWavePad;       // entries of row 0 / column 0
+    uint32_t *row0 = reinterpret_cast<uint32_t *>(colbase + npar);      // L + 1 words: EH = CB of row 0
+    uint32_t carry = GO;
+    for (int base_e = 0; base_e < (int)npar; base_e += 32) {
+        const int e = base_e + lane, j = e - kWavePad, i = j;
+        uint4 cv = make_uint4(0, 0, 0, 0), rv = make_uint4(0, 0, 0, 0);
+        uint32_t gr = 0;
+        if (j >= 1 && j <= ag.L) {                                      // column parameters (:3585-3595)
+            const uint32_t lj = __ldg(pL + j - 1), lp = j == 1 ? g : __ldg(pL + j - 2);
+            gr = tcm.gapc[lj];
+            const uint32_t go = !(!(g & lp) && (g & lj)) ? GO : 0u;
+            const uint32_t he = gr + ((j > 1 && (lp & g) && !(lj & g)) ? go : 0u);
+            cv = make_uint4(4u * he, 4u * (go + gr), 4u * go, ((lj & (g - 1u)) << ent_shift) | ((lj & g) ? 0x80000000u : 0u));
+        }
+        if (i >= 1 && i <= ag.S) {                                      // row parameters (:3614-3625)
+            const uint32_t si = __ldg(pS + i - 1), sp = i == 1 ? g : __ldg(pS + i - 2);
+            const uint32_t ge = tcm.cgap[si];
+            const uint32_t so = !(!(g & sp) && (g & si)) ? GO : 0u;
+            const uint32_t ve = (i > 1 && (sp & g) && !(si & g)) ? so + ge : ge;
+            rv = make_uint4(4u * ve, 4u * (so + ge), 4u * so,
+                            (((si & (g - 1u)) << (tcm.a - 1)) << ent_shift) | ((si & g) ? 0x80000000u : 0u));
+        }
+        if (e < (int)npar) { colbase[e] = cv; rowbase[e] = rv; }
+        uint32_t sfx = gr;                                              // inclusive prefix of gr for row 0
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFullA, sfx, d);
+            if (lane >= d) sfx += o;
+        }
+        if (j >= 1 && j <= ag.L) row0[j] = carry + sfx;
+        carry += __shfl_sync(kFullA, sfx, 31);
+    }
+    __syncwarp();
+    uint32_t fc4;
+    if constexpr (WIDE) {
+        fc4 = aff_wave_fill<16>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+    } else {
+        if (B == 4) fc4 = aff_wave_fill<4>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        else        fc4 = aff_wave_fill<8>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+    }
+    return fc4 >> 2;
+}
+
+// The row-wise fill of one pair (column / row parameters in the scratch slot, prefix scan per row).
+template <bool WIDE>
+__device__ __forceinline__ uint32_t aff_pair_rowwise(const TcmDev &tcm, const AffGeom &ag, int B, uint32_t GO,
+                                                     const uint16_t *s_sub, const uint8_t *pL, const uint8_t *pS,
+                                                     uint32_t *slot, int lane)
+{
+    const uint32_t g = tcm.gap;
+    uint32_t *dirw = slot;
+    uint32_t *ops = dirw + aff_dir_words(ag, B);
+    uint2 *colbase = reinterpret_cast<uint2 *>(ops + aff_ops_words(ag));
+    uint2 *colpar = colbase + kColPad;                            // entry of column j = 0
+    uint2 *rowpar = colbase + aff_col_entries(ag, B);
+    uint32_t *row0 = reinterpret_cast<uint32_t *>(rowpar + ag.S + 8);   // L + 1 words: EH = CB of row 0
+    // ---- per-column parameters (:3585-3595) and row 0 prefix; per-row parameters (:3614-3625)
+    const int ncol = (int)aff_col_entries(ag, B);
+    uint32_t carry = GO;
+    for (int base_j = -kColPad; base_j < ncol - kColPad; base_j += 32) {
+        const int j = base_j + lane;
+        uint32_t gr = 0, y = 0;
+        if (j >= 0 && j <= ag.L) {
+            const uint32_t lj = j == 0 ? g : __ldg(pL + j - 1);
+            const uint32_t lp = j <= 1 ? g : __ldg(pL + j - 2);       // l_{j-1}; l_0 = gap
+            if (j >= 1) {
+                gr = tcm.gapc[lj];
+                const uint32_t go_open = !(!(g & lp) && (g & lj));
+                uint32_t he_open = ((lp & g) && !(lj & g)) ? go_open : 0u;
+                if (j == 1) he_open = 0u;                             // he[1] = gr[1]
+                y = (lj & (g - 1u)) | (((lj & g) ? 1u : 0u) << 8) | (go_open << 9) | (he_open << 10);
+            }
+        }
+        if (j < ncol - kColPad) colpar[j] = make_uint2(gr, y);
+        uint32_t sfx = gr;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFullA, sfx, d);
+            if (lane >= d) sfx += o;
+        }
+        if (j >= 1 && j <= ag.L) row0[j] = carry + sfx;
+        carry += __shfl_sync(kFullA, sfx, 31);
+    }
+    for (int i = 1 + lane; i <= ag.S; i += 32) {
+        const uint32_t si = __ldg(pS + i - 1), sp = i == 1 ? g : __ldg(pS + i - 2);
+        const uint32_t ge = tcm.cgap[si];
+        const uint32_t so_open = !(!(g & sp) && (g & si));
+        const uint32_t so = so_open ? GO : 0u;
+        const uint32_t ve = (i > 1 && (sp & g) && !(si & g)) ? so + ge : ge;
+        rowpar[i] = make_uint2(ve, ge | (so_open << 16) | (((si & g) ? 1u : 0u) << 17) | ((si & (g - 1u)) << 24));
+    }
+    __syncwarp();
+    if (ag.S <= 0) return ag.L > 0 ? row0[ag.L] : 0u;
+    if constexpr (WIDE) {
+        return aff_fill<32>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, row0, dirw, lane);
+    } else {
+        switch (B) {
+            case 4:  return aff_fill<4>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, row0, dirw, lane);
+            case 8:  return aff_fill<8>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, row0, dirw, lane);
+            case 16: return aff_fill<16>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, row0, dirw, lane);
+            default: return aff_fill<32>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, row0, dirw, lane);
+        }
+    }
+}
+
+// WIDE = false: 512 threads (128 registers); takes pairs straight from the batch.  With the wavefront fill it keeps
+//               the pairs whose band fits 8 diagonals per lane and queues the others on big_list.
+// WIDE = true : 256 threads (255 registers: 16 diagonals per lane with four planes and two parameter windows
+//               each); takes its pairs from big_list.  Bands beyond 512 diagonals use the row-wise fill.
+// Shared memory: [both substitution tables | per warp: flags[32], nal[32], off[32], pair[32]].
+template <bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const AffParams p)
 {
     const TcmDev &tcm = p.tcm;
     const BatchDev &b = p.b;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int hdim = 1 << (tcm.a - 1);
-    // shared: substitution table between gap-stripped elements, then per-warp bookkeeping
-    uint16_t *s_sub = reinterpret_cast<uint16_t *>(aff_smem);
-    uint32_t *s_meta = reinterpret_cast<uint32_t *>(aff_smem + (size_t)hdim * hdim * 2) + warp * 96;
-    uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64;
+    const bool repl = hdim <= 16;
+    // wavefront fill: 32-bit entries 4 * cost, for small alphabets replicated 32 times with copy k wholly in bank k;
+    // row-wise fill: the plain 16-bit table
+    const size_t wave_bytes = p.wave ? (size_t)hdim * hdim * (repl ? 128 : 4) : 0;
+    uint16_t *s_sub = reinterpret_cast<uint16_t *>(aff_smem + wave_bytes);
+    const size_t tab_bytes = wave_bytes + (((size_t)hdim * hdim * 2 + 15) & ~(size_t)15);
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(aff_smem + tab_bytes) + warp * 128;
+    uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64, *s_pair = s_meta + 96;
+    if (p.wave) {
+        uint32_t *t32 = reinterpret_cast<uint32_t *>(aff_smem);
+        if (repl) {
+            for (int x = threadIdx.x; x < hdim * hdim * 32; x += blockDim.x) t32[x] = 4u * p.aff_sub[x >> 5];
+        } else {
+            for (int x = threadIdx.x; x < hdim * hdim; x += blockDim.x) t32[x] = 4u * p.aff_sub[x];
+        }
+    }
     for (int x = threadIdx.x; x < hdim * hdim; x += blockDim.x) s_sub[x] = p.aff_sub[x];
     __syncthreads();
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(aff_smem) + (repl ? 4u * lane : 0u);
+    const uint32_t ent_shift = repl ? 7 : 2;      // bytes per table entry: 128 (replicated) or 4
 
-    const uint32_t GO = p.gap_open, g = tcm.gap;
+    const uint32_t GO = p.gap_open;
     const int G = p.pairs_per_warp;
     uint32_t *arena = p.arena + ((size_t)blockIdx.x * nwarps + warp) * (size_t)p.arena_words;
     const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
+    const uint32_t n_work = WIDE ? *p.big_count : b.n_pairs;
+    unsigned int *counter = WIDE ? p.counter + 2 : p.counter;
+    if (n_work == 0) return;
 
+    // pairs are heavy (a million cells): take them one at a time, trace up to G of them at once
+    uint32_t gpos = 0, gend = 0;
+    bool exhausted = false;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
-        base = __shfl_sync(kFullA, base, 0);
-        if (base >= b.n_pairs) break;
-        const int npw = (int)min((uint32_t)G, b.n_pairs - base);
-        int pi = 0;
-        while (pi < npw) {
-            const int start = pi;
-            uint32_t cur = 0;
-            for (; pi < npw; ++pi) {
-                const uint32_t k = base + pi;
-                const uint32_t n1 = b.len1[k], n2 = b.len2[k];
-                const bool fl = n1 >= n2;                                    // c_alignment_interface.c:212
-                const uint8_t *pL = b.elems + (fl ? b.off1[k] : b.off2[k]), *pS = b.elems + (fl ? b.off2[k] : b.off1[k]);
-                const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
-                const int B = aff_choose_b(ag.wq_need);
-                const uint32_t need = B ? aff_need_words(ag, B) : 0u;
-                if (!B || need > p.arena_words) {
-                    if (lane == 0) { s_flags[pi] = 0; atomicAdd(p.overflow_count, 1u); }
-                    continue;
-                }
-                if (cur + need > p.arena_words) break;
-                if (lane == 0) { s_flags[pi] = (fl ? 1u : 0u) | 2u; s_off[pi] = cur; }
-                uint32_t *slot = arena + cur;
-                cur += need;
-                uint32_t *dirw = slot;
-                uint32_t *ops = dirw + aff_dir_words(ag, B);
-                uint2 *colbase = reinterpret_cast<uint2 *>(ops + aff_ops_words(ag));
-                uint2 *colpar = colbase + kColPad;                            // entry of column j = 0
-                uint2 *rowpar = colbase + aff_col_entries(ag, B);
-                uint32_t *row0 = reinterpret_cast<uint32_t *>(rowpar + ag.S + 8);   // L + 1 words: EH = CB of row 0
-                // ---- per-column parameters (:3585-3595) and row 0 prefix; per-row parameters (:3614-3625)
-                const int ncol = (int)aff_col_entries(ag, B);
-                uint32_t carry = GO;
-                for (int base_j = -kColPad; base_j < ncol - kColPad; base_j += 32) {
-                    const int j = base_j + lane;
-                    uint32_t gr = 0, y = 0;
-                    if (j >= 0 && j <= ag.L) {
-                        const uint32_t lj = j == 0 ? g : __ldg(pL + j - 1);
-                        const uint32_t lp = j <= 1 ? g : __ldg(pL + j - 2);       // l_{j-1}; l_0 = gap
-                        if (j >= 1) {
-                            gr = tcm.gapc[lj];
-                            const uint32_t go_open = !(!(g & lp) && (g & lj));
-                            uint32_t he_open = ((lp & g) && !(lj & g)) ? go_open : 0u;
-                            if (j == 1) he_open = 0u;                             // he[1] = gr[1]
-                            y = (lj & (g - 1u)) | (((lj & g) ? 1u : 0u) << 8) | (go_open << 9) | (he_open << 10);
-                        }
-                    }
-                    if (j < ncol - kColPad) colpar[j] = make_uint2(gr, y);
-                    // inclusive prefix of gr over the warp for row 0
-                    uint32_t s = gr;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t o = __shfl_up_sync(kFullA, s, d);
-                        if (lane >= d) s += o;
-                    }
-                    if (j >= 1 && j <= ag.L) row0[j] = carry + s;
-                    carry += __shfl_sync(kFullA, s, 31);
-                }
-                for (int i = 1 + lane; i <= ag.S; i += 32) {
-                    const uint32_t si = __ldg(pS + i - 1), sp = i == 1 ? g : __ldg(pS + i - 2);
-                    const uint32_t ge = tcm.cgap[si];
-                    const uint32_t so_open = !(!(g & sp) && (g & si));
-                    const uint32_t so = so_open ? GO : 0u;
-                    const uint32_t ve = (i > 1 && (sp & g) && !(si & g)) ? so + ge : ge;
-                    rowpar[i] = make_uint2(ve, ge | (so_open << 16) | (((si & g) ? 1u : 0u) << 17) | ((si & (g - 1u)) << 24));
-                }
-                __syncwarp();
-                uint32_t fc = 0;
-                const uint32_t *r0p = row0;
-                if (ag.S > 0) {
-                    switch (B) {
-                        case 4:  fc = aff_fill<4>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
-                        case 8:  fc = aff_fill<8>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
-                        case 16: fc = aff_fill<16>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
-                        default: fc = aff_fill<32>(ag, GO, s_sub, tcm.a - 1, colpar, rowpar, r0p, dirw, lane); break;
-                    }
-                } else {
-                    fc = ag.L > 0 ? r0p[ag.L] : 0u;
-                }
-                if (lane == 0) b.cost[k] = (int32_t)fc;
-                if (b.cells && lane == 0) {
-                    unsigned long long c = 0;
-                    for (int i = 1; i <= ag.S; ++i) {
-                        int lo = i > 40 ? i - 39 : 1, hi = ag.E0 + i - 1;
-                        if (hi > ag.L) hi = ag.L;
-                        if (hi >= lo) c += (unsigned long long)(hi - lo + 1);
-                    }
-                    b.cells[k] = c;
-                }
-                __syncwarp();
+        int cnt = 0;
+        uint32_t cur = 0;
+        for (;;) {
+            if (cnt == G) break;
+            if (gpos == gend) {
+                if (exhausted) break;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(counter, 1u);
+                base = __shfl_sync(kFullA, base, 0);
+                if (base >= n_work) { exhausted = true; break; }
+                gpos = base;
+                gend = base + 1;
             }
+            const uint32_t k = WIDE ? p.big_list[gpos] : gpos;
+            const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+            const bool fl = n1 >= n2;                                    // c_alignment_interface.c:212
+            const uint8_t *pL = b.elems + (fl ? b.off1[k] : b.off2[k]), *pS = b.elems + (fl ? b.off2[k] : b.off1[k]);
+            const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
+            const int B = aff_choose_b(ag.wq_need);
+            if (!WIDE && p.wave && B > 8) {                              // -> the 255-register kernel
+                if (lane == 0) p.big_list[atomicAdd(p.big_count, 1u)] = k;
+                ++gpos;
+                continue;
+            }
+            const bool wave = p.wave && ag.S > 0 && B <= 16;
+            const uint32_t need = !B ? 0u : wave ? aff_wave_need_words(ag, B) : aff_need_words(ag, B);
+            if (!B || need > p.arena_words) {
+                if (lane == 0) atomicAdd(p.overflow_count, 1u);
+                ++gpos;
+                continue;
+            }
+            if (cur + need > p.arena_words) break;
+            uint32_t *slot = arena + cur;
+            const uint32_t fc = wave ? aff_pair_wave<WIDE>(tcm, ag, B, GO, tab_lane, ent_shift, pL, pS, slot, lane)
+                                     : aff_pair_rowwise<WIDE>(tcm, ag, B, GO, s_sub, pL, pS, slot, lane);
+            if (lane == 0) {
+                s_flags[cnt] = (fl ? 1u : 0u) | (wave ? 4u : 0u);
+                s_off[cnt] = cur;
+                s_pair[cnt] = k;
+                b.cost[k] = (int32_t)fc;
+                if (b.cells) b.cells[k] = aff_band_cells(ag);
+            }
+            cur += need;
+            ++cnt;
+            ++gpos;
             __syncwarp();
-            if (!want_out) continue;
-            const int pj = start + lane;
-            if (pj < pi && (s_flags[pj] & 2u)) {
-                const uint32_t k = base + pj;
+        }
+        __syncwarp();
+        if (cnt && want_out) {
+            if (lane < cnt) {
+                const uint32_t k = s_pair[lane];
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
-                const bool fl = s_flags[pj] & 1u;
+                const bool fl = s_flags[lane] & 1u;
                 const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
                 const int B = aff_choose_b(ag.wq_need);
-                uint32_t *slot = arena + s_off[pj];
-                const uint32_t n = aff_trace(slot, 32u * B, ag.S, ag.L, slot + aff_dir_words(ag, B));
-                s_nal[pj] = n;
+                uint32_t *slot = arena + s_off[lane];
+                const uint32_t n = (s_flags[lane] & 4u)
+                                       ? aff_trace_wave(slot, 32u * B, ag.S, ag.L, slot + aff_wave_dir_words(ag, B))
+                                       : aff_trace(slot, 32u * B, ag.S, ag.L, slot + aff_dir_words(ag, B));
+                s_nal[lane] = n;
                 if (b.out_len) b.out_len[k] = n;
             }
             __syncwarp();
             if (b.out_gapped || b.out_slot1 || b.out_slot2) {
-                for (int pe = start; pe < pi; ++pe) {
-                    if (!(s_flags[pe] & 2u)) continue;
-                    const uint32_t k = base + pe;
+                for (int pe = 0; pe < cnt; ++pe) {
+                    const uint32_t k = s_pair[pe];
                     const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                     const bool fl = s_flags[pe] & 1u;
                     const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
                     const int B = aff_choose_b(ag.wq_need);
-                    const uint32_t *ops = arena + s_off[pe] + aff_dir_words(ag, B);
+                    const uint32_t *ops = arena + s_off[pe] + ((s_flags[pe] & 4u) ? aff_wave_dir_words(ag, B) : aff_dir_words(ag, B));
                     const uint64_t oo = b.out_off[k];
                     aff_emit(tcm, b.elems + (fl ? b.off1[k] : b.off2[k]), b.elems + (fl ? b.off2[k] : b.off1[k]), ops,
                              s_nal[pe], fl, b.out_gapped ? b.out_gapped + oo : nullptr,
@@ -461,6 +811,7 @@ __global__ void __launch_bounds__(512, 1) do_affine_kernel(const AffParams p)
             }
             __syncwarp();
         }
+        if (exhausted && gpos == gend) break;
     }
 }
 
@@ -468,18 +819,23 @@ uint32_t aff_words_for(uint32_t n1, uint32_t n2)
 {
     const AffGeom g = make_aff_geom((int)(n1 < n2 ? n1 : n2), (int)(n1 < n2 ? n2 : n1));
     const int B = aff_choose_b(g.wq_need);
-    return B ? aff_need_words(g, B) : 0u;
+    if (!B) return 0u;
+    const uint32_t w1 = aff_need_words(g, B), w2 = aff_wave_need_words(g, B);
+    return w1 > w2 ? w1 : w2;
 }
 
-cudaError_t launch_affine(const AffParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+cudaError_t launch_affine(const AffParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(do_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(do_affine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(do_affine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    do_affine_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    if (wide) do_affine_kernel<true><<<grid, block, smem_bytes, stream>>>(p);
+    else      do_affine_kernel<false><<<grid, block, smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -30,9 +30,12 @@ struct AffParams {
     int       pairs_per_warp;
     unsigned int *counter;
     unsigned int *overflow_count;
+    int       wave;
+    unsigned int *big_count;
+    uint32_t     *big_list;
 };
 uint32_t aff_words_for(uint32_t n1, uint32_t n2);
-cudaError_t launch_affine(const AffParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_affine(const AffParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 }
 #include "do_metric.cuh"
 #include "do_explicit.h"
@@ -483,7 +486,9 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const size_t hdim = (size_t)1 << (tcm->a - 1);
     const int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
-    const size_t smem = hdim * hdim * 2 + (size_t)warps * 96 * 4;
+    const int wave = getenv("PCGDO_AFFINE_ROWWISE") ? 0 : 1;
+    const size_t tabs = (wave ? hdim * hdim * (hdim <= 16 ? 128 : 4) : 0) + ((hdim * hdim * 2 + 15) & ~(size_t)15);
+    const size_t smem = tabs + (size_t)warps * 128 * 4;
     if (smem > 227 * 1024) {
         ctx->err = "alphabet too large for the affine kernel's shared-memory table";
         return PCGDO_ERR_UNSUPPORTED;
@@ -499,6 +504,7 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)b->n_pairs * 4))) return rc;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
     AffParams p{};
     p.tcm = tcm->dev;
@@ -512,6 +518,7 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     p.b.cost = b->cost;
     p.b.cells = b->cells;
     p.aff_sub = (const uint16_t *)tcm->d_aff_sub;
+    p.wave = wave;
     p.gap_open = tcm->gap_open;
     p.arena = (uint32_t *)ctx->arena.p;
     p.arena_words = (uint32_t)arena_words;
@@ -519,10 +526,17 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     p.counter = (unsigned int *)ctx->counters.p;
     p.overflow_count = p.counter + 8;
     CK(cudaEventRecord(ctx->ev0, st));
-    CK(launch_affine(p, grid, warps * 32, smem, st));
+    p.big_count = p.counter + 3;
+    p.big_list = (uint32_t *)ctx->big.p;
+    CK(launch_affine(p, false, grid, warps * 32, smem, st));
+    ctx->last_launches = 1;
+    if (wave) {     // consumes the queue the first kernel built on the device; exits at once when it is empty
+        const int ww = warps < 8 ? warps : 8;
+        CK(launch_affine(p, true, grid, ww * 32, tabs + (size_t)ww * 128 * 4, st));
+        ctx->last_launches = 2;
+    }
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
-    ctx->last_launches = 1;
     unsigned int h_over = 0;
     CK(cudaMemcpyAsync(&h_over, p.overflow_count, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
