@@ -50,6 +50,17 @@ __host__ __device__ inline int aff_choose_b(int wq_need)
     if (wq_need <= 1024) return 32;
     return 0;
 }
+// wavefront fill: finer steps (6 and 12 diagonals per lane: a quarter fewer cell updates for bands just above 128 / 256)
+__host__ __device__ inline int aff_choose_b_wave(int wq_need)
+{
+    if (wq_need <= 128) return 4;
+    if (wq_need <= 192) return 6;
+    if (wq_need <= 256) return 8;
+    if (wq_need <= 384) return 12;
+    if (wq_need <= 512) return 16;
+    if (wq_need <= 1024) return 32;       // row-wise fill
+    return 0;
+}
 // per-pair scratch (32-bit words): direction words | op stream | column params (2 words each) | row params
 __host__ __device__ inline uint32_t aff_dir_words(const AffGeom &g, int B) { return (uint32_t)(g.S / 4 + 1) * 32u * (uint32_t)B; }
 __host__ __device__ inline uint32_t aff_ops_words(const AffGeom &g) { return ((uint32_t)(g.S + g.L) / 16u + 4u) & ~1u; }
@@ -69,11 +80,12 @@ struct AffParams {
     uint32_t *arena;
     uint32_t  arena_words;
     int       pairs_per_warp;
-    unsigned int *counter;         // [0] narrow hand-out, [2] wide hand-out
+    unsigned int *counter;
     unsigned int *overflow_count;
     int       wave;            // 1: wavefront fill (default), 0: the row-wise fill with its prefix scan
-    unsigned int *big_count;       // pairs whose band needs 16+ diagonals per lane (wavefront mode):
-    uint32_t     *big_list;        //   queued by the 512-thread kernel, consumed by the 256-thread one
+    unsigned int *class_count;     // [6] pairs per band class (filled by aff_classify_kernel)
+    unsigned int *class_take;      // [6] hand-out counters
+    uint32_t     *big_list;        // [6][n_pairs] pair indices per class
 };
 
 // column entry: .x = gr (cost[gap][l_j]); .y = l'_j | lgap << 8 | go_is_open << 9 | he_has_open << 10
@@ -353,7 +365,7 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
                                                AffWin<B / 2> &cw, uint32_t tab, const uint4 *&rptr, const uint4 *&cptr,
                                                int n_iter, int i_even0, int j_even0, int lane, uint32_t *&out)
 {
-    constexpr int H = B / 2, CH = H < 4 ? 4 : H;
+    constexpr int H = B / 2, CH = (H % 4 == 0) ? H : (H % 2 == 0 ? 2 * H : 4 * H);
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
@@ -387,8 +399,13 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
         }
         aff_win_load<H>(rw, (tt + 1) % H, __ldg(rptr + r));
         if ((r & 3) == 3 || (TAIL && r == n_iter - 1)) {
+            if constexpr (B % 4 == 0) {
 #pragma unroll
-            for (int m = 0; m < B; m += 4) *reinterpret_cast<uint4 *>(out + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+                for (int m = 0; m < B; m += 4) *reinterpret_cast<uint4 *>(out + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < B; m += 2) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m], dw[m + 1]);
+            }
 #pragma unroll
             for (int m = 0; m < B; ++m) dw[m] = 0;
             out += 32 * B;
@@ -403,7 +420,7 @@ template <int B>
 __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uint32_t tab, const uint4 *rowp,
                                                const uint4 *colp, const uint32_t *row0, uint32_t *dirw, int lane)
 {
-    constexpr int H = B / 2, CH = H < 4 ? 4 : H;
+    constexpr int H = B / 2, CH = (H % 4 == 0) ? H : (H % 2 == 0 ? 2 * H : 4 * H);
     uint32_t CB[B], EB[B], EV[B], EH[B], penup[B], dw[B];
     AffWin<H> rw, cw;
     const int qE = g.E0 - kDB;
@@ -445,7 +462,11 @@ __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uin
 }
 
 // per-pair scratch of the wavefront fill (32-bit words): direction words | op stream | row params | column params | row 0
-__host__ __device__ inline int aff_wave_chunk_len(int B) { return B / 2 < 4 ? 4 : B / 2; }
+__host__ __device__ inline int aff_wave_chunk_len(int B)
+{
+    const int H = B / 2;
+    return (H % 4 == 0) ? H : (H % 2 == 0 ? 2 * H : 4 * H);
+}
 __host__ __device__ inline uint32_t aff_wave_iters(const AffGeom &g, int B)
 {
     const int ch = aff_wave_chunk_len(B);
@@ -617,10 +638,12 @@ __device__ __forceinline__ uint32_t aff_pair_wave(const TcmDev &tcm, const AffGe
     __syncwarp();
     uint32_t fc4;
     if constexpr (WIDE) {
-        fc4 = aff_wave_fill<16>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        if (B == 12) fc4 = aff_wave_fill<12>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        else         fc4 = aff_wave_fill<16>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
     } else {
-        if (B == 4) fc4 = aff_wave_fill<4>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
-        else        fc4 = aff_wave_fill<8>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        if (B == 4)      fc4 = aff_wave_fill<4>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        else if (B == 6) fc4 = aff_wave_fill<6>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        else             fc4 = aff_wave_fill<8>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
     }
     return fc4 >> 2;
 }
@@ -687,6 +710,24 @@ __device__ __forceinline__ uint32_t aff_pair_rowwise(const TcmDev &tcm, const Af
     }
 }
 
+// Pairs are sorted into per-band-class lists first: the fill variants are long unrolled loops, and warps of one SM
+// running different variants at the same time thrash the instruction cache (measured: 1.7x slower on config 3).
+// class 0..5 = 4, 6, 8 | 12, 16, 32 diagonals per lane (wavefront chooser) or 4, -, 8 | -, 16, 32 (row-wise chooser).
+__host__ __device__ inline int aff_class_of(int B) { return B == 4 ? 0 : B == 6 ? 1 : B == 8 ? 2 : B == 12 ? 3 : B == 16 ? 4 : 5; }
+
+__global__ void aff_classify_kernel(const AffParams p)
+{
+    const BatchDev &b = p.b;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < b.n_pairs; k += gridDim.x * blockDim.x) {
+        const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+        const AffGeom ag = make_aff_geom((int)(n1 >= n2 ? n2 : n1), (int)(n1 >= n2 ? n1 : n2));
+        const int B = p.wave ? aff_choose_b_wave(ag.wq_need) : aff_choose_b(ag.wq_need);
+        if (!B) { atomicAdd(p.overflow_count, 1u); continue; }
+        const int c = aff_class_of(B);
+        p.big_list[(size_t)c * b.n_pairs + atomicAdd(p.class_count + c, 1u)] = k;
+    }
+}
+
 // WIDE = false: 512 threads (128 registers); takes pairs straight from the batch.  With the wavefront fill it keeps
 //               the pairs whose band fits 8 diagonals per lane and queues the others on big_list.
 // WIDE = true : 256 threads (255 registers: 16 diagonals per lane with four planes and two parameter windows
@@ -724,9 +765,9 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
     const int G = p.pairs_per_warp;
     uint32_t *arena = p.arena + ((size_t)blockIdx.x * nwarps + warp) * (size_t)p.arena_words;
     const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len;
-    const uint32_t n_work = WIDE ? *p.big_count : b.n_pairs;
-    unsigned int *counter = WIDE ? p.counter + 2 : p.counter;
-    if (n_work == 0) return;
+    // classes this kernel owns: wavefront mode 0..2 (narrow) / 3..5 (wide); row-wise mode: everything in the narrow one
+    int cls = WIDE ? 3 : 0;
+    const int cls_end = (WIDE || !p.wave) ? 6 : 3;
 
     // pairs are heavy (a million cells): take them one at a time, trace up to G of them at once
     uint32_t gpos = 0, gend = 0;
@@ -739,23 +780,21 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
             if (gpos == gend) {
                 if (exhausted) break;
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(counter, 1u);
+                if (lane == 0) base = atomicAdd(p.class_take + cls, 1u);
                 base = __shfl_sync(kFullA, base, 0);
-                if (base >= n_work) { exhausted = true; break; }
+                if (base >= p.class_count[cls]) {                        // this class is handed out: on to the next
+                    if (++cls >= cls_end) { exhausted = true; break; }
+                    continue;
+                }
                 gpos = base;
                 gend = base + 1;
             }
-            const uint32_t k = WIDE ? p.big_list[gpos] : gpos;
+            const uint32_t k = p.big_list[(size_t)cls * b.n_pairs + gpos];
             const uint32_t n1 = b.len1[k], n2 = b.len2[k];
             const bool fl = n1 >= n2;                                    // c_alignment_interface.c:212
             const uint8_t *pL = b.elems + (fl ? b.off1[k] : b.off2[k]), *pS = b.elems + (fl ? b.off2[k] : b.off1[k]);
             const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
-            const int B = aff_choose_b(ag.wq_need);
-            if (!WIDE && p.wave && B > 8) {                              // -> the 255-register kernel
-                if (lane == 0) p.big_list[atomicAdd(p.big_count, 1u)] = k;
-                ++gpos;
-                continue;
-            }
+            const int B = p.wave ? aff_choose_b_wave(ag.wq_need) : aff_choose_b(ag.wq_need);
             const bool wave = p.wave && ag.S > 0 && B <= 16;
             const uint32_t need = !B ? 0u : wave ? aff_wave_need_words(ag, B) : aff_need_words(ag, B);
             if (!B || need > p.arena_words) {
@@ -768,7 +807,7 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
             const uint32_t fc = wave ? aff_pair_wave<WIDE>(tcm, ag, B, GO, tab_lane, ent_shift, pL, pS, slot, lane)
                                      : aff_pair_rowwise<WIDE>(tcm, ag, B, GO, s_sub, pL, pS, slot, lane);
             if (lane == 0) {
-                s_flags[cnt] = (fl ? 1u : 0u) | (wave ? 4u : 0u);
+                s_flags[cnt] = (fl ? 1u : 0u) | (wave ? 4u : 0u) | ((uint32_t)B << 8);
                 s_off[cnt] = cur;
                 s_pair[cnt] = k;
                 b.cost[k] = (int32_t)fc;
@@ -786,7 +825,7 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                 const bool fl = s_flags[lane] & 1u;
                 const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
-                const int B = aff_choose_b(ag.wq_need);
+                const int B = (int)(s_flags[lane] >> 8);
                 uint32_t *slot = arena + s_off[lane];
                 const uint32_t n = (s_flags[lane] & 4u)
                                        ? aff_trace_wave(slot, 32u * B, ag.S, ag.L, slot + aff_wave_dir_words(ag, B))
@@ -801,7 +840,7 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
                     const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                     const bool fl = s_flags[pe] & 1u;
                     const AffGeom ag = make_aff_geom((int)(fl ? n2 : n1), (int)(fl ? n1 : n2));
-                    const int B = aff_choose_b(ag.wq_need);
+                    const int B = (int)(s_flags[pe] >> 8);
                     const uint32_t *ops = arena + s_off[pe] + ((s_flags[pe] & 4u) ? aff_wave_dir_words(ag, B) : aff_dir_words(ag, B));
                     const uint64_t oo = b.out_off[k];
                     aff_emit(tcm, b.elems + (fl ? b.off1[k] : b.off2[k]), b.elems + (fl ? b.off2[k] : b.off1[k]), ops,
@@ -818,10 +857,16 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
 uint32_t aff_words_for(uint32_t n1, uint32_t n2)
 {
     const AffGeom g = make_aff_geom((int)(n1 < n2 ? n1 : n2), (int)(n1 < n2 ? n2 : n1));
-    const int B = aff_choose_b(g.wq_need);
-    if (!B) return 0u;
-    const uint32_t w1 = aff_need_words(g, B), w2 = aff_wave_need_words(g, B);
+    const int B = aff_choose_b(g.wq_need), Bw = aff_choose_b_wave(g.wq_need);
+    if (!B || !Bw) return 0u;
+    const uint32_t w1 = aff_need_words(g, B), w2 = aff_wave_need_words(g, Bw);
     return w1 > w2 ? w1 : w2;
+}
+
+cudaError_t launch_affine_classify(const AffParams &p, int grid, cudaStream_t stream)
+{
+    aff_classify_kernel<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_affine(const AffParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)

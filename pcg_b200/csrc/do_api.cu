@@ -31,10 +31,12 @@ struct AffParams {
     unsigned int *counter;
     unsigned int *overflow_count;
     int       wave;
-    unsigned int *big_count;
+    unsigned int *class_count;
+    unsigned int *class_take;
     uint32_t     *big_list;
 };
 uint32_t aff_words_for(uint32_t n1, uint32_t n2);
+cudaError_t launch_affine_classify(const AffParams &p, int grid, cudaStream_t stream);
 cudaError_t launch_affine(const AffParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 }
 #include "do_metric.cuh"
@@ -504,8 +506,9 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)b->n_pairs * 4))) return rc;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 128))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)b->n_pairs * 4 * 6))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
     AffParams p{};
     p.tcm = tcm->dev;
     p.b.n_pairs = (uint32_t)b->n_pairs;
@@ -526,14 +529,16 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     p.counter = (unsigned int *)ctx->counters.p;
     p.overflow_count = p.counter + 8;
     CK(cudaEventRecord(ctx->ev0, st));
-    p.big_count = p.counter + 3;
+    p.class_count = p.counter + 16;
+    p.class_take = p.counter + 24;
     p.big_list = (uint32_t *)ctx->big.p;
+    CK(launch_affine_classify(p, grid, st));
     CK(launch_affine(p, false, grid, warps * 32, smem, st));
-    ctx->last_launches = 1;
+    ctx->last_launches = 2;
     if (wave) {     // consumes the queue the first kernel built on the device; exits at once when it is empty
         const int ww = warps < 8 ? warps : 8;
         CK(launch_affine(p, true, grid, ww * 32, tabs + (size_t)ww * 128 * 4, st));
-        ctx->last_launches = 2;
+        ctx->last_launches = 3;
     }
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;

@@ -16,7 +16,7 @@ ctx = P.Context(0)
 ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=5400, max_b=32)
 tcm = ctx.tcm((1 - np.eye(5, dtype=np.uint32)).astype(np.uint32), gap_open=3, affine_variant=1)
 rng = np.random.default_rng(1)
-for delta in (0, 60, 150, 300, 480):
+for delta in [int(x) for x in os.environ.get("DELTAS", "0,60,150,300,480").split(",")]:
     L1, L2 = 5000, 5000 - delta
     a = (1 << rng.integers(0, 4, size=(n, L1))).astype(np.uint8)
     b = (1 << rng.integers(0, 4, size=(n, L2))).astype(np.uint8)
