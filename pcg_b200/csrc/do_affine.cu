@@ -308,6 +308,21 @@ __device__ __forceinline__ void aff_win_load(AffWin<H> &w, int slot, const uint4
     w.o[slot] = v.w & 0x7fffffffu;
 }
 
+template <int H, int S>
+__device__ __forceinline__ void aff_rot(uint32_t (&a)[H])
+{
+    uint32_t t[H];
+#pragma unroll
+    for (int x = 0; x < H; ++x) t[x] = a[(x + S) % H];
+#pragma unroll
+    for (int x = 0; x < H; ++x) a[x] = t[x];
+}
+template <int H, int S>
+__device__ __forceinline__ void aff_win_rotate(AffWin<H> &w)
+{
+    aff_rot<H, S>(w.a); aff_rot<H, S>(w.b); aff_rot<H, S>(w.c); aff_rot<H, S>(w.m); aff_rot<H, S>(w.o);
+}
+
 __device__ __forceinline__ uint32_t aff_lds32(uint32_t saddr)
 {
     uint32_t v;
@@ -365,7 +380,7 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
                                                AffWin<B / 2> &cw, uint32_t tab, const uint4 *&rptr, const uint4 *&cptr,
                                                int n_iter, int i_even0, int j_even0, int lane, uint32_t *&out)
 {
-    constexpr int H = B / 2, CH = (H % 4 == 0) ? H : (H % 2 == 0 ? 2 * H : 4 * H);
+    constexpr int H = B / 2, CH = 4;       // 4 iterations unrolled: larger bodies fall out of the instruction cache
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
@@ -413,6 +428,12 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
     }
     rptr += CH;
     cptr += CH;
+    // the window slots are addressed with compile-time indices that assume the chunk starts at rotation 0: when the
+    // chunk length is not a multiple of the rotation period, rotate the windows by register moves
+    if constexpr (CH % H != 0) {
+        aff_win_rotate<H, CH % H>(rw);
+        aff_win_rotate<H, CH % H>(cw);
+    }
 }
 
 // rowp / colp point at the entries of row 0 / column 0 (padded on both sides).  Returns 4 * FC at (S, L).
@@ -420,7 +441,7 @@ template <int B>
 __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uint32_t tab, const uint4 *rowp,
                                                const uint4 *colp, const uint32_t *row0, uint32_t *dirw, int lane)
 {
-    constexpr int H = B / 2, CH = (H % 4 == 0) ? H : (H % 2 == 0 ? 2 * H : 4 * H);
+    constexpr int H = B / 2, CH = 4;
     uint32_t CB[B], EB[B], EV[B], EH[B], penup[B], dw[B];
     AffWin<H> rw, cw;
     const int qE = g.E0 - kDB;
@@ -462,11 +483,7 @@ __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uin
 }
 
 // per-pair scratch of the wavefront fill (32-bit words): direction words | op stream | row params | column params | row 0
-__host__ __device__ inline int aff_wave_chunk_len(int B)
-{
-    const int H = B / 2;
-    return (H % 4 == 0) ? H : (H % 2 == 0 ? 2 * H : 4 * H);
-}
+__host__ __device__ inline int aff_wave_chunk_len(int) { return 4; }
 __host__ __device__ inline uint32_t aff_wave_iters(const AffGeom &g, int B)
 {
     const int ch = aff_wave_chunk_len(B);

@@ -882,6 +882,7 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.dialect = dialect;
     p.kind = memo ? 2 : 0;
     p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
+    p.skip_b = getenv("PCGDO_SKIP_B") ? (uint32_t)atoi(getenv("PCGDO_SKIP_B")) : 0u;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
     p.delta = memo ? memo->delta : 1u;
     p.k_64k = 65536u;
@@ -898,13 +899,45 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.k_minus1 = 0xffffffffu;
     p.k_one = 1u;
     CK(cudaEventRecord(ctx->ev0, st));
-    CK(launch_explicit(p, grid, warps * 32, smem, st));
+    unsigned int h_left = 0;
+    if (dialect == 0 || getenv("PCGDO_EXPLICIT_SINGLE_PASS")) {
+        CK(launch_explicit(p, grid, warps * 32, smem, st));
+        ctx->last_launches = 1;
+    } else {
+        // one launch per offset of the doubling schedule; lists and counters live on the device, launches whose list
+        // is empty return at once.  The offset at least doubles per pass and a band of max_len covers everything,
+        // after which the thresholds grow with the offset while the cost does not: 2 * log2 passes are plenty.
+        int npass = 8;
+        for (int x = ctx->max_len; x > 0; x >>= 1) npass += 2;
+        if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)b->n_pairs * 8))) return rc;
+        if ((rc = pcgdo_ensure(ctx, ctx->overflow, (size_t)b->n_pairs * 8))) return rc;
+        if ((rc = pcgdo_ensure(ctx, ctx->counters, 64 + 8 * (size_t)(npass + 2)))) return rc;
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 64 + 8 * (size_t)(npass + 2), st));
+        p.counter = (unsigned int *)ctx->counters.p;
+        p.overflow_count = p.counter + 8;
+        unsigned int *take = p.counter + 16, *cnt = take + (npass + 2);
+        uint32_t *lists[2] = {(uint32_t *)ctx->big.p, (uint32_t *)ctx->big.p + b->n_pairs};
+        p.pair_off = (long long *)ctx->overflow.p;
+        for (int pass = 0; pass < npass; ++pass) {
+            p.counter = take + pass;
+            p.in_list = pass ? lists[(pass - 1) & 1] : nullptr;
+            p.in_count = pass ? cnt + (pass - 1) : nullptr;
+            p.out_list = lists[pass & 1];
+            p.out_count = cnt + pass;
+            CK(launch_explicit(p, grid, warps * 32, smem, st));
+        }
+        ctx->last_launches = npass;
+        CK(cudaMemcpyAsync(&h_left, cnt + (npass - 1), 4, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
-    ctx->last_launches = 1;
     unsigned int h_over[2] = {0, 0};
     CK(cudaMemcpyAsync(h_over, p.overflow_count, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (h_left) {
+        ctx->err = "explicit-matrix path: the doubling schedule did not terminate within the launched passes";
+        return PCGDO_ERR_OVERFLOW;
+    }
     if (h_over[0]) {
         char msg[260];
         snprintf(msg, sizeof msg, "%u pair(s) exceed the explicit-matrix kernel's limits (band wider than 1023 diagonals, "

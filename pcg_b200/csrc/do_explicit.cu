@@ -354,6 +354,14 @@ __device__ __forceinline__ void x_emit(const uint32_t *sg, int a, int kind, cons
     }
 }
 
+// fewer fill variants = smaller instruction footprint when every warp walks through the doubling schedule
+__device__ __forceinline__ int x_choose_b(int wb, uint32_t skip)
+{
+    int B = m_choose_b(wb);
+    while (B && B < 32 && (skip & (uint32_t)B)) B *= 2;
+    return B;
+}
+
 __host__ __device__ inline uint32_t x_hash_size(uint32_t n)
 {
     uint32_t h = 32;
@@ -432,19 +440,23 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
     uint32_t *ts = p.tscratch + warp_global * (size_t)p.tscratch_words;
     const bool want_out = b.out_med || b.out_a1 || b.out_a2 || b.out_len;
+    // multi-pass mode: one Ukkonen offset per launch.  Pairs whose band must double are queued for the next launch,
+    // so that all warps of the GPU run the same fill variant at the same time (with every warp walking its own
+    // schedule the unrolled variants thrash the instruction cache: 40 % "no instruction" stalls measured)
+    const uint32_t n_work = p.in_count ? *p.in_count : b.n_pairs;
 
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
         base = __shfl_sync(kFullM, base, 0);
-        if (base >= b.n_pairs) break;
-        const int npw = (int)min((uint32_t)G, b.n_pairs - base);
+        if (base >= n_work) break;
+        const int npw = (int)min((uint32_t)G, n_work - base);
         int pi = 0;
         while (pi < npw) {
             const int start = pi;
             uint32_t cur = 0;
             for (; pi < npw; ++pi) {
-                const uint32_t k = base + pi;
+                const uint32_t k = p.in_list ? p.in_list[base + pi] : base + pi;
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
                 const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
                 bool swapped = n1 > n2;                     // measureCharacters on the median strings
@@ -475,6 +487,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 const bool full = p.dialect == 0 || no_gain;
                 const bool s2 = p.dialect == 2 && !no_gain;
                 long long off = p.dialect == 2 ? 2 + Gc : 2;
+                if (p.in_list) off = p.pair_off[k];                  // a later pass: the offset this pair was queued with
+                bool requeue = false;
 
                 // ---------------- number the distinct elements, build profiles, indel costs and the pair's table
                 const uint32_t HL = x_hash_size((uint32_t)n), HS = x_hash_size((uint32_t)m);
@@ -591,7 +605,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 const MGeom gfull = make_mgeom(lg, sh, -(lg - 1), sh - 1);
                 uint32_t fw = 0, csum = 0;
                 MGeom g = gfull;
-                int B = m_choose_b(gfull.wb);
+                int B = x_choose_b(gfull.wb, p.skip_b);
                 uint32_t need = 0;
                 int final_off = -1;
                 bool used16 = false;
@@ -599,7 +613,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     if (!full) {
                         const int a_off = (int)(off < m ? off : m);
                         g = make_mgeom(lg, sh, -(n - m) - a_off, a_off);
-                        B = m_choose_b(g.wb);
+                        B = x_choose_b(g.wb, p.skip_b);
                         final_off = (int)(off > 0x7fffffff ? 0x7fffffff : off);
                     }
                     MSeq sl = {0, 0, 0, 0};
@@ -655,6 +669,15 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                         if (thr < 0) thr = 0;
                         if (thr <= cost) off *= 2; else break;
                     }
+                    if (p.out_list) { requeue = true; break; }       // the doubled band is the next launch's work
+                }
+                if (ok && requeue) {
+                    if (lane == 0) {
+                        s_flags[pi] = 0;
+                        p.pair_off[k] = off;
+                        p.out_list[atomicAdd(p.out_count, 1u)] = k;
+                    }
+                    continue;
                 }
                 if (!ok) {
                     if (lane == 0) { s_flags[pi] = 0; atomicAdd(p.overflow_count, 1u); if (bad) atomicAdd(p.overflow_count + 1, 1u); }
@@ -681,11 +704,11 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
             if (!want_out) continue;
             const int pj = start + lane;
             if (pj < pi && (s_flags[pj] & 2u)) {
-                const uint32_t k = base + pj;
+                const uint32_t k = p.in_list ? p.in_list[base + pj] : base + pj;
                 const bool swapped = s_flags[pj] & 1u;
                 const int n = (int)(swapped ? b.len1[k] : b.len2[k]), m = (int)(swapped ? b.len2[k] : b.len1[k]);
                 const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pj] & 0xffffu), (int)(int16_t)(s_geo[pj] >> 16));
-                const int B = m_choose_b(g.wb);
+                const int B = x_choose_b(g.wb, p.skip_b);
                 uint32_t *slot = arena + s_off[pj];
                 const uint32_t na = (s_flags[pj] & 4u) ? trace_lane16(slot, B, g.q0, g.lg, g.sh, slot + m_dir_words(g, B))
                                                        : m_trace(slot, 32u * B, g.q0, g.lg, g.sh, slot + m_dir_words(g, B));
@@ -696,12 +719,12 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
             if (b.out_med || b.out_a1 || b.out_a2) {
                 for (int pe = start; pe < pi; ++pe) {
                     if (!(s_flags[pe] & 2u)) continue;
-                    const uint32_t k = base + pe;
+                    const uint32_t k = p.in_list ? p.in_list[base + pe] : base + pe;
                     const bool swapped = s_flags[pe] & 1u;
                     const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
                     const int n = (int)(swapped ? b.len1[k] : b.len2[k]), m = (int)(swapped ? b.len2[k] : b.len1[k]);
                     const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pe] & 0xffffu), (int)(int16_t)(s_geo[pe] >> 16));
-                    const int B = m_choose_b(g.wb);
+                    const int B = x_choose_b(g.wb, p.skip_b);
                     const uint32_t *ops = arena + s_off[pe] + m_dir_words(g, B);
                     const uint64_t oo = b.out_off[k];
                     x_emit(sg, a, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe], swapped,

@@ -10,6 +10,7 @@ struct ExplicitParams {
     int       dialect;        // 0 S1 full, 1 S1 Ukkonen, 2 S2 Ukkonen
     int       kind;           // 0 discrete metric (closed form, sigma unused), 2 explicit sigma
     int       pack16;         // allow the packed 16-bit fill
+    uint32_t  skip_b;         // bit mask of diagonals-per-lane values (2, 4, 8, 16) not to use: round up instead
     const uint32_t *sigma;    // device [a*a]: sigma[s*a + j], s = median symbol, j = input symbol
     uint32_t  delta;          // cheapest indel of a single non-gap symbol (Ukkonen coefficient)
     uint32_t *arena;          // per warp: direction words + op streams
@@ -22,6 +23,12 @@ struct ExplicitParams {
     unsigned int *counter;
     unsigned int *overflow_count;
     uint32_t  k_four, k_minus1, k_one, k_64k;
+    // multi-pass mode (one Ukkonen offset per launch); all NULL = every warp walks the whole schedule of its pairs
+    const uint32_t     *in_list;    // pairs of this pass (NULL in the first pass: all pairs)
+    const unsigned int *in_count;
+    uint32_t           *out_list;   // pairs whose band must double: the next pass
+    unsigned int       *out_count;
+    long long          *pair_off;   // [n_pairs] offset a queued pair continues with
 };
 
 size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries);
