@@ -900,10 +900,11 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.k_one = 1u;
     CK(cudaEventRecord(ctx->ev0, st));
     unsigned int h_left = 0;
-    if (dialect == 0 || getenv("PCGDO_EXPLICIT_SINGLE_PASS")) {
+    if (dialect == 0 || !getenv("PCGDO_EXPLICIT_MULTI_PASS")) {
         CK(launch_explicit(p, grid, warps * 32, smem, st));
         ctx->last_launches = 1;
     } else {
+        // (experiment, off by default: it re-builds every pair's table per pass and measured slower than one launch)
         // one launch per offset of the doubling schedule; lists and counters live on the device, launches whose list
         // is empty return at once.  The offset at least doubles per pass and a band of max_len covers everything,
         // after which the thresholds grow with the offset while the cost does not: 2 * log2 passes are plenty.

@@ -199,9 +199,9 @@ __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (
                                           uint32_t k64k, const char *gtab, const uint32_t *&lptr, const uint32_t *&sptr,
                                           int n_iter, uint32_t *&out)
 {
-    constexpr int H = B / 2, Q = H / 2;
+    constexpr int H = B / 2, Q = H / 2, CH = pack16_chunk(B);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
         const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
@@ -248,8 +248,9 @@ __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (
             out += 32 * H;
         }
     }
-    lptr += 16;
-    sptr += 16;
+    lptr += CH;
+    sptr += CH;
+    if constexpr (CH % H != 0) { rot16<H, CH % H>(lw); rot16<H, CH % H>(sw); }
 }
 
 // returns the last cell in the 32-bit convention of x_fill, or kOverflow16
@@ -285,15 +286,16 @@ __device__ __noinline__ uint32_t x_fill16(const MGeom g, uint32_t k4, uint32_t k
     }
     const uint32_t *lptr = Lb + (I0 + 1), *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
-    const int nfull = g.T >> 4, rem = g.T & 15;
+    constexpr int CH = pack16_chunk(B), RB = 32 / CH;
+    const int nfull = g.T / CH, rem = g.T % CH;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
-        if (c && !(c & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, 16, out);
+        if (c && c % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, CH, out);
     }
     if (rem) {
-        if (nfull && !(nfull & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        if (nfull && nfull % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
         x_chunk16<B, GLOBAL, true>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, rem, out);
     }
     ok = rebase16<H>(R, total_shift, spread_limit) && ok;
@@ -440,9 +442,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
     uint32_t *ts = p.tscratch + warp_global * (size_t)p.tscratch_words;
     const bool want_out = b.out_med || b.out_a1 || b.out_a2 || b.out_len;
-    // multi-pass mode: one Ukkonen offset per launch.  Pairs whose band must double are queued for the next launch,
-    // so that all warps of the GPU run the same fill variant at the same time (with every warp walking its own
-    // schedule the unrolled variants thrash the instruction cache: 40 % "no instruction" stalls measured)
+    // optional multi-pass mode (PCGDO_EXPLICIT_MULTI_PASS): one Ukkonen offset per launch, pairs whose band must
+    // double are queued for the next launch so that all warps run the same fill variant at the same time
     const uint32_t n_work = p.in_count ? *p.in_count : b.n_pairs;
 
     for (;;) {

@@ -231,9 +231,9 @@ __device__ __forceinline__ void run_chunk16(uint32_t (&R)[B / 2], const uint32_t
                                             uint32_t tab_lane, const char *&lptr, const char *&sptr, int n_iter,
                                             uint32_t *&out)
 {
-    constexpr int H = B / 2, Q = H / 2;
+    constexpr int H = B / 2, Q = H / 2, CH = pack16_chunk(B);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
         // ---- even diagonals (registers with even m): anti-diagonal s = 2t
@@ -278,8 +278,9 @@ __device__ __forceinline__ void run_chunk16(uint32_t (&R)[B / 2], const uint32_t
             out += 32 * H;
         }
     }
-    lptr += 16;
-    sptr += 32;
+    lptr += CH;
+    sptr += 2 * CH;
+    if constexpr (CH % H != 0) { rot16<H, CH % H>(lw); rot16<H, CH % H>(sw); }
 }
 
 // Returns the final cell's 4*(v - C - G) + kBias4 | code in the 32-bit convention of fill_pair, or kOverflow16.
@@ -316,15 +317,16 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
     const char *lptr = Lb + (I0 + 1);
     const char *sptr = Sb + 2 * (J0 + H);
     uint32_t *out = slot + lane * H;
-    const int nfull = g.T >> 4, rem = g.T & 15;
+    constexpr int CH = pack16_chunk(B), RB = 32 / CH;        // re-base every 32 iterations
+    const int nfull = g.T / CH, rem = g.T % CH;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
-        if (c && !(c & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        run_chunk16<B, false>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, 16, out);
+        if (c && c % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        run_chunk16<B, false>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, CH, out);
     }
     if (rem) {
-        if (nfull && !(nfull & 1)) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
+        if (nfull && nfull % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
         run_chunk16<B, true>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, rem, out);
     }
     // one last look at the window: everything since the previous check stayed inside it iff that check passed

@@ -7,6 +7,20 @@
 namespace pcgdo {
 
 constexpr unsigned kFull = 0xffffffffu;
+// Iterations unrolled per chunk of the packed fill: 16 up to 8 diagonals per lane, 8 beyond — the unrolled body of the
+// wider variants would otherwise be tens of KB and fall out of the instruction cache.  With 32 diagonals per lane the
+// register windows rotate with period 16, so every 8-iteration chunk ends with a rotation by register moves (rot16).
+__host__ __device__ constexpr int pack16_chunk(int B) { return B <= 8 ? 16 : 8; }
+template <int H, int S>
+__device__ __forceinline__ void rot16(uint32_t (&a)[H])
+{
+    uint32_t t[H];
+#pragma unroll
+    for (int x = 0; x < H; ++x) t[x] = a[(x + S) % H];
+#pragma unroll
+    for (int x = 0; x < H; ++x) a[x] = t[x];
+}
+
 constexpr uint32_t kTop16 = 0x7000u;
 constexpr uint32_t kOverflow16 = 0xffffffffu;
 

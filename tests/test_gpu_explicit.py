@@ -118,3 +118,25 @@ def test_explicit_discrete_matrix_equals_metric_kernel(gpu_ctx):
         for k in range(len(pairs)):
             for x, y in zip(r0.pair(k)[1:], r1.pair(k)[1:]):
                 assert np.array_equal(x, y), (dialect, k)
+
+
+def test_multi_pass_schedule_equals_single_launch(gpu_ctx, monkeypatch):
+    """PCGDO_EXPLICIT_MULTI_PASS=1 runs one Ukkonen offset per launch with device-side queues; same results."""
+    from pcg_b200.pairwise import metric_do_batch
+    rng = np.random.default_rng(99)
+    a = 21
+    pairs = _pairs(rng, a, 200, 250)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=300, max_b=32, arena_words=0)
+    memo = gpu_ctx.memo(_sigma("pref-gap", a, rng))
+    f, s = [p[0] for p in pairs], [p[1] for p in pairs]
+    for dialect in (1, 2):
+        for alpha in (a, memo):
+            ref = metric_do_batch(gpu_ctx, alpha, dialect, f, s)
+            monkeypatch.setenv("PCGDO_EXPLICIT_MULTI_PASS", "1")
+            r = metric_do_batch(gpu_ctx, alpha, dialect, f, s)
+            monkeypatch.delenv("PCGDO_EXPLICIT_MULTI_PASS")
+            assert np.array_equal(ref.cost, r.cost) and np.array_equal(ref.final_offset, r.final_offset)
+            assert np.array_equal(ref.out_len, r.out_len) and np.array_equal(ref.cells, r.cells)
+            for k in range(len(pairs)):
+                for x, y in zip(ref.pair(k)[1:], r.pair(k)[1:]):
+                    assert np.array_equal(x, y), (dialect, k)
