@@ -240,12 +240,18 @@ uint32_t pcgdo_forest_levels(const pcgdo_forest *forest);
  * alignment per unrooted edge; per-tree cost = sum over characters of the minimum over the 2*n_taxa-3 edges (each
  * dynamic character picks its own root edge).  enable_rerooting grows the node storage to 3 slots per internal
  * node.  get_edges: (u, v) node ids of one tree's edges (edge 0 = the original root edge) and, for one character,
- * the total / local cost of rooting on each. */
-int  pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *forest);
+ * the total / local cost of rooting on each.  keep_edge_data = 1 additionally keeps every edge's datum (the median of
+ * rooting the tree there) for Wagner-build edge trials (app/pcg/PCG/Command/Build/Evaluate.hs:494-527, tryEdge):
+ * pcgdo_forest_try_leaf aligns a new leaf (HOST strings, one per character) with every edge datum of every tree, cost
+ * only, and returns delta[tree * n_edges + edge] = sum over characters of the local cost (HOST int64) — the cost
+ * increase of attaching the leaf to that edge. */
+int  pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *forest, int keep_edge_data);
 int  pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *forest, void *cuda_stream);
 int  pcgdo_forest_get_edges(pcgdo_ctx *ctx, pcgdo_forest *forest, uint32_t tree, uint32_t character, int32_t *edge_uv,
                             int64_t *edge_total, int32_t *edge_local);
 uint32_t pcgdo_forest_edges(const pcgdo_forest *forest);
+int  pcgdo_forest_try_leaf(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *forest, const uint8_t *elems,
+                           const uint64_t *off, const uint32_t *len, int64_t *delta_out, void *cuda_stream);
 uint64_t pcgdo_forest_alignments(const pcgdo_forest *forest);
 
 /* Measured integer instruction-issue rate of this GPU in lane-instructions/s (roofline denominator of the

@@ -146,13 +146,13 @@ class Oracle:
         return int(cost), np.stack([om[:k], ol[:k], orr[:k]], axis=1), int(cells.value)
 
 
-def reroot(oracle: "Oracle", children, leaves):
+def reroot(oracle: "Oracle", children, leaves, trial=None):
     """Re-rooting pass of one tree / one character (reroot_oracle.c).  children: (n_taxa-1, 2) int32, leaves: list of
-    element strings.  Returns (min cost, edges [(u, v)], edge_cost, edge_local)."""
+    element strings.  Returns (min cost, edges [(u, v)], edge_cost, edge_local); with `trial` (a new leaf's string)
+    a fifth item: the Wagner edge-trial cost per edge."""
     lib = oracle.lib
-    lib.oracle_reroot.restype = C.c_int64
-    lib.oracle_reroot.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_reroot_trial.restype = C.c_int64
+    lib.oracle_reroot_trial.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]
     ch = np.ascontiguousarray(np.asarray(children, np.int32))
     n_taxa = ch.shape[0] + 1
     arrs = [_as_u32(x) for x in leaves]
@@ -161,9 +161,14 @@ def reroot(oracle: "Oracle", children, leaves):
     ne = 2 * n_taxa - 3
     eu, ev = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
     ec, el = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
-    best = lib.oracle_reroot(oracle.t, n_taxa, ch.ctypes.data, ptrs, lens, eu.ctypes.data, ev.ctypes.data,
-                             ec.ctypes.data, el.ctypes.data, None)
-    return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el
+    tr = _as_u32(trial) if trial is not None else None
+    et = np.zeros(ne, np.int64)
+    best = lib.oracle_reroot_trial(oracle.t, n_taxa, ch.ctypes.data, ptrs, lens, eu.ctypes.data, ev.ctypes.data,
+                                   ec.ctypes.data, el.ctypes.data, None, tr.ctypes.data if tr is not None else None,
+                                   len(tr) if tr is not None else 0, et.ctypes.data)
+    if trial is None:
+        return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el
+    return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el, et
 
 
 def haskell_do(dialect: int, a: int, in1, in2, sigma=None):

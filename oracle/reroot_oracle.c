@@ -87,9 +87,35 @@ static const datum_t *entering(rr_t *R, uint32_t n, uint32_t from)
 /* One tree, one character.  leaf[v] / leaf_len[v]: ungapped element strings of the taxa.
  * Outputs (2*n_taxa - 3 edges): edge_u/edge_v endpoints, edge_cost total cost of rooting there, edge_local the
  * local cost of that rooting.  Edge 0 is the original root edge.  Returns the minimum edge cost. */
+static int64_t trial_cost(rr_t *R, const datum_t *edge, const uint32_t *leaf, size_t n)
+{
+    /* iterativeBuild.tryEdge (app/pcg/PCG/Command/Build/Evaluate.hs:494-527): the local cost of the post-order
+     * function applied to (edge datum, new leaf) */
+    datum_t l = { (uint32_t *)leaf, n, 0, 0, 1 }, out;
+    memset(&out, 0, sizeof out);
+    apply(R, edge, &l, &out);
+    free(out.s);
+    return out.local;
+}
+
+int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *children,
+                            const uint32_t *const *leaf, const size_t *leaf_len,
+                            int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells,
+                            const uint32_t *trial, size_t trial_len, int64_t *edge_trial);
+
 int64_t oracle_reroot(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *children,
                       const uint32_t *const *leaf, const size_t *leaf_len,
                       int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells)
+{
+    return oracle_reroot_trial(t, n_taxa, children, leaf, leaf_len, edge_u, edge_v, edge_cost, edge_local, cells,
+                               NULL, 0, NULL);
+}
+
+/* As oracle_reroot; with `trial` != NULL also edge_trial[e] = cost increase of attaching that new leaf to edge e. */
+int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *children,
+                            const uint32_t *const *leaf, const size_t *leaf_len,
+                            int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells,
+                            const uint32_t *trial, size_t trial_len, int64_t *edge_trial)
 {
     rr_t R;
     memset(&R, 0, sizeof R);
@@ -120,7 +146,9 @@ int64_t oracle_reroot(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *chi
     /* the root edge keeps the post-order root resolution */
     {
         const datum_t *d = down_of(&R, R.root);
-        edge_u[ne] = rc[0]; edge_v[ne] = rc[1]; edge_cost[ne] = d->total; edge_local[ne] = d->local; ne++;
+        edge_u[ne] = rc[0]; edge_v[ne] = rc[1]; edge_cost[ne] = d->total; edge_local[ne] = d->local;
+        if (trial) edge_trial[ne] = trial_cost(&R, d, trial, trial_len);
+        ne++;
         best = d->total;
     }
     for (uint32_t i = n_taxa; i < R.n_nodes; i++) {
@@ -131,7 +159,9 @@ int64_t oracle_reroot(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *chi
             datum_t e;
             memset(&e, 0, sizeof e);
             apply(&R, entering(&R, i, j), entering(&R, j, i), &e);
-            edge_u[ne] = (int32_t)i; edge_v[ne] = (int32_t)j; edge_cost[ne] = e.total; edge_local[ne] = e.local; ne++;
+            edge_u[ne] = (int32_t)i; edge_v[ne] = (int32_t)j; edge_cost[ne] = e.total; edge_local[ne] = e.local;
+            if (trial) edge_trial[ne] = trial_cost(&R, &e, trial, trial_len);
+            ne++;
             if (e.total < best) best = e.total;
             free(e.s);
         }

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
-    "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges",
+    "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges", "pcgdo_forest_try_leaf",
     "pcgdo_memo_create", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
     "pcgdo_explicit_batch_device", "pcgdo_explicit_batch_host",
     "matrixInit", "matrixDestroy", "getCostAndMedian2D",
@@ -122,7 +122,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_forest_levels.restype = C.c_uint32
     L.pcgdo_forest_alignments.argtypes = [C.c_void_p]
     L.pcgdo_forest_alignments.restype = C.c_uint64
-    L.pcgdo_forest_enable_rerooting.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_enable_rerooting.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.pcgdo_forest_try_leaf.argtypes = [C.c_void_p] * 8
     L.pcgdo_forest_score_rerooted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pcgdo_forest_get_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pcgdo_forest_edges.argtypes = [C.c_void_p]
@@ -315,8 +316,24 @@ class Forest:
         self.ctx.check(self.ctx.lib.pcgdo_forest_copy_tree_costs(self.ctx.h, self.h, C.c_void_p(dst_device_ptr),
                                                                  C.c_void_p(stream)), "pcgdo_forest_copy_tree_costs")
 
-    def enable_rerooting(self) -> None:
-        self.ctx.check(self.ctx.lib.pcgdo_forest_enable_rerooting(self.ctx.h, self.h), "pcgdo_forest_enable_rerooting")
+    def enable_rerooting(self, keep_edge_data: bool = False) -> None:
+        self.ctx.check(self.ctx.lib.pcgdo_forest_enable_rerooting(self.ctx.h, self.h, int(keep_edge_data)),
+                       "pcgdo_forest_enable_rerooting")
+
+    def try_leaf(self, tcm: Tcm, leaf_strings, stream: int = 0) -> np.ndarray:
+        """Wagner edge trial (``iterativeBuild.tryEdge``): cost increase of attaching a new taxon (one element string
+        per character) to every edge of every tree -> int64 (n_trees, n_edges).  Needs a re-rooted sweep with
+        ``enable_rerooting(keep_edge_data=True)``."""
+        flat = [np.asarray(x, np.uint8) for x in leaf_strings]
+        ln = np.array([len(x) for x in flat], np.uint32)
+        off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
+        elems = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1, np.uint8)
+        ne = int(self.ctx.lib.pcgdo_forest_edges(self.h))
+        out = np.zeros((self.n_trees, ne), np.int64)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_try_leaf(self.ctx.h, tcm.h, self.h, elems.ctypes.data, off.ctypes.data,
+                                                          ln.ctypes.data, out.ctypes.data, C.c_void_p(stream)),
+                       "pcgdo_forest_try_leaf")
+        return out
 
     def score_rerooted(self, tcm: Tcm, stream: int = 0) -> np.ndarray:
         """Post-order + re-rooting: per-tree sum over characters of the cheapest root edge."""

@@ -44,6 +44,10 @@ struct pcgdo_forest {
     std::vector<std::pair<size_t, size_t>> up_levels;         // pre-order levels (by depth) of directed-datum jobs
     std::pair<size_t, size_t> edge_items{0, 0};
     DevBuf edge_total, edge_local, char_min;                  // i64 / i32 [n_trees*n_chars*n_edges], i64 [n_trees*n_chars]
+    bool keep_edges = false;             // edge data (median of rooting on each edge) kept for Wagner edge trials
+    size_t trial_off = 0;                // byte offset of the trial leaf's slots in `store`
+    DevBuf trial_len, trial_delta;       // u32 [n_chars], i64 [n_trees * n_edges]
+    std::pair<size_t, size_t> trial_items{0, 0};
     size_t leaf_bytes = 0;
     DevBuf store;        // [leaf slots | internal-node slots], cap bytes each
     DevBuf leaf_len;     // u32 [n_taxa * n_chars]
@@ -64,6 +68,8 @@ namespace {
 struct ForestDev {
     uint32_t n_taxa, n_chars, n_internal, cap;        // n_internal = result slots per column (stride)
     uint64_t leaf_bytes;
+    uint64_t trial_off;                               // refs >= n_taxa + n_internal: the trial leaf
+    const uint32_t *trial_len;
     const uint32_t *leaf_len;
     uint32_t *node_len;
     int32_t *node_local;
@@ -73,6 +79,7 @@ struct ForestDev {
 __device__ __forceinline__ uint64_t slot_of(const ForestDev &f, uint32_t tree, uint32_t c, int32_t node)
 {
     if ((uint32_t)node < f.n_taxa) return ((uint64_t)node * f.n_chars + c) * f.cap;
+    if ((uint32_t)node >= f.n_taxa + f.n_internal) return f.trial_off + (uint64_t)c * f.cap;
     return f.leaf_bytes + (((uint64_t)tree * f.n_chars + c) * f.n_internal + (uint32_t)(node - f.n_taxa)) * f.cap;
 }
 __device__ __forceinline__ uint64_t nidx(const ForestDev &f, uint32_t tree, uint32_t c, uint32_t x)
@@ -93,7 +100,8 @@ __global__ void forest_prep_kernel(ForestDev f, const LevelItem *items, uint32_t
     len1[k] = (uint32_t)it.left < f.n_taxa ? f.leaf_len[(uint64_t)it.left * f.n_chars + c]
                                            : f.node_len[nidx(f, it.tree, c, it.left - f.n_taxa)];
     len2[k] = (uint32_t)it.right < f.n_taxa ? f.leaf_len[(uint64_t)it.right * f.n_chars + c]
-                                            : f.node_len[nidx(f, it.tree, c, it.right - f.n_taxa)];
+              : (uint32_t)it.right >= f.n_taxa + f.n_internal ? f.trial_len[c]
+                                                              : f.node_len[nidx(f, it.tree, c, it.right - f.n_taxa)];
 }
 
 __global__ void forest_post_kernel(ForestDev f, const LevelItem *items, uint32_t n_items, const int32_t *cost,
@@ -138,6 +146,37 @@ __global__ void forest_edge_post_kernel(ForestDev f, const LevelItem *items, uin
     edge_local[e] = cost[k];
 }
 
+// edge jobs that keep their datum: totals per edge as above, plus the datum's length in its slot
+__global__ void forest_edge_keep_kernel(ForestDev f, const LevelItem *items, uint32_t n_items, const int32_t *cost,
+                                        const uint32_t *ulen, uint32_t n_edges, uint32_t edge_slot0, int64_t *edge_total,
+                                        int32_t *edge_local)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (uint64_t)n_items * f.n_chars) return;
+    const LevelItem it = items[k / f.n_chars];
+    const uint32_t c = (uint32_t)(k % f.n_chars);
+    int64_t tot = cost[k];
+    if ((uint32_t)it.left >= f.n_taxa) tot += f.node_total[nidx(f, it.tree, c, it.left - f.n_taxa)];
+    if ((uint32_t)it.right >= f.n_taxa) tot += f.node_total[nidx(f, it.tree, c, it.right - f.n_taxa)];
+    const uint32_t edge = (uint32_t)it.out - edge_slot0;
+    const uint64_t e = ((uint64_t)it.tree * f.n_chars + c) * n_edges + edge;
+    edge_total[e] = tot;
+    edge_local[e] = cost[k];
+    f.node_len[nidx(f, it.tree, c, it.out)] = ulen[k];
+}
+
+// Wagner edge trial: delta[tree][edge] = sum over characters of the local cost of (edge datum, new leaf)
+__global__ void forest_trial_sum_kernel(const LevelItem *items, uint32_t n_items, uint32_t n_chars, uint32_t n_edges,
+                                        const int32_t *cost, int64_t *delta)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_items) return;
+    const LevelItem it = items[k];
+    int64_t s = 0;
+    for (uint32_t c = 0; c < n_chars; ++c) s += cost[(uint64_t)k * n_chars + c];
+    delta[(uint64_t)it.tree * n_edges + (uint32_t)it.out] = s;
+}
+
 // per (tree, character): the root edge keeps the post-order root; minimum over all edges
 __global__ void forest_edge_min_kernel(ForestDev f, const int32_t *roots, uint32_t n_trees, uint32_t n_edges,
                                        int64_t *edge_total, int32_t *edge_local, int64_t *char_min)
@@ -168,6 +207,8 @@ ForestDev dev_view(const pcgdo_forest *F)
     ForestDev f;
     f.n_taxa = F->n_taxa; f.n_chars = F->n_chars; f.n_internal = F->stride; f.cap = F->cap;
     f.leaf_bytes = F->leaf_bytes;
+    f.trial_off = F->trial_off;
+    f.trial_len = (const uint32_t *)F->trial_len.p;
     f.leaf_len = (const uint32_t *)F->leaf_len.p;
     f.node_len = (uint32_t *)F->node_len.p;
     f.node_local = (int32_t *)F->node_local.p;
@@ -275,7 +316,7 @@ extern "C" void pcgdo_forest_destroy(pcgdo_ctx *ctx, pcgdo_forest *F)
     if (ctx) cudaSetDevice(ctx->device);
     DevBuf *bufs[] = {&F->store, &F->leaf_len, &F->node_len, &F->node_local, &F->node_total, &F->items, &F->roots,
                       &F->tree_cost, &F->boff1, &F->boff2, &F->buoff, &F->blen1, &F->blen2, &F->bcost, &F->bulen,
-                      &F->edge_total, &F->edge_local, &F->char_min};
+                      &F->edge_total, &F->edge_local, &F->char_min, &F->trial_len, &F->trial_delta};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete F;
@@ -324,7 +365,7 @@ static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *
         bd.off1 = (const uint64_t *)F->boff1.p; bd.off2 = (const uint64_t *)F->boff2.p;
         bd.len1 = (const uint32_t *)F->blen1.p; bd.len2 = (const uint32_t *)F->blen2.p;
         bd.cost = (int32_t *)F->bcost.p;
-        if (mode == 0) {
+        if (mode == 0 || mode == 2) {
             bd.out_ungapped = (uint8_t *)F->store.p;
             bd.out_uoff = (const uint64_t *)F->buoff.p;
             bd.out_ulen = (uint32_t *)F->bulen.p;
@@ -336,9 +377,17 @@ static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *
         if (mode == 0)
             forest_post_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p,
                                                        (const uint32_t *)F->bulen.p);
-        else
+        else if (mode == 1)
             forest_edge_post_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p, F->n_edges,
                                                             (int64_t *)F->edge_total.p, (int32_t *)F->edge_local.p);
+        else if (mode == 2)
+            forest_edge_keep_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p,
+                                                            (const uint32_t *)F->bulen.p, F->n_edges, 3 * F->n_internal,
+                                                            (int64_t *)F->edge_total.p, (int32_t *)F->edge_local.p);
+        else
+            forest_trial_sum_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(items, n_items, F->n_chars, F->n_edges,
+                                                                           (const int32_t *)F->bcost.p,
+                                                                           (int64_t *)F->trial_delta.p);
         CK(cudaGetLastError());
         ctx->last_launches += 2;
     }
@@ -388,10 +437,11 @@ extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_fo
 
 // Builds the pre-order (directed data) and edge job lists and grows the node storage to 3 result slots per
 // internal node.  Call once, before or after pcgdo_forest_set_leaves.
-extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F)
+extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, int keep_edge_data)
 {
     if (!ctx || !F) return PCGDO_ERR_ARG;
-    if (F->reroot) return PCGDO_OK;
+    if (F->reroot) return (keep_edge_data && !F->keep_edges) ? PCGDO_ERR_ARG : PCGDO_OK;
+    F->keep_edges = keep_edge_data != 0;
     if (F->n_taxa < 3) {
         ctx->err = "re-rooting needs at least 3 taxa";
         return PCGDO_ERR_ARG;
@@ -452,8 +502,10 @@ extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F)
             by_depth[d].push_back({(int32_t)t, (int32_t)(ni + 2 * (uint32_t)x + 0), c2, ps});
             by_depth[d].push_back({(int32_t)t, (int32_t)(ni + 2 * (uint32_t)x + 1), ps, c1});
             // the two edges below n: DO("n entered from the child", the child's post-order datum)
-            edges.push_back({(int32_t)t, (int32_t)ne, up_ref(n, 0), c1}); he[2 * ne] = n; he[2 * ne + 1] = c1; ++ne;
-            edges.push_back({(int32_t)t, (int32_t)ne, up_ref(n, 1), c2}); he[2 * ne] = n; he[2 * ne + 1] = c2; ++ne;
+            // (with kept edge data the result slot of edge e is 3 * n_internal + e)
+            const int32_t eslot = F->keep_edges ? (int32_t)(3 * ni) : 0;
+            edges.push_back({(int32_t)t, eslot + (int32_t)ne, up_ref(n, 0), c1}); he[2 * ne] = n; he[2 * ne + 1] = c1; ++ne;
+            edges.push_back({(int32_t)t, eslot + (int32_t)ne, up_ref(n, 1), c2}); he[2 * ne] = n; he[2 * ne + 1] = c2; ++ne;
         }
         if (ne != F->n_edges) {
             ctx->err = "re-rooting: internal error enumerating the unrooted edges";
@@ -472,14 +524,26 @@ extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F)
     }
     F->edge_items = {all.size(), edges.size()};
     all.insert(all.end(), edges.begin(), edges.end());
+    const uint32_t stride = 3 * ni + (F->keep_edges ? F->n_edges : 0u);
+    if (F->keep_edges) {
+        // trial jobs: (edge datum, trial leaf) for every tree and edge; edge 0's datum is the post-order root
+        F->trial_items = {all.size(), (size_t)F->n_trees * F->n_edges};
+        for (uint32_t t = 0; t < F->n_trees; ++t)
+            for (uint32_t e = 0; e < F->n_edges; ++e)
+                all.push_back({(int32_t)t, (int32_t)e,
+                               e == 0 ? (int32_t)(n_taxa + (uint32_t)F->h_roots[t]) : (int32_t)(n_taxa + 3 * ni + e),
+                               (int32_t)(n_taxa + stride)});
+    }
     int rc;
     if ((rc = pcgdo_ensure(ctx, F->items, all.size() * sizeof(LevelItem)))) return rc;
     CK(cudaMemcpy(F->items.p, all.data(), all.size() * sizeof(LevelItem), cudaMemcpyHostToDevice));
-    // 3 result slots per internal node; the leaf region (front of the store) is preserved
-    const uint32_t stride = 3 * ni;
+    // 3 result slots per internal node (+ one per edge, + the trial leaf); the leaf region (front of the store) is preserved
     const size_t n_slots = (size_t)F->n_trees * F->n_chars * stride;
     DevBuf store;
-    if ((rc = pcgdo_ensure(ctx, store, F->leaf_bytes + n_slots * F->cap + 64))) return rc;
+    F->trial_off = F->leaf_bytes + n_slots * F->cap;
+    if ((rc = pcgdo_ensure(ctx, store, F->trial_off + (size_t)F->n_chars * F->cap + 64))) return rc;
+    if ((rc = pcgdo_ensure(ctx, F->trial_len, (size_t)F->n_chars * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, F->trial_delta, (size_t)F->n_trees * F->n_edges * 8))) return rc;
     CK(cudaMemcpy(store.p, F->store.p, F->leaf_bytes, cudaMemcpyDeviceToDevice));
     CK(cudaFree(F->store.p));
     F->store = store;
@@ -522,7 +586,8 @@ extern "C" int pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm,
         if ((rc = forest_run_items(ctx, tcm, F, st, lv.first, lv.second, 0, first, p))) return rc;
     for (const auto &lv : F->up_levels)
         if ((rc = forest_run_items(ctx, tcm, F, st, lv.first, lv.second, 0, first, p))) return rc;
-    if ((rc = forest_run_items(ctx, tcm, F, st, F->edge_items.first, F->edge_items.second, 1, first, p))) return rc;
+    if ((rc = forest_run_items(ctx, tcm, F, st, F->edge_items.first, F->edge_items.second, F->keep_edges ? 2 : 1, first, p)))
+        return rc;
     const uint64_t n_cols = (uint64_t)F->n_trees * F->n_chars;
     forest_edge_min_kernel<<<(uint32_t)((n_cols + 127) / 128), 128, 0, st>>>(
         f, (const int32_t *)F->roots.p, F->n_trees, F->n_edges, (int64_t *)F->edge_total.p, (int32_t *)F->edge_local.p,
@@ -534,6 +599,43 @@ extern "C" int pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm,
     ctx->last_launches += 2;
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
+    return forest_check(ctx, F, p, st);
+}
+
+// Wagner-build edge trials (app/pcg/PCG/Command/Build/Evaluate.hs:494-527, iterativeBuild.tryEdge): attaching a new leaf
+// to edge e costs  cost(DO(edge datum, leaf)) - cost(edge datum) - cost(leaf) = the LOCAL cost of that alignment; the
+// edge datum is the median of rooting the tree on e, kept by the re-rooting pass (keep_edge_data).  One cost-only
+// batch over all trees x edges x characters.  leaf strings: HOST, character c = elems[off[c] .. off[c]+len[c]).
+// delta_out: HOST int64[n_trees * n_edges], summed over this forest's characters.
+extern "C" int pcgdo_forest_try_leaf(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, const uint8_t *elems,
+                                     const uint64_t *off, const uint32_t *len, int64_t *delta_out, void *cuda_stream)
+{
+    if (!ctx || !tcm || !F || !elems || !off || !len || !delta_out) return PCGDO_ERR_ARG;
+    if (!F->reroot || !F->keep_edges) {
+        ctx->err = "edge trials need pcgdo_forest_enable_rerooting(..., keep_edge_data = 1) and a re-rooted sweep";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    std::vector<uint8_t> stage((size_t)F->n_chars * F->cap, 0);
+    for (uint32_t c = 0; c < F->n_chars; ++c) {
+        if (len[c] > F->cap) {
+            ctx->err = "forest: the trial leaf is longer than the node capacity";
+            return PCGDO_ERR_ARG;
+        }
+        std::copy(elems + off[c], elems + off[c] + len[c], stage.begin() + (size_t)c * F->cap);
+    }
+    CK(cudaMemcpyAsync((uint8_t *)F->store.p + F->trial_off, stage.data(), stage.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(F->trial_len.p, len, (size_t)F->n_chars * 4, cudaMemcpyHostToDevice, st));
+    ctx->last_launches = 0;
+    CK(cudaEventRecord(ctx->ev0, st));
+    bool first = true;
+    LinearParams p{};
+    int rc;
+    if ((rc = forest_run_items(ctx, tcm, F, st, F->trial_items.first, F->trial_items.second, 3, first, p))) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    CK(cudaMemcpyAsync(delta_out, F->trial_delta.p, (size_t)F->n_trees * F->n_edges * 8, cudaMemcpyDeviceToHost, st));
     return forest_check(ctx, F, p, st);
 }
 

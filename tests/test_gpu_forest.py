@@ -180,3 +180,48 @@ def test_forest_rerooting_on_reference_golden_tree(gpu_ctx):
     k = int(np.argmin(tot))
     assert (tot == 336).sum() == 1 and int(loc[k]) == 49 == g["nodes"][0]["local_cost"]
     f.close()
+
+
+def test_forest_wagner_edge_trials_match_oracle(oracle_mod, gpu_ctx):
+    """iterativeBuild.tryEdge on the device: cost increase of attaching a new taxon to every edge of every tree."""
+    import pcg_b200 as P
+    from pcg_b200.postorder import random_binary_trees
+    sig = tcm_matrix("1:2")
+    o = oracle_mod.Oracle(sig)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=600, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(sig)
+    n_trees, n_taxa, n_chars = 4, 10, 3
+    rng = np.random.default_rng(123)
+    children = random_binary_trees(n_trees, n_taxa, seed=5)
+    base = [random_string(rng, 60, amb=0.0) for _ in range(n_chars)]
+
+    def variant(c):
+        s = base[c].copy()
+        mut = rng.random(len(s)) < 0.3
+        s = np.where(mut, random_string(rng, len(s), amb=0.1), s).astype(np.uint8)
+        s = s[rng.random(len(s)) > 0.1]
+        s[s == 16] = 4
+        return s
+    leaves = [[variant(c) for c in range(n_chars)] for _ in range(n_taxa)]
+    new_leaf = [variant(c) for c in range(n_chars)]
+    f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=768)
+    f.enable_rerooting(keep_edge_data=True)
+    costs = f.score_rerooted(tcm)
+    delta = f.try_leaf(tcm, new_leaf)
+    assert delta.shape == (n_trees, 2 * n_taxa - 3)
+    for t in range(n_trees):
+        want_cost = 0
+        want_delta = np.zeros(2 * n_taxa - 3, np.int64)
+        order = None
+        for c in range(n_chars):
+            best, edges, ec, el, et = oracle_mod.reroot(o, children[t], [leaves[v][c] for v in range(n_taxa)], new_leaf[c])
+            uv, tot, loc = f.edges(t, c)
+            dev_pos = {tuple(sorted((int(a), int(b)))): k for k, (a, b) in enumerate(uv)}
+            for (a, b), x, tr in zip(edges, ec, et):
+                k = dev_pos[tuple(sorted((a, b)))]
+                assert int(tot[k]) == int(x)
+                want_delta[k] += int(tr)
+            want_cost += best
+        assert int(costs[t]) == want_cost
+        assert np.array_equal(delta[t], want_delta), t
+    f.close()
