@@ -234,6 +234,14 @@ int  pcgdo_forest_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *forest, int64_t *host
 int  pcgdo_forest_copy_tree_costs(pcgdo_ctx *ctx, pcgdo_forest *forest, void *dst_device, void *cuda_stream);
 int  pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *forest, uint32_t tree, uint32_t character, uint32_t node,
                            uint8_t *median_out, uint32_t *len_out, int32_t *local_cost, int64_t *total_cost);
+/* Large alphabets (a > 8): the same scheduler over 32-bit elements, every alignment by the Haskell dialects of
+ * pcgdo_metric_batch_* / pcgdo_explicit_batch_* (memo = NULL: discrete metric over `alphabet` symbols; dialect 2 =
+ * unboxedUkkonenFullSpaceDO, what selectDynamicMetric picks for a > 8).  score / score_rerooted / try_leaf /
+ * get_node take such a forest with tcm = NULL; strings are then uint32 elements (get_node, try_leaf: cast). */
+int  pcgdo_forest_create32(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
+                           const int32_t *children, const pcgdo_memo *memo, int alphabet, int dialect, pcgdo_forest **out);
+int  pcgdo_forest_set_leaves32(pcgdo_ctx *ctx, pcgdo_forest *forest, const uint32_t *elems, const uint64_t *off,
+                               const uint32_t *len);
 uint32_t pcgdo_forest_levels(const pcgdo_forest *forest);
 /* Re-rooting of dynamic characters (Bio/Graph/PhylogeneticDAG/DynamicCharacterRerooting.hs:70-420, trees only): after
  * the post-order, directed subtree data for every internal node (a pre-order sweep by depth) and one cost-only

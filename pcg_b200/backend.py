@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_forest_create", "pcgdo_forest_destroy", "pcgdo_forest_set_leaves", "pcgdo_forest_score",
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
-    "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges", "pcgdo_forest_try_leaf",
+    "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges", "pcgdo_forest_try_leaf", "pcgdo_forest_create32", "pcgdo_forest_set_leaves32",
     "pcgdo_memo_create", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
     "pcgdo_explicit_batch_device", "pcgdo_explicit_batch_host",
     "matrixInit", "matrixDestroy", "getCostAndMedian2D",
@@ -110,6 +110,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_forest_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                       C.POINTER(C.c_void_p)]
     L.pcgdo_forest_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_create32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.pcgdo_forest_set_leaves32.argtypes = [C.c_void_p] * 5
     L.pcgdo_forest_set_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pcgdo_forest_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pcgdo_forest_tree_cost_ptr.argtypes = [C.c_void_p]
@@ -276,27 +279,38 @@ class Forest:
     ``children``: int32 array (n_trees, n_taxa-1, 2) of child node ids (leaves 0..n_taxa-1, internal node x
     has id n_taxa + x).  ``leaves``: list over taxa of lists over characters of uint8 element strings."""
 
-    def __init__(self, ctx: Context, children, n_taxa: int, leaves, node_cap: int):
+    def __init__(self, ctx: Context, children, n_taxa: int, leaves, node_cap: int, metric=None, dialect: int = 2):
+        """``metric``: None = 8-bit elements under a dense TCM (passed to ``score``); an int = 32-bit elements under the
+        discrete metric over that many symbols; a ``Memo`` = 32-bit elements under its explicit matrix (large
+        alphabets: every alignment by Haskell dialect ``dialect``, default ``unboxedUkkonenFullSpaceDO``)."""
         self.ctx = ctx
+        self.metric = metric
+        self.dtype = np.uint8 if metric is None else np.uint32
         ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
         assert ch.ndim == 3 and ch.shape[1] == n_taxa - 1 and ch.shape[2] == 2
         self.n_trees, self.n_taxa = int(ch.shape[0]), int(n_taxa)
         self.n_chars = len(leaves[0])
         self.node_cap = (int(node_cap) + 3) & ~3
         h = C.c_void_p()
-        ctx.check(ctx.lib.pcgdo_forest_create(ctx.h, self.n_trees, self.n_taxa, self.n_chars, self.node_cap,
-                                              ch.ctypes.data, C.byref(h)), "pcgdo_forest_create")
+        if metric is None:
+            ctx.check(ctx.lib.pcgdo_forest_create(ctx.h, self.n_trees, self.n_taxa, self.n_chars, self.node_cap,
+                                                  ch.ctypes.data, C.byref(h)), "pcgdo_forest_create")
+        else:
+            memo_h, alpha = (None, int(metric)) if isinstance(metric, int) else (metric.h, metric.a)
+            ctx.check(ctx.lib.pcgdo_forest_create32(ctx.h, self.n_trees, self.n_taxa, self.n_chars, self.node_cap,
+                                                    ch.ctypes.data, memo_h, alpha, dialect, C.byref(h)),
+                      "pcgdo_forest_create32")
         self.h = h
-        flat = [np.asarray(s, np.uint8) for taxon in leaves for s in taxon]
+        flat = [np.asarray(s, self.dtype) for taxon in leaves for s in taxon]
         ln = np.array([len(s) for s in flat], np.uint32)
         off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
-        elems = np.concatenate(flat) if flat else np.zeros(0, np.uint8)
+        elems = np.concatenate(flat) if flat else np.zeros(0, self.dtype)
         elems = np.ascontiguousarray(elems)
-        ctx.check(ctx.lib.pcgdo_forest_set_leaves(ctx.h, self.h, elems.ctypes.data, off.ctypes.data, ln.ctypes.data),
-                  "pcgdo_forest_set_leaves")
+        fn = ctx.lib.pcgdo_forest_set_leaves if metric is None else ctx.lib.pcgdo_forest_set_leaves32
+        ctx.check(fn(ctx.h, self.h, elems.ctypes.data, off.ctypes.data, ln.ctypes.data), "pcgdo_forest_set_leaves")
 
     def score(self, tcm: Tcm, stream: int = 0) -> np.ndarray:
-        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h if tcm is not None else None, self.h, C.c_void_p(stream)),
                        "pcgdo_forest_score")
         out = np.zeros(self.n_trees, np.int64)
         self.ctx.check(self.ctx.lib.pcgdo_forest_tree_costs(self.ctx.h, self.h, out.ctypes.data),
@@ -305,13 +319,13 @@ class Forest:
 
     def score_async(self, tcm: Tcm, stream: int = 0) -> int:
         """Sweep only; returns the DEVICE pointer of the int64[n_trees] cost vector."""
-        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h if tcm is not None else None, self.h, C.c_void_p(stream)),
                        "pcgdo_forest_score")
         return int(self.ctx.lib.pcgdo_forest_tree_cost_ptr(self.h))
 
     def score_into(self, tcm: Tcm, dst_device_ptr: int, stream: int = 0) -> None:
         """Sweep on `stream`, then copy the int64[n_trees] costs into device memory at dst_device_ptr."""
-        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score(self.ctx.h, tcm.h if tcm is not None else None, self.h, C.c_void_p(stream)),
                        "pcgdo_forest_score")
         self.ctx.check(self.ctx.lib.pcgdo_forest_copy_tree_costs(self.ctx.h, self.h, C.c_void_p(dst_device_ptr),
                                                                  C.c_void_p(stream)), "pcgdo_forest_copy_tree_costs")
@@ -324,20 +338,20 @@ class Forest:
         """Wagner edge trial (``iterativeBuild.tryEdge``): cost increase of attaching a new taxon (one element string
         per character) to every edge of every tree -> int64 (n_trees, n_edges).  Needs a re-rooted sweep with
         ``enable_rerooting(keep_edge_data=True)``."""
-        flat = [np.asarray(x, np.uint8) for x in leaf_strings]
+        flat = [np.asarray(x, self.dtype) for x in leaf_strings]
         ln = np.array([len(x) for x in flat], np.uint32)
         off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
-        elems = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1, np.uint8)
+        elems = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1, self.dtype)
         ne = int(self.ctx.lib.pcgdo_forest_edges(self.h))
         out = np.zeros((self.n_trees, ne), np.int64)
-        self.ctx.check(self.ctx.lib.pcgdo_forest_try_leaf(self.ctx.h, tcm.h, self.h, elems.ctypes.data, off.ctypes.data,
+        self.ctx.check(self.ctx.lib.pcgdo_forest_try_leaf(self.ctx.h, tcm.h if tcm is not None else None, self.h, elems.ctypes.data, off.ctypes.data,
                                                           ln.ctypes.data, out.ctypes.data, C.c_void_p(stream)),
                        "pcgdo_forest_try_leaf")
         return out
 
     def score_rerooted(self, tcm: Tcm, stream: int = 0) -> np.ndarray:
         """Post-order + re-rooting: per-tree sum over characters of the cheapest root edge."""
-        self.ctx.check(self.ctx.lib.pcgdo_forest_score_rerooted(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score_rerooted(self.ctx.h, tcm.h if tcm is not None else None, self.h, C.c_void_p(stream)),
                        "pcgdo_forest_score_rerooted")
         out = np.zeros(self.n_trees, np.int64)
         self.ctx.check(self.ctx.lib.pcgdo_forest_tree_costs(self.ctx.h, self.h, out.ctypes.data),
@@ -345,7 +359,7 @@ class Forest:
         return out
 
     def score_rerooted_into(self, tcm: Tcm, dst_device_ptr: int, stream: int = 0) -> None:
-        self.ctx.check(self.ctx.lib.pcgdo_forest_score_rerooted(self.ctx.h, tcm.h, self.h, C.c_void_p(stream)),
+        self.ctx.check(self.ctx.lib.pcgdo_forest_score_rerooted(self.ctx.h, tcm.h if tcm is not None else None, self.h, C.c_void_p(stream)),
                        "pcgdo_forest_score_rerooted")
         self.ctx.check(self.ctx.lib.pcgdo_forest_copy_tree_costs(self.ctx.h, self.h, C.c_void_p(dst_device_ptr),
                                                                  C.c_void_p(stream)), "pcgdo_forest_copy_tree_costs")
@@ -359,7 +373,7 @@ class Forest:
         return uv, tot, loc
 
     def node(self, tree: int, character: int, node: int):
-        buf = np.zeros(self.node_cap, np.uint8)
+        buf = np.zeros(self.node_cap, self.dtype)
         n, lc, tc = C.c_uint32(0), C.c_int32(0), C.c_int64(0)
         self.ctx.check(self.ctx.lib.pcgdo_forest_get_node(self.ctx.h, self.h, tree, character, node, buf.ctypes.data,
                                                           C.byref(n), C.byref(lc), C.byref(tc)),

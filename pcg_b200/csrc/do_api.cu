@@ -819,6 +819,68 @@ extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *mem
 }
 
 // memo == NULL: the discrete metric over `alphabet` symbols through the same per-pair table machinery
+// Enqueue the per-pair table kernel for one batch described on the device (the forest scheduler's levels): no
+// synchronisation, failure counters accumulate in counters[8..10] unless reset_overflow.
+int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const MetricBatchDev &bd,
+                        cudaStream_t st, bool reset_overflow, unsigned int **counters_out)
+{
+    const int a = memo ? (int)memo->a : alphabet;
+    if (a < 2 || a > 32 || dialect < 0 || dialect > 2) {
+        ctx->err = "table path: alphabet size must be 2..32, dialect 0..2";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    const uint32_t seq_cap = metric_seq_cap(ctx->max_len);
+    const uint32_t tab_entries = 1024;
+    const size_t sg_bytes = ((size_t)a * a * 4 + 15) & ~(size_t)15;
+    const size_t per_warp = 512 + (size_t)seq_cap + 2 * (size_t)tab_entries;
+    int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    while (warps > 1 && sg_bytes + (size_t)warps * per_warp > 227 * 1024) --warps;
+    const size_t smem = sg_bytes + (size_t)warps * per_warp;
+    if (smem > 227 * 1024) {
+        ctx->err = "max_len too large for the explicit-matrix kernel's staging window";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    size_t arena_words = ctx->arena_words;
+    if (!arena_words) {
+        const size_t per = metric_words_for((uint32_t)ctx->max_len, (uint32_t)ctx->max_len);
+        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 4096);
+    }
+    arena_words = (arena_words + 3) & ~(size_t)3;
+    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
+    size_t ts_words = (explicit_scratch_words(ctx->max_len, a, (size_t)1 << 20) + 3) & ~(size_t)3;
+    const int grid = ctx->sm_count;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->tscratch, (size_t)grid * warps * ts_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 16, st));
+    ExplicitParams p{};
+    p.b = bd;
+    p.a = a;
+    p.dialect = dialect;
+    p.kind = memo ? 2 : 0;
+    p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
+    p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
+    p.delta = memo ? memo->delta : 1u;
+    p.k_64k = 65536u;
+    p.arena = (uint32_t *)ctx->arena.p;
+    p.arena_words = (uint32_t)arena_words;
+    p.tscratch = (uint32_t *)ctx->tscratch.p;
+    p.tscratch_words = (uint32_t)ts_words;
+    p.seq_cap = seq_cap;
+    p.smem_tab_entries = tab_entries;
+    p.pairs_per_warp = ctx->pairs_per_warp;
+    p.counter = (unsigned int *)ctx->counters.p;
+    p.overflow_count = p.counter + 8;
+    p.k_four = 4u;
+    p.k_minus1 = 0xffffffffu;
+    p.k_one = 1u;
+    CK(launch_explicit(p, grid, warps * 32, smem, st));
+    ctx->last_launches += 1;
+    if (counters_out) *counters_out = p.counter;
+    return PCGDO_OK;
+}
+
 static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const pcgdo_batch32 *b,
                               void *cuda_stream)
 {

@@ -58,3 +58,9 @@ int pcgdo_ensure(pcgdo_ctx *ctx, DevBuf &b, size_t bytes);
 // *out_p receives the parameters used (for the caller's overflow handling).
 int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo::BatchDev &bd, cudaStream_t st,
                          bool reset_overflow, pcgdo::LinearParams *out_p, bool *wide_ok_out);
+
+// Large alphabets (do_explicit.cu): enqueue the per-pair table kernel for a batch described on the device.
+struct pcgdo_memo;
+namespace pcgdo { struct MetricBatchDev; }
+int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const pcgdo::MetricBatchDev &bd,
+                        cudaStream_t st, bool reset_overflow, unsigned int **counters_out);

@@ -325,11 +325,11 @@ __device__ __forceinline__ uint32_t x_dispatch16(int B, const MGeom &g, uint32_t
     }
 }
 
-__device__ __forceinline__ void x_emit(const uint32_t *sg, int a, int kind, const uint32_t *pL, const uint32_t *pS, uint32_t gap,
-                                       uint32_t mask, const uint32_t *ops, uint32_t nal, bool swapped, uint32_t *om,
-                                       uint32_t *o1, uint32_t *o2, int lane)
+__device__ __forceinline__ uint32_t x_emit(const uint32_t *sg, int a, int kind, const uint32_t *pL, const uint32_t *pS, uint32_t gap,
+                                           uint32_t mask, const uint32_t *ops, uint32_t nal, bool swapped, uint32_t *om,
+                                           uint32_t *o1, uint32_t *o2, int lane, uint32_t *ou = nullptr, uint32_t ucap = 0)
 {
-    uint32_t base_i = 0, base_j = 0;
+    uint32_t base_i = 0, base_j = 0, base_u = 0;
     for (uint32_t c0 = 0; c0 < nal; c0 += 32) {
         const uint32_t c = c0 + lane;
         uint32_t code = 3u;
@@ -340,6 +340,8 @@ __device__ __forceinline__ void x_emit(const uint32_t *sg, int a, int kind, cons
         const unsigned bl = __ballot_sync(kFullM, code < 2u), bs = __ballot_sync(kFullM, code == 0u || code == 2u);
         const unsigned lt = (1u << lane) - 1u;
         const uint32_t il = base_i + __popc(bl & lt), js = base_j + __popc(bs & lt);
+        bool keep = false;
+        uint32_t mdv = 0;
         if (c < nal) {
             const uint32_t y = code < 2u ? (__ldg(pL + il) & mask) : 0u;
             const uint32_t x = (code == 0u || code == 2u) ? (__ldg(pS + js) & mask) : 0u;
@@ -350,10 +352,19 @@ __device__ __forceinline__ void x_emit(const uint32_t *sg, int a, int kind, cons
             if (om) om[c] = md;
             if (o1) o1[c] = swapped ? y : x;
             if (o2) o2[c] = swapped ? x : y;
+            keep = md != gap;
+            mdv = md;
+        }
+        if (ou) {       // deleteGaps on the medians: what the parent's alignment consumes
+            const unsigned bk = __ballot_sync(kFullM, keep);
+            const uint32_t pos = base_u + __popc(bk & lt);
+            if (keep && pos < ucap) ou[pos] = mdv;
+            base_u += __popc(bk);
         }
         base_i += __popc(bl);
         base_j += __popc(bs);
     }
+    return base_u;
 }
 
 // fewer fill variants = smaller instruction footprint when every warp walks through the doubling schedule
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
     uint32_t *ts = p.tscratch + warp_global * (size_t)p.tscratch_words;
-    const bool want_out = b.out_med || b.out_a1 || b.out_a2 || b.out_len;
+    const bool want_out = b.out_med || b.out_a1 || b.out_a2 || b.out_len || b.out_ungapped;
     // optional multi-pass mode (PCGDO_EXPLICIT_MULTI_PASS): one Ukkonen offset per launch, pairs whose band must
     // double are queued for the next launch so that all warps run the same fill variant at the same time
     const uint32_t n_work = p.in_count ? *p.in_count : b.n_pairs;
@@ -717,7 +728,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 if (b.out_len) b.out_len[k] = na;
             }
             __syncwarp();
-            if (b.out_med || b.out_a1 || b.out_a2) {
+            if (b.out_med || b.out_a1 || b.out_a2 || b.out_ungapped) {
                 for (int pe = start; pe < pi; ++pe) {
                     if (!(s_flags[pe] & 2u)) continue;
                     const uint32_t k = p.in_list ? p.in_list[base + pe] : base + pe;
@@ -727,10 +738,15 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pe] & 0xffffu), (int)(int16_t)(s_geo[pe] >> 16));
                     const int B = x_choose_b(g.wb, p.skip_b);
                     const uint32_t *ops = arena + s_off[pe] + m_dir_words(g, B);
-                    const uint64_t oo = b.out_off[k];
-                    x_emit(sg, a, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe], swapped,
-                           b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
-                           b.out_a2 ? b.out_a2 + oo : nullptr, lane);
+                    const uint64_t oo = b.out_off ? b.out_off[k] : 0;
+                    const uint32_t nu = x_emit(sg, a, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe],
+                                               swapped, b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
+                                               b.out_a2 ? b.out_a2 + oo : nullptr, lane,
+                                               b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+                    if (b.out_ungapped && lane == 0) {
+                        b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
+                        if (nu > b.ucap) atomicAdd(p.overflow_count + 2, 1u);   // node string does not fit its slot
+                    }
                 }
             }
             __syncwarp();

@@ -24,6 +24,7 @@
 // (q, child), "q entered from child" with the child's post-order datum (:176-199); per character the minimum over
 // the 2n-3 edges (the root edge keeps the post-order root) is the re-rooted cost (:345-420).
 #include "do_ctx.h"
+#include "do_metric.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -44,11 +45,14 @@ struct pcgdo_forest {
     std::vector<std::pair<size_t, size_t>> up_levels;         // pre-order levels (by depth) of directed-datum jobs
     std::pair<size_t, size_t> edge_items{0, 0};
     DevBuf edge_total, edge_local, char_min;                  // i64 / i32 [n_trees*n_chars*n_edges], i64 [n_trees*n_chars]
+    uint32_t elem_bytes = 1;             // 1: dense-TCM alphabets (do_linear.cu); 4: large alphabets (do_explicit.cu)
+    const pcgdo_memo *memo = nullptr;    // elem_bytes 4: explicit matrix, or NULL = discrete metric over `alphabet` symbols
+    int alphabet = 0, dialect = 2;
     bool keep_edges = false;             // edge data (median of rooting on each edge) kept for Wagner edge trials
     size_t trial_off = 0;                // byte offset of the trial leaf's slots in `store`
     DevBuf trial_len, trial_delta;       // u32 [n_chars], i64 [n_trees * n_edges]
     std::pair<size_t, size_t> trial_items{0, 0};
-    size_t leaf_bytes = 0;
+    size_t leaf_bytes = 0;               // leaf region of `store`, in ELEMENTS (as every offset below)
     DevBuf store;        // [leaf slots | internal-node slots], cap bytes each
     DevBuf leaf_len;     // u32 [n_taxa * n_chars]
     DevBuf node_len;     // u32 [n_trees * n_chars * n_internal]
@@ -218,12 +222,37 @@ ForestDev dev_view(const pcgdo_forest *F)
 
 }  // namespace
 
+static int forest_create_impl(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
+                              const int32_t *children, uint32_t elem_bytes, pcgdo_forest **out);
+
 extern "C" int pcgdo_forest_create(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars,
                                    uint32_t node_cap, const int32_t *children, pcgdo_forest **out)
+{
+    return forest_create_impl(ctx, n_trees, n_taxa, n_chars, node_cap, children, 1, out);
+}
+
+// Large alphabets: 32-bit elements, aligned by the Haskell dialects of do_explicit.cu.  memo = NULL selects the
+// discrete metric over `alphabet` symbols; dialect as pcgdo_metric_batch_* (2 = unboxedUkkonenFullSpaceDO).
+extern "C" int pcgdo_forest_create32(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars,
+                                     uint32_t node_cap, const int32_t *children, const pcgdo_memo *memo, int alphabet,
+                                     int dialect, pcgdo_forest **out)
+{
+    if (dialect < 0 || dialect > 2 || (!memo && (alphabet < 2 || alphabet > 32))) return PCGDO_ERR_ARG;
+    int rc = forest_create_impl(ctx, n_trees, n_taxa, n_chars, node_cap, children, 4, out);
+    if (rc) return rc;
+    (*out)->memo = memo;
+    (*out)->alphabet = alphabet;
+    (*out)->dialect = dialect;
+    return PCGDO_OK;
+}
+
+static int forest_create_impl(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
+                              const int32_t *children, uint32_t elem_bytes, pcgdo_forest **out)
 {
     if (!ctx || !children || !out || n_trees == 0 || n_taxa < 2 || n_chars == 0 || node_cap < 4) return PCGDO_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     pcgdo_forest *F = new pcgdo_forest();
+    F->elem_bytes = elem_bytes;
     F->n_trees = n_trees; F->n_taxa = n_taxa; F->n_chars = n_chars;
     F->cap = (node_cap + 3u) & ~3u;
     F->n_internal = n_taxa - 1;
@@ -290,7 +319,7 @@ extern "C" int pcgdo_forest_create(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_
     const size_t n_slots = (size_t)n_trees * n_chars * ni;
     int rc;
     auto fail = [&](int r) { delete F; return r; };
-    if ((rc = pcgdo_ensure(ctx, F->store, F->leaf_bytes + n_slots * F->cap + 64))) return fail(rc);
+    if ((rc = pcgdo_ensure(ctx, F->store, (F->leaf_bytes + n_slots * F->cap + 64) * F->elem_bytes))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->leaf_len, (size_t)n_taxa * n_chars * 4))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->node_len, n_slots * 4))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->node_local, n_slots * 4))) return fail(rc);
@@ -324,23 +353,40 @@ extern "C" void pcgdo_forest_destroy(pcgdo_ctx *ctx, pcgdo_forest *F)
 
 // Leaf strings (host): character c of taxon v = elems[off[v*n_chars+c] .. +len[...]) — one byte per element,
 // already free of gap elements (leaves are ungapped sequences).
-extern "C" int pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *F, const uint8_t *elems, const uint64_t *off,
-                                       const uint32_t *len)
+static int forest_set_leaves_impl(pcgdo_ctx *ctx, pcgdo_forest *F, const void *elems, const uint64_t *off, const uint32_t *len,
+                                  uint32_t elem_bytes)
 {
     if (!ctx || !F || !elems || !off || !len) return PCGDO_ERR_ARG;
+    if (F->elem_bytes != elem_bytes) {
+        ctx->err = "forest: element width of the leaves does not match the forest";
+        return PCGDO_ERR_ARG;
+    }
     CK(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)F->n_taxa * F->n_chars;
-    std::vector<uint8_t> stage(n * F->cap, 0);
+    const size_t n = (size_t)F->n_taxa * F->n_chars, eb = elem_bytes;
+    std::vector<uint8_t> stage(n * F->cap * eb, 0);
     for (size_t i = 0; i < n; ++i) {
         if (len[i] > F->cap) {
             ctx->err = "forest: a leaf string is longer than the node capacity";
             return PCGDO_ERR_ARG;
         }
-        std::copy(elems + off[i], elems + off[i] + len[i], stage.begin() + i * F->cap);
+        const uint8_t *src = (const uint8_t *)elems + off[i] * eb;
+        std::copy(src, src + (size_t)len[i] * eb, stage.begin() + i * F->cap * eb);
     }
     CK(cudaMemcpy(F->store.p, stage.data(), stage.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(F->leaf_len.p, len, n * 4, cudaMemcpyHostToDevice));
     return PCGDO_OK;
+}
+
+extern "C" int pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *F, const uint8_t *elems, const uint64_t *off,
+                                       const uint32_t *len)
+{
+    return forest_set_leaves_impl(ctx, F, elems, off, len, 1);
+}
+
+extern "C" int pcgdo_forest_set_leaves32(pcgdo_ctx *ctx, pcgdo_forest *F, const uint32_t *elems, const uint64_t *off,
+                                         const uint32_t *len)
+{
+    return forest_set_leaves_impl(ctx, F, elems, off, len, 4);
 }
 
 // Enqueue one batch of forest jobs: mode 0 = data (ungapped median of the result kept in its slot, totals
@@ -359,19 +405,42 @@ static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *
                                                    (uint64_t *)F->buoff.p, (uint32_t *)F->blen1.p,
                                                    (uint32_t *)F->blen2.p);
         CK(cudaGetLastError());
-        BatchDev bd{};
-        bd.n_pairs = (uint32_t)n_pairs;
-        bd.elems = (const uint8_t *)F->store.p;
-        bd.off1 = (const uint64_t *)F->boff1.p; bd.off2 = (const uint64_t *)F->boff2.p;
-        bd.len1 = (const uint32_t *)F->blen1.p; bd.len2 = (const uint32_t *)F->blen2.p;
-        bd.cost = (int32_t *)F->bcost.p;
-        if (mode == 0 || mode == 2) {
-            bd.out_ungapped = (uint8_t *)F->store.p;
-            bd.out_uoff = (const uint64_t *)F->buoff.p;
-            bd.out_ulen = (uint32_t *)F->bulen.p;
-            bd.ucap = F->cap;
+        int rc;
+        if (F->elem_bytes == 4) {
+            MetricBatchDev md{};
+            md.n_pairs = (uint32_t)n_pairs;
+            md.elems = (const uint32_t *)F->store.p;
+            md.off1 = (const uint64_t *)F->boff1.p; md.off2 = (const uint64_t *)F->boff2.p;
+            md.len1 = (const uint32_t *)F->blen1.p; md.len2 = (const uint32_t *)F->blen2.p;
+            md.cost = (int32_t *)F->bcost.p;
+            if (mode == 0 || mode == 2) {
+                md.out_ungapped = (uint32_t *)F->store.p;
+                md.out_uoff = (const uint64_t *)F->buoff.p;
+                md.out_ulen = (uint32_t *)F->bulen.p;
+                md.ucap = F->cap;
+            }
+            unsigned int *cnt = nullptr;
+            rc = pcgdo_enqueue_table(ctx, F->memo, F->alphabet, F->dialect, md, st, first, &cnt);
+            p.counter = cnt;
+        } else {
+            BatchDev bd{};
+            bd.n_pairs = (uint32_t)n_pairs;
+            bd.elems = (const uint8_t *)F->store.p;
+            bd.off1 = (const uint64_t *)F->boff1.p; bd.off2 = (const uint64_t *)F->boff2.p;
+            bd.len1 = (const uint32_t *)F->blen1.p; bd.len2 = (const uint32_t *)F->blen2.p;
+            bd.cost = (int32_t *)F->bcost.p;
+            if (mode == 0 || mode == 2) {
+                bd.out_ungapped = (uint8_t *)F->store.p;
+                bd.out_uoff = (const uint64_t *)F->buoff.p;
+                bd.out_ulen = (uint32_t *)F->bulen.p;
+                bd.ucap = F->cap;
+            }
+            if (!tcm) {
+                ctx->err = "forest: a dense TCM is required for 8-bit forests";
+                return PCGDO_ERR_ARG;
+            }
+            rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, first, &p, nullptr);
         }
-        int rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, first, &p, nullptr);
         if (rc) return rc;
         first = false;
         if (mode == 0)
@@ -398,9 +467,13 @@ static int forest_check(pcgdo_ctx *ctx, pcgdo_forest *F, const LinearParams &p, 
 {
     // one look at the failure counters for the whole sweep: pairs beyond the warp kernels' limits, wide pairs
     // with the wide kernel disabled, node strings beyond their slot
-    unsigned int h[10] = {0};
+    unsigned int h[11] = {0};
     CK(cudaMemcpyAsync(h, p.counter, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (F->elem_bytes == 4) {           // table kernel: [8] pairs beyond its limits, [10] node strings beyond their slot
+        h[9] = h[10];
+        h[3] = 0;
+    }
     if (h[8] || h[9] || (ctx->max_b <= 8 && h[3])) {
         char msg[200];
         snprintf(msg, sizeof msg,
@@ -415,7 +488,7 @@ static int forest_check(pcgdo_ctx *ctx, pcgdo_forest *F, const LinearParams &p, 
 // One post-order sweep over all trees and this forest's characters; per-tree cost = sum of the root totals.
 extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, void *cuda_stream)
 {
-    if (!ctx || !tcm || !F) return PCGDO_ERR_ARG;
+    if (!ctx || !F || (!tcm && F->elem_bytes == 1)) return PCGDO_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const ForestDev f = dev_view(F);
@@ -541,10 +614,10 @@ extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, in
     const size_t n_slots = (size_t)F->n_trees * F->n_chars * stride;
     DevBuf store;
     F->trial_off = F->leaf_bytes + n_slots * F->cap;
-    if ((rc = pcgdo_ensure(ctx, store, F->trial_off + (size_t)F->n_chars * F->cap + 64))) return rc;
+    if ((rc = pcgdo_ensure(ctx, store, (F->trial_off + (size_t)F->n_chars * F->cap + 64) * F->elem_bytes))) return rc;
     if ((rc = pcgdo_ensure(ctx, F->trial_len, (size_t)F->n_chars * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, F->trial_delta, (size_t)F->n_trees * F->n_edges * 8))) return rc;
-    CK(cudaMemcpy(store.p, F->store.p, F->leaf_bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(store.p, F->store.p, F->leaf_bytes * F->elem_bytes, cudaMemcpyDeviceToDevice));
     CK(cudaFree(F->store.p));
     F->store = store;
     if ((rc = pcgdo_ensure(ctx, F->node_len, n_slots * 4)) || (rc = pcgdo_ensure(ctx, F->node_local, n_slots * 4)) ||
@@ -569,7 +642,7 @@ extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, in
 // over the tree's unrooted edges (every dynamic character picks its own best root edge).
 extern "C" int pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, void *cuda_stream)
 {
-    if (!ctx || !tcm || !F) return PCGDO_ERR_ARG;
+    if (!ctx || !F || (!tcm && F->elem_bytes == 1)) return PCGDO_ERR_ARG;
     if (!F->reroot) {
         ctx->err = "call pcgdo_forest_enable_rerooting first";
         return PCGDO_ERR_ARG;
@@ -610,22 +683,24 @@ extern "C" int pcgdo_forest_score_rerooted(pcgdo_ctx *ctx, const pcgdo_tcm *tcm,
 extern "C" int pcgdo_forest_try_leaf(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *F, const uint8_t *elems,
                                      const uint64_t *off, const uint32_t *len, int64_t *delta_out, void *cuda_stream)
 {
-    if (!ctx || !tcm || !F || !elems || !off || !len || !delta_out) return PCGDO_ERR_ARG;
+    // (elements of `elems` are F's element width: bytes, or 32-bit words for a forest made by pcgdo_forest_create32)
+    if (!ctx || !F || (!tcm && F->elem_bytes == 1) || !elems || !off || !len || !delta_out) return PCGDO_ERR_ARG;
     if (!F->reroot || !F->keep_edges) {
         ctx->err = "edge trials need pcgdo_forest_enable_rerooting(..., keep_edge_data = 1) and a re-rooted sweep";
         return PCGDO_ERR_ARG;
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    std::vector<uint8_t> stage((size_t)F->n_chars * F->cap, 0);
+    const size_t eb = F->elem_bytes;
+    std::vector<uint8_t> stage((size_t)F->n_chars * F->cap * eb, 0);
     for (uint32_t c = 0; c < F->n_chars; ++c) {
         if (len[c] > F->cap) {
             ctx->err = "forest: the trial leaf is longer than the node capacity";
             return PCGDO_ERR_ARG;
         }
-        std::copy(elems + off[c], elems + off[c] + len[c], stage.begin() + (size_t)c * F->cap);
+        std::copy(elems + off[c] * eb, elems + (off[c] + len[c]) * eb, stage.begin() + (size_t)c * F->cap * eb);
     }
-    CK(cudaMemcpyAsync((uint8_t *)F->store.p + F->trial_off, stage.data(), stage.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy((uint8_t *)F->store.p + F->trial_off * eb, stage.data(), stage.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpyAsync(F->trial_len.p, len, (size_t)F->n_chars * 4, cudaMemcpyHostToDevice, st));
     ctx->last_launches = 0;
     CK(cudaEventRecord(ctx->ev0, st));
@@ -690,8 +765,9 @@ extern "C" int pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *F, uint32_t t
     if (len_out) *len_out = len;
     if (local_cost) CK(cudaMemcpy(local_cost, (int32_t *)F->node_local.p + me, 4, cudaMemcpyDeviceToHost));
     if (total_cost) CK(cudaMemcpy(total_cost, (int64_t *)F->node_total.p + me, 8, cudaMemcpyDeviceToHost));
-    if (median_out && len)
-        CK(cudaMemcpy(median_out, (uint8_t *)F->store.p + F->leaf_bytes + me * F->cap, len, cudaMemcpyDeviceToHost));
+    if (median_out && len)      // (len elements of F's element width)
+        CK(cudaMemcpy(median_out, (uint8_t *)F->store.p + (F->leaf_bytes + me * F->cap) * F->elem_bytes,
+                      (size_t)len * F->elem_bytes, cudaMemcpyDeviceToHost));
     return PCGDO_OK;
 }
 

@@ -18,6 +18,12 @@ struct MetricBatchDev {
     int32_t        *cost;
     uint64_t       *cells;
     int32_t        *final_offset;     // may be NULL
+    // post-order mode (do_explicit.cu only): the median with its gap elements dropped, at element offset
+    // out_uoff[k], at most ucap elements, length to out_ulen
+    uint32_t       *out_ungapped;
+    const uint64_t *out_uoff;
+    uint32_t       *out_ulen;
+    uint32_t        ucap;
 };
 
 struct MetricParams {

@@ -225,3 +225,64 @@ def test_forest_wagner_edge_trials_match_oracle(oracle_mod, gpu_ctx):
         assert int(costs[t]) == want_cost
         assert np.array_equal(delta[t], want_delta), t
     f.close()
+
+
+@pytest.mark.parametrize("kind", ["discrete", "explicit"])
+def test_forest_large_alphabet_postorder(oracle_mod, gpu_ctx, kind):
+    """Post-order over 21-symbol characters (32-bit elements, unboxedUkkonenFullSpaceDO at every node) against a
+    host-side post-order that calls the restated dialect pair by pair."""
+    import pcg_b200 as P
+    from pcg_b200.postorder import random_binary_trees
+    from tests.test_gpu_metric import _rand_str
+    a, gap = 21, 1 << 20
+    rng = np.random.default_rng(2024)
+    sigma = None
+    if kind == "explicit":
+        sigma = 2 * (1 - np.eye(a, dtype=np.uint32))
+        sigma[-1, :-1] = 1
+        sigma[:-1, -1] = 1
+        sigma = sigma.astype(np.uint32)
+    n_trees, n_taxa, n_chars = 3, 9, 2
+    children = random_binary_trees(n_trees, n_taxa, seed=8)
+    base = [_rand_str(rng, 70, a, amb=0.0, gapful=0.0) for _ in range(n_chars)]
+
+    def variant(c):
+        s = base[c].copy()
+        mut = rng.random(len(s)) < 0.2
+        s = np.where(mut, _rand_str(rng, len(s), a, amb=0.1, gapful=0.0), s).astype(np.uint32)
+        return s[rng.random(len(s)) > 0.08]
+    leaves = [[variant(c) for c in range(n_chars)] for _ in range(n_taxa)]
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=300, max_b=32, arena_words=0)
+    metric = a if sigma is None else gpu_ctx.memo(sigma)
+    f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=256, metric=metric, dialect=2)
+    costs = f.score(None)
+    for t in range(n_trees):
+        tree_cost = 0
+        for c in range(n_chars):
+            res = {v: (leaves[v][c], 0) for v in range(n_taxa)}
+            pending = {n_taxa + x: tuple(int(z) for z in children[t][x]) for x in range(n_taxa - 1)}
+            while pending:
+                for n in [n for n, (l, r) in pending.items() if l in res and r in res]:
+                    l, r = pending.pop(n)
+                    cost, med, _, _, _, _ = oracle_mod.haskell_do(2, a, res[l][0], res[r][0], sigma=sigma)
+                    res[n] = (med[med != gap], cost + res[l][1] + res[r][1])
+                    got_med, got_local, got_total = f.node(t, c, n)
+                    assert got_local == cost and got_total == res[n][1], (t, c, n)
+                    assert np.array_equal(got_med, res[n][0]), (t, c, n)
+            is_child = set(int(z) for z in children[t].reshape(-1))
+            root = [n_taxa + x for x in range(n_taxa - 1) if n_taxa + x not in is_child][0]
+            tree_cost += res[root][1]
+        assert int(costs[t]) == tree_cost
+    # re-rooting and edge trials run on the same scheduler: structural checks (the pass itself is pinned on DNA)
+    f.enable_rerooting(keep_edge_data=True)
+    rer = f.score_rerooted(None)
+    assert (rer <= costs).all()
+    for t in range(n_trees):
+        for c in range(n_chars):
+            uv, tot, loc = f.edges(t, c)
+            is_child = set(int(z) for z in children[t].reshape(-1))
+            root = [n_taxa + x for x in range(n_taxa - 1) if n_taxa + x not in is_child][0]
+            assert int(tot[0]) == f.node(t, c, root)[2]
+    delta = f.try_leaf(None, [variant(c) for c in range(n_chars)])
+    assert delta.shape == (n_trees, 2 * n_taxa - 3) and (delta >= 0).all()
+    f.close()
