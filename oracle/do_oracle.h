@@ -107,6 +107,11 @@ int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_
                             int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells,
                             const uint32_t *trial, size_t trial_len, int64_t *edge_trial);
 
+/* re-rooting with every alignment by a Haskell dialect (alphabets > 8) */
+int64_t oracle_reroot_haskell(int dialect, int metric_kind, const uint32_t *sigma, int a, uint32_t n_taxa,
+                              const int32_t *children, const uint32_t *const *leaf, const size_t *leaf_len,
+                              int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local);
+
 /* the same with every overlap answered by `lookup` (returns the cost, writes the median) */
 typedef uint64_t (*oracle_lookup_fn)(void *ctx, uint32_t x, uint32_t y, uint32_t *med);
 int64_t oracle_haskell_do_lookup(int dialect, oracle_lookup_fn lookup, void *lookup_ctx, int a,

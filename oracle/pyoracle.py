@@ -171,6 +171,28 @@ def reroot(oracle: "Oracle", children, leaves, trial=None):
     return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el, et
 
 
+def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None):
+    """Re-rooting pass with every alignment by a restated Haskell dialect (alphabets > 8).
+    Returns (min cost, edges, edge_cost, edge_local)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.oracle_reroot_haskell.restype = C.c_int64
+    lib.oracle_reroot_haskell.argtypes = [C.c_int, C.c_int, _u32p, C.c_int, C.c_uint32] + [C.c_void_p] * 7
+    ch = np.ascontiguousarray(np.asarray(children, np.int32))
+    n_taxa = ch.shape[0] + 1
+    arrs = [_as_u32(x) for x in leaves]
+    ptrs = (C.c_void_p * n_taxa)(*[x.ctypes.data for x in arrs])
+    lens = (C.c_size_t * n_taxa)(*[len(x) for x in arrs])
+    ne = 2 * n_taxa - 3
+    eu, ev = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
+    ec, el = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
+    sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
+    best = lib.oracle_reroot_haskell(dialect, 0 if sigma is None else 1, _ptr(sg), a, n_taxa, ch.ctypes.data, ptrs, lens,
+                                     eu.ctypes.data, ev.ctypes.data, ec.ctypes.data, el.ctypes.data)
+    return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el
+
+
 def haskell_do(dialect: int, a: int, in1, in2, sigma=None):
     """S1 / S2 Haskell dialects on median strings (see do_oracle.c). sigma=None -> discrete metric.
     Returns (cost, median, aligned1, aligned2, cells, final_offset)."""

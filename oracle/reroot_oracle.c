@@ -27,7 +27,10 @@
 typedef struct { uint32_t *s; size_t n; int64_t total; int64_t local; int done; } datum_t;
 
 typedef struct {
-    const oracle_tcm_t *t;
+    const oracle_tcm_t *t;            /* dense C-linear aligner (NULL: the Haskell dialect below) */
+    int hs_dialect, hs_kind, hs_a;    /* oracle_haskell_do parameters for large alphabets */
+    const uint32_t *hs_sigma;
+    uint32_t gap;
     uint32_t n_taxa, n_nodes, root;
     const int32_t *children;          /* [(n_taxa-1)*2], internal node x has id n_taxa + x */
     int32_t *parent;                  /* original parent, -1 for the root */
@@ -43,12 +46,15 @@ static void apply(rr_t *R, const datum_t *l, const datum_t *r, datum_t *out)
     uint32_t *g = malloc(sizeof(uint32_t) * 3 * cap);
     size_t nal = 0;
     uint64_t c = 0;
-    const int64_t cost = oracle_align2d(R->t, l->s, l->n, r->s, r->n, g, g + cap, g + 2 * cap, &nal, &c);
+    int fo = 0;
+    const int64_t cost = R->t ? oracle_align2d(R->t, l->s, l->n, r->s, r->n, g, g + cap, g + 2 * cap, &nal, &c)
+                              : oracle_haskell_do(R->hs_dialect, R->hs_kind, R->hs_sigma, R->hs_a, l->s, l->n, r->s, r->n,
+                                                  g, g + cap, g + 2 * cap, &nal, &c, &fo);
     R->cells += c;
     out->s = malloc(sizeof(uint32_t) * (nal + 1));
     out->n = 0;
     for (size_t k = 0; k < nal; k++)
-        if (g[k] != R->t->gap) out->s[out->n++] = g[k];
+        if (g[k] != R->gap) out->s[out->n++] = g[k];
     out->local = cost;
     out->total = cost + l->total + r->total;
     out->done = 1;
@@ -111,6 +117,11 @@ int64_t oracle_reroot(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *chi
                                NULL, 0, NULL);
 }
 
+static int64_t reroot_run(rr_t *Rp, uint32_t n_taxa, const int32_t *children, const uint32_t *const *leaf,
+                          const size_t *leaf_len, int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost,
+                          int64_t *edge_local, uint64_t *cells, const uint32_t *trial, size_t trial_len,
+                          int64_t *edge_trial);
+
 /* As oracle_reroot; with `trial` != NULL also edge_trial[e] = cost increase of attaching that new leaf to edge e. */
 int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *children,
                             const uint32_t *const *leaf, const size_t *leaf_len,
@@ -119,7 +130,30 @@ int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_
 {
     rr_t R;
     memset(&R, 0, sizeof R);
-    R.t = t; R.n_taxa = n_taxa; R.n_nodes = 2 * n_taxa - 1; R.children = children;
+    R.t = t; R.gap = t->gap;
+    return reroot_run(&R, n_taxa, children, leaf, leaf_len, edge_u, edge_v, edge_cost, edge_local, cells, trial,
+                      trial_len, edge_trial);
+}
+
+/* The same pass with every alignment done by a Haskell dialect over an alphabet of `a` symbols (dialect / metric_kind /
+ * sigma as oracle_haskell_do): what PCG runs for alphabets > 8. */
+int64_t oracle_reroot_haskell(int dialect, int metric_kind, const uint32_t *sigma, int a, uint32_t n_taxa,
+                              const int32_t *children, const uint32_t *const *leaf, const size_t *leaf_len,
+                              int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local)
+{
+    rr_t R;
+    memset(&R, 0, sizeof R);
+    R.t = NULL; R.hs_dialect = dialect; R.hs_kind = metric_kind; R.hs_sigma = sigma; R.hs_a = a; R.gap = 1u << (a - 1);
+    return reroot_run(&R, n_taxa, children, leaf, leaf_len, edge_u, edge_v, edge_cost, edge_local, NULL, NULL, 0, NULL);
+}
+
+static int64_t reroot_run(rr_t *Rp, uint32_t n_taxa, const int32_t *children, const uint32_t *const *leaf,
+                          const size_t *leaf_len, int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost,
+                          int64_t *edge_local, uint64_t *cells, const uint32_t *trial, size_t trial_len,
+                          int64_t *edge_trial)
+{
+    rr_t R = *Rp;
+    R.n_taxa = n_taxa; R.n_nodes = 2 * n_taxa - 1; R.children = children;
     R.parent = malloc(sizeof(int32_t) * R.n_nodes);
     R.adj = calloc(R.n_nodes, sizeof *R.adj);
     R.down = calloc(R.n_nodes, sizeof(datum_t));

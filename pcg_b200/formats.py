@@ -128,3 +128,44 @@ def read_tcm(text: str) -> Tuple[List[str], np.ndarray]:
     if len(rows) != n or any(len(r) != n for r in rows):
         raise ValueError(f"TCM: expected a {n} x {n} matrix after the alphabet line")
     return alphabet, np.array([[int(float(x)) for x in r] for r in rows], dtype=np.uint32)
+
+
+def read_newick_binary(text: str, taxa: Sequence[str]):
+    """A rooted binary Newick tree over `taxa` -> children[(n-1), 2] int32 in the forest's numbering (leaf = index in
+    `taxa`, internal node x = len(taxa) + x, children listed before parents).  Branch lengths and labels of internal
+    nodes are ignored (lib/file-parsers/src/File/Format/Newick)."""
+    import re
+    idx = {n: i for i, n in enumerate(taxa)}
+    n_taxa = len(taxa)
+    s = "".join(text.split()).rstrip(";")
+    children: List[List[int]] = []
+
+    def skip_annot(pos):
+        m = re.match(r"[^,():;]*(:[^,():;]*)?", s[pos:])
+        return pos + len(m.group(0))
+
+    def parse(pos):
+        if s[pos] == "(":
+            kids, pos = [], pos + 1
+            while True:
+                k, pos = parse(pos)
+                kids.append(k)
+                if s[pos] == ",":
+                    pos += 1
+                    continue
+                if s[pos] == ")":
+                    pos += 1
+                    break
+                raise ValueError("malformed Newick")
+            if len(kids) != 2:
+                raise ValueError("not a binary tree")
+            children.append(kids)
+            return n_taxa + len(children) - 1, skip_annot(pos)
+        m = re.match(r"[^,():;]+", s[pos:])
+        name = m.group(0)
+        return idx[name], skip_annot(pos + len(name)) if s[pos + len(name):pos + len(name) + 1] == ":" else pos + len(name)
+
+    parse(0)
+    if len(children) != n_taxa - 1:
+        raise ValueError("tree does not span the taxa")
+    return np.array(children, dtype=np.int32)

@@ -94,3 +94,21 @@ def chel_golden_tree():
         c = np.array(nodes[gid]["context"], np.uint8)
         leaves.append(c[c[:, 0] != 16][:, 0].copy())
     return g, children, leaves, to_mine
+
+
+def invertebrates_golden():
+    """tests/golden/invertebrates_protein.json -> (children[21, 2], leaves (uint32 strings, a = 21), {name: (sigma, cost)})."""
+    import json
+    from pcg_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "invertebrates_protein.json")))
+    seqs = dict(formats.read_fasta(g["fasta"]))
+    names = sorted(seqs)
+    codes = formats.iupac_amino_codes()
+    leaves = [formats.encode_fasta(seqs[n], codes, np.uint32) for n in names]
+    children = formats.read_newick_binary(g["tree"], names)
+    cases = {}
+    for name, text in g["tcm"].items():
+        alphabet, sigma = formats.read_tcm(text)
+        assert alphabet == formats.AMINO
+        cases[name] = (sigma, g["dag_cost"][name])
+    return children, leaves, cases

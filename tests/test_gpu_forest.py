@@ -286,3 +286,20 @@ def test_forest_large_alphabet_postorder(oracle_mod, gpu_ctx, kind):
     delta = f.try_leaf(None, [variant(c) for c in range(n_chars)])
     assert delta.shape == (n_trees, 2 * n_taxa - 3) and (delta >= 0).all()
     f.close()
+
+
+@pytest.mark.parametrize("name", ["1-2", "2-1"])
+def test_large_alphabet_forest_reproduces_script_test_costs(gpu_ctx, name):
+    """The reference's script-test KATs (ScriptTests.hs:199-204: DAG cost 1948 / 1242) through the device: 22 protein
+    taxa, a = 21, explicit matrix through the per-pair memo table, S2 Ukkonen at every node, re-rooting."""
+    import pcg_b200 as P
+    from tests.helpers import invertebrates_golden
+    children, leaves, cases = invertebrates_golden()
+    sigma, want = cases[name]
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=400, max_b=32, arena_words=0)
+    memo = gpu_ctx.memo(sigma)
+    f = P.Forest(gpu_ctx, children[None], len(leaves), [[s] for s in leaves], node_cap=512, metric=memo, dialect=2)
+    plain = f.score(None)
+    f.enable_rerooting()
+    assert int(f.score_rerooted(None)[0]) == want < int(plain[0])
+    f.close()

@@ -167,3 +167,19 @@ def test_reroot_oracle_reproduces_chel_golden_total(oracle_mod):
     k = int(np.argmin(ec))
     assert (ec == best).sum() == 1 and int(el[k]) == root["local_cost"] == 49
     assert ec[0] > best and len(edges) == 2 * 17 - 3
+
+
+@pytest.mark.parametrize("name", ["1-2", "2-1"])
+def test_large_alphabet_restatement_reproduces_script_test_costs(oracle_mod, name):
+    """PIN for the a > 8 path: the reference's own script tests assert DAG costs 1948 / 1242 for the invertebrates
+    protein data under the 1:2 / 2:1 matrices (test/TestSuite/ScriptTests.hs:199-204).  Post-order + re-rooting with
+    every alignment by the restated unboxedUkkonenFullSpaceDO (S2) over the Sankoff overlap reproduces both; the S1
+    full-matrix dialect gives 1241 for 2:1, so the check tells the dialects apart."""
+    from tests.helpers import invertebrates_golden
+    children, leaves, cases = invertebrates_golden()
+    sigma, want = cases[name]
+    best, edges, ec, el = oracle_mod.reroot_haskell(2, 21, children, leaves, sigma=sigma)
+    assert best == want
+    assert int(ec[0]) > best                      # the input rooting is not the cheapest: re-rooting is exercised
+    if name == "2-1":
+        assert oracle_mod.reroot_haskell(0, 21, children, leaves, sigma=sigma)[0] == want - 1
