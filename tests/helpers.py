@@ -112,3 +112,19 @@ def invertebrates_golden():
         assert alphabet == formats.AMINO
         cases[name] = (sigma, g["dag_cost"][name])
     return children, leaves, cases
+
+
+def missing_values_golden():
+    """tests/golden/missing_values_dna.json -> (children, ungapped leaves (uint8, a = 5), sigma, asserted DAG cost)."""
+    import json
+    from pcg_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "missing_values_dna.json")))
+    seqs = dict(formats.read_fasta(g["fasta"]))
+    names = sorted(seqs)
+    codes = formats.iupac_dna_codes()
+    leaves = []
+    for n in names:
+        e = formats.encode_fasta(seqs[n], codes, np.uint8)
+        leaves.append(e[e != 16])
+    _, sigma = formats.read_tcm(g["tcm"])
+    return formats.read_newick_binary(g["tree"], names), leaves, sigma, g["dag_cost"]

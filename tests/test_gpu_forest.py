@@ -303,3 +303,15 @@ def test_large_alphabet_forest_reproduces_script_test_costs(gpu_ctx, name):
     f.enable_rerooting()
     assert int(f.score_rerooted(None)[0]) == want < int(plain[0])
     f.close()
+
+
+def test_forest_reproduces_missing_values_script_cost(gpu_ctx):
+    """scriptCheckCost 28 (ScriptTests.hs) through the device: dense g4t4 TCM, '?' elements, re-rooting."""
+    import pcg_b200 as P
+    from tests.helpers import missing_values_golden
+    children, leaves, sigma, want = missing_values_golden()
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=64, max_b=32, arena_words=0)
+    f = P.Forest(gpu_ctx, children[None], len(leaves), [[s] for s in leaves], node_cap=64)
+    f.enable_rerooting()
+    assert int(f.score_rerooted(gpu_ctx.tcm(sigma))[0]) == want
+    f.close()

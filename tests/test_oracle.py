@@ -183,3 +183,10 @@ def test_large_alphabet_restatement_reproduces_script_test_costs(oracle_mod, nam
     assert int(ec[0]) > best                      # the input rooting is not the cheapest: re-rooting is exercised
     if name == "2-1":
         assert oracle_mod.reroot_haskell(0, 21, children, leaves, sigma=sigma)[0] == want - 1
+
+
+def test_reroot_oracle_reproduces_missing_values_script_cost(oracle_mod):
+    """scriptCheckCost 28 "dynamic/single-block/missing/missing-values.pcg": IUPAC + '?' elements, g4t4 matrix."""
+    from tests.helpers import missing_values_golden
+    children, leaves, sigma, want = missing_values_golden()
+    assert oracle_mod.reroot(oracle_mod.Oracle(sigma), children, leaves)[0] == want == 28
