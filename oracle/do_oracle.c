@@ -508,10 +508,10 @@ int64_t oracle_align2d_affine(const oracle_tcm_t *t, int variant,
  * Rows i = 0..m follow the lesser string, columns j = 0..n the longer one, exactly as in the Haskell.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
-    int kind;                /* 0 discrete metric, 1 explicit symbol-change matrix, 2 external lookup (compiled tcm-memo) */
+    int kind;                /* 0 discrete metric, 1 explicit symbol-change matrix, 2 L1 norm (closed form), 9 external lookup (compiled tcm-memo) */
     int a;
     const uint32_t *sigma;   /* a*a, indexed [median symbol][input symbol] (Overlap.hs:75-86) */
-    oracle_lookup_fn lookup; /* kind 2 */
+    oracle_lookup_fn lookup; /* kind 9 */
     void *lookup_ctx;
 } hs_metric_t;
 
@@ -521,7 +521,25 @@ static void hs_overlap(const hs_metric_t *mt, uint32_t x, uint32_t y, uint32_t *
         if (x & y) { *med = x & y; *cost = 0; } else { *med = x | y; *cost = 1; }
         return;
     }
-    if (mt->kind == 2) { *cost = mt->lookup(mt->lookup_ctx, x, y, med); return; }
+    if (mt->kind == 9) { *cost = mt->lookup(mt->lookup_ctx, x, y, med); return; }
+    if (mt->kind == 2) {
+        /* firstLinearNormPairwiseLogic (Data/MetricRepresentation.hs:166-190) over Ranged AmbiguityGroup
+         * (Bio/Character/Encodable/Dynamic/AmbiguityGroup.hs:154-172) and Data/Range.hs:100-190.  toRange = (lowest set
+         * symbol, highest set symbol) — PINNED by the L1 script costs 3483 / 21851 through hs_wide.c, the same logic on
+         * multi-word elements; fromRange of lb < ub sets symbols lb .. ub-1 only ((2^ub - 1) xor (2^lb - 1)). */
+        const int a = mt->a;
+        const int xl = x ? __builtin_ctz(x) : a, xh = x ? 31 - __builtin_clz(x) : 0;
+        const int yl = y ? __builtin_ctz(y) : a, yh = y ? 31 - __builtin_clz(y) : 0;
+        const int lo0 = xl < xh ? xl : xh, hi0 = xl < xh ? xh : xl, lo1 = yl < yh ? yl : yh, hi1 = yl < yh ? yh : yl;
+        const int isect = lo1 <= hi0 && hi1 >= lo0;
+        int nl, nu;
+        if (isect) { nl = lo0 > lo1 ? lo0 : lo1; nu = hi0 < hi1 ? hi0 : hi1; }
+        else       { nl = hi0 < hi1 ? hi0 : hi1; nu = lo0 > lo1 ? lo0 : lo1; }
+        const uint64_t full = (a >= 32) ? 0xffffffffull : ((1ull << a) - 1);
+        *med = (uint32_t)((nu == nl ? (1ull << nu) : (((1ull << nu) - 1) ^ ((1ull << nl) - 1))) & full);
+        *cost = isect ? 0 : (uint64_t)(nu - nl);
+        return;
+    }
     uint64_t best = UINT64_MAX;
     uint32_t bits = 0;
     for (int s = mt->a - 1; s >= 0; s--) {                   /* overlap: every symbol attaining the minimum */
@@ -612,7 +630,7 @@ int64_t oracle_haskell_do_lookup(int dialect, oracle_lookup_fn lookup, void *loo
                                  uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
                                  uint64_t *cells, int *final_offset)
 {
-    const hs_metric_t mt = { 2, a, NULL, lookup, lookup_ctx };
+    const hs_metric_t mt = { 9, a, NULL, lookup, lookup_ctx };
     return hs_do(mt, dialect, a, in1, n1, in2, n2, out_med, out_a1, out_a2, out_len, cells, final_offset);
 }
 

@@ -107,7 +107,14 @@ int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_
                             int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells,
                             const uint32_t *trial, size_t trial_len, int64_t *edge_trial);
 
-/* re-rooting with every alignment by a Haskell dialect (alphabets > 8) */
+/* Alphabets of more than 32 symbols (hs_wide.c): an element is W = ceil(a/32) consecutive words, lengths count elements. */
+int64_t oracle_haskell_do_w(int dialect, int metric_kind, const uint32_t *sigma, int a,
+                            const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
+                            uint32_t *out_med, uint32_t *out_a1, uint32_t *out_a2, size_t *out_len,
+                            uint64_t *cells, int *final_offset);
+uint64_t oracle_overlap_w(int metric_kind, const uint32_t *sigma, int a, const uint32_t *x, const uint32_t *y, uint32_t *med);
+
+/* re-rooting with every alignment by a Haskell dialect (alphabets > 8; elements of ceil(a/32) words) */
 int64_t oracle_reroot_haskell(int dialect, int metric_kind, const uint32_t *sigma, int a, uint32_t n_taxa,
                               const int32_t *children, const uint32_t *const *leaf, const size_t *leaf_len,
                               int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local);

@@ -171,8 +171,9 @@ def reroot(oracle: "Oracle", children, leaves, trial=None):
     return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el, et
 
 
-def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None):
+def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None, metric_kind=None):
     """Re-rooting pass with every alignment by a restated Haskell dialect (alphabets > 8).
+    metric_kind: None -> 0 (discrete) without sigma / 1 (explicit) with; 2 = L1 norm (firstLinearNormPairwiseLogic).
     Returns (min cost, edges, edge_cost, edge_local)."""
     if not os.path.exists(ORACLE_SO):
         build(ref=False)
@@ -181,14 +182,16 @@ def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None):
     lib.oracle_reroot_haskell.argtypes = [C.c_int, C.c_int, _u32p, C.c_int, C.c_uint32] + [C.c_void_p] * 7
     ch = np.ascontiguousarray(np.asarray(children, np.int32))
     n_taxa = ch.shape[0] + 1
-    arrs = [_as_u32(x) for x in leaves]
+    W = (a + 31) // 32                      # leaves: (n, W) uint32 arrays when the alphabet exceeds 32 symbols
+    arrs = [_as_u32(x).reshape(-1) for x in leaves]
     ptrs = (C.c_void_p * n_taxa)(*[x.ctypes.data for x in arrs])
-    lens = (C.c_size_t * n_taxa)(*[len(x) for x in arrs])
+    lens = (C.c_size_t * n_taxa)(*[len(x) // W for x in arrs])
     ne = 2 * n_taxa - 3
     eu, ev = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
     ec, el = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
     sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
-    best = lib.oracle_reroot_haskell(dialect, 0 if sigma is None else 1, _ptr(sg), a, n_taxa, ch.ctypes.data, ptrs, lens,
+    kind = metric_kind if metric_kind is not None else (0 if sigma is None else 1)
+    best = lib.oracle_reroot_haskell(dialect, kind, _ptr(sg), a, n_taxa, ch.ctypes.data, ptrs, lens,
                                      eu.ctypes.data, ev.ctypes.data, ec.ctypes.data, el.ctypes.data)
     return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el
 
@@ -424,3 +427,28 @@ def cpu_bench_haskell(dialect: int, a: int, elems, off1, len1, off2, len2, threa
     if rc:
         raise RuntimeError(f"cpu_bench_haskell failed: {rc}")
     return float(sec.value), cost, cells, int(lk.value)
+
+
+def haskell_do_w(dialect: int, a: int, in1, in2, sigma=None, metric_kind=None):
+    """As haskell_do for alphabets of more than 32 symbols: in1 / in2 are (n, W) uint32 arrays, W = ceil(a / 32).
+    Returns (cost, median (k, W), aligned1, aligned2, cells, final_offset)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.oracle_haskell_do_w.restype = C.c_int64
+    lib.oracle_haskell_do_w.argtypes = [C.c_int, C.c_int, _u32p, C.c_int, _u32p, C.c_size_t, _u32p, C.c_size_t,
+                                        _u32p, _u32p, _u32p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_int)]
+    W = (a + 31) // 32
+    a1, a2 = _as_u32(in1).reshape(-1, W), _as_u32(in2).reshape(-1, W)
+    sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
+    cap = len(a1) + len(a2) + 2
+    m, x, y = (np.zeros((cap, W), np.uint32) for _ in range(3))
+    n = C.c_size_t(0)
+    cells = C.c_uint64(0)
+    off = C.c_int(0)
+    kind = metric_kind if metric_kind is not None else (0 if sigma is None else 1)
+    cost = lib.oracle_haskell_do_w(dialect, kind, _ptr(sg), a, _ptr(a1), len(a1), _ptr(a2), len(a2),
+                                   _ptr(m), _ptr(x), _ptr(y), C.byref(n), C.byref(cells), C.byref(off))
+    k = n.value
+    return int(cost), m[:k].copy(), x[:k].copy(), y[:k].copy(), int(cells.value), int(off.value)

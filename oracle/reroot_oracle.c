@@ -31,6 +31,7 @@ typedef struct {
     int hs_dialect, hs_kind, hs_a;    /* oracle_haskell_do parameters for large alphabets */
     const uint32_t *hs_sigma;
     uint32_t gap;
+    int W;                            /* words per element (1 unless the alphabet exceeds 32 symbols) */
     uint32_t n_taxa, n_nodes, root;
     const int32_t *children;          /* [(n_taxa-1)*2], internal node x has id n_taxa + x */
     int32_t *parent;                  /* original parent, -1 for the root */
@@ -42,19 +43,29 @@ typedef struct {
 
 static void apply(rr_t *R, const datum_t *l, const datum_t *r, datum_t *out)
 {
-    const size_t cap = l->n + r->n + 2;
+    const int W = R->W > 1 ? R->W : 1;
+    const size_t cap = (l->n + r->n + 2) * (size_t)W;
     uint32_t *g = malloc(sizeof(uint32_t) * 3 * cap);
     size_t nal = 0;
     uint64_t c = 0;
     int fo = 0;
-    const int64_t cost = R->t ? oracle_align2d(R->t, l->s, l->n, r->s, r->n, g, g + cap, g + 2 * cap, &nal, &c)
-                              : oracle_haskell_do(R->hs_dialect, R->hs_kind, R->hs_sigma, R->hs_a, l->s, l->n, r->s, r->n,
-                                                  g, g + cap, g + 2 * cap, &nal, &c, &fo);
+    int64_t cost;
+    if (R->t) cost = oracle_align2d(R->t, l->s, l->n, r->s, r->n, g, g + cap, g + 2 * cap, &nal, &c);
+    else if (W == 1) cost = oracle_haskell_do(R->hs_dialect, R->hs_kind, R->hs_sigma, R->hs_a, l->s, l->n, r->s, r->n,
+                                              g, g + cap, g + 2 * cap, &nal, &c, &fo);
+    else cost = oracle_haskell_do_w(R->hs_dialect, R->hs_kind, R->hs_sigma, R->hs_a, l->s, l->n, r->s, r->n,
+                                    g, g + cap, g + 2 * cap, &nal, &c, &fo);
     R->cells += c;
-    out->s = malloc(sizeof(uint32_t) * (nal + 1));
+    out->s = malloc(sizeof(uint32_t) * (nal + 1) * (size_t)W);
     out->n = 0;
-    for (size_t k = 0; k < nal; k++)
-        if (g[k] != R->gap) out->s[out->n++] = g[k];
+    for (size_t k = 0; k < nal; k++) {
+        int is_gap = 1;                                      /* deleteGaps: the median is exactly the gap */
+        for (int w = 0; w < W; w++) {
+            const uint32_t want = (W == 1) ? R->gap : ((R->hs_a - 1) >> 5) == w ? 1u << ((R->hs_a - 1) & 31) : 0u;
+            if (g[k * W + w] != want) is_gap = 0;
+        }
+        if (!is_gap) { memcpy(out->s + out->n * W, g + k * W, sizeof(uint32_t) * (size_t)W); out->n++; }
+    }
     out->local = cost;
     out->total = cost + l->total + r->total;
     out->done = 1;
@@ -143,7 +154,9 @@ int64_t oracle_reroot_haskell(int dialect, int metric_kind, const uint32_t *sigm
 {
     rr_t R;
     memset(&R, 0, sizeof R);
-    R.t = NULL; R.hs_dialect = dialect; R.hs_kind = metric_kind; R.hs_sigma = sigma; R.hs_a = a; R.gap = 1u << (a - 1);
+    R.t = NULL; R.hs_dialect = dialect; R.hs_kind = metric_kind; R.hs_sigma = sigma; R.hs_a = a;
+    R.W = (a + 31) / 32;
+    R.gap = a <= 32 ? 1u << (a - 1) : 0u;
     return reroot_run(&R, n_taxa, children, leaf, leaf_len, edge_u, edge_v, edge_cost, edge_local, NULL, NULL, 0, NULL);
 }
 

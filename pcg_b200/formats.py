@@ -119,6 +119,42 @@ def encode_fastc(groups: Sequence[Sequence[str]], alphabet: Sequence[str], dtype
     return np.fromiter((full if g == ["?"] else sum(bit[s] for s in g) for g in groups), dtype=dtype, count=len(groups))
 
 
+def encode_fastc_wide(groups: Sequence[Sequence[str]], alphabet: Sequence[str]) -> np.ndarray:
+    """As ``encode_fastc`` for alphabets of any size: (n, W) uint32, W = ceil((len(alphabet) + 1) / 32); bit i of an
+    element = bit i % 32 of word i // 32 (the layout of the 32-bit-word forest, ``pcgdo_forest_create32`` with a > 32)."""
+    a = len(alphabet) + 1
+    W = (a + 31) // 32
+    idx = {s: i for i, s in enumerate(alphabet)}
+    idx["-"] = a - 1
+    out = np.zeros((len(groups), W), np.uint32)
+    for k, g in enumerate(groups):
+        for i in (range(a) if list(g) == ["?"] else (idx[s] for s in g)):
+            out[k, i >> 5] |= np.uint32(1 << (i & 31))
+    return out
+
+
+def diagnose_tcm(sigma: np.ndarray) -> Tuple[int, np.ndarray, str]:
+    """``diagnoseTcm`` as far as the DO dispatch needs it (lib/core/tcm/src/Data/TCM/Internal.hs:506-524, 549-590;
+    used by ``dynamicMetadata``, Bio/Metadata/Dynamic/Internal.hs:286-300): (weight, factored matrix, structure) with
+    structure ``"additive"`` (sigma(i,j) = |i-j| -> ``firstLinearNormPairwiseLogic``), ``"nonadditive"`` (0 on / 1 off the
+    diagonal -> ``discreteMetricPairwiseLogic``) or ``"explicit"`` (memoized Sankoff overlap).  The common factor of all
+    entries is divided out first (``factorTCM``); the DO runs on the factored matrix and PCG multiplies the weight back."""
+    m = np.asarray(sigma, dtype=np.int64)
+    n = m.shape[0]
+    factor = int(np.gcd.reduce(m.reshape(-1)))
+    f = m // factor if factor > 1 else m
+    i, j = np.indices((n, n))
+    # |i-j| and 0/1 matrices are symmetric metrics (the 0/1 one ultrametric too), so the guards above them in diagnoseTcm
+    # always pass; Additive is tested first, which matters for the 2 x 2 matrix that is both
+    if bool((f == np.abs(i - j)).all()):
+        kind = "additive"
+    elif bool((f == (i != j)).all()):
+        kind = "nonadditive"
+    else:
+        kind = "explicit"
+    return max(factor, 1), f.astype(np.uint32), kind
+
+
 def read_tcm(text: str) -> Tuple[List[str], np.ndarray]:
     """(alphabet without gap, (n+1) x (n+1) uint32 matrix with the gap as last row / column)."""
     lines = [ln.split() for ln in text.splitlines() if ln.strip()]

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Generates tests/golden/custom_alphabet_scripts.json: inputs and asserted DAG costs of the reference's script tests on
+custom alphabets of MORE THAN 32 symbols (test/TestSuite/ScriptTests.hs:205-266):
+
+    slashes   (81 symbols + gap):  L1-norm 3483, discrete 197, 2-1 228, hamming 671, levenshtein 488
+    large-mix (255 symbols + gap): discrete 133
+    huge-mix  (432 symbols + gap): discrete 246, L1-norm 21851, 1-2 325, hamming 872, levenshtein 698
+
+Each script reads shared-data/<set>/<set>.fasta (space-separated symbols, one dynamic character per taxon) under
+shared-data/tcms/<set>-<matrix>.tcm and the tree shared-data/<set>/<set>.tree; the asserted number is the cost of the
+decorated DAG (post-order + re-rooting).  PCG diagnoses each matrix (Data/TCM/Internal.hs:506-524): |i-j| -> the L1
+closed form (firstLinearNormPairwiseLogic), 0/1 -> the discrete closed form, anything else -> memoized Sankoff overlap.
+Matrices are stored zlib-compressed (uint16, row-major, base64).
+Run in the build container (needs /root/reference):  python tests/golden/make_custom_alphabet_golden.py
+"""
+import base64
+import json
+import os
+import re
+import zlib
+
+import numpy as np
+
+SRC = "/root/reference/test/data-sets/shared-data"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "custom_alphabet_scripts.json")
+CASES = {"slashes": ["L1-norm", "discrete", "2-1", "hamming", "levenshtein"],
+         "large-mix": ["discrete"],
+         "huge-mix": ["discrete", "L1-norm", "1-2", "hamming", "levenshtein"]}
+
+
+def main():
+    src = open("/root/reference/test/TestSuite/ScriptTests.hs").read()
+    out = {"source": "test/data-sets/shared-data/{slashes,large-mix,huge-mix}, shared-data/tcms; expected costs from "
+                     "test/TestSuite/ScriptTests.hs:205-266", "sets": {}}
+    for ds, mats in CASES.items():
+        entry = {"fasta": open(os.path.join(SRC, ds, ds + ".fasta")).read(),
+                 "tree": open(os.path.join(SRC, ds, ds + ".tree")).read().strip(), "cases": {}}
+        for mname in mats:
+            m = re.search(r"^\s*,\s*scriptCheckCost\s+(\d+)\s+\"dynamic/single-block/%s/%s/test.pcg\"" % (ds, mname), src, re.M)
+            fname = mname.replace("levenshtein", "leveshtein")            # the file name is spelt that way upstream
+            lines = [l for l in open(os.path.join(SRC, "tcms", f"{ds}-{fname}.tcm")).read().splitlines() if l.strip()]
+            alphabet = lines[0].split()
+            sig = np.array([[int(v) for v in l.split()] for l in lines[1:]], np.int64)
+            assert sig.shape == (len(alphabet) + 1,) * 2 and sig.max() < 65536
+            entry.setdefault("alphabet", alphabet)
+            assert entry["alphabet"] == alphabet
+            entry["cases"][mname] = {"dag_cost": int(m.group(1)),
+                                     "sigma_u16_zlib_b64": base64.b64encode(zlib.compress(sig.astype("<u2").tobytes(), 9)).decode()}
+        out["sets"][ds] = entry
+    json.dump(out, open(OUT, "w"), separators=(",", ":"))
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -128,3 +128,26 @@ def missing_values_golden():
         leaves.append(e[e != 16])
     _, sigma = formats.read_tcm(g["tcm"])
     return formats.read_newick_binary(g["tree"], names), leaves, sigma, g["dag_cost"]
+
+
+def custom_alphabet_golden(ds):
+    """tests/golden/custom_alphabet_scripts.json -> (a, children, leaves ((n, W) uint32 each), {matrix name: (metric kind,
+    factored sigma, weight, asserted DAG cost)}) for one of "slashes" / "large-mix" / "huge-mix".  metric kind as the oracle
+    numbers them: 0 discrete, 1 explicit (Sankoff), 2 L1 norm — chosen by pcg_b200.formats.diagnose_tcm like PCG does."""
+    import base64
+    import json
+    import zlib
+    from pcg_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "custom_alphabet_scripts.json")))["sets"][ds]
+    alphabet = g["alphabet"]
+    a = len(alphabet) + 1
+    seqs = dict(formats.read_fastc(g["fasta"]))
+    names = sorted(seqs)
+    leaves = [formats.encode_fastc_wide(seqs[n], alphabet) for n in names]
+    children = formats.read_newick_binary(g["tree"], names)
+    cases = {}
+    for name, c in g["cases"].items():
+        sig = np.frombuffer(zlib.decompress(base64.b64decode(c["sigma_u16_zlib_b64"])), "<u2").reshape(a, a)
+        weight, f, kind = formats.diagnose_tcm(sig)
+        cases[name] = ({"nonadditive": 0, "explicit": 1, "additive": 2}[kind], f, weight, c["dag_cost"])
+    return a, children, leaves, cases

@@ -190,3 +190,27 @@ def test_reroot_oracle_reproduces_missing_values_script_cost(oracle_mod):
     from tests.helpers import missing_values_golden
     children, leaves, sigma, want = missing_values_golden()
     assert oracle_mod.reroot(oracle_mod.Oracle(sigma), children, leaves)[0] == want == 28
+
+
+_CUSTOM = [("slashes", "L1-norm"), ("slashes", "discrete"), ("slashes", "2-1"), ("slashes", "hamming"),
+           ("slashes", "levenshtein"), ("large-mix", "discrete"), ("huge-mix", "discrete"), ("huge-mix", "L1-norm"),
+           ("huge-mix", "1-2"), ("huge-mix", "hamming"), ("huge-mix", "levenshtein")]
+
+
+@pytest.mark.parametrize("ds,name", _CUSTOM)
+def test_wide_alphabet_script_costs(oracle_mod, ds, name):
+    """PIN for alphabets of more than 32 symbols AND for the L1 closed form: the reference's script tests on the slashes
+    (82 symbols with the gap), large-mix (256) and huge-mix (433) data (test/TestSuite/ScriptTests.hs:205-266) assert the
+    DAG costs below; post-order + re-rooting with the restated unboxedUkkonenFullSpaceDO over W-word elements
+    (oracle/hs_wide.c) reproduces all eleven.  The two L1 numbers (3483, 21851) settle how firstLinearNormPairwiseLogic
+    reads an ambiguity set: range = lowest..highest set symbol (bv-little counts "leading" zeros from index 0) and
+    fromRange drops the upper bound's bit — the mirrored reading gives 4380 and the true Sankoff median 3371 on slashes."""
+    from tests.helpers import custom_alphabet_golden
+    a, children, leaves, cases = custom_alphabet_golden(ds)
+    kind, sigma, weight, want = cases[name]
+    assert kind == {"L1-norm": 2, "discrete": 0}.get(name, 1)
+    best = oracle_mod.reroot_haskell(2, a, children, leaves, sigma=sigma, metric_kind=kind)[0]
+    assert weight * best == want
+    if (ds, name) == ("slashes", "L1-norm"):
+        assert oracle_mod.reroot_haskell(2, a, children, leaves, sigma=sigma, metric_kind=3)[0] == 4380
+        assert oracle_mod.reroot_haskell(2, a, children, leaves, sigma=sigma, metric_kind=1)[0] == 3371
