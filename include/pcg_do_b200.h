@@ -159,8 +159,9 @@ int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const 
  * Inputs are median strings (what `measureAndUngapCharacters` leaves); outputs per pair: median, aligned first
  * input, aligned second input (0 = gap), at element offset out_off[k] (room for len1+len2 elements).
  * Upstream has neither golden vectors nor (here) an executable for these paths: parity is against the restatement
- * in oracle/do_oracle.c only.  Explicit matrices: pcgdo_explicit_batch_* below.  The additive (L1) metric for
- * a > 8 is not built (its reference semantics hinge on the un-vendored bv-little bit order). */
+ * in oracle/do_oracle.c, itself pinned end to end by the reference's script-test DAG costs.  Explicit
+ * matrices, the additive (L1) closed form and alphabets of more than 32 symbols: pcgdo_explicit_batch_* below.
+ * elems_count / out_count count 32-bit WORDS (= elements up to 32 symbols). */
 typedef struct pcgdo_batch32 {
     size_t          n_pairs;
     const uint32_t *elems;
@@ -187,6 +188,25 @@ int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcg
 typedef struct pcgdo_memo pcgdo_memo;
 int  pcgdo_memo_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, pcgdo_memo **out);
 void pcgdo_memo_destroy(pcgdo_ctx *ctx, pcgdo_memo *memo);
+/* The metric representation PCG derives from a (factored) symbol-change matrix — `dynamicMetadata`,
+ * Bio/Metadata/Dynamic/Internal.hs:286-300 over `diagnoseTcm`, Data/TCM/Internal.hs:506-524 — decides the overlap function
+ * of the a > 8 path (`retreivePairwiseTCM`, Data/MetricRepresentation.hs:84-91):
+ *   PCGDO_METRIC_EXPLICIT  memoized Sankoff overlap of the matrix (tcm-memo)        sigma required
+ *   PCGDO_METRIC_DISCRETE  discreteMetricPairwiseLogic  (:116-128)                  sigma may be NULL
+ *   PCGDO_METRIC_L1        firstLinearNormPairwiseLogic (:166-190), as coded: a set is read as the interval lowest..highest
+ *                          set symbol and the median of [lb, ub], lb < ub, is the symbols lb..ub-1   sigma may be NULL
+ *   PCGDO_METRIC_AUTO      diagnose sigma like PCG: |i-j| -> L1, 0/1 -> discrete, else explicit (factor the matrix first)
+ * Alphabets of up to PCGDO_MAX_ALPHABET symbols: beyond 32 an element is W = ceil(a / 32) consecutive 32-bit words (bit i
+ * of the set = bit i % 32 of word i / 32, gap = symbol a-1; elements order as unsigned naturals, most significant word
+ * first), in pcgdo_batch32 and in forests alike; offsets, lengths and capacities keep counting ELEMENTS. */
+#define PCGDO_MAX_ALPHABET     512
+#define PCGDO_METRIC_AUTO     (-1)
+#define PCGDO_METRIC_EXPLICIT   0
+#define PCGDO_METRIC_DISCRETE   1
+#define PCGDO_METRIC_L1         2
+int  pcgdo_memo_create_metric(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, int structure, pcgdo_memo **out);
+int  pcgdo_memo_structure(const pcgdo_memo *memo);
+uint32_t pcgdo_memo_alphabet(const pcgdo_memo *memo);
 /* n independent overlap lookups: median[k], cost[k] = Sankoff median / cost of the sets e1[k], e2[k]. */
 int  pcgdo_overlap2d_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, size_t n, const uint32_t *e1, const uint32_t *e2,
                                   uint32_t *median, uint32_t *cost, void *cuda_stream);

@@ -196,9 +196,9 @@ def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None, metric_ki
     return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el
 
 
-def haskell_do(dialect: int, a: int, in1, in2, sigma=None):
-    """S1 / S2 Haskell dialects on median strings (see do_oracle.c). sigma=None -> discrete metric.
-    Returns (cost, median, aligned1, aligned2, cells, final_offset)."""
+def haskell_do(dialect: int, a: int, in1, in2, sigma=None, metric_kind=None):
+    """S1 / S2 Haskell dialects on median strings (see do_oracle.c). sigma=None -> discrete metric; metric_kind 2 = the L1
+    closed form.  Returns (cost, median, aligned1, aligned2, cells, final_offset)."""
     if not os.path.exists(ORACLE_SO):
         build(ref=False)
     lib = C.CDLL(ORACLE_SO)
@@ -213,7 +213,8 @@ def haskell_do(dialect: int, a: int, in1, in2, sigma=None):
     n = C.c_size_t(0)
     cells = C.c_uint64(0)
     off = C.c_int(0)
-    cost = lib.oracle_haskell_do(dialect, 0 if sigma is None else 1, _ptr(sg), a, _ptr(a1), len(a1), _ptr(a2), len(a2),
+    kind = metric_kind if metric_kind is not None else (0 if sigma is None else 1)
+    cost = lib.oracle_haskell_do(dialect, kind, _ptr(sg), a, _ptr(a1), len(a1), _ptr(a2), len(a2),
                                  _ptr(m), _ptr(x), _ptr(y), C.byref(n), C.byref(cells), C.byref(off))
     k = n.value
     return int(cost), m[:k].copy(), x[:k].copy(), y[:k].copy(), int(cells.value), int(off.value)

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "pcgdo_forest_tree_cost_ptr", "pcgdo_forest_tree_costs", "pcgdo_forest_copy_tree_costs", "pcgdo_forest_get_node", "pcgdo_forest_levels",
     "pcgdo_forest_alignments",
     "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges", "pcgdo_forest_try_leaf", "pcgdo_forest_create32", "pcgdo_forest_set_leaves32",
-    "pcgdo_memo_create", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
+    "pcgdo_memo_create", "pcgdo_memo_create_metric", "pcgdo_memo_structure", "pcgdo_memo_alphabet", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
     "pcgdo_explicit_batch_device", "pcgdo_explicit_batch_host",
     "matrixInit", "matrixDestroy", "getCostAndMedian2D",
 ]
@@ -132,6 +132,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_forest_edges.argtypes = [C.c_void_p]
     L.pcgdo_forest_edges.restype = C.c_uint32
     L.pcgdo_memo_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.pcgdo_memo_create_metric.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    L.pcgdo_memo_structure.argtypes = [C.c_void_p]
+    L.pcgdo_memo_alphabet.argtypes = [C.c_void_p]
+    L.pcgdo_memo_alphabet.restype = C.c_uint32
     L.pcgdo_memo_destroy.argtypes = [C.c_void_p, C.c_void_p]
     L.pcgdo_overlap2d_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 5
     L.pcgdo_overlap2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
@@ -188,8 +192,8 @@ class Context:
     def tcm(self, sigma, gap_open: int = 0, affine_variant: int = 0) -> "Tcm":
         return Tcm(self, sigma, gap_open, affine_variant)
 
-    def memo(self, sigma) -> "Memo":
-        return Memo(self, sigma)
+    def memo(self, sigma, structure="explicit", a=None) -> "Memo":
+        return Memo(self, sigma, structure, a)
 
     def int32_peak(self, mode: int = 0) -> float:
         """Measured integer lane-ops/s of this GPU (roofline denominator for the DP fill)."""
@@ -240,19 +244,33 @@ class Tcm:
             pass
 
 
-class Memo:
-    """Explicit symbol-change matrix for alphabets the dense table cannot hold (pcgdo_memo): the device-side
-    replacement of the reference's memoized TCM (lib/tcm-memo).  sigma[s, j]: median symbol s, input symbol j."""
+METRIC_AUTO, METRIC_EXPLICIT, METRIC_DISCRETE, METRIC_L1 = -1, 0, 1, 2
+_STRUCTURES = {"auto": METRIC_AUTO, "explicit": METRIC_EXPLICIT, "discrete": METRIC_DISCRETE, "nonadditive": METRIC_DISCRETE,
+               "l1": METRIC_L1, "additive": METRIC_L1}
 
-    def __init__(self, ctx: Context, sigma):
+
+class Memo:
+    """Overlap function of the a > 8 path (pcgdo_memo): the device-side replacement of the reference's memoized TCM
+    (lib/tcm-memo) for an explicit matrix — sigma[s, j]: median symbol s, input symbol j — or one of the closed forms PCG
+    picks after diagnosing the matrix (``structure``: "explicit", "discrete", "l1", or "auto" = diagnose sigma like
+    ``dynamicMetadata``).  Alphabets of up to 512 symbols; beyond 32 an element is ``words`` = ceil(a / 32) uint32."""
+
+    def __init__(self, ctx: Context, sigma, structure="explicit", a=None):
         self.ctx = ctx
-        sigma = np.ascontiguousarray(np.asarray(sigma, dtype=np.uint32))
-        self.a = int(sigma.shape[0])
-        assert sigma.shape == (self.a, self.a)
+        if sigma is not None:
+            sigma = np.ascontiguousarray(np.asarray(sigma, dtype=np.uint32))
+            self.a = int(sigma.shape[0])
+            assert sigma.shape == (self.a, self.a)
+        else:
+            self.a = int(a)
+        self.words = (self.a + 31) // 32
         self.gap = 1 << (self.a - 1)
         h = C.c_void_p()
-        ctx.check(ctx.lib.pcgdo_memo_create(ctx.h, sigma.ctypes.data_as(_u32p), self.a, C.byref(h)), "pcgdo_memo_create")
+        ctx.check(ctx.lib.pcgdo_memo_create_metric(ctx.h, sigma.ctypes.data_as(_u32p) if sigma is not None else None, self.a,
+                                                   _STRUCTURES[structure] if isinstance(structure, str) else int(structure),
+                                                   C.byref(h)), "pcgdo_memo_create_metric")
         self.h = h
+        self.structure = int(ctx.lib.pcgdo_memo_structure(h))
 
     def overlap(self, e1, e2):
         """``getMedianAndCost2D`` over arrays of ambiguity sets: (median[uint32], cost[uint32])."""
@@ -286,6 +304,8 @@ class Forest:
         self.ctx = ctx
         self.metric = metric
         self.dtype = np.uint8 if metric is None else np.uint32
+        # words per element: large alphabets beyond 32 symbols use (n, words) uint32 strings
+        self.words = 1 if metric is None else ((int(metric) if isinstance(metric, int) else metric.a) + 31) // 32
         ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
         assert ch.ndim == 3 and ch.shape[1] == n_taxa - 1 and ch.shape[2] == 2
         self.n_trees, self.n_taxa = int(ch.shape[0]), int(n_taxa)
@@ -301,11 +321,11 @@ class Forest:
                                                     ch.ctypes.data, memo_h, alpha, dialect, C.byref(h)),
                       "pcgdo_forest_create32")
         self.h = h
-        flat = [np.asarray(s, self.dtype) for taxon in leaves for s in taxon]
+        flat = [np.asarray(s, self.dtype).reshape(-1, self.words) for taxon in leaves for s in taxon]
         ln = np.array([len(s) for s in flat], np.uint32)
         off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
-        elems = np.concatenate(flat) if flat else np.zeros(0, self.dtype)
-        elems = np.ascontiguousarray(elems)
+        elems = np.concatenate(flat) if flat else np.zeros((0, self.words), self.dtype)
+        elems = np.ascontiguousarray(elems.reshape(-1))
         fn = ctx.lib.pcgdo_forest_set_leaves if metric is None else ctx.lib.pcgdo_forest_set_leaves32
         ctx.check(fn(ctx.h, self.h, elems.ctypes.data, off.ctypes.data, ln.ctypes.data), "pcgdo_forest_set_leaves")
 
@@ -338,10 +358,10 @@ class Forest:
         """Wagner edge trial (``iterativeBuild.tryEdge``): cost increase of attaching a new taxon (one element string
         per character) to every edge of every tree -> int64 (n_trees, n_edges).  Needs a re-rooted sweep with
         ``enable_rerooting(keep_edge_data=True)``."""
-        flat = [np.asarray(x, self.dtype) for x in leaf_strings]
+        flat = [np.asarray(x, self.dtype).reshape(-1, self.words) for x in leaf_strings]
         ln = np.array([len(x) for x in flat], np.uint32)
         off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
-        elems = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1, self.dtype)
+        elems = np.ascontiguousarray(np.concatenate(flat).reshape(-1)) if flat else np.zeros(1, self.dtype)
         ne = int(self.ctx.lib.pcgdo_forest_edges(self.h))
         out = np.zeros((self.n_trees, ne), np.int64)
         self.ctx.check(self.ctx.lib.pcgdo_forest_try_leaf(self.ctx.h, tcm.h if tcm is not None else None, self.h, elems.ctypes.data, off.ctypes.data,
@@ -373,12 +393,13 @@ class Forest:
         return uv, tot, loc
 
     def node(self, tree: int, character: int, node: int):
-        buf = np.zeros(self.node_cap, self.dtype)
+        buf = np.zeros(self.node_cap * self.words, self.dtype)
         n, lc, tc = C.c_uint32(0), C.c_int32(0), C.c_int64(0)
         self.ctx.check(self.ctx.lib.pcgdo_forest_get_node(self.ctx.h, self.h, tree, character, node, buf.ctypes.data,
                                                           C.byref(n), C.byref(lc), C.byref(tc)),
                        "pcgdo_forest_get_node")
-        return buf[:n.value].copy(), int(lc.value), int(tc.value)
+        med = buf[:n.value * self.words].copy()
+        return (med if self.words == 1 else med.reshape(-1, self.words)), int(lc.value), int(tc.value)
 
     @property
     def levels(self) -> int:

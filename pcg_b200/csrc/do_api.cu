@@ -704,53 +704,65 @@ extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect
 
 struct pcgdo_memo {
     size_t a = 0;
+    int kind = 2;            // kernel numbering: 0 discrete closed form, 1 L1 closed form, 2 explicit (Sankoff)
     uint32_t delta = 0;
     std::vector<uint32_t> sigma;
     void *d_sigma = nullptr;
 };
 
-static void host_overlap(const uint32_t *sg, size_t a, uint64_t x, uint64_t y, uint64_t *med, uint32_t *cost)
+// diagnoseTcm as far as the DO dispatch needs it (lib/core/tcm/src/Data/TCM/Internal.hs:506-524, 573-590): sigma(i,j) =
+// |i-j| is Additive (tested first), 0/1 is NonAdditive, anything else keeps its explicit layout.  The caller factors the
+// matrix (factorTCM) before handing it over — PCG applies the weight outside the DO.
+static int diagnose_structure(const unsigned int *sigma, size_t a)
 {
-    uint32_t best = 0xffffffffu;
-    uint64_t bits = 0;
-    for (size_t s = 0; s < a; ++s) {
-        uint32_t dx = 0xffffffffu, dy = 0xffffffffu;
+    bool additive = true, discrete = true;
+    for (size_t i = 0; i < a; ++i)
         for (size_t j = 0; j < a; ++j) {
-            if ((x >> j) & 1) dx = std::min(dx, sg[s * a + j]);
-            if ((y >> j) & 1) dy = std::min(dy, sg[s * a + j]);
+            const unsigned int v = sigma[i * a + j];
+            if (v != (unsigned int)(i > j ? i - j : j - i)) additive = false;
+            if (v != (i == j ? 0u : 1u)) discrete = false;
         }
-        const uint32_t c = dx + dy;
-        if (c < best) { best = c; bits = (uint64_t)1 << s; }
-        else if (c == best) bits |= (uint64_t)1 << s;
-    }
-    *med = bits; *cost = best;
+    return additive ? PCGDO_METRIC_L1 : discrete ? PCGDO_METRIC_DISCRETE : PCGDO_METRIC_EXPLICIT;
 }
 
-extern "C" int pcgdo_memo_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, pcgdo_memo **out)
+extern "C" int pcgdo_memo_create_metric(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, int structure, pcgdo_memo **out)
 {
-    if (!ctx || !sigma || !out) return PCGDO_ERR_ARG;
-    if (a < 2 || a > 32) {
-        ctx->err = "explicit-matrix path: alphabet size must be 2..32";
+    if (!ctx || !out) return PCGDO_ERR_ARG;
+    if (a < 2 || a > PCGDO_MAX_ALPHABET) {
+        ctx->err = "large-alphabet path: alphabet size must be 2..512";
         return PCGDO_ERR_UNSUPPORTED;
     }
-    for (size_t i = 0; i < a * a; ++i)
-        if (sigma[i] > 2000u) {
-            ctx->err = "explicit-matrix path: symbol-change costs above 2000 do not fit the 16-bit device table";
-            return PCGDO_ERR_UNSUPPORTED;
-        }
+    if (structure == PCGDO_METRIC_AUTO) {
+        if (!sigma) return PCGDO_ERR_ARG;
+        structure = diagnose_structure(sigma, a);
+    }
+    if (structure != PCGDO_METRIC_EXPLICIT && structure != PCGDO_METRIC_DISCRETE && structure != PCGDO_METRIC_L1)
+        return PCGDO_ERR_ARG;
+    if (structure == PCGDO_METRIC_EXPLICIT) {
+        if (!sigma) return PCGDO_ERR_ARG;
+        for (size_t i = 0; i < a * a; ++i)
+            if (sigma[i] > 2000u) {
+                ctx->err = "explicit-matrix path: symbol-change costs above 2000 do not fit the 16-bit device table";
+                return PCGDO_ERR_UNSUPPORTED;
+            }
+    }
     CK(cudaSetDevice(ctx->device));
     pcgdo_memo *m = new pcgdo_memo();
     m->a = a;
-    m->sigma.assign(sigma, sigma + a * a);
+    m->kind = structure == PCGDO_METRIC_DISCRETE ? 0 : structure == PCGDO_METRIC_L1 ? 1 : 2;
     // Ukkonen coefficient: cheapest indel of a single non-gap symbol (UnboxedUkkonenSwapping.hs:436-459) —
     // setup-time table work on a*a numbers, like setUp2dCostMtx
+    if (m->kind != 2) {
+        m->delta = a >= 2 ? 1u : 0u;          // discrete: 1; L1: |(a-1) - s| is smallest (1) for s = a-2
+        *out = m;
+        return PCGDO_OK;
+    }
+    m->sigma.assign(sigma, sigma + a * a);
     uint32_t delta = 0xffffffffu;
-    const uint64_t gap = (uint64_t)1 << (a - 1);
-    for (size_t s = 0; s + 1 < a; ++s) {
-        uint64_t md; uint32_t c1, c2;
-        host_overlap(m->sigma.data(), a, (uint64_t)1 << s, gap, &md, &c1);
-        host_overlap(m->sigma.data(), a, gap, (uint64_t)1 << s, &md, &c2);
-        delta = std::min(delta, std::min(c1, c2));
+    for (size_t s = 0; s + 1 < a; ++s) {      // overlap({s}, {gap}) = min over medians t of sigma(t,s) + sigma(t,gap)
+        uint32_t c = 0xffffffffu;
+        for (size_t t = 0; t < a; ++t) c = std::min(c, m->sigma[t * a + s] + m->sigma[t * a + a - 1]);
+        delta = std::min(delta, c);
     }
     m->delta = delta;
     cudaError_t e = cudaMalloc(&m->d_sigma, a * a * 4);
@@ -762,6 +774,23 @@ extern "C" int pcgdo_memo_create(pcgdo_ctx *ctx, const unsigned int *sigma, size
     }
     *out = m;
     return PCGDO_OK;
+}
+
+extern "C" int pcgdo_memo_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, pcgdo_memo **out)
+{
+    if (!ctx || !sigma || !out) return PCGDO_ERR_ARG;
+    if (a < 2 || a > 32) {
+        ctx->err = "explicit-matrix path: alphabet size must be 2..32";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    return pcgdo_memo_create_metric(ctx, sigma, a, PCGDO_METRIC_EXPLICIT, out);
+}
+
+extern "C" uint32_t pcgdo_memo_alphabet(const pcgdo_memo *m) { return m ? (uint32_t)m->a : 0u; }
+
+extern "C" int pcgdo_memo_structure(const pcgdo_memo *m)
+{
+    return !m ? PCGDO_METRIC_DISCRETE : m->kind == 0 ? PCGDO_METRIC_DISCRETE : m->kind == 1 ? PCGDO_METRIC_L1 : PCGDO_METRIC_EXPLICIT;
 }
 
 extern "C" void pcgdo_memo_destroy(pcgdo_ctx *ctx, pcgdo_memo *m)
@@ -776,6 +805,10 @@ extern "C" int pcgdo_overlap2d_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *me
                                             const uint32_t *e2, uint32_t *median, uint32_t *cost, void *cuda_stream)
 {
     if (!ctx || !memo || (n && (!e1 || !e2))) return PCGDO_ERR_ARG;
+    if (memo->kind != 2 || memo->a > 32) {
+        ctx->err = "pcgdo_overlap2d_batch: needs an explicit matrix over at most 32 symbols";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
     ctx->timed = false;
     ctx->last_launches = 0;
     if (n == 0) return PCGDO_OK;
@@ -818,6 +851,38 @@ extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *mem
     return table_batch_device(ctx, memo, (int)memo->a, dialect, b, cuda_stream);
 }
 
+// launch geometry of the per-pair table kernel for an alphabet of `a` symbols
+struct TableCfg { uint32_t seq_cap, tab_entries; int warps; size_t smem, arena_words, ts_words; };
+static int table_config(pcgdo_ctx *ctx, int a, TableCfg &c)
+{
+    c.seq_cap = metric_seq_cap(ctx->max_len);
+    c.tab_entries = 1024;                                  // 2 KB of shared memory per warp for small tables
+    // a <= 32: sigma staged in shared memory; wider alphabets keep it in global memory and stage the gap element only
+    const size_t sg_bytes = a > 32 ? 64 : (((size_t)a * a * 4 + 15) & ~(size_t)15);
+    const size_t per_warp = 512 + (size_t)c.seq_cap + 2 * (size_t)c.tab_entries;
+    c.warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    if (a > 32 && c.warps > 4) c.warps = 4;                // per-warp profile scratch grows with a * max_len
+    while (c.warps > 1 && sg_bytes + (size_t)c.warps * per_warp > 227 * 1024) --c.warps;
+    c.smem = sg_bytes + (size_t)c.warps * per_warp;
+    if (c.smem > 227 * 1024) {
+        ctx->err = "max_len too large for the explicit-matrix kernel's staging window";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    c.arena_words = ctx->arena_words;
+    if (!c.arena_words) {
+        const size_t per = metric_words_for((uint32_t)ctx->max_len, (uint32_t)ctx->max_len);
+        c.arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 4096);
+    }
+    c.arena_words = (c.arena_words + 3) & ~(size_t)3;
+    if (c.arena_words > 0xfffffff0u) c.arena_words = 0xfffffff0u;
+    c.ts_words = (explicit_scratch_words(ctx->max_len, a, (size_t)1 << 20) + 3) & ~(size_t)3;
+    if (c.ts_words > 0xfffffff0u) {
+        ctx->err = "max_len x alphabet too large for the table kernel's per-warp scratch (lower max_len)";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    return PCGDO_OK;
+}
+
 // memo == NULL: the discrete metric over `alphabet` symbols through the same per-pair table machinery
 // Enqueue the per-pair table kernel for one batch described on the device (the forest scheduler's levels): no
 // synchronisation, failure counters accumulate in counters[8..10] unless reset_overflow.
@@ -825,31 +890,16 @@ int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, in
                         cudaStream_t st, bool reset_overflow, unsigned int **counters_out)
 {
     const int a = memo ? (int)memo->a : alphabet;
-    if (a < 2 || a > 32 || dialect < 0 || dialect > 2) {
-        ctx->err = "table path: alphabet size must be 2..32, dialect 0..2";
+    if (a < 2 || a > PCGDO_MAX_ALPHABET || dialect < 0 || dialect > 2) {
+        ctx->err = "table path: alphabet size must be 2..512, dialect 0..2";
         return PCGDO_ERR_UNSUPPORTED;
     }
-    const uint32_t seq_cap = metric_seq_cap(ctx->max_len);
-    const uint32_t tab_entries = 1024;
-    const size_t sg_bytes = ((size_t)a * a * 4 + 15) & ~(size_t)15;
-    const size_t per_warp = 512 + (size_t)seq_cap + 2 * (size_t)tab_entries;
-    int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
-    while (warps > 1 && sg_bytes + (size_t)warps * per_warp > 227 * 1024) --warps;
-    const size_t smem = sg_bytes + (size_t)warps * per_warp;
-    if (smem > 227 * 1024) {
-        ctx->err = "max_len too large for the explicit-matrix kernel's staging window";
-        return PCGDO_ERR_UNSUPPORTED;
-    }
-    size_t arena_words = ctx->arena_words;
-    if (!arena_words) {
-        const size_t per = metric_words_for((uint32_t)ctx->max_len, (uint32_t)ctx->max_len);
-        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 4096);
-    }
-    arena_words = (arena_words + 3) & ~(size_t)3;
-    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
-    size_t ts_words = (explicit_scratch_words(ctx->max_len, a, (size_t)1 << 20) + 3) & ~(size_t)3;
-    const int grid = ctx->sm_count;
+    TableCfg c;
     int rc;
+    if ((rc = table_config(ctx, a, c))) return rc;
+    const uint32_t seq_cap = c.seq_cap, tab_entries = c.tab_entries;
+    const int warps = c.warps, grid = ctx->sm_count;
+    const size_t smem = c.smem, arena_words = c.arena_words, ts_words = c.ts_words;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->tscratch, (size_t)grid * warps * ts_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
@@ -858,7 +908,7 @@ int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, in
     p.b = bd;
     p.a = a;
     p.dialect = dialect;
-    p.kind = memo ? 2 : 0;
+    p.kind = memo ? memo->kind : 0;
     p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
     p.delta = memo ? memo->delta : 1u;
@@ -900,32 +950,16 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     const int a = alphabet;
-    if (a < 2 || a > 32) {
-        ctx->err = "table path: alphabet size must be 2..32";
+    if (a < 2 || a > PCGDO_MAX_ALPHABET) {
+        ctx->err = "table path: alphabet size must be 2..512";
         return PCGDO_ERR_UNSUPPORTED;
     }
-    const uint32_t seq_cap = metric_seq_cap(ctx->max_len);
-    const uint32_t tab_entries = 1024;                     // 2 KB of shared memory per warp for small tables
-    const size_t sg_bytes = ((size_t)a * a * 4 + 15) & ~(size_t)15;
-    const size_t per_warp = 512 + (size_t)seq_cap + 2 * (size_t)tab_entries;
-    int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
-    while (warps > 1 && sg_bytes + (size_t)warps * per_warp > 227 * 1024) --warps;
-    const size_t smem = sg_bytes + (size_t)warps * per_warp;
-    if (smem > 227 * 1024) {
-        ctx->err = "max_len too large for the explicit-matrix kernel's staging window";
-        return PCGDO_ERR_UNSUPPORTED;
-    }
-    size_t arena_words = ctx->arena_words;
-    if (!arena_words) {
-        const size_t per = metric_words_for((uint32_t)ctx->max_len, (uint32_t)ctx->max_len);
-        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 4096);
-    }
-    arena_words = (arena_words + 3) & ~(size_t)3;
-    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
-    size_t ts_words = explicit_scratch_words(ctx->max_len, a, (size_t)1 << 20);
-    ts_words = (ts_words + 3) & ~(size_t)3;
-    const int grid = ctx->sm_count;
+    TableCfg c;
     int rc;
+    if ((rc = table_config(ctx, a, c))) return rc;
+    const uint32_t seq_cap = c.seq_cap, tab_entries = c.tab_entries;
+    const int warps = c.warps, grid = ctx->sm_count;
+    const size_t smem = c.smem, arena_words = c.arena_words, ts_words = c.ts_words;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->tscratch, (size_t)grid * warps * ts_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
@@ -942,7 +976,7 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.b.final_offset = b->final_offset;
     p.a = a;
     p.dialect = dialect;
-    p.kind = memo ? 2 : 0;
+    p.kind = memo ? memo->kind : 0;
     p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
     p.skip_b = getenv("PCGDO_SKIP_B") ? (uint32_t)atoi(getenv("PCGDO_SKIP_B")) : 0u;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;

@@ -37,6 +37,121 @@ __device__ __forceinline__ void ov_explicit(const uint32_t *sg, int a, uint32_t 
     med = bits; cost = best;
 }
 
+// firstLinearNormPairwiseLogic (lib/core/tcm/src/Data/MetricRepresentation.hs:166-190) over Ranged AmbiguityGroup
+// (Bio/Character/Encodable/Dynamic/AmbiguityGroup.hs:154-172, lib/utility/src/Data/Range.hs:100-190): each set is read as
+// the interval lowest..highest set symbol; overlapping intervals intersect at cost 0, disjoint ones give the closed gap
+// between them at its length; fromRange of lb < ub sets symbols lb .. ub-1 ((2^ub - 1) xor (2^lb - 1)), of lb == ub the
+// one symbol.  Returns the median as an inclusive symbol range [mlo, mhi] (empty when mlo > mhi).
+// PINNED: the reference's L1 script costs 3483 / 21851 (tests/golden/custom_alphabet_scripts.json).
+__device__ __forceinline__ uint32_t l1_ranges(int a, int lo0, int hi0, int lo1, int hi1, int &mlo, int &mhi)
+{
+    const bool isect = lo1 <= hi0 && hi1 >= lo0;
+    int nl, nu;
+    if (isect) { nl = max(lo0, lo1); nu = min(hi0, hi1); }
+    else       { nl = min(hi0, hi1); nu = max(lo0, lo1); }
+    if (nu == nl) { mlo = nl; mhi = nl < a ? nl : -1; }
+    else          { mlo = nl; mhi = min(nu - 1, a - 1); }
+    return isect ? 0u : (uint32_t)(nu - nl);
+}
+__device__ __forceinline__ void l1_lohi(uint32_t x, int a, int &lo, int &hi)
+{
+    const int l = x ? __ffs(x) - 1 : a, h = x ? 31 - __clz(x) : 0;
+    lo = min(l, h); hi = max(l, h);
+}
+__device__ __forceinline__ void ov_l1(int a, uint32_t x, uint32_t y, uint32_t &med, uint32_t &cost)
+{
+    int lo0, hi0, lo1, hi1, mlo, mhi;
+    l1_lohi(x, a, lo0, hi0);
+    l1_lohi(y, a, lo1, hi1);
+    cost = l1_ranges(a, lo0, hi0, lo1, hi1, mlo, mhi);
+    med = (mhi < mlo) ? 0u : (uint32_t)((((1ull << (mhi + 1)) - 1ull) ^ ((1ull << mlo) - 1ull)) & 0xffffffffull);
+}
+
+// ---- alphabets of more than 32 symbols: an element is W = ceil(a / 32) consecutive words, bit i of the set = bit i % 32
+// of word i / 32; offsets and lengths keep counting elements.  Ordering of elements (measureCharacters' tie-break) is
+// that of unsigned naturals, most significant word first, like bv-little's Ord.  Plain (generic) loads: an operand may
+// be the gap element staged in shared memory.
+__device__ __forceinline__ int w_cmp(const uint32_t *x, const uint32_t *y, int W)
+{
+    for (int w = W - 1; w >= 0; --w) {
+        const uint32_t a = x[w], b = y[w];
+        if (a != b) return a < b ? -1 : 1;
+    }
+    return 0;
+}
+__device__ __forceinline__ bool w_eq(const uint32_t *x, const uint32_t *y, int W)
+{
+    for (int w = 0; w < W; ++w) if (x[w] != y[w]) return false;
+    return true;
+}
+__device__ __forceinline__ bool w_zero(const uint32_t *x, int W)
+{
+    for (int w = 0; w < W; ++w) if (x[w]) return false;
+    return true;
+}
+__device__ __forceinline__ bool w_test(const uint32_t *x, int bit) { return (x[bit >> 5] >> (bit & 31)) & 1u; }
+__device__ __forceinline__ uint32_t w_hash(const uint32_t *x, int W)
+{
+    uint32_t h = 0x811C9DC5u;
+    for (int w = 0; w < W; ++w) h = (h ^ x[w]) * 0x01000193u;
+    return (h * 0x9E3779B1u) >> 7;
+}
+__device__ __forceinline__ void w_lohi(const uint32_t *x, int W, int a, int &lo, int &hi)
+{
+    int l = a, h = 0;
+    bool any = false;
+    for (int w = 0; w < W; ++w) {
+        const uint32_t v = x[w];
+        if (v) {
+            if (!any) { l = 32 * w + __ffs(v) - 1; any = true; }
+            h = 32 * w + 31 - __clz(v);
+        }
+    }
+    lo = min(l, h); hi = max(l, h);
+}
+// min over the set symbols j of x of row[j]
+__device__ __forceinline__ uint32_t w_rowmin(const uint32_t *row, const uint32_t *x, int W)
+{
+    uint32_t mn = 0xffffffffu;
+    for (int w = 0; w < W; ++w)
+        for (uint32_t t = x[w]; t; t &= t - 1) mn = min(mn, row[32 * w + __ffs(t) - 1]);
+    return mn;
+}
+// the overlap of two W-word sets; med (W words, may be NULL) receives the median.  kind: 0 discrete, 1 L1, 2 explicit.
+__device__ __forceinline__ uint32_t w_overlap(int kind, const uint32_t *sg, int a, int W, const uint32_t *x, const uint32_t *y,
+                                              uint32_t *med)
+{
+    if (kind == 0) {
+        bool inter = false;
+        for (int w = 0; w < W; ++w) inter = inter || (x[w] & y[w]);
+        if (med) for (int w = 0; w < W; ++w) med[w] = inter ? (x[w] & y[w]) : (x[w] | y[w]);
+        return inter ? 0u : 1u;
+    }
+    if (kind == 1) {
+        int lo0, hi0, lo1, hi1, mlo, mhi;
+        w_lohi(x, W, a, lo0, hi0);
+        w_lohi(y, W, a, lo1, hi1);
+        const uint32_t c = l1_ranges(a, lo0, hi0, lo1, hi1, mlo, mhi);
+        if (med)
+            for (int w = 0; w < W; ++w) {
+                const int b0 = max(mlo, 32 * w) - 32 * w, b1 = min(mhi, 32 * w + 31) - 32 * w;
+                med[w] = (b1 < b0) ? 0u : (uint32_t)((((1ull << (b1 + 1)) - 1ull) ^ ((1ull << b0) - 1ull)) & 0xffffffffull);
+            }
+        return c;
+    }
+    uint32_t best = 0xffffffffu;
+    if (med) for (int w = 0; w < W; ++w) med[w] = 0u;
+    for (int s = 0; s < a; ++s) {
+        const uint32_t *row = sg + (size_t)s * a;
+        const uint32_t c = w_rowmin(row, x, W) + w_rowmin(row, y, W);
+        if (c < best) {
+            best = c;
+            if (med) { for (int w = 0; w < W; ++w) med[w] = 0u; med[s >> 5] = 1u << (s & 31); }
+        } else if (c == best && med) med[s >> 5] |= 1u << (s & 31);
+    }
+    return best;
+}
+
 __global__ void overlap2d_kernel(const uint32_t *sigma, int a, size_t n, const uint32_t *e1, const uint32_t *e2,
                                  uint32_t *med, uint32_t *cost)
 {
@@ -348,6 +463,7 @@ __device__ __forceinline__ uint32_t x_emit(const uint32_t *sg, int a, int kind, 
             uint32_t md, cc;
             const uint32_t xx = x ? x : gap, yy = y ? y : gap;
             if (kind == 0) md = (xx & yy) ? (xx & yy) : (xx | yy);       // discreteMetricPairwiseLogic
+            else if (kind == 1) ov_l1(a, xx, yy, md, cc);
             else ov_explicit(sg, a, xx, yy, md, cc);
             if (om) om[c] = md;
             if (o1) o1[c] = swapped ? y : x;
@@ -365,6 +481,99 @@ __device__ __forceinline__ uint32_t x_emit(const uint32_t *sg, int a, int kind, 
         base_j += __popc(bs);
     }
     return base_u;
+}
+
+constexpr int kMaxW = 16;          // alphabets of up to 512 symbols
+
+// x_emit for W-word elements; gapw = the gap element (W words).  Outputs are W words per position.
+__device__ __forceinline__ uint32_t x_emit_w(const uint32_t *sg, int a, int W, int kind, const uint32_t *pL, const uint32_t *pS,
+                                             const uint32_t *gapw, const uint32_t *ops, uint32_t nal, bool swapped,
+                                             uint32_t *om, uint32_t *o1, uint32_t *o2, int lane, uint32_t *ou, uint32_t ucap)
+{
+    uint32_t base_i = 0, base_j = 0, base_u = 0;
+    for (uint32_t c0 = 0; c0 < nal; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        uint32_t code = 3u;
+        if (c < nal) {
+            const uint32_t r = nal - 1u - c;
+            code = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
+        }
+        const unsigned bl = __ballot_sync(kFullM, code < 2u), bs = __ballot_sync(kFullM, code == 0u || code == 2u);
+        const unsigned lt = (1u << lane) - 1u;
+        const uint32_t il = base_i + __popc(bl & lt), js = base_j + __popc(bs & lt);
+        bool keep = false;
+        uint32_t md[kMaxW];
+        if (c < nal) {
+            const uint32_t *y = code < 2u ? pL + (size_t)il * W : nullptr;
+            const uint32_t *x = (code == 0u || code == 2u) ? pS + (size_t)js * W : nullptr;
+            if (y && w_zero(y, W)) y = nullptr;
+            if (x && w_zero(x, W)) x = nullptr;
+            w_overlap(kind, sg, a, W, x ? x : gapw, y ? y : gapw, md);
+            keep = false;
+            for (int w = 0; w < W; ++w) {
+                const uint32_t xv = x ? x[w] : 0u, yv = y ? y[w] : 0u;
+                if (om) om[(size_t)c * W + w] = md[w];
+                if (o1) o1[(size_t)c * W + w] = swapped ? yv : xv;
+                if (o2) o2[(size_t)c * W + w] = swapped ? xv : yv;
+                keep = keep || md[w] != gapw[w];
+            }
+        }
+        if (ou) {       // deleteGaps on the medians: what the parent's alignment consumes
+            const unsigned bk = __ballot_sync(kFullM, keep);
+            const uint32_t pos = base_u + __popc(bk & lt);
+            if (keep && pos < ucap)
+                for (int w = 0; w < W; ++w) ou[(size_t)pos * W + w] = md[w];
+            base_u += __popc(bk);
+        }
+        base_i += __popc(bl);
+        base_j += __popc(bs);
+    }
+    return base_u;
+}
+
+// x_number for W-word elements: the hash key of a slot is 1 + the position of the first string element that claimed it;
+// el[r] = that position.
+__device__ __forceinline__ uint32_t x_number_w(const uint32_t *str, int len, int W, uint32_t H, uint32_t *hk, uint32_t *hv,
+                                               uint32_t *el, uint32_t *idx, int lane)
+{
+    for (uint32_t i = lane; i < H; i += 32) hk[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t *e = str + (size_t)i * W;
+        if (w_zero(e, W)) continue;
+        uint32_t h = w_hash(e, W) & (H - 1);
+        for (;;) {
+            const uint32_t old = atomicCAS(hk + h, 0u, (uint32_t)i + 1u);
+            if (old == 0u || w_eq(str + (size_t)(old - 1u) * W, e, W)) break;
+            h = (h + 1) & (H - 1);
+        }
+    }
+    __syncwarp();
+    uint32_t D = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < H; base += 32) {
+        const uint32_t k = __ldcg(hk + base + lane);
+        const unsigned bal = __ballot_sync(kFullM, k != 0u);
+        if (k) {
+            const uint32_t r = D + __popc(bal & lt);
+            hv[base + lane] = r + 2u;
+            el[r] = k - 1u;
+        }
+        D += __popc(bal);
+    }
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t *e = str + (size_t)i * W;
+        uint32_t v = 0;
+        if (!w_zero(e, W)) {
+            uint32_t h = w_hash(e, W) & (H - 1);
+            while (!w_eq(str + (size_t)(__ldcg(hk + h) - 1u) * W, e, W)) h = (h + 1) & (H - 1);
+            v = hv[h];
+        }
+        idx[i] = v;
+    }
+    __syncwarp();
+    return D;
 }
 
 // fewer fill variants = smaller instruction footprint when every warp walks through the doubling schedule
@@ -430,24 +639,32 @@ __device__ __forceinline__ uint32_t x_number(const uint32_t *str, int len, uint3
 
 extern __shared__ __align__(16) char x_smem[];
 
+template <bool WIDE>
 __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParams p)
 {
     const MetricBatchDev &b = p.b;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int a = p.a;
-    uint32_t *sg = reinterpret_cast<uint32_t *>(x_smem);                       // sigma[a*a]
-    const uint32_t sg_bytes = ((uint32_t)(a * a) * 4u + 15u) & ~15u;
+    const int W = WIDE ? (a + 31) >> 5 : 1;                 // words per element
+    // narrow: sigma[a*a] staged in shared memory; wide: sigma stays in global memory (L2), the first 64 bytes of
+    // shared memory hold the gap element
+    uint32_t *sg = WIDE ? const_cast<uint32_t *>(p.sigma) : reinterpret_cast<uint32_t *>(x_smem);
+    uint32_t *gapw = reinterpret_cast<uint32_t *>(x_smem);
+    const uint32_t sg_bytes = WIDE ? 64u : (((uint32_t)(a * a) * 4u + 15u) & ~15u);
     const uint32_t per_warp = 512u + p.seq_cap + 2u * p.smem_tab_entries;
     uint32_t *s_meta = reinterpret_cast<uint32_t *>(x_smem + sg_bytes + (size_t)warp * per_warp);
     uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64, *s_geo = s_meta + 96;
     uint32_t *seq = s_meta + 128;
     int16_t *stab = reinterpret_cast<int16_t *>(reinterpret_cast<char *>(seq) + p.seq_cap);
-    if (p.kind != 0)
+    if (WIDE) {
+        if (threadIdx.x < kMaxW) gapw[threadIdx.x] = ((a - 1) >> 5) == (int)threadIdx.x ? 1u << ((a - 1) & 31) : 0u;
+    } else if (p.kind == 2) {
         for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = p.sigma[i];
+    }
     __syncthreads();
 
-    const uint32_t gap = 1u << (a - 1);
-    const uint32_t mask = a >= 32 ? 0xffffffffu : ((1u << a) - 1u);
+    const uint32_t gap = WIDE ? 0u : 1u << ((a - 1) & 31);                      // narrow only
+    const uint32_t mask = (WIDE || a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
     const int G = p.pairs_per_warp;
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.arena_words;
@@ -470,18 +687,24 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
             for (; pi < npw; ++pi) {
                 const uint32_t k = p.in_list ? p.in_list[base + pi] : base + pi;
                 const uint32_t n1 = b.len1[k], n2 = b.len2[k];
-                const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                const uint32_t *p1 = b.elems + b.off1[k] * (uint64_t)W, *p2 = b.elems + b.off2[k] * (uint64_t)W;
                 bool swapped = n1 > n2;                     // measureCharacters on the median strings
                 if (n1 == n2) {
                     for (uint32_t bs = 0; bs < n1; bs += 32) {
                         const uint32_t i = bs + lane;
-                        uint32_t x = 0, y = 0;
-                        if (i < n1) { x = __ldg(p1 + i); y = __ldg(p2 + i); }
-                        const unsigned df = __ballot_sync(kFullM, x != y);
-                        if (df) {
-                            const int src = __ffs(df) - 1;
-                            swapped = __shfl_sync(kFullM, x, src) > __shfl_sync(kFullM, y, src);
-                            break;
+                        if constexpr (WIDE) {
+                            const int c = i < n1 ? w_cmp(p1 + (size_t)i * W, p2 + (size_t)i * W, W) : 0;
+                            const unsigned df = __ballot_sync(kFullM, c != 0);
+                            if (df) { swapped = __shfl_sync(kFullM, c, __ffs(df) - 1) > 0; break; }
+                        } else {
+                            uint32_t x = 0, y = 0;
+                            if (i < n1) { x = __ldg(p1 + i); y = __ldg(p2 + i); }
+                            const unsigned df = __ballot_sync(kFullM, x != y);
+                            if (df) {
+                                const int src = __ffs(df) - 1;
+                                swapped = __shfl_sync(kFullM, x, src) > __shfl_sync(kFullM, y, src);
+                                break;
+                            }
                         }
                     }
                 }
@@ -489,8 +712,13 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 const int n = (int)(swapped ? n1 : n2), m = (int)(swapped ? n2 : n1);     // longer, lesser
                 const int lg = n + 1, sh = m + 1;
                 uint32_t gcnt = 0;
-                for (int i = lane; i < n; i += 32) gcnt += (__ldg(pL + i) & gap) != 0u;
-                for (int j = lane; j < m; j += 32) gcnt += (__ldg(pS + j) & gap) != 0u;
+                if constexpr (WIDE) {
+                    for (int i = lane; i < n; i += 32) gcnt += w_test(pL + (size_t)i * W, a - 1);
+                    for (int j = lane; j < m; j += 32) gcnt += w_test(pS + (size_t)j * W, a - 1);
+                } else {
+                    for (int i = lane; i < n; i += 32) gcnt += (__ldg(pL + i) & gap) != 0u;
+                    for (int j = lane; j < m; j += 32) gcnt += (__ldg(pS + j) & gap) != 0u;
+                }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) gcnt += __shfl_xor_sync(kFullM, gcnt, d);
                 const long long Gc = gcnt, qd = n - m + 1, delta = p.delta;
@@ -515,8 +743,13 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 const char *gtab = nullptr;
                 uint32_t tab32 = 0;
                 if (ok) {
-                    DL = x_number(pL, n, mask, HL, hkL, hvL, elL, idxL, lane);
-                    DS = x_number(pS, m, mask, HS, hkS, hvS, elS, idxS, lane);
+                    if constexpr (WIDE) {
+                        DL = x_number_w(pL, n, W, HL, hkL, hvL, elL, idxL, lane);
+                        DS = x_number_w(pS, m, W, HS, hkS, hvS, elS, idxS, lane);
+                    } else {
+                        DL = x_number(pL, n, mask, HL, hkL, hvL, elL, idxL, lane);
+                        DS = x_number(pS, m, mask, HS, hkS, hvS, elS, idxS, lane);
+                    }
                     Wt = DS + 2u;
                     entries = (DL + 2u) * Wt;
                     gtable = entries > p.smem_tab_entries;
@@ -524,10 +757,31 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 }
                 uint32_t bad = 0;
                 int emin = -1, emax = -1;                   // range of the finite table entries (leading gap: -1)
-                if (ok && p.kind == 0) {
-                    // discrete metric (Data/MetricRepresentation.hs:116-128): cost(x, y) = x & y ? 0 : 1 — no profiles
-                    for (uint32_t d = lane; d < DL + 2u; d += 32) cL[d] = (d >= 2u && !(elL[d - 2u] & gap)) ? 1u : 0u;
-                    for (uint32_t d = lane; d < DS + 2u; d += 32) gS[d] = (d >= 2u && !(elS[d - 2u] & gap)) ? 1u : 0u;
+                if (ok && p.kind != 2) {
+                    // closed forms — discrete metric (Data/MetricRepresentation.hs:116-128): cost(x, y) = x & y ? 0 : 1;
+                    // L1 norm (:166-190): interval logic — no profiles.  An element is elL[d] (narrow) or the string
+                    // element at position elL[d] (wide).
+                    auto ovc = [&](uint32_t dl, uint32_t ds, bool &is_gap) -> uint32_t {   // dl / ds: 1 = the gap element
+                        if constexpr (WIDE) {
+                            const uint32_t *x = dl == 1u ? gapw : pL + (size_t)elL[dl - 2u] * W;
+                            const uint32_t *y = ds == 1u ? gapw : pS + (size_t)elS[ds - 2u] * W;
+                            uint32_t md[kMaxW];
+                            const uint32_t c = w_overlap(p.kind, sg, a, W, x, y, md);
+                            is_gap = true;
+                            for (int w = 0; w < W; ++w) is_gap = is_gap && md[w] == gapw[w];
+                            return c;
+                        } else {
+                            const uint32_t x = dl == 1u ? gap : elL[dl - 2u], y = ds == 1u ? gap : elS[ds - 2u];
+                            uint32_t md, c;
+                            if (p.kind == 0) { const uint32_t t2 = x & y; md = t2 ? t2 : (x | y); c = t2 ? 0u : 1u; }
+                            else ov_l1(a, x, y, md, c);
+                            is_gap = md == gap;
+                            return c;
+                        }
+                    };
+                    bool ig;
+                    for (uint32_t d = lane; d < DL + 2u; d += 32) cL[d] = d >= 2u ? ovc(d, 1u, ig) : 0u;
+                    for (uint32_t d = lane; d < DS + 2u; d += 32) gS[d] = d >= 2u ? ovc(1u, d, ig) : 0u;
                     __syncwarp();
                     int16_t *tab = gtable ? reinterpret_cast<int16_t *>(tail) : stab;
                     for (uint32_t t = lane; t < entries; t += 32) {
@@ -536,12 +790,17 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                         if (dl == 0u || ds == 0u) v = kBigSub;
                         else if (dl == 1u || ds == 1u) v = -1;
                         else {
-                            const uint32_t x = elL[dl - 2u], y = elS[ds - 2u], t2 = x & y;
-                            v = 4 * ((t2 ? 0 : 1) - (int)cL[dl] - (int)gS[ds]) - 1 + ((s2 && t2 == gap) ? 1 : 0);
+                            bool is_gap;
+                            const long long c = ovc(dl, ds, is_gap);
+                            const long long f = 4ll * (c - (long long)cL[dl] - (long long)gS[ds]) - 1ll + ((s2 && is_gap) ? 1ll : 0ll);
+                            if (f < -32000ll || f >= (long long)kBigSub) bad = 1;
+                            v = (int)f;
                             emin = min(emin, v); emax = max(emax, v);
                         }
                         tab[t] = (int16_t)v;
                     }
+                    bad = __any_sync(kFullM, bad != 0u) ? 1u : 0u;
+                    if (bad) ok = false;
                     gtab = reinterpret_cast<const char *>(tail);
                     tab32 = (uint32_t)__cvta_generic_to_shared(stab);
                     __syncwarp();
@@ -549,13 +808,15 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     for (uint32_t t = lane; t < DL * (uint32_t)a; t += 32) {
                         const uint32_t d = t / a, s = t - d * a;
                         uint32_t mn = 0xffffffffu;
-                        for (uint32_t x = elL[d]; x; x &= x - 1) mn = min(mn, sg[s * a + __ffs(x) - 1]);
+                        if constexpr (WIDE) mn = w_rowmin(sg + (size_t)s * a, pL + (size_t)elL[d] * W, W);
+                        else for (uint32_t x = elL[d]; x; x &= x - 1) mn = min(mn, sg[s * a + __ffs(x) - 1]);
                         mxL[t] = mn;
                     }
                     for (uint32_t t = lane; t < DS * (uint32_t)a; t += 32) {
                         const uint32_t d = t / a, s = t - d * a;
                         uint32_t mn = 0xffffffffu;
-                        for (uint32_t x = elS[d]; x; x &= x - 1) mn = min(mn, sg[s * a + __ffs(x) - 1]);
+                        if constexpr (WIDE) mn = w_rowmin(sg + (size_t)s * a, pS + (size_t)elS[d] * W, W);
+                        else for (uint32_t x = elS[d]; x; x &= x - 1) mn = min(mn, sg[s * a + __ffs(x) - 1]);
                         mxS[t] = mn;
                     }
                     __syncwarp();
@@ -584,14 +845,15 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                         else if (dl == 1u || ds == 1u) v = -1;
                         else {
                             const uint32_t *ml = mxL + (size_t)(dl - 2u) * a, *ms = mxS + (size_t)(ds - 2u) * a;
-                            uint32_t best = 0xffffffffu, bits = 0;
+                            uint32_t best = 0xffffffffu;
+                            int nmin = 0, smin = -1;                 // median == {gap}  <=>  the only minimal symbol is a-1
                             for (int s = 0; s < a; ++s) {
                                 const uint32_t c = ml[s] + ms[s];
-                                if (c < best) { best = c; bits = 1u << s; }
-                                else if (c == best) bits |= 1u << s;
+                                if (c < best) { best = c; nmin = 1; smin = s; }
+                                else if (c == best) ++nmin;
                             }
                             const long long f = 4ll * ((long long)best - (long long)cL[dl] - (long long)gS[ds]) - 1ll +
-                                                ((s2 && bits == gap) ? 1ll : 0ll);
+                                                ((s2 && nmin == 1 && smin == a - 1) ? 1ll : 0ll);
                             if (f < -32000ll || f >= (long long)kBigSub) bad = 1;
                             v = (int)f;
                             emin = min(emin, v); emax = max(emax, v);
@@ -733,16 +995,22 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     if (!(s_flags[pe] & 2u)) continue;
                     const uint32_t k = p.in_list ? p.in_list[base + pe] : base + pe;
                     const bool swapped = s_flags[pe] & 1u;
-                    const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                    const uint32_t *p1 = b.elems + b.off1[k] * (uint64_t)W, *p2 = b.elems + b.off2[k] * (uint64_t)W;
                     const int n = (int)(swapped ? b.len1[k] : b.len2[k]), m = (int)(swapped ? b.len2[k] : b.len1[k]);
                     const MGeom g = make_mgeom(n + 1, m + 1, (int)(int16_t)(s_geo[pe] & 0xffffu), (int)(int16_t)(s_geo[pe] >> 16));
                     const int B = x_choose_b(g.wb, p.skip_b);
                     const uint32_t *ops = arena + s_off[pe] + m_dir_words(g, B);
-                    const uint64_t oo = b.out_off ? b.out_off[k] : 0;
-                    const uint32_t nu = x_emit(sg, a, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe],
-                                               swapped, b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
-                                               b.out_a2 ? b.out_a2 + oo : nullptr, lane,
-                                               b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+                    const uint64_t oo = (b.out_off ? b.out_off[k] : 0) * (uint64_t)W;
+                    uint32_t *ou = b.out_ungapped ? b.out_ungapped + b.out_uoff[k] * (uint64_t)W : nullptr;
+                    uint32_t nu;
+                    if constexpr (WIDE)
+                        nu = x_emit_w(sg, a, W, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gapw, ops, s_nal[pe], swapped,
+                                      b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
+                                      b.out_a2 ? b.out_a2 + oo : nullptr, lane, ou, b.ucap);
+                    else
+                        nu = x_emit(sg, a, p.kind, swapped ? p1 : p2, swapped ? p2 : p1, gap, mask, ops, s_nal[pe],
+                                    swapped, b.out_med ? b.out_med + oo : nullptr, b.out_a1 ? b.out_a1 + oo : nullptr,
+                                    b.out_a2 ? b.out_a2 + oo : nullptr, lane, ou, b.ucap);
                     if (b.out_ungapped && lane == 0) {
                         b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
                         if (nu > b.ucap) atomicAdd(p.overflow_count + 2, 1u);   // node string does not fit its slot
@@ -769,11 +1037,14 @@ cudaError_t launch_explicit(const ExplicitParams &p, int grid, int block, size_t
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(do_explicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(do_explicit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(do_explicit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    do_explicit_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    if (p.a > 32) do_explicit_kernel<true><<<grid, block, smem_bytes, stream>>>(p);
+    else          do_explicit_kernel<false><<<grid, block, smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 

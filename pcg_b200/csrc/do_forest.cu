@@ -45,7 +45,7 @@ struct pcgdo_forest {
     std::vector<std::pair<size_t, size_t>> up_levels;         // pre-order levels (by depth) of directed-datum jobs
     std::pair<size_t, size_t> edge_items{0, 0};
     DevBuf edge_total, edge_local, char_min;                  // i64 / i32 [n_trees*n_chars*n_edges], i64 [n_trees*n_chars]
-    uint32_t elem_bytes = 1;             // 1: dense-TCM alphabets (do_linear.cu); 4: large alphabets (do_explicit.cu)
+    uint32_t elem_bytes = 1;             // 1: dense-TCM alphabets (do_linear.cu); 4 * ceil(a/32): large alphabets (do_explicit.cu)
     const pcgdo_memo *memo = nullptr;    // elem_bytes 4: explicit matrix, or NULL = discrete metric over `alphabet` symbols
     int alphabet = 0, dialect = 2;
     bool keep_edges = false;             // edge data (median of rooting on each edge) kept for Wagner edge trials
@@ -237,8 +237,10 @@ extern "C" int pcgdo_forest_create32(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t 
                                      uint32_t node_cap, const int32_t *children, const pcgdo_memo *memo, int alphabet,
                                      int dialect, pcgdo_forest **out)
 {
-    if (dialect < 0 || dialect > 2 || (!memo && (alphabet < 2 || alphabet > 32))) return PCGDO_ERR_ARG;
-    int rc = forest_create_impl(ctx, n_trees, n_taxa, n_chars, node_cap, children, 4, out);
+    if (dialect < 0 || dialect > 2 || (!memo && (alphabet < 2 || alphabet > PCGDO_MAX_ALPHABET))) return PCGDO_ERR_ARG;
+    // elements are ceil(a / 32) 32-bit words (one word up to 32 symbols)
+    const uint32_t a = memo ? pcgdo_memo_alphabet(memo) : (uint32_t)alphabet;
+    int rc = forest_create_impl(ctx, n_trees, n_taxa, n_chars, node_cap, children, 4u * ((a + 31u) / 32u), out);
     if (rc) return rc;
     (*out)->memo = memo;
     (*out)->alphabet = alphabet;
@@ -386,7 +388,7 @@ extern "C" int pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *F, const ui
 extern "C" int pcgdo_forest_set_leaves32(pcgdo_ctx *ctx, pcgdo_forest *F, const uint32_t *elems, const uint64_t *off,
                                          const uint32_t *len)
 {
-    return forest_set_leaves_impl(ctx, F, elems, off, len, 4);
+    return forest_set_leaves_impl(ctx, F, elems, off, len, F ? F->elem_bytes : 4);
 }
 
 // Enqueue one batch of forest jobs: mode 0 = data (ungapped median of the result kept in its slot, totals
@@ -406,7 +408,7 @@ static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *
                                                    (uint32_t *)F->blen2.p);
         CK(cudaGetLastError());
         int rc;
-        if (F->elem_bytes == 4) {
+        if (F->elem_bytes >= 4) {
             MetricBatchDev md{};
             md.n_pairs = (uint32_t)n_pairs;
             md.elems = (const uint32_t *)F->store.p;
@@ -470,7 +472,7 @@ static int forest_check(pcgdo_ctx *ctx, pcgdo_forest *F, const LinearParams &p, 
     unsigned int h[11] = {0};
     CK(cudaMemcpyAsync(h, p.counter, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (F->elem_bytes == 4) {           // table kernel: [8] pairs beyond its limits, [10] node strings beyond their slot
+    if (F->elem_bytes >= 4) {           // table kernel: [8] pairs beyond its limits, [10] node strings beyond their slot
         h[9] = h[10];
         h[3] = 0;
     }

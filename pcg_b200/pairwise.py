@@ -250,30 +250,38 @@ def metric_do_batch(ctx: Context, alphabet, dialect: int, first: Sequence[np.nda
                     second: Sequence[np.ndarray]) -> MetricResult:
     """``naiveDO`` / ``ukkonenDO`` / ``unboxedUkkonenFullSpaceDO`` on median strings (uint32 ambiguity sets), one
     launch for the whole batch.  ``alphabet``: an int selects the discrete metric over that many symbols
-    (``discreteMetricPairwiseLogic``); a ``Memo`` selects its explicit matrix (the reference's memoized
-    ``getMedianAndCost2D`` path, ``extractPairwiseTransitionCostMatrix``, Bio/Metadata/Dynamic/Internal.hs:352-374)."""
+    (``discreteMetricPairwiseLogic``); a ``Memo`` selects its overlap function — the explicit matrix (the reference's
+    memoized ``getMedianAndCost2D`` path, ``extractPairwiseTransitionCostMatrix``, Bio/Metadata/Dynamic/Internal.hs:352-374)
+    or the closed form PCG's TCM diagnosis picks.  Beyond 32 symbols strings are (n, W) uint32 arrays, W = ceil(a / 32),
+    and so are the three outputs of ``MetricResult.pair``."""
     n = len(first)
+    a = alphabet if isinstance(alphabet, int) else alphabet.a
+    W = (a + 31) // 32
+    first = [np.asarray(x, np.uint32).reshape(-1, W) for x in first]
+    second = [np.asarray(x, np.uint32).reshape(-1, W) for x in second]
     len1 = np.fromiter((len(x) for x in first), dtype=np.uint32, count=n)
     len2 = np.fromiter((len(x) for x in second), dtype=np.uint32, count=n)
     tot = len1.astype(np.uint64) + len2.astype(np.uint64)
     starts = np.concatenate([[0], np.cumsum(tot)]).astype(np.uint64)
     off1 = starts[:-1].copy()
     off2 = off1 + len1
-    elems = np.zeros(int(starts[-1]) + 4, np.uint32)
+    elems = np.zeros((int(starts[-1]) + 4, W), np.uint32)
     for k in range(n):
         elems[int(off1[k]):int(off1[k]) + int(len1[k])] = first[k]
         elems[int(off2[k]):int(off2[k]) + int(len2[k])] = second[k]
     out_off = off1.copy()
     cnt = int(starts[-1]) + 4
-    med, a1, a2 = (np.zeros(cnt, np.uint32) for _ in range(3))
+    med, a1, a2 = (np.zeros((cnt, W), np.uint32) for _ in range(3))
     cost = np.zeros(n, np.int32)
     out_len = np.zeros(n, np.uint32)
     cells = np.zeros(n, np.uint64)
     fo = np.zeros(n, np.int32)
-    b = Batch32(n, _p(elems), elems.size, _p(off1), _p(off2), _p(len1), _p(len2), _p(out_off), cnt,
+    b = Batch32(n, _p(elems), elems.size, _p(off1), _p(off2), _p(len1), _p(len2), _p(out_off), cnt * W,
                 _p(med), _p(a1), _p(a2), _p(out_len), _p(cost), _p(cells), _p(fo))
     if isinstance(alphabet, int):
         ctx.check(ctx.lib.pcgdo_metric_batch_host(ctx.h, alphabet, dialect, C.byref(b)), "pcgdo_metric_batch_host")
     else:
         ctx.check(ctx.lib.pcgdo_explicit_batch_host(ctx.h, alphabet.h, dialect, C.byref(b)), "pcgdo_explicit_batch_host")
+    if W == 1:
+        med, a1, a2 = med.reshape(-1), a1.reshape(-1), a2.reshape(-1)
     return MetricResult(cost, out_len, med, a1, a2, cells, fo, out_off)
