@@ -128,7 +128,18 @@ typedef struct pcgdo_batch {
     uint32_t       *out_len;
     int32_t        *cost;
     uint64_t       *cells;
+    /* HOST entry point only, may be NULL.  Non-NULL selects COMPACT TRANSFER: out_off[] still reserves each pair's
+     * capacity (and must be monotone), but only the bytes the alignments produced cross the PCIe link, packed per
+     * pipelined chunk inside the chunk's reserved region; pair k's three outputs are then at out_off_actual[k] of
+     * out_gapped / out_slot1 / out_slot2 — not at out_off[k].  With pinned out arrays (pcgdo_host_alloc, or any
+     * cudaHostAlloc'ed / registered memory) the kernel stores them there directly over PCIe, whole 128-byte lines at a time. */
+    uint64_t       *out_off_actual;
 } pcgdo_batch;
+
+/* Pinned, mapped host memory for batch buffers (cudaHostAlloc): transfers to and from it run at the full PCIe rate,
+ * and with out_off_actual set the kernel writes the aligned strings straight into it (zero-copy, no staging). */
+void *pcgdo_host_alloc(pcgdo_ctx *ctx, size_t bytes);
+void  pcgdo_host_free(pcgdo_ctx *ctx, void *p);
 
 /* Enqueue on `cuda_stream` (a cudaStream_t passed as void*, NULL = the context's stream);
  * asynchronous unless a pair overflows the fast path's scratch. */

@@ -20,7 +20,7 @@ _i32p = C.POINTER(C.c_int32)
 # every symbol include/pcg_do_b200.h declares
 EXPORTED_SYMBOLS = [
     "setUp2dCostMtx", "align2d", "align2dAffine",
-    "pcgdo_create", "pcgdo_destroy", "pcgdo_last_error", "pcgdo_configure",
+    "pcgdo_create", "pcgdo_destroy", "pcgdo_last_error", "pcgdo_configure", "pcgdo_host_alloc", "pcgdo_host_free",
     "pcgdo_tcm_create", "pcgdo_tcm_destroy",
     "pcgdo_align2d_batch_device", "pcgdo_align2d_batch_host", "pcgdo_last_kernel_ms",
     "pcgdo_configure_ex", "pcgdo_int32_peak",
@@ -55,7 +55,7 @@ class Batch(C.Structure):
                 ("off1", C.c_void_p), ("off2", C.c_void_p), ("len1", C.c_void_p), ("len2", C.c_void_p),
                 ("out_off", C.c_void_p), ("out_bytes", C.c_size_t),
                 ("out_gapped", C.c_void_p), ("out_slot1", C.c_void_p), ("out_slot2", C.c_void_p),
-                ("out_len", C.c_void_p), ("cost", C.c_void_p), ("cells", C.c_void_p)]
+                ("out_len", C.c_void_p), ("cost", C.c_void_p), ("cells", C.c_void_p), ("out_off_actual", C.c_void_p)]
 
 
 class Batch32(C.Structure):
@@ -95,6 +95,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_last_error.restype = C.c_char_p
     L.pcgdo_last_error.argtypes = [C.c_void_p]
     L.pcgdo_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.pcgdo_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
+    L.pcgdo_host_alloc.restype = C.c_void_p
+    L.pcgdo_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_host_free.restype = None
     L.pcgdo_configure_ex.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     L.pcgdo_tcm_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_uint, C.POINTER(C.c_void_p)]
     L.pcgdo_tcm_destroy.argtypes = [C.c_void_p, C.c_void_p]
@@ -188,6 +192,19 @@ class Context:
     def configure(self, pairs_per_warp=0, warps_per_cta=0, max_len=0, max_b=0, arena_words=0):
         self.check(self.lib.pcgdo_configure(self.h, pairs_per_warp, warps_per_cta, max_len), "pcgdo_configure")
         self.check(self.lib.pcgdo_configure_ex(self.h, max_b, arena_words), "pcgdo_configure_ex")
+
+    def pinned_empty(self, count: int, dtype=np.uint8) -> np.ndarray:
+        """A numpy array over pinned, mapped host memory (pcgdo_host_alloc); freed with the array."""
+        import weakref
+        nbytes = int(count) * np.dtype(dtype).itemsize
+        p = self.lib.pcgdo_host_alloc(self.h, nbytes)
+        if not p:
+            raise BackendError(f"pcgdo_host_alloc({nbytes}) failed: {self.lib.pcgdo_last_error(self.h).decode()}")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(count))
+        lib, h = self.lib, self.h
+        weakref.finalize(buf, lambda: lib.pcgdo_host_free(h, p))
+        return arr
 
     def tcm(self, sigma, gap_open: int = 0, affine_variant: int = 0) -> "Tcm":
         return Tcm(self, sigma, gap_open, affine_variant)

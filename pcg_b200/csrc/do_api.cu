@@ -6,8 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -105,13 +107,34 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
-                      &ctx->d_olen, &ctx->d_cost, &ctx->d_cells};
+                      &ctx->d_olen, &ctx->d_cost, &ctx->d_cells, &ctx->d_stage, &ctx->d_actual, &ctx->d_total};
+    if (ctx->h_total) cudaFreeHost(ctx->h_total);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// Pinned, mapped host memory for the caller's batch buffers: copies to and from it run at full PCIe rate, and the
+// compact transfer writes aligned strings straight into it from the kernel (no staging).
+extern "C" void *pcgdo_host_alloc(pcgdo_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        ctx->err = std::string("pcgdo_host_alloc: ") + cudaGetErrorString(cudaGetLastError());
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void pcgdo_host_free(pcgdo_ctx *ctx, void *p)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" const char *pcgdo_last_error(const pcgdo_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1110,6 +1133,8 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
 {
     if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
     if (b->n_pairs == 0) return PCGDO_OK;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto ms_since_entry = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
     CK(cudaSetDevice(ctx->device));
     const size_t n = b->n_pairs;
     const bool want_str = b->out_gapped || b->out_slot1 || b->out_slot2;
@@ -1153,15 +1178,57 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     // the host buffers; chunk c+1 is copied in and chunk c-1 copied out while chunk c is aligned
     // (three streams, PCIe is full duplex).  Needs monotone layouts, which the packers produce; anything
     // else, and any pair that overflows the warp kernels, takes the plain path below.
-    const size_t chunk = ctx->host_chunk_pairs ? ctx->host_chunk_pairs : 65536;
+    size_t chunk = ctx->host_chunk_pairs ? ctx->host_chunk_pairs : 65536;
+    if (const char *e = getenv("PCGDO_HOST_CHUNK_PAIRS")) { const long v = atol(e); if (v >= 256 && v <= (1 << 20)) chunk = (size_t)v; }
     bool pipelined = !affine && n > chunk && ctx->max_b > 8;      // (wide kernel on: no per-chunk queue left behind)
-    std::vector<size_t> e_lo, e_hi, o_lo, o_hi;
+    // COMPACT TRANSFER (b->out_off_actual).  The reference hands every alignment back in buffers of capacity
+    // len1 + len2 + 2 (DO/Pairwise/FFI.hsc:474-481), of which an alignment of two similar strings fills about half;
+    // copying capacity-sized slots back made the PCIe link, not the aligner, the end-to-end bound.  Here the warps of a
+    // chunk claim packed output ranges from a per-chunk cursor once a pair's alignment length is known (pack_claim):
+    //  * staged (default): into one of kRing device slots, 16-byte units, copied out chunk by chunk; the host learns
+    //    the byte count from a pinned word once the chunk is done.  Measured on B200 / PCIe 5: 127 -> 92 ms per 2^20
+    //    pairs of 1 kb (the aligner alone: 72.6 ms);
+    //  * zero-copy (PCGDO_ZERO_COPY=1, pinned mapped out arrays): the emit stores go straight into the caller's arrays
+    //    over PCIe, one whole 128-byte line per warp store.  No staging and no drain, but SM-issued posted writes reached
+    //    only ~23 GB/s against ~52 GB/s for the copy engine and stalled the aligner (158 ms): kept as an experiment.
+    const bool compact = pipelined && want_str && b->out_off_actual && b->out_len;
+    uint8_t *zc_out[3] = {nullptr, nullptr, nullptr};
+    bool zero_copy = compact && getenv("PCGDO_ZERO_COPY") != nullptr;
+    if (zero_copy) {
+        uint8_t *host[3] = {b->out_gapped, b->out_slot1, b->out_slot2};
+        for (int a = 0; a < 3 && zero_copy; ++a) {
+            if (!host[a]) continue;
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, host[a]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                zero_copy = false;
+            } else {
+                zc_out[a] = (uint8_t *)at.devicePointer;
+            }
+        }
+    }
+    std::vector<size_t> cb;                                       // chunk c = pairs [cb[c], cb[c+1])
     if (pipelined) {
-        size_t prev_e = 0, prev_o = 0;
-        for (size_t c0 = 0; c0 < n && pipelined; c0 += chunk) {
-            const size_t c1 = std::min(n, c0 + chunk);
+        if (zero_copy) {
+            size_t sz = std::max<size_t>(chunk / 4, 256), at = 0;
+            while (at < n) { cb.push_back(at); at += sz; if (sz < 4 * chunk) sz *= 2; }
+        } else {
+            // a short first chunk gets the aligner going early; the copy-out lags by one chunk whatever the sizes
+            // (its rate is within 10 % of the aligner's), so the rest stay equal
+            size_t at = 0;
+            for (size_t sz = std::max<size_t>(chunk / 4, 256); at < n && sz < chunk; sz *= 2) { cb.push_back(at); at += sz; }
+            for (; at < n; at += chunk) cb.push_back(at);
+        }
+        cb.push_back(n);
+    }
+    const size_t nch = pipelined ? cb.size() - 1 : 0;
+    std::vector<size_t> e_lo(nch), e_hi(nch), o_lo(nch), o_hi(nch);
+    if (pipelined) {
+        // per-chunk byte ranges of the strings and of the reserved outputs (a pass over 40 bytes of descriptors per
+        // pair: spread over a few threads, it is on the critical path before the first copy)
+        auto range_of = [&](size_t c) {
             size_t lo = SIZE_MAX, hi = 0, olo = SIZE_MAX, ohi = 0;
-            for (size_t k = c0; k < c1; ++k) {
+            for (size_t k = cb[c]; k < cb[c + 1]; ++k) {
                 const size_t a1 = b->off1[k], a2 = b->off2[k];
                 lo = std::min(lo, std::min(a1, a2));
                 hi = std::max(hi, std::max(a1 + b->len1[k], a2 + b->len2[k]));
@@ -1171,9 +1238,18 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
                     ohi = std::max(ohi, o + (((size_t)b->len1[k] + b->len2[k] + 3) & ~(size_t)3));
                 }
             }
-            if (lo < prev_e || hi > b->elems_bytes || (want_str && (olo < prev_o || ohi > b->out_bytes))) pipelined = false;
-            prev_e = hi; prev_o = want_str ? ohi : 0;
-            e_lo.push_back(lo); e_hi.push_back(hi); o_lo.push_back(olo); o_hi.push_back(ohi);
+            e_lo[c] = lo; e_hi[c] = hi; o_lo[c] = olo; o_hi[c] = ohi;
+        };
+        const size_t nthr = std::min<size_t>(8, nch);
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < nthr; ++t)
+            pool.emplace_back([&, t] { for (size_t c = t; c < nch; c += nthr) range_of(c); });
+        for (size_t c = 0; c < nch; c += nthr) range_of(c);
+        for (auto &th : pool) th.join();
+        size_t prev_e = 0, prev_o = 0;
+        for (size_t c = 0; c < nch; ++c) {
+            if (e_lo[c] < prev_e || e_hi[c] > b->elems_bytes || (want_str && (o_lo[c] < prev_o || o_hi[c] > b->out_bytes))) pipelined = false;
+            prev_e = e_hi[c]; prev_o = want_str ? o_hi[c] : 0;
         }
     }
     if (pipelined) {
@@ -1181,25 +1257,83 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
             CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
             CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
         }
-        const size_t nch = e_lo.size();
-        std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
-        for (size_t c = 0; c < nch; ++c) {
-            CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        constexpr size_t kRing = 3;
+        size_t slot_bytes = 0;
+        if (compact) {
+            if (!zero_copy) {
+                for (size_t c = 0; c < nch; ++c)                 // a chunk's packed size <= its capacity + 16 per pair
+                    slot_bytes = std::max(slot_bytes, o_hi[c] - o_lo[c] + 16 * (cb[c + 1] - cb[c]));
+                slot_bytes = (slot_bytes + 255) & ~(size_t)255;
+                if ((rc = pcgdo_ensure(ctx, ctx->d_stage, kRing * 3 * slot_bytes))) return rc;
+                if (ctx->h_total_cap < nch) {
+                    if (ctx->h_total) cudaFreeHost(ctx->h_total);
+                    ctx->h_total = nullptr;
+                    CK(cudaHostAlloc((void **)&ctx->h_total, nch * 8, cudaHostAllocDefault));
+                    ctx->h_total_cap = nch;
+                }
+            }
+            if ((rc = pcgdo_ensure(ctx, ctx->d_actual, n * 8)) || (rc = pcgdo_ensure(ctx, ctx->d_total, nch * 8 + 8))) return rc;
+            CK(cudaMemsetAsync(ctx->d_total.p, 0, nch * 8 + 8, st));
         }
+        std::vector<cudaEvent_t> ev_in(nch), ev_done(nch), ev_out(nch);
+        const bool trace = getenv("PCGDO_TRACE_PIPELINE") != nullptr;     // per-chunk completion times to stderr
+        const unsigned evf = trace ? cudaEventDefault : cudaEventDisableTiming;
+        for (size_t c = 0; c < nch; ++c) {
+            CK(cudaEventCreateWithFlags(&ev_in[c], evf));
+            CK(cudaEventCreateWithFlags(&ev_done[c], evf));
+            CK(cudaEventCreateWithFlags(&ev_out[c], evf));
+        }
+        size_t h2d_ahead = nch;
+        if (const char *e = getenv("PCGDO_H2D_AHEAD")) { const long v = atol(e); if (v >= 1) h2d_ahead = (size_t)v; }
         cudaEvent_t ev_desc;
         CK(cudaEventCreateWithFlags(&ev_desc, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_desc, st));
         CK(cudaStreamWaitEvent(ctx->s_h2d, ev_desc, 0));
         ctx->last_launches = 0;
         CK(cudaEventRecord(ctx->ev0, st));
+        const double t_setup = ms_since_entry();
         LinearParams p{};
         bool wide_ok = false;
-        for (size_t c = 0; c < nch; ++c) {
-            const size_t c0 = c * chunk, c1 = std::min(n, c0 + chunk);
+        unsigned int *pack_overflow = (unsigned int *)((unsigned long long *)ctx->d_total.p + nch);
+        auto copy_in = [&](size_t c) -> int {
             CK(cudaMemcpyAsync((uint8_t *)ctx->d_elems.p + e_lo[c], b->elems + e_lo[c], e_hi[c] - e_lo[c],
                                cudaMemcpyHostToDevice, ctx->s_h2d));
             CK(cudaEventRecord(ev_in[c], ctx->s_h2d));
+            return PCGDO_OK;
+        };
+        auto copy_out = [&](size_t c) -> int {
+            const size_t c0 = cb[c], c1 = cb[c + 1];
+            cudaStream_t so = ctx->s_d2h;
+            if (compact && !zero_copy) CK(cudaEventSynchronize(ev_done[c]));           // h_total[c] is valid from here on
+            else CK(cudaStreamWaitEvent(so, ev_done[c], 0));
+            CK(cudaMemcpyAsync(b->cost + c0, d.cost + c0, (c1 - c0) * 4, cudaMemcpyDeviceToHost, so));
+            if (b->out_len) CK(cudaMemcpyAsync(b->out_len + c0, d.out_len + c0, (c1 - c0) * 4, cudaMemcpyDeviceToHost, so));
+            if (b->cells) CK(cudaMemcpyAsync(b->cells + c0, d.cells + c0, (c1 - c0) * 8, cudaMemcpyDeviceToHost, so));
+            if (compact)
+                CK(cudaMemcpyAsync(b->out_off_actual + c0, (uint64_t *)ctx->d_actual.p + c0, (c1 - c0) * 8, cudaMemcpyDeviceToHost, so));
+            if (compact && zero_copy) {
+                // the strings are already in the caller's buffers
+            } else if (compact) {
+                const size_t tot = (size_t)ctx->h_total[c];
+                uint8_t *slot = (uint8_t *)ctx->d_stage.p + (c % kRing) * 3 * slot_bytes;
+                if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped + o_lo[c], slot, tot, cudaMemcpyDeviceToHost, so));
+                if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1 + o_lo[c], slot + slot_bytes, tot, cudaMemcpyDeviceToHost, so));
+                if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2 + o_lo[c], slot + 2 * slot_bytes, tot, cudaMemcpyDeviceToHost, so));
+            } else {
+                const size_t ob = want_str ? o_hi[c] - o_lo[c] : 0;
+                if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped + o_lo[c], d.out_gapped + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+                if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1 + o_lo[c], d.out_slot1 + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+                if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2 + o_lo[c], d.out_slot2 + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+            }
+            CK(cudaEventRecord(ev_out[c], so));
+            return PCGDO_OK;
+        };
+        // the strings of the first chunks are queued on the copy-in stream right away, the rest h2d_ahead chunks ahead
+        for (size_t c = 0; c < nch && c < h2d_ahead; ++c)
+            if ((rc = copy_in(c))) return rc;
+        for (size_t c = 0; c < nch; ++c) {
+            const size_t c0 = cb[c], c1 = cb[c + 1];
+            if (c + h2d_ahead < nch && (rc = copy_in(c + h2d_ahead))) return rc;
             CK(cudaStreamWaitEvent(st, ev_in[c], 0));
             BatchDev bd{};
             bd.n_pairs = (uint32_t)(c1 - c0);
@@ -1211,29 +1345,64 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
             bd.out_len = d.out_len ? d.out_len + c0 : nullptr;
             bd.cost = d.cost + c0;
             bd.cells = d.cells ? d.cells + c0 : nullptr;
+            if (compact) {
+                bd.pack_cursor = (unsigned long long *)ctx->d_total.p + c;
+                bd.out_off_actual = (uint64_t *)ctx->d_actual.p + c0;
+                bd.pack_overflow = pack_overflow;
+                if (zero_copy) {
+                    // 4-byte units inside the chunk's reserved region of the caller's arrays: always fits (an alignment
+                    // is never longer than len1 + len2); emit_pair aligns its stores to 128-byte lines by itself
+                    bd.out_gapped = zc_out[0] ? zc_out[0] + o_lo[c] : nullptr;
+                    bd.out_slot1 = zc_out[1] ? zc_out[1] + o_lo[c] : nullptr;
+                    bd.out_slot2 = zc_out[2] ? zc_out[2] + o_lo[c] : nullptr;
+                    bd.pack_base = o_lo[c];
+                    bd.pack_limit = o_hi[c] - o_lo[c];
+                    bd.pack_gran = 3;
+                } else {
+                    if (c >= kRing) CK(cudaStreamWaitEvent(st, ev_out[c - kRing], 0));      // the staging slot is free again
+                    uint8_t *slot = (uint8_t *)ctx->d_stage.p + (c % kRing) * 3 * slot_bytes;
+                    bd.out_gapped = b->out_gapped ? slot : nullptr;
+                    bd.out_slot1 = b->out_slot1 ? slot + slot_bytes : nullptr;
+                    bd.out_slot2 = b->out_slot2 ? slot + 2 * slot_bytes : nullptr;
+                    bd.pack_base = o_lo[c];
+                    bd.pack_limit = slot_bytes;
+                    bd.pack_gran = 15;
+                }
+            }
             if ((rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, c == 0, &p, &wide_ok))) return rc;
+            if (compact && !zero_copy)
+                CK(cudaMemcpyAsync(ctx->h_total + c, (unsigned long long *)ctx->d_total.p + c, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(ev_done[c], st));
-            CK(cudaStreamWaitEvent(ctx->s_d2h, ev_done[c], 0));
-            cudaStream_t so = ctx->s_d2h;
-            CK(cudaMemcpyAsync(b->cost + c0, d.cost + c0, (c1 - c0) * 4, cudaMemcpyDeviceToHost, so));
-            if (b->out_len) CK(cudaMemcpyAsync(b->out_len + c0, d.out_len + c0, (c1 - c0) * 4, cudaMemcpyDeviceToHost, so));
-            if (b->cells) CK(cudaMemcpyAsync(b->cells + c0, d.cells + c0, (c1 - c0) * 8, cudaMemcpyDeviceToHost, so));
-            const size_t ob = want_str ? o_hi[c] - o_lo[c] : 0;
-            if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped + o_lo[c], d.out_gapped + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
-            if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1 + o_lo[c], d.out_slot1 + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
-            if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2 + o_lo[c], d.out_slot2 + o_lo[c], ob, cudaMemcpyDeviceToHost, so));
+            // chunk c-1 goes out while chunk c is aligned (staged compact mode blocks the host on chunk c-1 here, with
+            // chunk c already queued behind it)
+            if (c >= 1 && (rc = copy_out(c - 1))) return rc;
         }
+        if ((rc = copy_out(nch - 1))) return rc;
+        const double t_issued = ms_since_entry();
         CK(cudaEventRecord(ctx->ev1, st));
         ctx->timed = true;
-        unsigned int h_cnt[10] = {0};
+        unsigned int h_cnt[10] = {0}, h_pack = 0;
         CK(cudaMemcpyAsync(h_cnt, p.counter, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+        if (compact) CK(cudaMemcpyAsync(&h_pack, pack_overflow, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaStreamSynchronize(ctx->s_d2h));
-        for (size_t c = 0; c < nch; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); }
+        if (trace) {
+            fprintf(stderr, "pcgdo pipeline: %zu chunks (first %zu pairs), compact=%d zero_copy=%d (ms after the first launch: in / aligned / out)\n",
+                    nch, cb[1] - cb[0], (int)compact, (int)zero_copy);
+            fprintf(stderr, "  host, ms after entry: set up %.2f, all issued %.2f, all done %.2f\n", t_setup, t_issued, ms_since_entry());
+            for (size_t c = 0; c < nch; ++c) {
+                float a = 0, d2 = 0, o = 0;
+                cudaEventElapsedTime(&a, ctx->ev0, ev_in[c]);
+                cudaEventElapsedTime(&d2, ctx->ev0, ev_done[c]);
+                cudaEventElapsedTime(&o, ctx->ev0, ev_out[c]);
+                fprintf(stderr, "  chunk %3zu  %8zu pairs  %8.2f %8.2f %8.2f\n", c, cb[c + 1] - cb[c], a, d2, o);
+            }
+        }
+        for (size_t c = 0; c < nch; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); cudaEventDestroy(ev_out[c]); }
         cudaEventDestroy(ev_desc);
         // the overflow counter accumulates over the chunks; with the wide kernel enabled every pair that
         // fits a warp has been handled in its own chunk
-        if (h_cnt[8] == 0 && wide_ok) return PCGDO_OK;
+        if (h_cnt[8] == 0 && wide_ok && h_pack == 0) return PCGDO_OK;
         // fall through: some pairs need the general-geometry kernel — redo the batch on the plain path
     } else {
         CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));
@@ -1249,6 +1418,7 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1, d.out_slot1, b->out_bytes, cudaMemcpyDeviceToHost, st));
     if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2, d.out_slot2, b->out_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (b->out_off_actual && b->out_off) std::copy(b->out_off, b->out_off + n, b->out_off_actual);   // nothing was packed
     return PCGDO_OK;
 }
 

@@ -38,6 +38,10 @@ struct pcgdo_ctx {
     DevBuf arena, counters, overflow, big, gen_scratch, gen_off, tscratch;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
+    // compact transfer (do_compact.cu): ring of packed output slots, per-pair actual offsets, per-chunk byte counts
+    DevBuf d_stage, d_actual, d_total;
+    unsigned long long *h_total = nullptr;   // pinned
+    size_t h_total_cap = 0;
     std::string err;
 };
 

@@ -44,7 +44,29 @@ struct BatchDev {
     const uint64_t *out_uoff;
     uint32_t       *out_ulen;
     uint32_t        ucap;
+    // packed outputs (the host entry point's compact transfer): instead of out_off[k], a pair's three strings go to
+    // offset atomicAdd(pack_cursor, round16(length)) of the out arrays, and out_off_actual[k] = pack_base + that offset
+    // (out_off_actual[k] = ~0 and *pack_overflow += 1 when the range would end beyond pack_limit: the strings of that
+    // pair are not written).  pack_gran = granularity - 1: 15 for a device staging slot, 3 when the out arrays are the
+    // caller's pinned host buffers written over PCIe (never overflows the reserved capacity).
+    unsigned long long *pack_cursor;
+    uint64_t           *out_off_actual;
+    uint64_t            pack_base, pack_limit;
+    uint32_t            pack_gran;
+    unsigned int       *pack_overflow;
 };
+
+__device__ __forceinline__ void pack_claim(const BatchDev &b, uint32_t k, uint32_t n)
+{
+    const unsigned long long sz = ((unsigned long long)n + b.pack_gran) & ~(unsigned long long)b.pack_gran;
+    const unsigned long long oo = atomicAdd(b.pack_cursor, sz);
+    if (oo + sz > b.pack_limit) {
+        b.out_off_actual[k] = ~0ull;
+        atomicAdd(b.pack_overflow, 1u);
+    } else {
+        b.out_off_actual[k] = b.pack_base + oo;
+    }
+}
 
 struct LinearParams {
     TcmDev    tcm;

@@ -379,16 +379,21 @@ __device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *
 {
     uint32_t base_i = 0, base_j = 0, base_u = 0;
     const uint32_t gap = tcm.gap;
-    for (uint32_t c0 = 0; c0 < nal; c0 += 128) {
-        const uint32_t c = c0 + 4u * lane;
+    // The first pass is shortened so that every later one starts on a 128-byte line of the output arrays (their offsets
+    // are multiples of 4, and equal for the three): each warp store then covers exactly one whole line — what a posted
+    // write over PCIe wants when the arrays are the caller's pinned host buffers, and full sectors in HBM otherwise.
+    const uint8_t *oany = og ? og : (o1 ? o1 : o2);
+    const int mis = (int)(reinterpret_cast<uintptr_t>(oany) & 124u);
+    for (int c0 = -mis; c0 < (int)nal; c0 += 128) {
+        const int c = c0 + 4 * lane;
         uint32_t code[4];
         uint32_t nl = 0, ns = 0;
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-            const uint32_t cc = c + x;
+            const int cc = c + x;
             code[x] = 3u;
-            if (cc < nal) {
-                const uint32_t r = nal - 1u - cc;
+            if (cc >= 0 && cc < (int)nal) {
+                const uint32_t r = nal - 1u - (uint32_t)cc;
                 code[x] = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
             }
             nl += (code[x] < 2u);
@@ -435,7 +440,7 @@ __device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *
             }
             base_u += __shfl_sync(kFull, inc, 31);
         }
-        if (c < nal) {
+        if (c >= 0 && c < (int)nal) {
             if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
             if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wx : wy;
             if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? wy : wx;
@@ -544,6 +549,9 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     // grab per warp) and filled back to back; once `G` pairs are waiting in the arena — or the arena is full, or the
     // batch is exhausted — the warp traces them all at once, one lane per pair, and emits them.
     const uint32_t grab = p.grab ? p.grab : 1u;
+    // (Handing the last pairs of a batch out one at a time from a second counter was tried for the many short launches
+    // of the host pipeline and the forest: no gain — what a short launch loses is its final trace + emit phase, which all
+    // warps reach together and which is latency-bound, not the imbalance of the last grabs.)
     uint32_t gpos = 0, gend = 0;
     bool exhausted = false;
     for (;;) {
@@ -665,6 +673,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                                                         : trace_lane(slot, 32u * B, g.q0, g.lg, g.sh, slot + dir_words(g, B));
                 s_nal[lane] = n;
                 if (b.out_len) b.out_len[k] = n;
+                if (b.pack_cursor) pack_claim(b, k, n);      // the length is known: claim the pair's packed output range
             }
             __syncwarp();
 
@@ -678,11 +687,13 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                     const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
                     const int B = choose_b(g.wb);
                     const uint32_t *ops = arena + s_off[pe] + dir_words(g, B);
-                    const uint64_t oo = b.out_off ? b.out_off[k] : 0;
+                    const uint64_t oa = b.pack_cursor ? __ldcg(b.out_off_actual + k) : 0;
+                    const bool wr = oa != ~0ull;                 // (a packed range that did not fit: see pack_claim)
+                    const uint64_t oo = b.pack_cursor ? oa - b.pack_base : b.out_off ? b.out_off[k] : 0;
                     const uint32_t nu = emit_pair(tcm, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
-                                                  b.out_gapped ? b.out_gapped + oo : nullptr,
-                                                  b.out_slot1 ? b.out_slot1 + oo : nullptr,
-                                                  b.out_slot2 ? b.out_slot2 + oo : nullptr, lane,
+                                                  b.out_gapped && wr ? b.out_gapped + oo : nullptr,
+                                                  b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
+                                                  b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane,
                                                   b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
                     if (b.out_ungapped && lane == 0) {
                         b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
@@ -778,16 +789,19 @@ __global__ void __launch_bounds__(256) do_general_kernel(const LinearParams p, c
         if (want_out) {
             n = trace_lane(dirw, wq, g.q0, g.lg, g.sh, ops);
             if (b.out_len) b.out_len[k] = n;
+            if (b.pack_cursor) pack_claim(b, k, n);
         }
         s_n = n;
         __threadfence_block();
     }
     __syncthreads();
     if (warp == 0 && (b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_ungapped)) {
-        const uint64_t oo = b.out_off ? b.out_off[k] : 0;
-        const uint32_t nu = emit_pair(tcm, pL, pS, ops, s_n, fl, b.out_gapped ? b.out_gapped + oo : nullptr,
-                                      b.out_slot1 ? b.out_slot1 + oo : nullptr,
-                                      b.out_slot2 ? b.out_slot2 + oo : nullptr, lane,
+        const uint64_t oa = b.pack_cursor ? __ldcg(b.out_off_actual + k) : 0;
+        const bool wr = oa != ~0ull;
+        const uint64_t oo = b.pack_cursor ? oa - b.pack_base : b.out_off ? b.out_off[k] : 0;
+        const uint32_t nu = emit_pair(tcm, pL, pS, ops, s_n, fl, b.out_gapped && wr ? b.out_gapped + oo : nullptr,
+                                      b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
+                                      b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane,
                                       b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
         if (b.out_ungapped && lane == 0) {
             b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;

@@ -80,9 +80,10 @@ class BatchResult:
     slot1: Optional[np.ndarray]
     slot2: Optional[np.ndarray]
     cells: Optional[np.ndarray]        # uint64
+    out_off: Optional[np.ndarray] = None   # compact transfer: where each pair's outputs actually are
 
     def pair(self, pp: PackedPairs, k: int):
-        o, n = int(pp.out_off[k]), int(self.out_len[k])
+        o, n = int((pp.out_off if self.out_off is None else self.out_off)[k]), int(self.out_len[k])
         return int(self.cost[k]), self.gapped[o:o + n], self.slot1[o:o + n], self.slot2[o:o + n]
 
 
@@ -91,22 +92,25 @@ def _p(a: Optional[np.ndarray]):
 
 
 def align2d_batch(ctx: Context, tcm: Tcm, pp: PackedPairs, want_strings: bool = True,
-                  want_cells: bool = False) -> BatchResult:
-    """Host buffers in / host buffers out through ``pcgdo_align2d_batch_host``."""
+                  want_cells: bool = False, compact: bool = False, pinned: bool = False) -> BatchResult:
+    """Host buffers in / host buffers out through ``pcgdo_align2d_batch_host``.  ``compact``: only the bytes the
+    alignments produced come back over PCIe (``pcgdo_batch.out_off_actual``); ``BatchResult.pair`` follows the offsets.
+    ``pinned``: the three output arrays are pinned host memory — with ``compact`` the kernel then writes them directly."""
     n = pp.n
     cost = np.zeros(n, np.int32)
     out_len = np.zeros(n, np.uint32) if want_strings else None
     g = s1 = s2 = None
     if want_strings:
-        g, s1, s2 = (np.zeros(pp.out_bytes, np.uint8) for _ in range(3))
+        g, s1, s2 = ((ctx.pinned_empty(pp.out_bytes) if pinned else np.zeros(pp.out_bytes, np.uint8)) for _ in range(3))
     cells = np.zeros(n, np.uint64) if want_cells else None
+    actual = np.zeros(n, np.uint64) if (compact and want_strings) else None
     b = Batch(n, _p(pp.elems), pp.elems.nbytes, _p(pp.off1), _p(pp.off2), _p(pp.len1), _p(pp.len2),
-              _p(pp.out_off), pp.out_bytes, _p(g), _p(s1), _p(s2), _p(out_len), _p(cost), _p(cells))
+              _p(pp.out_off), pp.out_bytes, _p(g), _p(s1), _p(s2), _p(out_len), _p(cost), _p(cells), _p(actual))
     if getattr(tcm, "gap_open", 0):       # getAlignmentStrategy (FFI.hsc:287-290): affine iff cost_model_type says so
         ctx.check(ctx.lib.pcgdo_align2d_affine_batch_host(ctx.h, tcm.h, C.byref(b)), "pcgdo_align2d_affine_batch_host")
     else:
         ctx.check(ctx.lib.pcgdo_align2d_batch_host(ctx.h, tcm.h, C.byref(b)), "pcgdo_align2d_batch_host")
-    return BatchResult(cost, out_len, g, s1, s2, cells)
+    return BatchResult(cost, out_len, g, s1, s2, cells, actual)
 
 
 # ------------------------------------------------------------------------------------------------

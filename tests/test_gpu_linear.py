@@ -253,6 +253,56 @@ def test_pipelined_host_entry_point(oracle_mod, gpu_ctx):
             assert np.array_equal(x, y), k
 
 
+@pytest.mark.parametrize("chunk,pinned", [(0, False), (8192, False), (0, True), (8192, True)])
+def test_compact_transfer_equals_plain(oracle_mod, gpu_ctx, monkeypatch, chunk, pinned):
+    """pcgdo_batch.out_off_actual: outputs packed per pipelined chunk (warps claim ranges from a per-chunk cursor once
+    a pair's alignment length is known) must be, pair by pair, the bytes the plain transfer returns — with the default
+    chunk (2 chunks) and with 9 chunks cycling through the 3 staging slots; with pinned output arrays the kernel writes
+    them directly over PCIe (zero-copy, growing chunks); a batch that takes the plain path (one chunk, or a pair only
+    the general kernel can hold) reports out_off unchanged."""
+    import pcg_b200 as P
+    if chunk:
+        monkeypatch.setenv("PCGDO_HOST_CHUNK_PAIRS", str(chunk))
+    if pinned:
+        monkeypatch.setenv("PCGDO_ZERO_COPY", "1")       # the direct-store experiment (opt-in: measured slower than staging)
+    sig = tcm_matrix("l1")
+    o = oracle_mod.Oracle(sig)
+    tcm = gpu_ctx.tcm(sig)
+    rng = np.random.default_rng(15)
+    pairs = [random_pair(rng, 120) for _ in range(70000)]
+    pairs[100] = (random_string(rng, 600), random_string(rng, 420))       # band of 284 diagonals: wide kernel (B = 16)
+    pairs[300] = (random_string(rng, 1), random_string(rng, 1))
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=720, max_b=32, arena_words=0)
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    plain = P.align2d_batch(gpu_ctx, tcm, pp)
+    packed = P.align2d_batch(gpu_ctx, tcm, pp, compact=True, pinned=pinned)
+    assert np.array_equal(plain.cost, packed.cost) and np.array_equal(plain.out_len, packed.out_len)
+    # it did pack: the ranges are disjoint and a chunk's last byte lies well before its reserved capacity ends
+    order = np.argsort(packed.out_off)
+    ends = packed.out_off[order] + ((packed.out_len[order].astype(np.uint64) + 3) & ~np.uint64(3))
+    assert (ends[:-1] <= packed.out_off[order][1:]).all()
+    assert int(ends[-1]) < int(pp.out_off[-1])
+    for k in range(70000):
+        a, b = plain.pair(pp, k), packed.pair(pp, k)
+        assert all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:])), k
+    for k in (0, 100, 300, 8191, 8192, 65535, 65536, 69999):
+        oc = o.align2d(*pairs[k])
+        gc = packed.pair(pp, k)
+        assert gc[0] == oc[0] and all(np.array_equal(x, y) for x, y in zip(gc[1:], oc[1:4])), k
+    small = P.PackedPairs.from_lists([p[0] for p in pairs[:500]], [p[1] for p in pairs[:500]])
+    r = P.align2d_batch(gpu_ctx, tcm, small, compact=True, pinned=pinned)   # one chunk: plain path, offsets as reserved
+    assert np.array_equal(r.out_off, small.out_off)
+    assert all(np.array_equal(x, y) for x, y in zip(r.pair(small, 499)[1:], plain.pair(pp, 499)[1:]))
+    pairs[5] = (random_string(rng, 2000), random_string(rng, 600))    # general kernel: the batch is redone on the plain path
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    r = P.align2d_batch(gpu_ctx, tcm, pp, compact=True, pinned=pinned)
+    assert np.array_equal(r.out_off, pp.out_off)
+    for k in (5, 6, 69999):
+        oc = o.align2d(*pairs[k])
+        gc = r.pair(pp, k)
+        assert gc[0] == oc[0] and all(np.array_equal(x, y) for x, y in zip(gc[1:], oc[1:4])), k
+
+
 @pytest.mark.parametrize("tcm_file", ["dna-discrete.tcm", "dna-L1-norm.tcm", "dna-pref-gap.tcm", "dna-pref-sub.tcm"])
 def test_bench_strings_golden_through_gpu(gpu_ctx, tcm_file):
     """BASELINE config 1 on the device against the committed outputs of the compiled reference (no oracle
