@@ -47,6 +47,7 @@ data PcgdoBatch = PcgdoBatch
     , outLen     :: Ptr Word32
     , cost       :: Ptr Int32
     , cells      :: Ptr Word64
+    , outOffActual :: Ptr Word64   -- ^ may be null; non-null = compact transfer: pair k's strings are at outOffActual[k]
     }
 
 instance Storable PcgdoBatch where
@@ -61,6 +62,7 @@ instance Storable PcgdoBatch where
         <*> (#peek pcgdo_batch, out_gapped)  p <*> (#peek pcgdo_batch, out_slot1)  p
         <*> (#peek pcgdo_batch, out_slot2)   p <*> (#peek pcgdo_batch, out_len)    p
         <*> (#peek pcgdo_batch, cost)        p <*> (#peek pcgdo_batch, cells)      p
+        <*> (#peek pcgdo_batch, out_off_actual) p
     poke p PcgdoBatch{..} = do
         (#poke pcgdo_batch, n_pairs)     p nPairs
         (#poke pcgdo_batch, elems)       p elems
@@ -77,6 +79,7 @@ instance Storable PcgdoBatch where
         (#poke pcgdo_batch, out_len)     p outLen
         (#poke pcgdo_batch, cost)        p cost
         (#poke pcgdo_batch, cells)       p cells
+        (#poke pcgdo_batch, out_off_actual) p outOffActual
 
 foreign import ccall unsafe "pcg_do_b200.h pcgdo_create"
     pcgdoCreate :: Ptr (Ptr PcgdoCtx) -> CInt -> IO CInt
@@ -132,16 +135,18 @@ foreignPairwiseDOBatch (ctx, tcm) pairs = do
       withArray (init offs1) $ \pOff1 -> withArray offs2 $ \pOff2 ->
       withArray lens1 $ \pLen1 -> withArray lens2 $ \pLen2 -> withArray (init oOffs) $ \pOOff ->
       allocaBytes oBytes $ \pG -> allocaBytes oBytes $ \pS1 -> allocaBytes oBytes $ \pS2 ->
-      allocaArray n $ \pOLen -> allocaArray n $ \pCost ->
+      allocaArray n $ \pOLen -> allocaArray n $ \pCost -> allocaArray n $ \pActual ->
       with PcgdoBatch { nPairs = fromIntegral n, elems = pElems, elemsBytes = fromIntegral nBytes
                       , off1 = pOff1, off2 = pOff2, len1 = pLen1, len2 = pLen2
                       , outOff = pOOff, outBytes = fromIntegral oBytes
                       , outGapped = pG, outSlot1 = pS1, outSlot2 = pS2
-                      , outLen = pOLen, cost = pCost, cells = nullPtr } $ \pBatch -> do
+                      , outLen = pOLen, cost = pCost, cells = nullPtr
+                      , outOffActual = pActual } $ \pBatch -> do     -- compact transfer: only produced bytes come back
         rc <- pcgdoAlign2dBatchHost ctx tcm pBatch
         when (rc /= 0) $ pcgdoLastError ctx >>= peekCString >>= fail
         costs <- peekArray n pCost
         oLens <- peekArray n pOLen
+        actual <- peekArray n pActual        -- where each pair's strings are (== init oOffs when nothing was packed)
         let slice p o l = peekArray (fromIntegral l) (p `plusPtr` fromIntegral o)
         sequence [ (,,,) (fromIntegral c) <$> slice pG o l <*> slice pS1 o l <*> slice pS2 o l
-                 | (c, o, l) <- zip3 costs (init oOffs) oLens ]
+                 | (c, o, l) <- zip3 costs (actual :: [Word64]) oLens ]
