@@ -665,6 +665,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # Everything below runs on one explicit stream: its handle is what the library launches on (a NULL handle would mean
+    # the context's own non-blocking stream, which neither torch's events nor NCCL's stream ordering can see), the timing
+    # events are recorded on it, and the all-reduce of config 5 is ordered after the sweep through it.
+    torch.cuda.set_stream(torch.cuda.Stream(device=torch.device("cuda", local_rank)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
