@@ -254,7 +254,12 @@ typedef struct pcgdo_forest pcgdo_forest;
 int  pcgdo_forest_create(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
                          const int32_t *children, pcgdo_forest **out);
 void pcgdo_forest_destroy(pcgdo_ctx *ctx, pcgdo_forest *forest);
-/* HOST buffers: character c of taxon v = elems[off[v*n_chars+c] .. +len[v*n_chars+c]) (no gap elements). */
+/* HOST buffers: character c of taxon v = elems[off[v*n_chars+c] .. +len[v*n_chars+c]) (no gap elements).
+ * len = PCGDO_MISSING marks a Missing character (a taxon without data for that character): aligning it with anything
+ * costs nothing and yields the other operand (`handleMissingCharacter`, DO/Pairwise/Internal.hs:247-259); a node whose
+ * two children are Missing — or both empty once ungapped — is Missing itself (get_node reports that length), and an
+ * alignment with ONE empty operand is free, as in the reference (`directOptimization`, :224-233). */
+#define PCGDO_MISSING 0xffffffffu
 int  pcgdo_forest_set_leaves(pcgdo_ctx *ctx, pcgdo_forest *forest, const uint8_t *elems, const uint64_t *off,
                              const uint32_t *len);
 /* One sweep: every internal node's local cost, total cost (local + children, DO/Internal.hs:133-137) and

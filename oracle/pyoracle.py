@@ -155,9 +155,9 @@ def reroot(oracle: "Oracle", children, leaves, trial=None):
     lib.oracle_reroot_trial.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]
     ch = np.ascontiguousarray(np.asarray(children, np.int32))
     n_taxa = ch.shape[0] + 1
-    arrs = [_as_u32(x) for x in leaves]
+    arrs = [_as_u32(x if x is not None else np.zeros(1, np.uint32)) for x in leaves]     # None = a Missing character
     ptrs = (C.c_void_p * n_taxa)(*[a.ctypes.data for a in arrs])
-    lens = (C.c_size_t * n_taxa)(*[len(a) for a in arrs])
+    lens = (C.c_size_t * n_taxa)(*[len(a) if x is not None else C.c_size_t(-1).value for a, x in zip(arrs, leaves)])
     ne = 2 * n_taxa - 3
     eu, ev = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
     ec, el = np.zeros(ne, np.int64), np.zeros(ne, np.int64)
@@ -183,9 +183,9 @@ def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None, metric_ki
     ch = np.ascontiguousarray(np.asarray(children, np.int32))
     n_taxa = ch.shape[0] + 1
     W = (a + 31) // 32                      # leaves: (n, W) uint32 arrays when the alphabet exceeds 32 symbols
-    arrs = [_as_u32(x).reshape(-1) for x in leaves]
+    arrs = [_as_u32(x if x is not None else np.zeros(W, np.uint32)).reshape(-1) for x in leaves]    # None = Missing
     ptrs = (C.c_void_p * n_taxa)(*[x.ctypes.data for x in arrs])
-    lens = (C.c_size_t * n_taxa)(*[len(x) // W for x in arrs])
+    lens = (C.c_size_t * n_taxa)(*[len(a) // W if x is not None else C.c_size_t(-1).value for a, x in zip(arrs, leaves)])
     ne = 2 * n_taxa - 3
     eu, ev = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
     ec, el = np.zeros(ne, np.int64), np.zeros(ne, np.int64)

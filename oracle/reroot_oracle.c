@@ -41,9 +41,42 @@ typedef struct {
     uint64_t cells;
 } rr_t;
 
+#define RR_MISSING ((size_t)-1)       /* length of a Missing dynamic character */
+
 static void apply(rr_t *R, const datum_t *l, const datum_t *r, datum_t *out)
 {
     const int W = R->W > 1 ? R->W : 1;
+    /* handleMissingCharacter (DO/Pairwise/Internal.hs:247-259): a Missing operand costs nothing and yields the other;
+     * directOptimization / algn2d (:224-233, FFI.hsc:240-248): both empty once ungapped -> Missing (toMissing), one
+     * empty -> cost 0 and the medians of (element, gap). */
+    const int ml = l->n == RR_MISSING, mr = r->n == RR_MISSING;
+    if (ml || mr || l->n == 0 || r->n == 0) {
+        out->local = 0;
+        out->total = l->total + r->total;
+        out->done = 1;
+        if ((ml && mr) || (!ml && !mr && l->n == 0 && r->n == 0)) { out->s = NULL; out->n = RR_MISSING; return; }
+        const datum_t *x = (ml || (!mr && l->n == 0)) ? r : l;          /* the operand that survives */
+        out->s = malloc(sizeof(uint32_t) * (x->n + 1) * (size_t)W);
+        if (ml || mr) { memcpy(out->s, x->s, sizeof(uint32_t) * x->n * (size_t)W); out->n = x->n; return; }
+        out->n = 0;
+        for (size_t k = 0; k < x->n; k++) {
+            uint32_t md[64];
+            int is_gap = 1;
+            if (R->t) md[0] = R->t->median[((size_t)x->s[k] << R->t->a) + R->gap];
+            else if (W == 1) oracle_overlap(R->hs_kind, R->hs_sigma, R->hs_a, x->s[k], R->gap, md);
+            else {
+                uint32_t gw[64] = {0};
+                gw[(R->hs_a - 1) >> 5] = 1u << ((R->hs_a - 1) & 31);
+                oracle_overlap_w(R->hs_kind, R->hs_sigma, R->hs_a, x->s + k * W, gw, md);
+            }
+            for (int w = 0; w < W; w++) {
+                const uint32_t want = (W == 1) ? R->gap : ((R->hs_a - 1) >> 5) == w ? 1u << ((R->hs_a - 1) & 31) : 0u;
+                if (md[w] != want) is_gap = 0;
+            }
+            if (!is_gap) { memcpy(out->s + out->n * W, md, sizeof(uint32_t) * (size_t)W); out->n++; }
+        }
+        return;
+    }
     const size_t cap = (l->n + r->n + 2) * (size_t)W;
     uint32_t *g = malloc(sizeof(uint32_t) * 3 * cap);
     size_t nal = 0;

@@ -262,6 +262,7 @@ class Tcm:
 
 
 METRIC_AUTO, METRIC_EXPLICIT, METRIC_DISCRETE, METRIC_L1 = -1, 0, 1, 2
+MISSING = 0xffffffff      # PCGDO_MISSING: the length of a Missing dynamic character
 _STRUCTURES = {"auto": METRIC_AUTO, "explicit": METRIC_EXPLICIT, "discrete": METRIC_DISCRETE, "nonadditive": METRIC_DISCRETE,
                "l1": METRIC_L1, "additive": METRIC_L1}
 
@@ -338,9 +339,13 @@ class Forest:
                                                     ch.ctypes.data, memo_h, alpha, dialect, C.byref(h)),
                       "pcgdo_forest_create32")
         self.h = h
-        flat = [np.asarray(s, self.dtype).reshape(-1, self.words) for taxon in leaves for s in taxon]
-        ln = np.array([len(s) for s in flat], np.uint32)
-        off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
+        # a leaf string of None is a Missing character (PCGDO_MISSING)
+        raw = [s for taxon in leaves for s in taxon]
+        flat = [np.zeros((0, self.words), self.dtype) if s is None else np.asarray(s, self.dtype).reshape(-1, self.words)
+                for s in raw]
+        real = np.array([len(s) for s in flat], np.uint64)
+        ln = np.array([MISSING if r is None else len(s) for r, s in zip(raw, flat)], np.uint32)
+        off = np.concatenate([[0], np.cumsum(real)[:-1]]).astype(np.uint64)
         elems = np.concatenate(flat) if flat else np.zeros((0, self.words), self.dtype)
         elems = np.ascontiguousarray(elems.reshape(-1))
         fn = ctx.lib.pcgdo_forest_set_leaves if metric is None else ctx.lib.pcgdo_forest_set_leaves32
@@ -375,9 +380,12 @@ class Forest:
         """Wagner edge trial (``iterativeBuild.tryEdge``): cost increase of attaching a new taxon (one element string
         per character) to every edge of every tree -> int64 (n_trees, n_edges).  Needs a re-rooted sweep with
         ``enable_rerooting(keep_edge_data=True)``."""
-        flat = [np.asarray(x, self.dtype).reshape(-1, self.words) for x in leaf_strings]
-        ln = np.array([len(x) for x in flat], np.uint32)
-        off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
+        raw = list(leaf_strings)
+        flat = [np.zeros((0, self.words), self.dtype) if x is None else np.asarray(x, self.dtype).reshape(-1, self.words)
+                for x in raw]
+        real = np.array([len(x) for x in flat], np.uint64)
+        ln = np.array([MISSING if r is None else len(x) for r, x in zip(raw, flat)], np.uint32)
+        off = np.concatenate([[0], np.cumsum(real)[:-1]]).astype(np.uint64)
         elems = np.ascontiguousarray(np.concatenate(flat).reshape(-1)) if flat else np.zeros(1, self.dtype)
         ne = int(self.ctx.lib.pcgdo_forest_edges(self.h))
         out = np.zeros((self.n_trees, ne), np.int64)
@@ -415,6 +423,8 @@ class Forest:
         self.ctx.check(self.ctx.lib.pcgdo_forest_get_node(self.ctx.h, self.h, tree, character, node, buf.ctypes.data,
                                                           C.byref(n), C.byref(lc), C.byref(tc)),
                        "pcgdo_forest_get_node")
+        if n.value == MISSING:
+            return None, int(lc.value), int(tc.value)
         med = buf[:n.value * self.words].copy()
         return (med if self.words == 1 else med.reshape(-1, self.words)), int(lc.value), int(tc.value)
 

@@ -78,7 +78,11 @@ struct ForestDev {
     uint32_t *node_len;
     int32_t *node_local;
     int64_t *node_total;
+    uint32_t *store32;                                // the node store as 32-bit words (slots are 4-element aligned)
+    uint32_t elem_bytes;
 };
+
+constexpr uint32_t kMissing = PCGDO_MISSING;          // length of a Missing dynamic character
 
 __device__ __forceinline__ uint64_t slot_of(const ForestDev &f, uint32_t tree, uint32_t c, int32_t node)
 {
@@ -91,6 +95,15 @@ __device__ __forceinline__ uint64_t nidx(const ForestDev &f, uint32_t tree, uint
     return ((uint64_t)tree * f.n_chars + c) * f.n_internal + x;
 }
 
+__device__ __forceinline__ void child_lengths(const ForestDev &f, const LevelItem &it, uint32_t c, uint32_t &l1, uint32_t &l2)
+{
+    l1 = (uint32_t)it.left < f.n_taxa ? f.leaf_len[(uint64_t)it.left * f.n_chars + c]
+                                      : f.node_len[nidx(f, it.tree, c, it.left - f.n_taxa)];
+    l2 = (uint32_t)it.right < f.n_taxa ? f.leaf_len[(uint64_t)it.right * f.n_chars + c]
+         : (uint32_t)it.right >= f.n_taxa + f.n_internal ? f.trial_len[c]
+                                                         : f.node_len[nidx(f, it.tree, c, it.right - f.n_taxa)];
+}
+
 __global__ void forest_prep_kernel(ForestDev f, const LevelItem *items, uint32_t n_items, uint64_t *off1,
                                    uint64_t *off2, uint64_t *uoff, uint32_t *len1, uint32_t *len2)
 {
@@ -101,11 +114,44 @@ __global__ void forest_prep_kernel(ForestDev f, const LevelItem *items, uint32_t
     off1[k] = slot_of(f, it.tree, c, it.left);
     off2[k] = slot_of(f, it.tree, c, it.right);
     uoff[k] = slot_of(f, it.tree, c, (int32_t)(f.n_taxa + it.out));
-    len1[k] = (uint32_t)it.left < f.n_taxa ? f.leaf_len[(uint64_t)it.left * f.n_chars + c]
-                                           : f.node_len[nidx(f, it.tree, c, it.left - f.n_taxa)];
-    len2[k] = (uint32_t)it.right < f.n_taxa ? f.leaf_len[(uint64_t)it.right * f.n_chars + c]
-              : (uint32_t)it.right >= f.n_taxa + f.n_internal ? f.trial_len[c]
-                                                              : f.node_len[nidx(f, it.tree, c, it.right - f.n_taxa)];
+    uint32_t l1, l2;
+    child_lengths(f, it, c, l1, l2);
+    if (l1 == kMissing || l2 == kMissing) l1 = l2 = 0;      // nothing to align: forest_special_kernel supplies the result
+    len1[k] = l1;
+    len2[k] = l2;
+}
+
+// The cases the reference settles before (or instead of) aligning — `handleMissingCharacter`
+// (DO/Pairwise/Internal.hs:247-259) and the empty-after-ungapping branches of `directOptimization` / `algn2d`
+// (:224-233, DO/Pairwise/FFI.hsc:240-248) — applied to the batch after the aligner ran and before the totals are taken:
+//   a Missing child            -> cost 0, the node is the other child's string (Missing if both are);
+//   both children empty        -> cost 0, the node is Missing (`toMissing`);
+//   one child empty            -> cost 0 (the aligner's medians of (x, gap) stand; the reference charges nothing).
+// data = the batch keeps node strings (post-order / directed data / kept edge data), else it is cost-only.
+__global__ void forest_special_kernel(ForestDev f, const LevelItem *items, uint32_t n_items, const uint64_t *off1,
+                                      const uint64_t *off2, const uint64_t *uoff, int32_t *cost, uint32_t *ulen, int data)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (uint64_t)n_items * f.n_chars) return;
+    const LevelItem it = items[k / f.n_chars];
+    const uint32_t c = (uint32_t)(k % f.n_chars);
+    uint32_t l1, l2;
+    child_lengths(f, it, c, l1, l2);
+    const bool m1 = l1 == kMissing, m2 = l2 == kMissing;
+    if (!m1 && !m2 && l1 != 0 && l2 != 0) return;
+    cost[k] = 0;
+    if (!data) return;
+    if (m1 && m2) { ulen[k] = kMissing; return; }
+    if (m1 || m2) {
+        const uint32_t n = m1 ? l2 : l1;
+        const uint32_t *src = f.store32 + (m1 ? off2[k] : off1[k]) * f.elem_bytes / 4;
+        uint32_t *dst = f.store32 + uoff[k] * f.elem_bytes / 4;
+        const uint32_t words = (uint32_t)(((uint64_t)n * f.elem_bytes + 3) / 4);
+        for (uint32_t w = 0; w < words; ++w) dst[w] = src[w];
+        ulen[k] = n;
+        return;
+    }
+    if (l1 == 0 && l2 == 0) ulen[k] = kMissing;
 }
 
 __global__ void forest_post_kernel(ForestDev f, const LevelItem *items, uint32_t n_items, const int32_t *cost,
@@ -217,6 +263,8 @@ ForestDev dev_view(const pcgdo_forest *F)
     f.node_len = (uint32_t *)F->node_len.p;
     f.node_local = (int32_t *)F->node_local.p;
     f.node_total = (int64_t *)F->node_total.p;
+    f.store32 = (uint32_t *)F->store.p;
+    f.elem_bytes = F->elem_bytes;
     return f;
 }
 
@@ -367,6 +415,7 @@ static int forest_set_leaves_impl(pcgdo_ctx *ctx, pcgdo_forest *F, const void *e
     const size_t n = (size_t)F->n_taxa * F->n_chars, eb = elem_bytes;
     std::vector<uint8_t> stage(n * F->cap * eb, 0);
     for (size_t i = 0; i < n; ++i) {
+        if (len[i] == PCGDO_MISSING) continue;           // a Missing character: nothing to store
         if (len[i] > F->cap) {
             ctx->err = "forest: a leaf string is longer than the node capacity";
             return PCGDO_ERR_ARG;
@@ -445,6 +494,10 @@ static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *
         }
         if (rc) return rc;
         first = false;
+        forest_special_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const uint64_t *)F->boff1.p, (const uint64_t *)F->boff2.p,
+                                                      (const uint64_t *)F->buoff.p, (int32_t *)F->bcost.p,
+                                                      (uint32_t *)F->bulen.p, mode == 0 || mode == 2);
+        CK(cudaGetLastError());
         if (mode == 0)
             forest_post_kernel<<<blocks, 256, 0, st>>>(f, items, n_items, (const int32_t *)F->bcost.p,
                                                        (const uint32_t *)F->bulen.p);
@@ -460,7 +513,7 @@ static int forest_run_items(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *
                                                                            (const int32_t *)F->bcost.p,
                                                                            (int64_t *)F->trial_delta.p);
         CK(cudaGetLastError());
-        ctx->last_launches += 2;
+        ctx->last_launches += 3;
     }
     return PCGDO_OK;
 }
@@ -696,6 +749,7 @@ extern "C" int pcgdo_forest_try_leaf(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo
     const size_t eb = F->elem_bytes;
     std::vector<uint8_t> stage((size_t)F->n_chars * F->cap * eb, 0);
     for (uint32_t c = 0; c < F->n_chars; ++c) {
+        if (len[c] == PCGDO_MISSING) continue;
         if (len[c] > F->cap) {
             ctx->err = "forest: the trial leaf is longer than the node capacity";
             return PCGDO_ERR_ARG;
@@ -767,7 +821,7 @@ extern "C" int pcgdo_forest_get_node(pcgdo_ctx *ctx, pcgdo_forest *F, uint32_t t
     if (len_out) *len_out = len;
     if (local_cost) CK(cudaMemcpy(local_cost, (int32_t *)F->node_local.p + me, 4, cudaMemcpyDeviceToHost));
     if (total_cost) CK(cudaMemcpy(total_cost, (int64_t *)F->node_total.p + me, 8, cudaMemcpyDeviceToHost));
-    if (median_out && len)      // (len elements of F's element width)
+    if (median_out && len && len != PCGDO_MISSING)      // (len elements of F's element width)
         CK(cudaMemcpy(median_out, (uint8_t *)F->store.p + (F->leaf_bytes + me * F->cap) * F->elem_bytes,
                       (size_t)len * F->elem_bytes, cudaMemcpyDeviceToHost));
     return PCGDO_OK;

@@ -26,6 +26,11 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "custom_alphabet_
 CASES = {"slashes": ["L1-norm", "discrete", "2-1", "hamming", "levenshtein"],
          "large-mix": ["discrete"],
          "huge-mix": ["discrete", "L1-norm", "1-2", "hamming", "levenshtein"]}
+# Entries the reference keeps COMMENTED OUT ("Impossible Happened in Implied Alignment": the pre-order pass fails, the
+# post-order + re-rooting cost they record is still the DO path's): stored with "asserted": false.  Not included: the two
+# commented-out L1 entries (large-mix 7185, protein 11036) — the restatement that reproduces the two ASSERTED L1 costs
+# gives 7212 / 11645 for them; they predate the current firstLinearNormPairwiseLogic or were never checked.
+UNASSERTED = {"slashes": ["1-2"], "large-mix": ["1-2", "2-1", "hamming", "levenshtein"], "huge-mix": ["2-1"]}
 
 
 def main():
@@ -35,8 +40,10 @@ def main():
     for ds, mats in CASES.items():
         entry = {"fasta": open(os.path.join(SRC, ds, ds + ".fasta")).read(),
                  "tree": open(os.path.join(SRC, ds, ds + ".tree")).read().strip(), "cases": {}}
-        for mname in mats:
-            m = re.search(r"^\s*,\s*scriptCheckCost\s+(\d+)\s+\"dynamic/single-block/%s/%s/test.pcg\"" % (ds, mname), src, re.M)
+        for mname in mats + UNASSERTED.get(ds, []):
+            asserted = mname in mats
+            lead = r"^\s*," if asserted else r"^--\s*,"
+            m = re.search(lead + r"\s*scriptCheckCost\s+(\d+)\s*\n(?:--)?\s*\"dynamic/single-block/%s/%s/test.pcg\"" % (ds, mname), src, re.M)
             fname = mname.replace("levenshtein", "leveshtein")            # the file name is spelt that way upstream
             lines = [l for l in open(os.path.join(SRC, "tcms", f"{ds}-{fname}.tcm")).read().splitlines() if l.strip()]
             alphabet = lines[0].split()
@@ -44,7 +51,7 @@ def main():
             assert sig.shape == (len(alphabet) + 1,) * 2 and sig.max() < 65536
             entry.setdefault("alphabet", alphabet)
             assert entry["alphabet"] == alphabet
-            entry["cases"][mname] = {"dag_cost": int(m.group(1)),
+            entry["cases"][mname] = {"dag_cost": int(m.group(1)), "asserted": asserted,
                                      "sigma_u16_zlib_b64": base64.b64encode(zlib.compress(sig.astype("<u2").tobytes(), 9)).decode()}
         out["sets"][ds] = entry
     json.dump(out, open(OUT, "w"), separators=(",", ":"))

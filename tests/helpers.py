@@ -149,5 +149,28 @@ def custom_alphabet_golden(ds):
     for name, c in g["cases"].items():
         sig = np.frombuffer(zlib.decompress(base64.b64decode(c["sigma_u16_zlib_b64"])), "<u2").reshape(a, a)
         weight, f, kind = formats.diagnose_tcm(sig)
-        cases[name] = ({"nonadditive": 0, "explicit": 1, "additive": 2}[kind], f, weight, c["dag_cost"])
+        cases[name] = ({"nonadditive": 0, "explicit": 1, "additive": 2}[kind], f, weight, c["dag_cost"])   # (c["asserted"]: upstream state)
     return a, children, leaves, cases
+
+
+def multiblock_missing_golden():
+    """tests/golden/multiblock_missing_dna.json -> (children, [(leaves with None for a taxon missing from the block, sigma)
+    per block], asserted DAG cost).  Leaves are ungapped uint8 strings, a = 5."""
+    import json
+    import re
+    from pcg_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "multiblock_missing_dna.json")))
+    names = sorted(set(re.findall(r"[A-Za-z]+", g["tree"])))
+    codes = formats.iupac_dna_codes()
+    blocks = []
+    for b in g["blocks"]:
+        seqs = dict(formats.read_fasta(b["fasta"]))
+        leaves = []
+        for n in names:
+            if n in seqs:
+                e = formats.encode_fasta(seqs[n], codes, np.uint8)
+                leaves.append(e[e != 16])
+            else:
+                leaves.append(None)
+        blocks.append((leaves, formats.read_tcm(b["tcm"])[1]))
+    return formats.read_newick_binary(g["tree"], names), blocks, g["dag_cost"]

@@ -315,3 +315,92 @@ def test_forest_reproduces_missing_values_script_cost(gpu_ctx):
     f.enable_rerooting()
     assert int(f.score_rerooted(gpu_ctx.tcm(sigma))[0]) == want
     f.close()
+
+
+def test_forest_reproduces_multiblock_missing_script_cost(gpu_ctx):
+    """scriptCheckCost 45 (ScriptTests.hs:184-186) through the device: two blocks with their own dense TCMs, each with
+    one taxon Missing (PCGDO_MISSING leaves), re-rooting; 16 + 29."""
+    import pcg_b200 as P
+    from tests.helpers import multiblock_missing_golden
+    children, blocks, want = multiblock_missing_golden()
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=64, max_b=32, arena_words=0)
+    costs = []
+    for leaves, sigma in blocks:
+        f = P.Forest(gpu_ctx, children[None], len(leaves), [[s] for s in leaves], node_cap=64)
+        f.enable_rerooting()
+        costs.append(int(f.score_rerooted(gpu_ctx.tcm(sigma))[0]))
+        f.close()
+    assert costs == [16, 29] and sum(costs) == want
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_forest_missing_and_empty_leaves_match_oracle(oracle_mod, gpu_ctx, wide):
+    """Random trees whose leaves are, here and there, Missing or empty (all-gap taxa ungap to nothing): post-order and
+    re-rooted costs, every edge's cost and the surviving node strings against the oracle's restatement of
+    handleMissingCharacter / the empty branches of directOptimization — dense 8-bit forest and 32-bit (discrete, a = 12)."""
+    import pcg_b200 as P
+    from tests.helpers import tcm_matrix, random_string
+    from tests.test_gpu_metric import _rand_str
+    rng = np.random.default_rng(2024 + int(wide))
+    n_taxa, n_trees, n_chars = 9, 6, 5
+    from pcg_b200.postorder import random_binary_trees
+    children = random_binary_trees(n_trees, n_taxa, 77)
+    a = 12
+    leaves = []
+    for v in range(n_taxa):
+        row = []
+        for c in range(n_chars):
+            r = rng.random()
+            if r < 0.25:
+                row.append(None)
+            elif r < 0.4:
+                row.append(np.zeros(0, np.uint32 if wide else np.uint8))
+            else:
+                n = int(rng.integers(5, 50))
+                row.append(_rand_str(rng, n, a) if wide else random_string(rng, n))
+        leaves.append(row)
+    for c in range(n_chars):                 # one character with a single surviving taxon, one with none
+        if c == 3:
+            for v in range(1, n_taxa):
+                leaves[v][c] = None
+        if c == 4:
+            for v in range(n_taxa):
+                leaves[v][c] = None
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=128, max_b=32, arena_words=0)
+    if wide:
+        f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=128, metric=a, dialect=2)
+        tcm = None
+    else:
+        sig = tcm_matrix("l1")
+        f = P.Forest(gpu_ctx, children, n_taxa, leaves, node_cap=128)
+        tcm = gpu_ctx.tcm(sig)
+        o = oracle_mod.Oracle(sig)
+    plain = f.score(tcm)
+    f.enable_rerooting()
+    best = f.score_rerooted(tcm)
+    for t in range(n_trees):
+        want_plain = want_best = 0
+        for c in range(n_chars):
+            col = [leaves[v][c] for v in range(n_taxa)]
+            if wide:
+                r = oracle_mod.reroot_haskell(2, a, children[t], col)
+            else:
+                r = oracle_mod.reroot(o, children[t], col)
+            want_best += r[0]
+            want_plain += int(r[2][0])
+            uv, tot, loc = f.edges(t, c)
+            assert np.array_equal(tot, r[2]) and np.array_equal(loc, r[3]), (t, c)
+        assert int(plain[t]) == want_plain and int(best[t]) == want_best, t
+    f.close()
+
+
+def test_large_alphabet_forest_protein_discrete_cost(gpu_ctx):
+    """DAG cost 1131 (ScriptTests.hs:200-202, commented out upstream) for the protein data under the discrete metric."""
+    import pcg_b200 as P
+    from tests.helpers import invertebrates_golden
+    children, leaves, _ = invertebrates_golden()
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=400, max_b=32, arena_words=0)
+    f = P.Forest(gpu_ctx, children[None], len(leaves), [[s] for s in leaves], node_cap=512, metric=21, dialect=2)
+    f.enable_rerooting()
+    assert int(f.score_rerooted(None)[0]) == 1131
+    f.close()

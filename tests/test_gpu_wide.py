@@ -109,7 +109,10 @@ def test_wide_alphabet_dialects_fuzz(oracle_mod, gpu_ctx, dialect, a, kind):
 
 _CUSTOM = [("slashes", "L1-norm"), ("slashes", "discrete"), ("slashes", "2-1"), ("slashes", "hamming"),
            ("slashes", "levenshtein"), ("large-mix", "discrete"), ("huge-mix", "discrete"), ("huge-mix", "L1-norm"),
-           ("huge-mix", "1-2"), ("huge-mix", "hamming"), ("huge-mix", "levenshtein")]
+           ("huge-mix", "1-2"), ("huge-mix", "hamming"), ("huge-mix", "levenshtein"),
+           # commented out upstream (their pre-order pass fails; the DO cost they record still holds):
+           ("slashes", "1-2"), ("large-mix", "1-2"), ("large-mix", "2-1"), ("large-mix", "hamming"),
+           ("large-mix", "levenshtein"), ("huge-mix", "2-1")]
 
 
 @pytest.mark.parametrize("ds,name", _CUSTOM)

@@ -194,7 +194,10 @@ def test_reroot_oracle_reproduces_missing_values_script_cost(oracle_mod):
 
 _CUSTOM = [("slashes", "L1-norm"), ("slashes", "discrete"), ("slashes", "2-1"), ("slashes", "hamming"),
            ("slashes", "levenshtein"), ("large-mix", "discrete"), ("huge-mix", "discrete"), ("huge-mix", "L1-norm"),
-           ("huge-mix", "1-2"), ("huge-mix", "hamming"), ("huge-mix", "levenshtein")]
+           ("huge-mix", "1-2"), ("huge-mix", "hamming"), ("huge-mix", "levenshtein"),
+           # commented out upstream (their pre-order pass fails; the DO cost they record still holds):
+           ("slashes", "1-2"), ("large-mix", "1-2"), ("large-mix", "2-1"), ("large-mix", "hamming"),
+           ("large-mix", "levenshtein"), ("huge-mix", "2-1")]
 
 
 @pytest.mark.parametrize("ds,name", _CUSTOM)
@@ -202,7 +205,8 @@ def test_wide_alphabet_script_costs(oracle_mod, ds, name):
     """PIN for alphabets of more than 32 symbols AND for the L1 closed form: the reference's script tests on the slashes
     (82 symbols with the gap), large-mix (256) and huge-mix (433) data (test/TestSuite/ScriptTests.hs:205-266) assert the
     DAG costs below; post-order + re-rooting with the restated unboxedUkkonenFullSpaceDO over W-word elements
-    (oracle/hs_wide.c) reproduces all eleven.  The two L1 numbers (3483, 21851) settle how firstLinearNormPairwiseLogic
+    (oracle/hs_wide.c) reproduces all eleven — and six more that upstream keeps commented out because its pre-order pass
+    fails on them.  The two L1 numbers (3483, 21851) settle how firstLinearNormPairwiseLogic
     reads an ambiguity set: range = lowest..highest set symbol (bv-little counts "leading" zeros from index 0) and
     fromRange drops the upper bound's bit — the mirrored reading gives 4380 and the true Sankoff median 3371 on slashes."""
     from tests.helpers import custom_alphabet_golden
@@ -214,3 +218,38 @@ def test_wide_alphabet_script_costs(oracle_mod, ds, name):
     if (ds, name) == ("slashes", "L1-norm"):
         assert oracle_mod.reroot_haskell(2, a, children, leaves, sigma=sigma, metric_kind=3)[0] == 4380
         assert oracle_mod.reroot_haskell(2, a, children, leaves, sigma=sigma, metric_kind=1)[0] == 3371
+
+
+def test_reroot_oracle_reproduces_multiblock_missing_script_cost(oracle_mod):
+    """scriptCheckCost 45 "dynamic/multi-block/missing/missing.pcg": two blocks, each without one taxon -> Missing
+    characters (cost 0, the other operand passes through); 16 + 29 over the blocks."""
+    from tests.helpers import multiblock_missing_golden
+    children, blocks, want = multiblock_missing_golden()
+    costs = [oracle_mod.reroot(oracle_mod.Oracle(sigma), children, leaves)[0] for leaves, sigma in blocks]
+    assert costs == [16, 29] and sum(costs) == want == 45
+
+
+def test_reroot_oracle_missing_equals_pruned_tree(oracle_mod):
+    """A Missing leaf behaves like a pruned one: the re-rooted cost of a tree with taxon k Missing equals that of the tree
+    without it (same remaining topology)."""
+    from pcg_b200 import formats
+    from tests.helpers import tcm_matrix, random_string
+    rng = np.random.default_rng(3)
+    o = oracle_mod.Oracle(tcm_matrix("l1"))
+    names = list("ABCDEF")
+    leaves = [random_string(rng, int(rng.integers(20, 60))) for _ in names]
+    full = formats.read_newick_binary("((A,B),((C,D),(E,F)));", names)
+    with_missing = [x if n != "D" else None for n, x in zip(names, leaves)]
+    pruned_names = [n for n in names if n != "D"]
+    pruned = formats.read_newick_binary("((A,B),(C,(E,F)));", pruned_names)
+    a = oracle_mod.reroot(o, full, with_missing)[0]
+    b = oracle_mod.reroot(o, pruned, [x for n, x in zip(names, leaves) if n != "D"])[0]
+    assert a == b
+
+
+def test_protein_discrete_script_cost_commented_out_upstream(oracle_mod):
+    """ScriptTests.hs:200-202 (commented out upstream: "Impossible Happened in Implied Alignment") records DAG cost 1131 for
+    the invertebrates protein data under the discrete metric; the a = 21 S2 dialect with the discrete closed form gives it."""
+    from tests.helpers import invertebrates_golden
+    children, leaves, _ = invertebrates_golden()
+    assert oracle_mod.reroot_haskell(2, 21, children, leaves)[0] == 1131
