@@ -167,6 +167,8 @@ int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const 
  *   dialect 0 = S1 full matrix   : naiveDO / naiveDOMemo / unboxedSwappingDO
  *   dialect 1 = S1 Ukkonen ribbon: ukkonenDO
  *   dialect 2 = S2 Ukkonen band  : unboxedUkkonenFullSpaceDO  (PCG's production path for a > 8)
+ *   dialect 3 = S2 full matrix   : unboxedFullMatrixDO, with its first column seeded from row 0 as coded upstream
+ *                                  (batch entry points only, a <= 32; a plain kernel — it is not on PCG's dispatch path)
  * Inputs are median strings (what `measureAndUngapCharacters` leaves); outputs per pair: median, aligned first
  * input, aligned second input (0 = gap), at element offset out_off[k] (room for len1+len2 elements).
  * Upstream has neither golden vectors nor (here) an executable for these paths: parity is against the restatement

@@ -576,13 +576,25 @@ static uint64_t hs_fill(const hs_metric_t *mt, int s2, const uint32_t *les, size
     const uint32_t gap = 1u << (mt->a - 1);
     const size_t W = n + 1;
     uint64_t *prev = malloc(sizeof(uint64_t) * W), *cur = malloc(sizeof(uint64_t) * W), cnt = 0;
+    /* s2 bit 0: getMinimalResult's relabel; bit 1: unboxedFullMatrixDO's first column, seeded from ROW 0 —
+     * (i,0) = cost(left_i, gap) + m(0, i-1), "firstPrevCost <- ref (0, i - 1)" (UnboxedFullMatrix.hs:86-90), restated
+     * literally (rows <= columns, so the cell exists) */
+    const int quirk = (s2 & 2) != 0;
+    uint64_t *row0 = quirk ? malloc(sizeof(uint64_t) * W) : NULL;
+    s2 &= 1;
     for (size_t i = 0; i <= m; i++) {
         for (size_t j = 0; j <= n; j++) {
             const long x = (long)j - (long)i;
             if (x < -off || x > (long)(n - m) + off) { cur[j] = HS_INF; continue; }
             cnt++;
-            if (i == 0 && j == 0) { cur[0] = 0; dir[0] = HS_DIAG; continue; }
+            if (i == 0 && j == 0) { cur[0] = 0; dir[0] = HS_DIAG; if (quirk) row0[0] = 0; continue; }
             uint32_t md; uint64_t c;
+            if (quirk && j == 0) {
+                hs_overlap(mt, les[i - 1], gap, &md, &c);
+                cur[0] = row0[i - 1] + c;
+                dir[i * W] = HS_UP;
+                continue;
+            }
             uint64_t best = HS_INF; uint8_t bd = HS_DIAG; int relabel = 0;
             if (i > 0 && j > 0 && prev[j - 1] < HS_INF) {
                 hs_overlap(mt, lon[j - 1], les[i - 1], &md, &c);
@@ -597,18 +609,20 @@ static uint64_t hs_fill(const hs_metric_t *mt, int s2, const uint32_t *les, size
                 if (prev[j] + c < best) { best = prev[j] + c; bd = HS_UP; relabel = 0; }
             }
             cur[j] = best;
+            if (quirk && i == 0) row0[j] = best;
             dir[i * W + j] = relabel ? HS_LEFT : bd;
         }
         uint64_t *t = prev; prev = cur; cur = t;
     }
     const uint64_t res = prev[n];
-    free(prev); free(cur);
+    free(prev); free(cur); free(row0);
     if (cells) *cells += cnt;
     return res;
 }
 
 /* dialect: 0 S1 full (naiveDO / naiveDOMemo / unboxedSwappingDO), 1 S1 Ukkonen (ukkonenDO),
- *          2 S2 Ukkonen (unboxedUkkonenFullSpaceDO).  in1 / in2: median strings (no gap-only elements).
+ *          2 S2 Ukkonen (unboxedUkkonenFullSpaceDO), 3 S2 full with the first column seeded from row 0
+ *          (unboxedFullMatrixDO, as coded).  in1 / in2: median strings (no gap-only elements).
  * Outputs (length *out_len): median, aligned first input, aligned second input (0 = gap). */
 static int64_t hs_do(const hs_metric_t mt, int dialect, int a,
                      const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,
@@ -666,7 +680,9 @@ static int64_t hs_do(const hs_metric_t mt, int dialect, int a,
     if (dialect == 2) no_gain = no_gain || G >= n;
 
     uint64_t cost;
-    if (dialect == 0 || no_gain) {
+    if (dialect == 3) {                                         /* unboxedFullMatrixDO (UnboxedFullMatrix.hs:57-144) */
+        cost = hs_fill(&mt, 3, les, m, lon, n, (long)(m + n + 2), dir, cells);   /* full matrix, S2 cell, row-0-seeded column */
+    } else if (dialect == 0 || no_gain) {
         cost = hs_fill(&mt, 0, les, m, lon, n, (long)(m + n + 2), dir, cells);   /* full matrix, S1 cell */
     } else if (dialect == 1) {                                  /* Ukkonen/Internal.hs:130-202 */
         uint64_t off = 2;

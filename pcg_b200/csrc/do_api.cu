@@ -961,8 +961,12 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     ctx->timed = false;
     ctx->last_launches = 0;
     if (b->n_pairs == 0) return PCGDO_OK;
-    if (dialect < 0 || dialect > 2) {
-        ctx->err = "explicit-matrix path: dialect must be 0..2";
+    if (dialect < 0 || dialect > 3) {
+        ctx->err = "explicit-matrix path: dialect must be 0..3";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    if (dialect == 3 && alphabet > 32) {
+        ctx->err = "dialect 3 (unboxedFullMatrixDO) is built for alphabets of at most 32 symbols";
         return PCGDO_ERR_UNSUPPORTED;
     }
     if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost ||
@@ -984,7 +988,7 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     const int warps = c.warps, grid = ctx->sm_count;
     const size_t smem = c.smem, arena_words = c.arena_words, ts_words = c.ts_words;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->tscratch, (size_t)grid * warps * ts_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->tscratch, (size_t)grid * (dialect == 3 && warps < 8 ? 8 : warps) * ts_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
     ExplicitParams p{};
@@ -1019,7 +1023,10 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.k_one = 1u;
     CK(cudaEventRecord(ctx->ev0, st));
     unsigned int h_left = 0;
-    if (dialect == 0 || !getenv("PCGDO_EXPLICIT_MULTI_PASS")) {
+    if (dialect == 3) {                 // unboxedFullMatrixDO: its own plain kernel (8 warps per CTA, scratch from tscratch)
+        CK(launch_fullmatrix(p, grid, st));
+        ctx->last_launches = 1;
+    } else if (dialect == 0 || !getenv("PCGDO_EXPLICIT_MULTI_PASS")) {
         CK(launch_explicit(p, grid, warps * 32, smem, st));
         ctx->last_launches = 1;
     } else {

@@ -1022,6 +1022,125 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------ dialect 3
+// unboxedFullMatrixDO (DO/Pairwise/UnboxedFullMatrix.hs:48-144): the S2 cell over the full matrix, with its first column
+// seeded from ROW 0 as the reference codes it — (i,0) = cost(left_i, gap) + m(0, i-1) (`ref (0, i - 1)`, :86-90).  Not on
+// PCG's dispatch path (selectDynamicMetric never picks it); kept for the reference's own cross-implementation checks, so
+// this kernel is plain: one warp per pair, lanes across an anti-diagonal, the overlap evaluated per cell (no memo table),
+// values and one direction byte per cell in the warp's global scratch, traceback and medians by lane 0.
+__device__ __forceinline__ uint32_t ov_any(int kind, const uint32_t *sg, int a, uint32_t x, uint32_t y, uint32_t &med)
+{
+    uint32_t c;
+    if (kind == 0) { const uint32_t t = x & y; med = t ? t : (x | y); c = t ? 0u : 1u; }
+    else if (kind == 1) ov_l1(a, x, y, med, c);
+    else ov_explicit(sg, a, x, y, med, c);
+    return c;
+}
+
+__global__ void __launch_bounds__(256) do_fullmatrix_kernel(const ExplicitParams p)
+{
+    const MetricBatchDev &b = p.b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int a = p.a;
+    __shared__ uint32_t sg[32 * 32];
+    if (p.kind == 2)
+        for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = p.sigma[i];
+    __syncthreads();
+    const uint32_t gap = 1u << (a - 1), mask = a >= 32 ? 0xffffffffu : ((1u << a) - 1u);
+    const size_t warp_global = (size_t)blockIdx.x * nwarps + warp, warps_total = (size_t)gridDim.x * nwarps;
+    uint32_t *ts = p.tscratch + warp_global * (size_t)p.tscratch_words;
+    for (size_t k = warp_global; k < b.n_pairs; k += warps_total) {
+        const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+        const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+        bool swapped = n1 > n2;                                     // measureCharacters on the median strings
+        if (n1 == n2) {
+            for (uint32_t bs = 0; bs < n1; bs += 32) {
+                const uint32_t i = bs + lane;
+                uint32_t x = 0, y = 0;
+                if (i < n1) { x = __ldg(p1 + i); y = __ldg(p2 + i); }
+                const unsigned df = __ballot_sync(kFullM, x != y);
+                if (df) {
+                    const int src = __ffs(df) - 1;
+                    swapped = __shfl_sync(kFullM, x, src) > __shfl_sync(kFullM, y, src);
+                    break;
+                }
+            }
+        }
+        const uint32_t *top = swapped ? p1 : p2, *left = swapped ? p2 : p1;        // longer = columns, lesser = rows
+        const int n = (int)(swapped ? n1 : n2), m = (int)(swapped ? n2 : n1);
+        const size_t Wd = (size_t)n + 1;
+        uint32_t *va = ts, *vb = va + (m + 2), *vc = vb + (m + 2), *row0 = vc + (m + 2);
+        uint8_t *dir = reinterpret_cast<uint8_t *>(row0 + Wd);
+        if ((size_t)3 * (m + 2) + Wd + ((size_t)(m + 1) * Wd + 3) / 4 > p.tscratch_words) {
+            if (lane == 0) atomicAdd(p.overflow_count, 1u);
+            continue;
+        }
+        for (int d = 0; d <= m + n; ++d) {
+            const int ilo = max(0, d - n), ihi = min(m, d);
+            for (int i = ilo + lane; i <= ihi; i += 32) {
+                const int j = d - i;
+                uint32_t v, md;
+                uint8_t dr;
+                if (i == 0 && j == 0) { v = 0; dr = 0; }
+                else if (i == 0) { v = vb[0] + ov_any(p.kind, sg, a, gap, __ldg(top + j - 1) & mask, md); dr = 1; }
+                else if (j == 0) { v = row0[i - 1] + ov_any(p.kind, sg, a, __ldg(left + i - 1) & mask, gap, md); dr = 2; }
+                else {
+                    const uint32_t te = __ldg(top + j - 1) & mask, le = __ldg(left + i - 1) & mask;
+                    uint32_t mdd, tmp;
+                    const uint32_t cd = va[i - 1] + ov_any(p.kind, sg, a, te, le, mdd);
+                    const uint32_t cl = vb[i] + ov_any(p.kind, sg, a, te, gap, tmp);
+                    const uint32_t cu = vb[i - 1] + ov_any(p.kind, sg, a, gap, le, tmp);
+                    v = cd; dr = 0;                                  // minimum of (cost, direction): Diag < Left < Up
+                    if (cl < v) { v = cl; dr = 1; }
+                    if (cu < v) { v = cu; dr = 2; }
+                    if (dr == 0 && mdd == gap) dr = 1;               // getMinimalResult
+                }
+                vc[i] = v;
+                if (i == 0) row0[j] = v;
+                dir[(size_t)i * Wd + j] = dr;
+            }
+            __syncwarp();
+            uint32_t *t = va; va = vb; vb = vc; vc = t;
+        }
+        // traceback + outputs (Pairwise/Internal.hs:531-581), lane 0; vb holds the last anti-diagonal
+        if (lane == 0) {
+            b.cost[k] = (int32_t)vb[m];
+            if (b.cells) b.cells[k] = (unsigned long long)(m + 1) * (unsigned long long)(n + 1);
+            if (b.final_offset) b.final_offset[k] = -1;
+            uint32_t nal = 0;
+            for (int i = m, j = n; i > 0 || j > 0; ++nal) {
+                const uint8_t dr = dir[(size_t)i * Wd + j];
+                i -= (dr != 1);
+                j -= (dr != 2);
+            }
+            if (b.out_len) b.out_len[k] = nal;
+            const uint64_t oo = b.out_off ? b.out_off[k] : 0;
+            uint32_t c = nal;
+            for (int i = m, j = n; i > 0 || j > 0;) {
+                const uint8_t dr = dir[(size_t)i * Wd + j];
+                const uint32_t x = dr != 1 ? (__ldg(left + i - 1) & mask) : 0u, y = dr != 2 ? (__ldg(top + j - 1) & mask) : 0u;
+                uint32_t md;
+                if (dr == 1) ov_any(p.kind, sg, a, gap, y, md);
+                else if (dr == 2) ov_any(p.kind, sg, a, x, gap, md);
+                else ov_any(p.kind, sg, a, x, y, md);
+                --c;
+                if (b.out_med) b.out_med[oo + c] = md;
+                if (b.out_a1) b.out_a1[oo + c] = swapped ? y : x;
+                if (b.out_a2) b.out_a2[oo + c] = swapped ? x : y;
+                i -= (dr != 1);
+                j -= (dr != 2);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_fullmatrix(const ExplicitParams &p, int grid, cudaStream_t stream)
+{
+    do_fullmatrix_kernel<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 // per-warp global scratch (32-bit words) for strings of up to max_len elements over `a` symbols:
 // two hash tables, distinct elements, indices, indel costs, profiles, and the table itself (capped)
 size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries)

@@ -7,7 +7,7 @@ namespace pcgdo {
 struct ExplicitParams {
     MetricBatchDev b;
     int       a;              // alphabet size (incl. gap), <= 32
-    int       dialect;        // 0 S1 full, 1 S1 Ukkonen, 2 S2 Ukkonen
+    int       dialect;        // 0 S1 full, 1 S1 Ukkonen, 2 S2 Ukkonen (3 = unboxedFullMatrixDO: its own kernel)
     int       kind;           // 0 discrete metric (closed form, sigma unused), 2 explicit sigma
     int       pack16;         // allow the packed 16-bit fill
     uint32_t  skip_b;         // bit mask of diagonals-per-lane values (2, 4, 8, 16) not to use: round up instead
@@ -33,6 +33,7 @@ struct ExplicitParams {
 
 size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries);
 cudaError_t launch_explicit(const ExplicitParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_fullmatrix(const ExplicitParams &p, int grid, cudaStream_t stream);
 cudaError_t launch_overlap2d(const uint32_t *sigma, int a, size_t n, const uint32_t *e1, const uint32_t *e2,
                              uint32_t *med, uint32_t *cost, int sm_count, cudaStream_t st);
 

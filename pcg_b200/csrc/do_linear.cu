@@ -352,13 +352,13 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
 __device__ __forceinline__ uint32_t trace_lane(const uint32_t *dirw, uint32_t wq, int q0, int lg, int sh, uint32_t *ops)
 {
     int i = lg - 1, j = sh - 1;
-    uint32_t n = 0, acc = 0, cur_idx = 0xffffffffu, cur_word = 0;
+    uint32_t n = 0, acc = 0;
+    DirReader rd(dirw, wq);
     while (i > 0 || j > 0) {
         const int q = j - i + q0;
         const int t = (i + j - (q & 1)) >> 1;
         const uint32_t idx = (uint32_t)(t >> 4) * wq + (uint32_t)q;
-        if (idx != cur_idx) { cur_word = __ldcg(dirw + idx); cur_idx = idx; }
-        const uint32_t code = (cur_word >> (2 * (15 - (t & 15)))) & 3u;
+        const uint32_t code = (rd.get(idx) >> (2 * (15 - (t & 15)))) & 3u;
         acc |= code << (2 * (n & 15));
         ++n;
         if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }

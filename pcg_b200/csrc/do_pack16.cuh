@@ -72,17 +72,18 @@ __device__ __forceinline__ bool rebase16(uint32_t (&R)[H], int &total_shift, uin
 // one lane per pair, packed layout
 __device__ __forceinline__ uint32_t trace_lane16(const uint32_t *dirw, int B, int q0, int lg, int sh, uint32_t *ops)
 {
-    const int H = B >> 1;
+    // B is a power of two (4 .. 32): the walk is one long dependent chain per lane, so no division in it
+    const int H = B >> 1, lh = __ffs(H) - 1;
     int i = lg - 1, j = sh - 1;
-    uint32_t n = 0, acc = 0, cur_idx = 0xffffffffu, cur_word = 0;
+    uint32_t n = 0, acc = 0;
+    DirReader rd(dirw, 32u << lh);
     while (i > 0 || j > 0) {
         const int q = j - i + q0;
         const int t = (i + j - (q & 1)) >> 1;
-        const int ln = q / B, mm = q - ln * B;
-        const int half = mm >= H ? 1 : 0, reg = mm - half * H;
-        const uint32_t idx = (uint32_t)(t >> 3) * (uint32_t)(32 * H) + (uint32_t)(ln * H + reg);
-        if (idx != cur_idx) { cur_word = __ldcg(dirw + idx); cur_idx = idx; }
-        const uint32_t code = (cur_word >> (16 * half + 2 * (7 - (t & 7)))) & 3u;
+        // diagonal q = lane ln, slot mm of its B; slot mm lives in register mm % H, half mm / H
+        const int half = (q >> lh) & 1, col = ((q >> (lh + 1)) << lh) | (q & (H - 1));     // col = ln * H + reg
+        const uint32_t idx = ((uint32_t)(t >> 3) << (lh + 5)) + (uint32_t)col;
+        const uint32_t code = (rd.get(idx) >> (16 * half + 2 * (7 - (t & 7)))) & 3u;
         acc |= code << (2 * (n & 15));
         ++n;
         if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }

@@ -231,7 +231,7 @@ def foreign_pairwise_do(ctx: Context, tcm: Tcm, c1, c2, median_of_gap=None):
 # ------------------------------------------------------------------------------------------------
 # Large alphabets: the Haskell dialects over the discrete metric (reference dispatch: DO/Internal.hs:67-83)
 # ------------------------------------------------------------------------------------------------
-S1_FULL, S1_UKKONEN, S2_UKKONEN = 0, 1, 2      # naiveDO / ukkonenDO / unboxedUkkonenFullSpaceDO
+S1_FULL, S1_UKKONEN, S2_UKKONEN, S2_FULL = 0, 1, 2, 3      # naiveDO / ukkonenDO / unboxedUkkonenFullSpaceDO / unboxedFullMatrixDO
 
 
 @dataclass

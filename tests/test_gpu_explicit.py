@@ -140,3 +140,29 @@ def test_multi_pass_schedule_equals_single_launch(gpu_ctx, monkeypatch):
             for k in range(len(pairs)):
                 for x, y in zip(ref.pair(k)[1:], r.pair(k)[1:]):
                     assert np.array_equal(x, y), (dialect, k)
+
+
+@pytest.mark.parametrize("a,kind", [(12, "discrete"), (21, "explicit"), (9, "l1"), (32, "explicit")])
+def test_unboxed_full_matrix_dialect(oracle_mod, gpu_ctx, a, kind):
+    """Dialect 3 = unboxedFullMatrixDO as coded (S2 cell over the full matrix, first column seeded from row 0,
+    UnboxedFullMatrix.hs:86-90) against the oracle's restatement, all three overlap kinds.  PARITY UNPINNED upstream."""
+    from pcg_b200.pairwise import metric_do_batch, S2_FULL
+    rng = np.random.default_rng(600 + a)
+    sg = _sigma("random-sym", a, rng) if kind == "explicit" else None
+    pairs = _pairs(rng, a, 150, 90)
+    # strings whose best alignment opens with deletions of the lesser string: the seeded first column decides
+    for _ in range(20):
+        s = _rand_str(rng, 40, a)
+        pairs.append((np.concatenate([_rand_str(rng, int(rng.integers(1, 6)), a), s]), np.concatenate([s, _rand_str(rng, 8, a)])))
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=128, max_b=32, arena_words=0)
+    memo = gpu_ctx.memo(sg, kind, a=a)
+    r = metric_do_batch(gpu_ctx, memo, S2_FULL, [p[0] for p in pairs], [p[1] for p in pairs])
+    differs = 0
+    for k, (s1, s2) in enumerate(pairs):
+        oc = oracle_mod.haskell_do(3, a, s1, s2, sigma=sg, metric_kind={"discrete": 0, "explicit": 1, "l1": 2}[kind])
+        gc = r.pair(k)
+        assert gc[0] == oc[0], (k, len(s1), len(s2), gc[0], oc[0])
+        for x, y in zip(gc[1:], oc[1:4]):
+            assert np.array_equal(x, y), (k, len(s1), len(s2))
+        differs += oc[0] != oracle_mod.haskell_do(0, a, s1, s2, sigma=sg, metric_kind={"discrete": 0, "explicit": 1, "l1": 2}[kind])[0]
+    assert int(r.cells[0]) == (len(pairs[0][0]) + 1) * (len(pairs[0][1]) + 1)
