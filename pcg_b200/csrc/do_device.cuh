@@ -56,34 +56,6 @@ struct BatchDev {
     unsigned int       *pack_overflow;
 };
 
-// Direction-word reader of the tracebacks (one lane per pair, one long dependent chain per lane).  The walk moves towards
-// smaller iteration blocks: row r of the direction matrix, then r-1, ... (`stride` words apart), drifting a diagonal or two
-// sideways per row.  By the time it happens the words have left the L2 (the fill of the warp's other pairs streams tens of
-// MB through it), so an on-demand load pays an HBM round trip every few steps — the bulk of a launch's final trace phase.
-// Here the word straight above (same diagonal, row r-1) is loaded speculatively when row r is entered, and row r-2's
-// sector is prefetched into L2, so the on-demand path mostly finds its word in a register or in L2.
-struct DirReader {
-    const uint32_t *dirw;
-    uint32_t stride;
-    uint32_t cur_idx = 0xffffffffu, cur_word = 0, pre_idx = 0xffffffffu, pre_word = 0;
-    __device__ __forceinline__ DirReader(const uint32_t *d, uint32_t s) : dirw(d), stride(s) {}
-    __device__ __forceinline__ uint32_t get(uint32_t idx)
-    {
-        if (idx != cur_idx) {
-            cur_word = (idx == pre_idx) ? pre_word : __ldcg(dirw + idx);
-            cur_idx = idx;
-            if (idx >= stride) {
-                pre_idx = idx - stride;
-                pre_word = __ldcg(dirw + pre_idx);
-                if (pre_idx >= stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(dirw + (pre_idx - stride)));
-            } else {
-                pre_idx = 0xffffffffu;
-            }
-        }
-        return cur_word;
-    }
-};
-
 __device__ __forceinline__ void pack_claim(const BatchDev &b, uint32_t k, uint32_t n)
 {
     const unsigned long long sz = ((unsigned long long)n + b.pack_gran) & ~(unsigned long long)b.pack_gran;

@@ -351,19 +351,21 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t trace_lane(const uint32_t *dirw, uint32_t wq, int q0, int lg, int sh, uint32_t *ops)
 {
-    int i = lg - 1, j = sh - 1;
-    uint32_t n = 0, acc = 0;
-    DirReader rd(dirw, wq);
-    while (i > 0 || j > 0) {
-        const int q = j - i + q0;
-        const int t = (i + j - (q & 1)) >> 1;
-        const uint32_t idx = (uint32_t)(t >> 4) * wq + (uint32_t)q;
-        const uint32_t code = (rd.get(idx) >> (2 * (15 - (t & 15)))) & 3u;
+    int s = (lg - 1) + (sh - 1), q = (sh - 1) - (lg - 1) + q0;        // (i + j, diagonal): see trace_lane16
+    uint32_t n = 0, acc = 0, w = 0;
+    int sft = 32;
+    while (s > 0) {
+        if (sft == 32) {
+            const int t = (s - (q & 1)) >> 1;
+            w = __ldcg(dirw + ((uint32_t)(t >> 4) * wq + (uint32_t)q));
+            sft = 2 * (15 - (t & 15));
+        }
+        const uint32_t code = (w >> sft) & 3u;
         acc |= code << (2 * (n & 15));
         ++n;
         if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
-        i -= (code != 2u);
-        j -= (code != 1u);
+        if (code == 0u) { s -= 2; sft += 2; }
+        else { s -= 1; q += (code == 1u) ? 1 : -1; sft = 32; }
     }
     if (n & 15) ops[n >> 4] = acc;
     return n;

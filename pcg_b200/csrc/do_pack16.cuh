@@ -72,23 +72,29 @@ __device__ __forceinline__ bool rebase16(uint32_t (&R)[H], int &total_shift, uin
 // one lane per pair, packed layout
 __device__ __forceinline__ uint32_t trace_lane16(const uint32_t *dirw, int B, int q0, int lg, int sh, uint32_t *ops)
 {
-    // B is a power of two (4 .. 32): the walk is one long dependent chain per lane, so no division in it
+    // B is a power of two (4 .. 32).  The walk is one long dependent chain per lane — and, with one lane per pair, an
+    // instruction stream the warp issues in full however few of its lanes hold a pair (a launch with 2 pairs per warp
+    // spent a third of its instructions here).  State is (s, q) = (i + j, diagonal); an ALIGN move stays on its diagonal
+    // and, 7 times out of 8, inside its direction word: only the other moves recompute the word's address.  One move per
+    // iteration for every lane, so the lanes of a warp stay in step.
     const int H = B >> 1, lh = __ffs(H) - 1;
-    int i = lg - 1, j = sh - 1;
-    uint32_t n = 0, acc = 0;
-    DirReader rd(dirw, 32u << lh);
-    while (i > 0 || j > 0) {
-        const int q = j - i + q0;
-        const int t = (i + j - (q & 1)) >> 1;
-        // diagonal q = lane ln, slot mm of its B; slot mm lives in register mm % H, half mm / H
-        const int half = (q >> lh) & 1, col = ((q >> (lh + 1)) << lh) | (q & (H - 1));     // col = ln * H + reg
-        const uint32_t idx = ((uint32_t)(t >> 3) << (lh + 5)) + (uint32_t)col;
-        const uint32_t code = (rd.get(idx) >> (16 * half + 2 * (7 - (t & 7)))) & 3u;
+    int s = (lg - 1) + (sh - 1), q = (sh - 1) - (lg - 1) + q0;
+    uint32_t n = 0, acc = 0, w = 0;
+    int sft = 16;
+    while (s > 0) {
+        if (sft == 16) {
+            const int t = (s - (q & 1)) >> 1;
+            // diagonal q = lane ln, slot mm of its B; slot mm lives in register mm % H, half mm / H
+            const int half = (q >> lh) & 1, col = ((q >> (lh + 1)) << lh) | (q & (H - 1));     // col = ln * H + reg
+            w = __ldcg(dirw + (((uint32_t)(t >> 3) << (lh + 5)) + (uint32_t)col)) >> (16 * half);
+            sft = 2 * (7 - (t & 7));
+        }
+        const uint32_t code = (w >> sft) & 3u;
         acc |= code << (2 * (n & 15));
         ++n;
         if ((n & 15) == 0) { ops[(n >> 4) - 1] = acc; acc = 0; }
-        i -= (code != 2u);
-        j -= (code != 1u);
+        if (code == 0u) { s -= 2; sft += 2; }
+        else { s -= 1; q += (code == 1u) ? 1 : -1; sft = 16; }      // 1: consume longer (i--), 2: consume lesser (j--)
     }
     if (n & 15) ops[n >> 4] = acc;
     return n;
