@@ -178,11 +178,11 @@ int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const 
 typedef struct pcgdo_batch32 {
     size_t          n_pairs;
     const uint32_t *elems;
-    size_t          elems_count;     /* host variant: elements to copy in              */
+    size_t          elems_count;     /* host variant: 32-bit words to copy in          */
     const uint64_t *off1, *off2;     /* element offsets                                */
     const uint32_t *len1, *len2;
     const uint64_t *out_off;
-    size_t          out_count;       /* host variant: elements to copy back per array  */
+    size_t          out_count;       /* host variant: 32-bit words to copy back per array */
     uint32_t       *out_med, *out_a1, *out_a2;
     uint32_t       *out_len;
     int32_t        *cost;

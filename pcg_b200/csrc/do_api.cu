@@ -114,6 +114,8 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     delete ctx;
 }
 
