@@ -729,6 +729,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 long long off = p.dialect == 2 ? 2 + Gc : 2;
                 if (p.in_list) off = p.pair_off[k];                  // a later pass: the offset this pair was queued with
                 bool requeue = false;
+                long long jump_base = 0;                         // first skipped level while a jump of the schedule is unchecked
+                bool may_jump = p.skip_ahead && !p.out_list;     // (one failed jump per pair, then level by level)
 
                 // ---------------- number the distinct elements, build profiles, indel costs and the pair's table
                 const uint32_t HL = x_hash_size((uint32_t)n), HS = x_hash_size((uint32_t)m);
@@ -935,9 +937,37 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     if (full) break;
                     const long long cost = (long long)((fw >> 2) - (kBias4 >> 2) + csum);
                     if (p.dialect == 2) {
+                        // The reference doubles the offset until the threshold exceeds the band's cost, re-filling at every
+                        // level.  cost(offset) never grows with the offset, so a fill further up the schedule settles the
+                        // levels it skipped: they would all have doubled if threshold(o) <= cost(later band) for the largest
+                        // of them (thresholds grow with o).  After a level that doubles, `first_stop` is the first level that
+                        // must stop given this level's cost (an upper bound on every later cost): the schedule jumps there
+                        // when that level is at most 4x the cells of this one, and falls back — to the first level that may
+                        // stop given the jumped-to band's cost, sequentially from there — when the check fails.  Same final
+                        // offset, band and alignment as level-by-level doubling (final_offset is compared with the oracle's).
+                        auto thr2 = [&](long long o) { return (qd + o <= Gc) ? 0ll : delta * (qd + o - Gc); };
+                        auto first_stop = [&](long long from, long long c) {
+                            long long o = from;
+                            while (!(qd + o > n) && !(thr2(o) > c)) o *= 2;
+                            return o;
+                        };
+                        if (jump_base) {                       // this fill was a jump: were the skipped levels sure to double?
+                            const long long base = jump_base;
+                            jump_base = 0;
+                            if (thr2(off / 2) > cost) { off = first_stop(base, cost); may_jump = false; continue; }
+                        }
                         if (qd + off > n) break;
-                        const long long thr = (qd + off <= Gc) ? 0 : delta * (qd + off - Gc);
-                        if (thr <= cost) off *= 2; else break;
+                        if (thr2(off) > cost) break;
+                        const long long nxt = off * 2;
+                        off = nxt;
+                        if (may_jump) {
+                            const long long L = first_stop(nxt, cost);
+                            auto cells_of = [&](long long o) {
+                                const long long a_o = o < m ? o : m, w = 2 * a_o + qd;
+                                return (w < sh ? w : (long long)sh) * lg;
+                            };
+                            if (L > nxt && cells_of(L) <= 4 * cells_of(nxt / 2)) { jump_base = nxt; off = L; }
+                        }
                     } else {
                         long long thr = delta * (qd + off - Gc);
                         if (thr < 0) thr = 0;
