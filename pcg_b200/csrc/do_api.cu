@@ -935,7 +935,7 @@ int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, in
     p.dialect = dialect;
     p.kind = memo ? memo->kind : 0;
     p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
-    p.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : 1;
+    p.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : getenv("PCGDO_SKIP_FACTOR") ? atoi(getenv("PCGDO_SKIP_FACTOR")) : 64;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
     p.delta = memo ? memo->delta : 1u;
     p.k_64k = 65536u;
@@ -1008,7 +1008,7 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.dialect = dialect;
     p.kind = memo ? memo->kind : 0;
     p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
-    p.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : 1;
+    p.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : getenv("PCGDO_SKIP_FACTOR") ? atoi(getenv("PCGDO_SKIP_FACTOR")) : 64;
     p.skip_b = getenv("PCGDO_SKIP_B") ? (uint32_t)atoi(getenv("PCGDO_SKIP_B")) : 0u;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
     p.delta = memo ? memo->delta : 1u;

@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                         // levels it skipped: they would all have doubled if threshold(o) <= cost(later band) for the largest
                         // of them (thresholds grow with o).  After a level that doubles, `first_stop` is the first level that
                         // must stop given this level's cost (an upper bound on every later cost): the schedule jumps there
-                        // when that level is at most 4x the cells of this one, and falls back — to the first level that may
+                        // when that level is at most skip_ahead (64) x the cells of this one, and falls back — to the first level that may
                         // stop given the jumped-to band's cost, sequentially from there — when the check fails.  Same final
                         // offset, band and alignment as level-by-level doubling (final_offset is compared with the oracle's).
                         auto thr2 = [&](long long o) { return (qd + o <= Gc) ? 0ll : delta * (qd + o - Gc); };
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                                 const long long a_o = o < m ? o : m, w = 2 * a_o + qd;
                                 return (w < sh ? w : (long long)sh) * lg;
                             };
-                            if (L > nxt && cells_of(L) <= 4 * cells_of(nxt / 2)) { jump_base = nxt; off = L; }
+                            if (L > nxt && cells_of(L) <= (long long)p.skip_ahead * cells_of(nxt / 2)) { jump_base = nxt; off = L; }
                         }
                     } else {
                         long long thr = delta * (qd + off - Gc);

@@ -10,7 +10,8 @@ struct ExplicitParams {
     int       dialect;        // 0 S1 full, 1 S1 Ukkonen, 2 S2 Ukkonen (3 = unboxedFullMatrixDO: its own kernel)
     int       kind;           // 0 discrete metric (closed form, sigma unused), 2 explicit sigma
     int       pack16;         // allow the packed 16-bit fill
-    int       skip_ahead;     // dialect 2: let the doubling schedule jump levels it can prove would double
+    int       skip_ahead;     // dialect 2: let the doubling schedule jump levels it can prove would double, to a band of at
+                              // most this many times the current one's cells (0 = plain level-by-level doubling)
     uint32_t  skip_b;         // bit mask of diagonals-per-lane values (2, 4, 8, 16) not to use: round up instead
     const uint32_t *sigma;    // device [a*a]: sigma[s*a + j], s = median symbol, j = input symbol
     uint32_t  delta;          // cheapest indel of a single non-gap symbol (Ukkonen coefficient)
