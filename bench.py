@@ -852,6 +852,9 @@ def main():
                 "frac": achieved_tops / int_peak if int_peak else None, "traffic": traffic,
                 "peak_source": "measured live (pcgdo_int32_peak: independent VIADDMNMX+IMAD chains on all SMs)",
                 "alg_ops_per_cell": ALG_OPS_PER_CELL, "kernel_ms": k_ms,
+                # the stricter denominator: both integer pipes issuing every cycle, as the dedicated micro-benchmark
+                # reaches (profiles/r01_int_pipes_ubench.txt: 125.6 of 128 lane-instructions per clock per SM at 1965 MHz)
+                "frac_vs_dual_pipe_peak": achieved_tops / 36.5, "dual_pipe_peak": 36.5,
                 "hbm": {"alg_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak}}
