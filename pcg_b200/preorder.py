@@ -1,0 +1,103 @@
+"""Host-side mirror of the pre-order pass's primitives for dynamic characters — the pure list scans the
+reference runs after the alignments, restated literally; no alignment work happens here.
+
+Reference (DO = lib/core/analysis/src/Analysis/Parsimony/Dynamic/DirectOptimization):
+* ``get_context``                  — ``getContext`` (lib/core/data-structures/src/Bio/Character/Encodable/Dynamic/Element.hs:140-146)
+* ``derive_implied_alignment``     — ``deriveImpliedAlignment`` (DO/Internal.hs:236-286)
+* ``lexically_disambiguate``       — ``lexicallyDisambiguate`` / ``disambiguateElement`` (DO/Internal.hs:186-211)
+* ``preorder_implied_alignments``  — ``directOptimizationPreorder`` over a rooted tree: ``initializeRoot`` (:166-177) and
+                                     ``updateFromParent`` (:216-233).  The reference drives it from the re-rooted traversal
+                                     foci (``preorderFromRooting``, Bio/Graph/PhylogeneticDAG/Preorder.hs:359-520); that
+                                     driver is NOT mirrored — see DESIGN.md, row (f)3: upstream offers nothing to pin it
+                                     against (its golden file prints the alignment context in the implied-alignment field,
+                                     its script tests are disabled where the pass fails).
+
+A dynamic character is ``None`` (Missing) or an (n, 3) array of (median, left, right) ambiguity sets.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+GAPPING, DELETION, INSERTION, ALIGNMENT = 0, 1, 2, 3
+
+
+def get_context(e) -> int:
+    """(left, right) non-empty? -> Gapping / Deletion (right only) / Insertion (left only) / Alignment."""
+    left, right = int(e[1]) != 0, int(e[2]) != 0
+    return ALIGNMENT if (left and right) else INSERTION if left else DELETION if right else GAPPING
+
+
+def derive_implied_alignment(is_left_child: bool, p_alignment: np.ndarray, p_context: np.ndarray,
+                             c_context: np.ndarray, gap: int) -> np.ndarray:
+    """The child's final alignment from the parent's final alignment, the parent's preliminary context and the child's
+    preliminary context: one fold over the parent's alignment (same length out)."""
+    gap_elem = (gap, 0, 0)                                   # gapElement
+    xs = [tuple(int(v) for v in t) for t in c_context]
+    ys = [tuple(int(v) for v in t) for t in p_context]
+    xi = yi = 0
+    ys_dropped = False
+    acc = []
+    for e in p_alignment:
+        if xi >= len(xs):                                    # go (acc, [], _) _ = (gap : acc, [], [])
+            acc.append(gap_elem)
+            ys_dropped = True
+            continue
+        if ys_dropped or yi >= len(ys):
+            raise RuntimeError("Impossible happened in 'deriveImpliedAlignment'")     # as the reference
+        c = get_context(e)
+        x, y = xs[xi], ys[yi]
+        if c == GAPPING:
+            acc.append(tuple(int(v) for v in e))
+        elif c == ALIGNMENT:
+            acc.append(x); xi += 1; yi += 1
+        elif c == DELETION:
+            if get_context(y) == DELETION and not is_left_child:
+                acc.append(x); xi += 1; yi += 1
+            else:
+                acc.append(gap_elem); yi += 1
+        else:
+            if get_context(y) == INSERTION and is_left_child:
+                acc.append(x); xi += 1; yi += 1
+            else:
+                acc.append(gap_elem); yi += 1
+    dtype = np.asarray(p_alignment).dtype
+    return np.array(acc, dtype=dtype).reshape(-1, 3)
+
+
+def lexically_disambiguate(char: np.ndarray, a: int) -> np.ndarray:
+    """Every element becomes (v, v, v) with v the single symbol at index min(a - 1, countLeadingZeros median); bv-little
+    counts "leading" zeros from index 0 (pinned by the L1 script costs), so v is the LOWEST set symbol, and
+    an empty median gives the gap."""
+    out = np.zeros_like(char)
+    for k, e in enumerate(char):
+        m = int(e[0]) & ((1 << a) - 1)
+        idx = min(a - 1, (m & -m).bit_length() - 1) if m else a - 1
+        out[k] = (1 << idx,) * 3
+    return out
+
+
+def preorder_implied_alignments(children: np.ndarray, n_taxa: int, contexts: Dict[int, Optional[np.ndarray]], a: int,
+                                root: Optional[int] = None):
+    """Final (implied) alignments and single disambiguations of every node below ``root`` (default: the tree's root) from
+    the post-order contexts, in the node numbering of ``pcg_b200.Forest`` (internal node x = n_taxa + x)."""
+    gap = 1 << (a - 1)
+    kids = {n_taxa + x: (int(children[x, 0]), int(children[x, 1])) for x in range(len(children))}
+    if root is None:
+        is_child = {c for pair in kids.values() for c in pair}
+        root = next(n for n in kids if n not in is_child)
+    ia = {root: contexts[root]}                                                   # initializeRoot
+    single = {root: None if contexts[root] is None else lexically_disambiguate(contexts[root], a)}
+    stack = [root]
+    while stack:
+        p = stack.pop()
+        for side, c in enumerate(kids.get(p, ())):
+            cac = contexts[c]
+            if cac is None or ia[p] is None:                                      # isMissing: inherit the parent's
+                ia[c], single[c] = ia[p], single[p]
+            else:
+                ia[c] = derive_implied_alignment(side == 0, ia[p], contexts[p], cac, gap)
+                single[c] = lexically_disambiguate(ia[c], a)
+            stack.append(c)
+    return ia, single

@@ -406,3 +406,36 @@ def test_large_alphabet_forest_protein_discrete_cost(gpu_ctx):
     f.enable_rerooting()
     assert int(f.score_rerooted(None)[0]) == 1131
     f.close()
+
+
+def test_preorder_implied_alignments_over_device_contexts(gpu_ctx):
+    """Post-order contexts aligned on the device (postorder_contexts), then the pre-order primitives over them
+    (pcg_b200.preorder): all implied alignments share the root's length, each node's ungapped implied alignment is its own
+    ungapped median string (for a leaf: its sequence), and no "Impossible happened" branch is reached."""
+    from pcg_b200.postorder import postorder_contexts, random_binary_trees
+    from pcg_b200.preorder import preorder_implied_alignments
+    from tests.helpers import tcm_matrix, random_string
+    rng = np.random.default_rng(41)
+    n_taxa = 24
+    children = random_binary_trees(3, n_taxa, 5)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=512, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(tcm_matrix("discrete"))
+    for t in range(3):
+        base = random_string(rng, 120, amb=0.05)
+        leaves = []
+        for _ in range(n_taxa):                         # related sequences: mutations and indels of one ancestor
+            s = base.copy()
+            mut = rng.random(len(s)) < 0.1
+            s[mut] = random_string(rng, int(mut.sum()), amb=0.0)
+            s = s[rng.random(len(s)) > 0.05]
+            leaves.append(s[s != 16])
+        ctxs, local, total = postorder_contexts(gpu_ctx, tcm, children[t], n_taxa, leaves)
+        ia, single = preorder_implied_alignments(children[t], n_taxa, ctxs, 5)
+        root_len = len(ia[max(ia, key=lambda n: len(ia[n]))])
+        assert len(ia) == 2 * n_taxa - 1 and {len(v) for v in ia.values()} == {root_len}
+        for n, v in ia.items():
+            med, own = v[:, 0], ctxs[n][:, 0]
+            assert np.array_equal(med[med != 16], own[own != 16]), (t, n)
+        for v in range(n_taxa):
+            med = ia[v][:, 0]
+            assert np.array_equal(med[med != 16], leaves[v]), (t, v)

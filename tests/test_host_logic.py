@@ -80,3 +80,49 @@ def test_wrapper_on_golden_nodes(oracle_mod):
     for i, (cost, ctx) in zip(ids, got):
         assert cost == nodes[i]["local_cost"]
         assert ctx.tolist() == nodes[i]["context"]
+
+
+def test_preorder_primitives_on_golden_subtree():
+    """deriveImpliedAlignment / lexicallyDisambiguate (DO/Internal.hs:186-286) on the reference's own post-order contexts
+    (chel golden, the subtree under node 1, which re-rooting leaves untouched): every node's implied alignment has the
+    root's length, no "Impossible happened" branch is reached, ungapping a leaf's implied alignment gives back the leaf's
+    sequence, and an internal node's gives back its ungapped median string.  (Upstream offers no vector to pin the pass
+    against: its golden file prints the alignment context in the implied-alignment field.)"""
+    import json
+    from pcg_b200 import preorder as PR
+    from tests.helpers import ROOT
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "chel_golden.json")))
+    ctx = {n["id"]: np.array(n["context"], np.uint8) for n in g["nodes"]}
+    kids = {n["id"]: sorted(n["children"]) for n in g["nodes"] if n["children"]}
+    root, gap, a = 1, 16, 5
+    ia = {root: ctx[root]}
+    stack = [root]
+    while stack:
+        p = stack.pop()
+        for side, c in enumerate(kids.get(p, ())):
+            ia[c] = PR.derive_implied_alignment(side == 0, ia[p], ctx[p], ctx[c], gap)
+            stack.append(c)
+    assert len(ia) == 29 and {len(v) for v in ia.values()} == {len(ctx[root])}
+    for n, v in ia.items():
+        med = v[:, 0]
+        own = ctx[n][:, 0]
+        assert np.array_equal(med[med != gap], own[own != gap]), n
+    single = PR.lexically_disambiguate(ia[9], a)
+    assert single.shape == ia[9].shape and all(bin(int(x)).count("1") == 1 for x in single[:, 0])
+    assert (single[:, 0] == single[:, 1]).all() and (single[:, 0] == single[:, 2]).all()
+
+
+def test_preorder_primitive_cases():
+    from pcg_b200 import preorder as PR
+    assert [PR.get_context(e) for e in ((16, 0, 0), (3, 0, 2), (3, 1, 0), (3, 1, 2))] == \
+        [PR.GAPPING, PR.DELETION, PR.INSERTION, PR.ALIGNMENT]
+    # lowest set symbol; an empty median disambiguates to the gap
+    d = PR.lexically_disambiguate(np.array([[6, 6, 6], [16, 0, 0], [0, 0, 0], [24, 8, 16]], np.uint8), 5)
+    assert d[:, 0].tolist() == [2, 16, 16, 8]
+    # a parent insertion column (left only) is taken by the LEFT child only when the parent's context has it too
+    pa = np.array([[1, 1, 0], [2, 2, 2]], np.uint8)
+    pc = np.array([[1, 1, 0], [2, 2, 2]], np.uint8)
+    cc = np.array([[1, 1, 1], [2, 2, 2]], np.uint8)
+    assert PR.derive_implied_alignment(True, pa, pc, cc, 16).tolist() == [[1, 1, 1], [2, 2, 2]]
+    cr = np.array([[2, 2, 2]], np.uint8)
+    assert PR.derive_implied_alignment(False, pa, pc, cr, 16).tolist() == [[16, 0, 0], [2, 2, 2]]
