@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                         // must stop given this level's cost (an upper bound on every later cost): the schedule jumps there
                         // when that level is at most skip_ahead (64) x the cells of this one, and falls back — to the first level that may
                         // stop given the jumped-to band's cost, sequentially from there — when the check fails.  Same final
-                        // offset, band and alignment as level-by-level doubling (final_offset is compared with the oracle's).
+                        // offset, band and alignment as level-by-level doubling (final_offset is part of what the parity tests compare).
                         auto thr2 = [&](long long o) { return (qd + o <= Gc) ? 0ll : delta * (qd + o - Gc); };
                         auto first_stop = [&](long long from, long long c) {
                             long long o = from;
