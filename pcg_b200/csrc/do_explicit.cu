@@ -637,6 +637,34 @@ __device__ __forceinline__ uint32_t x_number(const uint32_t *str, int len, uint3
     return D;
 }
 
+// Stage one fill's row offsets (bytes into the pair's table) and column offsets (+ the table's shared address), returning
+// the indel costs folded out of the cell values.  Its own function: inside the kernel body these loops ran on spilled
+// pointers (the body holds the whole schedule's state at 128 registers) — 10 % of the config-4 stall samples.
+__device__ __noinline__ uint32_t x_stage(uint32_t *Lr, uint32_t *Sr, int sizeL, int offL, int sizeS, int offS, int lg, int sh,
+                                         const uint32_t *idxL, const uint32_t *idxS, const uint32_t *cL, const uint32_t *gS,
+                                         uint32_t rowb, uint32_t sbase, int lane)
+{
+    uint32_t csum = 0;
+    for (int idx = lane; idx < sizeL; idx += 32) {
+        const int i = idx - offL;
+        uint32_t d = 0;
+        if (i == 0) d = 1;
+        else if (i > 0 && i < lg) { d = idxL[i - 1]; csum += cL[d]; }
+        Lr[idx] = d * rowb;
+    }
+    for (int idx = lane; idx < sizeS; idx += 32) {
+        const int j = idx - offS;
+        uint32_t d = 0;
+        if (j == 0) d = 1;
+        else if (j > 0 && j < sh) { d = idxS[j - 1]; csum += gS[d]; }
+        Sr[idx] = d * 2u + sbase;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFullM, csum, d);
+    __syncwarp();
+    return csum;
+}
+
 extern __shared__ __align__(16) char x_smem[];
 
 template <bool WIDE>
@@ -903,25 +931,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     if (cur + need > p.arena_words) break;
                     // stage row offsets (bytes into the table) and column offsets (+ the table's shared address)
                     uint32_t *Sr = seq, *Lr = seq + sl.sizeS;
-                    csum = 0;
-                    const uint32_t rowb = Wt * 2u, sbase = gtable ? 0u : tab32;
-                    for (int idx = lane; idx < sl.sizeL; idx += 32) {
-                        const int i = idx - sl.offL;
-                        uint32_t d = 0;
-                        if (i == 0) d = 1;
-                        else if (i > 0 && i < lg) { d = idxL[i - 1]; csum += cL[d]; }
-                        Lr[idx] = d * rowb;
-                    }
-                    for (int idx = lane; idx < sl.sizeS; idx += 32) {
-                        const int j = idx - sl.offS;
-                        uint32_t d = 0;
-                        if (j == 0) d = 1;
-                        else if (j > 0 && j < sh) { d = idxS[j - 1]; csum += gS[d]; }
-                        Sr[idx] = d * 2u + sbase;
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFullM, csum, d);
-                    __syncwarp();
+                    csum = x_stage(Lr, Sr, sl.sizeL, sl.offL, sl.sizeS, sl.offS, lg, sh, idxL, idxS, cL, gS, Wt * 2u,
+                                   gtable ? 0u : tab32, lane);
                     uint32_t *slot = arena + cur;
                     used16 = packed && B >= 4;
                     if (used16) {
