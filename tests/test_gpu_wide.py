@@ -82,6 +82,8 @@ def _wide_pairs(rng, a, count, max_len):
     out += [(s, s.copy()), (s[:7], s[:7].copy())]          # equal strings: measureCharacters falls through to EQ
     t = s.copy()
     t[20, -1] ^= np.uint32(1)                               # equal length, first difference in the most significant word
+    if not t[20].any():                                     # (never an empty ambiguity set: not a valid element)
+        t[20, -1] = np.uint32(2)
     out.append((s, t))
     return out
 
