@@ -1,5 +1,6 @@
 """GPU stress: the parity checks of tests/ with fresh random seeds, for a wall-clock budget (seconds, argv[1]).
 Prints the seed of any mismatch and exits 1.  Test infrastructure (uses the oracle); not part of the product."""
+import os
 import sys
 import time
 
@@ -31,9 +32,14 @@ while time.time() < t_end:
         o = O.Oracle(sig)
         ctx.configure(pairs_per_warp=int(rng.choice([2, 8, 32])), warps_per_cta=32, max_len=700, max_b=32, arena_words=0)
         tcm = ctx.tcm(sig)
-        pairs = [random_pair(rng, int(rng.choice([60, 250, 650]))) for _ in range(400)]
+        pairs = [random_pair(rng, int(rng.choice([60, 250, 650]))) for _ in range(1200)]
         pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
-        r = P.align2d_batch(ctx, tcm, pp, want_cells=True)
+        # every other round through the pipelined host path with packed outputs (tiny chunks: 6 chunks, ring of 3 slots)
+        compact = bool(seed & 1)
+        os.environ["PCGDO_HOST_CHUNK_PAIRS"] = "256" if compact else "1048576"
+        r = P.align2d_batch(ctx, tcm, pp, want_cells=True, compact=compact, pinned=bool(seed & 2))
+        if compact:                          # rounds whose outputs really came back packed (not the plain fallback)
+            n_checked["packed_rounds"] = n_checked.get("packed_rounds", 0) + int((r.out_off != pp.out_off).any())
         for k, (s1, s2) in enumerate(pairs):
             oc = o.align2d(s1, s2)
             gc = r.pair(pp, k)
