@@ -59,9 +59,32 @@ typedef struct cost_matrices_2d_t {
     unsigned int *tail_cost;
 } cost_matrices_2d_t;
 
+/* EXT/costMatrix.h:102-130 — what setUp3dCostMtx fills.  PCG builds it next to every 2D matrix
+ * (Data/TCM/Dense/FFI.hsc:461-476) although the 3D aligner itself is disabled upstream (DO/Pairwise.hs:18). */
+typedef struct cost_matrices_3d_t {
+    size_t        alphSize;
+    size_t        costMatrixDimension;
+    elem_t        gap_char;
+    int           cost_model_type;
+    int           include_ambiguities;
+    unsigned int  gap_open_cost;
+    size_t        num_elements;
+    unsigned int *cost;
+    elem_t       *median;
+} cost_matrices_3d_t;
+
 /* Builds the dense 2^a x 2^a cost / median tables on the host (same loops and the same
  * sigma[pos*a + nucleotide] indexing as the reference) into caller-provided storage. */
 void setUp2dCostMtx(cost_matrices_2d_t *retMtx, unsigned int *tcm, size_t alphSize, unsigned int gap_open);
+
+/* EXT/c_code_alloc_setup.c:208-270 — the three-way tables, (2^a + 1)^3 entries each, indexed
+ * (((e1 << a) + e2) << a) + e3 (EXT/costMatrix.c:111-120): setup-time host work like setUp2dCostMtx, bound at
+ * Data/TCM/Dense/FFI.hsc:327-334.  Same sums of `distance` and the same median-set rule as the reference. */
+void setUp3dCostMtx(cost_matrices_3d_t *retMtx, unsigned int *tcm, size_t alphSize, unsigned int gap_open);
+
+/* EXT/c_code_alloc_setup.c:52-66: frees the tables AND the struct (both malloc'ed, as PCG allocates them); also drops
+ * the device copy the align2d / align2dAffine shims cache for a 2D matrix. */
+void freeCostMtx(void *input, int is_2d);
 
 /* Pairwise DO of one pair on the GPU.  Same contract as the reference's align2d for the flag
  * combination PCG uses (getUngapped=0, getGapped=1, getUnion=0): on return
@@ -103,6 +126,9 @@ const char *pcgdo_last_error(const pcgdo_ctx *ctx);
  *   max_len        : longest string (elements, without the leading gap) the fast path must hold
  *                    in shared memory; longer pairs take the general-geometry kernel            */
 int pcgdo_configure(pcgdo_ctx *ctx, int pairs_per_warp, int warps_per_cta, int max_len);
+/* The experiment switches of DESIGN.md (PCGDO_* environment variables) are read once, in pcgdo_create; this re-reads
+ * them (tests flip them between calls).  No entry point consults the environment on its own. */
+int pcgdo_configure_env(pcgdo_ctx *ctx);
 
 /* sigma: a*a row-major symbol-change costs, gap is symbol a-1.  a <= 8. */
 int  pcgdo_tcm_create(pcgdo_ctx *ctx, const unsigned int *sigma, size_t a, unsigned int gap_open, pcgdo_tcm **out);
@@ -229,15 +255,26 @@ int  pcgdo_overlap2d_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, size_t n
 int  pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b, void *cuda_stream);
 int  pcgdo_explicit_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b);
 
+/* n independent lookups over alphabets of up to PCGDO_MAX_ALPHABET symbols and over two OR THREE sets (nsets = 2 / 3;
+ * e3 ignored for 2): set k of array ex is the W = ceil(a / 32) words ex[k*W .. k*W+W), median[k*W ..] likewise.  The
+ * three-set form is costMatrix_3d.cpp:168-211 (computeCostMedian over three keys).  One warp per lookup. */
+int  pcgdo_overlap_sets_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int nsets, size_t n, const uint32_t *e1,
+                                     const uint32_t *e2, const uint32_t *e3, uint32_t *median, uint32_t *cost, void *cuda_stream);
+int  pcgdo_overlap_sets_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, int nsets, size_t n, const uint32_t *e1,
+                                   const uint32_t *e2, const uint32_t *e3, uint32_t *median, uint32_t *cost);
+
 /* Reference-compatible tcm-memo symbols (lib/tcm-memo/ffi/memoized-tcm/costMatrixWrapper.h:12-31,
  * dynamicCharacterOperations.h; bound at lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:49-69): one lookup per call
- * through the GPU, alphabets <= 32.  getCostAndMedian2D frees and re-allocates retElem->element like the
- * reference (costMatrix_2d.cpp:156-166).  The 3D lookup is not on this path (3D DO is disabled upstream). */
+ * through the GPU, alphabets up to PCGDO_MAX_ALPHABET (elements are ceil(a / 64) uint64 words, as the reference packs
+ * them).  getCostAndMedian2D / 3D free and re-allocate retElem->element like the reference
+ * (costMatrix_2d.cpp:156-166, costMatrix_3d.cpp:142-145); retElem may be NULL for the 3D lookup (cost only). */
 typedef struct dcElement_t { size_t alphSize; uint64_t *element; } dcElement_t;
 typedef void *costMatrix_p;
 costMatrix_p matrixInit(size_t alphSize, unsigned int *tcm);
 void         matrixDestroy(costMatrix_p untyped_ptr);
 unsigned int getCostAndMedian2D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *retElem, costMatrix_p tcm);
+unsigned int getCostAndMedian3D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *elem3, dcElement_t *retElem,
+                                costMatrix_p tcm);
 
 /* Finer tunables: widest diagonals-per-lane variant the warp kernels must accommodate (2,4,8,16,32; pairs
  * needing more go to the general-geometry kernel) and the per-warp scratch arena in 32-bit words (0 = derive
@@ -299,6 +336,53 @@ uint32_t pcgdo_forest_edges(const pcgdo_forest *forest);
 int  pcgdo_forest_try_leaf(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_forest *forest, const uint8_t *elems,
                            const uint64_t *off, const uint32_t *len, int64_t *delta_out, void *cuda_stream);
 uint64_t pcgdo_forest_alignments(const pcgdo_forest *forest);
+/* Candidate-tree turnover: replace all n_trees topologies (same layout as `children` at creation) over the resident
+ * leaves.  The new trees are validated and levelled ON THE DEVICE into the buffers allocated at creation (sized for any
+ * topology over these taxa): nothing is allocated, the next score / score_rerooted sweeps the new candidates.  This is
+ * what a search does between sweeps (app/pcg/PCG/Command/Build/Evaluate.hs:494-527 yields new topologies over fixed leaves). */
+int  pcgdo_forest_set_trees(pcgdo_ctx *ctx, pcgdo_forest *forest, const int32_t *children);
+/* DP cells of the reference's band over the alignments of the last post-order sweep (8-bit forests): the numerator of the
+ * sweep's GCUPS / roofline figures. */
+int  pcgdo_forest_cells(pcgdo_ctx *ctx, pcgdo_forest *forest, uint64_t *cells_out);
+
+/* ---------------------------------------------------------------- several GPUs in one process
+ * north_star item (4) as a LIBRARY feature: a caller that is one process (PCG is) hands the library a device list; forests
+ * are sharded by CHARACTER BLOCKS across the devices (every device keeps all node strings of its characters resident and
+ * runs all levels locally — no traffic during the sweep), and the per-tree sums int64[n_trees] are added across devices
+ * after the last level.  When there are fewer characters than devices the trees are split instead (no reduction at all).
+ * reduce_mode: PCGDO_REDUCE_HOST  one 8 KB device-to-host copy per device, added on the host;
+ *              PCGDO_REDUCE_PEER  one kernel on the first device reads the other devices' sums over NVLink (peer access);
+ *              PCGDO_REDUCE_NCCL  ncclAllReduce(sum, int64) over a single-process communicator (libnccl.so.2 is loaded at
+ *                                 run time; PCGDO_ERR_UNSUPPORTED when it cannot be). */
+typedef struct pcgdo_multi pcgdo_multi;
+typedef struct pcgdo_mforest pcgdo_mforest;
+typedef struct pcgdo_mtcm pcgdo_mtcm;
+enum { PCGDO_REDUCE_HOST = 0, PCGDO_REDUCE_PEER = 1, PCGDO_REDUCE_NCCL = 2 };
+int  pcgdo_multi_create(pcgdo_multi **out, const int *devices, int n_devices);
+void pcgdo_multi_destroy(pcgdo_multi *m);
+int  pcgdo_multi_devices(const pcgdo_multi *m);
+pcgdo_ctx  *pcgdo_multi_ctx(pcgdo_multi *m, int i);
+const char *pcgdo_multi_last_error(const pcgdo_multi *m);
+int  pcgdo_multi_configure(pcgdo_multi *m, int pairs_per_warp, int warps_per_cta, int max_len, int max_b);
+int  pcgdo_multi_tcm_create(pcgdo_multi *m, const unsigned int *sigma, size_t a, pcgdo_mtcm **out);
+void pcgdo_multi_tcm_destroy(pcgdo_multi *m, pcgdo_mtcm *t);
+int  pcgdo_mforest_create(pcgdo_multi *m, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
+                          const int32_t *children, pcgdo_mforest **out);
+void pcgdo_mforest_destroy(pcgdo_multi *m, pcgdo_mforest *f);
+/* leaves as pcgdo_forest_set_leaves (all n_chars characters; each device takes its block) */
+int  pcgdo_mforest_set_leaves(pcgdo_multi *m, pcgdo_mforest *f, const uint8_t *elems, const uint64_t *off, const uint32_t *len);
+int  pcgdo_mforest_set_trees(pcgdo_multi *m, pcgdo_mforest *f, const int32_t *children);
+/* one sweep on all devices at once + the reduction; tree_costs: HOST int64[n_trees]; rerooted != 0 adds the re-rooting pass
+ * (pcgdo_mforest_enable_rerooting first).  wall_ms (may be NULL): host wall time of the call; sweep_ms (may be NULL): the
+ * slowest device's sweep by its own CUDA events; reduce_ms (may be NULL): host wall time of the reduction step alone. */
+int  pcgdo_mforest_enable_rerooting(pcgdo_multi *m, pcgdo_mforest *f);
+int  pcgdo_mforest_score(pcgdo_multi *m, const pcgdo_mtcm *tcm, pcgdo_mforest *f, int rerooted, int reduce_mode,
+                         int64_t *tree_costs, double *wall_ms, float *sweep_ms, double *reduce_ms);
+/* the character block [lo, hi) (or tree block when the forest is split by trees: *by_trees = 1) of device i */
+int  pcgdo_mforest_block(const pcgdo_mforest *f, int i, uint32_t *lo, uint32_t *hi, int *by_trees);
+/* Pair batches over several devices: the pairs are split evenly, each device runs the pipelined host entry point on its
+ * share from its own host thread (weak sharding, no collective).  Same pcgdo_batch contract as pcgdo_align2d_batch_host. */
+int  pcgdo_multi_align2d_batch_host(pcgdo_multi *m, const pcgdo_mtcm *tcm, const pcgdo_batch *b);
 
 /* Measured integer instruction-issue rate of this GPU in lane-instructions/s (roofline denominator of the
  * DP fill; mode 0: ALU-pipe mix, 1: VIADDMNMX + IMAD, one per pipe). */

@@ -17,6 +17,32 @@
 
 #include "do_oracle.h"
 
+/* zlib-compatible CRC-32 (reflected 0xEDB88320), so that tests can compare whole output strings of many pairs
+ * through zlib.crc32 on their side */
+static uint32_t crc_table[256];
+static void crc_init(void)
+{
+    if (crc_table[1]) return;
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        crc_table[i] = c;
+    }
+}
+static uint32_t crc_u8_of_u32(const unsigned int *v, size_t n)      /* elements as ONE byte each */
+{
+    uint32_t c = 0xffffffffu;
+    for (size_t i = 0; i < n; i++) c = crc_table[(c ^ (uint8_t)v[i]) & 0xff] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+static uint32_t crc_bytes(const void *p, size_t n)
+{
+    const uint8_t *b = p;
+    uint32_t c = 0xffffffffu;
+    for (size_t i = 0; i < n; i++) c = crc_table[(c ^ b[i]) & 0xff] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+
 typedef struct { unsigned int *character; size_t length; size_t capacity; } aio_t;
 typedef int (*align2d_fn)(aio_t *, aio_t *, aio_t *, aio_t *, void *, int, int, int);
 typedef int (*align2daff_fn)(aio_t *, aio_t *, aio_t *, aio_t *, void *, int);
@@ -35,6 +61,8 @@ typedef struct {
     const oracle_tcm_t *port;
     align2daff_fn ref_affine;      /* non-NULL: affine dialect through the reference */
     int affine_variant;            /* port, affine: 0 as coded, 1 patched; -1 = linear */
+    uint32_t *out_len;             /* optional [n]: alignment length */
+    uint32_t *crc;                 /* optional [n][3]: CRC-32 of gappedOutput, inputChar1, inputChar2 after the call */
 } job_t;
 
 static void fill_aio(aio_t *io, const uint8_t *src, size_t n, size_t cap)
@@ -60,6 +88,12 @@ static void *worker(void *arg)
             fill_aio(&u, NULL, 0, cap);
             j->cost[k] = j->ref_affine ? j->ref_affine(&a, &b, &g, &u, j->ref_cm, 1)
                                        : j->ref_align(&a, &b, &g, &u, j->ref_cm, 0, 1, 0);
+            if (j->out_len) j->out_len[k] = (uint32_t)g.length;
+            if (j->crc) {
+                j->crc[3 * k + 0] = crc_u8_of_u32(g.character + (g.capacity - g.length), g.length);
+                j->crc[3 * k + 1] = crc_u8_of_u32(a.character + (a.capacity - a.length), a.length);
+                j->crc[3 * k + 2] = crc_u8_of_u32(b.character + (b.capacity - b.length), b.length);
+            }
             free(a.character); free(b.character); free(g.character); free(u.character);
             if (j->cells && !j->ref_affine) {
                 size_t lg = (n1 > n2 ? n1 : n2) + 1, sh = (n1 > n2 ? n2 : n1) + 1;
@@ -77,6 +111,12 @@ static void *worker(void *arg)
             else
                 j->cost[k] = (int32_t)oracle_align2d(j->port, x1, n1, x2, n2, og, o1, o2, &nal, &c);
             if (j->cells) j->cells[k] = c;
+            if (j->out_len) j->out_len[k] = (uint32_t)nal;
+            if (j->crc) {
+                j->crc[3 * k + 0] = crc_u8_of_u32(og, nal);
+                j->crc[3 * k + 1] = crc_u8_of_u32(o1, nal);
+                j->crc[3 * k + 2] = crc_u8_of_u32(o2, nal);
+            }
             free(buf);
         }
     }
@@ -97,12 +137,29 @@ int cpu_bench_align2d(const char *ref_so, const uint32_t *sigma, int a,
     return cpu_bench_align2d_ex(ref_so, sigma, a, 0, -1, elems, off1, len1, off2, len2, n, threads, cost, cells, seconds);
 }
 
-/* gap_open > 0: the affine dialect (reference align2dAffine, or the port with affine_variant 0 / 1). */
+int cpu_bench_align2d_full(const char *ref_so, const uint32_t *sigma, int a, uint32_t gap_open, int affine_variant,
+                           const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
+                           const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                           int32_t *cost, uint64_t *cells, uint32_t *out_len, uint32_t *crc, double *seconds);
+
 int cpu_bench_align2d_ex(const char *ref_so, const uint32_t *sigma, int a, uint32_t gap_open, int affine_variant,
                          const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
                          const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
                          int32_t *cost, uint64_t *cells, double *seconds)
 {
+    return cpu_bench_align2d_full(ref_so, sigma, a, gap_open, affine_variant, elems, off1, len1, off2, len2, n, threads,
+                                  cost, cells, NULL, NULL, seconds);
+}
+
+/* gap_open > 0: the affine dialect (reference align2dAffine, or the port with affine_variant 0 / 1).
+ * out_len / crc (optional): per pair the alignment length and the CRC-32 of the three output strings — whole-string
+ * parity of large batches against the compiled reference without shipping the strings. */
+int cpu_bench_align2d_full(const char *ref_so, const uint32_t *sigma, int a, uint32_t gap_open, int affine_variant,
+                           const uint8_t *elems, const uint64_t *off1, const uint32_t *len1,
+                           const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                           int32_t *cost, uint64_t *cells, uint32_t *out_len, uint32_t *crc, double *seconds)
+{
+    crc_init();
     align2d_fn ref_align = NULL;
     align2daff_fn ref_affine = NULL;
     void *cm = NULL;
@@ -129,7 +186,8 @@ int cpu_bench_align2d_ex(const char *ref_so, const uint32_t *sigma, int a, uint3
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
-        jobs[t] = (job_t){ t, threads, n, elems, off1, off2, len1, len2, cost, cells, ref_align, cm, port, ref_affine, affine_variant };
+        jobs[t] = (job_t){ t, threads, n, elems, off1, off2, len1, len2, cost, cells, ref_align, cm, port, ref_affine, affine_variant,
+                           out_len, crc };
         pthread_create(&th[t], NULL, worker, &jobs[t]);
     }
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
@@ -159,6 +217,9 @@ typedef struct {
     void *ref_cm;
     const oracle_tcm_t *port;
     uint32_t gap;
+    int64_t *node_total;       /* optional [n_cols][n_taxa-1]: total cost of every internal node */
+    int32_t *node_local;       /* optional, same shape: local cost */
+    uint32_t *node_crc;        /* optional, same shape: CRC-32 of the node's ungapped median string */
 } po_job_t;
 
 static void *po_worker(void *arg)
@@ -219,6 +280,9 @@ static void *po_worker(void *arg)
                 str[node] = out;
                 len[node] = no;
                 tot[node] = cost + tot[l] + tot[r];
+                if (j->node_total) j->node_total[(size_t)col * ni + x] = tot[node];
+                if (j->node_local) j->node_local[(size_t)col * ni + x] = (int32_t)cost;
+                if (j->node_crc) j->node_crc[(size_t)col * ni + x] = crc_bytes(out, no);
                 done[node] = 1;
                 root = node;
                 remaining--;
@@ -232,11 +296,30 @@ static void *po_worker(void *arg)
     return NULL;
 }
 
+int cpu_bench_postorder_full(const char *ref_so, const uint32_t *sigma, int a, uint32_t n_trees, uint32_t n_taxa,
+                             uint32_t n_chars, const int32_t *children, const uint8_t *leaf_elems,
+                             const uint64_t *leaf_off, const uint32_t *leaf_len, uint32_t col0, uint32_t n_cols,
+                             int threads, int64_t *col_cost, uint64_t *col_cells, int64_t *node_total, int32_t *node_local,
+                             uint32_t *node_crc, double *seconds);
+
 int cpu_bench_postorder(const char *ref_so, const uint32_t *sigma, int a, uint32_t n_trees, uint32_t n_taxa,
                         uint32_t n_chars, const int32_t *children, const uint8_t *leaf_elems,
                         const uint64_t *leaf_off, const uint32_t *leaf_len, uint32_t col0, uint32_t n_cols,
                         int threads, int64_t *col_cost, uint64_t *col_cells, double *seconds)
 {
+    return cpu_bench_postorder_full(ref_so, sigma, a, n_trees, n_taxa, n_chars, children, leaf_elems, leaf_off, leaf_len,
+                                    col0, n_cols, threads, col_cost, col_cells, NULL, NULL, NULL, seconds);
+}
+
+/* node_total / node_local / node_crc (optional, [n_cols][n_taxa - 1]): every internal node's decoration, for parity
+ * of a whole forest column set against the compiled reference. */
+int cpu_bench_postorder_full(const char *ref_so, const uint32_t *sigma, int a, uint32_t n_trees, uint32_t n_taxa,
+                             uint32_t n_chars, const int32_t *children, const uint8_t *leaf_elems,
+                             const uint64_t *leaf_off, const uint32_t *leaf_len, uint32_t col0, uint32_t n_cols,
+                             int threads, int64_t *col_cost, uint64_t *col_cells, int64_t *node_total, int32_t *node_local,
+                             uint32_t *node_crc, double *seconds)
+{
+    crc_init();
     align2d_fn ref_align = NULL;
     void *cm = NULL;
     oracle_tcm_t *port = NULL;
@@ -261,7 +344,8 @@ int cpu_bench_postorder(const char *ref_so, const uint32_t *sigma, int a, uint32
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
         jobs[t] = (po_job_t){ t, threads, n_trees, n_taxa, n_chars, col0, n_cols, children, leaf_elems, leaf_off,
-                              leaf_len, col_cost, col_cells, ref_align, cm, port, 1u << (a - 1) };
+                              leaf_len, col_cost, col_cells, ref_align, cm, port, 1u << (a - 1), node_total, node_local,
+                              node_crc };
         pthread_create(&th[t], NULL, po_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
@@ -308,6 +392,9 @@ typedef struct {
     int32_t *cost;
     uint64_t *cells;
     memo_ctx_t *memo;      /* per thread, or NULL */
+    uint32_t *out_len;     /* optional [n] */
+    uint32_t *crc;         /* optional [n][3]: CRC-32 over the little-endian words of median, aligned first, aligned second */
+    int32_t *final_offset; /* optional [n] */
 } hs_job_t;
 
 static void *hs_worker(void *arg)
@@ -327,16 +414,37 @@ static void *hs_worker(void *arg)
             j->cost[k] = (int32_t)oracle_haskell_do(j->dialect, j->metric_kind, j->sigma, j->a, s1, n1, s2, n2,
                                                     buf, buf + cap, buf + 2 * cap, &nal, &c, &off);
         if (j->cells) j->cells[k] = c;
+        if (j->out_len) j->out_len[k] = (uint32_t)nal;
+        if (j->final_offset) j->final_offset[k] = off;
+        if (j->crc)
+            for (int x = 0; x < 3; x++) j->crc[3 * k + x] = crc_bytes(buf + x * cap, 4 * nal);
         free(buf);
     }
     return NULL;
 }
+
+int cpu_bench_haskell_full(const char *memo_so, int dialect, int metric_kind, const uint32_t *sigma, int a,
+                           const uint32_t *elems, const uint64_t *off1, const uint32_t *len1,
+                           const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                           int32_t *cost, uint64_t *cells, uint32_t *out_len, uint32_t *crc, int32_t *final_offset,
+                           double *seconds, uint64_t *lookups);
 
 int cpu_bench_haskell(const char *memo_so, int dialect, int metric_kind, const uint32_t *sigma, int a,
                       const uint32_t *elems, const uint64_t *off1, const uint32_t *len1,
                       const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
                       int32_t *cost, uint64_t *cells, double *seconds, uint64_t *lookups)
 {
+    return cpu_bench_haskell_full(memo_so, dialect, metric_kind, sigma, a, elems, off1, len1, off2, len2, n, threads, cost,
+                                  cells, NULL, NULL, NULL, seconds, lookups);
+}
+
+int cpu_bench_haskell_full(const char *memo_so, int dialect, int metric_kind, const uint32_t *sigma, int a,
+                           const uint32_t *elems, const uint64_t *off1, const uint32_t *len1,
+                           const uint64_t *off2, const uint32_t *len2, size_t n, int threads,
+                           int32_t *cost, uint64_t *cells, uint32_t *out_len, uint32_t *crc, int32_t *final_offset,
+                           double *seconds, uint64_t *lookups)
+{
+    crc_init();
     if (threads < 1) threads = 1;
     memo_ctx_t *memos = NULL;
     if (memo_so) {
@@ -359,7 +467,7 @@ int cpu_bench_haskell(const char *memo_so, int dialect, int metric_kind, const u
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
         jobs[t] = (hs_job_t){ t, threads, dialect, metric_kind, a, sigma, n, elems, off1, off2, len1, len2, cost, cells,
-                              memos ? &memos[t] : NULL };
+                              memos ? &memos[t] : NULL, out_len, crc, final_offset };
         pthread_create(&th[t], NULL, hs_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);

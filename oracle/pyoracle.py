@@ -453,3 +453,99 @@ def haskell_do_w(dialect: int, a: int, in1, in2, sigma=None, metric_kind=None):
                                    _ptr(m), _ptr(x), _ptr(y), C.byref(n), C.byref(cells), C.byref(off))
     k = n.value
     return int(cost), m[:k].copy(), x[:k].copy(), y[:k].copy(), int(cells.value), int(off.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# Whole-batch parity helpers: the CPU path over many pairs on host threads, returning per pair the alignment
+# length and the zlib-compatible CRC-32 of each of the three output strings (cpu_bench.c), so that tests can
+# compare thousands of complete alignments with the compiled reference without shipping the strings.
+# ------------------------------------------------------------------------------------------------
+def cpu_align2d_full(sigma, pp, threads: int, kind: str = "reference", gap_open: int = 0, affine_variant: int = 0):
+    """Returns (cost[int32], out_len[uint32], crc[uint32 (n, 3)] of gapped / slot1 / slot2 as one byte per element)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.cpu_bench_align2d_full.restype = C.c_int
+    lib.cpu_bench_align2d_full.argtypes = [C.c_char_p, _u32p, C.c_int, C.c_uint32, C.c_int] + [C.c_void_p] * 5 + \
+                                          [C.c_size_t, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_double)]
+    sigma = _as_u32(sigma)
+    cost = np.zeros(pp.n, np.int32)
+    out_len = np.zeros(pp.n, np.uint32)
+    crc = np.zeros((pp.n, 3), np.uint32)
+    sec = C.c_double(0)
+    ref_path = REF_PATCHED_SO if (gap_open and affine_variant == 1) else REF_SO
+    so = ref_path.encode() if kind == "reference" else None
+    if kind == "reference" and not os.path.exists(ref_path):
+        raise FileNotFoundError(ref_path)
+    rc = lib.cpu_bench_align2d_full(so, _ptr(sigma), int(sigma.shape[0]), gap_open, affine_variant, pp.elems.ctypes.data,
+                                    pp.off1.ctypes.data, pp.len1.ctypes.data, pp.off2.ctypes.data, pp.len2.ctypes.data,
+                                    pp.n, threads, cost.ctypes.data, None, out_len.ctypes.data, crc.ctypes.data,
+                                    C.byref(sec))
+    if rc:
+        raise RuntimeError(f"cpu_bench_align2d_full failed: {rc}")
+    return cost, out_len, crc
+
+
+def cpu_postorder_full(sigma, children, n_taxa, n_chars, leaf_elems, leaf_off, leaf_len, col0, n_cols, threads: int,
+                       kind: str = "reference"):
+    """Post-order over columns col0.. of the (tree x character) grid; returns (col_cost[int64], node_total[int64
+    (n_cols, n_taxa-1)], node_local[int32 same], node_crc[uint32 same]: CRC-32 of each node's ungapped median)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.cpu_bench_postorder_full.restype = C.c_int
+    lib.cpu_bench_postorder_full.argtypes = [C.c_char_p, _u32p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32] + \
+                                            [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32, C.c_int] + [C.c_void_p] * 5 + \
+                                            [C.POINTER(C.c_double)]
+    sigma = _as_u32(sigma)
+    ch = np.ascontiguousarray(np.asarray(children, np.int32))
+    ni = n_taxa - 1
+    cost = np.zeros(n_cols, np.int64)
+    tot = np.zeros((n_cols, ni), np.int64)
+    loc = np.zeros((n_cols, ni), np.int32)
+    crc = np.zeros((n_cols, ni), np.uint32)
+    sec = C.c_double(0)
+    so = REF_SO.encode() if kind == "reference" else None
+    if kind == "reference" and not os.path.exists(REF_SO):
+        raise FileNotFoundError(REF_SO)
+    rc = lib.cpu_bench_postorder_full(so, _ptr(sigma), int(sigma.shape[0]), ch.shape[0], n_taxa, n_chars, ch.ctypes.data,
+                                      leaf_elems.ctypes.data, leaf_off.ctypes.data, leaf_len.ctypes.data, col0, n_cols,
+                                      threads, cost.ctypes.data, None, tot.ctypes.data, loc.ctypes.data, crc.ctypes.data,
+                                      C.byref(sec))
+    if rc:
+        raise RuntimeError(f"cpu_bench_postorder_full failed: {rc}")
+    return cost, tot, loc, crc
+
+
+def cpu_haskell_full(dialect: int, a: int, elems, off1, len1, off2, len2, threads: int, sigma=None,
+                     through_reference_memo: bool = False):
+    """The restated Haskell dialect over many pairs (a <= 32); every overlap answered by the compiled reference
+    tcm-memo when `through_reference_memo`.  Returns (cost, cells, out_len, crc (n, 3) over uint32 words, final_offset)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    lib = C.CDLL(ORACLE_SO)
+    lib.cpu_bench_haskell_full.restype = C.c_int
+    lib.cpu_bench_haskell_full.argtypes = [C.c_char_p, C.c_int, C.c_int, _u32p, C.c_int] + [C.c_void_p] * 5 + \
+                                          [C.c_size_t, C.c_int] + [C.c_void_p] * 5 + \
+                                          [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    n = len(len1)
+    sg = _as_u32(sigma) if sigma is not None else np.zeros(1, np.uint32)
+    cost = np.zeros(n, np.int32)
+    cells = np.zeros(n, np.uint64)
+    out_len = np.zeros(n, np.uint32)
+    crc = np.zeros((n, 3), np.uint32)
+    fo = np.zeros(n, np.int32)
+    sec = C.c_double(0)
+    lk = C.c_uint64(0)
+    so = None
+    if through_reference_memo:
+        if not os.path.exists(REF_MEMO_SO):
+            raise FileNotFoundError(REF_MEMO_SO)
+        so = REF_MEMO_SO.encode()
+    rc = lib.cpu_bench_haskell_full(so, dialect, 0 if sigma is None else 1, _ptr(sg), a, elems.ctypes.data, off1.ctypes.data,
+                                    len1.ctypes.data, off2.ctypes.data, len2.ctypes.data, n, threads, cost.ctypes.data,
+                                    cells.ctypes.data, out_len.ctypes.data, crc.ctypes.data, fo.ctypes.data,
+                                    C.byref(sec), C.byref(lk))
+    if rc:
+        raise RuntimeError(f"cpu_bench_haskell_full failed: {rc}")
+    return cost, cells, out_len, crc, fo

@@ -32,7 +32,14 @@ EXPORTED_SYMBOLS = [
     "pcgdo_forest_enable_rerooting", "pcgdo_forest_score_rerooted", "pcgdo_forest_get_edges", "pcgdo_forest_edges", "pcgdo_forest_try_leaf", "pcgdo_forest_create32", "pcgdo_forest_set_leaves32",
     "pcgdo_memo_create", "pcgdo_memo_create_metric", "pcgdo_memo_structure", "pcgdo_memo_alphabet", "pcgdo_memo_destroy", "pcgdo_overlap2d_batch_device", "pcgdo_overlap2d_batch_host",
     "pcgdo_explicit_batch_device", "pcgdo_explicit_batch_host",
-    "matrixInit", "matrixDestroy", "getCostAndMedian2D",
+    "matrixInit", "matrixDestroy", "getCostAndMedian2D", "getCostAndMedian3D",
+    "setUp3dCostMtx", "freeCostMtx", "pcgdo_configure_env",
+    "pcgdo_overlap_sets_batch_device", "pcgdo_overlap_sets_batch_host",
+    "pcgdo_forest_set_trees", "pcgdo_forest_cells",
+    "pcgdo_multi_create", "pcgdo_multi_destroy", "pcgdo_multi_devices", "pcgdo_multi_ctx", "pcgdo_multi_last_error",
+    "pcgdo_multi_configure", "pcgdo_multi_tcm_create", "pcgdo_multi_tcm_destroy",
+    "pcgdo_mforest_create", "pcgdo_mforest_destroy", "pcgdo_mforest_set_leaves", "pcgdo_mforest_set_trees",
+    "pcgdo_mforest_enable_rerooting", "pcgdo_mforest_score", "pcgdo_mforest_block", "pcgdo_multi_align2d_batch_host",
 ]
 
 
@@ -47,6 +54,13 @@ class CostMatrices2D(C.Structure):
                 ("cost_model_type", C.c_int), ("include_ambiguities", C.c_int), ("gap_open_cost", C.c_uint),
                 ("is_metric", C.c_int), ("num_elements", C.c_size_t), ("cost", _u32p), ("median", _u32p),
                 ("worst", _u32p), ("prepend_cost", _u32p), ("tail_cost", _u32p)]
+
+
+class CostMatrices3D(C.Structure):
+    """cost_matrices_3d_t (reference: costMatrix.h:102-130)."""
+    _fields_ = [("alphSize", C.c_size_t), ("costMatrixDimension", C.c_size_t), ("gap_char", C.c_uint),
+                ("cost_model_type", C.c_int), ("include_ambiguities", C.c_int), ("gap_open_cost", C.c_uint),
+                ("num_elements", C.c_size_t), ("cost", _u32p), ("median", _u32p)]
 
 
 class Batch(C.Structure):
@@ -153,6 +167,40 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.getCostAndMedian2D.restype = C.c_uint
     L.setUp2dCostMtx.argtypes = [C.POINTER(CostMatrices2D), _u32p, C.c_size_t, C.c_uint]
     L.setUp2dCostMtx.restype = None
+    L.setUp3dCostMtx.argtypes = [C.POINTER(CostMatrices3D), _u32p, C.c_size_t, C.c_uint]
+    L.setUp3dCostMtx.restype = None
+    L.freeCostMtx.argtypes = [C.c_void_p, C.c_int]
+    L.freeCostMtx.restype = None
+    L.getCostAndMedian3D.argtypes = [C.POINTER(DcElement)] * 4 + [C.c_void_p]
+    L.getCostAndMedian3D.restype = C.c_uint
+    L.pcgdo_configure_env.argtypes = [C.c_void_p]
+    L.pcgdo_forest_set_trees.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pcgdo_forest_cells.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.pcgdo_multi_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+    L.pcgdo_multi_destroy.argtypes = [C.c_void_p]
+    L.pcgdo_multi_destroy.restype = None
+    L.pcgdo_multi_devices.argtypes = [C.c_void_p]
+    L.pcgdo_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.pcgdo_multi_ctx.restype = C.c_void_p
+    L.pcgdo_multi_last_error.argtypes = [C.c_void_p]
+    L.pcgdo_multi_last_error.restype = C.c_char_p
+    L.pcgdo_multi_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pcgdo_multi_tcm_create.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.pcgdo_multi_tcm_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_multi_tcm_destroy.restype = None
+    L.pcgdo_mforest_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.POINTER(C.c_void_p)]
+    L.pcgdo_mforest_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_mforest_destroy.restype = None
+    L.pcgdo_mforest_set_leaves.argtypes = [C.c_void_p] * 5
+    L.pcgdo_mforest_set_trees.argtypes = [C.c_void_p] * 3
+    L.pcgdo_mforest_enable_rerooting.argtypes = [C.c_void_p] * 2
+    L.pcgdo_mforest_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    L.pcgdo_mforest_block.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.pcgdo_multi_align2d_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Batch)]
+    L.pcgdo_overlap_sets_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t] + [C.c_void_p] * 6
+    L.pcgdo_overlap_sets_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t] + [C.c_void_p] * 5
     L.align2d.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int, C.c_int, C.c_int]
     L.align2d.restype = C.c_int
     L.align2dAffine.argtypes = [C.POINTER(AlignIO)] * 4 + [C.POINTER(CostMatrices2D), C.c_int]
@@ -192,6 +240,10 @@ class Context:
     def configure(self, pairs_per_warp=0, warps_per_cta=0, max_len=0, max_b=0, arena_words=0):
         self.check(self.lib.pcgdo_configure(self.h, pairs_per_warp, warps_per_cta, max_len), "pcgdo_configure")
         self.check(self.lib.pcgdo_configure_ex(self.h, max_b, arena_words), "pcgdo_configure_ex")
+
+    def reload_env(self):
+        """Re-read the PCGDO_* experiment switches from the environment (they are otherwise read once, at creation)."""
+        self.check(self.lib.pcgdo_configure_env(self.h), "pcgdo_configure_env")
 
     def pinned_empty(self, count: int, dtype=np.uint8) -> np.ndarray:
         """A numpy array over pinned, mapped host memory (pcgdo_host_alloc); freed with the array."""
@@ -300,6 +352,19 @@ class Memo:
                                                                med.ctypes.data, cost.ctypes.data),
                        "pcgdo_overlap2d_batch_host")
         return med.reshape(e1.shape), cost.reshape(e1.shape)
+
+    def overlap_sets(self, *sets):
+        """Sankoff median / cost over two or three arrays of ambiguity sets, any alphabet up to 512 symbols: each array is
+        (n, words) uint32.  Returns (median (n, words), cost (n,)) — getCostAndMedian2D / getCostAndMedian3D in bulk."""
+        assert len(sets) in (2, 3)
+        arrs = [np.ascontiguousarray(np.asarray(e, np.uint32).reshape(-1, self.words)) for e in sets]
+        n = arrs[0].shape[0]
+        assert all(a.shape == arrs[0].shape for a in arrs)
+        med, cost = np.zeros((n, self.words), np.uint32), np.zeros(n, np.uint32)
+        self.ctx.check(self.ctx.lib.pcgdo_overlap_sets_batch_host(
+            self.ctx.h, self.h, len(arrs), n, arrs[0].ctypes.data, arrs[1].ctypes.data,
+            arrs[2].ctypes.data if len(arrs) == 3 else None, med.ctypes.data, cost.ctypes.data), "pcgdo_overlap_sets_batch_host")
+        return med, cost
 
     def __del__(self):
         try:
@@ -428,6 +493,19 @@ class Forest:
         med = buf[:n.value * self.words].copy()
         return (med if self.words == 1 else med.reshape(-1, self.words)), int(lc.value), int(tc.value)
 
+    def set_trees(self, children) -> None:
+        """Replace all candidate topologies over the resident leaves (``pcgdo_forest_set_trees``): levelled on the
+        device into the buffers allocated at creation."""
+        ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
+        assert ch.shape == (self.n_trees, self.n_taxa - 1, 2)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_set_trees(self.ctx.h, self.h, ch.ctypes.data), "pcgdo_forest_set_trees")
+
+    def cells(self) -> int:
+        """DP cells of the reference's band over the alignments of the last post-order sweep."""
+        v = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.pcgdo_forest_cells(self.ctx.h, self.h, C.byref(v)), "pcgdo_forest_cells")
+        return int(v.value)
+
     @property
     def levels(self) -> int:
         return int(self.ctx.lib.pcgdo_forest_levels(self.h))
@@ -439,6 +517,92 @@ class Forest:
     def close(self):
         if getattr(self, "h", None) and self.h.value and self.ctx.h.value:
             self.ctx.lib.pcgdo_forest_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+REDUCE_HOST, REDUCE_PEER, REDUCE_NCCL = 0, 1, 2
+
+
+class Multi:
+    """Several GPUs driven from this one process (``pcgdo_multi``): forests sharded by character blocks, pair batches
+    split evenly; one host thread per device inside the library."""
+
+    def __init__(self, devices):
+        self.lib = load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.pcgdo_multi_create(C.byref(h), devs, len(devices))
+        if rc != 0 or not h.value:
+            raise BackendError(f"pcgdo_multi_create({list(devices)}) failed with code {rc} (no CPU fallback)")
+        self.h = h
+        self.n = len(devices)
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise BackendError(f"{what} failed ({rc}): {self.lib.pcgdo_multi_last_error(self.h).decode()}")
+
+    def configure(self, pairs_per_warp=0, warps_per_cta=0, max_len=0, max_b=0):
+        self.check(self.lib.pcgdo_multi_configure(self.h, pairs_per_warp, warps_per_cta, max_len, max_b), "pcgdo_multi_configure")
+
+    def tcm(self, sigma):
+        sigma = np.ascontiguousarray(np.asarray(sigma, dtype=np.uint32))
+        h = C.c_void_p()
+        self.check(self.lib.pcgdo_multi_tcm_create(self.h, sigma.ctypes.data_as(_u32p), int(sigma.shape[0]), C.byref(h)),
+                   "pcgdo_multi_tcm_create")
+        return h
+
+    def forest(self, children, n_taxa, leaves, node_cap):
+        """``leaves``: uint8 array (n_taxa, n_chars, L) of equal-length leaf strings, or a list over taxa of lists over
+        characters.  Returns an opaque handle for ``score`` / ``set_trees``."""
+        ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
+        n_trees = int(ch.shape[0])
+        flat = [np.asarray(s, np.uint8) for taxon in leaves for s in taxon]
+        n_chars = len(leaves[0])
+        ln = np.array([len(s) for s in flat], np.uint32)
+        off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
+        elems = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1, np.uint8)
+        h = C.c_void_p()
+        self.check(self.lib.pcgdo_mforest_create(self.h, n_trees, int(n_taxa), n_chars, int(node_cap), ch.ctypes.data, C.byref(h)),
+                   "pcgdo_mforest_create")
+        self.check(self.lib.pcgdo_mforest_set_leaves(self.h, h, elems.ctypes.data, off.ctypes.data, ln.ctypes.data),
+                   "pcgdo_mforest_set_leaves")
+        return h, n_trees
+
+    def set_trees(self, forest, children):
+        ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
+        self.check(self.lib.pcgdo_mforest_set_trees(self.h, forest[0], ch.ctypes.data), "pcgdo_mforest_set_trees")
+
+    def enable_rerooting(self, forest):
+        self.check(self.lib.pcgdo_mforest_enable_rerooting(self.h, forest[0]), "pcgdo_mforest_enable_rerooting")
+
+    def score(self, tcm, forest, rerooted=False, reduce_mode=REDUCE_HOST):
+        """(tree costs int64[n_trees], wall ms, slowest device's sweep ms, reduction ms)."""
+        out = np.zeros(forest[1], np.int64)
+        wall, sweep, red = C.c_double(0), C.c_float(0), C.c_double(0)
+        self.check(self.lib.pcgdo_mforest_score(self.h, tcm, forest[0], int(rerooted), int(reduce_mode), out.ctypes.data,
+                                                C.byref(wall), C.byref(sweep), C.byref(red)), "pcgdo_mforest_score")
+        return out, float(wall.value), float(sweep.value), float(red.value)
+
+    def block(self, forest, i):
+        lo, hi, bt = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
+        self.check(self.lib.pcgdo_mforest_block(forest[0], i, C.byref(lo), C.byref(hi), C.byref(bt)), "pcgdo_mforest_block")
+        return int(lo.value), int(hi.value), bool(bt.value)
+
+    def destroy_forest(self, forest):
+        self.lib.pcgdo_mforest_destroy(self.h, forest[0])
+
+    def align2d_batch_host(self, tcm, batch):
+        self.check(self.lib.pcgdo_multi_align2d_batch_host(self.h, tcm, C.byref(batch)), "pcgdo_multi_align2d_batch_host")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.pcgdo_multi_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -888,13 +888,14 @@ cudaError_t launch_affine_classify(const AffParams &p, int grid, cudaStream_t st
 
 cudaError_t launch_affine(const AffParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(do_affine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(do_affine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        once.mark(dev);
     }
     if (wide) do_affine_kernel<true><<<grid, block, smem_bytes, stream>>>(p);
     else      do_affine_kernel<false><<<grid, block, smem_bytes, stream>>>(p);

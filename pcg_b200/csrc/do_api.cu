@@ -64,6 +64,27 @@ int pcgdo_ensure(pcgdo_ctx *ctx, DevBuf &b, size_t bytes)
     return PCGDO_OK;
 }
 
+// The experiment switches of DESIGN.md are environment variables; they are read here, once per context (and again
+// when a test asks for it), so that no entry point calls getenv on its hot path.
+extern "C" int pcgdo_configure_env(pcgdo_ctx *ctx)
+{
+    if (!ctx) return PCGDO_ERR_ARG;
+    pcgdo_ctx::Knobs k;
+    if (const char *e = getenv("PCGDO_HOST_CHUNK_PAIRS")) { const long v = atol(e); if (v >= 256 && v <= (1 << 20)) k.host_chunk_pairs = (size_t)v; }
+    if (const char *e = getenv("PCGDO_H2D_AHEAD")) { const long v = atol(e); if (v >= 1) k.h2d_ahead = (size_t)v; }
+    k.zero_copy = getenv("PCGDO_ZERO_COPY") != nullptr;
+    k.trace_pipeline = getenv("PCGDO_TRACE_PIPELINE") != nullptr;
+    k.no_pack16 = getenv("PCGDO_NO_PACK16") != nullptr;
+    k.affine_rowwise = getenv("PCGDO_AFFINE_ROWWISE") != nullptr;
+    k.metric_registers = getenv("PCGDO_METRIC_REGISTERS") != nullptr;
+    k.explicit_multi_pass = getenv("PCGDO_EXPLICIT_MULTI_PASS") != nullptr;
+    k.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : getenv("PCGDO_SKIP_FACTOR") ? atoi(getenv("PCGDO_SKIP_FACTOR")) : 64;
+    k.skip_b = getenv("PCGDO_SKIP_B") ? (unsigned)atoi(getenv("PCGDO_SKIP_B")) : 0u;
+    { const char *e = getenv("PCGDO_AFFINE_VARIANT"); k.affine_variant = (e && e[0] == '1') ? 1 : 0; }
+    ctx->knobs = k;
+    return PCGDO_OK;
+}
+
 extern "C" int pcgdo_create(pcgdo_ctx **out, int device)
 {
     if (!out) return PCGDO_ERR_ARG;
@@ -96,6 +117,7 @@ extern "C" int pcgdo_create(pcgdo_ctx **out, int device)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("event", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("event", e);
+    pcgdo_configure_env(ctx);
     *out = ctx;
     return PCGDO_OK;
 }
@@ -107,7 +129,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
-                      &ctx->d_olen, &ctx->d_cost, &ctx->d_cells, &ctx->d_stage, &ctx->d_actual, &ctx->d_total};
+                      &ctx->d_olen, &ctx->d_cost, &ctx->d_cells, &ctx->d_stage, &ctx->d_actual, &ctx->d_total, &ctx->d_strag};
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -265,7 +287,7 @@ static int tcm_from_tables(pcgdo_ctx *ctx, size_t a, unsigned int gap_open, cons
         const long long spread = 0x7000 - 64 * s_minus - 64;
         t->dev.pack_ok = (0x7000 + 64 * s_plus < 0x7800 && spread >= 8192) ? 1 : 0;
         t->dev.spread16 = t->dev.pack_ok ? (uint32_t)spread : 0u;
-        if (getenv("PCGDO_NO_PACK16")) t->dev.pack_ok = 0;
+        if (ctx->knobs.no_pack16) t->dev.pack_ok = 0;
     }
     t->dev.sub4 = (const int16_t *)t->d_sub4;
     t->dev.sub4_nat = (const int16_t *)t->d_sub4_nat;
@@ -356,6 +378,8 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps_max * arena_words * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    // (growing a buffer frees the old one, which synchronises the device: callers that enqueue many batches back to
+    // back — the host pipeline, the forest — size these for their largest batch before the first one)
     if ((rc = pcgdo_ensure(ctx, ctx->overflow, (size_t)bd.n_pairs * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4))) return rc;
     CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 16, st));
@@ -370,6 +394,9 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     p.overflow_count = p.counter + 8;
     p.big_count = p.counter + 3;
     p.overflow_list = (uint32_t *)ctx->overflow.p;
+    // the failure counter may accumulate over several batches (reset_overflow = false) while the list is sized for
+    // one: entries beyond the list are counted, not written
+    p.overflow_cap = (uint32_t)std::min<size_t>(ctx->overflow.cap / 4, 0xffffffffu);
     p.big_list = (uint32_t *)ctx->big.p;
     p.k_four = 4u;
     p.k_minus1 = 0xffffffffu;
@@ -422,7 +449,7 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     LinearParams p{};
     bool wide_ok = false;
     int rc;
-    CK(cudaEventRecord(ctx->ev0, st));
+    if (!ctx->hold_ev0) CK(cudaEventRecord(ctx->ev0, st));
     if ((rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, true, &p, &wide_ok))) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
@@ -490,6 +517,74 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
 
 // --------------------------------------------------------------------------------------------- affine
 
+// Enqueue the affine kernels (classify + narrow + wide) for one batch on `st`: no synchronisation.  The failure
+// counter (counter[8]) is reset only when `reset_overflow`; the pipelined host path accumulates it over its chunks.
+static int enqueue_affine(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &bd, cudaStream_t st, bool reset_overflow,
+                          unsigned int **overflow_out)
+{
+    const size_t hdim = (size_t)1 << (tcm->a - 1);
+    const int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+    const int wave = ctx->knobs.affine_rowwise ? 0 : 1;
+    const size_t tabs = (wave ? hdim * hdim * (hdim <= 16 ? 128 : 4) : 0) + ((hdim * hdim * 2 + 15) & ~(size_t)15);
+    const size_t smem = tabs + (size_t)warps * 128 * 4;
+    if (smem > 227 * 1024) {
+        ctx->err = "alphabet too large for the affine kernel's shared-memory table";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    size_t arena_words = ctx->arena_words;
+    if (!arena_words) {
+        const size_t per = aff_words_for((uint32_t)ctx->max_len, (uint32_t)(ctx->max_len - ctx->max_len / 20));
+        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 1024);
+    }
+    arena_words = (arena_words + 3) & ~(size_t)3;
+    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
+    const int grid = ctx->sm_count;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 128))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4 * 6))) return rc;
+    unsigned int *counter = (unsigned int *)ctx->counters.p;
+    if (reset_overflow) {
+        CK(cudaMemsetAsync(counter, 0, 128, st));
+    } else {                                            // everything but the failure counter at [8..15]
+        CK(cudaMemsetAsync(counter, 0, 32, st));
+        CK(cudaMemsetAsync(counter + 16, 0, 64, st));
+    }
+    AffParams p{};
+    p.tcm = tcm->dev;
+    p.b = bd;
+    p.aff_sub = (const uint16_t *)tcm->d_aff_sub;
+    p.wave = wave;
+    p.gap_open = tcm->gap_open;
+    p.arena = (uint32_t *)ctx->arena.p;
+    p.arena_words = (uint32_t)arena_words;
+    p.pairs_per_warp = ctx->pairs_per_warp;
+    p.counter = counter;
+    p.overflow_count = counter + 8;
+    p.class_count = counter + 16;
+    p.class_take = counter + 24;
+    p.big_list = (uint32_t *)ctx->big.p;
+    CK(launch_affine_classify(p, grid, st));
+    CK(launch_affine(p, false, grid, warps * 32, smem, st));
+    ctx->last_launches += 2;
+    if (wave) {     // consumes the queue the first kernel built on the device; exits at once when it is empty
+        const int ww = warps < 8 ? warps : 8;
+        CK(launch_affine(p, true, grid, ww * 32, tabs + (size_t)ww * 128 * 4, st));
+        ctx->last_launches += 1;
+    }
+    if (overflow_out) *overflow_out = p.overflow_count;
+    return PCGDO_OK;
+}
+
+static int affine_overflow_error(pcgdo_ctx *ctx, unsigned int h_over)
+{
+    char msg[200];
+    snprintf(msg, sizeof msg, "%u affine pair(s) exceed the kernel's limits (band wider than 1024 diagonals or "
+                              "scratch larger than the arena: raise max_len / arena_words)", h_over);
+    ctx->err = msg;
+    return PCGDO_ERR_OVERFLOW;
+}
+
 extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b,
                                                  void *cuda_stream)
 {
@@ -511,72 +606,26 @@ extern "C" int pcgdo_align2d_affine_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    const size_t hdim = (size_t)1 << (tcm->a - 1);
-    const int warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
-    const int wave = getenv("PCGDO_AFFINE_ROWWISE") ? 0 : 1;
-    const size_t tabs = (wave ? hdim * hdim * (hdim <= 16 ? 128 : 4) : 0) + ((hdim * hdim * 2 + 15) & ~(size_t)15);
-    const size_t smem = tabs + (size_t)warps * 128 * 4;
-    if (smem > 227 * 1024) {
-        ctx->err = "alphabet too large for the affine kernel's shared-memory table";
-        return PCGDO_ERR_UNSUPPORTED;
-    }
-    size_t arena_words = ctx->arena_words;
-    if (!arena_words) {
-        const size_t per = aff_words_for((uint32_t)ctx->max_len, (uint32_t)(ctx->max_len - ctx->max_len / 20));
-        arena_words = (size_t)ctx->pairs_per_warp * (per ? per : 1024);
-    }
-    arena_words = (arena_words + 3) & ~(size_t)3;
-    if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
-    const int grid = ctx->sm_count;
+    BatchDev bd{};
+    bd.n_pairs = (uint32_t)b->n_pairs;
+    bd.elems = b->elems;
+    bd.off1 = b->off1; bd.off2 = b->off2;
+    bd.len1 = b->len1; bd.len2 = b->len2;
+    bd.out_off = b->out_off;
+    bd.out_gapped = b->out_gapped; bd.out_slot1 = b->out_slot1; bd.out_slot2 = b->out_slot2;
+    bd.out_len = b->out_len;
+    bd.cost = b->cost;
+    bd.cells = b->cells;
+    if (!ctx->hold_ev0) CK(cudaEventRecord(ctx->ev0, st));
+    unsigned int *d_over = nullptr;
     int rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps * arena_words * 4))) return rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->counters, 128))) return rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)b->n_pairs * 4 * 6))) return rc;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
-    AffParams p{};
-    p.tcm = tcm->dev;
-    p.b.n_pairs = (uint32_t)b->n_pairs;
-    p.b.elems = b->elems;
-    p.b.off1 = b->off1; p.b.off2 = b->off2;
-    p.b.len1 = b->len1; p.b.len2 = b->len2;
-    p.b.out_off = b->out_off;
-    p.b.out_gapped = b->out_gapped; p.b.out_slot1 = b->out_slot1; p.b.out_slot2 = b->out_slot2;
-    p.b.out_len = b->out_len;
-    p.b.cost = b->cost;
-    p.b.cells = b->cells;
-    p.aff_sub = (const uint16_t *)tcm->d_aff_sub;
-    p.wave = wave;
-    p.gap_open = tcm->gap_open;
-    p.arena = (uint32_t *)ctx->arena.p;
-    p.arena_words = (uint32_t)arena_words;
-    p.pairs_per_warp = ctx->pairs_per_warp;
-    p.counter = (unsigned int *)ctx->counters.p;
-    p.overflow_count = p.counter + 8;
-    CK(cudaEventRecord(ctx->ev0, st));
-    p.class_count = p.counter + 16;
-    p.class_take = p.counter + 24;
-    p.big_list = (uint32_t *)ctx->big.p;
-    CK(launch_affine_classify(p, grid, st));
-    CK(launch_affine(p, false, grid, warps * 32, smem, st));
-    ctx->last_launches = 2;
-    if (wave) {     // consumes the queue the first kernel built on the device; exits at once when it is empty
-        const int ww = warps < 8 ? warps : 8;
-        CK(launch_affine(p, true, grid, ww * 32, tabs + (size_t)ww * 128 * 4, st));
-        ctx->last_launches = 3;
-    }
+    if ((rc = enqueue_affine(ctx, tcm, bd, st, true, &d_over))) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->timed = true;
     unsigned int h_over = 0;
-    CK(cudaMemcpyAsync(&h_over, p.overflow_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (h_over) {
-        char msg[200];
-        snprintf(msg, sizeof msg, "%u affine pair(s) exceed the kernel's limits (band wider than 1024 diagonals or "
-                                  "scratch larger than the arena: raise max_len / arena_words)", h_over);
-        ctx->err = msg;
-        return PCGDO_ERR_OVERFLOW;
-    }
+    if (h_over) return affine_overflow_error(ctx, h_over);
     return PCGDO_OK;
 }
 
@@ -592,7 +641,7 @@ extern "C" int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int diale
     if (!ctx || !b) return PCGDO_ERR_ARG;
     // The per-pair table kernel (do_explicit.cu) with the closed-form discrete overlap; PCGDO_METRIC_REGISTERS=1
     // selects the older kernel that evaluates the overlap per cell in registers (do_metric.cu, a <= 24).
-    if (!getenv("PCGDO_METRIC_REGISTERS")) return table_batch_device(ctx, nullptr, alphabet, dialect, b, cuda_stream);
+    if (!ctx->knobs.metric_registers) return table_batch_device(ctx, nullptr, alphabet, dialect, b, cuda_stream);
     ctx->timed = false;
     ctx->last_launches = 0;
     if (b->n_pairs == 0) return PCGDO_OK;
@@ -934,8 +983,8 @@ int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, in
     p.a = a;
     p.dialect = dialect;
     p.kind = memo ? memo->kind : 0;
-    p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
-    p.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : getenv("PCGDO_SKIP_FACTOR") ? atoi(getenv("PCGDO_SKIP_FACTOR")) : 64;
+    p.pack16 = ctx->knobs.no_pack16 ? 0 : 1;
+    p.skip_ahead = ctx->knobs.skip_ahead;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
     p.delta = memo ? memo->delta : 1u;
     p.k_64k = 65536u;
@@ -1007,9 +1056,9 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     p.a = a;
     p.dialect = dialect;
     p.kind = memo ? memo->kind : 0;
-    p.pack16 = getenv("PCGDO_NO_PACK16") ? 0 : 1;
-    p.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : getenv("PCGDO_SKIP_FACTOR") ? atoi(getenv("PCGDO_SKIP_FACTOR")) : 64;
-    p.skip_b = getenv("PCGDO_SKIP_B") ? (uint32_t)atoi(getenv("PCGDO_SKIP_B")) : 0u;
+    p.pack16 = ctx->knobs.no_pack16 ? 0 : 1;
+    p.skip_ahead = ctx->knobs.skip_ahead;
+    p.skip_b = ctx->knobs.skip_b;
     p.sigma = memo ? (const uint32_t *)memo->d_sigma : nullptr;
     p.delta = memo ? memo->delta : 1u;
     p.k_64k = 65536u;
@@ -1030,7 +1079,7 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     if (dialect == 3) {                 // unboxedFullMatrixDO: its own plain kernel (8 warps per CTA, scratch from tscratch)
         CK(launch_fullmatrix(p, grid, st));
         ctx->last_launches = 1;
-    } else if (dialect == 0 || !getenv("PCGDO_EXPLICIT_MULTI_PASS")) {
+    } else if (dialect == 0 || !ctx->knobs.explicit_multi_pass) {
         CK(launch_explicit(p, grid, warps * 32, smem, st));
         ctx->last_launches = 1;
     } else {
@@ -1102,7 +1151,10 @@ extern "C" int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches)
 }
 
 // Measured INT32 throughput of this GPU (integer lane-operations per second), the roofline
-// denominator bench.py reports the fill kernel against.  mode 0: add/min/logic only, 1: + multiply-add.
+// denominator bench.py reports the fill kernel against.  mode 0: add/min/logic only, 1: one VIADDMNMX (ALU pipe) +
+// one IMAD (FMA pipe) per pair of instructions — the most any integer kernel can issue.  The launches are short
+// (2 ms), so the GPU is first held busy for ~60 ms: measured cold (round 1) the SM clock had not ramped up yet and
+// the figure came out 21 % low (28.9 T against the 36.5 T the same kernel reaches when run back to back).
 extern "C" int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, float *ms_out)
 {
     if (!ctx || !ops_per_s) return PCGDO_ERR_ARG;
@@ -1110,9 +1162,11 @@ extern "C" int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, flo
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
     const int grid = ctx->sm_count * 8;
+    for (int rep = 0; rep < 30; ++rep) launch_int_peak(mode, grid, 2048, (uint32_t *)ctx->counters.p + 8, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
     double best = 0;
     float best_ms = 0;
-    for (int rep = 0; rep < 5; ++rep) {
+    for (int rep = 0; rep < 20; ++rep) {
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         const double ops = launch_int_peak(mode, grid, 2048, (uint32_t *)ctx->counters.p + 8, ctx->stream);
         CK(cudaGetLastError());
@@ -1120,7 +1174,7 @@ extern "C" int pcgdo_int32_peak(pcgdo_ctx *ctx, int mode, double *ops_per_s, flo
         CK(cudaEventSynchronize(ctx->ev1));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        if (rep > 0 && ops / (ms * 1e-3) > best) { best = ops / (ms * 1e-3); best_ms = ms; }
+        if (ops / (ms * 1e-3) > best) { best = ops / (ms * 1e-3); best_ms = ms; }
     }
     *ops_per_s = best;
     if (ms_out) *ms_out = best_ms;
@@ -1140,15 +1194,125 @@ extern "C" int pcgdo_align2d_affine_batch_host(pcgdo_ctx *ctx, const pcgdo_tcm *
     return batch_host_impl(ctx, tcm, b, true);
 }
 
+namespace {
+// events of one host call: destroyed on every exit path
+struct EventPool {
+    std::vector<cudaEvent_t> all;
+    ~EventPool() { for (cudaEvent_t e : all) cudaEventDestroy(e); }
+    cudaError_t make(cudaEvent_t *out, unsigned flags)
+    {
+        const cudaError_t e = cudaEventCreateWithFlags(out, flags);
+        if (e == cudaSuccess) all.push_back(*out);
+        return e;
+    }
+};
+struct HoldEv0 {
+    pcgdo_ctx *c;
+    explicit HoldEv0(pcgdo_ctx *ctx) : c(ctx) { c->hold_ev0 = true; }
+    ~HoldEv0() { c->hold_ev0 = false; }
+};
+constexpr size_t kMaxStragglers = 4096;
+}  // namespace
+
+// The pairs of a pipelined batch that only the general-geometry kernel can align (band beyond 1023 diagonals, strings
+// beyond the staging window, scratch beyond the warp arena): aligned as one small batch into the full-size device
+// arrays at their reserved offsets, then copied out pair by pair.  `ks` = batch-wide pair indices, ascending.
+// Compact transfer: their strings go behind the packed bytes of their chunk (the chunk's reserved region has room for
+// them: they never claimed a packed range), out_off_actual tells the caller where.
+static int host_stragglers(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, const pcgdo_batch &d,
+                           const std::vector<uint32_t> &ks, bool compact, const std::vector<size_t> &cb,
+                           const std::vector<size_t> &o_lo, const std::vector<size_t> &o_hi,
+                           const std::vector<uint32_t> &gran, cudaStream_t st)
+{
+    const size_t m = ks.size();
+    const bool want_str = b->out_gapped || b->out_slot1 || b->out_slot2;
+    // descriptors: [off1 | off2 | out_off] u64, [len1 | len2 | cost | out_len] u32, [cells] u64
+    std::vector<uint64_t> h64(3 * m);
+    std::vector<uint32_t> h32(2 * m);
+    for (size_t i = 0; i < m; ++i) {
+        const uint32_t k = ks[i];
+        h64[i] = b->off1[k]; h64[m + i] = b->off2[k]; h64[2 * m + i] = want_str ? b->out_off[k] : 0;
+        h32[i] = b->len1[k]; h32[m + i] = b->len2[k];
+    }
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_strag, m * (3 * 8 + 4 * 4 + 8) + 64))) return rc;
+    uint64_t *d64 = (uint64_t *)ctx->d_strag.p;
+    uint64_t *d_cells = d64 + 3 * m;
+    uint32_t *d32 = (uint32_t *)(d_cells + m);
+    CK(cudaMemcpyAsync(d64, h64.data(), 3 * m * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d32, h32.data(), 2 * m * 4, cudaMemcpyHostToDevice, st));
+    pcgdo_batch sub = d;
+    sub.n_pairs = m;
+    sub.off1 = d64; sub.off2 = d64 + m; sub.out_off = want_str ? d64 + 2 * m : nullptr;
+    sub.len1 = d32; sub.len2 = d32 + m;
+    sub.cost = (int32_t *)(d32 + 2 * m);
+    sub.out_len = d32 + 3 * m;
+    sub.cells = b->cells ? d_cells : nullptr;
+    sub.out_off_actual = nullptr;
+    const int launches = ctx->last_launches;
+    {
+        HoldEv0 hold(ctx);
+        if ((rc = pcgdo_align2d_batch_device(ctx, tcm, &sub, st))) return rc;
+    }
+    ctx->last_launches += launches;
+    std::vector<uint32_t> r32(2 * m);
+    std::vector<uint64_t> rcells(b->cells ? m : 0);
+    CK(cudaMemcpyAsync(r32.data(), d32 + 2 * m, 2 * m * 4, cudaMemcpyDeviceToHost, st));
+    if (b->cells) CK(cudaMemcpyAsync(rcells.data(), d_cells, m * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t c = 0, tail = 0;
+    bool fresh = true;
+    for (size_t i = 0; i < m; ++i) {
+        const uint32_t k = ks[i];
+        b->cost[k] = (int32_t)r32[i];
+        if (b->out_len) b->out_len[k] = r32[m + i];
+        if (b->cells) b->cells[k] = rcells[i];
+        if (!want_str) continue;
+        const size_t from = b->out_off[k], bytes = ((size_t)r32[m + i] + 3) & ~(size_t)3;
+        size_t to = from;
+        if (compact) {
+            while (k >= cb[c + 1]) { ++c; fresh = true; }
+            if (fresh) {
+                tail = o_lo[c] + (((size_t)ctx->h_total[c] + gran[c]) & ~(size_t)gran[c]);
+                fresh = false;
+            }
+            to = tail;
+            tail += (bytes + gran[c]) & ~(size_t)gran[c];
+            if (tail > o_hi[c]) {
+                ctx->err = "compact transfer: a chunk's reserved output region is smaller than its alignments (overlapping out_off?)";
+                return PCGDO_ERR_ARG;
+            }
+            b->out_off_actual[k] = to;
+        }
+        if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped + to, d.out_gapped + from, bytes, cudaMemcpyDeviceToHost, st));
+        if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1 + to, d.out_slot1 + from, bytes, cudaMemcpyDeviceToHost, st));
+        if (b->out_slot2) CK(cudaMemcpyAsync(b->out_slot2 + to, d.out_slot2 + from, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return PCGDO_OK;
+}
+
 static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_batch *b, bool affine)
 {
     if (!ctx || !tcm || !b) return PCGDO_ERR_ARG;
     if (b->n_pairs == 0) return PCGDO_OK;
+    if (affine && !tcm->d_aff_sub) {
+        ctx->err = "not an affine TCM (create it with pcgdo_tcm_create_affine)";
+        return PCGDO_ERR_ARG;
+    }
+    if (b->n_pairs > 0x7fffffffu || !b->elems || !b->off1 || !b->off2 || !b->len1 || !b->len2 || !b->cost) {
+        ctx->err = "bad batch description";
+        return PCGDO_ERR_ARG;
+    }
     const auto t_entry = std::chrono::steady_clock::now();
     auto ms_since_entry = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
     CK(cudaSetDevice(ctx->device));
     const size_t n = b->n_pairs;
     const bool want_str = b->out_gapped || b->out_slot1 || b->out_slot2;
+    if (want_str && !b->out_off) {
+        ctx->err = "out_off required when aligned strings are requested";
+        return PCGDO_ERR_ARG;
+    }
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->d_elems, b->elems_bytes + 16))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->d_off1, n * 8))) return rc;
@@ -1190,13 +1354,15 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     d.out_len = b->out_len ? (uint32_t *)ctx->d_olen.p : nullptr;
     d.cost = (int32_t *)ctx->d_cost.p;
     d.cells = b->cells ? (uint64_t *)ctx->d_cells.p : nullptr;
+    d.out_off_actual = nullptr;
     // ---- pipelined path: the batch is cut into chunks whose strings and outputs are contiguous ranges of
     // the host buffers; chunk c+1 is copied in and chunk c-1 copied out while chunk c is aligned
     // (three streams, PCIe is full duplex).  Needs monotone layouts, which the packers produce; anything
-    // else, and any pair that overflows the warp kernels, takes the plain path below.
-    size_t chunk = ctx->host_chunk_pairs ? ctx->host_chunk_pairs : 65536;
-    if (const char *e = getenv("PCGDO_HOST_CHUNK_PAIRS")) { const long v = atol(e); if (v >= 256 && v <= (1 << 20)) chunk = (size_t)v; }
-    bool pipelined = !affine && n > chunk && ctx->max_b > 8;      // (wide kernel on: no per-chunk queue left behind)
+    // else takes the plain path below.  Affine pairs are three orders of magnitude heavier per byte: smaller chunks.
+    size_t chunk = ctx->knobs.host_chunk_pairs ? ctx->knobs.host_chunk_pairs
+                   : ctx->host_chunk_pairs     ? ctx->host_chunk_pairs
+                   : affine                    ? 4096 : 65536;
+    bool pipelined = n > chunk && (affine || ctx->max_b > 8);     // (wide kernel on: no per-chunk queue left behind)
     // COMPACT TRANSFER (b->out_off_actual).  The reference hands every alignment back in buffers of capacity
     // len1 + len2 + 2 (DO/Pairwise/FFI.hsc:474-481), of which an alignment of two similar strings fills about half;
     // copying capacity-sized slots back made the PCIe link, not the aligner, the end-to-end bound.  Here the warps of a
@@ -1207,9 +1373,9 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     //  * zero-copy (PCGDO_ZERO_COPY=1, pinned mapped out arrays): the emit stores go straight into the caller's arrays
     //    over PCIe, one whole 128-byte line per warp store.  No staging and no drain, but SM-issued posted writes reached
     //    only ~23 GB/s against ~52 GB/s for the copy engine and stalled the aligner (158 ms): kept as an experiment.
-    const bool compact = pipelined && want_str && b->out_off_actual && b->out_len;
+    const bool compact = pipelined && !affine && want_str && b->out_off_actual && b->out_len;
     uint8_t *zc_out[3] = {nullptr, nullptr, nullptr};
-    bool zero_copy = compact && getenv("PCGDO_ZERO_COPY") != nullptr;
+    bool zero_copy = compact && ctx->knobs.zero_copy;
     if (zero_copy) {
         uint8_t *host[3] = {b->out_gapped, b->out_slot1, b->out_slot2};
         for (int a = 0; a < 3 && zero_copy; ++a) {
@@ -1239,22 +1405,28 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     }
     const size_t nch = pipelined ? cb.size() - 1 : 0;
     std::vector<size_t> e_lo(nch), e_hi(nch), o_lo(nch), o_hi(nch);
+    std::vector<uint32_t> gran(nch, 3u);                          // packing granularity - 1 of each chunk
+    size_t max_chunk_pairs = 0;
     if (pipelined) {
         // per-chunk byte ranges of the strings and of the reserved outputs (a pass over 40 bytes of descriptors per
         // pair: spread over a few threads, it is on the critical path before the first copy)
         auto range_of = [&](size_t c) {
-            size_t lo = SIZE_MAX, hi = 0, olo = SIZE_MAX, ohi = 0;
+            size_t lo = SIZE_MAX, hi = 0, olo = SIZE_MAX, ohi = 0, worst16 = 0;
             for (size_t k = cb[c]; k < cb[c + 1]; ++k) {
                 const size_t a1 = b->off1[k], a2 = b->off2[k];
                 lo = std::min(lo, std::min(a1, a2));
                 hi = std::max(hi, std::max(a1 + b->len1[k], a2 + b->len2[k]));
                 if (want_str) {
-                    const size_t o = b->out_off[k];
+                    const size_t o = b->out_off[k], cap = (size_t)b->len1[k] + b->len2[k];
                     olo = std::min(olo, o);
-                    ohi = std::max(ohi, o + (((size_t)b->len1[k] + b->len2[k] + 3) & ~(size_t)3));
+                    ohi = std::max(ohi, o + ((cap + 3) & ~(size_t)3));
+                    worst16 += (cap + 15) & ~(size_t)15;
                 }
             }
             e_lo[c] = lo; e_hi[c] = hi; o_lo[c] = olo; o_hi[c] = ohi;
+            // 16-byte units (vector-friendly staging) only where even the longest possible alignments fit the
+            // chunk's reserved region that way; chunks of very short strings pack in 4-byte units, which always fit
+            gran[c] = (want_str && worst16 <= ohi - olo) ? 15u : 3u;
         };
         const size_t nthr = std::min<size_t>(8, nch);
         std::vector<std::thread> pool;
@@ -1266,6 +1438,7 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
         for (size_t c = 0; c < nch; ++c) {
             if (e_lo[c] < prev_e || e_hi[c] > b->elems_bytes || (want_str && (o_lo[c] < prev_o || o_hi[c] > b->out_bytes))) pipelined = false;
             prev_e = e_hi[c]; prev_o = want_str ? o_hi[c] : 0;
+            max_chunk_pairs = std::max(max_chunk_pairs, cb[c + 1] - cb[c]);
         }
     }
     if (pipelined) {
@@ -1277,13 +1450,13 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
         size_t slot_bytes = 0;
         if (compact) {
             if (!zero_copy) {
-                for (size_t c = 0; c < nch; ++c)                 // a chunk's packed size <= its capacity + 16 per pair
-                    slot_bytes = std::max(slot_bytes, o_hi[c] - o_lo[c] + 16 * (cb[c + 1] - cb[c]));
+                for (size_t c = 0; c < nch; ++c) slot_bytes = std::max(slot_bytes, o_hi[c] - o_lo[c]);
                 slot_bytes = (slot_bytes + 255) & ~(size_t)255;
                 if ((rc = pcgdo_ensure(ctx, ctx->d_stage, kRing * 3 * slot_bytes))) return rc;
                 if (ctx->h_total_cap < nch) {
                     if (ctx->h_total) cudaFreeHost(ctx->h_total);
                     ctx->h_total = nullptr;
+                    ctx->h_total_cap = 0;
                     CK(cudaHostAlloc((void **)&ctx->h_total, nch * 8, cudaHostAllocDefault));
                     ctx->h_total_cap = nch;
                 }
@@ -1291,26 +1464,31 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
             if ((rc = pcgdo_ensure(ctx, ctx->d_actual, n * 8)) || (rc = pcgdo_ensure(ctx, ctx->d_total, nch * 8 + 8))) return rc;
             CK(cudaMemsetAsync(ctx->d_total.p, 0, nch * 8 + 8, st));
         }
+        // scratch of the kernels sized once for the largest chunk: growing it mid-pipeline would free the old
+        // buffer (a device-wide synchronisation); the failure list holds batch-wide pair indices of ALL chunks
+        if ((rc = pcgdo_ensure(ctx, ctx->overflow, std::max(max_chunk_pairs, std::min(n, 4 * kMaxStragglers)) * 4))) return rc;
+        if ((rc = pcgdo_ensure(ctx, ctx->big, max_chunk_pairs * 4 * (affine ? 6 : 1)))) return rc;
+        EventPool events;
         std::vector<cudaEvent_t> ev_in(nch), ev_done(nch), ev_out(nch);
-        const bool trace = getenv("PCGDO_TRACE_PIPELINE") != nullptr;     // per-chunk completion times to stderr
+        const bool trace = ctx->knobs.trace_pipeline;             // per-chunk completion times to stderr
         const unsigned evf = trace ? cudaEventDefault : cudaEventDisableTiming;
         for (size_t c = 0; c < nch; ++c) {
-            CK(cudaEventCreateWithFlags(&ev_in[c], evf));
-            CK(cudaEventCreateWithFlags(&ev_done[c], evf));
-            CK(cudaEventCreateWithFlags(&ev_out[c], evf));
+            CK(events.make(&ev_in[c], evf));
+            CK(events.make(&ev_done[c], evf));
+            CK(events.make(&ev_out[c], evf));
         }
-        size_t h2d_ahead = nch;
-        if (const char *e = getenv("PCGDO_H2D_AHEAD")) { const long v = atol(e); if (v >= 1) h2d_ahead = (size_t)v; }
+        const size_t h2d_ahead = ctx->knobs.h2d_ahead ? ctx->knobs.h2d_ahead : nch;
         cudaEvent_t ev_desc;
-        CK(cudaEventCreateWithFlags(&ev_desc, cudaEventDisableTiming));
+        CK(events.make(&ev_desc, cudaEventDisableTiming));
         CK(cudaEventRecord(ev_desc, st));
         CK(cudaStreamWaitEvent(ctx->s_h2d, ev_desc, 0));
         ctx->last_launches = 0;
         CK(cudaEventRecord(ctx->ev0, st));
         const double t_setup = ms_since_entry();
         LinearParams p{};
-        bool wide_ok = false;
-        unsigned int *pack_overflow = (unsigned int *)((unsigned long long *)ctx->d_total.p + nch);
+        bool wide_ok = affine;
+        unsigned int *d_fail = nullptr;                           // the kernels' failure counter (accumulates over the chunks)
+        unsigned int *pack_overflow = compact ? (unsigned int *)((unsigned long long *)ctx->d_total.p + nch) : nullptr;
         auto copy_in = [&](size_t c) -> int {
             int r = copy_desc(cb[c], cb[c + 1], ctx->s_h2d);
             if (r) return r;
@@ -1332,7 +1510,8 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
             if (compact && zero_copy) {
                 // the strings are already in the caller's buffers
             } else if (compact) {
-                const size_t tot = (size_t)ctx->h_total[c];
+                // the kernel never claims beyond the chunk's reserved region (pack_limit), so neither does this copy
+                const size_t tot = std::min((size_t)ctx->h_total[c], o_hi[c] - o_lo[c]);
                 uint8_t *slot = (uint8_t *)ctx->d_stage.p + (c % kRing) * 3 * slot_bytes;
                 if (b->out_gapped) CK(cudaMemcpyAsync(b->out_gapped + o_lo[c], slot, tot, cudaMemcpyDeviceToHost, so));
                 if (b->out_slot1) CK(cudaMemcpyAsync(b->out_slot1 + o_lo[c], slot + slot_bytes, tot, cudaMemcpyDeviceToHost, so));
@@ -1355,6 +1534,7 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
             CK(cudaStreamWaitEvent(st, ev_in[c], 0));
             BatchDev bd{};
             bd.n_pairs = (uint32_t)(c1 - c0);
+            bd.pair_base = (uint32_t)c0;
             bd.elems = d.elems;
             bd.off1 = d.off1 + c0; bd.off2 = d.off2 + c0;
             bd.len1 = d.len1 + c0; bd.len2 = d.len2 + c0;
@@ -1367,14 +1547,15 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
                 bd.pack_cursor = (unsigned long long *)ctx->d_total.p + c;
                 bd.out_off_actual = (uint64_t *)ctx->d_actual.p + c0;
                 bd.pack_overflow = pack_overflow;
+                bd.pack_base = o_lo[c];
+                bd.pack_limit = o_hi[c] - o_lo[c];          // never beyond the chunk's reserved region of the caller's arrays
+                bd.pack_gran = gran[c];
                 if (zero_copy) {
-                    // 4-byte units inside the chunk's reserved region of the caller's arrays: always fits (an alignment
-                    // is never longer than len1 + len2); emit_pair aligns its stores to 128-byte lines by itself
+                    // inside the chunk's reserved region of the caller's arrays; emit_pair aligns its stores to
+                    // 128-byte lines by itself
                     bd.out_gapped = zc_out[0] ? zc_out[0] + o_lo[c] : nullptr;
                     bd.out_slot1 = zc_out[1] ? zc_out[1] + o_lo[c] : nullptr;
                     bd.out_slot2 = zc_out[2] ? zc_out[2] + o_lo[c] : nullptr;
-                    bd.pack_base = o_lo[c];
-                    bd.pack_limit = o_hi[c] - o_lo[c];
                     bd.pack_gran = 3;
                 } else {
                     if (c >= kRing) CK(cudaStreamWaitEvent(st, ev_out[c - kRing], 0));      // the staging slot is free again
@@ -1382,12 +1563,14 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
                     bd.out_gapped = b->out_gapped ? slot : nullptr;
                     bd.out_slot1 = b->out_slot1 ? slot + slot_bytes : nullptr;
                     bd.out_slot2 = b->out_slot2 ? slot + 2 * slot_bytes : nullptr;
-                    bd.pack_base = o_lo[c];
-                    bd.pack_limit = slot_bytes;
-                    bd.pack_gran = 15;
                 }
             }
-            if ((rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, c == 0, &p, &wide_ok))) return rc;
+            if (affine) rc = enqueue_affine(ctx, tcm, bd, st, c == 0, &d_fail);
+            else {
+                rc = pcgdo_enqueue_linear(ctx, tcm, bd, st, c == 0, &p, &wide_ok);
+                d_fail = p.overflow_count;
+            }
+            if (rc) return rc;
             if (compact && !zero_copy)
                 CK(cudaMemcpyAsync(ctx->h_total + c, (unsigned long long *)ctx->d_total.p + c, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(ev_done[c], st));
@@ -1399,8 +1582,8 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
         const double t_issued = ms_since_entry();
         CK(cudaEventRecord(ctx->ev1, st));
         ctx->timed = true;
-        unsigned int h_cnt[10] = {0}, h_pack = 0;
-        CK(cudaMemcpyAsync(h_cnt, p.counter, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+        unsigned int h_fail = 0, h_pack = 0;
+        CK(cudaMemcpyAsync(&h_fail, d_fail, 4, cudaMemcpyDeviceToHost, st));
         if (compact) CK(cudaMemcpyAsync(&h_pack, pack_overflow, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaStreamSynchronize(ctx->s_d2h));
@@ -1416,12 +1599,21 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
                 fprintf(stderr, "  chunk %3zu  %8zu pairs  %8.2f %8.2f %8.2f\n", c, cb[c + 1] - cb[c], a, d2, o);
             }
         }
-        for (size_t c = 0; c < nch; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_done[c]); cudaEventDestroy(ev_out[c]); }
-        cudaEventDestroy(ev_desc);
-        // the overflow counter accumulates over the chunks; with the wide kernel enabled every pair that
-        // fits a warp has been handled in its own chunk
-        if (h_cnt[8] == 0 && wide_ok && h_pack == 0) return PCGDO_OK;
-        // fall through: some pairs need the general-geometry kernel — redo the batch on the plain path
+        if (affine) return h_fail ? affine_overflow_error(ctx, h_fail) : PCGDO_OK;
+        // with the wide kernel enabled every pair that fits a warp has been handled in its own chunk
+        if (h_fail == 0 && wide_ok && h_pack == 0) return PCGDO_OK;
+        // a few pairs need the general-geometry kernel: align just those (their batch-wide indices are on the failure list)
+        if (wide_ok && h_pack == 0 && !zero_copy && h_fail <= kMaxStragglers && h_fail <= p.overflow_cap) {
+            std::vector<uint32_t> ks(h_fail);
+            CK(cudaMemcpyAsync(ks.data(), p.overflow_list, (size_t)h_fail * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::sort(ks.begin(), ks.end());
+            rc = host_stragglers(ctx, tcm, b, d, ks, compact, cb, o_lo, o_hi, gran, st);
+            if (rc == PCGDO_OK) CK(cudaEventRecord(ctx->ev1, st));
+            return rc;
+        }
+        // otherwise (many such pairs, or a packed range that did not fit its chunk): redo the batch on the plain path
+        CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));   // (all of it: chunks may leave gaps)
     } else {
         if ((rc = copy_desc(0, n, st))) return rc;
         CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_bytes, cudaMemcpyHostToDevice, st));
@@ -1442,42 +1634,123 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
 }
 
 // --------------------------------------------------------------------------------------------- shims
+// Reference-compatible entry points: one pair / one lookup per call through the GPU.  GHC calls them concurrently
+// from its capability threads (`parZipWith rpar` over `unsafePerformIO`), so every calling thread gets its
+// own small context (one stream, one warp's worth of scratch) and the calls of different threads overlap on the
+// device; the only shared state is the cache of device TCMs, locked for the lookup alone.
 
-namespace {
-std::mutex g_mu;
-pcgdo_ctx *g_ctx = nullptr;
-std::unordered_map<const void *, pcgdo_tcm *> g_tcms;   // keyed by the caller's cost-table pointer
-
-pcgdo_ctx *shim_ctx()
+extern "C" int pcgdo_overlap_sets_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int nsets, size_t n, const uint32_t *e1,
+                                               const uint32_t *e2, const uint32_t *e3, uint32_t *median, uint32_t *cost,
+                                               void *cuda_stream)
 {
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_ctx && pcgdo_create(&g_ctx, 0) != PCGDO_OK) {
-        fprintf(stderr, "pcg_do_b200: cannot create a GPU context (no CPU fallback)\n");
-        abort();
+    if (!ctx || !memo || (nsets != 2 && nsets != 3) || (n && (!e1 || !e2 || (nsets == 3 && !e3)))) return PCGDO_ERR_ARG;
+    if (memo->kind != 2) {
+        ctx->err = "pcgdo_overlap_sets_batch: needs an explicit matrix (pcgdo_memo_create_metric(..., PCGDO_METRIC_EXPLICIT))";
+        return PCGDO_ERR_UNSUPPORTED;
     }
-    return g_ctx;
+    ctx->timed = false;
+    ctx->last_launches = 0;
+    if (n == 0) return PCGDO_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(launch_overlap_sets((const uint32_t *)memo->d_sigma, (int)memo->a, nsets, n, e1, e2, nsets == 3 ? e3 : nullptr, median,
+                           cost, ctx->sm_count, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->timed = true;
+    ctx->last_launches = 1;
+    return PCGDO_OK;
 }
 
+extern "C" int pcgdo_overlap_sets_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, int nsets, size_t n, const uint32_t *e1,
+                                             const uint32_t *e2, const uint32_t *e3, uint32_t *median, uint32_t *cost)
+{
+    if (!ctx || !memo || (nsets != 2 && nsets != 3) || (n && (!e1 || !e2 || (nsets == 3 && !e3)))) return PCGDO_ERR_ARG;
+    if (n == 0) return PCGDO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t W = (memo->a + 31) / 32, words = n * W;
+    int rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->d_elems, 3 * words * 4)) || (rc = pcgdo_ensure(ctx, ctx->d_og, (words + n) * 4))) return rc;
+    cudaStream_t st = ctx->stream;
+    uint32_t *d1 = (uint32_t *)ctx->d_elems.p, *d2 = d1 + words, *d3 = d2 + words, *dm = (uint32_t *)ctx->d_og.p, *dc = dm + words;
+    CK(cudaMemcpyAsync(d1, e1, words * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d2, e2, words * 4, cudaMemcpyHostToDevice, st));
+    if (nsets == 3) CK(cudaMemcpyAsync(d3, e3, words * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = pcgdo_overlap_sets_batch_device(ctx, memo, nsets, n, d1, d2, d3, dm, dc, st))) return rc;
+    if (median) CK(cudaMemcpyAsync(median, dm, words * 4, cudaMemcpyDeviceToHost, st));
+    if (cost) CK(cudaMemcpyAsync(cost, dc, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PCGDO_OK;
+}
+
+namespace {
 [[noreturn]] void die(const char *what, const char *detail)
 {
     fprintf(stderr, "pcg_do_b200: %s: %s (no CPU fallback)\n", what, detail ? detail : "");
     abort();
 }
-}  // namespace
 
-extern "C" int align2d(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignIO_t *ungapped,
-                       cost_matrices_2d_t *cm, int getUngapped, int getGapped, int getUnion)
+// One context per calling thread, sized for single pairs.  Never destroyed: the threads are the host runtime's
+// capabilities and live as long as the process (tearing CUDA objects down from thread-exit handlers is not safe).
+pcgdo_ctx *shim_ctx(const char *who)
 {
-    (void)ungapped;
-    if (getUngapped || getUnion) die("align2d", "only the (0,1,0) / (0,0,0) flag combinations PCG uses are implemented");
-    if (cm->cost_model_type != 0) die("align2d", "affine cost matrix passed to the linear entry point");
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_ctx && pcgdo_create(&g_ctx, 0) != PCGDO_OK) die("align2d", "cannot create a GPU context");
-    pcgdo_ctx *ctx = g_ctx;
-    pcgdo_tcm *&t = g_tcms[cm->cost];
-    if (!t && tcm_from_tables(ctx, cm->alphSize, 0, cm->cost, cm->median, &t) != PCGDO_OK)
-        die("align2d", ctx->err.c_str());
+    static thread_local pcgdo_ctx *tl = nullptr;
+    if (!tl) {
+        if (pcgdo_create(&tl, 0) != PCGDO_OK) die(who, "cannot create a GPU context");
+        tl->pairs_per_warp = 4;          // (room in the warp arena for one pair with a band of 32 diagonals per lane)
+        tl->warps_per_cta = 1;
+        tl->max_b = 32;
+    }
+    return tl;
+}
 
+// Device TCMs of the caller's cost matrices, keyed by the address of their cost table and VERIFIED on every hit
+// against the symbol-change costs they were built from (the dense table is a function of those a x a entries): a
+// matrix freed and re-allocated at the same address is rebuilt, not silently reused.  freeCostMtx drops the entry.
+struct ShimTcm {
+    pcgdo_tcm *t = nullptr;
+    size_t a = 0;
+    unsigned gap_open = 0;
+    int variant = 0;
+    std::vector<unsigned> sigma;
+};
+std::mutex g_mu;
+std::unordered_map<const void *, ShimTcm> g_tcms[2];     // [0] linear, [1] affine
+
+std::vector<unsigned> sigma_of(const cost_matrices_2d_t *cm)
+{
+    const size_t a = cm->alphSize;
+    std::vector<unsigned> s(a * a);
+    for (size_t i = 0; i < a; ++i)
+        for (size_t j = 0; j < a; ++j) s[i * a + j] = cm->cost[(((size_t)1 << i) << a) + ((size_t)1 << j)];
+    return s;
+}
+
+pcgdo_tcm *shim_tcm(pcgdo_ctx *ctx, const cost_matrices_2d_t *cm, bool affine, int variant, const char *who)
+{
+    std::vector<unsigned> sig = sigma_of(cm);
+    std::lock_guard<std::mutex> lock(g_mu);
+    ShimTcm &e = g_tcms[affine ? 1 : 0][cm->cost];
+    const unsigned go = affine ? cm->gap_open_cost : 0u;
+    if (e.t && (e.a != cm->alphSize || e.gap_open != go || e.variant != variant || e.sigma != sig)) {
+        pcgdo_tcm_destroy(ctx, e.t);
+        e.t = nullptr;
+    }
+    if (!e.t) {
+        if (tcm_from_tables(ctx, cm->alphSize, go, cm->cost, cm->median, &e.t, variant) != PCGDO_OK) die(who, ctx->err.c_str());
+        e.a = cm->alphSize; e.gap_open = go; e.variant = variant; e.sigma = std::move(sig);
+    }
+    return e.t;
+}
+
+// One pair through the host entry point; the three output strings come back right-aligned like dynCharToAlignIO
+// leaves them (c_alignment_interface.c:544-585).
+int shim_align(const char *who, bool affine, alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignIO_t *ungapped,
+               cost_matrices_2d_t *cm, bool want)
+{
+    pcgdo_ctx *ctx = shim_ctx(who);
+    const int variant = affine ? ctx->knobs.affine_variant : 0;
+    pcgdo_tcm *t = shim_tcm(ctx, cm, affine, variant, who);
     const size_t n1 = in1->length, n2 = in2->length;
     const size_t cap = (n1 + n2 + 3) & ~(size_t)3;
     std::vector<uint8_t> elems(n1 + n2 + 1), og(cap + 4), o1(cap + 4), o2(cap + 4);
@@ -1493,20 +1766,15 @@ extern "C" int align2d(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignI
     b.off1 = &off1; b.off2 = &off2; b.len1 = &len1; b.len2 = &len2;
     b.out_off = &out_off; b.out_bytes = cap;
     b.cost = &cost;
-    if (getGapped) { b.out_gapped = og.data(); b.out_slot1 = o1.data(); b.out_slot2 = o2.data(); b.out_len = &out_len; }
-    const int saved_len = ctx->max_len, saved_b = ctx->max_b;
-    size_t need_len = n1 > n2 ? n1 : n2;
-    if ((int)need_len > ctx->max_len) ctx->max_len = (int)need_len;
-    ctx->max_b = 32;
-    int rc = pcgdo_align2d_batch_host(ctx, t, &b);
-    ctx->max_len = saved_len; ctx->max_b = saved_b;
-    if (rc != PCGDO_OK) die("align2d", ctx->err.c_str());
-
-    if (getGapped) {
+    if (want) { b.out_gapped = og.data(); b.out_slot1 = o1.data(); b.out_slot2 = o2.data(); b.out_len = &out_len; }
+    const size_t need_len = n1 > n2 ? n1 : n2;
+    if ((int)need_len > ctx->max_len) ctx->max_len = (int)need_len;          // this thread's context only grows
+    const int rc = affine ? pcgdo_align2d_affine_batch_host(ctx, t, &b) : pcgdo_align2d_batch_host(ctx, t, &b);
+    if (rc != PCGDO_OK) die(who, ctx->err.c_str());
+    if (want) {
         auto put = [&](alignIO_t *io, const std::vector<uint8_t> &v) {
-            // same observable effect as dynCharToAlignIO (c_alignment_interface.c:544-585)
             io->character = (elem_t *)realloc(io->character, io->capacity * sizeof(elem_t));
-            if (!io->character || out_len > io->capacity) die("align2d", "output buffer too small");
+            if (!io->character || out_len > io->capacity) die(who, "output buffer too small");
             io->length = out_len;
             elem_t *dst = io->character + (io->capacity - out_len);
             for (uint32_t k = 0; k < out_len; ++k) dst[k] = v[k];
@@ -1514,8 +1782,18 @@ extern "C" int align2d(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignI
         put(gapped, og);
         put(in1, o1);
         put(in2, o2);
+        if (affine && ungapped) ungapped->length = 0;
     }
     return cost;
+}
+}  // namespace
+
+extern "C" int align2d(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, alignIO_t *ungapped,
+                       cost_matrices_2d_t *cm, int getUngapped, int getGapped, int getUnion)
+{
+    if (getUngapped || getUnion) die("align2d", "only the (0,1,0) / (0,0,0) flag combinations PCG uses are implemented");
+    if (cm->cost_model_type != 0) die("align2d", "affine cost matrix passed to the linear entry point");
+    return shim_align("align2d", false, in1, in2, gapped, ungapped, cm, getGapped != 0);
 }
 
 // Reference-compatible affine entry point (EXT/c_alignment_interface.h:45-52; bound at DO/Pairwise/FFI.hsc:135-143).
@@ -1526,82 +1804,78 @@ extern "C" int align2dAffine(alignIO_t *in1, alignIO_t *in2, alignIO_t *gapped, 
                              cost_matrices_2d_t *cm, int getMedians)
 {
     if (cm->cost_model_type == 0 || cm->gap_open_cost == 0) die("align2dAffine", "linear cost matrix passed to the affine entry point");
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_ctx && pcgdo_create(&g_ctx, 0) != PCGDO_OK) die("align2dAffine", "cannot create a GPU context");
-    pcgdo_ctx *ctx = g_ctx;
-    const char *ev = getenv("PCGDO_AFFINE_VARIANT");
-    const int variant = (ev && ev[0] == '1') ? 1 : 0;
-    pcgdo_tcm *&t = g_tcms[(const char *)cm->cost + 1 + variant];      // distinct keys from the linear cache
-    if (!t && tcm_from_tables(ctx, cm->alphSize, cm->gap_open_cost, cm->cost, cm->median, &t, variant) != PCGDO_OK)
-        die("align2dAffine", ctx->err.c_str());
-    const size_t n1 = in1->length, n2 = in2->length;
-    const size_t cap = (n1 + n2 + 3) & ~(size_t)3;
-    std::vector<uint8_t> elems(n1 + n2 + 1), og(cap + 4), o1(cap + 4), o2(cap + 4);
-    const elem_t *s1 = in1->character + (in1->capacity - n1), *s2 = in2->character + (in2->capacity - n2);
-    for (size_t i = 0; i < n1; ++i) elems[i] = (uint8_t)s1[i];
-    for (size_t i = 0; i < n2; ++i) elems[n1 + i] = (uint8_t)s2[i];
-    uint64_t off1 = 0, off2 = n1, out_off = 0;
-    uint32_t len1 = (uint32_t)n1, len2 = (uint32_t)n2, out_len = 0;
-    int32_t cost = 0;
-    pcgdo_batch b{};
-    b.n_pairs = 1;
-    b.elems = elems.data(); b.elems_bytes = elems.size();
-    b.off1 = &off1; b.off2 = &off2; b.len1 = &len1; b.len2 = &len2;
-    b.out_off = &out_off; b.out_bytes = cap;
-    b.cost = &cost;
-    if (getMedians) { b.out_gapped = og.data(); b.out_slot1 = o1.data(); b.out_slot2 = o2.data(); b.out_len = &out_len; }
-    const int saved_len = ctx->max_len;
-    const size_t need_len = n1 > n2 ? n1 : n2;
-    if ((int)need_len > ctx->max_len) ctx->max_len = (int)need_len;
-    const int rc = pcgdo_align2d_affine_batch_host(ctx, t, &b);
-    ctx->max_len = saved_len;
-    if (rc != PCGDO_OK) die("align2dAffine", ctx->err.c_str());
-    if (getMedians) {
-        auto put = [&](alignIO_t *io, const std::vector<uint8_t> &v, uint32_t n) {
-            io->character = (elem_t *)realloc(io->character, io->capacity * sizeof(elem_t));
-            if (!io->character || n > io->capacity) die("align2dAffine", "output buffer too small");
-            io->length = n;
-            elem_t *dst = io->character + (io->capacity - n);
-            for (uint32_t k = 0; k < n; ++k) dst[k] = v[k];
-        };
-        put(gapped, og, out_len);
-        put(in1, o1, out_len);
-        put(in2, o2, out_len);
-        if (ungapped) ungapped->length = 0;
+    return shim_align("align2dAffine", true, in1, in2, gapped, ungapped, cm, getMedians != 0);
+}
+
+// EXT/c_code_alloc_setup.c:52-66: frees the tables and the struct itself; here it also drops the device copy.
+extern "C" void freeCostMtx(void *input, int is_2d)
+{
+    if (!input) return;
+    if (is_2d) {
+        cost_matrices_2d_t *m = (cost_matrices_2d_t *)input;
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            for (auto &cache : g_tcms) {
+                auto it = cache.find(m->cost);
+                if (it != cache.end()) {
+                    if (it->second.t) { cudaDeviceSynchronize(); pcgdo_tcm_destroy(nullptr, it->second.t); }
+                    cache.erase(it);
+                }
+            }
+        }
+        free(m->cost); free(m->median); free(m->worst); free(m->prepend_cost); free(m->tail_cost);
+    } else {
+        cost_matrices_3d_t *m = (cost_matrices_3d_t *)input;
+        free(m->cost); free(m->median);
     }
-    return cost;
+    free(input);
 }
 
 // Reference-compatible tcm-memo entry points (lib/tcm-memo/ffi/memoized-tcm/costMatrixWrapper.h:12-31, bound at
 // lib/tcm-memo/src/Data/TCM/Memoized/FFI.hsc:49-69).  One lookup per call through the GPU: correct, never fast —
 // the batched kernels above are the product; these keep the existing binding linkable against this library.
+// Alphabets up to PCGDO_MAX_ALPHABET (the reference's script tests use 82 / 256 / 433 symbols here); elements are
+// ceil(a / 64) uint64 words on the C side (dynamicCharacterOperations.h), W = ceil(a / 32) 32-bit words on the device.
 extern "C" costMatrix_p matrixInit(size_t alphSize, unsigned int *tcm)
 {
-    pcgdo_ctx *ctx = shim_ctx();
+    pcgdo_ctx *ctx = shim_ctx("matrixInit");
     pcgdo_memo *m = nullptr;
-    if (pcgdo_memo_create(ctx, tcm, alphSize, &m) != PCGDO_OK) {
-        fprintf(stderr, "pcg_do_b200: matrixInit: %s (no CPU fallback)\n", ctx->err.c_str());
-        abort();
-    }
+    if (pcgdo_memo_create_metric(ctx, tcm, alphSize, PCGDO_METRIC_EXPLICIT, &m) != PCGDO_OK) die("matrixInit", ctx->err.c_str());
     return (costMatrix_p)m;
 }
 
-extern "C" void matrixDestroy(costMatrix_p untyped_ptr) { pcgdo_memo_destroy(shim_ctx(), (pcgdo_memo *)untyped_ptr); }
+extern "C" void matrixDestroy(costMatrix_p untyped_ptr) { pcgdo_memo_destroy(shim_ctx("matrixDestroy"), (pcgdo_memo *)untyped_ptr); }
 
-extern "C" unsigned int getCostAndMedian2D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *retElem, costMatrix_p tcm)
+static unsigned int shim_lookup(const char *who, int nsets, dcElement_t *const *in, dcElement_t *retElem, costMatrix_p tcm)
 {
-    pcgdo_ctx *ctx = shim_ctx();
+    pcgdo_ctx *ctx = shim_ctx(who);
     const pcgdo_memo *m = (const pcgdo_memo *)tcm;
-    uint32_t e1 = (uint32_t)elem1->element[0], e2 = (uint32_t)elem2->element[0], med = 0, cost = 0;
-    std::lock_guard<std::mutex> lock(g_mu);          // one context, shared staging buffers
-    if (pcgdo_overlap2d_batch_host(ctx, m, 1, &e1, &e2, &med, &cost) != PCGDO_OK) {
-        fprintf(stderr, "pcg_do_b200: getCostAndMedian2D: %s (no CPU fallback)\n", ctx->err.c_str());
-        abort();
+    const size_t W = (m->a + 31) / 32, W64 = (m->a + 63) / 64;
+    std::vector<uint32_t> e((size_t)3 * W, 0u), med(W, 0u);
+    for (int x = 0; x < nsets; ++x)
+        for (size_t w = 0; w < W; ++w) e[x * W + w] = (uint32_t)(in[x]->element[w / 2] >> (32 * (w & 1)));
+    uint32_t cost = 0;
+    if (pcgdo_overlap_sets_batch_host(ctx, m, nsets, 1, e.data(), e.data() + W, e.data() + 2 * W, retElem ? med.data() : nullptr,
+                                      &cost) != PCGDO_OK)
+        die(who, ctx->err.c_str());
+    if (retElem) {      // callee frees and re-allocates the median buffer (costMatrix_2d.cpp:156-166, costMatrix_3d.cpp:142-145)
+        if (retElem->element != NULL) free(retElem->element);
+        retElem->element = (uint64_t *)calloc(W64, sizeof(uint64_t));
+        if (!retElem->element) die(who, "out of memory");
+        for (size_t w = 0; w < W; ++w) retElem->element[w / 2] |= (uint64_t)med[w] << (32 * (w & 1));
     }
-    // callee frees and re-allocates the median buffer (costMatrix_2d.cpp:156-166)
-    if (retElem->element != NULL) free(retElem->element);
-    retElem->element = (uint64_t *)calloc((m->a + 63) / 64, sizeof(uint64_t));
-    retElem->element[0] = med;
     return cost;
 }
 
+extern "C" unsigned int getCostAndMedian2D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *retElem, costMatrix_p tcm)
+{
+    dcElement_t *in[3] = {elem1, elem2, nullptr};
+    return shim_lookup("getCostAndMedian2D", 2, in, retElem, tcm);
+}
+
+extern "C" unsigned int getCostAndMedian3D(dcElement_t *elem1, dcElement_t *elem2, dcElement_t *elem3, dcElement_t *retElem,
+                                           costMatrix_p tcm)
+{
+    dcElement_t *in[3] = {elem1, elem2, elem3};
+    return shim_lookup("getCostAndMedian3D", 3, in, retElem, tcm);
+}

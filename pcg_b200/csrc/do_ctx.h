@@ -27,6 +27,7 @@ struct pcgdo_ctx {
     size_t host_chunk_pairs = 0;     // pairs per pipelined chunk of the host entry point (0 = 65536)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    bool hold_ev0 = false;           // an enclosing host call owns ev0 (its timing spans the nested device call)
     int last_launches = 0;
     // tunables
     int pairs_per_warp = 32;
@@ -34,11 +35,26 @@ struct pcgdo_ctx {
     int max_len = 1024;
     int max_b = 8;
     size_t arena_words = 0;          // 0 = derive from max_len
+    // experiment switches, read from the environment ONCE (pcgdo_create / pcgdo_configure_env), never per call
+    struct Knobs {
+        size_t host_chunk_pairs = 0;   // PCGDO_HOST_CHUNK_PAIRS   pairs per pipelined chunk of the host entry point
+        size_t h2d_ahead = 0;          // PCGDO_H2D_AHEAD          chunks whose strings are queued ahead (0 = all)
+        bool zero_copy = false;        // PCGDO_ZERO_COPY          emit straight into pinned host arrays
+        bool trace_pipeline = false;   // PCGDO_TRACE_PIPELINE     per-chunk completion times to stderr
+        bool no_pack16 = false;        // PCGDO_NO_PACK16          32-bit fills only
+        bool affine_rowwise = false;   // PCGDO_AFFINE_ROWWISE     first-generation affine fill
+        bool metric_registers = false; // PCGDO_METRIC_REGISTERS   do_metric.cu instead of the table kernel
+        bool explicit_multi_pass = false;  // PCGDO_EXPLICIT_MULTI_PASS
+        int  skip_ahead = 64;          // PCGDO_SKIP_FACTOR / PCGDO_NO_SKIP_AHEAD (0)
+        unsigned skip_b = 0;           // PCGDO_SKIP_B
+        int  affine_variant = 0;       // PCGDO_AFFINE_VARIANT     reading of the reference's UB shift in the align2dAffine shim
+    } knobs;
     // device scratch
     DevBuf arena, counters, overflow, big, gen_scratch, gen_off, tscratch;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
-    // compact transfer (do_compact.cu): ring of packed output slots, per-pair actual offsets, per-chunk byte counts
+    DevBuf d_strag;                  // descriptors of the few pairs a pipelined batch hands to the general-geometry kernel
+    // compact transfer: ring of packed output slots, per-pair actual offsets, per-chunk byte counts
     DevBuf d_stage, d_actual, d_total;
     unsigned long long *h_total = nullptr;   // pinned
     size_t h_total_cap = 0;

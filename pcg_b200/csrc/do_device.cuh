@@ -1,9 +1,22 @@
 // do_device.cuh — shared device-side types for the DO kernels (sm_100a).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace pcgdo {
+
+// cudaFuncSetAttribute applies to the CURRENT device only: with several GPUs driven from one process (do_multi.cu, one
+// host thread per device) every device needs its own call.  One bit per device ordinal.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask[4] = {};
+    bool pending(int *dev)
+    {
+        if (cudaGetDevice(dev) != cudaSuccess) *dev = 0;
+        return !((mask[(*dev >> 6) & 3].load() >> (*dev & 63)) & 1ull);
+    }
+    void mark(int dev) { mask[(dev >> 6) & 3].fetch_or(1ull << (dev & 63)); }
+};
 
 constexpr uint32_t kInfW   = 0x80000001u;  // "infinite" cell in stored form (bit 31 = out of band / unreachable)
 constexpr uint32_t kBias4  = 1u << 30;     // 4 * BIAS; finite cells live in [0, 2^31)
@@ -54,6 +67,8 @@ struct BatchDev {
     uint64_t            pack_base, pack_limit;
     uint32_t            pack_gran;
     unsigned int       *pack_overflow;
+    // added to the pair indices written to the failure list (a pipelined chunk reports batch-wide indices)
+    uint32_t            pair_base;
 };
 
 __device__ __forceinline__ void pack_claim(const BatchDev &b, uint32_t k, uint32_t n)
@@ -78,7 +93,8 @@ struct LinearParams {
     uint32_t  grab;         // pairs taken from the work counter at a time
     unsigned int *counter;  // work counter (pairs handed out); counter[2] = hand-out counter of the wide kernel
     unsigned int *overflow_count;
-    uint32_t     *overflow_list;   // pair indices the fast path could not hold
+    uint32_t     *overflow_list;   // pair indices the fast path could not hold (first overflow_cap of them)
+    uint32_t      overflow_cap;
     unsigned int *big_count;       // pairs whose band needs more than 8 diagonals per lane:
     uint32_t     *big_list;        //   queued by the narrow kernel, consumed by the wide one
     // run-time "constants" (1, 4, -1, table row stride) kept opaque to ptxas so that the table-address add

@@ -177,6 +177,46 @@ cudaError_t launch_overlap2d(const uint32_t *sigma, int a, size_t n, const uint3
     return cudaGetLastError();
 }
 
+// One WARP per lookup, any alphabet up to PCGDO_MAX_ALPHABET, two or three sets of W words each: the Sankoff median /
+// cost of costMatrix_2d.cpp:175-267 (computeCostMedian / findDistance) and costMatrix_3d.cpp:168-211.  Lanes take the
+// candidate median symbols s = lane, lane + 32, ...; the median word j is the ballot of "symbol 32 j + lane attains the
+// minimum".  Empty sets wrap like the reference's unsigned arithmetic.
+__global__ void overlap_sets_kernel(const uint32_t *sigma, int a, int W, int nsets, size_t n, const uint32_t *e1,
+                                    const uint32_t *e2, const uint32_t *e3, uint32_t *med, uint32_t *cost)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t k = warp; k < n; k += nwarps) {
+        const uint32_t *x = e1 + k * W, *y = e2 + k * W, *z = nsets > 2 ? e3 + k * W : nullptr;
+        auto cost_of = [&](int s) {
+            const uint32_t *row = sigma + (size_t)s * a;
+            uint32_t c = w_rowmin(row, x, W) + w_rowmin(row, y, W);
+            if (z) c += w_rowmin(row, z, W);
+            return c;
+        };
+        uint32_t best = 0xffffffffu;
+        for (int s = lane; s < a; s += 32) best = min(best, cost_of(s));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+        for (int j = 0; j < W; ++j) {
+            const int s = 32 * j + lane;
+            const unsigned bits = __ballot_sync(0xffffffffu, s < a && cost_of(s) == best);
+            if (med && lane == 0) med[k * W + j] = bits;
+        }
+        if (cost && lane == 0) cost[k] = best;
+    }
+}
+
+cudaError_t launch_overlap_sets(const uint32_t *sigma, int a, int nsets, size_t n, const uint32_t *e1, const uint32_t *e2,
+                                const uint32_t *e3, uint32_t *med, uint32_t *cost, int sm_count, cudaStream_t st)
+{
+    size_t blocks = (n + 7) / 8;
+    if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
+    if (blocks == 0) blocks = 1;
+    overlap_sets_kernel<<<(unsigned)blocks, 256, 0, st>>>(sigma, a, (a + 31) / 32, nsets, n, e1, e2, e3, med, cost);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ fill
 __device__ __forceinline__ uint32_t x_lds_s16(uint32_t saddr)
 {
@@ -1195,13 +1235,14 @@ size_t explicit_scratch_words(int max_len, int a, size_t table_cap_entries)
 
 cudaError_t launch_explicit(const ExplicitParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(do_explicit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(do_explicit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        once.mark(dev);
     }
     if (p.a > 32) do_explicit_kernel<true><<<grid, block, smem_bytes, stream>>>(p);
     else          do_explicit_kernel<false><<<grid, block, smem_bytes, stream>>>(p);

@@ -39,4 +39,7 @@ cudaError_t launch_fullmatrix(const ExplicitParams &p, int grid, cudaStream_t st
 cudaError_t launch_overlap2d(const uint32_t *sigma, int a, size_t n, const uint32_t *e1, const uint32_t *e2,
                              uint32_t *med, uint32_t *cost, int sm_count, cudaStream_t st);
 
+cudaError_t launch_overlap_sets(const uint32_t *sigma, int a, int nsets, size_t n, const uint32_t *e1, const uint32_t *e2,
+                                const uint32_t *e3, uint32_t *med, uint32_t *cost, int sm_count, cudaStream_t st);
+
 }  // namespace pcgdo

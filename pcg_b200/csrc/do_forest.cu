@@ -63,8 +63,14 @@ struct pcgdo_forest {
     DevBuf tree_cost;    // i64 [n_trees]
     DevBuf boff1, boff2, buoff, blen1, blen2, bcost, bulen;   // per-level batch descriptors
     std::vector<std::pair<size_t, size_t>> levels;            // (first item, count)
-    size_t max_level_items = 0;
+    size_t max_level_items = 0;          // items per launch (fixed at creation: room for the widest possible level)
     std::vector<int32_t> h_roots;
+    // candidate-tree turnover (pcgdo_forest_set_trees): topologies are levelled ON THE DEVICE into the existing buffers
+    DevBuf d_children;   // i32 [n_trees][n_internal][2]
+    DevBuf d_height;     // i32 [n_trees][n_internal]
+    DevBuf d_hist;       // u32 [n_taxa + 2 | n_taxa + 2 | 4]: nodes per height, scatter cursors, error flags
+    size_t items_cap = 0;                // LevelItem entries allocated
+    bool keep_requested = false;
 };
 
 namespace {
@@ -252,6 +258,91 @@ __global__ void forest_reduce_min_kernel(uint32_t n_chars, const int64_t *char_m
     tree_cost[t] = s;
 }
 
+// ---- levelling of a fresh set of topologies (pcgdo_forest_set_trees).  One CTA per tree: heights by relaxation in
+// shared memory (a node is settled once both children are: at most `depth` rounds), validation (every id in range and
+// the child of exactly one node, one root, no cycle), the root, and this tree's share of the per-height histogram.
+__global__ void forest_height_kernel(const int32_t *children, uint32_t n_taxa, int32_t *height_out, int32_t *roots,
+                                     unsigned int *hist, unsigned int *err)
+{
+    extern __shared__ int32_t fh_smem[];
+    const uint32_t ni = n_taxa - 1, nn = 2 * n_taxa - 1, t = blockIdx.x;
+    int32_t *height = fh_smem;                 // [nn]
+    int32_t *uses = fh_smem + nn;              // [nn] times a node appears as a child
+    int32_t *lh = uses + nn;                   // [n_taxa] this tree's histogram
+    __shared__ int s_changed, s_bad, s_root, s_nroot;
+    const int32_t *ch = children + (size_t)t * ni * 2;
+    for (uint32_t v = threadIdx.x; v < nn; v += blockDim.x) { height[v] = v < n_taxa ? 0 : -1; uses[v] = 0; }
+    for (uint32_t v = threadIdx.x; v < n_taxa; v += blockDim.x) lh[v] = 0;
+    if (threadIdx.x == 0) { s_bad = 0; s_root = -1; s_nroot = 0; }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < 2 * ni; e += blockDim.x) {
+        const int32_t c = ch[e];
+        if (c < 0 || (uint32_t)c >= nn) s_bad = 1;
+        else if (atomicAdd(&uses[c], 1) != 0) s_bad = 1;
+    }
+    __syncthreads();
+    if (!s_bad) {
+        for (uint32_t round = 0; round <= ni; ++round) {
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            for (uint32_t x = threadIdx.x; x < ni; x += blockDim.x) {
+                if (height[n_taxa + x] >= 0) continue;
+                const int32_t hl = height[ch[2 * x]], hr = height[ch[2 * x + 1]];
+                if (hl >= 0 && hr >= 0) { height[n_taxa + x] = 1 + max(hl, hr); s_changed = 1; }
+            }
+            __syncthreads();
+            const int changed = s_changed;
+            __syncthreads();
+            if (!changed) break;
+        }
+        for (uint32_t x = threadIdx.x; x < ni; x += blockDim.x) {
+            const int32_t h = height[n_taxa + x];
+            if (h < 0) s_bad = 1;                                     // a cycle
+            else atomicAdd(&lh[h], 1);
+            if (!uses[n_taxa + x]) { atomicAdd(&s_nroot, 1); s_root = (int)x; }
+            height_out[(size_t)t * ni + x] = h;
+        }
+    }
+    __syncthreads();
+    if (s_bad || s_nroot != 1) { if (threadIdx.x == 0) atomicAdd(err, 1u); return; }
+    if (threadIdx.x == 0) roots[t] = s_root;
+    for (uint32_t h = threadIdx.x; h < n_taxa; h += blockDim.x)
+        if (lh[h]) atomicAdd(&hist[h], (unsigned int)lh[h]);
+}
+
+// Items grouped by height: item position = start of its height's range + a ticket from that height's cursor.
+__global__ void forest_scatter_kernel(const int32_t *children, const int32_t *height, uint32_t n_trees, uint32_t n_taxa,
+                                      unsigned int *cursor, LevelItem *items)
+{
+    const uint32_t ni = n_taxa - 1;
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (uint64_t)n_trees * ni) return;
+    const int32_t h = height[k];
+    const unsigned int pos = atomicAdd(&cursor[h], 1u);
+    const uint32_t t = (uint32_t)(k / ni), x = (uint32_t)(k % ni);
+    items[pos] = {(int32_t)t, (int32_t)x, children[2 * k], children[2 * k + 1]};
+}
+
+// DP cells of the reference's band over the alignments of the last post-order sweep (roofline accounting): one thread
+// per (item, character), lengths as resident after the sweep.
+__global__ void forest_cells_kernel(ForestDev f, const LevelItem *items, uint64_t n_items, unsigned long long *total)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (k < n_items * f.n_chars) {
+        const LevelItem it = items[k / f.n_chars];
+        uint32_t l1, l2;
+        child_lengths(f, it, (uint32_t)(k % f.n_chars), l1, l2);
+        if (l1 != kMissing && l2 != kMissing && l1 && l2) {
+            const Geom g = make_geom((int)max(l1, l2) + 1, (int)min(l1, l2) + 1);
+            c = band_cells(g, 0, 1);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+
 ForestDev dev_view(const pcgdo_forest *F)
 {
     ForestDev f;
@@ -296,10 +387,72 @@ extern "C" int pcgdo_forest_create32(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t 
     return PCGDO_OK;
 }
 
+static int forest_build_reroot(pcgdo_ctx *ctx, pcgdo_forest *F);
+
+// Levels a set of topologies into F's item array: heights, validation and grouping by height run on the device
+// (forest_height_kernel / forest_scatter_kernel); the host reads back one small histogram to know the level sizes.
+static int forest_level_trees(pcgdo_ctx *ctx, pcgdo_forest *F, const int32_t *children)
+{
+    const uint32_t n_trees = F->n_trees, n_taxa = F->n_taxa, ni = F->n_internal;
+    const size_t n_ch = (size_t)n_trees * ni * 2;
+    if (children != F->h_children.data()) F->h_children.assign(children, children + n_ch);
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(F->d_children.p, F->h_children.data(), n_ch * 4, cudaMemcpyHostToDevice, st));
+    unsigned int *hist = (unsigned int *)F->d_hist.p, *cursor = hist + (n_taxa + 2), *err = cursor + (n_taxa + 2);
+    CK(cudaMemsetAsync(hist, 0, (2 * (size_t)(n_taxa + 2) + 4) * 4, st));
+    const size_t smem = ((size_t)2 * (2 * n_taxa - 1) + n_taxa) * 4;
+    if (smem > 48 * 1024) {
+        static DeviceOnce once;
+        int dev = 0;
+        if (once.pending(&dev)) {
+            CK(cudaFuncSetAttribute(forest_height_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            once.mark(dev);
+        }
+    }
+    forest_height_kernel<<<n_trees, 256, smem, st>>>((const int32_t *)F->d_children.p, n_taxa, (int32_t *)F->d_height.p,
+                                                     (int32_t *)F->roots.p, hist, err);
+    CK(cudaGetLastError());
+    std::vector<unsigned int> h_hist(n_taxa + 2);
+    unsigned int h_err = 0;
+    F->h_roots.resize(n_trees);
+    CK(cudaMemcpyAsync(h_hist.data(), hist, (size_t)(n_taxa + 2) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(F->h_roots.data(), F->roots.p, (size_t)n_trees * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_err) {
+        ctx->err = "forest: children[] is not a set of binary trees over the taxa (bad id, shared child, cycle, or several roots)";
+        return PCGDO_ERR_ARG;
+    }
+    F->levels.clear();
+    std::vector<unsigned int> h_cursor(n_taxa + 2, 0u);
+    size_t at = 0;
+    for (uint32_t h = 1; h < n_taxa; ++h) {
+        h_cursor[h] = (unsigned int)at;
+        if (!h_hist[h]) continue;
+        F->levels.push_back({at, (size_t)h_hist[h]});
+        at += h_hist[h];
+    }
+    if (at != (size_t)n_trees * ni) {
+        ctx->err = "forest: internal error levelling the trees";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaMemcpyAsync(cursor, h_cursor.data(), (size_t)(n_taxa + 2) * 4, cudaMemcpyHostToDevice, st));
+    const uint64_t n_nodes = (uint64_t)n_trees * ni;
+    forest_scatter_kernel<<<(uint32_t)((n_nodes + 255) / 256), 256, 0, st>>>(
+        (const int32_t *)F->d_children.p, (const int32_t *)F->d_height.p, n_trees, n_taxa, cursor, (LevelItem *)F->items.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return PCGDO_OK;
+}
+
 static int forest_create_impl(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, uint32_t node_cap,
                               const int32_t *children, uint32_t elem_bytes, pcgdo_forest **out)
 {
     if (!ctx || !children || !out || n_trees == 0 || n_taxa < 2 || n_chars == 0 || node_cap < 4) return PCGDO_ERR_ARG;
+    if (((size_t)2 * (2 * n_taxa - 1) + n_taxa) * 4 > 227 * 1024) {
+        ctx->err = "forest: more taxa than the levelling kernel's shared memory holds (about 11 000)";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
     CK(cudaSetDevice(ctx->device));
     pcgdo_forest *F = new pcgdo_forest();
     F->elem_bytes = elem_bytes;
@@ -308,84 +461,74 @@ static int forest_create_impl(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa,
     F->n_internal = n_taxa - 1;
     F->stride = F->n_internal;
     F->n_edges = n_taxa >= 3 ? 2 * n_taxa - 3 : 1;
-    F->h_children.assign(children, children + (size_t)n_trees * (n_taxa - 1) * 2);
-    const uint32_t ni = F->n_internal, n_nodes = 2 * n_taxa - 1;
-    // heights per tree -> items grouped by height
-    std::vector<std::vector<LevelItem>> by_h;
-    F->h_roots.resize(n_trees);
-    std::vector<int> height(n_nodes), is_child(n_nodes);
-    for (uint32_t t = 0; t < n_trees; ++t) {
-        const int32_t *ch = children + (size_t)t * ni * 2;
-        std::fill(height.begin(), height.end(), -1);
-        std::fill(is_child.begin(), is_child.end(), 0);
-        for (uint32_t v = 0; v < n_taxa; ++v) height[v] = 0;
-        for (uint32_t x = 0; x < ni; ++x)
-            for (int s = 0; s < 2; ++s) {
-                const int32_t c = ch[2 * x + s];
-                if (c < 0 || (uint32_t)c >= n_nodes || is_child[c]) {
-                    ctx->err = "forest: children[] is not a binary tree over the taxa";
-                    delete F;
-                    return PCGDO_ERR_ARG;
-                }
-                is_child[c] = 1;
-            }
-        // iterate to a fixed point (children may be listed in any order)
-        bool progress = true;
-        uint32_t done = 0;
-        while (progress && done < ni) {
-            progress = false;
-            for (uint32_t x = 0; x < ni; ++x) {
-                if (height[n_taxa + x] >= 0) continue;
-                const int hl = height[ch[2 * x]], hr = height[ch[2 * x + 1]];
-                if (hl < 0 || hr < 0) continue;
-                height[n_taxa + x] = 1 + std::max(hl, hr);
-                progress = true;
-                ++done;
-            }
-        }
-        int root = -1;
-        for (uint32_t x = 0; x < ni; ++x)
-            if (!is_child[n_taxa + x]) root = root < 0 ? (int)x : -2;
-        if (done < ni || root < 0) {
-            ctx->err = "forest: children[] has a cycle or more than one root";
-            delete F;
-            return PCGDO_ERR_ARG;
-        }
-        F->h_roots[t] = root;
-        for (uint32_t x = 0; x < ni; ++x) {
-            const size_t h = (size_t)height[n_taxa + x];
-            if (by_h.size() <= h) by_h.resize(h + 1);
-            by_h[h].push_back({(int32_t)t, (int32_t)x, ch[2 * x], ch[2 * x + 1]});
-        }
-    }
-    std::vector<LevelItem> all;
-    for (size_t h = 1; h < by_h.size(); ++h) {
-        if (by_h[h].empty()) continue;
-        F->levels.push_back({all.size(), by_h[h].size()});
-        F->max_level_items = std::max(F->max_level_items, by_h[h].size());
-        all.insert(all.end(), by_h[h].begin(), by_h[h].end());
-    }
+    const uint32_t ni = F->n_internal;
+    // Everything is sized for ANY set of n_trees topologies over these taxa, so that pcgdo_forest_set_trees never
+    // allocates: a launch holds at most n_trees * ceil(n_taxa / 2) items (no level of a binary tree is wider; wider
+    // batches — the edge jobs of the re-rooting pass — are cut into launches of that size).
+    F->max_level_items = (size_t)n_trees * ((n_taxa + 1) / 2);
     F->leaf_bytes = (size_t)n_taxa * n_chars * F->cap;
     const size_t n_slots = (size_t)n_trees * n_chars * ni;
+    F->items_cap = (size_t)n_trees * ni;
     int rc;
-    auto fail = [&](int r) { delete F; return r; };
+    auto fail = [&](int r) { pcgdo_forest_destroy(ctx, F); return r; };
     if ((rc = pcgdo_ensure(ctx, F->store, (F->leaf_bytes + n_slots * F->cap + 64) * F->elem_bytes))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->leaf_len, (size_t)n_taxa * n_chars * 4))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->node_len, n_slots * 4))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->node_local, n_slots * 4))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->node_total, n_slots * 8))) return fail(rc);
-    if ((rc = pcgdo_ensure(ctx, F->items, all.size() * sizeof(LevelItem)))) return fail(rc);
+    if ((rc = pcgdo_ensure(ctx, F->items, F->items_cap * sizeof(LevelItem)))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->roots, (size_t)n_trees * 4))) return fail(rc);
     if ((rc = pcgdo_ensure(ctx, F->tree_cost, (size_t)n_trees * 8))) return fail(rc);
+    if ((rc = pcgdo_ensure(ctx, F->d_children, (size_t)n_trees * ni * 2 * 4))) return fail(rc);
+    if ((rc = pcgdo_ensure(ctx, F->d_height, (size_t)n_trees * ni * 4))) return fail(rc);
+    if ((rc = pcgdo_ensure(ctx, F->d_hist, (2 * (size_t)(n_taxa + 2) + 4) * 4 + 16))) return fail(rc);
     const size_t mb = F->max_level_items * n_chars;
     if ((rc = pcgdo_ensure(ctx, F->boff1, mb * 8)) || (rc = pcgdo_ensure(ctx, F->boff2, mb * 8)) ||
         (rc = pcgdo_ensure(ctx, F->buoff, mb * 8)) || (rc = pcgdo_ensure(ctx, F->blen1, mb * 4)) ||
         (rc = pcgdo_ensure(ctx, F->blen2, mb * 4)) || (rc = pcgdo_ensure(ctx, F->bcost, mb * 4)) ||
         (rc = pcgdo_ensure(ctx, F->bulen, mb * 4)))
         return fail(rc);
-    CK(cudaMemcpy(F->items.p, all.data(), all.size() * sizeof(LevelItem), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(F->roots.p, F->h_roots.data(), (size_t)n_trees * 4, cudaMemcpyHostToDevice));
+    if ((rc = forest_level_trees(ctx, F, children))) return fail(rc);
     *out = F;
+    return PCGDO_OK;
+}
+
+// Candidate-tree turnover: a fresh set of n_trees topologies over the same taxa (same layout as at creation) replaces
+// the current one.  Nothing is allocated and the leaves stay resident; the next sweep scores the new trees.  This is
+// what a tree search does between sweeps (the Wagner build and the branch swappers of
+// app/pcg/PCG/Command/Build/Evaluate.hs:494-527 produce new candidate topologies over fixed leaves).
+extern "C" int pcgdo_forest_set_trees(pcgdo_ctx *ctx, pcgdo_forest *F, const int32_t *children)
+{
+    if (!ctx || !F || !children) return PCGDO_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = forest_level_trees(ctx, F, children))) return rc;
+    if (F->reroot) return forest_build_reroot(ctx, F);
+    return PCGDO_OK;
+}
+
+// DP cells the reference's band fills over the n_trees * n_chars * (n_taxa - 1) alignments of the last post-order
+// sweep (lengths as resident after it): the numerator of the sweep's GCUPS / roofline figures.
+extern "C" int pcgdo_forest_cells(pcgdo_ctx *ctx, pcgdo_forest *F, uint64_t *cells_out)
+{
+    if (!ctx || !F || !cells_out) return PCGDO_ERR_ARG;
+    if (F->elem_bytes != 1) {
+        ctx->err = "pcgdo_forest_cells: defined for dense-TCM (8-bit) forests, whose band is a function of the lengths";
+        return PCGDO_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    unsigned long long *d_tot = (unsigned long long *)((unsigned int *)F->d_hist.p + 2 * (size_t)(F->n_taxa + 2) + 4);
+    d_tot = (unsigned long long *)(((uintptr_t)d_tot + 7) & ~(uintptr_t)7);
+    CK(cudaMemsetAsync(d_tot, 0, 8, st));
+    const ForestDev f = dev_view(F);
+    const uint64_t n_items = (uint64_t)F->n_trees * F->n_internal, n = n_items * F->n_chars;
+    forest_cells_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>(f, (const LevelItem *)F->items.p, n_items, d_tot);
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *cells_out = h;
     return PCGDO_OK;
 }
 
@@ -395,7 +538,8 @@ extern "C" void pcgdo_forest_destroy(pcgdo_ctx *ctx, pcgdo_forest *F)
     if (ctx) cudaSetDevice(ctx->device);
     DevBuf *bufs[] = {&F->store, &F->leaf_len, &F->node_len, &F->node_local, &F->node_total, &F->items, &F->roots,
                       &F->tree_cost, &F->boff1, &F->boff2, &F->buoff, &F->blen1, &F->blen2, &F->bcost, &F->bulen,
-                      &F->edge_total, &F->edge_local, &F->char_min, &F->trial_len, &F->trial_delta};
+                      &F->edge_total, &F->edge_local, &F->char_min, &F->trial_len, &F->trial_delta, &F->d_children,
+                      &F->d_height, &F->d_hist};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     delete F;
@@ -563,18 +707,11 @@ extern "C" int pcgdo_forest_score(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, pcgdo_fo
     return forest_check(ctx, F, p, st);
 }
 
-// Builds the pre-order (directed data) and edge job lists and grows the node storage to 3 result slots per
-// internal node.  Call once, before or after pcgdo_forest_set_leaves.
-extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, int keep_edge_data)
+// Builds the pre-order (directed data) and edge job lists of the CURRENT topologies behind the post-order items.
+// Their sizes do not depend on the topologies (2 directed data per internal non-root node, one job per non-root
+// edge, one trial job per edge), so the item array allocated by pcgdo_forest_enable_rerooting always fits.
+static int forest_build_reroot(pcgdo_ctx *ctx, pcgdo_forest *F)
 {
-    if (!ctx || !F) return PCGDO_ERR_ARG;
-    if (F->reroot) return (keep_edge_data && !F->keep_edges) ? PCGDO_ERR_ARG : PCGDO_OK;
-    F->keep_edges = keep_edge_data != 0;
-    if (F->n_taxa < 3) {
-        ctx->err = "re-rooting needs at least 3 taxa";
-        return PCGDO_ERR_ARG;
-    }
-    CK(cudaSetDevice(ctx->device));
     const uint32_t n_taxa = F->n_taxa, ni = F->n_internal, n_nodes = 2 * n_taxa - 1;
     std::vector<std::vector<LevelItem>> by_depth;
     std::vector<LevelItem> edges;
@@ -640,31 +777,60 @@ extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, in
             return PCGDO_ERR_ARG;
         }
     }
-    // append the new job lists to the item array
-    const size_t n_post = F->levels.empty() ? 0 : F->levels.back().first + F->levels.back().second;
-    std::vector<LevelItem> all(n_post);
-    CK(cudaMemcpy(all.data(), F->items.p, n_post * sizeof(LevelItem), cudaMemcpyDeviceToHost));
+    const size_t n_post = (size_t)F->n_trees * ni;
+    std::vector<LevelItem> extra;
+    F->up_levels.clear();
     for (auto &lv : by_depth) {
         if (lv.empty()) continue;
-        F->up_levels.push_back({all.size(), lv.size()});
-        F->max_level_items = std::max(F->max_level_items, lv.size());
-        all.insert(all.end(), lv.begin(), lv.end());
+        F->up_levels.push_back({n_post + extra.size(), lv.size()});
+        extra.insert(extra.end(), lv.begin(), lv.end());
     }
-    F->edge_items = {all.size(), edges.size()};
-    all.insert(all.end(), edges.begin(), edges.end());
+    F->edge_items = {n_post + extra.size(), edges.size()};
+    extra.insert(extra.end(), edges.begin(), edges.end());
     const uint32_t stride = 3 * ni + (F->keep_edges ? F->n_edges : 0u);
     if (F->keep_edges) {
         // trial jobs: (edge datum, trial leaf) for every tree and edge; edge 0's datum is the post-order root
-        F->trial_items = {all.size(), (size_t)F->n_trees * F->n_edges};
+        F->trial_items = {n_post + extra.size(), (size_t)F->n_trees * F->n_edges};
         for (uint32_t t = 0; t < F->n_trees; ++t)
             for (uint32_t e = 0; e < F->n_edges; ++e)
-                all.push_back({(int32_t)t, (int32_t)e,
-                               e == 0 ? (int32_t)(n_taxa + (uint32_t)F->h_roots[t]) : (int32_t)(n_taxa + 3 * ni + e),
-                               (int32_t)(n_taxa + stride)});
+                extra.push_back({(int32_t)t, (int32_t)e,
+                                 e == 0 ? (int32_t)(n_taxa + (uint32_t)F->h_roots[t]) : (int32_t)(n_taxa + 3 * ni + e),
+                                 (int32_t)(n_taxa + stride)});
     }
+    if (n_post + extra.size() > F->items_cap) {
+        ctx->err = "re-rooting: internal error sizing the job lists";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaMemcpy((LevelItem *)F->items.p + n_post, extra.data(), extra.size() * sizeof(LevelItem), cudaMemcpyHostToDevice));
+    return PCGDO_OK;
+}
+
+// Grows the node storage to 3 result slots per internal node (+ one per edge with keep_edge_data) and builds the
+// job lists.  Call once, before or after pcgdo_forest_set_leaves.
+extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, int keep_edge_data)
+{
+    if (!ctx || !F) return PCGDO_ERR_ARG;
+    if (F->reroot) return (keep_edge_data && !F->keep_edges) ? PCGDO_ERR_ARG : PCGDO_OK;
+    if (F->n_taxa < 3) {
+        ctx->err = "re-rooting needs at least 3 taxa";
+        return PCGDO_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    F->keep_edges = keep_edge_data != 0;
+    const uint32_t ni = F->n_internal;
     int rc;
-    if ((rc = pcgdo_ensure(ctx, F->items, all.size() * sizeof(LevelItem)))) return rc;
-    CK(cudaMemcpy(F->items.p, all.data(), all.size() * sizeof(LevelItem), cudaMemcpyHostToDevice));
+    // item array: post-order items + 2 (ni - 1) directed data + (n_edges - 1) edge jobs (+ n_edges trial jobs) per tree
+    const size_t n_post = (size_t)F->n_trees * ni;
+    const size_t cap = n_post + (size_t)F->n_trees * (2 * (size_t)(ni - 1) + (F->n_edges - 1) + (F->keep_edges ? F->n_edges : 0));
+    {
+        DevBuf items;
+        if ((rc = pcgdo_ensure(ctx, items, cap * sizeof(LevelItem)))) return rc;
+        CK(cudaMemcpy(items.p, F->items.p, n_post * sizeof(LevelItem), cudaMemcpyDeviceToDevice));
+        CK(cudaFree(F->items.p));
+        F->items = items;
+        F->items_cap = cap;
+    }
+    const uint32_t stride = 3 * ni + (F->keep_edges ? F->n_edges : 0u);
     // 3 result slots per internal node (+ one per edge, + the trial leaf); the leaf region (front of the store) is preserved
     const size_t n_slots = (size_t)F->n_trees * F->n_chars * stride;
     DevBuf store;
@@ -682,15 +848,9 @@ extern "C" int pcgdo_forest_enable_rerooting(pcgdo_ctx *ctx, pcgdo_forest *F, in
     if ((rc = pcgdo_ensure(ctx, F->edge_total, n_cols * F->n_edges * 8)) ||
         (rc = pcgdo_ensure(ctx, F->edge_local, n_cols * F->n_edges * 4)) || (rc = pcgdo_ensure(ctx, F->char_min, n_cols * 8)))
         return rc;
-    const size_t mb = F->max_level_items * F->n_chars;
-    if ((rc = pcgdo_ensure(ctx, F->boff1, mb * 8)) || (rc = pcgdo_ensure(ctx, F->boff2, mb * 8)) ||
-        (rc = pcgdo_ensure(ctx, F->buoff, mb * 8)) || (rc = pcgdo_ensure(ctx, F->blen1, mb * 4)) ||
-        (rc = pcgdo_ensure(ctx, F->blen2, mb * 4)) || (rc = pcgdo_ensure(ctx, F->bcost, mb * 4)) ||
-        (rc = pcgdo_ensure(ctx, F->bulen, mb * 4)))
-        return rc;
     F->stride = stride;
     F->reroot = true;
-    return PCGDO_OK;
+    return forest_build_reroot(ctx, F);
 }
 
 // Post-order, directed data (pre-order by depth), edge costs; per-tree cost = sum over characters of the minimum

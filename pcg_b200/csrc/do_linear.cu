@@ -596,7 +596,10 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                 ok = seq_bytes(sl) <= p.seq_cap && need <= p.arena_words;
             }
             if (!ok) {
-                if (lane == 0) p.overflow_list[atomicAdd(p.overflow_count, 1u)] = k;
+                if (lane == 0) {
+                    const uint32_t ix = atomicAdd(p.overflow_count, 1u);
+                    if (ix < p.overflow_cap) p.overflow_list[ix] = k + b.pair_base;
+                }
                 ++gpos;
                 continue;
             }
@@ -828,13 +831,14 @@ cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_
 // Host-side launchers (called from do_api.cu).
 cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(do_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(do_linear_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        once.mark(dev);
     }
     if (wide) do_linear_kernel<32><<<grid, block, smem_bytes, stream>>>(p);
     else      do_linear_kernel<8><<<grid, block, smem_bytes, stream>>>(p);

@@ -354,11 +354,12 @@ uint32_t metric_words_for(uint32_t n1, uint32_t n2)
 
 cudaError_t launch_metric(const MetricParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(do_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        once.mark(dev);
     }
     do_metric_kernel<<<grid, block, smem_bytes, stream>>>(p);
     return cudaGetLastError();

@@ -69,3 +69,53 @@ extern "C" void setUp2dCostMtx(cost_matrices_2d_t *m, unsigned int *tcm, size_t 
         m->tail_cost[i] = m->cost[(i << alphSize) + gap];
     }
 }
+
+// c_code_alloc_setup.c:208-270 with cm_alloc_3d (costMatrix.c:408-449): (dim + 1)^3 zero-initialised entries, entry
+// (((e1 << a) + e2) << a) + e3 = min over symbols s of d(s,e1) + d(s,e2) + d(s,e3) and the set of symbols attaining it;
+// d is the same transposed-index `distance` as in the 2D tables.  The per-element distances are tabulated first
+// (the reference recomputes them inside the triple loop).
+extern "C" void setUp3dCostMtx(cost_matrices_3d_t *m, unsigned int *tcm, size_t alphSize, unsigned int gap_open)
+{
+    const size_t a = alphSize, dim = (size_t)1 << a;
+    m->alphSize = a;
+    m->costMatrixDimension = dim;
+    m->gap_char = 1u << (a - 1);
+    m->cost_model_type = gap_open == 0 ? 0 : 3;
+    m->include_ambiguities = 1;
+    m->gap_open_cost = gap_open;
+    m->num_elements = dim - 1;
+    const size_t size = (dim + 1) * (dim + 1) * (dim + 1);
+    m->cost = (unsigned int *)calloc(size * sizeof(int), 1);
+    m->median = (elem_t *)calloc(size * sizeof(elem_t), 1);
+    if (!m->cost || !m->median) abort();
+    std::vector<int> d(dim * a, INT_MAX);
+    for (size_t e = 1; e < dim; ++e)
+        for (size_t s = 0; s < a; ++s) {
+            int best = INT_MAX;
+            for (size_t pos = 0; pos < a; ++pos)
+                if (e & ((size_t)1 << pos)) {
+                    const int c = (int)tcm[pos * a + s];
+                    if (c < best) best = c;
+                }
+            d[e * a + s] = best;
+        }
+    std::vector<int> d12(a);
+    for (size_t e1 = 1; e1 < dim; ++e1)
+        for (size_t e2 = 1; e2 < dim; ++e2) {
+            for (size_t s = 0; s < a; ++s) d12[s] = d[e1 * a + s] + d[e2 * a + s];
+            unsigned int *crow = m->cost + (((e1 << a) + e2) << a);
+            elem_t *mrow = m->median + (((e1 << a) + e2) << a);
+            for (size_t e3 = 1; e3 < dim; ++e3) {
+                int best = INT_MAX;
+                unsigned int med = 0;
+                const int *d3 = &d[e3 * a];
+                for (size_t s = 0; s < a; ++s) {
+                    const int c = d12[s] + d3[s];
+                    if (c < best)       { best = c; med = 1u << s; }
+                    else if (c == best) { med |= 1u << s; }
+                }
+                crow[e3] = (unsigned int)best;
+                mrow[e3] = med;
+            }
+        }
+}

@@ -37,6 +37,7 @@ while time.time() < t_end:
         # every other round through the pipelined host path with packed outputs (tiny chunks: 6 chunks, ring of 3 slots)
         compact = bool(seed & 1)
         os.environ["PCGDO_HOST_CHUNK_PAIRS"] = "256" if compact else "1048576"
+        ctx.reload_env()
         r = P.align2d_batch(ctx, tcm, pp, want_cells=True, compact=compact, pinned=bool(seed & 2))
         if compact:                          # rounds whose outputs really came back packed (not the plain fallback)
             n_checked["packed_rounds"] = n_checked.get("packed_rounds", 0) + int((r.out_off != pp.out_off).any())

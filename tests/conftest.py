@@ -21,8 +21,17 @@ def oracle_mod():
 
 
 @pytest.fixture(scope="session")
-def gpu_ctx():
+def _gpu_ctx_session():
     import pcg_b200
     ctx = pcg_b200.Context(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture
+def gpu_ctx(_gpu_ctx_session):
+    """The session's context with the PCGDO_* switches re-read: the library reads the environment once per context,
+    tests flip the variables (monkeypatch) and call ``reload_env`` themselves after each change."""
+    _gpu_ctx_session.reload_env()
+    yield _gpu_ctx_session
+    _gpu_ctx_session.reload_env()

@@ -133,8 +133,10 @@ def test_multi_pass_schedule_equals_single_launch(gpu_ctx, monkeypatch):
         for alpha in (a, memo):
             ref = metric_do_batch(gpu_ctx, alpha, dialect, f, s)
             monkeypatch.setenv("PCGDO_EXPLICIT_MULTI_PASS", "1")
+            gpu_ctx.reload_env()
             r = metric_do_batch(gpu_ctx, alpha, dialect, f, s)
             monkeypatch.delenv("PCGDO_EXPLICIT_MULTI_PASS")
+            gpu_ctx.reload_env()
             assert np.array_equal(ref.cost, r.cost) and np.array_equal(ref.final_offset, r.final_offset)
             assert np.array_equal(ref.out_len, r.out_len) and np.array_equal(ref.cells, r.cells)
             for k in range(len(pairs)):

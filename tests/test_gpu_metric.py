@@ -94,8 +94,10 @@ def test_register_kernel_equals_table_kernel(gpu_ctx, monkeypatch):
         ref = metric_do_batch(gpu_ctx, 21, dialect, f, s)
         for env in ("PCGDO_METRIC_REGISTERS", "PCGDO_NO_PACK16"):
             monkeypatch.setenv(env, "1")
+            gpu_ctx.reload_env()
             r = metric_do_batch(gpu_ctx, 21, dialect, f, s)
             monkeypatch.delenv(env)
+            gpu_ctx.reload_env()
             assert np.array_equal(ref.cost, r.cost) and np.array_equal(ref.final_offset, r.final_offset), (dialect, env)
             for k in range(len(pairs)):
                 for x, y in zip(ref.pair(k)[1:], r.pair(k)[1:]):
