@@ -97,6 +97,30 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+DUAL_PIPE_PEAK_T = 36.5      # profiles/r01_int_pipes_ubench.txt: VIADDMNMX + IMAD together, 125.6 lane-instr/clk/SM at 1965 MHz
+
+
+def int_issue_peak(ctx):
+    """Roofline denominator of the DP fills: integer lane-instructions/s with BOTH integer pipes issuing (one VIADDMNMX on
+    the ALU pipe + one IMAD on the FMA pipe per pair) — measured live after a warm-up, and never taken below the figure the
+    dedicated micro-benchmark reached on this pool (a low live number would flatter the fraction)."""
+    live = max(ctx.int32_peak(0), ctx.int32_peak(1)) / 1e12
+    return {"peak": max(live, DUAL_PIPE_PEAK_T), "live": live,
+            "source": "max(live pcgdo_int32_peak after warm-up, 36.5 T of profiles/r01_int_pipes_ubench.txt); "
+                      "nominal 148 SMs x 128 lanes x 1.965 GHz = 37.2 T"}
+
+
+def source_hash():
+    """Hash of the kernel sources: ties profiles/traffic.json (an ncu capture) to the build being timed."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "pcg_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -130,7 +154,7 @@ def cpu_arm(n_sample_hint, threads, kind_pref="reference", seconds_target=12.0):
     pp = PackedPairs.uniform(make_strings(n))
     sec, cost, cells = po.cpu_bench_align2d(sig, pp, threads, kind)
     return {"gcups": float(cells.sum() / sec / 1e9), "seconds": sec, "pairs": n, "kind": kind,
-            "cores": threads, "cost_checksum": int(cost.astype(np.int64).sum())}
+            "cores": threads, "cost_checksum": int(cost.astype(np.int64).sum()), "cost": cost}
 
 
 
@@ -223,14 +247,59 @@ def run_postorder(args, rank, world, local_rank, ctx, torch, dist, full=True):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     n_align = n_trees * n_chars * ((n_taxa - 1) + ((4 * n_taxa - 8) if args.reroot else 0))
+    launches = ctx.last_kernel_ms()[1]
+    # ---- roofline of the sweep: the same integer-issue bound as config 2, over the band cells of all alignments
+    roofline = None
+    if not args.reroot:
+        cells_rank = float(forest.cells())
+        cells_all = cells_rank
+        if world > 1:
+            tt = torch.tensor([cells_rank], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt)
+            cells_all = float(tt.item())
+        pk = int_issue_peak(ctx)
+        ach = cells_rank * ALG_OPS_PER_CELL / (ms * 1e-3) / 1e12
+        roofline = {"bound": "int32-issue", "achieved": ach, "peak": pk["peak"], "unit": "Tinstr/s", "frac": ach / pk["peak"],
+                    "peak_live": pk["live"], "peak_source": pk["source"], "alg_ops_per_cell": ALG_OPS_PER_CELL,
+                    "cells_per_sweep": cells_all, "gcups": cells_all / (ms * 1e-3) / 1e9, "traffic": None,
+                    "note": "whole sweep (all levels: descriptor prep + DO kernels + totals) timed as one region; per-level "
+                            "shares in profiles/"}
+    # ---- candidate-tree turnover: a FRESH set of topologies is uploaded and levelled (on the device) before every
+    # sweep, as a search does; alternates between two sets so that no sweep re-scores resident trees
+    fresh = None
+    if not args.reroot and not args.no_fresh_trees:
+        from pcg_b200.postorder import random_binary_trees
+        alt = [children, random_binary_trees(n_trees, n_taxa, PO["tree_seed"] + 1)]
+
+        def fstep(i):
+            forest.set_trees(alt[i & 1])
+            step()
+        fstep(1); fstep(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fstep(i + 1)
+        barrier()
+        fms = (time.perf_counter() - t0) / steps * 1e3
+        if world > 1:
+            tt = torch.tensor([fms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            fms = float(tt.item())
+        forest.set_trees(children)
+        step(); barrier()
+        assert int(costs.sum().item()) == checksum, "scores changed after the trees were swapped out and back in"
+        fresh = {"value": n_trees / (fms * 1e-3), "unit": "tree-evals/s", "ms_per_sweep": fms,
+                 "how": "pcgdo_forest_set_trees (upload 4 MB of child ids, validate + level on the device) + sweep, host wall "
+                        "clock, every sweep on topologies the forest has not scored in the previous sweep"}
     out = {"metric": "postorder tree cost evals/sec" + (" (with re-rooting)" if args.reroot else ""),
            "value": n_trees / (ms * 1e-3), "unit": "tree-evals/s",
-           "ms_per_sweep": ms, "scaling": "strong", "levels": forest.levels,
+           "ms_per_sweep": ms, "steps": steps, "scaling": "strong", "levels": forest.levels,
+           "roofline": roofline, "fresh_trees": fresh,
            "alignments_per_sweep": n_align,
            "config": {"workload": "config5: post-order of random binary trees x dynamic DNA characters, discrete TCM",
                       "n_trees": n_trees, "n_taxa": n_taxa, "n_chars": n_chars, "leaf_len": leaf_len,
                       "chars_per_gpu": cpr, "collective": "1 all_reduce(int64[n_trees]) per sweep" if world > 1 else "none"},
-           "cost_checksum": checksum, "gpu_launches_per_sweep": ctx.last_kernel_ms()[1]}
+           "cost_checksum": checksum, "gpu_launches_per_sweep": launches}
     if rank == 0 and world == 1 and not args.no_cpu and not args.reroot:
         info = po_cpu_arm(children, leaves, host_threads(), seconds_target=8.0)
         # parity spot check of the same columns against the device totals
@@ -250,7 +319,54 @@ def run_postorder(args, rank, world, local_rank, ctx, torch, dist, full=True):
                                          f"{info['cores']} host threads; root totals of the first 64 columns checked "
                                          f"equal to the device's"}
     forest.close()
+    del forest
+    torch.cuda.empty_cache()
+    # ---- the same sweep through the library's own multi-GPU path (pcgdo_multi: one process, all N devices, forests sharded
+    # by character blocks, the three reductions).  Under torchrun rank 0 alone drives it while the other ranks — whose
+    # forests are closed — wait on a CPU barrier (an NCCL barrier would spin on their GPUs).
+    if world > 1 and not args.reroot and not args.no_library_multi:
+        g = getattr(run_postorder, "_gloo", None)
+        if g is None:
+            g = dist.new_group(backend="gloo")
+            run_postorder._gloo = g
+        torch.cuda.synchronize()
+        dist.barrier(group=g)
+        if rank == 0:
+            try:
+                out["library_multi_gpu"] = library_multi_sweep(world, children, leaves, n_trees, n_taxa, args, checksum)
+            except Exception as ex:
+                out["library_multi_gpu"] = {"value": None, "error": str(ex)[:300]}
+        dist.barrier(group=g)
     return out
+
+
+def library_multi_sweep(n_dev, children, leaves, n_trees, n_taxa, args, checksum):
+    import pcg_b200 as P
+    from pcg_b200.backend import REDUCE_HOST, REDUCE_PEER, REDUCE_NCCL
+    m = P.Multi(list(range(n_dev)))
+    m.configure(args.ppw, args.warps, PO["node_cap"], 32)
+    mt = m.tcm(discrete_tcm())
+    mf = m.forest(children, n_taxa, leaves, PO["node_cap"])
+    res = {}
+    for name, mode in (("host_add", REDUCE_HOST), ("peer_kernel", REDUCE_PEER), ("nccl_allreduce", REDUCE_NCCL)):
+        try:
+            m.score(mt, mf, reduce_mode=mode)
+            walls, sweeps, reds = [], [], []
+            for _ in range(max(2, args.po_steps)):
+                cost, wall, sweep, red = m.score(mt, mf, reduce_mode=mode)
+                walls.append(wall); sweeps.append(sweep); reds.append(red)
+            assert int(cost.sum()) == checksum, "library multi-GPU costs differ from the torch.distributed run"
+            res[name] = {"ms_per_sweep_wall": float(np.mean(walls)), "slowest_device_sweep_ms": float(np.mean(sweeps)),
+                         "reduce_ms": float(np.mean(reds)), "tree_evals_per_s": n_trees / (float(np.mean(walls)) * 1e-3)}
+        except Exception as ex:
+            res[name] = {"error": str(ex)[:200]}
+    m.destroy_forest(mf)
+    m.close()
+    ok = [v for v in res.values() if "tree_evals_per_s" in v]
+    return {"value": max(v["tree_evals_per_s"] for v in ok) if ok else None, "unit": "tree-evals/s", "devices": n_dev,
+            "how": "ONE process: pcgdo_mforest_score over all devices (one host thread per device inside the library, "
+                   "characters sharded), host wall clock per sweep including the reduction of int64[n_trees]",
+            "reductions": res, "cost_checksum": checksum}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -279,14 +395,16 @@ def config3_pairs(n_pairs, rank=0):
     return PackedPairs(n_pairs, elems, off1, off2, len1, len2, ostarts[:-1].copy(), int(ostarts[-1]) + 16)
 
 
-def run_config3(args, rank, world, local_rank, ctx, torch, dist):
+def run_config3(args, rank, world, local_rank, ctx, torch, dist, steps=None, n=None):
     import ctypes as C
     from pcg_b200.backend import Batch
-    n = args.pairs if args.pairs != (1 << 20) else 100000
+    if n is None:
+        n = args.pairs if args.pairs != (1 << 20) else 100000
+    steps = steps or args.steps
+    warm = max(args.warmup, 3)
     GO, VARIANT = 3, 1
     pp = config3_pairs(n, rank)
     ctx.configure(pairs_per_warp=min(args.ppw, 8), warps_per_cta=16, max_len=5250, max_b=32)
-    tcm = ctx.tcm(discrete_tcm(), gap_open=GO, affine_variant=VARIANT)
     dev = torch.device("cuda", local_rank)
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
     d_elems = t(pp.elems)
@@ -303,43 +421,94 @@ def run_config3(args, rank, world, local_rank, ctx, torch, dist):
               d_s2.data_ptr(), d_olen.data_ptr(), d_cost.data_ptr(), d_cells.data_ptr())
     stream = torch.cuda.current_stream()
 
-    def step():
-        ctx.check(ctx.lib.pcgdo_align2d_affine_batch_device(ctx.h, tcm.h, C.byref(b), C.c_void_p(stream.cuda_stream)),
-                  "pcgdo_align2d_affine_batch_device")
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    total_cells = float(d_cells.sum().item())
-    checksum = int(d_cost.to(torch.int64).sum().item())
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-        kms.append(ctx.last_kernel_ms()[0])
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        tt = torch.tensor([ms, total_cells], device=dev, dtype=torch.float64)
-        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, total_cells = float(mx[0].item()), float(sm[1].item())
-    value = total_cells / (ms * 1e-3) / 1e9
+    def timed(tcm, k_steps):
+        def step():
+            ctx.check(ctx.lib.pcgdo_align2d_affine_batch_device(ctx.h, tcm.h, C.byref(b), C.c_void_p(stream.cuda_stream)),
+                      "pcgdo_align2d_affine_batch_device")
+        for _ in range(warm):
+            step()
+        cells = float(d_cells.sum().item())
+        checksum = int(d_cost.to(torch.int64).sum().item())
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = []
+        e0.record(stream)
+        for _ in range(k_steps):
+            step()
+            kms.append(ctx.last_kernel_ms()[0])
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1) / k_steps
+        cells_all = cells
+        if world > 1:
+            tt = torch.tensor([ms, cells], device=dev, dtype=torch.float64)
+            mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, cells_all = float(mx[0].item()), float(sm[1].item())
+        return {"ms": ms, "kernel_ms": float(np.mean(kms)), "cells_rank": cells, "cells_all": cells_all,
+                "gcups": cells_all / (ms * 1e-3) / 1e9, "checksum": checksum, "clocks": clocks,
+                "launches": ctx.last_kernel_ms()[1]}
+
+    tcm = ctx.tcm(discrete_tcm(), gap_open=GO, affine_variant=VARIANT)
+    rd = timed(tcm, steps)
+    cost_d = d_cost.cpu().numpy().copy()
+    olen_d = d_olen.cpu().numpy().copy()
+    # BASELINE.md §2 runs gap-open 3 with the L1-norm matrix as well (app/affine-safety.hs:71-87): second arm, fewer steps
+    tcm_l1 = ctx.tcm(l1_tcm(), gap_open=GO, affine_variant=VARIANT)
+    rl = timed(tcm_l1, max(3, steps // 3))
+
+    # ---- end to end: pinned host buffers through pcgdo_align2d_affine_batch_host (chunked copy / align / copy pipeline)
+    e2e = None
+    if not args.no_e2e:
+        try:
+            pin = lambda a: torch.from_numpy(a).pin_memory().numpy()   # noqa: E731
+            h_elems = pin(pp.elems)
+            h_g, h_s1, h_s2 = (torch.empty(pp.out_bytes, dtype=torch.uint8).pin_memory().numpy() for _ in range(3))
+            h_cost, h_olen = (torch.empty(n, dtype=torch.int32).pin_memory().numpy() for _ in range(2))
+            h_off1, h_off2, h_len1, h_len2, h_ooff = (pin(a) for a in (pp.off1, pp.off2, pp.len1, pp.len2, pp.out_off))
+            hb = Batch(n, h_elems.ctypes.data, pp.elems.nbytes, h_off1.ctypes.data, h_off2.ctypes.data, h_len1.ctypes.data,
+                       h_len2.ctypes.data, h_ooff.ctypes.data, pp.out_bytes, h_g.ctypes.data, h_s1.ctypes.data,
+                       h_s2.ctypes.data, h_olen.ctypes.data, h_cost.ctypes.data, None, None)
+
+            def estep():
+                ctx.check(ctx.lib.pcgdo_align2d_affine_batch_host(ctx.h, tcm.h, C.byref(hb)), "pcgdo_align2d_affine_batch_host")
+            estep()
+            barrier()
+            esteps = max(3, steps // 2)
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                estep()
+            barrier()
+            dt = (time.perf_counter() - t0) / esteps
+            if world > 1:
+                tt = torch.tensor([dt], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            assert np.array_equal(h_cost, cost_d) and np.array_equal(h_olen, olen_d), "host path differs from the device-resident run"
+            step_dev = lambda: ctx.check(ctx.lib.pcgdo_align2d_affine_batch_device(ctx.h, tcm.h, C.byref(b), C.c_void_p(stream.cuda_stream)), "affine")  # noqa: E731
+            step_dev(); torch.cuda.synchronize()
+            for k in np.linspace(0, n - 1, 16).astype(np.int64):
+                o, ln = int(pp.out_off[k]), int(h_olen[k])
+                for hbuf, dbuf in ((h_g, d_g), (h_s1, d_s1), (h_s2, d_s2)):
+                    assert np.array_equal(hbuf[o:o + ln], dbuf[o:o + ln].cpu().numpy()), int(k)
+            e2e = {"value": rd["cells_all"] / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "steps": esteps,
+                   "h2d_bytes_per_step": int(pp.elems.nbytes + 40 * n),
+                   "d2h_bytes_per_step": int(3 * int(pp.out_off[-1] + ((int(pp.len1[-1]) + int(pp.len2[-1]) + 3) & ~3)) + 8 * n)}
+            del h_elems, h_g, h_s1, h_s2
+        except Exception as ex:
+            e2e = {"value": None, "unit": "GCUPS", "error": str(ex)[:200]}
     if rank != 0:
         return None
-    k_ms = float(np.mean(kms))
-    int_peak = max(ctx.int32_peak(0), ctx.int32_peak(1)) / 1e12
-    ach = total_cells / max(world, 1) * 24 / (k_ms * 1e-3) / 1e12      # 24 integer ops per affine cell
+    pk = int_issue_peak(ctx)
+    ach = rd["cells_rank"] * 24 / (rd["kernel_ms"] * 1e-3) / 1e12      # 24 integer ops per affine cell
     cpu = None
     if not args.no_cpu and world == 1:
         from oracle import pyoracle as po
@@ -352,22 +521,25 @@ def run_config3(args, rank, world, local_rank, ctx, torch, dist):
         sec, cost, _ = po.cpu_bench_align2d(discrete_tcm(), sub, threads, kind, want_cells=False, gap_open=GO,
                                             affine_variant=VARIANT)
         cells_s = float(d_cells[:ns].sum().item())
-        assert np.array_equal(cost, d_cost[:ns].cpu().numpy()), "device costs differ from the CPU arm on the sample"
+        assert np.array_equal(cost, cost_d[:ns]), "device costs differ from the CPU arm on the sample"
         cpu = {"value": cells_s / sec / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
                "sample": f"first {ns} pairs, {sec:.1f} s on {threads} host threads "
                          f"(align2dAffine of the one-expression-patched reference build); costs equal to the device's"}
-    return {"metric": "2D DO alignment GCUPS (affine)", "value": value, "unit": "GCUPS", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+    return {"metric": "2D DO alignment GCUPS (affine)", "value": rd["gcups"], "unit": "GCUPS", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": rd["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "config3: affine-gap DO, ~5 kb IUPAC-ambiguous DNA pairs, discrete TCM, gap-open 3, "
                                    "C-affine dialect (patched substitution lookup)",
-                       "pairs_per_gpu": n, "len": "U[4750,5250]", "cells_per_pair_avg": total_cells / world / n,
+                       "pairs_per_gpu": n, "len": "U[4750,5250]", "cells_per_pair_avg": rd["cells_rank"] / n,
                        "l2": "inputs (1 GB) and direction scratch exceed the 126 MB L2"},
-            "clocks": clocks, "gpu_launches": args.steps,
-            "roofline": {"bound": "int32-issue", "achieved": ach, "peak": int_peak, "unit": "Tinstr/s",
-                         "frac": ach / int_peak if int_peak else None, "alg_ops_per_cell": 24, "kernel_ms": k_ms,
-                         "traffic": None},
-            "cpu_baseline": cpu, "cost_checksum": checksum}
+            "clocks": rd["clocks"], "e2e": e2e, "gpu_launches": rd["launches"] * steps,
+            "roofline": {"bound": "int32-issue", "achieved": ach, "peak": pk["peak"], "unit": "Tinstr/s",
+                         "frac": ach / pk["peak"], "peak_live": pk["live"], "peak_source": pk["source"],
+                         "alg_ops_per_cell": 24, "kernel_ms": rd["kernel_ms"], "traffic": None},
+            "cpu_baseline": cpu, "cost_checksum": rd["checksum"],
+            "l1_tcm": {"workload": "same pairs, L1-norm matrix, gap-open 3", "value": rl["gcups"], "unit": "GCUPS",
+                       "ms_per_step": rl["ms"], "kernel_ms": rl["kernel_ms"], "steps": max(3, steps // 3),
+                       "cost_checksum": rl["checksum"], "clocks": rl["clocks"]}}
 
 # ------------------------------------------------------------------------------------------------
 # Config 4 (BASELINE.json configs[3]): amino-acid DO, 21-state alphabet, 500 000 pairs of 400 residues
@@ -393,11 +565,13 @@ def pref_gap_tcm(a=21):
     return m.astype(np.uint32)                                     # bench/strings/protein/protein-pref-gap.tcm
 
 
-def run_config4(args, rank, world, local_rank, ctx, torch, dist):
+def run_config4(args, rank, world, local_rank, ctx, torch, dist, steps=None, n=None):
     import ctypes as C
     from pcg_b200.backend import Batch32
     A, L4, DIALECT = 21, 400, 2
-    n = args.pairs if args.pairs != (1 << 20) else 500000
+    if n is None:
+        n = args.pairs if args.pairs != (1 << 20) else 500000
+    steps = steps or args.steps
     strings = config4_strings(n, rank, L4)
     elems = np.ascontiguousarray(strings.reshape(-1))
     k = np.arange(n, dtype=np.uint64)
@@ -446,13 +620,13 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kms = []
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
             kms.append(ctx.last_kernel_ms()[0])
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
-        ms = e0.elapsed_time(e1) / args.steps
+        ms = e0.elapsed_time(e1) / steps
         if world > 1:
             tt = torch.tensor([ms, cells], device=dev, dtype=torch.float64)
             mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -487,10 +661,10 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist):
             estep()
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
+            for _ in range(steps):
                 estep()
             barrier()
-            dt = (time.perf_counter() - t0) / args.steps
+            dt = (time.perf_counter() - t0) / steps
             if world > 1:
                 tt = torch.tensor([dt], device=dev)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -503,8 +677,10 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist):
             e2e = {"value": None, "unit": "GCUPS", "error": str(ex)[:200]}
     if rank != 0:
         return None
-    int_peak = max(ctx.int32_peak(0), ctx.int32_peak(1)) / 1e12
+    pk = int_issue_peak(ctx)
+    int_peak = pk["peak"]
     ach = rd["cells_rank"] * ALG_OPS_PER_CELL / (rd["kernel_ms"] * 1e-3) / 1e12
+    ach_x = rx["cells_rank"] * ALG_OPS_PER_CELL / (rx["kernel_ms"] * 1e-3) / 1e12
     cpu = cpu_x = None
     if not args.no_cpu and world == 1:
         from oracle import pyoracle as po
@@ -526,23 +702,132 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist):
                  "sample": f"first {nx} pairs, {sec:.1f} s on {threads} host threads (restated dialect; every overlap "
                            f"answered by the compiled reference tcm-memo getCostAndMedian2D, one memo per thread)"}
     return {"metric": "2D DO alignment GCUPS (amino acids, a=21)", "value": rd["gcups"], "unit": "GCUPS", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rd["ms"], "higher_is_better": True,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": rd["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "config4: amino-acid DO, a=21, 400-residue pairs, discrete metric, S2 Ukkonen dialect "
                                    "(unboxedUkkonenFullSpaceDO)",
                        "pairs_per_gpu": n, "len": L4, "cells_per_pair_avg": rd["cells_rank"] / n,
                        "cells": "final Ukkonen band per pair (doubling refills not counted)",
                        "l2": "inputs (1.6 GB) and direction scratch exceed the 126 MB L2"},
-            "clocks": rd["clocks"], "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "clocks": rd["clocks"], "e2e": e2e, "gpu_launches": 2 * steps,
             "roofline": {"bound": "int32-issue", "achieved": ach, "peak": int_peak, "unit": "Tinstr/s",
-                         "frac": ach / int_peak if int_peak else None, "alg_ops_per_cell": ALG_OPS_PER_CELL,
-                         "kernel_ms": rd["kernel_ms"], "traffic": None},
+                         "frac": ach / int_peak if int_peak else None, "peak_live": pk["live"], "peak_source": pk["source"],
+                         "alg_ops_per_cell": ALG_OPS_PER_CELL, "kernel_ms": rd["kernel_ms"], "traffic": None,
+                         "cells": "final Ukkonen band only: the refills of the doubling schedule are work the reference "
+                                  "does too but are not counted on either arm"},
             "cpu_baseline": cpu, "cost_checksum": rd["checksum"],
             "explicit": {"workload": "same pairs, explicit matrix protein-pref-gap.tcm (sub 2 / indel 1) through the "
                                      "per-pair memo table (tcm-memo replacement)",
                          "value": rx["gcups"], "unit": "GCUPS", "ms_per_step": rx["ms"], "kernel_ms": rx["kernel_ms"],
                          "cells_per_pair_avg": rx["cells_rank"] / n, "cost_checksum": rx["checksum"],
+                         "clocks": rx["clocks"],
+                         "roofline": {"bound": "int32-issue", "achieved": ach_x, "peak": int_peak, "unit": "Tinstr/s",
+                                      "frac": ach_x / int_peak, "alg_ops_per_cell": ALG_OPS_PER_CELL},
                          "cpu_baseline": cpu_x}}
+
+# ------------------------------------------------------------------------------------------------
+# Config 2, secondary dialect: the same 1 kb DNA pairs and L1 matrix through `ukkonenDO`
+# (DO/Pairwise/Ukkonen/Internal.hs:79-202; S1 recurrence on a ribbon that doubles until the threshold exceeds the
+# cost).  Device: dialect 1 of pcgdo_explicit_batch_* over the matrix as an explicit overlap.  CPU: north_star asks for
+# the reference's ukkonenDO on the host cores; it is Haskell (no GHC here), so the timed code is the restatement
+# ("port").  cells = cells of each pair's FINAL ribbon, on both arms.
+# ------------------------------------------------------------------------------------------------
+def run_config2_ukkonen(args, rank, world, local_rank, ctx, torch, dist, steps=10, n=1 << 17):
+    import ctypes as C
+    from pcg_b200.backend import Batch32
+    A, DIALECT = 5, 1
+    # Unrelated 1 kb strings drive ukkonenDO's ribbon to the whole 1001 x 1001 matrix (2001 diagonals); the warp kernels
+    # hold bands of up to 1023 diagonals, so the DEVICE runs the 500-element prefixes of the same strings (1001
+    # diagonals) — stated in the line — while the CPU port is timed on both lengths.
+    LU = 500
+    full = make_strings(n, rank).astype(np.uint32)
+    strings = np.ascontiguousarray(full[:, :LU])
+    elems = np.ascontiguousarray(strings.reshape(-1))
+    k = np.arange(n, dtype=np.uint64)
+    off1 = k * np.uint64(2 * LU); off2 = off1 + np.uint64(LU)
+    ln = np.full(n, LU, np.uint32)
+    cnt = elems.size + 4
+    ctx.configure(pairs_per_warp=min(args.ppw, 8), warps_per_cta=16, max_len=LU, max_b=32)
+    memo = ctx.memo(l1_tcm(A), structure="explicit")
+    dev = torch.device("cuda", local_rank)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    d_elems = t(elems.view(np.int32))
+    d_off1, d_off2 = t(off1.view(np.int64)), t(off2.view(np.int64))
+    d_len = t(ln.view(np.int32))
+    d_m = torch.empty(cnt, dtype=torch.int32, device=dev)
+    d_a1, d_a2 = torch.empty_like(d_m), torch.empty_like(d_m)
+    d_olen, d_cost, d_fo = (torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3))
+    d_cells = torch.empty(n, dtype=torch.int64, device=dev)
+    b = Batch32(n, d_elems.data_ptr(), elems.size, d_off1.data_ptr(), d_off2.data_ptr(), d_len.data_ptr(), d_len.data_ptr(),
+                d_off1.data_ptr(), cnt, d_m.data_ptr(), d_a1.data_ptr(), d_a2.data_ptr(), d_olen.data_ptr(),
+                d_cost.data_ptr(), d_cells.data_ptr(), d_fo.data_ptr())
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ctx.check(ctx.lib.pcgdo_explicit_batch_device(ctx.h, memo.h, DIALECT, C.byref(b), C.c_void_p(stream.cuda_stream)),
+                  "pcgdo_explicit_batch_device")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(3):
+        step()
+    cells = float(d_cells.sum().item())
+    checksum = int(d_cost.to(torch.int64).sum().item())
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+        kms.append(ctx.last_kernel_ms()[0])
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / steps
+    cells_all = cells
+    if world > 1:
+        tt = torch.tensor([ms, cells], device=dev, dtype=torch.float64)
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, cells_all = float(mx[0].item()), float(sm[1].item())
+    if rank != 0:
+        return None
+    cpu = None
+    if not args.no_cpu and world == 1:
+        from oracle import pyoracle as po
+        threads = host_threads()
+        ns = max(threads, min(n, 8 * threads))
+        sec, cost, _, _ = po.cpu_bench_haskell(DIALECT, A, elems, off1[:ns].copy(), ln[:ns].copy(), off2[:ns].copy(),
+                                               ln[:ns].copy(), threads, sigma=l1_tcm(A))
+        assert np.array_equal(cost, d_cost[:ns].cpu().numpy()), "device costs differ from the restated ukkonenDO on the sample"
+        cpu = {"value": float(d_cells[:ns].sum().item()) / sec / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+               "sample": f"first {ns} pairs (500-element prefixes), {sec:.1f} s on {threads} host threads: ukkonenDO RESTATED in C "
+                         f"(oracle/do_oracle.c) — the reference's is Haskell and cannot be built here; costs equal to the device's"}
+        # the full 1 kb pairs of config 2 through the same port (CPU only: see above)
+        n1k = max(threads, 2 * threads)
+        e1k = np.ascontiguousarray(full[:2 * n1k].reshape(-1))
+        k1 = np.arange(n1k, dtype=np.uint64)
+        o1k = k1 * np.uint64(2 * L)
+        l1k = np.full(n1k, L, np.uint32)
+        sec1k, _, cells1k, _ = po.cpu_bench_haskell(DIALECT, A, e1k, o1k, l1k, o1k + np.uint64(L), l1k, threads, sigma=l1_tcm(A))
+        # the port counts the refills of the doubling schedule; the final ribbon of unrelated strings is the whole matrix
+        cpu["config2_1kb_pairs"] = {"value": float(n1k * (L + 1) * (L + 1)) / sec1k / 1e9, "unit": "GCUPS", "pairs": n1k,
+                                    "seconds": sec1k, "cells": "(L+1)^2 per pair (final ribbon = full matrix)",
+                                    "cells_incl_refills_gcups": float(cells1k.sum()) / sec1k / 1e9}
+    pk = int_issue_peak(ctx)
+    ach = cells * ALG_OPS_PER_CELL / (float(np.mean(kms)) * 1e-3) / 1e12
+    return {"metric": "2D DO alignment GCUPS (ukkonenDO, S1 ribbon)", "value": cells_all / (ms * 1e-3) / 1e9, "unit": "GCUPS",
+            "steps": steps, "ms_per_step": ms, "kernel_ms": float(np.mean(kms)), "pairs_per_gpu": n, "len": LU,
+            "workload": "500-element prefixes of the config-2 strings, L1 matrix as an explicit overlap, dialect 1 (ukkonenDO)",
+            "cells_per_pair_avg": cells / n, "cells": "final ribbon per pair", "clocks": clocks,
+            "roofline": {"bound": "int32-issue", "achieved": ach, "peak": pk["peak"], "unit": "Tinstr/s",
+                         "frac": ach / pk["peak"], "alg_ops_per_cell": ALG_OPS_PER_CELL},
+            "cpu_baseline": cpu, "cost_checksum": checksum}
+
 
 # ------------------------------------------------------------------------------------------------
 # Config 1 (BASELINE.json configs[0], "bench-string-alignment-small"): the 190 unordered pairs of the 20 strings of
@@ -643,6 +928,10 @@ def main():
     ap.add_argument("--po-steps", type=int, default=2)
     ap.add_argument("--reroot", action="store_true", help="config5: add the re-rooting pass (3 slots per node: use "
                                                            "--po-trees 256 to stay within HBM)")
+    ap.add_argument("--no-fresh-trees", action="store_true", help="config5: skip the candidate-tree turnover variant")
+    ap.add_argument("--no-library-multi", action="store_true", help="config5, N > 1: skip the one-process pcgdo_multi sweep")
+    ap.add_argument("--no-extra", action="store_true", help="default workload: skip the config-3 / config-4 / Ukkonen sections")
+    ap.add_argument("--section-steps", type=int, default=0, help="timed steps of the config-3 / config-4 sections (0 = 10)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="e2e: copy capacity-sized output slots back (no packing)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -741,6 +1030,7 @@ def main():
         step()
     assert int(d_cells[0].item()) == cpp, (int(d_cells[0].item()), cpp)
     cost_checksum = int(d_cost.to(torch.int64).sum().item())
+    cost_host = d_cost.cpu().numpy().copy()
 
     sampler = ClockSampler(local_rank)
     barrier()
@@ -818,13 +1108,35 @@ def main():
 
     # ---- second half of the metric: post-order tree scoring (config 5), same process, after the pair bench
     postorder = None
+    del d_elems, d_g, d_s1, d_s2
+    torch.cuda.empty_cache()
     if not args.no_postorder:
-        del d_elems, d_g, d_s1, d_s2
-        torch.cuda.empty_cache()
         try:
             postorder = run_postorder(args, rank, world, local_rank, ctx, torch, dist)
         except Exception as ex:
             postorder = {"value": None, "error": str(ex)[:300]}
+
+    # ---- the other BASELINE configs as sections of the same line (each with roofline, cpu_baseline, e2e, clocks)
+    sec_steps = args.section_steps or 10
+    config3 = config4 = ukkonen = None
+    if not args.no_extra:
+        for name in ("config3", "config4", "ukkonen"):
+            try:
+                if name == "config3":
+                    config3 = run_config3(args, rank, world, local_rank, ctx, torch, dist, steps=sec_steps, n=100000)
+                elif name == "config4":
+                    config4 = run_config4(args, rank, world, local_rank, ctx, torch, dist, steps=sec_steps, n=500000)
+                else:
+                    ukkonen = run_config2_ukkonen(args, rank, world, local_rank, ctx, torch, dist, steps=sec_steps)
+            except Exception as ex:
+                err = {"value": None, "error": str(ex)[:300]}
+                if name == "config3":
+                    config3 = err
+                elif name == "config4":
+                    config4 = err
+                else:
+                    ukkonen = err
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -838,23 +1150,26 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    int_peak = max(ctx.int32_peak(0), ctx.int32_peak(1)) / 1e12          # T lane-instr/s, measured now
+    pk = int_issue_peak(ctx)
     achieved_tops = total_cells * ALG_OPS_PER_CELL / (k_ms * 1e-3) / 1e12
     alg_bytes = n * (2 * L + 3 * 2 * L + 8) + total_cells / 4.0           # in + out + 2-bit directions spilled
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture committed for this build"
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("do_linear_kernel_bytes_per_launch_at_bench_size")
+            tj = json.load(open(tp))
+            if tj.get("source_hash") == source_hash():
+                traffic = tj.get("do_linear_kernel_bytes_per_launch_at_bench_size")
+                traffic_note = tj.get("how")
+            else:
+                traffic_note = ("profiles/traffic.json was captured for other kernel sources (hash %s, now %s): not reported"
+                                % (tj.get("source_hash"), source_hash()))
         except Exception:
             pass
-    roofline = {"bound": "int32-issue", "achieved": achieved_tops, "peak": int_peak, "unit": "Tinstr/s",
-                "frac": achieved_tops / int_peak if int_peak else None, "traffic": traffic,
-                "peak_source": "measured live (pcgdo_int32_peak: independent VIADDMNMX+IMAD chains on all SMs)",
+    roofline = {"bound": "int32-issue", "achieved": achieved_tops, "peak": pk["peak"], "unit": "Tinstr/s",
+                "frac": achieved_tops / pk["peak"], "traffic": traffic, "traffic_note": traffic_note,
+                "peak_live": pk["live"], "peak_source": pk["source"],
                 "alg_ops_per_cell": ALG_OPS_PER_CELL, "kernel_ms": k_ms,
-                # the stricter denominator: both integer pipes issuing every cycle, as the dedicated micro-benchmark
-                # reaches (profiles/r01_int_pipes_ubench.txt: 125.6 of 128 lane-instructions per clock per SM at 1965 MHz)
-                "frac_vs_dual_pipe_peak": achieved_tops / 36.5, "dual_pipe_peak": 36.5,
                 "hbm": {"alg_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak}}
@@ -862,9 +1177,12 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         info = cpu_arm(1 << 20, host_threads(), seconds_target=12.0)
+        # the CPU arm ran the first pairs of the timed workload: its costs must be the device's
+        assert np.array_equal(info["cost"], cost_host[:info["pairs"]]), "device costs differ from the reference's on the CPU sample"
         cpu = {"value": info["gcups"], "unit": "GCUPS", "cores": info["cores"], "kind": info["kind"],
                "sample": f"first {info['pairs']} pairs of the same seeded workload, {info['seconds']:.1f} s on "
-                         f"{info['cores']} host threads (oracle/_ref align2d, per-call malloc/free as FFI.hsc)"}
+                         f"{info['cores']} host threads (oracle/_ref align2d, per-call malloc/free as FFI.hsc); "
+                         f"its {info['pairs']} costs equal the device's"}
 
     line = {"metric": "2D DO alignment GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -872,8 +1190,9 @@ def main():
             "config": {"workload": "config2: batched 2D DO, 1 kb uniform DNA pairs, L1 TCM, align2d band (C-linear)",
                        "pairs_per_gpu": n, "len": L, "cells_per_pair": cpp, "full_equiv_gcups": value * L * L / cpp,
                        "l2": "inputs (2.1 GB) and direction scratch (>4 GB) exceed the 126 MB L2",
-                       "seed": SEED},
+                       "seed": SEED, "source_hash": source_hash()},
             "clocks": clocks, "e2e": e2e, "gpu_launches": ctx_launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "postorder": postorder,
+            "config3": config3, "config4": config4, "config2_ukkonen": ukkonen,
             "cost_checksum": cost_checksum}
     print(json.dumps(line), flush=True)
     if world > 1:

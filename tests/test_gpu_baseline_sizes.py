@@ -149,7 +149,15 @@ def test_config4_amino_acids_400(oracle_mod, gpu_ctx, kind):
             2, A, elems, off1, ln, off2, ln, THREADS, sigma=sig, through_reference_memo=oracle_mod.ReferenceMemo.available())
     assert np.array_equal(r.cost, cost)
     assert np.array_equal(r.final_offset, fo)
-    assert np.array_equal(r.cells, cells)
+    # the device counts the cells of the FINAL band (the restatement's counter also includes the refills of the
+    # doubling schedule): rows 0..m, columns j with j - i in [-o, (n - m) + o] clipped to 0..n; o = -1: full matrix
+    def final_band(o, m=L4, nn=L4):
+        if o < 0:
+            return (m + 1) * (nn + 1)
+        i = np.arange(m + 1)
+        return int((np.minimum(nn, i + (nn - m) + o) - np.maximum(0, i - o) + 1).clip(min=0).sum())
+    assert np.array_equal(r.cells, np.array([final_band(int(o)) for o in fo], np.uint64))
+    assert (cells >= r.cells).all()
     assert np.array_equal(r.out_len, out_len)
     for i in range(n):
         _, m, a1, a2 = r.pair(i)

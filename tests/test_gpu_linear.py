@@ -303,7 +303,7 @@ def test_compact_transfer_equals_plain(oracle_mod, gpu_ctx, monkeypatch, chunk, 
     if pinned:
         assert np.array_equal(r.out_off, pp.out_off)
     else:
-        assert int(r.out_off[6]) < int(pp.out_off[6])             # still packed
+        assert (r.out_off != pp.out_off).any() and int(r.out_off.max()) < int(pp.out_off[-1])      # still packed
         order = np.argsort(r.out_off)
         ends = r.out_off[order] + ((r.out_len[order].astype(np.uint64) + 3) & ~np.uint64(3))
         assert (ends[:-1] <= r.out_off[order][1:]).all()          # disjoint ranges, stragglers included
