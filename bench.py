@@ -104,7 +104,7 @@ def int_issue_peak(ctx):
     """Roofline denominator of the DP fills: integer lane-instructions/s with BOTH integer pipes issuing (one VIADDMNMX on
     the ALU pipe + one IMAD on the FMA pipe per pair) — measured live after a warm-up, and never taken below the figure the
     dedicated micro-benchmark reached on this pool (a low live number would flatter the fraction)."""
-    live = max(ctx.int32_peak(0), ctx.int32_peak(1)) / 1e12
+    live = max(ctx.int32_peak(0), ctx.int32_peak(1), ctx.int32_peak(2)) / 1e12
     return {"peak": max(live, DUAL_PIPE_PEAK_T), "live": live,
             "source": "max(live pcgdo_int32_peak after warm-up, 36.5 T of profiles/r01_int_pipes_ubench.txt); "
                       "nominal 148 SMs x 128 lanes x 1.965 GHz = 37.2 T"}
@@ -119,6 +119,32 @@ def source_hash():
         if f.endswith((".cu", ".cuh", ".h", ".cpp")):
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of its GPU's NUMA node BEFORE anything is allocated, so that its pinned host
+    buffers (first touch) and the copy engine's DMA stay on the GPU's side of the host.  With one process per GPU this
+    is what keeps N ranks from funnelling their 5.6 GB per step through one socket.  Returns what it did (for the line)."""
+    try:
+        import subprocess as sp
+        bus = sp.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                     capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"gpu": local_rank, "pci": bus, "numa_node": node, "bound": False}
+        txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        return {"gpu": local_rank, "pci": bus, "numa_node": node, "cpus": len(use), "bound": bool(cpus & allowed)}
+    except Exception as ex:
+        return {"gpu": local_rank, "bound": False, "error": str(ex)[:120]}
 
 
 def host_threads():
@@ -579,7 +605,7 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist, steps=None, n=N
     ln = np.full(n, L4, np.uint32)
     out_off = off1.copy()
     cnt = elems.size + 4
-    ctx.configure(pairs_per_warp=min(args.ppw, 8), warps_per_cta=16, max_len=L4, max_b=32)
+    ctx.configure(pairs_per_warp=min(args.ppw, int(os.environ.get("BENCH_C4_PPW", "8"))), warps_per_cta=16, max_len=L4, max_b=32)
     memo = ctx.memo(pref_gap_tcm(A))
     dev = torch.device("cuda", local_rank)
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
@@ -932,6 +958,7 @@ def main():
     ap.add_argument("--no-library-multi", action="store_true", help="config5, N > 1: skip the one-process pcgdo_multi sweep")
     ap.add_argument("--no-extra", action="store_true", help="default workload: skip the config-3 / config-4 / Ukkonen sections")
     ap.add_argument("--section-steps", type=int, default=0, help="timed steps of the config-3 / config-4 sections (0 = 10)")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="e2e: copy capacity-sized output slots back (no packing)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -945,6 +972,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa else None
     import torch
     import torch.distributed as dist
     import pcg_b200 as P
@@ -1190,7 +1218,7 @@ def main():
             "config": {"workload": "config2: batched 2D DO, 1 kb uniform DNA pairs, L1 TCM, align2d band (C-linear)",
                        "pairs_per_gpu": n, "len": L, "cells_per_pair": cpp, "full_equiv_gcups": value * L * L / cpp,
                        "l2": "inputs (2.1 GB) and direction scratch (>4 GB) exceed the 126 MB L2",
-                       "seed": SEED, "source_hash": source_hash()},
+                       "seed": SEED, "source_hash": source_hash(), "numa_binding_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": ctx_launches * args.steps, "roofline": roofline, "cpu_baseline": cpu, "postorder": postorder,
             "config3": config3, "config4": config4, "config2_ukkonen": ukkonen,
             "cost_checksum": cost_checksum}

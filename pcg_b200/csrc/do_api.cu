@@ -78,6 +78,7 @@ extern "C" int pcgdo_configure_env(pcgdo_ctx *ctx)
     k.affine_rowwise = getenv("PCGDO_AFFINE_ROWWISE") != nullptr;
     k.metric_registers = getenv("PCGDO_METRIC_REGISTERS") != nullptr;
     k.explicit_multi_pass = getenv("PCGDO_EXPLICIT_MULTI_PASS") != nullptr;
+    k.no_dict = getenv("PCGDO_NO_DICT") != nullptr;
     k.skip_ahead = getenv("PCGDO_NO_SKIP_AHEAD") ? 0 : getenv("PCGDO_SKIP_FACTOR") ? atoi(getenv("PCGDO_SKIP_FACTOR")) : 64;
     k.skip_b = getenv("PCGDO_SKIP_B") ? (unsigned)atoi(getenv("PCGDO_SKIP_B")) : 0u;
     { const char *e = getenv("PCGDO_AFFINE_VARIANT"); k.affine_variant = (e && e[0] == '1') ? 1 : 0; }
@@ -127,7 +128,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_dict, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
                       &ctx->d_olen, &ctx->d_cost, &ctx->d_cells, &ctx->d_stage, &ctx->d_actual, &ctx->d_total, &ctx->d_strag};
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
@@ -927,12 +928,13 @@ extern "C" int pcgdo_explicit_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *mem
 
 // launch geometry of the per-pair table kernel for an alphabet of `a` symbols
 struct TableCfg { uint32_t seq_cap, tab_entries; int warps; size_t smem, arena_words, ts_words; };
-static int table_config(pcgdo_ctx *ctx, int a, TableCfg &c)
+static int table_config(pcgdo_ctx *ctx, int a, TableCfg &c, bool dict = false)
 {
     c.seq_cap = metric_seq_cap(ctx->max_len);
-    c.tab_entries = 1024;                                  // 2 KB of shared memory per warp for small tables
-    // a <= 32: sigma staged in shared memory; wider alphabets keep it in global memory and stage the gap element only
-    const size_t sg_bytes = a > 32 ? 64 : (((size_t)a * a * 4 + 15) & ~(size_t)15);
+    c.tab_entries = dict ? 0 : 1024;                       // 2 KB of shared memory per warp for small per-pair tables
+    // a <= 32: sigma staged in shared memory; wider alphabets keep it in global memory and stage the gap element only;
+    // batch-dictionary mode: one replicated table per CTA instead of the per-warp ones
+    const size_t sg_bytes = (a > 32 ? 64 : (((size_t)a * a * 4 + 15) & ~(size_t)15)) + (dict ? kDictSmemBytes : 0);
     const size_t per_warp = 512 + (size_t)c.seq_cap + 2 * (size_t)c.tab_entries;
     c.warps = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
     if (a > 32 && c.warps > 4) c.warps = 4;                // per-warp profile scratch grows with a * max_len
@@ -1080,8 +1082,28 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
         CK(launch_fullmatrix(p, grid, st));
         ctx->last_launches = 1;
     } else if (dialect == 0 || !ctx->knobs.explicit_multi_pass) {
-        CK(launch_explicit(p, grid, warps * 32, smem, st));
-        ctx->last_launches = 1;
+        // Batch dictionary (a <= 32): one pass over the batch's elements; when they are few (amino-acid strings with a
+        // handful of ambiguity codes) a single table over them, replicated per shared-memory bank, serves every pair —
+        // see DictDev.  One small read-back decides; batches with many distinct sets keep the per-pair tables.
+        int launches = 1;
+        if (a <= 32 && !ctx->knobs.no_dict && b->n_pairs >= 64) {
+            if ((rc = pcgdo_ensure(ctx, ctx->d_dict, sizeof(DictDev)))) return rc;
+            DictDev *dd = (DictDev *)ctx->d_dict.p;
+            CK(launch_dict(p, dd, grid, st));
+            launches += 2;
+            uint32_t hdr[4] = {0, 0, 0, 0};
+            CK(cudaMemcpyAsync(hdr, dd, sizeof hdr, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            TableCfg cd;
+            if (hdr[2] && table_config(ctx, a, cd, true) == PCGDO_OK && cd.warps >= 8) {
+                p.dict = dd;
+                p.smem_tab_entries = cd.tab_entries;
+                const int dw = cd.warps < warps ? cd.warps : warps;      // (arena and scratch are sized for `warps`)
+                CK(launch_explicit(p, grid, dw * 32, cd.smem, st));
+            }
+        }
+        if (!p.dict) CK(launch_explicit(p, grid, warps * 32, smem, st));
+        ctx->last_launches = launches;
     } else {
         // (experiment, off by default: it re-builds every pair's table per pass and measured slower than one launch)
         // one launch per offset of the doubling schedule; lists and counters live on the device, launches whose list
@@ -1358,10 +1380,16 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     // ---- pipelined path: the batch is cut into chunks whose strings and outputs are contiguous ranges of
     // the host buffers; chunk c+1 is copied in and chunk c-1 copied out while chunk c is aligned
     // (three streams, PCIe is full duplex).  Needs monotone layouts, which the packers produce; anything
-    // else takes the plain path below.  Affine pairs are three orders of magnitude heavier per byte: smaller chunks.
+    // else takes the plain path below.  Affine chunks are sized by CELLS, not pairs: a 5 kb pair is a million cells
+    // and occupies a warp for milliseconds, so a chunk must hold many pairs per resident warp or the end of every
+    // chunk — warps idle while the last pairs finish, the narrow and the wide kernel one after the other — dominates
+    // (measured: 4096-pair chunks of config 3 ran 3.4x slower than one launch).
     size_t chunk = ctx->knobs.host_chunk_pairs ? ctx->knobs.host_chunk_pairs
-                   : ctx->host_chunk_pairs     ? ctx->host_chunk_pairs
-                   : affine                    ? 4096 : 65536;
+                   : ctx->host_chunk_pairs     ? ctx->host_chunk_pairs : 65536;
+    if (affine && !ctx->knobs.host_chunk_pairs && !ctx->host_chunk_pairs) {
+        const size_t warps = (size_t)ctx->sm_count * (size_t)std::min(ctx->warps_per_cta, 16);
+        chunk = std::max<size_t>(16 * warps, 8192);           // >= 16 pairs per resident warp
+    }
     bool pipelined = n > chunk && (affine || ctx->max_b > 8);     // (wide kernel on: no per-chunk queue left behind)
     // COMPACT TRANSFER (b->out_off_actual).  The reference hands every alignment back in buffers of capacity
     // len1 + len2 + 2 (DO/Pairwise/FFI.hsc:474-481), of which an alignment of two similar strings fills about half;

@@ -45,12 +45,13 @@ struct pcgdo_ctx {
         bool affine_rowwise = false;   // PCGDO_AFFINE_ROWWISE     first-generation affine fill
         bool metric_registers = false; // PCGDO_METRIC_REGISTERS   do_metric.cu instead of the table kernel
         bool explicit_multi_pass = false;  // PCGDO_EXPLICIT_MULTI_PASS
+        bool no_dict = false;          // PCGDO_NO_DICT            large alphabets: per-pair tables only (no batch dictionary)
         int  skip_ahead = 64;          // PCGDO_SKIP_FACTOR / PCGDO_NO_SKIP_AHEAD (0)
         unsigned skip_b = 0;           // PCGDO_SKIP_B
         int  affine_variant = 0;       // PCGDO_AFFINE_VARIANT     reading of the reference's UB shift in the align2dAffine shim
     } knobs;
     // device scratch
-    DevBuf arena, counters, overflow, big, gen_scratch, gen_off, tscratch;
+    DevBuf arena, counters, overflow, big, gen_scratch, gen_off, tscratch, d_dict;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
     DevBuf d_strag;                  // descriptors of the few pairs a pipelined batch hands to the general-geometry kernel

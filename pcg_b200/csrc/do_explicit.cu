@@ -235,7 +235,7 @@ template <int B, bool GLOBAL, bool TAIL>
 __device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)[B], uint32_t (&dw)[B],
                                         uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t k4, uint32_t km1,
                                         uint32_t k1, const char *gtab, const uint32_t *&lptr, const uint32_t *&sptr,
-                                        int n_iter)
+                                        int n_iter, uint32_t lane_off, int lane)
 {
     constexpr int H = B / 2;
 #pragma unroll
@@ -255,7 +255,15 @@ __device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)
             dw[m] = m_imad(wn, km1, m_imad(dw[m], k4, mn));
             w[m] = wn;
         }
-        sw[tt] = sptr[r];
+        // Sliding windows by shuffle: the column this lane needs next is the one its right neighbour is about to drop
+        // (windows of adjacent lanes are H columns apart), the row it needs next the one its left neighbour drops; only
+        // lane 31 / lane 0 read the staged strings.  The per-lane loads this replaces were H-way bank conflicts (lanes H
+        // words apart): as many shared-memory wavefronts per iteration as all the table lookups together.
+        {
+            uint32_t nv = __shfl_down_sync(kFullM, sw[tt], 1) - (lane_off ? 4u : 0u);
+            if (lane == 31) nv = sptr[r] + lane_off;
+            sw[tt] = nv;
+        }
         const uint32_t wr = __shfl_down_sync(kFullM, w[0], 1);
 #pragma unroll
         for (int u = 0; u < H; ++u) {
@@ -269,7 +277,11 @@ __device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)
             dw[m] = m_imad(wn, km1, m_imad(dw[m], k4, mn));
             w[m] = wn;
         }
-        lw[(tt + 1) % H] = lptr[r];
+        {
+            uint32_t nl = __shfl_up_sync(kFullM, lw[(tt + 1) % H], 1);
+            if (lane == 0) nl = lptr[r];
+            lw[(tt + 1) % H] = nl;
+        }
     }
     lptr += 16;
     sptr += 16;
@@ -278,7 +290,7 @@ __device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)
 // Lb / Sb: staged row-offset / column-offset words, entry 0 = the leading gap.
 template <int B, bool GLOBAL>
 __device__ __noinline__ uint32_t x_fill(const MGeom g, uint32_t k4, uint32_t km1, uint32_t k1, const char *gtab,
-                                        const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot, int lane)
+                                        const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot, int lane, uint32_t lane_off)
 {
     constexpr int H = B / 2;
     uint32_t w[B], penc[B], dw[B], lw[H], sw[H];
@@ -295,20 +307,20 @@ __device__ __noinline__ uint32_t x_fill(const MGeom g, uint32_t k4, uint32_t km1
 #pragma unroll
     for (int u = 0; u < H; ++u) {
         lw[(H - u) % H] = Lb[I0 - u];
-        sw[u] = Sb[J0 + u];
+        sw[u] = Sb[J0 + u] + lane_off;
     }
     const uint32_t *lptr = Lb + (I0 + 1), *sptr = Sb + (J0 + H);
     uint32_t *out = slot + qb;
     const int nfull = g.T >> 4, rem = g.T & 15;
     for (int c = 0; c < nfull; ++c) {
-        x_chunk<B, GLOBAL, false>(w, penc, dw, lw, sw, k4, km1, k1, gtab, lptr, sptr, 16);
+        x_chunk<B, GLOBAL, false>(w, penc, dw, lw, sw, k4, km1, k1, gtab, lptr, sptr, 16, lane_off, lane);
         m_store<B>(out, dw, 16);
         out += 32 * B;
     }
     if (rem) {
 #pragma unroll
         for (int m = 0; m < B; ++m) dw[m] = 0;
-        x_chunk<B, GLOBAL, true>(w, penc, dw, lw, sw, k4, km1, k1, gtab, lptr, sptr, rem);
+        x_chunk<B, GLOBAL, true>(w, penc, dw, lw, sw, k4, km1, k1, gtab, lptr, sptr, rem, lane_off, lane);
         m_store<B>(out, dw, rem);
     }
     const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0, m_last = q_last % B;
@@ -322,14 +334,14 @@ __device__ __noinline__ uint32_t x_fill(const MGeom g, uint32_t k4, uint32_t km1
 template <bool GLOBAL>
 __device__ __forceinline__ uint32_t x_dispatch(int B, const MGeom &g, uint32_t k4, uint32_t km1, uint32_t k1,
                                                const char *gtab, const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot,
-                                               int lane)
+                                               int lane, uint32_t lane_off)
 {
     switch (B) {
-        case 2:  return x_fill<2, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
-        case 4:  return x_fill<4, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
-        case 8:  return x_fill<8, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
-        case 16: return x_fill<16, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
-        default: return x_fill<32, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane);
+        case 2:  return x_fill<2, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane, lane_off);
+        case 4:  return x_fill<4, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane, lane_off);
+        case 8:  return x_fill<8, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane, lane_off);
+        case 16: return x_fill<16, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane, lane_off);
+        default: return x_fill<32, GLOBAL>(g, k4, km1, k1, gtab, Lb, Sb, slot, lane, lane_off);
     }
 }
 
@@ -348,17 +360,25 @@ __device__ __forceinline__ uint32_t x_ldg_u16(const char *base, uint32_t off)
     return v;
 }
 
+// Iterations unrolled per chunk of the packed fill.  32 diagonals per lane: FOUR — the 8-iteration body was 22 KB of
+// SASS; with the code of the other phases (staging, trace, emit, the narrow fills of the doubling schedule) running on
+// the same SM it fell out of the 32 KB instruction cache: a quarter of the fill's stall samples on config 4 were
+// "no instruction".  A direction word still covers 8 iterations: `phase` says which half of it a 4-iteration chunk is.
+__host__ __device__ constexpr int x_chunk_len(int B) { return B <= 8 ? 16 : (B == 16 ? 8 : 4); }
+
 template <int B, bool GLOBAL, bool TAIL>
 __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (&penc)[B / 2], uint32_t (&dw)[B / 2],
                                           uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t k4, uint32_t k1,
                                           uint32_t k64k, const char *gtab, const uint32_t *&lptr, const uint32_t *&sptr,
-                                          int n_iter, uint32_t *&out)
+                                          int n_iter, uint32_t *&out, uint32_t lane_off, int lane, bool phase)
 {
-    constexpr int H = B / 2, Q = H / 2, CH = pack16_chunk(B);
+    constexpr int H = B / 2, Q = H / 2, CH = x_chunk_len(B);
+    constexpr bool HALF = CH < 8;               // the chunk is half a direction word: `phase` = second half
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
+        const bool first = HALF ? (r == 0 && !phase) : (r % 8 == 0);       // first iteration of a direction word
         const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
         const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);
 #pragma unroll
@@ -374,9 +394,14 @@ __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (
             const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
             R[m] = (mn & 0xfffcfffcu) | penc[m];
             const uint32_t c2 = mn & 0x00030003u;
-            dw[m] = (r % 8 == 0) ? c2 : m_imad(dw[m], k4, c2);
+            if (HALF && r == 0) dw[m] = m_imad(first ? 0u : dw[m], k4, c2);
+            else dw[m] = first ? c2 : m_imad(dw[m], k4, c2);
         }
-        sw[tt] = sptr[r];
+        {       // sliding windows by shuffle (see x_chunk)
+            uint32_t nv = __shfl_down_sync(kFull, sw[tt], 1) - (lane_off ? 4u : 0u);
+            if (lane == 31) nv = sptr[r] + lane_off;
+            sw[tt] = nv;
+        }
         const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
         const uint32_t upl = __funnelshift_r(R[0], next, 16);
 #pragma unroll
@@ -392,10 +417,21 @@ __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (
             const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
             R[m] = (mn & 0xfffcfffcu) | penc[m];
             const uint32_t c2 = mn & 0x00030003u;
-            dw[m] = (r % 8 == 0) ? c2 : m_imad(dw[m], k4, c2);
+            if (HALF && r == 0) dw[m] = m_imad(first ? 0u : dw[m], k4, c2);
+            else dw[m] = first ? c2 : m_imad(dw[m], k4, c2);
         }
-        lw[(tt + 1) % H] = lptr[r];
-        if (r % 8 == 7) {
+        {
+            uint32_t nl = __shfl_up_sync(kFull, lw[(tt + 1) % H], 1);
+            if (lane == 0) nl = lptr[r];
+            lw[(tt + 1) % H] = nl;
+        }
+        if (HALF) {
+            const int done = (phase ? 4 : 0) + r + 1;                  // iterations of the current direction word so far
+            if (TAIL ? (r == n_iter - 1) : (r == CH - 1 && phase)) {
+                store_words16<H>(out, dw, done);
+                out += 32 * H;
+            }
+        } else if (r % 8 == 7) {
             store_words16<H>(out, dw, 8);
             out += 32 * H;
         } else if (TAIL && r == n_iter - 1) {
@@ -412,7 +448,7 @@ __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (
 template <int B, bool GLOBAL>
 __device__ __noinline__ uint32_t x_fill16(const MGeom g, uint32_t k4, uint32_t k1, uint32_t k64k, const char *gtab,
                                           const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot, int lane,
-                                          uint32_t spread_limit)
+                                          uint32_t spread_limit, uint32_t lane_off)
 {
     constexpr int H = B / 2;
     uint32_t R[H], penc[H], dw[H], lw[H], sw[H];
@@ -437,21 +473,24 @@ __device__ __noinline__ uint32_t x_fill16(const MGeom g, uint32_t k4, uint32_t k
 #pragma unroll
     for (int u = 0; u < H; ++u) {
         lw[(H - u) % H] = Lb[I0 - u];
-        sw[u] = Sb[J0 + u];
+        sw[u] = Sb[J0 + u] + lane_off;
     }
     const uint32_t *lptr = Lb + (I0 + 1), *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
-    constexpr int CH = pack16_chunk(B), RB = 32 / CH;
+    constexpr int CH = x_chunk_len(B), RB = 32 / CH;
     const int nfull = g.T / CH, rem = g.T % CH;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
         if (c && c % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, CH, out);
+        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, CH, out, lane_off, lane, (c & 1) != 0);
     }
     if (rem) {
         if (nfull && nfull % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        x_chunk16<B, GLOBAL, true>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, rem, out);
+        x_chunk16<B, GLOBAL, true>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, rem, out, lane_off, lane, (nfull & 1) != 0);
+    } else if (CH < 8 && (nfull & 1)) {
+        // the last direction word holds 4 iterations only: flush it
+        store_words16<H>(out, dw, 4);
     }
     ok = rebase16<H>(R, total_shift, spread_limit) && ok;
     if (!ok) return kOverflow16;
@@ -470,13 +509,13 @@ __device__ __noinline__ uint32_t x_fill16(const MGeom g, uint32_t k4, uint32_t k
 template <bool GLOBAL>
 __device__ __forceinline__ uint32_t x_dispatch16(int B, const MGeom &g, uint32_t k4, uint32_t k1, uint32_t k64k,
                                                  const char *gtab, const uint32_t *Lb, const uint32_t *Sb, uint32_t *slot,
-                                                 int lane, uint32_t spread)
+                                                 int lane, uint32_t spread, uint32_t lane_off)
 {
     switch (B) {
-        case 4:  return x_fill16<4, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
-        case 8:  return x_fill16<8, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
-        case 16: return x_fill16<16, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
-        default: return x_fill16<32, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread);
+        case 4:  return x_fill16<4, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread, lane_off);
+        case 8:  return x_fill16<8, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread, lane_off);
+        case 16: return x_fill16<16, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread, lane_off);
+        default: return x_fill16<32, GLOBAL>(g, k4, k1, k64k, gtab, Lb, Sb, slot, lane, spread, lane_off);
     }
 }
 
@@ -682,7 +721,7 @@ __device__ __forceinline__ uint32_t x_number(const uint32_t *str, int len, uint3
 // pointers (the body holds the whole schedule's state at 128 registers) — 10 % of the config-4 stall samples.
 __device__ __noinline__ uint32_t x_stage(uint32_t *Lr, uint32_t *Sr, int sizeL, int offL, int sizeS, int offS, int lg, int sh,
                                          const uint32_t *idxL, const uint32_t *idxS, const uint32_t *cL, const uint32_t *gS,
-                                         uint32_t rowb, uint32_t sbase, int lane)
+                                         uint32_t rowb, uint32_t sbase, int lane, bool repl)
 {
     uint32_t csum = 0;
     for (int idx = lane; idx < sizeL; idx += 32) {
@@ -697,12 +736,138 @@ __device__ __noinline__ uint32_t x_stage(uint32_t *Lr, uint32_t *Sr, int sizeL, 
         uint32_t d = 0;
         if (j == 0) d = 1;
         else if (j > 0 && j < sh) { d = idxS[j - 1]; csum += gS[d]; }
-        Sr[idx] = d * 2u + sbase;
+        // plain table: 2 bytes per column; replicated table (copy k in bank k): entry e at (e >> 1) * 128 + (e & 1) * 2
+        Sr[idx] = (repl ? (((d >> 1) << 7) | ((d & 1u) << 1)) : d * 2u) + sbase;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFullM, csum, d);
     __syncwarp();
     return csum;
+}
+
+// ------------------------------------------------------------------------------------------------ batch dictionary
+__device__ __forceinline__ uint32_t ov_any(int kind, const uint32_t *sg, int a, uint32_t x, uint32_t y, uint32_t &med)
+{
+    uint32_t c;
+    if (kind == 0) { const uint32_t t = x & y; med = t ? t : (x | y); c = t ? 0u : 1u; }
+    else if (kind == 1) ov_l1(a, x, y, med, c);
+    else ov_explicit(sg, a, x, y, med, c);
+    return c;
+}
+
+// Pass 1: every element of every string of the batch goes into a 64-slot global hash, through a per-CTA cache so that
+// the global table sees each CTA's distinct elements once.  More than kDictMax distinct elements: overflow, the batch
+// takes the per-pair path.
+__global__ void __launch_bounds__(256) dict_scan_kernel(const MetricBatchDev b, uint32_t mask, DictDev *d)
+{
+    __shared__ uint32_t seen[256];
+    __shared__ int s_stop;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) seen[i] = 0;
+    if (threadIdx.x == 0) s_stop = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = warp; k < b.n_pairs; k += nw) {
+        if (*reinterpret_cast<volatile int *>(&s_stop) || *reinterpret_cast<volatile uint32_t *>(&d->overflow)) break;
+        const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+        const uint32_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+        for (uint32_t t = lane; t < n1 + n2; t += 32) {
+            const uint32_t e = __ldg(t < n1 ? p1 + t : p2 + (t - n1)) & mask;
+            if (!e) continue;
+            uint32_t h = x_hash(e) & 255u, tries = 0;
+            bool fresh = false;
+            for (; tries < 256u; ++tries) {
+                uint32_t old = seen[h];
+                if (old == e) break;
+                if (old == 0u) {
+                    old = atomicCAS(&seen[h], 0u, e);
+                    if (old == 0u) { fresh = true; break; }
+                    if (old == e) break;
+                }
+                h = (h + 1u) & 255u;
+            }
+            if (tries >= 200u) { s_stop = 1; d->overflow = 1u; break; }
+            if (!fresh) continue;
+            uint32_t g = x_hash(e) & 63u;
+            for (uint32_t tr = 0; tr < 64u; ++tr) {
+                const uint32_t old = atomicCAS(&d->keys[g], 0u, e);
+                if (old == e) break;
+                if (old == 0u) {
+                    if (atomicAdd(&d->count, 1u) >= (uint32_t)kDictMax) d->overflow = 1u;
+                    break;
+                }
+                g = (g + 1u) & 63u;
+                if (tr == 63u) d->overflow = 1u;
+            }
+        }
+    }
+}
+
+// Pass 2 (one CTA): number the elements, indel costs, the 32 x 32 table in the folded form the fills consume.
+__global__ void __launch_bounds__(1024) dict_build_kernel(DictDev *d, int kind, const uint32_t *sigma, int a, int dialect)
+{
+    __shared__ uint32_t s_el[32], s_cL[32], s_gS[32];
+    __shared__ uint32_t s_D;
+    __shared__ int s_min, s_max, s_bad, s_gapmed;
+    const uint32_t gap = 1u << ((a - 1) & 31);
+    if (threadIdx.x == 0) {
+        uint32_t r = 0;
+        for (int sl = 0; sl < 64; ++sl) {
+            const uint32_t key = d->keys[sl];
+            if (key && r < (uint32_t)kDictMax) { d->vals[sl] = 2u + r; s_el[2u + r] = key; ++r; }
+        }
+        s_el[0] = 0; s_el[1] = gap;
+        s_D = r;
+        s_min = -1; s_max = -1; s_bad = 0; s_gapmed = 0;
+    }
+    __syncthreads();
+    const uint32_t D = s_D;
+    if (threadIdx.x < 32) {
+        const uint32_t dd = threadIdx.x;
+        uint32_t md, c1 = 0, c2 = 0;
+        if (dd >= 2u && dd < D + 2u) {
+            c1 = ov_any(kind, sigma, a, s_el[dd], gap, md);         // x from the longer string against the gap
+            c2 = ov_any(kind, sigma, a, gap, s_el[dd], md);
+        }
+        s_cL[dd] = c1; s_gS[dd] = c2;
+        d->cL[dd] = c1; d->gS[dd] = c2;
+        d->el[dd] = dd < D + 2u ? s_el[dd] : 0u;
+    }
+    __syncthreads();
+    {
+        const uint32_t dl = threadIdx.x >> 5, ds = threadIdx.x & 31u;
+        int v;
+        if (dl == 0u || ds == 0u || dl >= D + 2u || ds >= D + 2u) v = kBigSub;
+        else if (dl == 1u || ds == 1u) v = -1;
+        else {
+            uint32_t md;
+            const long long c = ov_any(kind, sigma, a, s_el[dl], s_el[ds], md);
+            const long long f = 4ll * (c - (long long)s_cL[dl] - (long long)s_gS[ds]) - 1ll;
+            if (md == gap) s_gapmed = 1;
+            if (f < -32000ll || f >= (long long)kBigSub) s_bad = 1;
+            v = (int)f;
+            atomicMin(&s_min, v); atomicMax(&s_max, v);
+        }
+        d->tab[threadIdx.x] = (int16_t)v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        d->emin = s_min; d->emax = s_max;
+        d->has_gap_median = (uint32_t)s_gapmed;
+        // S2 relabels cells whose median is exactly the gap (+1 on the entry): rare, and per pair (only pairs that do
+        // run the banded S2 schedule): such batches keep the per-pair tables
+        d->ok = (!d->overflow && !s_bad && D >= 1u && !(s_gapmed && dialect == 2)) ? 1u : 0u;
+    }
+}
+
+cudaError_t launch_dict(const ExplicitParams &p, DictDev *dict, int grid, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(dict, 0, sizeof(DictDev), stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t mask = p.a >= 32 ? 0xffffffffu : ((1u << p.a) - 1u);
+    dict_scan_kernel<<<grid * 4, 256, 0, stream>>>(p.b, mask, dict);
+    dict_build_kernel<<<1, 1024, 0, stream>>>(dict, p.kind, p.sigma, p.a, p.dialect);
+    return cudaGetLastError();
 }
 
 extern __shared__ __align__(16) char x_smem[];
@@ -720,7 +885,11 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     uint32_t *gapw = reinterpret_cast<uint32_t *>(x_smem);
     const uint32_t sg_bytes = WIDE ? 64u : (((uint32_t)(a * a) * 4u + 15u) & ~15u);
     const uint32_t per_warp = 512u + p.seq_cap + 2u * p.smem_tab_entries;
-    uint32_t *s_meta = reinterpret_cast<uint32_t *>(x_smem + sg_bytes + (size_t)warp * per_warp);
+    // batch-dictionary mode: [replicated table 64 KB | hash keys[64] vals[64] | cL[32] gS[32]] in front of the warps' windows
+    const bool dict = !WIDE && p.dict != nullptr;
+    char *dbase = x_smem + sg_bytes;
+    uint32_t *d_keys = reinterpret_cast<uint32_t *>(dbase + 65536), *d_vals = d_keys + 64, *d_cL = d_vals + 64, *d_gS = d_cL + 32;
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(x_smem + sg_bytes + (dict ? kDictSmemBytes : 0u) + (size_t)warp * per_warp);
     uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64, *s_geo = s_meta + 96;
     uint32_t *seq = s_meta + 128;
     int16_t *stab = reinterpret_cast<int16_t *>(reinterpret_cast<char *>(seq) + p.seq_cap);
@@ -729,7 +898,17 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     } else if (p.kind == 2) {
         for (int i = threadIdx.x; i < a * a; i += blockDim.x) sg[i] = p.sigma[i];
     }
+    if (dict) {
+        // 32 copies of the 32 x 32 table, copy k wholly in bank k: word (e >> 1) * 32 + k holds entries e, e + 1
+        uint32_t *rt = reinterpret_cast<uint32_t *>(dbase);
+        const uint32_t *nat = reinterpret_cast<const uint32_t *>(p.dict->tab);
+        for (uint32_t wi = threadIdx.x; wi < 512u * 32u; wi += blockDim.x) rt[wi] = __ldg(nat + (wi >> 5));
+        for (uint32_t i = threadIdx.x; i < 64u; i += blockDim.x) { d_keys[i] = p.dict->keys[i]; d_vals[i] = p.dict->vals[i]; }
+        for (uint32_t i = threadIdx.x; i < 32u; i += blockDim.x) { d_cL[i] = p.dict->cL[i]; d_gS[i] = p.dict->gS[i]; }
+    }
     __syncthreads();
+    const uint32_t rtab32 = (uint32_t)__cvta_generic_to_shared(dbase);
+    const uint32_t lane_off = dict ? 4u * (uint32_t)lane : 0u;
 
     const uint32_t gap = WIDE ? 0u : 1u << ((a - 1) & 31);                      // narrow only
     const uint32_t mask = (WIDE || a >= 32) ? 0xffffffffu : ((1u << a) - 1u);
@@ -804,15 +983,37 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                 const uint32_t HL = x_hash_size((uint32_t)n), HS = x_hash_size((uint32_t)m);
                 uint32_t *hkL = ts, *hvL = hkL + HL, *hkS = hvL + HL, *hvS = hkS + HS;
                 uint32_t *elL = hvS + HS, *elS = elL + n, *idxL = elS + m, *idxS = idxL + n;
-                uint32_t *cL = idxS + m, *gS = cL + (n + 2);
-                uint32_t *mxL = gS + (m + 2), *mxS = mxL + (size_t)n * a;
+                const uint32_t *cL = idxS + m, *gS = cL + (n + 2);
+                uint32_t *cLw = idxS + m, *gSw = cLw + (n + 2);
+                uint32_t *mxL = gSw + (m + 2), *mxS = mxL + (size_t)n * a;
                 uint32_t *tail = mxS + (size_t)m * a;
                 bool ok = (size_t)(tail - ts) <= p.tscratch_words;
                 uint32_t DL = 0, DS = 0, Wt = 0, entries = 0;
                 bool gtable = false;
                 const char *gtab = nullptr;
                 uint32_t tab32 = 0;
-                if (ok) {
+                uint32_t bad = 0;
+                int emin = -1, emax = -1;                   // range of the finite table entries (leading gap: -1)
+                if (ok && dict) {
+                    // table indices straight from the batch dictionary; no per-pair numbering, profiles or table
+                    uint32_t miss = 0;
+                    for (int t = lane; t < n + m; t += 32) {
+                        const uint32_t e = __ldg(t < n ? pL + t : pS + (t - n)) & mask;
+                        uint32_t v = 0;
+                        if (e) {
+                            uint32_t h = x_hash(e) & 63u, tries = 0;
+                            while (d_keys[h] != e && tries < 64u) { h = (h + 1u) & 63u; ++tries; }
+                            if (tries == 64u) miss = 1; else v = d_vals[h];
+                        }
+                        (t < n ? idxL : idxS)[t < n ? t : t - n] = v;
+                    }
+                    if (__any_sync(kFullM, miss != 0u)) ok = false;       // (cannot happen: the scan covered this batch)
+                    cL = d_cL; gS = d_gS;
+                    emin = p.dict->emin; emax = p.dict->emax;
+                    tab32 = rtab32;
+                    Wt = 1024u;                              // row stride of the replicated table: 2048 bytes
+                    __syncwarp();
+                } else if (ok) {
                     if constexpr (WIDE) {
                         DL = x_number_w(pL, n, W, HL, hkL, hvL, elL, idxL, lane);
                         DS = x_number_w(pS, m, W, HS, hkS, hvS, elS, idxS, lane);
@@ -825,9 +1026,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     gtable = entries > p.smem_tab_entries;
                     if (gtable) ok = (size_t)(tail - ts) + (entries + 1u) / 2u <= p.tscratch_words && Wt * 2u * (DL + 2u) < 0x7fffffffu;
                 }
-                uint32_t bad = 0;
-                int emin = -1, emax = -1;                   // range of the finite table entries (leading gap: -1)
-                if (ok && p.kind != 2) {
+                if (ok && !dict && p.kind != 2) {
                     // closed forms — discrete metric (Data/MetricRepresentation.hs:116-128): cost(x, y) = x & y ? 0 : 1;
                     // L1 norm (:166-190): interval logic — no profiles.  An element is elL[d] (narrow) or the string
                     // element at position elL[d] (wide).
@@ -850,8 +1049,8 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                         }
                     };
                     bool ig;
-                    for (uint32_t d = lane; d < DL + 2u; d += 32) cL[d] = d >= 2u ? ovc(d, 1u, ig) : 0u;
-                    for (uint32_t d = lane; d < DS + 2u; d += 32) gS[d] = d >= 2u ? ovc(1u, d, ig) : 0u;
+                    for (uint32_t d = lane; d < DL + 2u; d += 32) cLw[d] = d >= 2u ? ovc(d, 1u, ig) : 0u;
+                    for (uint32_t d = lane; d < DS + 2u; d += 32) gSw[d] = d >= 2u ? ovc(1u, d, ig) : 0u;
                     __syncwarp();
                     int16_t *tab = gtable ? reinterpret_cast<int16_t *>(tail) : stab;
                     for (uint32_t t = lane; t < entries; t += 32) {
@@ -874,7 +1073,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     gtab = reinterpret_cast<const char *>(tail);
                     tab32 = (uint32_t)__cvta_generic_to_shared(stab);
                     __syncwarp();
-                } else if (ok) {
+                } else if (ok && !dict) {
                     for (uint32_t t = lane; t < DL * (uint32_t)a; t += 32) {
                         const uint32_t d = t / a, s = t - d * a;
                         uint32_t mn = 0xffffffffu;
@@ -896,7 +1095,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                             c = 0xffffffffu;
                             for (int s = 0; s < a; ++s) c = min(c, mxL[(d - 2u) * a + s] + sg[s * a + a - 1]);
                         }
-                        cL[d] = c;
+                        cLw[d] = c;
                     }
                     for (uint32_t d = lane; d < DS + 2u; d += 32) {
                         uint32_t c = 0;
@@ -904,7 +1103,7 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                             c = 0xffffffffu;
                             for (int s = 0; s < a; ++s) c = min(c, mxS[(d - 2u) * a + s] + sg[s * a + a - 1]);
                         }
-                        gS[d] = c;
+                        gSw[d] = c;
                     }
                     __syncwarp();
                     int16_t *tab = gtable ? reinterpret_cast<int16_t *>(tail) : stab;
@@ -972,17 +1171,17 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
                     // stage row offsets (bytes into the table) and column offsets (+ the table's shared address)
                     uint32_t *Sr = seq, *Lr = seq + sl.sizeS;
                     csum = x_stage(Lr, Sr, sl.sizeL, sl.offL, sl.sizeS, sl.offS, lg, sh, idxL, idxS, cL, gS, Wt * 2u,
-                                   gtable ? 0u : tab32, lane);
+                                   gtable ? 0u : tab32, lane, dict);
                     uint32_t *slot = arena + cur;
                     used16 = packed && B >= 4;
                     if (used16) {
-                        if (gtable) fw = x_dispatch16<true>(B, g, p.k_four, p.k_one, p.k_64k, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, (uint32_t)spread16);
-                        else        fw = x_dispatch16<false>(B, g, p.k_four, p.k_one, p.k_64k, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, (uint32_t)spread16);
+                        if (gtable) fw = x_dispatch16<true>(B, g, p.k_four, p.k_one, p.k_64k, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, (uint32_t)spread16, 0u);
+                        else        fw = x_dispatch16<false>(B, g, p.k_four, p.k_one, p.k_64k, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, (uint32_t)spread16, lane_off);
                         if (fw == kOverflow16) { used16 = false; packed = false; }       // redo this and later fills in 32 bits
                     }
                     if (!used16) {
-                        if (gtable) fw = x_dispatch<true>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
-                        else        fw = x_dispatch<false>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane);
+                        if (gtable) fw = x_dispatch<true>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, 0u);
+                        else        fw = x_dispatch<false>(B, g, p.k_four, p.k_minus1, p.k_one, gtab, Lr + sl.offL, Sr + sl.offS, slot, lane, lane_off);
                     }
                     __syncwarp();
                     if (full) break;
@@ -1109,15 +1308,6 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
 // PCG's dispatch path (selectDynamicMetric never picks it); kept for the reference's own cross-implementation checks, so
 // this kernel is plain: one warp per pair, lanes across an anti-diagonal, the overlap evaluated per cell (no memo table),
 // values and one direction byte per cell in the warp's global scratch, traceback and medians by lane 0.
-__device__ __forceinline__ uint32_t ov_any(int kind, const uint32_t *sg, int a, uint32_t x, uint32_t y, uint32_t &med)
-{
-    uint32_t c;
-    if (kind == 0) { const uint32_t t = x & y; med = t ? t : (x | y); c = t ? 0u : 1u; }
-    else if (kind == 1) ov_l1(a, x, y, med, c);
-    else ov_explicit(sg, a, x, y, med, c);
-    return c;
-}
-
 __global__ void __launch_bounds__(256) do_fullmatrix_kernel(const ExplicitParams p)
 {
     const MetricBatchDev &b = p.b;

@@ -168,3 +168,63 @@ def test_unboxed_full_matrix_dialect(oracle_mod, gpu_ctx, a, kind):
             assert np.array_equal(x, y), (k, len(s1), len(s2))
         differs += oc[0] != oracle_mod.haskell_do(0, a, s1, s2, sigma=sg, metric_kind={"discrete": 0, "explicit": 1, "l1": 2}[kind])[0]
     assert int(r.cells[0]) == (len(pairs[0][0]) + 1) * (len(pairs[0][1]) + 1)
+
+
+@pytest.mark.parametrize("a,kind,amb", [(21, "discrete", 0.0), (21, "pref-gap", 0.0), (21, "random-asym", 0.0), (12, "l1", 0.0),
+                                        (4, "discrete", 0.5), (4, "random-sym", 0.5), (21, "pref-sub", 0.02)])
+def test_batch_dictionary_equals_per_pair_tables(oracle_mod, gpu_ctx, monkeypatch, a, kind, amb):
+    """When a whole batch draws its elements from at most 30 distinct ambiguity sets, one table over them — replicated
+    per shared-memory bank, conflict-free — replaces the per-pair memo tables (DictDev).  Same costs, offsets, cells and
+    alignments as the per-pair path (PCGDO_NO_DICT=1), every dialect; a = 4 with ambiguous elements brings gap-containing
+    sets and medians that are exactly the gap (dialect 2 then keeps the per-pair tables), 2 % ambiguity over 21 symbols
+    overflows the dictionary (more than 30 sets)."""
+    from pcg_b200.pairwise import metric_do_batch
+    rng = np.random.default_rng(7 * a + len(kind))
+
+    def rstr(n):
+        x = (1 << rng.integers(0, a - 1, size=n)).astype(np.uint32)
+        if amb:
+            m = rng.random(n) < amb
+            x = np.where(m, rng.integers(1, 1 << a, size=n), x).astype(np.uint32)
+        return x
+    pairs = []
+    for _ in range(200):
+        n1 = int(rng.integers(1, 200))
+        s1 = rstr(n1)
+        r = rng.random()
+        if r < 0.4:
+            s2 = s1.copy()
+            mut = rng.random(n1) < 0.1
+            s2 = np.where(mut, rstr(n1), s2).astype(np.uint32)[rng.random(n1) > 0.05]
+            if len(s2) == 0:
+                s2 = s1[:1].copy()
+        else:
+            s2 = rstr(int(rng.integers(1, 200)))
+        pairs.append((s1, s2) if rng.random() < 0.5 else (s2, s1))
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=256, max_b=32, arena_words=0)
+    if kind == "discrete":
+        alpha = a
+    elif kind == "l1":
+        idx = np.arange(a)
+        alpha = gpu_ctx.memo(np.abs(np.subtract.outer(idx, idx)).astype(np.uint32), structure="l1")
+    else:
+        alpha = gpu_ctx.memo(_sigma(kind, a, rng))
+    f, s = [p[0] for p in pairs], [p[1] for p in pairs]
+    for dialect in (0, 1, 2):
+        r = metric_do_batch(gpu_ctx, alpha, dialect, f, s)
+        monkeypatch.setenv("PCGDO_NO_DICT", "1")
+        gpu_ctx.reload_env()
+        ref = metric_do_batch(gpu_ctx, alpha, dialect, f, s)
+        monkeypatch.delenv("PCGDO_NO_DICT")
+        gpu_ctx.reload_env()
+        assert np.array_equal(r.cost, ref.cost) and np.array_equal(r.final_offset, ref.final_offset), dialect
+        assert np.array_equal(r.cells, ref.cells) and np.array_equal(r.out_len, ref.out_len), dialect
+        for k in range(len(pairs)):
+            for x, y in zip(r.pair(k)[1:], ref.pair(k)[1:]):
+                assert np.array_equal(x, y), (dialect, k)
+        if kind in ("discrete", "pref-gap") and a == 21:       # and against the restatement itself
+            sig = None if kind == "discrete" else _sigma(kind, a, rng)
+            for k in range(0, len(pairs), 9):
+                oc = oracle_mod.haskell_do(dialect, a, pairs[k][0], pairs[k][1], sigma=sig)
+                gc = r.pair(k)
+                assert gc[0] == oc[0] and all(np.array_equal(x, y) for x, y in zip(gc[1:], oc[1:4])), (dialect, k)
