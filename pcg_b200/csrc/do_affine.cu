@@ -86,6 +86,7 @@ struct AffParams {
     unsigned int *class_count;     // [6] pairs per band class (filled by aff_classify_kernel)
     unsigned int *class_take;      // [6] hand-out counters
     uint32_t     *big_list;        // [6][n_pairs] pair indices per class
+    uint32_t      k_one;           // 1, opaque to the compiler (keeps additions on the FMA pipe as IMAD)
 };
 
 // column entry: .x = gr (cost[gap][l_j]); .y = l'_j | lgap << 8 | go_is_open << 9 | he_has_open << 10
@@ -295,17 +296,18 @@ constexpr uint32_t kInf4 = 1u << 29;          // "very large" x 4
 constexpr uint32_t kCap4 = 1u << 30;          // clamp for sums of very large values
 
 // parameter entries (global scratch, 16 bytes each), decoded into the windows below
-//   row i   : .x = 4*ve, .y = 4*(so + ge), .z = 4*so, .w = table row offset (bytes) | sgap << 31
-//   column j: .x = 4*he, .y = 4*(go + gr), .z = 4*go, .w = table column offset (bytes) | lgap << 31
+//   row i   : .x = 4*ve + 1, .y = 4*(so + ge), .z = 4*so, .w = table row offset (bytes) | sgap << 31
+//   column j: .x = 4*he + 1, .y = 4*(go + gr), .z = 4*go, .w = table column offset (bytes) | lgap << 31
+//   (the + 1 marks "the run continues" in the candidate that extends it, see aff_cell)
 template <int H>
 struct AffWin { uint32_t a[H], b[H], c[H], m[H], o[H]; };
 
 template <int H>
-__device__ __forceinline__ void aff_win_load(AffWin<H> &w, int slot, const uint4 v)
+__device__ __forceinline__ void aff_win_load(AffWin<H> &w, int slot, const uint4 v, uint32_t obase)
 {
     w.a[slot] = v.x; w.b[slot] = v.y; w.c[slot] = v.z;
-    w.m[slot] = (uint32_t)((int32_t)v.w >> 31);
-    w.o[slot] = v.w & 0x7fffffffu;
+    w.m[slot] = (uint32_t)((int32_t)v.w >> 31) & 0xfffffffcu;      // all-ones above the two tag bits, or zero
+    w.o[slot] = (v.w & 0x7fffffffu) + obase;                       // rows carry the table's shared address
 }
 
 template <int H, int S>
@@ -330,46 +332,73 @@ __device__ __forceinline__ uint32_t aff_lds32(uint32_t saddr)
     return v;
 }
 
+// iterations unrolled per chunk of the wavefront fill (see aff_wave_chunk)
+__host__ __device__ constexpr int aff_wave_chunk_len(int B) { return B >= 12 ? 2 : 4; }
+
+// a * k + c on the FMA pipe (k is a run-time 1 or 4..64 the compiler cannot fold): the cell update is otherwise all
+// add / min / logic, i.e. all ALU pipe, which ncu showed saturated (73 % busy, math-pipe throttle the top stall) while
+// the FMA pipe idled at 10 %.  Every plain addition of the cell therefore goes through IMAD.
+__device__ __forceinline__ uint32_t aff_imad(uint32_t a, uint32_t k, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(k), "r"(c));
+    return d;
+}
+
 // One cell.  rs / cs: window slots of its row and column.  Returns the flag byte.
+// Plane values are multiples of 4; every two-way decision is taken by ONE min over candidates that carry the decision
+// in their low bits (the staged parameters ve and he arrive with +1 baked in: "this candidate extends the run"):
+//   ev  = min(uEV + ve + 1, uCB + so + ge)      bit 0 set  <=> the vertical run continues   (endv = !bit0)
+//   eh  = min(lEH + he + 1, lCB + go + gr)      bit 0 set  <=> the horizontal run continues (endh = !bit0)
+//   eb  = min(EB + 1, CB)                       bit 0 set  <=> the diagonal run continues   (endb = !bit0)
+//   cb  = min(fh, fd | 1, fv | 2, ca | 3)       low two bits = next mode out of an align step (H > D > V > stay)
+//   fc  = min(eh, cb | 1, ev | 2, eb | 3)       low two bits = plane that ends here         (H > A > V > D)
+// ties resolve exactly as the reference's strict comparisons do: the candidate with the smaller tag wins.
 template <int H, bool EARLY>
 __device__ __forceinline__ uint32_t aff_cell(uint32_t &CB, uint32_t &EB, uint32_t &EV, uint32_t &EH, uint32_t uEV,
                                              uint32_t uCB, uint32_t lEH, uint32_t lCB, uint32_t penup,
-                                             const AffWin<H> &rw, int rs, const AffWin<H> &cw, int cs, uint32_t tab,
+                                             const AffWin<H> &rw, int rs, const AffWin<H> &cw, int cs, uint32_t k1,
                                              bool border, int i, int j)
 {
-    const uint32_t ve = rw.a[rs], voa = rw.b[rs], so = rw.c[rs], sgM = rw.m[rs];
-    const uint32_t he = cw.a[cs], hoa = cw.b[cs], go = cw.c[cs], lgM = cw.m[cs];
+    const uint32_t ve1 = rw.a[rs], voa = rw.b[rs], so = rw.c[rs], sgM = rw.m[rs];
+    const uint32_t he1 = cw.a[cs], hoa = cw.b[cs], go = cw.c[cs], lgM = cw.m[cs];
     const uint32_t pen = (EARLY && i == 1) ? 0u : penup;      // row 1 still sees the real row-0 cell above the band
-    uEV |= pen;
-    uCB |= pen;
-    // extend vertical
-    const uint32_t vx = uEV + ve, vo = uCB + voa;
-    uint32_t ev = min(vx, vo);
-    uint32_t endv = !(vx < vo);
-    // extend block diagonal
+    // extend vertical: the cell above the last in-band diagonal is "very large" (pen)
+    const uint32_t t = aff_imad(uEV, k1, ve1);
+    uint32_t evm = max(__viaddmin_u32(uCB, voa, t), pen);
+    uint32_t ev = evm & ~3u;
+    // extend block diagonal (both strings have a gap here)
     const uint32_t gm = sgM & lgM;
-    uint32_t eb = (min(EB, CB) & gm) | (kInf4 & ~gm);
-    const uint32_t endb = !(EB < CB);
+    const uint32_t ebm = __viaddmin_u32(EB, 1u, CB);
+    uint32_t eb = (ebm & gm) | (kInf4 & ~gm);
     // close block diagonal: candidates carry the next mode in their low bits
-    const uint32_t dg = aff_lds32(tab + rw.o[rs] + cw.o[cs]);
-    const uint32_t fh = EH + dg + (lgM & so);
-    const uint32_t fd = EB + dg + ((go | so) | 1u);
-    const uint32_t fv = EV + dg + ((sgM & go) | 2u);
+    const uint32_t dg = aff_lds32(aff_imad(rw.o[rs], k1, cw.o[cs]));
+    const uint32_t fh = aff_imad(lgM & so, k1, aff_imad(EH, k1, dg));
+    const uint32_t fd = aff_imad((go | so) | 1u, k1, aff_imad(EB, k1, dg));
+    const uint32_t fv = aff_imad((sgM & go) | 2u, k1, aff_imad(EV, k1, dg));
     const uint32_t ca = CB + dg + 3u;
-    const uint32_t cbm = min(min(fh, fd), min(fv, ca));
-    const uint32_t an = cbm & 3u;
+    const uint32_t cbm = min(__vimin3_u32(fh, fd, fv), ca);
     uint32_t cb = cbm & ~3u;
     // extend horizontal: the left neighbour of this half step
-    const uint32_t hx = lEH + he, ho = lCB + hoa;
-    uint32_t eh = min(hx, ho);
-    const uint32_t endh = !(hx < ho);
-    if (border) { ev = vx; cb = kInf4; eb = kInf4; endv = 1u; eh = kCap4; }   // vertical extension only
-    if (EARLY && j < 0) { ev = kInf4; cb = kInf4; eb = kInf4; eh = kCap4; }
+    uint32_t ehm = __viaddmin_u32(lCB, hoa, aff_imad(lEH, k1, he1));
+    uint32_t eh = ehm & ~3u;
+    // (overridden cells: their markers are made to read "run ends here", evm = ev and ehm = eh)
+    if (border) { ev = t & ~3u; evm = ev; cb = kInf4; eb = kInf4; eh = kCap4; ehm = eh; }     // d = -40 / column 0: vertical extension only
+    if (EARLY && j < 0) { ev = kInf4; evm = ev; cb = kInf4; eb = kInf4; eh = kCap4; ehm = eh; }
     // no clamping: every candidate is ONE plane value plus a small term, so "very large" values only drift by
     // 4 * (a few costs) per step — they never wrap and never come near a finite value (checked on the host)
-    // which plane ends here
-    const uint32_t fcm = min(min(eh, cb | 1u), min(ev | 2u, eb | 3u));
-    const uint32_t fl = (fcm & 3u) | (an << 2) | (endv << 4) | (endh << 5) | (endb << 6);
+    // which plane ends here: the tags go on by addition (the values are clean multiples of 4), on the FMA pipe
+    const uint32_t fcm = min(__vimin3_u32(eh, aff_imad(cb, k1, 1u), aff_imad(ev, k1, 2u)), eb | 3u);
+    // flag byte td | an << 2 | endv << 4 | endh << 5 | endb << 6, end* = 1 - marker.  A marker is the difference between
+    // a decision value and its cleaned copy (evm - ev, ehm - eh, cbm - cb for `an`), so the byte is assembled by
+    // multiply-adds alone: 112 + td + 4 (cbm - cb) - 16 (evm - ev) - 32 (ehm - eh) - 64 (ebm & 1)
+    uint32_t fl = aff_imad(cbm, 4u * k1, (fcm & 3u) + 112u);
+    fl = aff_imad(cb, 0u - 4u * k1, fl);
+    fl = aff_imad(ev, 16u * k1, fl);
+    fl = aff_imad(evm, 0u - 16u * k1, fl);
+    fl = aff_imad(eh, 32u * k1, fl);
+    fl = aff_imad(ehm, 0u - 32u * k1, fl);
+    fl = aff_imad(ebm & 1u, 0u - 64u * k1, fl);
     if (!EARLY || i >= 1) { CB = cb; EB = eb; EV = ev; EH = eh; }             // rows <= 0: keep the row-0 value
     return fl;
 }
@@ -377,14 +406,19 @@ __device__ __forceinline__ uint32_t aff_cell(uint32_t &CB, uint32_t &EB, uint32_
 template <int B, bool EARLY, bool TAIL>
 __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)[B], uint32_t (&EV)[B], uint32_t (&EH)[B],
                                                const uint32_t (&penup)[B], uint32_t (&dw)[B], AffWin<B / 2> &rw,
-                                               AffWin<B / 2> &cw, uint32_t tab, const uint4 *&rptr, const uint4 *&cptr,
-                                               int n_iter, int i_even0, int j_even0, int lane, uint32_t *&out)
+                                               AffWin<B / 2> &cw, uint32_t tab, uint32_t k1, const uint4 *&rptr,
+                                               const uint4 *&cptr, int n_iter, int i_even0, int j_even0, int lane,
+                                               uint32_t *&out, int word_pos)
 {
-    constexpr int H = B / 2, CH = 4;       // 4 iterations unrolled: larger bodies fall out of the instruction cache
+    // iterations unrolled per chunk: the body must stay well inside the 32 KB instruction cache (ncu: 23 % of the wide
+    // kernel's stall samples were "no instruction" with 4 iterations of 16 diagonals = 51 KB)
+    constexpr int H = B / 2, CH = aff_wave_chunk_len(B);
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
+        // byte of the direction word this iteration fills: compile-time when a chunk is a whole word (CH = 4)
+        const uint32_t sh8 = (CH % 4 == 0) ? (1u << (8 * (r & 3))) : (1u << (8 * ((word_pos + r) & 3)));
         // ---- even diagonals (anti-diagonal 2t): m = 2u handles row i_even0 + r - u, column j_even0 + r + u
         const uint32_t lEH0 = __shfl_up_sync(kFullA, EH[B - 1], 1), lCB0 = __shfl_up_sync(kFullA, CB[B - 1], 1);
 #pragma unroll
@@ -395,10 +429,10 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
             const int i = i_even0 + r - u, j = j_even0 + r + u;
             const bool border = (u == 0 && lane == 0) || (EARLY && j == 0);     // d = -40 and column 0
             const uint32_t fl = aff_cell<H, EARLY>(CB[m], EB[m], EV[m], EH[m], EV[m + 1], CB[m + 1], lEH, lCB, penup[m],
-                                                   rw, (tt - u + 2 * H) % H, cw, (tt + u) % H, tab, border, i, j);
-            dw[m] = fl * (1u << (8 * (r & 3))) + dw[m];
+                                                   rw, (tt - u + 2 * H) % H, cw, (tt + u) % H, k1, border, i, j);
+            dw[m] = aff_imad(fl, sh8, dw[m]);
         }
-        aff_win_load<H>(cw, tt, __ldg(cptr + r));
+        aff_win_load<H>(cw, tt, __ldg(cptr + r), 0u);
         // ---- odd diagonals (anti-diagonal 2t + 1): m = 2u + 1 handles row i_even0 + r - u, column j_even0 + r + u + 1
         const uint32_t uEV0 = __shfl_down_sync(kFullA, EV[0], 1), uCB0 = __shfl_down_sync(kFullA, CB[0], 1);
 #pragma unroll
@@ -409,11 +443,11 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
             const int i = i_even0 + r - u, j = j_even0 + r + u + 1;
             const bool border = EARLY ? (j == 0) : false;
             const uint32_t fl = aff_cell<H, EARLY>(CB[m], EB[m], EV[m], EH[m], uEV, uCB, EH[m - 1], CB[m - 1], penup[m],
-                                                   rw, (tt - u + 2 * H) % H, cw, (tt + u + 1) % H, tab, border, i, j);
-            dw[m] = fl * (1u << (8 * (r & 3))) + dw[m];
+                                                   rw, (tt - u + 2 * H) % H, cw, (tt + u + 1) % H, k1, border, i, j);
+            dw[m] = aff_imad(fl, sh8, dw[m]);
         }
-        aff_win_load<H>(rw, (tt + 1) % H, __ldg(rptr + r));
-        if ((r & 3) == 3 || (TAIL && r == n_iter - 1)) {
+        aff_win_load<H>(rw, (tt + 1) % H, __ldg(rptr + r), tab);
+        if (((word_pos + r) & 3) == 3 || (TAIL && r == n_iter - 1)) {
             if constexpr (B % 4 == 0) {
 #pragma unroll
                 for (int m = 0; m < B; m += 4) *reinterpret_cast<uint4 *>(out + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
@@ -438,10 +472,10 @@ __device__ __forceinline__ void aff_wave_chunk(uint32_t (&CB)[B], uint32_t (&EB)
 
 // rowp / colp point at the entries of row 0 / column 0 (padded on both sides).  Returns 4 * FC at (S, L).
 template <int B>
-__device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uint32_t tab, const uint4 *rowp,
+__device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uint32_t tab, uint32_t k1, const uint4 *rowp,
                                                const uint4 *colp, const uint32_t *row0, uint32_t *dirw, int lane)
 {
-    constexpr int H = B / 2, CH = 4;
+    constexpr int H = B / 2, CH = aff_wave_chunk_len(B);
     uint32_t CB[B], EB[B], EV[B], EH[B], penup[B], dw[B];
     AffWin<H> rw, cw;
     const int qE = g.E0 - kDB;
@@ -458,8 +492,8 @@ __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uin
     const int I0 = 20 - lane * H, J0 = -20 + lane * H;
 #pragma unroll
     for (int u = 0; u < H; ++u) {
-        aff_win_load<H>(rw, (H - u) % H, __ldg(rowp + (I0 - u)));
-        aff_win_load<H>(cw, u, __ldg(colp + (J0 + u)));
+        aff_win_load<H>(rw, (H - u) % H, __ldg(rowp + (I0 - u)), tab);
+        aff_win_load<H>(cw, u, __ldg(colp + (J0 + u)), 0u);
     }
     const uint4 *rptr = rowp + (I0 + 1), *cptr = colp + (J0 + H);
     uint32_t *out = dirw + lane * B;
@@ -469,11 +503,21 @@ __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uin
     T0 = (T0 + CH - 1) / CH * CH;
     int t = 0;
     for (; t + CH <= T0 && t + CH <= T; t += CH)
-        aff_wave_chunk<B, true, false>(CB, EB, EV, EH, penup, dw, rw, cw, tab, rptr, cptr, CH, I0 + t, J0 + t, lane, out);
+        aff_wave_chunk<B, true, false>(CB, EB, EV, EH, penup, dw, rw, cw, tab, k1, rptr, cptr, CH, I0 + t, J0 + t, lane, out, t & 3);
     for (; t + CH <= T; t += CH)
-        aff_wave_chunk<B, false, false>(CB, EB, EV, EH, penup, dw, rw, cw, tab, rptr, cptr, CH, I0 + t, J0 + t, lane, out);
-    if (t < T)      // the last cell must stay in its register: stop exactly after iteration T - 1
-        aff_wave_chunk<B, true, true>(CB, EB, EV, EH, penup, dw, rw, cw, tab, rptr, cptr, T - t, I0 + t, J0 + t, lane, out);
+        aff_wave_chunk<B, false, false>(CB, EB, EV, EH, penup, dw, rw, cw, tab, k1, rptr, cptr, CH, I0 + t, J0 + t, lane, out, t & 3);
+    if (t < T) {    // the last cell must stay in its register: stop exactly after iteration T - 1
+        aff_wave_chunk<B, true, true>(CB, EB, EV, EH, penup, dw, rw, cw, tab, k1, rptr, cptr, T - t, I0 + t, J0 + t, lane, out, t & 3);
+    } else if (CH % 4 != 0 && (T & 3) != 0) {
+        // chunks shorter than a direction word: the last word is only partly filled and has not been stored yet
+        if constexpr (B % 4 == 0) {
+#pragma unroll
+            for (int m = 0; m < B; m += 4) *reinterpret_cast<uint4 *>(out + m) = make_uint4(dw[m], dw[m + 1], dw[m + 2], dw[m + 3]);
+        } else {
+#pragma unroll
+            for (int m = 0; m < B; m += 2) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m], dw[m + 1]);
+        }
+    }
     const int q_last = (g.L - g.S) - kDB, lane_last = q_last / B, m_last = q_last % B;
     uint32_t v = 0;
 #pragma unroll
@@ -483,7 +527,6 @@ __device__ __noinline__ uint32_t aff_wave_fill(const AffGeom g, uint32_t GO, uin
 }
 
 // per-pair scratch of the wavefront fill (32-bit words): direction words | op stream | row params | column params | row 0
-__host__ __device__ inline int aff_wave_chunk_len(int) { return 4; }
 __host__ __device__ inline uint32_t aff_wave_iters(const AffGeom &g, int B)
 {
     const int ch = aff_wave_chunk_len(B);
@@ -612,7 +655,7 @@ __device__ __forceinline__ unsigned long long aff_band_cells(const AffGeom &ag)
 template <bool WIDE>
 __device__ __forceinline__ uint32_t aff_pair_wave(const TcmDev &tcm, const AffGeom &ag, int B, uint32_t GO, uint32_t tab_lane,
                                                   uint32_t ent_shift, const uint8_t *pL, const uint8_t *pS, uint32_t *slot,
-                                                  int lane)
+                                                  int lane, uint32_t k1)
 {
     const uint32_t g = tcm.gap;
     uint32_t *dirw = slot;
@@ -632,14 +675,14 @@ __device__ __forceinline__ uint32_t aff_pair_wave(const TcmDev &tcm, const AffGe
             gr = tcm.gapc[lj];
             const uint32_t go = !(!(g & lp) && (g & lj)) ? GO : 0u;
             const uint32_t he = gr + ((j > 1 && (lp & g) && !(lj & g)) ? go : 0u);
-            cv = make_uint4(4u * he, 4u * (go + gr), 4u * go, ((lj & (g - 1u)) << ent_shift) | ((lj & g) ? 0x80000000u : 0u));
+            cv = make_uint4(4u * he + 1u, 4u * (go + gr), 4u * go, ((lj & (g - 1u)) << ent_shift) | ((lj & g) ? 0x80000000u : 0u));
         }
         if (i >= 1 && i <= ag.S) {                                      // row parameters (:3614-3625)
             const uint32_t si = __ldg(pS + i - 1), sp = i == 1 ? g : __ldg(pS + i - 2);
             const uint32_t ge = tcm.cgap[si];
             const uint32_t so = !(!(g & sp) && (g & si)) ? GO : 0u;
             const uint32_t ve = (i > 1 && (sp & g) && !(si & g)) ? so + ge : ge;
-            rv = make_uint4(4u * ve, 4u * (so + ge), 4u * so,
+            rv = make_uint4(4u * ve + 1u, 4u * (so + ge), 4u * so,
                             (((si & (g - 1u)) << (tcm.a - 1)) << ent_shift) | ((si & g) ? 0x80000000u : 0u));
         }
         if (e < (int)npar) { colbase[e] = cv; rowbase[e] = rv; }
@@ -655,12 +698,12 @@ __device__ __forceinline__ uint32_t aff_pair_wave(const TcmDev &tcm, const AffGe
     __syncwarp();
     uint32_t fc4;
     if constexpr (WIDE) {
-        if (B == 12) fc4 = aff_wave_fill<12>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
-        else         fc4 = aff_wave_fill<16>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        if (B == 12) fc4 = aff_wave_fill<12>(ag, GO, tab_lane, k1, rowp, colp, row0, dirw, lane);
+        else         fc4 = aff_wave_fill<16>(ag, GO, tab_lane, k1, rowp, colp, row0, dirw, lane);
     } else {
-        if (B == 4)      fc4 = aff_wave_fill<4>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
-        else if (B == 6) fc4 = aff_wave_fill<6>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
-        else             fc4 = aff_wave_fill<8>(ag, GO, tab_lane, rowp, colp, row0, dirw, lane);
+        if (B == 4)      fc4 = aff_wave_fill<4>(ag, GO, tab_lane, k1, rowp, colp, row0, dirw, lane);
+        else if (B == 6) fc4 = aff_wave_fill<6>(ag, GO, tab_lane, k1, rowp, colp, row0, dirw, lane);
+        else             fc4 = aff_wave_fill<8>(ag, GO, tab_lane, k1, rowp, colp, row0, dirw, lane);
     }
     return fc4 >> 2;
 }
@@ -821,7 +864,7 @@ __global__ void __launch_bounds__(WIDE ? 256 : 512, 1) do_affine_kernel(const Af
             }
             if (cur + need > p.arena_words) break;
             uint32_t *slot = arena + cur;
-            const uint32_t fc = wave ? aff_pair_wave<WIDE>(tcm, ag, B, GO, tab_lane, ent_shift, pL, pS, slot, lane)
+            const uint32_t fc = wave ? aff_pair_wave<WIDE>(tcm, ag, B, GO, tab_lane, ent_shift, pL, pS, slot, lane, p.k_one)
                                      : aff_pair_rowwise<WIDE>(tcm, ag, B, GO, s_sub, pL, pS, slot, lane);
             if (lane == 0) {
                 s_flags[cnt] = (fl ? 1u : 0u) | (wave ? 4u : 0u) | ((uint32_t)B << 8);

@@ -36,6 +36,7 @@ struct AffParams {
     unsigned int *class_count;
     unsigned int *class_take;
     uint32_t     *big_list;
+    uint32_t      k_one;
 };
 uint32_t aff_words_for(uint32_t n1, uint32_t n2);
 cudaError_t launch_affine_classify(const AffParams &p, int grid, cudaStream_t stream);
@@ -565,6 +566,7 @@ static int enqueue_affine(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &
     p.class_count = counter + 16;
     p.class_take = counter + 24;
     p.big_list = (uint32_t *)ctx->big.p;
+    p.k_one = 1u;
     CK(launch_affine_classify(p, grid, st));
     CK(launch_affine(p, false, grid, warps * 32, smem, st));
     ctx->last_launches += 2;
@@ -1380,15 +1382,17 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
     // ---- pipelined path: the batch is cut into chunks whose strings and outputs are contiguous ranges of
     // the host buffers; chunk c+1 is copied in and chunk c-1 copied out while chunk c is aligned
     // (three streams, PCIe is full duplex).  Needs monotone layouts, which the packers produce; anything
-    // else takes the plain path below.  Affine chunks are sized by CELLS, not pairs: a 5 kb pair is a million cells
-    // and occupies a warp for milliseconds, so a chunk must hold many pairs per resident warp or the end of every
-    // chunk — warps idle while the last pairs finish, the narrow and the wide kernel one after the other — dominates
-    // (measured: 4096-pair chunks of config 3 ran 3.4x slower than one launch).
+    // else takes the plain path below.  Affine pairs are three orders of magnitude heavier per byte (a 5 kb pair is a
+    // million cells and occupies a warp for milliseconds) and their kernels come in two launches per batch (narrow band
+    // classes, then wide ones): every chunk pays the end of both — warps idle while the last pairs finish.  Measured on
+    // config 3 (100 000 pairs, 341 ms of kernel time): 25 chunks of 4096 pairs 1275 ms, 4 chunks of 9 .. 38 k pairs
+    // 484 ms, while copy-in + one launch + copy-out is ~420 ms.  So affine batches are pipelined only when they are
+    // large enough for chunks of 64 pairs per resident warp.
     size_t chunk = ctx->knobs.host_chunk_pairs ? ctx->knobs.host_chunk_pairs
                    : ctx->host_chunk_pairs     ? ctx->host_chunk_pairs : 65536;
     if (affine && !ctx->knobs.host_chunk_pairs && !ctx->host_chunk_pairs) {
         const size_t warps = (size_t)ctx->sm_count * (size_t)std::min(ctx->warps_per_cta, 16);
-        chunk = std::max<size_t>(16 * warps, 8192);           // >= 16 pairs per resident warp
+        chunk = std::max<size_t>(64 * warps, 8192);
     }
     bool pipelined = n > chunk && (affine || ctx->max_b > 8);     // (wide kernel on: no per-chunk queue left behind)
     // COMPACT TRANSFER (b->out_off_actual).  The reference hands every alignment back in buffers of capacity
