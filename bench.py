@@ -605,7 +605,7 @@ def run_config4(args, rank, world, local_rank, ctx, torch, dist, steps=None, n=N
     ln = np.full(n, L4, np.uint32)
     out_off = off1.copy()
     cnt = elems.size + 4
-    ctx.configure(pairs_per_warp=min(args.ppw, int(os.environ.get("BENCH_C4_PPW", "8"))), warps_per_cta=16, max_len=L4, max_b=32)
+    ctx.configure(pairs_per_warp=min(args.ppw, int(os.environ.get("BENCH_C4_PPW", "16"))), warps_per_cta=16, max_len=L4, max_b=32)
     memo = ctx.memo(pref_gap_tcm(A))
     dev = torch.device("cuda", local_rank)
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <cstdint>
 #include <mutex>
@@ -717,13 +718,39 @@ extern "C" int pcgdo_metric_batch_device(pcgdo_ctx *ctx, int alphabet, int diale
     return PCGDO_OK;
 }
 
+namespace {
+struct EventPool32 {
+    std::vector<cudaEvent_t> all;
+    ~EventPool32() { for (cudaEvent_t e : all) cudaEventDestroy(e); }
+    cudaError_t make(cudaEvent_t *out)
+    {
+        const cudaError_t e = cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+        if (e == cudaSuccess) all.push_back(*out);
+        return e;
+    }
+};
+}  // namespace
+
+// Host buffers in, host buffers out for the large-alphabet dialects.  Batches whose strings and outputs are laid out
+// monotonically (what the packers produce) are cut into chunks: chunk c + 1 is copied in and chunk c - 1 copied out
+// while chunk c is aligned (three streams; the device call of a chunk returns when its kernel is done, with the
+// neighbouring copies already queued).  Everything else takes the one-shot path.
+// enqueue (may be empty): the same work as device_call but without any synchronisation — failure counters accumulate
+// on the device over the chunks (`first` resets them) and are looked at once, after the last chunk.  A device call that
+// reads anything back per chunk would queue its few bytes behind the bulk copies of the neighbouring chunks on the same
+// copy engine and hold the next launch back by milliseconds (measured: 22 ms instead of 14 per 65 536-pair chunk).
+using Enqueue32 = std::function<int(const pcgdo_batch32 *, cudaStream_t, bool first, unsigned int **counters)>;
+// the table kernel of one chunk, asynchronously (dialects 0..2; empty for what only the synchronous call handles)
+static Enqueue32 table_enqueue32(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect);
+
 template <class DeviceCall>
-static int batch32_host_impl(pcgdo_ctx *ctx, const pcgdo_batch32 *b, DeviceCall device_call)
+static int batch32_host_impl(pcgdo_ctx *ctx, const pcgdo_batch32 *b, int words, DeviceCall device_call,
+                             const Enqueue32 &enqueue = Enqueue32())
 {
     if (!ctx || !b) return PCGDO_ERR_ARG;
     if (b->n_pairs == 0) return PCGDO_OK;
     CK(cudaSetDevice(ctx->device));
-    const size_t n = b->n_pairs;
+    const size_t n = b->n_pairs, W = (size_t)(words > 0 ? words : 1);
     const bool want = b->out_med || b->out_a1 || b->out_a2;
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->d_elems, b->elems_count * 4 + 16))) return rc;
@@ -738,12 +765,6 @@ static int batch32_host_impl(pcgdo_ctx *ctx, const pcgdo_batch32 *b, DeviceCall 
             return rc;
     }
     cudaStream_t st = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_count * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_off1.p, b->off1, n * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_off2.p, b->off2, n * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_len1.p, b->len1, n * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_len2.p, b->len2, n * 4, cudaMemcpyHostToDevice, st));
-    if (want) CK(cudaMemcpyAsync(ctx->d_out_off.p, b->out_off, n * 8, cudaMemcpyHostToDevice, st));
     pcgdo_batch32 d = *b;
     d.elems = (const uint32_t *)ctx->d_elems.p;
     d.off1 = (const uint64_t *)ctx->d_off1.p; d.off2 = (const uint64_t *)ctx->d_off2.p;
@@ -756,6 +777,117 @@ static int batch32_host_impl(pcgdo_ctx *ctx, const pcgdo_batch32 *b, DeviceCall 
     d.cost = (int32_t *)ctx->d_cost.p;
     d.cells = b->cells ? (uint64_t *)ctx->d_cells.p : nullptr;
     d.final_offset = b->final_offset ? (int32_t *)((uint32_t *)ctx->d_olen.p + n) : nullptr;
+
+    // ---- pipelined path
+    const size_t chunk = ctx->knobs.host_chunk_pairs ? ctx->knobs.host_chunk_pairs : 65536;
+    if (n > chunk && b->out_off) {
+        std::vector<size_t> cb;
+        for (size_t at = 0; at < n; at += chunk) cb.push_back(at);
+        cb.push_back(n);
+        const size_t nch = cb.size() - 1;
+        std::vector<size_t> e_lo(nch), e_hi(nch), o_lo(nch), o_hi(nch);
+        bool mono = true;
+        size_t prev_e = 0, prev_o = 0;
+        for (size_t c = 0; c < nch && mono; ++c) {              // element / output ranges of the chunk, in ELEMENTS
+            size_t lo = SIZE_MAX, hi = 0, olo = SIZE_MAX, ohi = 0;
+            for (size_t k = cb[c]; k < cb[c + 1]; ++k) {
+                lo = std::min(lo, (size_t)std::min(b->off1[k], b->off2[k]));
+                hi = std::max(hi, (size_t)std::max(b->off1[k] + b->len1[k], b->off2[k] + b->len2[k]));
+                olo = std::min(olo, (size_t)b->out_off[k]);
+                ohi = std::max(ohi, (size_t)b->out_off[k] + b->len1[k] + b->len2[k]);
+            }
+            e_lo[c] = lo; e_hi[c] = hi; o_lo[c] = olo; o_hi[c] = ohi;
+            if (lo < prev_e || hi * W > b->elems_count || (want && (olo < prev_o || ohi * W > b->out_count))) mono = false;
+            prev_e = hi; prev_o = ohi;
+        }
+        if (mono) {
+            if (!ctx->s_h2d) {
+                CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+                CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+            }
+            EventPool32 events;
+            std::vector<cudaEvent_t> ev_in(nch), ev_done(nch);
+            for (size_t c = 0; c < nch; ++c) { CK(events.make(&ev_in[c])); CK(events.make(&ev_done[c])); }
+            auto copy_in = [&](size_t c) -> int {
+                const size_t c0 = cb[c], k = cb[c + 1] - c0;
+                cudaStream_t s = ctx->s_h2d;
+                CK(cudaMemcpyAsync((uint64_t *)ctx->d_off1.p + c0, b->off1 + c0, k * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync((uint64_t *)ctx->d_off2.p + c0, b->off2 + c0, k * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync((uint32_t *)ctx->d_len1.p + c0, b->len1 + c0, k * 4, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync((uint32_t *)ctx->d_len2.p + c0, b->len2 + c0, k * 4, cudaMemcpyHostToDevice, s));
+                if (want) CK(cudaMemcpyAsync((uint64_t *)ctx->d_out_off.p + c0, b->out_off + c0, k * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync((uint32_t *)ctx->d_elems.p + e_lo[c] * W, b->elems + e_lo[c] * W, (e_hi[c] - e_lo[c]) * W * 4,
+                                   cudaMemcpyHostToDevice, s));
+                CK(cudaEventRecord(ev_in[c], s));
+                return PCGDO_OK;
+            };
+            auto copy_out = [&](size_t c) -> int {
+                const size_t c0 = cb[c], k = cb[c + 1] - c0, ob = (o_hi[c] - o_lo[c]) * W * 4, oo = o_lo[c] * W;
+                cudaStream_t s = ctx->s_d2h;
+                CK(cudaStreamWaitEvent(s, ev_done[c], 0));
+                CK(cudaMemcpyAsync(b->cost + c0, d.cost + c0, k * 4, cudaMemcpyDeviceToHost, s));
+                if (b->out_len) CK(cudaMemcpyAsync(b->out_len + c0, d.out_len + c0, k * 4, cudaMemcpyDeviceToHost, s));
+                if (b->final_offset) CK(cudaMemcpyAsync(b->final_offset + c0, d.final_offset + c0, k * 4, cudaMemcpyDeviceToHost, s));
+                if (b->cells) CK(cudaMemcpyAsync(b->cells + c0, d.cells + c0, k * 8, cudaMemcpyDeviceToHost, s));
+                if (b->out_med) CK(cudaMemcpyAsync(b->out_med + oo, d.out_med + oo, ob, cudaMemcpyDeviceToHost, s));
+                if (b->out_a1) CK(cudaMemcpyAsync(b->out_a1 + oo, d.out_a1 + oo, ob, cudaMemcpyDeviceToHost, s));
+                if (b->out_a2) CK(cudaMemcpyAsync(b->out_a2 + oo, d.out_a2 + oo, ob, cudaMemcpyDeviceToHost, s));
+                return PCGDO_OK;
+            };
+            if ((rc = copy_in(0))) return rc;
+            int launches = 0;
+            unsigned int *counters = nullptr;
+            for (size_t c = 0; c < nch; ++c) {
+                if (c + 1 < nch && (rc = copy_in(c + 1))) return rc;
+                CK(cudaStreamWaitEvent(st, ev_in[c], 0));
+                const size_t c0 = cb[c];
+                pcgdo_batch32 dc = d;
+                dc.n_pairs = cb[c + 1] - c0;
+                dc.off1 = d.off1 + c0; dc.off2 = d.off2 + c0; dc.len1 = d.len1 + c0; dc.len2 = d.len2 + c0;
+                dc.out_off = d.out_off ? d.out_off + c0 : nullptr;
+                dc.out_len = d.out_len ? d.out_len + c0 : nullptr;
+                dc.cost = d.cost + c0;
+                dc.cells = d.cells ? d.cells + c0 : nullptr;
+                dc.final_offset = d.final_offset ? d.final_offset + c0 : nullptr;
+                if (enqueue) {
+                    if (c == 0) { ctx->last_launches = 0; CK(cudaEventRecord(ctx->ev0, st)); }
+                    if ((rc = enqueue(&dc, st, c == 0, &counters))) return rc;
+                } else {
+                    if ((rc = device_call(&dc, st))) return rc;      // returns when the chunk's kernels are done
+                    launches += ctx->last_launches;
+                }
+                CK(cudaEventRecord(ev_done[c], st));
+                if ((rc = copy_out(c))) return rc;
+            }
+            if (enqueue) {
+                CK(cudaEventRecord(ctx->ev1, st));
+                ctx->timed = true;
+                unsigned int h_over[2] = {0, 0};
+                CK(cudaMemcpyAsync(h_over, counters + 8, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                CK(cudaStreamSynchronize(ctx->s_d2h));
+                if (h_over[0]) {
+                    char msg[260];
+                    snprintf(msg, sizeof msg, "%u pair(s) exceed the table kernel's limits (band wider than 1023 diagonals, strings "
+                                              "longer than max_len=%d, or scratch beyond the arena); %u of them because a folded "
+                                              "cost does not fit 16 bits", h_over[0], ctx->max_len, h_over[1]);
+                    ctx->err = msg;
+                    return PCGDO_ERR_OVERFLOW;
+                }
+                return PCGDO_OK;
+            }
+            ctx->last_launches = launches;
+            CK(cudaStreamSynchronize(ctx->s_d2h));
+            return PCGDO_OK;
+        }
+    }
+
+    CK(cudaMemcpyAsync(ctx->d_elems.p, b->elems, b->elems_count * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off1.p, b->off1, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_off2.p, b->off2, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_len1.p, b->len1, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_len2.p, b->len2, n * 4, cudaMemcpyHostToDevice, st));
+    if (want) CK(cudaMemcpyAsync(ctx->d_out_off.p, b->out_off, n * 8, cudaMemcpyHostToDevice, st));
     if ((rc = device_call(&d, st))) return rc;
     CK(cudaMemcpyAsync(b->cost, d.cost, n * 4, cudaMemcpyDeviceToHost, st));
     if (b->out_len) CK(cudaMemcpyAsync(b->out_len, d.out_len, n * 4, cudaMemcpyDeviceToHost, st));
@@ -770,9 +902,11 @@ static int batch32_host_impl(pcgdo_ctx *ctx, const pcgdo_batch32 *b, DeviceCall 
 
 extern "C" int pcgdo_metric_batch_host(pcgdo_ctx *ctx, int alphabet, int dialect, const pcgdo_batch32 *b)
 {
-    return batch32_host_impl(ctx, b, [&](const pcgdo_batch32 *d, cudaStream_t st) {
+    Enqueue32 enq;
+    if (ctx && !ctx->knobs.metric_registers) enq = table_enqueue32(ctx, nullptr, alphabet, dialect);
+    return batch32_host_impl(ctx, b, (alphabet + 31) / 32, [&](const pcgdo_batch32 *d, cudaStream_t st) {
         return pcgdo_metric_batch_device(ctx, alphabet, dialect, d, st);
-    });
+    }, enq);
 }
 
 // --------------------------------------------------------------------------------------------- explicit matrices
@@ -933,7 +1067,9 @@ struct TableCfg { uint32_t seq_cap, tab_entries; int warps; size_t smem, arena_w
 static int table_config(pcgdo_ctx *ctx, int a, TableCfg &c, bool dict = false)
 {
     c.seq_cap = metric_seq_cap(ctx->max_len);
-    c.tab_entries = dict ? 0 : 1024;                       // 2 KB of shared memory per warp for small per-pair tables
+    // 2 KB of shared memory per warp for small per-pair tables; none next to the batch dictionary (if that turns out
+    // unusable the per-pair tables live in the warp's global scratch)
+    c.tab_entries = dict ? 0 : 1024;
     // a <= 32: sigma staged in shared memory; wider alphabets keep it in global memory and stage the gap element only;
     // batch-dictionary mode: one replicated table per CTA instead of the per-warp ones
     const size_t sg_bytes = (a > 32 ? 64 : (((size_t)a * a * 4 + 15) & ~(size_t)15)) + (dict ? kDictSmemBytes : 0);
@@ -965,16 +1101,23 @@ static int table_config(pcgdo_ctx *ctx, int a, TableCfg &c, bool dict = false)
 // Enqueue the per-pair table kernel for one batch described on the device (the forest scheduler's levels): no
 // synchronisation, failure counters accumulate in counters[8..10] unless reset_overflow.
 int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const MetricBatchDev &bd,
-                        cudaStream_t st, bool reset_overflow, unsigned int **counters_out)
+                        cudaStream_t st, bool reset_overflow, unsigned int **counters_out, bool try_dict)
 {
     const int a = memo ? (int)memo->a : alphabet;
     if (a < 2 || a > PCGDO_MAX_ALPHABET || dialect < 0 || dialect > 2) {
         ctx->err = "table path: alphabet size must be 2..512, dialect 0..2";
         return PCGDO_ERR_UNSUPPORTED;
     }
-    TableCfg c;
+    TableCfg c, cd;
     int rc;
     if ((rc = table_config(ctx, a, c))) return rc;
+    // Batch dictionary (a <= 32): one pass over the batch's elements; when they are few (amino-acid strings with a handful
+    // of ambiguity codes) a single table over them, replicated per shared-memory bank, serves every pair — see DictDev.
+    // The KERNEL decides (DictDev.ok, read on the device): nothing comes back to the host, the call stays asynchronous.
+    // Attempted when reserving the table's 65 KB costs at most a quarter of the resident warps.
+    bool dict = try_dict && a <= 32 && !ctx->knobs.no_dict && bd.n_pairs >= 64;
+    if (dict && (table_config(ctx, a, cd, true) != PCGDO_OK || 4 * cd.warps < 3 * c.warps)) dict = false;
+    if (dict) c = cd;
     const uint32_t seq_cap = c.seq_cap, tab_entries = c.tab_entries;
     const int warps = c.warps, grid = ctx->sm_count;
     const size_t smem = c.smem, arena_words = c.arena_words, ts_words = c.ts_words;
@@ -1004,6 +1147,12 @@ int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, in
     p.k_four = 4u;
     p.k_minus1 = 0xffffffffu;
     p.k_one = 1u;
+    if (dict) {
+        if ((rc = pcgdo_ensure(ctx, ctx->d_dict, sizeof(DictDev)))) return rc;
+        p.dict = (DictDev *)ctx->d_dict.p;
+        CK(launch_dict(p, (DictDev *)ctx->d_dict.p, grid, st));
+        ctx->last_launches += 2;
+    }
     CK(launch_explicit(p, grid, warps * 32, smem, st));
     ctx->last_launches += 1;
     if (counters_out) *counters_out = p.counter;
@@ -1084,25 +1233,18 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
         CK(launch_fullmatrix(p, grid, st));
         ctx->last_launches = 1;
     } else if (dialect == 0 || !ctx->knobs.explicit_multi_pass) {
-        // Batch dictionary (a <= 32): one pass over the batch's elements; when they are few (amino-acid strings with a
-        // handful of ambiguity codes) a single table over them, replicated per shared-memory bank, serves every pair —
-        // see DictDev.  One small read-back decides; batches with many distinct sets keep the per-pair tables.
+        // batch dictionary: see pcgdo_enqueue_table (the kernel reads DictDev.ok itself)
         int launches = 1;
-        if (a <= 32 && !ctx->knobs.no_dict && b->n_pairs >= 64) {
+        TableCfg cd;
+        if (a <= 32 && !ctx->knobs.no_dict && b->n_pairs >= 64 && table_config(ctx, a, cd, true) == PCGDO_OK &&
+            4 * cd.warps >= 3 * warps && cd.warps <= warps) {        // (arena and scratch are sized for `warps`)
             if ((rc = pcgdo_ensure(ctx, ctx->d_dict, sizeof(DictDev)))) return rc;
             DictDev *dd = (DictDev *)ctx->d_dict.p;
             CK(launch_dict(p, dd, grid, st));
             launches += 2;
-            uint32_t hdr[4] = {0, 0, 0, 0};
-            CK(cudaMemcpyAsync(hdr, dd, sizeof hdr, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            TableCfg cd;
-            if (hdr[2] && table_config(ctx, a, cd, true) == PCGDO_OK && cd.warps >= 8) {
-                p.dict = dd;
-                p.smem_tab_entries = cd.tab_entries;
-                const int dw = cd.warps < warps ? cd.warps : warps;      // (arena and scratch are sized for `warps`)
-                CK(launch_explicit(p, grid, dw * 32, cd.smem, st));
-            }
+            p.dict = dd;
+            p.smem_tab_entries = cd.tab_entries;                     // (the shared-memory layout of the dictionary configuration)
+            CK(launch_explicit(p, grid, cd.warps * 32, cd.smem, st));
         }
         if (!p.dict) CK(launch_explicit(p, grid, warps * 32, smem, st));
         ctx->last_launches = launches;
@@ -1153,11 +1295,30 @@ static int table_batch_device(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphab
     return PCGDO_OK;
 }
 
+static Enqueue32 table_enqueue32(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect)
+{
+    if (!ctx || dialect < 0 || dialect > 2 || (dialect != 0 && ctx->knobs.explicit_multi_pass)) return Enqueue32();
+    return [=](const pcgdo_batch32 *d, cudaStream_t st, bool first, unsigned int **counters) -> int {
+        MetricBatchDev bd{};
+        bd.n_pairs = (uint32_t)d->n_pairs;
+        bd.elems = d->elems;
+        bd.off1 = d->off1; bd.off2 = d->off2; bd.len1 = d->len1; bd.len2 = d->len2;
+        bd.out_off = d->out_off;
+        bd.out_med = d->out_med; bd.out_a1 = d->out_a1; bd.out_a2 = d->out_a2;
+        bd.out_len = d->out_len;
+        bd.cost = d->cost;
+        bd.cells = d->cells;
+        bd.final_offset = d->final_offset;
+        return pcgdo_enqueue_table(ctx, memo, alphabet, dialect, bd, st, first, counters, true);
+    };
+}
+
 extern "C" int pcgdo_explicit_batch_host(pcgdo_ctx *ctx, const pcgdo_memo *memo, int dialect, const pcgdo_batch32 *b)
 {
-    return batch32_host_impl(ctx, b, [&](const pcgdo_batch32 *d, cudaStream_t st) {
+    if (!memo) return PCGDO_ERR_ARG;
+    return batch32_host_impl(ctx, b, (int)((memo->a + 31) / 32), [&](const pcgdo_batch32 *d, cudaStream_t st) {
         return pcgdo_explicit_batch_device(ctx, memo, dialect, d, st);
-    });
+    }, table_enqueue32(ctx, memo, (int)memo->a, dialect));
 }
 
 extern "C" int pcgdo_last_kernel_ms(pcgdo_ctx *ctx, float *ms, int *launches)

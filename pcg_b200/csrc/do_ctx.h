@@ -84,4 +84,4 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo::Batc
 struct pcgdo_memo;
 namespace pcgdo { struct MetricBatchDev; }
 int pcgdo_enqueue_table(pcgdo_ctx *ctx, const pcgdo_memo *memo, int alphabet, int dialect, const pcgdo::MetricBatchDev &bd,
-                        cudaStream_t st, bool reset_overflow, unsigned int **counters_out);
+                        cudaStream_t st, bool reset_overflow, unsigned int **counters_out, bool try_dict = false);

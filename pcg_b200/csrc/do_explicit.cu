@@ -886,10 +886,13 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     const uint32_t sg_bytes = WIDE ? 64u : (((uint32_t)(a * a) * 4u + 15u) & ~15u);
     const uint32_t per_warp = 512u + p.seq_cap + 2u * p.smem_tab_entries;
     // batch-dictionary mode: [replicated table 64 KB | hash keys[64] vals[64] | cL[32] gS[32]] in front of the warps' windows
-    const bool dict = !WIDE && p.dict != nullptr;
+    // (the shared-memory layout depends on whether the host reserved room for the dictionary, p.dict != NULL; whether
+    // the dictionary is USED is decided here, from what dict_build_kernel found)
+    const bool dict_room = !WIDE && p.dict != nullptr;
+    const bool dict = dict_room && p.dict->ok != 0u;
     char *dbase = x_smem + sg_bytes;
     uint32_t *d_keys = reinterpret_cast<uint32_t *>(dbase + 65536), *d_vals = d_keys + 64, *d_cL = d_vals + 64, *d_gS = d_cL + 32;
-    uint32_t *s_meta = reinterpret_cast<uint32_t *>(x_smem + sg_bytes + (dict ? kDictSmemBytes : 0u) + (size_t)warp * per_warp);
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(x_smem + sg_bytes + (dict_room ? kDictSmemBytes : 0u) + (size_t)warp * per_warp);
     uint32_t *s_flags = s_meta, *s_nal = s_meta + 32, *s_off = s_meta + 64, *s_geo = s_meta + 96;
     uint32_t *seq = s_meta + 128;
     int16_t *stab = reinterpret_cast<int16_t *>(reinterpret_cast<char *>(seq) + p.seq_cap);
@@ -921,12 +924,23 @@ __global__ void __launch_bounds__(512, 1) do_explicit_kernel(const ExplicitParam
     // double are queued for the next launch so that all warps run the same fill variant at the same time
     const uint32_t n_work = p.in_count ? *p.in_count : b.n_pairs;
 
+    // Guided hand-out: a warp takes up to G pairs at a time (they are filled back to back and traced together, one lane
+    // per pair), but never more than its share of half of what is left — the grabs shrink towards the end of the launch,
+    // so that the warps finish together.  With fixed grabs of G the last wave left most of the SMs idle: a 65 536-pair
+    // chunk of config 4 ran at 60 % of the full batch's rate.
+    const uint32_t total_warps = gridDim.x * (uint32_t)nwarps;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.counter, (unsigned)G);
+        uint32_t base = 0, take = (uint32_t)G;
+        if (lane == 0) {
+            const uint32_t cur = *reinterpret_cast<volatile unsigned int *>(p.counter);
+            const uint32_t rem = cur < n_work ? n_work - cur : 0u;
+            take = min((uint32_t)G, max(1u, rem / (2u * total_warps)));
+            base = atomicAdd(p.counter, take);
+        }
         base = __shfl_sync(kFullM, base, 0);
+        take = __shfl_sync(kFullM, take, 0);
         if (base >= n_work) break;
-        const int npw = (int)min((uint32_t)G, n_work - base);
+        const int npw = (int)min(take, n_work - base);
         int pi = 0;
         while (pi < npw) {
             const int start = pi;

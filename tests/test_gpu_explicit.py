@@ -228,3 +228,33 @@ def test_batch_dictionary_equals_per_pair_tables(oracle_mod, gpu_ctx, monkeypatc
                 oc = oracle_mod.haskell_do(dialect, a, pairs[k][0], pairs[k][1], sigma=sig)
                 gc = r.pair(k)
                 assert gc[0] == oc[0] and all(np.array_equal(x, y) for x, y in zip(gc[1:], oc[1:4])), (dialect, k)
+
+
+@pytest.mark.parametrize("a", [21, 82])
+def test_pipelined_host_path_for_large_alphabets(gpu_ctx, monkeypatch, a):
+    """pcgdo_metric_batch_host / pcgdo_explicit_batch_host cut monotone batches into chunks (copy in / align / copy out on
+    three streams): same results as the one-shot path, for one-word and multi-word elements."""
+    from pcg_b200.pairwise import metric_do_batch
+    rng = np.random.default_rng(a)
+    W = (a + 31) // 32
+
+    def rstr(n):
+        sym = rng.integers(0, a - 1, size=n)
+        out = np.zeros((n, W), np.uint32)
+        out[np.arange(n), sym // 32] = (1 << (sym % 32)).astype(np.uint32)
+        return out if W > 1 else out.reshape(-1)
+    pairs = [(rstr(int(rng.integers(1, 120))), rstr(int(rng.integers(1, 120)))) for _ in range(1500)]
+    f, s = [p[0] for p in pairs], [p[1] for p in pairs]
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=16, max_len=128, max_b=32, arena_words=0)
+    alpha = a if a <= 32 else gpu_ctx.memo(None, structure="discrete", a=a)
+    monkeypatch.setenv("PCGDO_HOST_CHUNK_PAIRS", "1048576")
+    gpu_ctx.reload_env()
+    plain = metric_do_batch(gpu_ctx, alpha, 2, f, s)
+    monkeypatch.setenv("PCGDO_HOST_CHUNK_PAIRS", "256")
+    gpu_ctx.reload_env()
+    piped = metric_do_batch(gpu_ctx, alpha, 2, f, s)
+    monkeypatch.delenv("PCGDO_HOST_CHUNK_PAIRS")
+    gpu_ctx.reload_env()
+    for x, y in ((plain.cost, piped.cost), (plain.out_len, piped.out_len), (plain.cells, piped.cells),
+                 (plain.final_offset, piped.final_offset), (plain.median, piped.median), (plain.a1, piped.a1), (plain.a2, piped.a2)):
+        assert np.array_equal(x, y)
