@@ -17,6 +17,8 @@
 
 namespace pcgdo {
 cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_linear_quad(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+uint32_t quad_seq_cap_for(int max_len);
 uint32_t seq_cap_for(int max_len, int B);
 uint64_t general_words_for(uint32_t n1, uint32_t n2);
 cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_t *list, const uint64_t *scratch_off,
@@ -77,6 +79,8 @@ extern "C" int pcgdo_configure_env(pcgdo_ctx *ctx)
     k.zero_copy = getenv("PCGDO_ZERO_COPY") != nullptr;
     k.trace_pipeline = getenv("PCGDO_TRACE_PIPELINE") != nullptr;
     k.no_pack16 = getenv("PCGDO_NO_PACK16") != nullptr;
+    k.no_quad = getenv("PCGDO_NO_QUAD") != nullptr;
+    if (const char *e = getenv("PCGDO_QUAD_FLAGS")) k.quad_flags = (unsigned)atoi(e);
     k.affine_rowwise = getenv("PCGDO_AFFINE_ROWWISE") != nullptr;
     k.metric_registers = getenv("PCGDO_METRIC_REGISTERS") != nullptr;
     k.explicit_multi_pass = getenv("PCGDO_EXPLICIT_MULTI_PASS") != nullptr;
@@ -130,7 +134,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_dict, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->singles, &ctx->phase, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_dict, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
                       &ctx->d_olen, &ctx->d_cost, &ctx->d_cells, &ctx->d_stage, &ctx->d_actual, &ctx->d_total, &ctx->d_strag};
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
@@ -385,7 +389,20 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     // back — the host pipeline, the forest — size these for their largest batch before the first one)
     if ((rc = pcgdo_ensure(ctx, ctx->overflow, (size_t)bd.n_pairs * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4))) return rc;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 16, st));
+    // Four pairs per warp (do_linear_quad_kernel) first, when the TCM qualifies for the packed fill and one pair's
+    // strings fit a quarter of a warp's staging share; what it leaves over goes to the narrow kernel through a list.
+    uint32_t cap_q = 0;
+    int warps_q = 0;
+    if (tcm->dev.pack_ok && !ctx->knobs.no_pack16 && !ctx->knobs.no_quad && bd.n_pairs >= 4) {
+        const size_t dim = (size_t)1 << tcm->a;
+        const size_t fixed = tcm->dev.sub4_bytes + 2 * dim * 4;
+        warps_q = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
+        const size_t room = (227 * 1024 - fixed) / warps_q;
+        const uint32_t want = (quad_seq_cap_for(ctx->max_len) + 15u) & ~15u;
+        if (room >= 640 + 4 * 1024) cap_q = std::min<uint32_t>((uint32_t)((room - 640) / 4) & ~15u, want);
+    }
+    if (cap_q && (rc = pcgdo_ensure(ctx, ctx->singles, (size_t)bd.n_pairs * 4))) return rc;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 32, st));
 
     LinearParams p{};
     p.tcm = tcm->dev;
@@ -407,6 +424,21 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     p.k_64k = 65536u;
     p.grab = 2;
 
+    if (cap_q) {
+        p.single_count = p.counter + 5;
+        p.single_list = (uint32_t *)ctx->singles.p;
+        p.seq_cap = cap_q;
+        p.quad_flags = ctx->knobs.quad_flags;
+        if (ctx->knobs.quad_flags & 2u) {
+            if ((rc = pcgdo_ensure(ctx, ctx->phase, 64))) return rc;
+            CK(cudaMemsetAsync(ctx->phase.p, 0, 64, st));
+            p.phase_cycles = (unsigned long long *)ctx->phase.p;
+        }
+        p.quad_arena_words = (uint32_t)std::min<size_t>((arena_words * warps_max / warps_q) & ~(size_t)3, 0xfffffff0u);
+        const size_t dim = (size_t)1 << tcm->a;
+        CK(launch_linear_quad(p, grid, warps_q * 32, tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps_q * (640 + 4 * (size_t)cap_q), st));
+        ctx->last_launches += 1;
+    }
     p.seq_cap = cap_n;
     CK(launch_linear(p, false, grid, warps_n * 32, smem_for(tcm, warps_n, cap_n), st));
     ctx->last_launches += 1;
@@ -460,6 +492,12 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     unsigned int h_cnt[9] = {0};
     CK(cudaMemcpyAsync(h_cnt, p.counter, 36, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (p.phase_cycles) {
+        unsigned long long h_ph[4] = {0};
+        CK(cudaMemcpy(h_ph, p.phase_cycles, 32, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[pcgdo] quad kernel warp-cycles: stage %llu fill %llu trace %llu emit %llu; singles %u\n", h_ph[0], h_ph[1],
+                h_ph[2], h_ph[3], h_cnt[5]);
+    }
     // pairs the warp kernels could not hold (band wider than 1023 diagonals, strings longer than the
     // staging window, scratch larger than the arena; plus the wide queue when that kernel is disabled)
     // go through the general-geometry kernel: one CTA per pair, scratch sized from their lengths

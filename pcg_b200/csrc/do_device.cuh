@@ -88,6 +88,7 @@ struct LinearParams {
     BatchDev  b;
     uint32_t *arena;        // [n_warps_total][arena_words]: direction words + op streams of the
     uint32_t  arena_words;  //   pairs a warp has filled but not yet traced
+    uint32_t  quad_arena_words;   // the same for a warp of the four-pairs-per-warp kernel (fewer warps per CTA share the arena)
     uint32_t  seq_cap;      // u16 elements of sequence staging per warp
     int       pairs_per_warp;   // pairs a warp fills before it traces them, one lane per pair (1..32)
     uint32_t  grab;         // pairs taken from the work counter at a time
@@ -97,9 +98,15 @@ struct LinearParams {
     uint32_t      overflow_cap;
     unsigned int *big_count;       // pairs whose band needs more than 8 diagonals per lane:
     uint32_t     *big_list;        //   queued by the narrow kernel, consumed by the wide one
+    unsigned int *single_count;    // four-pairs-per-warp kernel: the pairs it did not take (bit 31: 32-bit fill),
+    uint32_t     *single_list;     //   consumed by the narrow kernel; NULL = the narrow kernel reads the batch itself
     // run-time "constants" (1, 4, -1, table row stride) kept opaque to ptxas so that the table-address add
     // and the direction accumulation are emitted as IMAD (FMA pipe) instead of IADD3/LEA/SHF (ALU pipe)
     uint32_t  k_four, k_minus1, l_stride, k_64k;
+    // experiment switches of the four-pairs-per-warp kernel: bit 0 = stagger the warps' first batches; and, when not
+    // NULL, per-phase cycle sums over all warps: [stage, fill, trace, emit]
+    uint32_t  quad_flags;
+    unsigned long long *phase_cycles;
 };
 
 // Geometry of one pair, identical on host and device (plain IEEE double multiplies only).

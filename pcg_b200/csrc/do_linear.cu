@@ -347,6 +347,259 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
 
 
 // ---------------------------------------------------------------------------------------------
+// multi-pair packed fill: FOUR pairs per warp, 8 lanes x 28 diagonals each
+//
+// A band of 129 .. 223 diagonals (1 kb strings: 200) leaves 22 % of a 32 x 8 warp as padding, and the per-iteration
+// overhead of the wavefront (two shuffles, the funnel shifts, the window loads, the loop) is paid for 4 packed updates.
+// Here a warp sweeps four pairs at once: lanes 8s .. 8s+7 own the diagonals of pair s, 28 per lane = 14 packed registers,
+// so the same overhead is spread over 14 updates and 224 diagonal slots serve a pair instead of 256.  Everything that
+// depends on the pair (geometry, string windows, masks) is per-lane data already; the shuffles stay warp-wide because
+// what crosses a segment border only ever lands in the always-masked diagonals q = 0 and q = 223 of a pair.
+// Pairs of a group may differ in length: all four run max(T) iterations.  Past a pair's own last cell the strings read
+// as padding (table entry kBigSub), moves along rows / columns are free in the folded cell values, and so the final
+// cell's value is carried unchanged down its diagonal — it is read after the common last iteration.
+// Direction words: word[(t >> 3) * 448 + lane * 14 + m] — the diagonals of a pair are consecutive words (two diagonals 14
+// apart share a word), so the trace's next word is usually in the 32-byte sector it already holds.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQuadB = 28, kQuadH = 14, kQuadLanes = 8, kQuadPairs = 4;
+constexpr uint32_t kQuadRow = 32u * kQuadH;        // direction words per 8 iterations of one group
+
+__host__ __device__ inline uint32_t quad_dir_words(int tmax) { return (uint32_t)((tmax + 7) / 8) * kQuadRow; }
+
+// Staging of one pair of a group: both strings as raw bytes (element 0 = padding), zero-padded for `tmax` iterations.
+__host__ __device__ inline SeqLayout seq_layout_quad(const Geom &g, int tmax)
+{
+    const int tpad = (tmax + 15) & ~15;
+    SeqLayout s;
+    s.offL = kQuadLanes * kQuadH;
+    int needL = tpad + g.q0 / 2 + 2;
+    s.sizeL = s.offL + (needL > g.lg ? needL : g.lg) + 2;
+    s.offS = g.q0 / 2;
+    int needS = tpad - g.q0 / 2 + kQuadLanes * kQuadH + 2;
+    if (needS < g.sh) needS = g.sh;
+    s.sizeS = s.offS + needS + 2;
+    s.sizeL = (s.sizeL + 3) & ~3;
+    s.sizeS = (s.sizeS + 3) & ~3;
+    return s;
+}
+
+// table offset of a lesser-string element (the dense kernels stage it precomputed as u16; here it is one LOP3 + IMAD
+// per lane and iteration)
+__device__ __forceinline__ uint32_t s_entry(uint32_t e, bool repl) { return repl ? (((e >> 1) << 7) | ((e & 1u) << 1)) : (e << 1); }
+
+template <bool TAIL>
+__device__ __forceinline__ void run_chunk16q(uint32_t (&R)[kQuadH], const uint32_t (&penc)[kQuadH], uint32_t (&dw)[kQuadH],
+                                             uint32_t (&lw)[kQuadH], uint32_t (&sw)[kQuadH], const FillConst fc,
+                                             uint32_t tab_lane, bool repl, const char *&lptr, const char *&sptr,
+                                             int n_iter, uint32_t *&out)
+{
+    constexpr int H = kQuadH, Q = H / 2, CH = 8, U = H / 2;
+#pragma unroll
+    for (int r = 0; r < CH; ++r) {
+        if (TAIL && r >= n_iter) break;
+        const int tt = r;
+        // All 28 table fetches of the iteration go out first — they depend on the string windows only, not on the cell
+        // values — so that their latency is paid once per iteration, behind the first half step's arithmetic, and not
+        // once per cell (with 4 warps per scheduler nothing else would cover it).
+        const uint32_t s_new = s_entry(ld_u8(sptr + r), repl) + tab_lane;
+        const uint32_t l_new = ld_u8(lptr + r);
+        uint32_t e_lo[U], e_hi[U], o_lo[U], o_hi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            e_lo[u] = lds_u16(imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u) % H]));
+            e_hi[u] = lds_u16(imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q) % H]));
+        }
+        sw[tt] = s_new;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            o_lo[u] = lds_u16(imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u + 1) % H]));
+            o_hi[u] = lds_u16(imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q + 1) % H]));
+        }
+        lw[(tt + 1) % H] = l_new;
+        // ---- even diagonals (registers with even m): anti-diagonal s = 2t
+        const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
+        const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);
+#pragma unroll
+        for (int m = 0; m < H; m += 2) {
+            const int u = m / 2;
+            const uint32_t left = (m == 0) ? left0 : R[m > 0 ? m - 1 : 0];
+            const uint32_t sub2 = imad(e_hi[u], fc.k64k, e_lo[u]);
+            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
+            const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
+            R[m] = (mn & 0xfffcfffcu) | penc[m];
+            const uint32_t c2 = mn & 0x00030003u;
+            dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
+        }
+        // ---- odd diagonals: anti-diagonal s = 2t + 1
+        const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
+        const uint32_t upl = __funnelshift_r(R[0], next, 16);
+#pragma unroll
+        for (int m = 1; m < H; m += 2) {
+            const int u = (m - 1) / 2;
+            const uint32_t up = (m == H - 1) ? upl : R[m + 1 < H ? m + 1 : H - 1];
+            const uint32_t sub2 = imad(o_hi[u], fc.k64k, o_lo[u]);
+            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
+            const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
+            R[m] = (mn & 0xfffcfffcu) | penc[m];
+            const uint32_t c2 = mn & 0x00030003u;
+            dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
+        }
+        if (r == CH - 1 || (TAIL && r == n_iter - 1)) {
+            const int sh = 2 * (CH - 1 - r);          // left-align a partial group
+#pragma unroll
+            for (int m = 0; m < H; m += 2) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m] << sh, dw[m + 1] << sh);
+            out += kQuadRow;
+        }
+    }
+    lptr += CH;
+    sptr += CH;
+    rot16<H, CH % H>(lw);
+    rot16<H, CH % H>(sw);
+}
+
+// rebase16 over the 8 lanes of one pair
+__device__ __forceinline__ bool rebase16q(uint32_t (&R)[kQuadH], int &total_shift, uint32_t spread_limit)
+{
+    uint32_t mx = 0u, mnv = 0xffffffffu;
+#pragma unroll
+    for (int m = 0; m < kQuadH; ++m) {
+        mx = __vmaxu2(mx, R[m] ^ 0x80008000u);
+        mnv = __vminu2(mnv, R[m]);
+    }
+    uint32_t hi = max(mx & 0xffffu, mx >> 16), lo = min(mnv & 0xffffu, mnv >> 16);
+#pragma unroll
+    for (int d = kQuadLanes / 2; d > 0; d >>= 1) {
+        hi = max(hi, __shfl_xor_sync(kFull, hi, d));
+        lo = min(lo, __shfl_xor_sync(kFull, lo, d));
+    }
+    if (hi < 0x8000u) return true;
+    const uint32_t maxf = hi & 0x7ffcu, minf = lo & 0xfffcu;
+    const int delta = (int)kTop16 - (int)maxf;
+    const uint32_t d2 = ((uint32_t)delta & 0xffffu) * 0x00010001u;
+#pragma unroll
+    for (int m = 0; m < kQuadH; ++m) {
+        const uint32_t unreach = ((R[m] >> 15) & 0x00010001u) * 0xffffu;
+        R[m] = __vadd2(R[m], d2 & ~unreach);
+    }
+    total_shift += delta;
+    return maxf - minf <= spread_limit;
+}
+
+// g, Lb, Sb: of the lane's own pair.  tmax: iterations of the group (warp-uniform).  slot: the group's direction words.
+__device__ __noinline__ uint32_t fill_quad16(const Geom g, int tmax, const FillConst fc, uint32_t tab_lane, bool repl,
+                                             const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg,
+                                             uint32_t spread_limit)
+{
+    constexpr int B = kQuadB, H = kQuadH;
+    uint32_t R[H], penc[H], dw[H], lw[H], sw[H];
+    const int ln = lane & (kQuadLanes - 1);
+    const int qb = ln * B;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        uint32_t pe = 0, wv = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = qb + m + h * H;
+            const uint32_t p1 = 1u | ((q < g.pad || q >= g.wb) ? 0x8000u : 0u);
+            const uint32_t w1 = (q == g.q0) ? ((kTop16 - (uint32_t)sub4gg) & 0xffffu) : 0x8001u;
+            pe |= p1 << (16 * h);
+            wv |= w1 << (16 * h);
+        }
+        penc[m] = pe;
+        asm volatile("" : "+r"(penc[m]));
+        R[m] = wv;
+        dw[m] = 0;
+    }
+    const int I0 = g.q0 / 2 - ln * H;
+    const int J0 = -(g.q0 / 2) + ln * H;
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        lw[(H - u) % H] = ld_u8(Lb + (I0 - u));
+        sw[u] = s_entry(ld_u8(Sb + (J0 + u)), repl) + tab_lane;
+    }
+    const char *lptr = Lb + (I0 + 1);
+    const char *sptr = Sb + (J0 + H);
+    uint32_t *out = slot + lane * H;
+    const int nfull = tmax / 8, rem = tmax % 8;
+    int total_shift = 0;
+    bool ok = true;
+    for (int c = 0; c < nfull; ++c) {
+        if (c && c % 4 == 0) ok = rebase16q(R, total_shift, spread_limit) && ok;       // every 32 iterations
+        run_chunk16q<false>(R, penc, dw, lw, sw, fc, tab_lane, repl, lptr, sptr, 8, out);
+    }
+    if (rem) {
+        if (nfull && nfull % 4 == 0) ok = rebase16q(R, total_shift, spread_limit) && ok;
+        run_chunk16q<true>(R, penc, dw, lw, sw, fc, tab_lane, repl, lptr, sptr, rem, out);
+    }
+    ok = rebase16q(R, total_shift, spread_limit) && ok;
+    const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
+    const int m_last = q_last % B;
+    uint32_t v = 0;
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        if (m == m_last) v = R[m] & 0xffffu;
+        if (m + H == m_last) v = R[m] >> 16;
+    }
+    v = __shfl_sync(kFull, v, (lane & ~(kQuadLanes - 1)) + q_last / B);
+    if (!ok) return kOverflow16;
+    const int x4 = (int)(v & 0x7ffcu) - (int)kTop16 - total_shift;
+    return (uint32_t)((int)kBias4 + x4) | 1u;
+}
+
+// Trace of a four-pair group's member: `dirw` = the direction words of the group, `seg` = the pair's position in it.
+// One lane per pair makes the walk a chain of dependent loads, so every lane walks TWO pairs at once (the loads of both
+// are issued before either is used), and each word load sends the sector below it on its way to L2: the walk gets to
+// that block of 8 iterations some 8 moves later, near the same diagonal.
+struct QWalk {
+    const uint32_t *dirw;
+    uint32_t *ops;
+    int s, q, sft, seg;
+    uint32_t n, acc, w;
+};
+__device__ __forceinline__ void qwalk_init(QWalk &x, const uint32_t *dirw, int seg, int q0, int lg, int sh, uint32_t *ops, bool live)
+{
+    x.dirw = dirw; x.ops = ops; x.seg = seg;
+    x.s = live ? (lg - 1) + (sh - 1) : 0;
+    x.q = (sh - 1) - (lg - 1) + q0;
+    x.sft = 16; x.n = 0; x.acc = 0; x.w = 0;
+}
+__device__ __forceinline__ void qwalk_step(QWalk &x)
+{
+    if (x.s > 0) {
+        const uint32_t code = (x.w >> x.sft) & 3u;
+        x.acc |= code << (2 * (x.n & 15));
+        ++x.n;
+        if ((x.n & 15) == 0) { x.ops[(x.n >> 4) - 1] = x.acc; x.acc = 0; }
+        if (code == 0u) { x.s -= 2; x.sft += 2; }
+        else { x.s -= 1; x.q += (code == 1u) ? 1 : -1; x.sft = 16; }      // 1: consume longer (i--), 2: consume lesser (j--)
+    }
+}
+__device__ __forceinline__ void trace_two16q(QWalk &a, QWalk &b)
+{
+    while (a.s > 0 || b.s > 0) {
+        const bool la = a.s > 0 && a.sft == 16, lb = b.s > 0 && b.sft == 16;
+        // diagonal q = 14 * h14 + r: lane h14 >> 1, register r, half h14 & 1 -> word 14 * lane + r of the pair's 112
+        const int ta = (a.s - (a.q & 1)) >> 1, tb = (b.s - (b.q & 1)) >> 1;
+        const uint32_t ha = (uint32_t)a.q / (uint32_t)kQuadH, hb = (uint32_t)b.q / (uint32_t)kQuadH;
+        const uint32_t *pa = a.dirw + ((uint32_t)(ta >> 3) * kQuadRow + (uint32_t)a.seg * (kQuadLanes * kQuadH) +
+                                       (uint32_t)a.q - (uint32_t)kQuadH * ((ha + 1u) >> 1));
+        const uint32_t *pb = b.dirw + ((uint32_t)(tb >> 3) * kQuadRow + (uint32_t)b.seg * (kQuadLanes * kQuadH) +
+                                       (uint32_t)b.q - (uint32_t)kQuadH * ((hb + 1u) >> 1));
+        uint32_t wa = 0, wb = 0;
+        if (la) wa = __ldcg(pa);
+        if (lb) wb = __ldcg(pb);
+        if (la && ta >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa - kQuadRow));
+        if (lb && tb >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb - kQuadRow));
+        if (la) { a.w = wa >> (16 * (ha & 1u)); a.sft = 2 * (7 - (ta & 7)); }
+        if (lb) { b.w = wb >> (16 * (hb & 1u)); b.sft = 2 * (7 - (tb & 7)); }
+        qwalk_step(a);
+        qwalk_step(b);
+    }
+    if (a.n & 15) a.ops[a.n >> 4] = a.acc;
+    if (b.n & 15) b.ops[b.n >> 4] = b.acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // trace: one lane per pair
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t trace_lane(const uint32_t *dirw, uint32_t wq, int q0, int lg, int sh, uint32_t *ops)
@@ -386,18 +639,32 @@ __device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *
     // write over PCIe wants when the arrays are the caller's pinned host buffers, and full sectors in HBM otherwise.
     const uint8_t *oany = og ? og : (o1 ? o1 : o2);
     const int mis = (int)(reinterpret_cast<uintptr_t>(oany) & 124u);
+    // the four op codes of this lane's columns in the pass that starts at column c0 (3 = no column), one byte each;
+    // fetched one pass ahead: a pass is a chain of dependent loads (ops, then the strings, then the median table)
+    auto fetch_codes = [&](int c0) -> uint32_t {
+        uint32_t pk = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int cc = c0 + 4 * lane + x;
+            uint32_t cd = 3u;
+            if (cc >= 0 && cc < (int)nal) {
+                const uint32_t r = nal - 1u - (uint32_t)cc;
+                cd = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
+            }
+            pk |= cd << (8 * x);
+        }
+        return pk;
+    };
+    uint32_t pk_next = fetch_codes(-mis);
     for (int c0 = -mis; c0 < (int)nal; c0 += 128) {
         const int c = c0 + 4 * lane;
         uint32_t code[4];
         uint32_t nl = 0, ns = 0;
+        const uint32_t pk = pk_next;
+        if (c0 + 128 < (int)nal) pk_next = fetch_codes(c0 + 128);
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-            const int cc = c + x;
-            code[x] = 3u;
-            if (cc >= 0 && cc < (int)nal) {
-                const uint32_t r = nal - 1u - (uint32_t)cc;
-                code[x] = (__ldcg(ops + (r >> 4)) >> (2 * (r & 15))) & 3u;
-            }
+            code[x] = (pk >> (8 * x)) & 3u;
             nl += (code[x] < 2u);
             ns += (code[x] == 0u || code[x] == 2u);
         }
@@ -452,6 +719,82 @@ __device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *
         base_j += tot >> 16;
     }
     return base_u;
+}
+
+// Emit for the 16-warp kernel: the same three strings, written without a loop-carried dependency.  emit_pair carries the
+// element indices from pass to pass through a warp scan, so every pass is a chain (ops -> scan -> strings -> median ->
+// store) that only many resident warps can hide.  Here the op stream is first copied to shared memory together with, per
+// 16-move word, the number of longer / lesser elements consumed by all LATER words (= earlier columns); a column's
+// element indices are then that count plus a popcount inside its own word, and passes are independent of each other
+// (two are kept in flight).  ops_s / suf: scratch in the warp's string windows, which are idle during this phase.
+__device__ __forceinline__ void emit_pair_q(const TcmDev &tcm, const uint8_t *med, const uint8_t *pL, const uint8_t *pS,
+                                            const uint32_t *ops, uint32_t nal, bool first_long, uint8_t *og, uint8_t *o1,
+                                            uint8_t *o2, int lane, uint32_t *ops_s, uint32_t *suf)
+{
+    const uint32_t gap = tcm.gap;
+    const uint32_t nw = (nal + 15u) >> 4, K = (nw + 31u) >> 5;
+    uint32_t mine = 0;                                   // (longer | lesser << 16) consumed by this lane's K words
+    for (uint32_t x = 0; x < K; ++x) {
+        const uint32_t w = (uint32_t)lane * K + x;
+        if (w < nw) {
+            uint32_t v = __ldcg(ops + w);
+            if (w == nw - 1u && (nal & 15u)) v |= 0xffffffffu << (2u * (nal & 15u));      // moves that do not exist: code 3
+            ops_s[w] = v;
+            mine += (uint32_t)__popc((~v >> 1) & 0x55555555u) | ((uint32_t)__popc(~v & 0x55555555u) << 16);
+        }
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_down_sync(kFull, incl, d);
+        if (lane + d < 32) incl += o;
+    }
+    uint32_t run = incl - mine;                          // consumed by the words of all higher lanes
+    for (uint32_t x = K; x-- > 0;) {
+        const uint32_t w = (uint32_t)lane * K + x;
+        if (w < nw) {
+            const uint32_t v = ops_s[w];
+            suf[w] = run;
+            run += (uint32_t)__popc((~v >> 1) & 0x55555555u) | ((uint32_t)__popc(~v & 0x55555555u) << 16);
+        }
+    }
+    __syncwarp();
+    const uint8_t *oany = og ? og : (o1 ? o1 : o2);
+    const int mis = (int)(reinterpret_cast<uintptr_t>(oany) & 124u);
+#pragma unroll 2
+    for (int c0 = -mis; c0 < (int)nal; c0 += 128) {
+        const int c = c0 + 4 * lane;
+        if (c < 0 || c >= (int)nal) continue;
+        uint32_t xx[4], yy[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            xx[x] = 0; yy[x] = 0;
+            const uint32_t r = nal - 1u - (uint32_t)(c + x);              // (wraps for columns past the end: r >= nal)
+            if (r < nal) {
+                const uint32_t v = ops_s[r >> 4], sh = 2u * (r & 15u), code = (v >> sh) & 3u;
+                const uint32_t above = (~v >> sh) >> 2, base = suf[r >> 4];
+                const uint32_t il = (base & 0xffffu) + (uint32_t)__popc((above >> 1) & 0x55555555u);
+                const uint32_t js = (base >> 16) + (uint32_t)__popc(above & 0x55555555u);
+                if (code < 2u) yy[x] = __ldg(pL + il);                    // consume longer
+                if (code == 0u || code == 2u) xx[x] = __ldg(pS + js);     // consume lesser
+            }
+        }
+        uint32_t wg = 0, wx = 0, wy = 0;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const uint32_t r = nal - 1u - (uint32_t)(c + x);
+            if (r < nal) {
+                const uint32_t md = med[((xx[x] ? xx[x] : gap) << tcm.a) | (yy[x] ? yy[x] : gap)];
+                wg |= md << (8 * x);
+                wx |= xx[x] << (8 * x);
+                wy |= yy[x] << (8 * x);
+            }
+        }
+        if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
+        if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wx : wy;
+        if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? wy : wx;
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -520,7 +863,9 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int dim = 1 << tcm.a;
     const BatchDev &b = p.b;
-    const uint32_t n_work = BMAX <= 8 ? b.n_pairs : *p.big_count;
+    // narrow kernel: straight from the batch, or — after the four-pairs-per-warp kernel — the pairs that one left over
+    const bool from_list = BMAX > 8 || p.single_list != nullptr;
+    const uint32_t n_work = BMAX <= 8 ? (p.single_list ? *p.single_count : b.n_pairs) : *p.big_count;
     if (n_work == 0) return;
 
     char *tab = smem;
@@ -572,7 +917,7 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
                 gend = min(base + grab, n_work);
             }
             // wide kernel: queue entries carry bit 31 = "the packed fill overflowed its window, use the 32-bit fill"
-            const uint32_t entry = BMAX <= 8 ? gpos : p.big_list[gpos];
+            const uint32_t entry = !from_list ? gpos : (BMAX <= 8 ? p.single_list[gpos] : p.big_list[gpos]);
             const uint32_t k = entry & 0x7fffffffu;
             const uint32_t n1 = b.len1[k], n2 = b.len2[k];
             const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
@@ -713,6 +1058,292 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Four pairs per warp (fill_quad16).  Takes groups of four consecutive pairs straight from the batch; a group all of
+// whose pairs have a band of 129 .. 223 diagonals, fit the staging windows and need about the same number of
+// iterations is swept at once, every other pair goes to single_list for the narrow kernel launched next.
+// Shared memory: [sub4 table | cgap | gapc | per warp: flags, nal, off, pair, ops (5 x 32 words) + 4 string windows].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool first_is_long_seg(const uint8_t *p1, uint32_t n1, const uint8_t *p2, uint32_t n2, int lane)
+{
+    const int ln = lane & (kQuadLanes - 1), sb = lane & ~(kQuadLanes - 1);
+    bool decided = n1 != n2 || n1 == 0, res = n1 >= n2;
+    for (uint32_t base = 0; __any_sync(kFull, !decided); base += kQuadLanes) {
+        const uint32_t i = base + ln;
+        uint32_t a = 0, b = 0;
+        if (!decided && i < n1) { a = __ldg(p1 + i); b = __ldg(p2 + i); }
+        const unsigned diff = (__ballot_sync(kFull, a != b) >> sb) & ((1u << kQuadLanes) - 1u);
+        const int src = diff ? sb + __ffs(diff) - 1 : lane;
+        const uint32_t aa = __shfl_sync(kFull, a, src), bb = __shfl_sync(kFull, b, src);
+        if (!decided) {
+            if (diff) { res = aa > bb; decided = true; }
+            else if (base + kQuadLanes >= n1) { res = true; decided = true; }
+        }
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearParams p)
+{
+    constexpr int NP = kQuadPairs, LP = kQuadLanes;
+    const TcmDev &tcm = p.tcm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int seg = lane / LP, ln = lane % LP;
+    const int dim = 1 << tcm.a;
+    const BatchDev &b = p.b;
+    const uint32_t n_work = b.n_pairs;
+    if (n_work == 0) return;
+
+    char *tab = smem;
+    uint32_t *s_cgap = reinterpret_cast<uint32_t *>(smem + tcm.sub4_bytes);
+    uint32_t *s_gapc = s_cgap + dim;
+    char *warp_base = reinterpret_cast<char *>(s_gapc + dim);
+    const uint32_t per_warp = 640u + NP * p.seq_cap;
+    // per group (16): arena offset of its direction words, of its op streams, words per op stream; per pair (64): index
+    // in the batch (bit 31: the first input is the longer one, bit 30: left to the narrow kernel) and alignment length
+    uint32_t *g_off = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
+    uint32_t *g_ops = g_off + 16, *g_opw = g_off + 32, *s_pair = g_off + 48;
+    uint16_t *s_nal = reinterpret_cast<uint16_t *>(g_off + 112);
+    // (each pair's window starts one bank further than the previous one's: with equal geometries the four segments'
+    // window loads would otherwise hit the same 8 banks)
+    uint8_t *win = reinterpret_cast<uint8_t *>(g_off) + 640 + (size_t)seg * p.seq_cap + 4 * seg;
+
+    for (uint32_t i = threadIdx.x; i < tcm.sub4_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tab)[i] = __ldg(reinterpret_cast<const uint4 *>(tcm.sub4) + i);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_cgap[i] = tcm.cgap[i]; s_gapc[i] = tcm.gapc[i]; }
+    __syncthreads();
+
+    const bool repl = tcm.repl != 0;
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(tab) + (repl ? 4u * lane : 0u);
+    const FillConst fc = {p.k_four, p.k_minus1, p.l_stride, p.k_64k};
+    int G = (2 * p.pairs_per_warp) & ~(NP - 1);        // two walks per lane in the trace
+    if (G < NP) G = NP;
+    // The warps of a CTA start together and a uniform batch keeps them in step: all fill (issue-bound) and then all trace
+    // (latency-bound) at the same time.  Experiment (quad_flags bit 0): a first batch of a different size per warp spreads
+    // the phases for good — measured SLOWER (67.5 -> 77.9 ms on config 2), so off by default.
+    int Gcur = (p.quad_flags & 1u) ? NP * (1 + (warp * (G / NP - 1)) / (nwarps > 1 ? nwarps - 1 : 1)) : G;
+    long long ph_t = p.phase_cycles ? clock64() : 0;
+    unsigned long long ph[4] = {0, 0, 0, 0};
+    auto phase = [&](int i) { if (p.phase_cycles) { const long long t = clock64(); ph[i] += (unsigned long long)(t - ph_t); ph_t = t; } };
+    const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
+    uint32_t *arena = p.arena + warp_global * (size_t)p.quad_arena_words;
+    unsigned int *counter = p.counter + 4;
+    const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len || b.out_ungapped;
+    const uint32_t emask = (uint32_t)dim - 1u;
+
+    constexpr uint32_t kNone = 0xffffffffu;
+    uint32_t pend = kNone, nxt = kNone;
+    bool exhausted = false;
+    for (;;) {
+        int cnt = 0;
+        uint32_t cur = 0;
+        // -------------------------------------------------------------- fill, group after group
+        for (;;) {
+            if (cnt + NP > Gcur) break;
+            if (pend == kNone) {
+                if (nxt != kNone) { pend = nxt; nxt = kNone; }
+                else {
+                    if (exhausted) break;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned int)NP);
+                    base = __shfl_sync(kFull, base, 0);
+                    if (base >= n_work) { exhausted = true; break; }
+                    pend = base;
+                }
+            }
+            if (nxt == kNone && !exhausted) {
+                // take the group after this one now and start its strings on their way from HBM to L2
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned int)NP);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= n_work) exhausted = true;
+                else {
+                    nxt = base;
+                    const uint32_t kn = base + (uint32_t)seg;
+                    if (kn < n_work) {
+                        const uint8_t *q1 = b.elems + b.off1[kn], *q2 = b.elems + b.off2[kn];
+                        const uint32_t m1 = b.len1[kn], m2 = b.len2[kn];
+                        for (uint32_t o = 128u * ln; m1 && o < m1 + 127u; o += 128u * LP)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + min(o, m1 - 1u)));
+                        for (uint32_t o = 128u * ln; m2 && o < m2 + 127u; o += 128u * LP)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(q2 + min(o, m2 - 1u)));
+                    }
+                }
+            }
+            const bool have = pend + (uint32_t)seg < n_work;
+            const uint32_t k = have ? pend + (uint32_t)seg : pend;
+            const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+            const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+            const bool fl = first_is_long_seg(p1, n1, p2, n2, lane);
+            const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
+            const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+            int tmax = g.T;
+            uint32_t opw = ops_words(g);
+#pragma unroll
+            for (int d = LP; d < 32; d <<= 1) {
+                tmax = max(tmax, __shfl_xor_sync(kFull, tmax, d));
+                opw = max(opw, __shfl_xor_sync(kFull, opw, d));
+            }
+            const SeqLayout sl = seq_layout_quad(g, tmax);
+            const uint32_t dirw = quad_dir_words(tmax);
+            const uint32_t need = (dirw + NP * opw + 3u) & ~3u;
+            const bool elig = have && g.wb + 1 <= LP * kQuadB && g.wb + 1 > 128 && g.sh > 8 &&
+                              (uint32_t)(sl.sizeL + sl.sizeS) + 16u <= p.seq_cap && (tmax - g.T) * 8 <= tmax &&
+                              need <= p.quad_arena_words && g.lg + g.sh < 65536 && k < (1u << 30);
+            if (!__all_sync(kFull, elig)) {
+                if (ln == 0 && have) p.single_list[atomicAdd(p.single_count, 1u)] = k;
+                pend = kNone;
+                continue;
+            }
+            if (cur + need > p.quad_arena_words) break;    // trace + emit what we have, then come back to this group
+            uint32_t *slot = arena + cur;
+
+            // stage the segment's pair; sum the indel costs that are folded out of the cell values
+            // (four bytes per lane and step, four steps in flight: the loads come from HBM and only 16 warps hide them)
+            uint8_t *Lr = win, *Sr = win + sl.sizeL;
+            uint32_t csum = 0;
+            phase(3);
+#pragma unroll 4
+            for (int w4 = ln; w4 < sl.sizeL / 4; w4 += LP) {
+                uint32_t e[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = 4 * w4 + x - sl.offL;
+                    e[x] = (i > 0 && i < g.lg) ? (uint32_t)__ldg(pL + i - 1) & emask : (i == 0 ? tcm.gap : 0u);
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = 4 * w4 + x - sl.offL;
+                    if (i > 0 && i < g.lg) csum += s_cgap[e[x]];
+                }
+                reinterpret_cast<uint32_t *>(Lr)[w4] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
+            }
+#pragma unroll 4
+            for (int w4 = ln; w4 < sl.sizeS / 4; w4 += LP) {
+                uint32_t e[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int j = 4 * w4 + x - sl.offS;
+                    e[x] = (j > 0 && j < g.sh) ? (uint32_t)__ldg(pS + j - 1) & emask : (j == 0 ? tcm.gap : 0u);
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int j = 4 * w4 + x - sl.offS;
+                    if (j > 0 && j < g.sh) csum += s_gapc[e[x]];
+                }
+                reinterpret_cast<uint32_t *>(Sr)[w4] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
+            }
+#pragma unroll
+            for (int d = LP / 2; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+            __syncwarp();
+            phase(0);
+
+            const uint32_t fw = fill_quad16(g, tmax, fc, tab_lane, repl, reinterpret_cast<const char *>(Lr + sl.offL),
+                                            reinterpret_cast<const char *>(Sr + sl.offS), slot, lane, tcm.sub4_gapgap,
+                                            tcm.spread16);
+            phase(1);
+            const bool over = fw == kOverflow16;           // the sweep's finite spread left the 15-bit window:
+            if (ln == 0) {                                 //   the narrow kernel redoes the pair with the 32-bit fill
+                if (over) p.single_list[atomicAdd(p.single_count, 1u)] = k | 0x80000000u;
+                else b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
+                s_pair[cnt + seg] = k | (fl ? 0x80000000u : 0u) | (over ? 0x40000000u : 0u);
+            }
+            if (lane == 0) { g_off[cnt / NP] = cur; g_ops[cnt / NP] = cur + dirw; g_opw[cnt / NP] = opw; }
+            if (b.cells && !over) {
+                unsigned long long c = band_cells(g, ln, LP);
+#pragma unroll
+                for (int d = LP / 2; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+                if (ln == 0) b.cells[k] = c;
+            }
+            cur += need;
+            cnt += NP;
+            pend = kNone;
+            __syncwarp();   // the staging windows are reused by the next group
+        }
+        __syncwarp();
+        if (cnt && want_out) {
+            // -------------------------------------------------------------- trace: lane = pairs `lane` and `lane + 32`
+            phase(3);
+            {
+                QWalk wk[2];
+                uint32_t kk[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int ix = lane + 32 * h;
+                    const bool live = ix < cnt && !(s_pair[ix < cnt ? ix : 0] & 0x40000000u);
+                    const uint32_t e = s_pair[live ? ix : 0];
+                    const uint32_t k = e & 0x3fffffffu;
+                    kk[h] = live ? k : 0xffffffffu;
+                    const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+                    const bool fl = e >> 31;
+                    const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+                    const int gi = (live ? ix : 0) / NP;
+                    qwalk_init(wk[h], arena + g_off[gi], ix % NP, g.q0, g.lg, g.sh, arena + g_ops[gi] + (uint32_t)(ix % NP) * g_opw[gi], live);
+                }
+                trace_two16q(wk[0], wk[1]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (kk[h] != 0xffffffffu) {
+                        s_nal[lane + 32 * h] = (uint16_t)wk[h].n;
+                        if (b.out_len) b.out_len[kk[h]] = wk[h].n;
+                        if (b.pack_cursor) pack_claim(b, kk[h], wk[h].n);
+                    }
+                }
+            }
+            __syncwarp();
+            phase(2);
+
+            // -------------------------------------------------------------- emit: warp per pair
+            if (b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_ungapped) {
+                // scratch in the (idle) string windows: op stream of the pair, per-word element counts, the median table
+                uint32_t *ops_s = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(g_off) + 640);
+                const uint32_t nws = p.seq_cap / 16u + 4u;
+                uint32_t *suf = ops_s + nws;
+                const uint8_t *med = tcm.median;
+                if ((uint32_t)(dim * dim) + 8u * nws <= NP * p.seq_cap && !b.out_ungapped) {
+                    uint32_t *ms = suf + nws;
+                    for (int i = lane; i < dim * dim / 4; i += 32) ms[i] = __ldg(reinterpret_cast<const uint32_t *>(tcm.median) + i);
+                    med = reinterpret_cast<const uint8_t *>(ms);
+                    __syncwarp();
+                }
+                for (int pe = 0; pe < cnt; ++pe) {
+                    const uint32_t e = s_pair[pe];
+                    if (e & 0x40000000u) continue;
+                    const uint32_t k = e & 0x3fffffffu;
+                    const bool fl = e >> 31;
+                    const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+                    const uint64_t oa = b.pack_cursor ? __ldcg(b.out_off_actual + k) : 0;
+                    const bool wr = oa != ~0ull;
+                    const uint64_t oo = b.pack_cursor ? oa - b.pack_base : b.out_off ? b.out_off[k] : 0;
+                    const uint32_t *ops = arena + g_ops[pe / NP] + (uint32_t)(pe % NP) * g_opw[pe / NP];
+                    if (!b.out_ungapped) {
+                        if (wr) emit_pair_q(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                                            b.out_gapped ? b.out_gapped + oo : nullptr, b.out_slot1 ? b.out_slot1 + oo : nullptr,
+                                            b.out_slot2 ? b.out_slot2 + oo : nullptr, lane, ops_s, suf);
+                        continue;
+                    }
+                    const uint32_t nu = emit_pair(tcm, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                                                  b.out_gapped && wr ? b.out_gapped + oo : nullptr,
+                                                  b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
+                                                  b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane,
+                                                  b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+                    if (b.out_ungapped && lane == 0) {
+                        b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
+                        if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        Gcur = G;
+        if (exhausted && pend == kNone && nxt == kNone) break;
+    }
+    if (p.phase_cycles && lane == 0) {
+        phase(3);
+        for (int i = 0; i < 4; ++i) atomicAdd(p.phase_cycles + i, ph[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // General-geometry kernel: one CTA per pair, any band width / string length.  Same recurrence, same
 // direction-word layout (so trace_lane / emit_pair are shared), but the diagonal values live in global
 // memory and each anti-diagonal is swept by the whole CTA with a barrier in between.  Used only for the
@@ -829,6 +1460,29 @@ cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_
 }
 
 // Host-side launchers (called from do_api.cu).
+cudaError_t launch_linear_quad(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
+        cudaError_t e = cudaFuncSetAttribute(do_linear_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        once.mark(dev);
+    }
+    do_linear_quad_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// staging bytes one pair of a four-pair group may need for strings of up to max_len elements
+uint32_t quad_seq_cap_for(int max_len)
+{
+    const int tpad = (max_len + 1 + 15) & ~15;
+    const int q0h = 16 * 8 + 1;                       // q0 / 2 <= wb / 2 <= 112
+    const int sizeL = kQuadLanes * kQuadH + tpad + q0h + 8;
+    const int sizeS = q0h + tpad + kQuadLanes * kQuadH + 8;
+    return (uint32_t)((sizeS + sizeL + 15) & ~15);
+}
+
 cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
     static DeviceOnce once;

@@ -362,3 +362,61 @@ def test_packed_fill_equals_32bit_fill(oracle_mod, gpu_ctx, monkeypatch):
         sig[:-1, -1] = indel
         o = oracle_mod.Oracle(sig)
         _check_batch(o, gpu_ctx, gpu_ctx.tcm(sig), pairs[:60] + pairs[-2:])
+
+
+def _grouped_pairs(rng, n_groups, lo=330, hi=1040):
+    """Groups of four consecutive pairs of about the same size (what the four-pairs-per-warp kernel sweeps at once),
+    with ragged members: unequal operands, related strings, ambiguity, the odd group that does not qualify."""
+    from tests.helpers import random_string
+    pairs = []
+    for gi in range(n_groups):
+        base = int(rng.integers(lo, hi))
+        for _ in range(4):
+            n1 = max(1, base + int(rng.integers(-25, 25)))
+            n2 = max(1, n1 - int(rng.integers(0, 40))) if rng.random() < 0.7 else n1
+            if gi % 11 == 10 and rng.random() < 0.3:
+                n2 = int(rng.integers(1, 200))                 # a member that breaks up its group
+            s1 = random_string(rng, n1, 5, 0.15)
+            if rng.random() < 0.5:
+                s2 = s1[:n2].copy()
+                mut = rng.random(n2) < 0.08
+                s2 = np.where(mut, random_string(rng, n2, 5, 0.15), s2).astype(np.uint8)
+            else:
+                s2 = random_string(rng, n2, 5, 0.15)
+            pairs.append((s1, s2) if rng.random() < 0.5 else (s2, s1))
+    return pairs
+
+
+@pytest.mark.parametrize("name", ["discrete", "l1", "1:2", "2:1", "weird"])
+def test_four_pairs_per_warp_kernel(oracle_mod, gpu_ctx, monkeypatch, name):
+    """do_linear_quad_kernel (bands of 129..223 diagonals, four pairs per warp) against the CPU side — the compiled
+    reference when present — and against the one-pair-per-warp kernels on the same batch."""
+    import zlib
+    import pcg_b200 as P
+    sig = tcm_matrix(name)
+    rng = np.random.default_rng(4242)
+    pairs = _grouped_pairs(rng, 150)
+    pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
+    gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=32, max_len=1100, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(sig)
+    r = P.align2d_batch(gpu_ctx, tcm, pp, want_cells=True)
+    n_launch_quad = gpu_ctx.last_kernel_ms()[1]
+    monkeypatch.setenv("PCGDO_NO_QUAD", "1")
+    gpu_ctx.reload_env()
+    try:
+        r1 = P.align2d_batch(gpu_ctx, tcm, pp, want_cells=True)
+        n_launch_single = gpu_ctx.last_kernel_ms()[1]
+    finally:
+        monkeypatch.delenv("PCGDO_NO_QUAD")
+        gpu_ctx.reload_env()
+    assert n_launch_quad == n_launch_single + 1                # the extra kernel did run
+    assert np.array_equal(r.cost, r1.cost) and np.array_equal(r.out_len, r1.out_len)
+    assert np.array_equal(r.cells, r1.cells)
+    kind = "reference" if oracle_mod.Reference.available() else "port"
+    cost, out_len, crc = oracle_mod.cpu_align2d_full(sig, pp, max(1, min(32, len(os.sched_getaffinity(0)))), kind)
+    assert np.array_equal(r.cost, cost) and np.array_equal(r.out_len, out_len)
+    for k in range(pp.n):
+        o, ln = int(pp.out_off[k]), int(r.out_len[k])
+        got = (zlib.crc32(r.gapped[o:o + ln].tobytes()), zlib.crc32(r.slot1[o:o + ln].tobytes()),
+               zlib.crc32(r.slot2[o:o + ln].tobytes()))
+        assert got == tuple(int(x) for x in crc[k]), (k, len(pairs[k][0]), len(pairs[k][1]))
