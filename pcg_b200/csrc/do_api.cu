@@ -493,10 +493,10 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     CK(cudaMemcpyAsync(h_cnt, p.counter, 36, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (p.phase_cycles) {
-        unsigned long long h_ph[4] = {0};
-        CK(cudaMemcpy(h_ph, p.phase_cycles, 32, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[pcgdo] quad kernel warp-cycles: stage %llu fill %llu trace %llu emit %llu; singles %u\n", h_ph[0], h_ph[1],
-                h_ph[2], h_ph[3], h_cnt[5]);
+        unsigned long long h_ph[6] = {0};
+        CK(cudaMemcpy(h_ph, p.phase_cycles, 48, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[pcgdo] quad kernel warp-cycles: stage %llu fill %llu trace %llu emit %llu prep %llu post %llu; singles %u\n", h_ph[0], h_ph[1],
+                h_ph[2], h_ph[3], h_ph[4], h_ph[5], h_cnt[5]);
     }
     // pairs the warp kernels could not hold (band wider than 1023 diagonals, strings longer than the
     // staging window, scratch larger than the arena; plus the wide queue when that kernel is disabled)

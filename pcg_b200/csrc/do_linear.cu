@@ -387,62 +387,108 @@ __host__ __device__ inline SeqLayout seq_layout_quad(const Geom &g, int tmax)
 // per lane and iteration)
 __device__ __forceinline__ uint32_t s_entry(uint32_t e, bool repl) { return repl ? (((e >> 1) << 7) | ((e & 1u) << 1)) : (e << 1); }
 
+// The 14 packed updates of an iteration (7 even-diagonal registers, then 7 odd ones) are numbered f = 0 .. 13.  The two
+// table fetches of update f + kQuadDist are issued right before the arithmetic of update f (they depend on the string
+// windows only, not on cell values), into a ring of kQuadDist register pairs: every fetch has kQuadDist updates of
+// arithmetic between issue and use — with 4 warps per scheduler nothing else would cover the shared-memory latency —
+// and each warp's instruction stream alternates between the ALU pipe (min-plus) and the FMA / LSU pipes (addresses,
+// fetches) instead of running them in separate bursts.
+constexpr int kQuadDist = 7;
+
+// issue the fetches of update g (0 .. 13 in the frame of iteration tt; 14 .. 27 = update g - 14 of iteration tt + 1)
+template <int G>
+__device__ __forceinline__ void quad_fetch(int tt, const uint32_t (&lw)[kQuadH], const uint32_t (&sw)[kQuadH], const FillConst fc,
+                                           uint32_t &lo, uint32_t &hi)
+{
+    constexpr int H = kQuadH, Q = H / 2;
+    constexpr int g = G % 14, odd = g >= 7 ? 1 : 0, u = g - 7 * odd;
+    const int t2 = tt + G / 14;
+    lo = lds_u16(imad(lw[(t2 - u + 2 * H) % H], fc.lstride, sw[(t2 + u + odd) % H]));
+    hi = lds_u16(imad(lw[(t2 - u - Q + 2 * H) % H], fc.lstride, sw[(t2 + u + Q + odd) % H]));
+}
+
+// (a & b) | c as ONE LOP3: ptxas splits the C expression in two for about half of the updates
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// s_entry without the branch: e * c1 - (e & 1) * c2 with (c1, c2) = (64, 62) for the replicated table, (2, 0) otherwise
+__device__ __forceinline__ uint32_t s_entry2(uint32_t e, uint32_t c1, uint32_t c2neg, uint32_t base)
+{
+    return imad(e & 1u, c2neg, imad(e, c1, base));
+}
+
 template <bool TAIL>
 __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[kQuadH], const uint32_t (&penc)[kQuadH], uint32_t (&dw)[kQuadH],
-                                             uint32_t (&lw)[kQuadH], uint32_t (&sw)[kQuadH], const FillConst fc,
-                                             uint32_t tab_lane, bool repl, const char *&lptr, const char *&sptr,
-                                             int n_iter, uint32_t *&out)
+                                             uint32_t (&lw)[kQuadH], uint32_t (&sw)[kQuadH], uint32_t (&p_lo)[kQuadDist],
+                                             uint32_t (&p_hi)[kQuadDist], const FillConst fc, uint32_t tab_lane, uint32_t sc1, uint32_t sc2,
+                                             const char *&lptr, const char *&sptr, int n_iter, uint32_t *&out)
 {
-    constexpr int H = kQuadH, Q = H / 2, CH = 8, U = H / 2;
+    constexpr int H = kQuadH, CH = 8, D = kQuadDist;
+    static_assert(D >= 1 && D <= 7, "fetch distance");
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r;
-        // All 28 table fetches of the iteration go out first — they depend on the string windows only, not on the cell
-        // values — so that their latency is paid once per iteration, behind the first half step's arithmetic, and not
-        // once per cell (with 4 warps per scheduler nothing else would cover it).
-        const uint32_t s_new = s_entry(ld_u8(sptr + r), repl) + tab_lane;
+        const uint32_t s_new = s_entry2(ld_u8(sptr + r), sc1, sc2, tab_lane);
         const uint32_t l_new = ld_u8(lptr + r);
-        uint32_t e_lo[U], e_hi[U], o_lo[U], o_hi[U];
+        uint32_t edge = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            e_lo[u] = lds_u16(imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u) % H]));
-            e_hi[u] = lds_u16(imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q) % H]));
-        }
-        sw[tt] = s_new;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            o_lo[u] = lds_u16(imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u + 1) % H]));
-            o_hi[u] = lds_u16(imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q + 1) % H]));
-        }
-        lw[(tt + 1) % H] = l_new;
-        // ---- even diagonals (registers with even m): anti-diagonal s = 2t
-        const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
-        const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);
-#pragma unroll
-        for (int m = 0; m < H; m += 2) {
-            const int u = m / 2;
-            const uint32_t left = (m == 0) ? left0 : R[m > 0 ? m - 1 : 0];
-            const uint32_t sub2 = imad(e_hi[u], fc.k64k, e_lo[u]);
-            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
-            const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
-            R[m] = (mn & 0xfffcfffcu) | penc[m];
-            const uint32_t c2 = mn & 0x00030003u;
-            dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
-        }
-        // ---- odd diagonals: anti-diagonal s = 2t + 1
-        const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
-        const uint32_t upl = __funnelshift_r(R[0], next, 16);
-#pragma unroll
-        for (int m = 1; m < H; m += 2) {
-            const int u = (m - 1) / 2;
-            const uint32_t up = (m == H - 1) ? upl : R[m + 1 < H ? m + 1 : H - 1];
-            const uint32_t sub2 = imad(o_hi[u], fc.k64k, o_lo[u]);
-            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
-            const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
-            R[m] = (mn & 0xfffcfffcu) | penc[m];
-            const uint32_t c2 = mn & 0x00030003u;
-            dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
+        for (int f = 0; f < 14; ++f) {
+            // the window slots are replaced once nothing issued later still wants the old element: the lesser string's
+            // before the first odd-diagonal fetch of this iteration, the longer string's before the first fetch of the next
+            if (f + D == 7) sw[tt] = s_new;
+            if (f + D == 14) lw[(tt + 1) % H] = l_new;
+            const uint32_t sub2 = imad(p_hi[f % D], fc.k64k, p_lo[f % D]);
+            switch (f + D) {        // (compile-time: the loop is unrolled)
+                case 1: quad_fetch<1>(tt, lw, sw, fc, p_lo[1 % D], p_hi[1 % D]); break;
+                case 2: quad_fetch<2>(tt, lw, sw, fc, p_lo[2 % D], p_hi[2 % D]); break;
+                case 3: quad_fetch<3>(tt, lw, sw, fc, p_lo[3 % D], p_hi[3 % D]); break;
+                case 4: quad_fetch<4>(tt, lw, sw, fc, p_lo[4 % D], p_hi[4 % D]); break;
+                case 5: quad_fetch<5>(tt, lw, sw, fc, p_lo[5 % D], p_hi[5 % D]); break;
+                case 6: quad_fetch<6>(tt, lw, sw, fc, p_lo[6 % D], p_hi[6 % D]); break;
+                case 7: quad_fetch<7>(tt, lw, sw, fc, p_lo[7 % D], p_hi[7 % D]); break;
+                case 8: quad_fetch<8>(tt, lw, sw, fc, p_lo[8 % D], p_hi[8 % D]); break;
+                case 9: quad_fetch<9>(tt, lw, sw, fc, p_lo[9 % D], p_hi[9 % D]); break;
+                case 10: quad_fetch<10>(tt, lw, sw, fc, p_lo[10 % D], p_hi[10 % D]); break;
+                case 11: quad_fetch<11>(tt, lw, sw, fc, p_lo[11 % D], p_hi[11 % D]); break;
+                case 12: quad_fetch<12>(tt, lw, sw, fc, p_lo[12 % D], p_hi[12 % D]); break;
+                case 13: quad_fetch<13>(tt, lw, sw, fc, p_lo[13 % D], p_hi[13 % D]); break;
+                case 14: quad_fetch<14>(tt, lw, sw, fc, p_lo[14 % D], p_hi[14 % D]); break;
+                case 15: quad_fetch<15>(tt, lw, sw, fc, p_lo[15 % D], p_hi[15 % D]); break;
+                case 16: quad_fetch<16>(tt, lw, sw, fc, p_lo[16 % D], p_hi[16 % D]); break;
+                case 17: quad_fetch<17>(tt, lw, sw, fc, p_lo[17 % D], p_hi[17 % D]); break;
+                case 18: quad_fetch<18>(tt, lw, sw, fc, p_lo[18 % D], p_hi[18 % D]); break;
+                case 19: quad_fetch<19>(tt, lw, sw, fc, p_lo[19 % D], p_hi[19 % D]); break;
+                default: quad_fetch<20>(tt, lw, sw, fc, p_lo[20 % D], p_hi[20 % D]); break;
+            }
+            if (f < 7) {            // ---- even diagonals (registers with even m): anti-diagonal s = 2t
+                const int m = 2 * f;
+                if (f == 0) {
+                    const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
+                    edge = __funnelshift_l(prev, R[H - 1], 16);      // (own diag H-1) << 16 | (left lane's diag B-1)
+                }
+                const uint32_t left = (m == 0) ? edge : R[m > 0 ? m - 1 : 0];
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
+                const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
+                R[m] = and_or(mn, 0xfffcfffcu, penc[m]);
+                const uint32_t c2 = mn & 0x00030003u;
+                dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
+            } else {                // ---- odd diagonals: anti-diagonal s = 2t + 1
+                const int m = 2 * (f - 7) + 1;
+                if (f == 7) {
+                    const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
+                    edge = __funnelshift_r(R[0], next, 16);          // (right lane's diag 0) << 16 | (own diag H)
+                }
+                const uint32_t up = (m == H - 1) ? edge : R[m + 1 < H ? m + 1 : H - 1];
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
+                const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
+                R[m] = and_or(mn, 0xfffcfffcu, penc[m]);
+                const uint32_t c2 = mn & 0x00030003u;
+                dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
+            }
         }
         if (r == CH - 1 || (TAIL && r == n_iter - 1)) {
             const int sh = 2 * (CH - 1 - r);          // left-align a partial group
@@ -520,16 +566,25 @@ __device__ __noinline__ uint32_t fill_quad16(const Geom g, int tmax, const FillC
     const char *lptr = Lb + (I0 + 1);
     const char *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
+    const uint32_t sc1 = repl ? 64u : 2u, sc2 = repl ? (uint32_t)-62 : 0u;
+    uint32_t p_lo[kQuadDist], p_hi[kQuadDist];
+    quad_fetch<0>(0, lw, sw, fc, p_lo[0], p_hi[0]);
+    if constexpr (kQuadDist > 1) quad_fetch<1 % 14>(0, lw, sw, fc, p_lo[1 % kQuadDist], p_hi[1 % kQuadDist]);
+    if constexpr (kQuadDist > 2) quad_fetch<2 % 14>(0, lw, sw, fc, p_lo[2 % kQuadDist], p_hi[2 % kQuadDist]);
+    if constexpr (kQuadDist > 3) quad_fetch<3 % 14>(0, lw, sw, fc, p_lo[3 % kQuadDist], p_hi[3 % kQuadDist]);
+    if constexpr (kQuadDist > 4) quad_fetch<4 % 14>(0, lw, sw, fc, p_lo[4 % kQuadDist], p_hi[4 % kQuadDist]);
+    if constexpr (kQuadDist > 5) quad_fetch<5 % 14>(0, lw, sw, fc, p_lo[5 % kQuadDist], p_hi[5 % kQuadDist]);
+    if constexpr (kQuadDist > 6) quad_fetch<6 % 14>(0, lw, sw, fc, p_lo[6 % kQuadDist], p_hi[6 % kQuadDist]);
     const int nfull = tmax / 8, rem = tmax % 8;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
         if (c && c % 4 == 0) ok = rebase16q(R, total_shift, spread_limit) && ok;       // every 32 iterations
-        run_chunk16q<false>(R, penc, dw, lw, sw, fc, tab_lane, repl, lptr, sptr, 8, out);
+        run_chunk16q<false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, 8, out);
     }
     if (rem) {
         if (nfull && nfull % 4 == 0) ok = rebase16q(R, total_shift, spread_limit) && ok;
-        run_chunk16q<true>(R, penc, dw, lw, sw, fc, tab_lane, repl, lptr, sptr, rem, out);
+        run_chunk16q<true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, rem, out);
     }
     ok = rebase16q(R, total_shift, spread_limit) && ok;
     const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
@@ -594,6 +649,9 @@ __device__ __forceinline__ void trace_two16q(QWalk &a, QWalk &b)
         if (lb) { b.w = wb >> (16 * (hb & 1u)); b.sft = 2 * (7 - (tb & 7)); }
         qwalk_step(a);
         qwalk_step(b);
+        // a second move from the same word where there is one (runs of ALIGN): fewer round trips per alignment
+        if (a.sft != 16) qwalk_step(a);
+        if (b.sft != 16) qwalk_step(b);
     }
     if (a.n & 15) a.ops[a.n >> 4] = a.acc;
     if (b.n & 15) b.ops[b.n >> 4] = b.acc;
@@ -1082,6 +1140,8 @@ __device__ __forceinline__ bool first_is_long_seg(const uint8_t *p1, uint32_t n1
     return res;
 }
 
+// PROFILE: per-phase cycle counts into p.phase_cycles (an instantiation of its own: the counters cost registers)
+template <bool PROFILE>
 __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearParams p)
 {
     constexpr int NP = kQuadPairs, LP = kQuadLanes;
@@ -1121,9 +1181,9 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
     // (latency-bound) at the same time.  Experiment (quad_flags bit 0): a first batch of a different size per warp spreads
     // the phases for good — measured SLOWER (67.5 -> 77.9 ms on config 2), so off by default.
     int Gcur = (p.quad_flags & 1u) ? NP * (1 + (warp * (G / NP - 1)) / (nwarps > 1 ? nwarps - 1 : 1)) : G;
-    long long ph_t = p.phase_cycles ? clock64() : 0;
-    unsigned long long ph[4] = {0, 0, 0, 0};
-    auto phase = [&](int i) { if (p.phase_cycles) { const long long t = clock64(); ph[i] += (unsigned long long)(t - ph_t); ph_t = t; } };
+    long long ph_t = PROFILE ? clock64() : 0;
+    unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
+    auto phase = [&](int i) { if constexpr (PROFILE) { const long long t = clock64(); ph[i] += (unsigned long long)(t - ph_t); ph_t = t; } };
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.quad_arena_words;
     unsigned int *counter = p.counter + 4;
@@ -1198,39 +1258,51 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
             uint32_t *slot = arena + cur;
 
             // stage the segment's pair; sum the indel costs that are folded out of the cell values
-            // (four bytes per lane and step, four steps in flight: the loads come from HBM and only 16 warps hide them)
+            // (four bytes per lane and step, four steps in flight; the loads are unconditional — clamped addresses — because
+            // ptxas keeps a predicated load next to its use, and these come from L2 / HBM with only 16 warps to hide them)
             uint8_t *Lr = win, *Sr = win + sl.sizeL;
             uint32_t csum = 0;
-            phase(3);
+            phase(4);
+            {
+                const int nL = g.lg - 1, nS = g.sh - 1;          // >= 8 (eligibility)
 #pragma unroll 4
-            for (int w4 = ln; w4 < sl.sizeL / 4; w4 += LP) {
-                uint32_t e[4];
+                for (int w4 = ln; w4 < sl.sizeL / 4; w4 += LP) {
+                    uint32_t e[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const int i = 4 * w4 + x - sl.offL;
-                    e[x] = (i > 0 && i < g.lg) ? (uint32_t)__ldg(pL + i - 1) & emask : (i == 0 ? tcm.gap : 0u);
-                }
+                    for (int x = 0; x < 4; ++x) {
+                        const int i = 4 * w4 + x - sl.offL - 1;
+                        e[x] = __ldg(pL + min(max(i, 0), nL - 1));
+                    }
+                    uint32_t word = 0;
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const int i = 4 * w4 + x - sl.offL;
-                    if (i > 0 && i < g.lg) csum += s_cgap[e[x]];
+                    for (int x = 0; x < 4; ++x) {
+                        const int i = 4 * w4 + x - sl.offL - 1;
+                        uint32_t v = e[x] & emask;
+                        if (i >= 0 && i < nL) csum += s_cgap[v];
+                        else v = (i == -1) ? tcm.gap : 0u;
+                        word |= v << (8 * x);
+                    }
+                    reinterpret_cast<uint32_t *>(Lr)[w4] = word;
                 }
-                reinterpret_cast<uint32_t *>(Lr)[w4] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
-            }
 #pragma unroll 4
-            for (int w4 = ln; w4 < sl.sizeS / 4; w4 += LP) {
-                uint32_t e[4];
+                for (int w4 = ln; w4 < sl.sizeS / 4; w4 += LP) {
+                    uint32_t e[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const int j = 4 * w4 + x - sl.offS;
-                    e[x] = (j > 0 && j < g.sh) ? (uint32_t)__ldg(pS + j - 1) & emask : (j == 0 ? tcm.gap : 0u);
-                }
+                    for (int x = 0; x < 4; ++x) {
+                        const int j = 4 * w4 + x - sl.offS - 1;
+                        e[x] = __ldg(pS + min(max(j, 0), nS - 1));
+                    }
+                    uint32_t word = 0;
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const int j = 4 * w4 + x - sl.offS;
-                    if (j > 0 && j < g.sh) csum += s_gapc[e[x]];
+                    for (int x = 0; x < 4; ++x) {
+                        const int j = 4 * w4 + x - sl.offS - 1;
+                        uint32_t v = e[x] & emask;
+                        if (j >= 0 && j < nS) csum += s_gapc[v];
+                        else v = (j == -1) ? tcm.gap : 0u;
+                        word |= v << (8 * x);
+                    }
+                    reinterpret_cast<uint32_t *>(Sr)[w4] = word;
                 }
-                reinterpret_cast<uint32_t *>(Sr)[w4] = e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24);
             }
 #pragma unroll
             for (int d = LP / 2; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
@@ -1258,11 +1330,12 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
             cnt += NP;
             pend = kNone;
             __syncwarp();   // the staging windows are reused by the next group
+            phase(5);
         }
         __syncwarp();
         if (cnt && want_out) {
             // -------------------------------------------------------------- trace: lane = pairs `lane` and `lane + 32`
-            phase(3);
+            phase(5);
             {
                 QWalk wk[2];
                 uint32_t kk[2];
@@ -1315,6 +1388,13 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
                     const bool wr = oa != ~0ull;
                     const uint64_t oo = b.pack_cursor ? oa - b.pack_base : b.out_off ? b.out_off[k] : 0;
                     const uint32_t *ops = arena + g_ops[pe / NP] + (uint32_t)(pe % NP) * g_opw[pe / NP];
+                    if (pe + 1 < cnt) {          // the next pair's strings: staged long ago, on their way back to L2 now
+                        const uint32_t kn = s_pair[pe + 1] & 0x3fffffffu;
+                        const uint8_t *q = b.elems + ((lane & 16) ? b.off2[kn] : b.off1[kn]);
+                        const uint32_t m = (lane & 16) ? b.len2[kn] : b.len1[kn];
+                        const uint32_t o = 128u * (uint32_t)(lane & 15);
+                        if (m && o < m + 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + min(o, m - 1u)));
+                    }
                     if (!b.out_ungapped) {
                         if (wr) emit_pair_q(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
                                             b.out_gapped ? b.out_gapped + oo : nullptr, b.out_slot1 ? b.out_slot1 + oo : nullptr,
@@ -1333,13 +1413,14 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
                 }
             }
             __syncwarp();
+            phase(3);
         }
         Gcur = G;
         if (exhausted && pend == kNone && nxt == kNone) break;
     }
-    if (p.phase_cycles && lane == 0) {
-        phase(3);
-        for (int i = 0; i < 4; ++i) atomicAdd(p.phase_cycles + i, ph[i]);
+    if (PROFILE && lane == 0) {
+        phase(4);
+        for (int i = 0; i < 6; ++i) atomicAdd(p.phase_cycles + i, ph[i]);
     }
 }
 
@@ -1465,11 +1546,14 @@ cudaError_t launch_linear_quad(const LinearParams &p, int grid, int block, size_
     static DeviceOnce once;
     int dev = 0;
     if (once.pending(&dev)) {
-        cudaError_t e = cudaFuncSetAttribute(do_linear_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(do_linear_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(do_linear_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         once.mark(dev);
     }
-    do_linear_quad_kernel<<<grid, block, smem_bytes, stream>>>(p);
+    if (p.phase_cycles) do_linear_quad_kernel<true><<<grid, block, smem_bytes, stream>>>(p);
+    else                do_linear_quad_kernel<false><<<grid, block, smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 

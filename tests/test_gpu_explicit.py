@@ -256,5 +256,9 @@ def test_pipelined_host_path_for_large_alphabets(gpu_ctx, monkeypatch, a):
     monkeypatch.delenv("PCGDO_HOST_CHUNK_PAIRS")
     gpu_ctx.reload_env()
     for x, y in ((plain.cost, piped.cost), (plain.out_len, piped.out_len), (plain.cells, piped.cells),
-                 (plain.final_offset, piped.final_offset), (plain.median, piped.median), (plain.a1, piped.a1), (plain.a2, piped.a2)):
+                 (plain.final_offset, piped.final_offset)):
         assert np.array_equal(x, y)
+    # the strings pair by pair: the one-shot path copies the whole output arrays back, unwritten padding behind the last
+    # pair included (whatever the device buffer held), the pipelined one only what its chunks wrote
+    for k in range(len(pairs)):
+        assert all(np.array_equal(u, v) for u, v in zip(plain.pair(k)[1:], piped.pair(k)[1:])), k
