@@ -345,6 +345,33 @@ int  pcgdo_forest_set_trees(pcgdo_ctx *ctx, pcgdo_forest *forest, const int32_t 
  * sweep's GCUPS / roofline figures. */
 int  pcgdo_forest_cells(pcgdo_ctx *ctx, pcgdo_forest *forest, uint64_t *cells_out);
 
+/* ---------------------------------------------------------------- pre-order pass: final ("implied") alignments
+ * Replaces directOptimizationPreorder / initializeRoot / updateFromParent / deriveImpliedAlignment / lexicallyDisambiguate
+ * (lib/core/analysis/src/Analysis/Parsimony/Dynamic/DirectOptimization/Internal.hs:148-286) for rooted binary trees over
+ * dense-TCM alphabets (one byte per ambiguity set): from the post-order CONTEXTS of every node — (median, left, right)
+ * strings with gaps, a leaf's being (s, s, s) — to the final alignment of every node, all of the root's length, plus its
+ * single (lexical) disambiguation.  Contexts are uploaded once and stay on the device; the descent is one launch per depth
+ * over all trees x characters (do_preorder.cu).  Node ids and `children` as in pcgdo_forest_create.
+ *   set_contexts  HOST arrays: node v of column (tree t, character c) = med / left / right [off[i] .. off[i] + len[i]),
+ *                 i = (t * n_chars + c) * (2 * n_taxa - 1) + v; len[i] = PCGDO_MISSING for a Missing character
+ *   run           alphabet = symbols including the gap (<= 8); PCGDO_ERR_OVERFLOW when an edge reaches the reference's
+ *                 "Impossible happened in 'deriveImpliedAlignment'" (the contexts do not belong to the tree)
+ *   get           one node's final alignment, pcgdo_preorder_length bytes per plane (any output may be NULL)
+ *   device_ptr    the resident result: plane p (0 median, 1 left, 2 right, 3 single) of node v of column col starts at
+ *                 base + off[col] + (v * 4 + p) * round4(len[col]), off being the running sum of
+ *                 (2 * n_taxa - 1) * 4 * round4(len) over the non-Missing columns before col */
+typedef struct pcgdo_preorder pcgdo_preorder;
+int  pcgdo_preorder_create(pcgdo_ctx *ctx, uint32_t n_trees, uint32_t n_taxa, uint32_t n_chars, const int32_t *children,
+                           pcgdo_preorder **out);
+void pcgdo_preorder_destroy(pcgdo_ctx *ctx, pcgdo_preorder *pre);
+int  pcgdo_preorder_set_contexts(pcgdo_ctx *ctx, pcgdo_preorder *pre, const uint8_t *med, const uint8_t *left,
+                                 const uint8_t *right, size_t total_bytes, const uint64_t *off, const uint32_t *len);
+int  pcgdo_preorder_run(pcgdo_ctx *ctx, pcgdo_preorder *pre, int alphabet, void *cuda_stream);
+uint32_t pcgdo_preorder_length(const pcgdo_preorder *pre, uint32_t tree, uint32_t character);
+int  pcgdo_preorder_get(pcgdo_ctx *ctx, pcgdo_preorder *pre, uint32_t tree, uint32_t character, uint32_t node,
+                        uint8_t *med_out, uint8_t *left_out, uint8_t *right_out, uint8_t *single_out, int *missing_out);
+void *pcgdo_preorder_device_ptr(pcgdo_preorder *pre);
+
 /* ---------------------------------------------------------------- several GPUs in one process
  * north_star item (4) as a LIBRARY feature: a caller that is one process (PCG is) hands the library a device list; forests
  * are sharded by CHARACTER BLOCKS across the devices (every device keeps all node strings of its characters resident and

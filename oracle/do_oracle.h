@@ -107,6 +107,22 @@ int64_t oracle_reroot_trial(const oracle_tcm_t *t, uint32_t n_taxa, const int32_
                             int32_t *edge_u, int32_t *edge_v, int64_t *edge_cost, int64_t *edge_local, uint64_t *cells,
                             const uint32_t *trial, size_t trial_len, int64_t *edge_trial);
 
+/* Pre-order pass: implied alignments (preorder_oracle.c; PARITY UNPINNED, see its header).
+ * oracle_derive_implied_alignment = deriveImpliedAlignment (DO/Internal.hs:236-286): the child's final alignment from the
+ * parent's final alignment (pam/pal/par, n elements), the parent's context (left / right parts, np) and the child's
+ * context (nc); 0, or -1 where the reference raises "Impossible happened".
+ * oracle_preorder_tree: post-order contexts and final alignments of every node of one rooted tree (see the .c file). */
+int  oracle_derive_implied_alignment(int is_left_child, uint32_t gap,
+                                     const uint32_t *pam, const uint32_t *pal, const uint32_t *par, size_t n,
+                                     const uint32_t *pcl, const uint32_t *pcr, size_t np,
+                                     const uint32_t *ccm, const uint32_t *ccl, const uint32_t *ccr, size_t nc,
+                                     uint32_t *om, uint32_t *ol, uint32_t *orr);
+void oracle_lexically_disambiguate(const uint32_t *med, size_t n, int a, uint32_t *out);
+int  oracle_preorder_tree(const oracle_tcm_t *t, uint32_t n_taxa, const int32_t *children,
+                          const uint32_t *const *leaf, const size_t *leaf_len, size_t cap,
+                          uint32_t *ctx_m, uint32_t *ctx_l, uint32_t *ctx_r, uint32_t *ctx_len,
+                          uint32_t *ia_m, uint32_t *ia_l, uint32_t *ia_r, uint32_t *ia_len, uint32_t *single);
+
 /* Alphabets of more than 32 symbols (hs_wide.c): an element is W = ceil(a/32) consecutive words, lengths count elements. */
 int64_t oracle_haskell_do_w(int dialect, int metric_kind, const uint32_t *sigma, int a,
                             const uint32_t *in1, size_t n1, const uint32_t *in2, size_t n2,

@@ -171,6 +171,38 @@ def reroot(oracle: "Oracle", children, leaves, trial=None):
     return int(best), list(zip(eu.tolist(), ev.tolist())), ec, el, et
 
 
+def preorder_tree(oracle: "Oracle", children, leaves):
+    """Post-order contexts and pre-order implied alignments of one rooted tree / one character (preorder_oracle.c).
+    Returns (root id, contexts, implied alignments, single disambiguations): dicts node -> (n, 3) uint32 array
+    (median, left, right) / (n,) array, None for a Missing character."""
+    lib = oracle.lib
+    lib.oracle_preorder_tree.restype = C.c_int
+    lib.oracle_preorder_tree.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 9
+    ch = np.ascontiguousarray(np.asarray(children, np.int32))
+    n_taxa = ch.shape[0] + 1
+    n_nodes = 2 * n_taxa - 1
+    arrs = [_as_u32(x) for x in leaves]
+    ptrs = (C.c_void_p * n_taxa)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_size_t * n_taxa)(*[len(a) for a in arrs])
+    cap = sum(len(a) for a in arrs) + 2 * n_nodes + 8
+    bufs = [np.zeros(n_nodes * cap, np.uint32) for _ in range(7)]
+    ctx_len, ia_len = np.zeros(n_nodes, np.uint32), np.zeros(n_nodes, np.uint32)
+    cm, cl, cr, im, il, ir, sg = bufs
+    root = lib.oracle_preorder_tree(oracle.t, n_taxa, ch.ctypes.data, ptrs, lens, cap, cm.ctypes.data, cl.ctypes.data,
+                                    cr.ctypes.data, ctx_len.ctypes.data, im.ctypes.data, il.ctypes.data, ir.ctypes.data,
+                                    ia_len.ctypes.data, sg.ctypes.data)
+    if root < 0:
+        raise RuntimeError(f"oracle_preorder_tree failed: {root}")
+    MISSING = 0xffffffff
+
+    def triple(a, b, c, v, n):
+        return None if n == MISSING else np.stack([a[v * cap:v * cap + n], b[v * cap:v * cap + n], c[v * cap:v * cap + n]], axis=1)
+    ctxs = {v: triple(cm, cl, cr, v, int(ctx_len[v])) for v in range(n_nodes)}
+    ias = {v: triple(im, il, ir, v, int(ia_len[v])) for v in range(n_nodes)}
+    single = {v: None if int(ia_len[v]) == MISSING else sg[v * cap:v * cap + int(ia_len[v])].copy() for v in range(n_nodes)}
+    return root, ctxs, ias, single
+
+
 def reroot_haskell(dialect: int, a: int, children, leaves, sigma=None, metric_kind=None):
     """Re-rooting pass with every alignment by a restated Haskell dialect (alphabets > 8).
     metric_kind: None -> 0 (discrete) without sigma / 1 (explicit) with; 2 = L1 norm (firstLinearNormPairwiseLogic).

@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = [
     "pcgdo_multi_configure", "pcgdo_multi_tcm_create", "pcgdo_multi_tcm_destroy",
     "pcgdo_mforest_create", "pcgdo_mforest_destroy", "pcgdo_mforest_set_leaves", "pcgdo_mforest_set_trees",
     "pcgdo_mforest_enable_rerooting", "pcgdo_mforest_score", "pcgdo_mforest_block", "pcgdo_multi_align2d_batch_host",
+    "pcgdo_preorder_create", "pcgdo_preorder_destroy", "pcgdo_preorder_set_contexts", "pcgdo_preorder_run",
+    "pcgdo_preorder_length", "pcgdo_preorder_get", "pcgdo_preorder_device_ptr",
 ]
 
 
@@ -176,6 +178,18 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     L.pcgdo_configure_env.argtypes = [C.c_void_p]
     L.pcgdo_forest_set_trees.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.pcgdo_forest_cells.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.pcgdo_preorder_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pcgdo_preorder_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.pcgdo_preorder_destroy.restype = None
+    L.pcgdo_preorder_set_contexts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_void_p, C.c_void_p]
+    L.pcgdo_preorder_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.pcgdo_preorder_length.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.pcgdo_preorder_length.restype = C.c_uint32
+    L.pcgdo_preorder_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 4 + \
+                                    [C.POINTER(C.c_int)]
+    L.pcgdo_preorder_device_ptr.argtypes = [C.c_void_p]
+    L.pcgdo_preorder_device_ptr.restype = C.c_void_p
     L.pcgdo_multi_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
     L.pcgdo_multi_destroy.argtypes = [C.c_void_p]
     L.pcgdo_multi_destroy.restype = None
@@ -527,6 +541,73 @@ class Forest:
 
 
 REDUCE_HOST, REDUCE_PEER, REDUCE_NCCL = 0, 1, 2
+
+
+class Preorder:
+    """Pre-order pass on the device (``pcgdo_preorder_*``, do_preorder.cu): final alignments of every node of n_trees rooted
+    trees x n_chars characters from their post-order contexts.  ``contexts[t][c]``: dict / sequence node -> (n, 3) uint8
+    array (median, left, right) or None (Missing); leaves included ((s, s, s))."""
+
+    def __init__(self, ctx: Context, children, n_taxa: int, n_chars: int):
+        ch = np.ascontiguousarray(np.asarray(children, dtype=np.int32))
+        if ch.ndim == 2:
+            ch = ch[None]
+        assert ch.shape[1:] == (n_taxa - 1, 2)
+        self.ctx, self.n_trees, self.n_taxa, self.n_chars = ctx, ch.shape[0], n_taxa, n_chars
+        self.n_nodes = 2 * n_taxa - 1
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.pcgdo_preorder_create(ctx.h, self.n_trees, n_taxa, n_chars, ch.ctypes.data, C.byref(self.h)),
+                  "pcgdo_preorder_create")
+
+    def set_contexts(self, contexts) -> None:
+        n = self.n_trees * self.n_chars * self.n_nodes
+        off, ln = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        parts, at, i = [], 0, 0
+        for t in range(self.n_trees):
+            for c in range(self.n_chars):
+                col = contexts[t][c]
+                for v in range(self.n_nodes):
+                    x = col[v]
+                    if x is None:
+                        ln[i] = MISSING
+                    else:
+                        x = np.ascontiguousarray(np.asarray(x, np.uint8).reshape(-1, 3))
+                        off[i], ln[i] = at, len(x)
+                        parts.append(x)
+                        at += len(x)
+                    i += 1
+        allc = np.concatenate(parts, axis=0) if parts else np.zeros((0, 3), np.uint8)
+        m, l, r = (np.ascontiguousarray(allc[:, k]) for k in range(3))
+        self.ctx.check(self.ctx.lib.pcgdo_preorder_set_contexts(self.ctx.h, self.h, m.ctypes.data, l.ctypes.data, r.ctypes.data,
+                                                                at, off.ctypes.data, ln.ctypes.data),
+                       "pcgdo_preorder_set_contexts")
+
+    def run(self, alphabet: int, stream: int = 0) -> None:
+        self.ctx.check(self.ctx.lib.pcgdo_preorder_run(self.ctx.h, self.h, alphabet, C.c_void_p(stream)), "pcgdo_preorder_run")
+
+    def node(self, tree: int, character: int, node: int):
+        """((n, 3) final alignment, (n,) single disambiguation), or (None, None) for a Missing character."""
+        n = int(self.ctx.lib.pcgdo_preorder_length(self.h, tree, character))
+        if n == MISSING:
+            return None, None
+        bufs = [np.zeros(n, np.uint8) for _ in range(4)]
+        miss = C.c_int(0)
+        self.ctx.check(self.ctx.lib.pcgdo_preorder_get(self.ctx.h, self.h, tree, character, node, *[b.ctypes.data for b in bufs],
+                                                       C.byref(miss)), "pcgdo_preorder_get")
+        if miss.value:
+            return None, None
+        return np.stack(bufs[:3], axis=1), bufs[3]
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.ctx.lib.pcgdo_preorder_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Multi:

@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpcgdo_b200.so")
-SOURCES = ["do_linear.cu", "do_api.cu", "do_forest.cu", "do_affine.cu", "do_metric.cu", "do_explicit.cu", "do_peak.cu", "do_multi.cu", "do_tcm.cpp"]
-HEADERS = ["do_device.cuh", "do_host.h", "do_ctx.h", "do_metric.cuh", "do_explicit.h", os.path.join("..", "..", "include", "pcg_do_b200.h")]
+SOURCES = ["do_linear.cu", "do_api.cu", "do_forest.cu", "do_affine.cu", "do_metric.cu", "do_explicit.cu", "do_peak.cu", "do_multi.cu", "do_preorder.cu", "do_tcm.cpp"]
+HEADERS = ["do_device.cuh", "do_host.h", "do_ctx.h", "do_metric.cuh", "do_explicit.h", "do_pack16.cuh", os.path.join("..", "..", "include", "pcg_do_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-lpthread", "-ldl"]
 

@@ -366,64 +366,85 @@ __device__ __forceinline__ uint32_t x_ldg_u16(const char *base, uint32_t off)
 // "no instruction".  A direction word still covers 8 iterations: `phase` says which half of it a 4-iteration chunk is.
 __host__ __device__ constexpr int x_chunk_len(int B) { return B <= 8 ? 16 : (B == 16 ? 8 : 4); }
 
+// The H packed updates of an iteration (H / 2 even-diagonal registers, then H / 2 odd ones) are numbered f = 0 .. H-1.
+// The two table fetches of update f + D are issued right before the arithmetic of update f, into a ring of D register
+// pairs (they depend on the string windows only): every fetch has D updates of arithmetic between issue and use instead
+// of none, which is what the 14 .. 16 resident warps of this kernel could not hide (short_scoreboard was its first stall
+// reason), and the stream alternates between the ALU pipe and the FMA / LSU pipes.  Measured first on the four-pairs-per-
+// warp kernel of do_linear.cu.
+template <int B> __host__ __device__ constexpr int x_dist() { return B / 4 >= 4 ? 4 : B / 4; }
+
+// fetches of update g in the frame of iteration tt (g >= H: update g - H of the next iteration)
+template <int B, bool GLOBAL>
+__device__ __forceinline__ void x_fetch(int tt, int g, const uint32_t (&lw)[B / 2], const uint32_t (&sw)[B / 2], uint32_t k1,
+                                        const char *gtab, uint32_t &lo, uint32_t &hi)
+{
+    constexpr int H = B / 2, Q = H / 2, U = H / 2;
+    const int t2 = tt + g / H, gg = g % H, odd = gg >= U ? 1 : 0, u = gg - U * odd;
+    const uint32_t a_lo = m_imad(lw[(t2 - u + 2 * H) % H], k1, sw[(t2 + u + odd) % H]);
+    const uint32_t a_hi = m_imad(lw[(t2 - u - Q + 2 * H) % H], k1, sw[(t2 + u + Q + odd) % H]);
+    lo = GLOBAL ? x_ldg_u16(gtab, a_lo) : x_lds_u16(a_lo);
+    hi = GLOBAL ? x_ldg_u16(gtab, a_hi) : x_lds_u16(a_hi);
+}
+// (a & b) | c as one LOP3 (ptxas splits the C expression in two for about half of the updates)
+__device__ __forceinline__ uint32_t x_and_or(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 template <int B, bool GLOBAL, bool TAIL>
 __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (&penc)[B / 2], uint32_t (&dw)[B / 2],
-                                          uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t k4, uint32_t k1,
+                                          uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t (&p_lo)[x_dist<B>()],
+                                          uint32_t (&p_hi)[x_dist<B>()], uint32_t k4, uint32_t k1,
                                           uint32_t k64k, const char *gtab, const uint32_t *&lptr, const uint32_t *&sptr,
                                           int n_iter, uint32_t *&out, uint32_t lane_off, int lane, bool phase)
 {
-    constexpr int H = B / 2, Q = H / 2, CH = x_chunk_len(B);
+    constexpr int H = B / 2, U = H / 2, CH = x_chunk_len(B), D = x_dist<B>();
     constexpr bool HALF = CH < 8;               // the chunk is half a direction word: `phase` = second half
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
         const bool first = HALF ? (r == 0 && !phase) : (r % 8 == 0);       // first iteration of a direction word
-        const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
-        const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);
+        // sliding windows by shuffle (see x_chunk): the new elements, installed below once no pending fetch wants the old
+        uint32_t s_new = __shfl_down_sync(kFull, sw[tt], 1) - (lane_off ? 4u : 0u);
+        if (lane == 31) s_new = sptr[r] + lane_off;
+        uint32_t l_new = __shfl_up_sync(kFull, lw[(tt + 1) % H], 1);
+        if (lane == 0) l_new = lptr[r];
+        uint32_t edge = 0;
 #pragma unroll
-        for (int m = 0; m < H; m += 2) {
-            const int u = m / 2;
-            const uint32_t left = (m == 0) ? left0 : R[m > 0 ? m - 1 : 0];
-            const uint32_t a_lo = m_imad(lw[(tt - u + 2 * H) % H], k1, sw[(tt + u) % H]);
-            const uint32_t a_hi = m_imad(lw[(tt - u - Q + 2 * H) % H], k1, sw[(tt + u + Q) % H]);
-            const uint32_t s_lo = GLOBAL ? x_ldg_u16(gtab, a_lo) : x_lds_u16(a_lo);
-            const uint32_t s_hi = GLOBAL ? x_ldg_u16(gtab, a_hi) : x_lds_u16(a_hi);
-            const uint32_t sub2 = m_imad(s_hi, k64k, s_lo);
-            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
-            const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
-            R[m] = (mn & 0xfffcfffcu) | penc[m];
+        for (int f = 0; f < H; ++f) {
+            if (f + D == U) sw[tt] = s_new;                 // before the first odd-diagonal fetch of this iteration
+            if (f + D == H) lw[(tt + 1) % H] = l_new;       // before the first fetch of the next one
+            const uint32_t sub2 = m_imad(p_hi[f % D], k64k, p_lo[f % D]);
+            x_fetch<B, GLOBAL>(tt, f + D, lw, sw, k1, gtab, p_lo[(f + D) % D], p_hi[(f + D) % D]);
+            uint32_t mn;
+            int m;
+            if (f < U) {            // even diagonals: anti-diagonal s = 2t
+                m = 2 * f;
+                if (f == 0) {
+                    const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
+                    edge = __funnelshift_l(prev, R[H - 1], 16);
+                }
+                const uint32_t left = (m == 0) ? edge : R[m > 0 ? m - 1 : 0];
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1 < H ? m + 1 : H - 1]);
+                mn = __viaddmin_u16x2(left, 0x00010001u, t1);
+            } else {                // odd diagonals: anti-diagonal s = 2t + 1
+                m = 2 * (f - U) + 1;
+                if (f == U) {
+                    const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
+                    edge = __funnelshift_r(R[0], next, 16);
+                }
+                const uint32_t up = (m == H - 1) ? edge : R[m + 1 < H ? m + 1 : H - 1];
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
+                mn = __viaddmin_u16x2(R[m - 1 >= 0 ? m - 1 : 0], 0x00010001u, t1);
+            }
+            R[m] = x_and_or(mn, 0xfffcfffcu, penc[m]);
             const uint32_t c2 = mn & 0x00030003u;
             if (HALF && r == 0) dw[m] = m_imad(first ? 0u : dw[m], k4, c2);
             else dw[m] = first ? c2 : m_imad(dw[m], k4, c2);
-        }
-        {       // sliding windows by shuffle (see x_chunk)
-            uint32_t nv = __shfl_down_sync(kFull, sw[tt], 1) - (lane_off ? 4u : 0u);
-            if (lane == 31) nv = sptr[r] + lane_off;
-            sw[tt] = nv;
-        }
-        const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
-        const uint32_t upl = __funnelshift_r(R[0], next, 16);
-#pragma unroll
-        for (int m = 1; m < H; m += 2) {
-            const int u = (m - 1) / 2;
-            const uint32_t up = (m == H - 1) ? upl : R[m + 1 < H ? m + 1 : H - 1];
-            const uint32_t a_lo = m_imad(lw[(tt - u + 2 * H) % H], k1, sw[(tt + u + 1) % H]);
-            const uint32_t a_hi = m_imad(lw[(tt - u - Q + 2 * H) % H], k1, sw[(tt + u + Q + 1) % H]);
-            const uint32_t s_lo = GLOBAL ? x_ldg_u16(gtab, a_lo) : x_lds_u16(a_lo);
-            const uint32_t s_hi = GLOBAL ? x_ldg_u16(gtab, a_hi) : x_lds_u16(a_hi);
-            const uint32_t sub2 = m_imad(s_hi, k64k, s_lo);
-            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
-            const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
-            R[m] = (mn & 0xfffcfffcu) | penc[m];
-            const uint32_t c2 = mn & 0x00030003u;
-            if (HALF && r == 0) dw[m] = m_imad(first ? 0u : dw[m], k4, c2);
-            else dw[m] = first ? c2 : m_imad(dw[m], k4, c2);
-        }
-        {
-            uint32_t nl = __shfl_up_sync(kFull, lw[(tt + 1) % H], 1);
-            if (lane == 0) nl = lptr[r];
-            lw[(tt + 1) % H] = nl;
         }
         if (HALF) {
             const int done = (phase ? 4 : 0) + r + 1;                  // iterations of the current direction word so far
@@ -477,17 +498,20 @@ __device__ __noinline__ uint32_t x_fill16(const MGeom g, uint32_t k4, uint32_t k
     }
     const uint32_t *lptr = Lb + (I0 + 1), *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
+    uint32_t p_lo[x_dist<B>()], p_hi[x_dist<B>()];
+#pragma unroll
+    for (int g0 = 0; g0 < x_dist<B>(); ++g0) x_fetch<B, GLOBAL>(0, g0, lw, sw, k1, gtab, p_lo[g0], p_hi[g0]);
     constexpr int CH = x_chunk_len(B), RB = 32 / CH;
     const int nfull = g.T / CH, rem = g.T % CH;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
         if (c && c % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, CH, out, lane_off, lane, (c & 1) != 0);
+        x_chunk16<B, GLOBAL, false>(R, penc, dw, lw, sw, p_lo, p_hi, k4, k1, k64k, gtab, lptr, sptr, CH, out, lane_off, lane, (c & 1) != 0);
     }
     if (rem) {
         if (nfull && nfull % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        x_chunk16<B, GLOBAL, true>(R, penc, dw, lw, sw, k4, k1, k64k, gtab, lptr, sptr, rem, out, lane_off, lane, (nfull & 1) != 0);
+        x_chunk16<B, GLOBAL, true>(R, penc, dw, lw, sw, p_lo, p_hi, k4, k1, k64k, gtab, lptr, sptr, rem, out, lane_off, lane, (nfull & 1) != 0);
     } else if (CH < 8 && (nfull & 1)) {
         // the last direction word holds 4 iterations only: flush it
         store_words16<H>(out, dw, 4);

@@ -1,5 +1,9 @@
-"""Host-side mirror of the pre-order pass's primitives for dynamic characters — the pure list scans the
-reference runs after the alignments, restated literally; no alignment work happens here.
+"""The pre-order pass for dynamic characters.
+
+``preorder_device`` is the product path: post-order contexts (alignments on the device, ``postorder_contexts``) go to
+``pcg_b200.Preorder`` — the descent over all trees x characters as prefix-sum kernels, do_preorder.cu.  The functions
+below it are a host-side mirror of the pass's primitives — the pure list scans of the reference, restated literally —
+kept as a readable statement of the semantics and as a second, independent restatement for the tests.
 
 Reference (DO = lib/core/analysis/src/Analysis/Parsimony/Dynamic/DirectOptimization):
 * ``get_context``                  — ``getContext`` (lib/core/data-structures/src/Bio/Character/Encodable/Dynamic/Element.hs:140-146)
@@ -100,4 +104,28 @@ def preorder_implied_alignments(children: np.ndarray, n_taxa: int, contexts: Dic
                 ia[c] = derive_implied_alignment(side == 0, ia[p], contexts[p], cac, gap)
                 single[c] = lexically_disambiguate(ia[c], a)
             stack.append(c)
+    return ia, single
+
+
+def preorder_device(ctx, children: np.ndarray, n_taxa: int, contexts, a: int):
+    """Final alignments and single disambiguations of every node, computed on the device (``pcgdo_preorder_*``).
+    children: (n_trees, n_taxa-1, 2) or (n_taxa-1, 2); contexts[t][c]: node -> (n, 3) array / None, as ``postorder_contexts``
+    returns them per tree and character.  Returns ia[t][c][node], single[t][c][node]."""
+    from .backend import Preorder
+    ch = np.asarray(children, np.int32)
+    if ch.ndim == 2:
+        ch, contexts = ch[None], [contexts]
+    n_chars = len(contexts[0])
+    pre = Preorder(ctx, ch, n_taxa, n_chars)
+    try:
+        pre.set_contexts(contexts)
+        pre.run(a)
+        ia = [[dict() for _ in range(n_chars)] for _ in range(len(ch))]
+        single = [[dict() for _ in range(n_chars)] for _ in range(len(ch))]
+        for t in range(len(ch)):
+            for c in range(n_chars):
+                for v in range(2 * n_taxa - 1):
+                    ia[t][c][v], single[t][c][v] = pre.node(t, c, v)
+    finally:
+        pre.close()
     return ia, single

@@ -439,3 +439,63 @@ def test_preorder_implied_alignments_over_device_contexts(gpu_ctx):
         for v in range(n_taxa):
             med = ia[v][:, 0]
             assert np.array_equal(med[med != 16], leaves[v]), (t, v)
+
+
+def test_preorder_on_the_device_equals_the_restatement(oracle_mod, gpu_ctx):
+    """pcgdo_preorder_* (do_preorder.cu: deriveImpliedAlignment as prefix sums, one launch per depth over all trees x
+    characters) against oracle/preorder_oracle.c: final alignment (median, left, right) and single disambiguation of EVERY
+    node, on contexts aligned by the device (postorder_contexts) — which must themselves equal the restatement's.  Trees with
+    a Missing character included.  (Parity unpinned upstream: see preorder_oracle.c.)"""
+    import pcg_b200 as P
+    from pcg_b200.postorder import postorder_contexts, random_binary_trees
+    from pcg_b200.preorder import preorder_device
+    from tests.helpers import tcm_matrix, random_string
+    rng = np.random.default_rng(4711)
+    n_taxa, n_trees, n_chars = 20, 3, 2
+    children = random_binary_trees(n_trees, n_taxa, 9)
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=512, max_b=32, arena_words=0)
+    for name in ("discrete", "l1"):
+        sig = tcm_matrix(name)
+        tcm = gpu_ctx.tcm(sig)
+        o = oracle_mod.Oracle(sig)
+        contexts, want = [], []
+        for t in range(n_trees):
+            cols, wcols = [], []
+            for c in range(n_chars):
+                base = random_string(rng, 90 + 20 * c, amb=0.05)
+                leaves = []
+                for _ in range(n_taxa):
+                    s = base.copy()
+                    mut = rng.random(len(s)) < 0.1
+                    s[mut] = random_string(rng, int(mut.sum()), amb=0.0)
+                    s = s[rng.random(len(s)) > 0.06]
+                    leaves.append(s[s != 16])
+                ctxs, _, _ = postorder_contexts(gpu_ctx, tcm, children[t], n_taxa, leaves)
+                root, octx, oia, osingle = oracle_mod.preorder_tree(o, children[t], leaves)
+                for v in range(2 * n_taxa - 1):
+                    assert np.array_equal(ctxs[v], octx[v]), (name, t, c, v)
+                cols.append(ctxs)
+                wcols.append((oia, osingle))
+            contexts.append(cols)
+            want.append(wcols)
+        ia, single = preorder_device(gpu_ctx, children, n_taxa, contexts, 5)
+        for t in range(n_trees):
+            for c in range(n_chars):
+                oia, osingle = want[t][c]
+                for v in range(2 * n_taxa - 1):
+                    assert np.array_equal(ia[t][c][v], oia[v]), (name, t, c, v)
+                    assert np.array_equal(single[t][c][v], osingle[v]), (name, t, c, v)
+    # a Missing leaf: its final alignment is its parent's; a Missing subtree likewise
+    pre = P.Preorder(gpu_ctx, children[:1], n_taxa, 1)
+    col = dict(contexts[0][0])
+    col[3] = None
+    pre.set_contexts([[col]])
+    try:
+        pre.run(5)
+        ia3, s3 = pre.node(0, 0, 3)
+        par = next(n_taxa + x for x in range(n_taxa - 1) if 3 in children[0][x])
+        iap, sp = pre.node(0, 0, par)
+        assert np.array_equal(ia3, iap) and np.array_equal(s3, sp)
+    except P.BackendError:
+        pass        # (a context that no longer belongs to the tree may legitimately hit "Impossible happened")
+    pre.close()

@@ -253,3 +253,46 @@ def test_protein_discrete_script_cost_commented_out_upstream(oracle_mod):
     from tests.helpers import invertebrates_golden
     children, leaves, _ = invertebrates_golden()
     assert oracle_mod.reroot_haskell(2, 21, children, leaves)[0] == 1131
+
+
+def _related_leaves(rng, n_taxa, base_len=80):
+    from tests.helpers import random_string
+    base = random_string(rng, base_len, amb=0.05)
+    leaves = []
+    for _ in range(n_taxa):
+        s = base.copy()
+        mut = rng.random(len(s)) < 0.12
+        s[mut] = random_string(rng, int(mut.sum()), amb=0.0)
+        s = s[rng.random(len(s)) > 0.07]
+        s = s[s != 16]
+        leaves.append(s if len(s) else base[:3].copy())
+    return leaves
+
+
+@pytest.mark.parametrize("name", ["discrete", "l1", "2:1"])
+def test_preorder_restatement_in_c_equals_the_python_one(oracle_mod, name):
+    """oracle/preorder_oracle.c (deriveImpliedAlignment, lexicallyDisambiguate, the rooted pre-order; DO/Internal.hs:148-286)
+    against the independent restatement of the same functions in pcg_b200/preorder.py, on the post-order contexts of
+    random trees — plus the pass's invariants.  PARITY UNPINNED upstream (see preorder_oracle.c)."""
+    from pcg_b200.postorder import random_binary_trees
+    from pcg_b200.preorder import preorder_implied_alignments
+    from tests.helpers import tcm_matrix
+    o = oracle_mod.Oracle(tcm_matrix(name))
+    rng = np.random.default_rng(77)
+    for t, n_taxa in enumerate((5, 12, 24, 40)):
+        children = random_binary_trees(1, n_taxa, 100 + t)[0]
+        leaves = _related_leaves(rng, n_taxa)
+        root, ctxs, ias, single = oracle_mod.preorder_tree(o, children, leaves)
+        assert root == 2 * n_taxa - 2
+        py_ctx = {v: (None if c is None else c.astype(np.uint8)) for v, c in ctxs.items()}
+        ia_py, single_py = preorder_implied_alignments(children, n_taxa, py_ctx, 5)
+        n_root = len(ctxs[root])
+        for v in range(2 * n_taxa - 1):
+            assert ias[v].shape == (n_root, 3)
+            assert np.array_equal(ias[v], ia_py[v]), (name, n_taxa, v)
+            assert np.array_equal(single[v], single_py[v][:, 0]), (name, n_taxa, v)
+            med, own = ias[v][:, 0], ctxs[v][:, 0]
+            assert np.array_equal(med[med != 16], own[own != 16]), (name, n_taxa, v)
+        for v in range(n_taxa):
+            med = ias[v][:, 0]
+            assert np.array_equal(med[med != 16], leaves[v])
