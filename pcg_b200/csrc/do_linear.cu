@@ -225,51 +225,77 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
     return v;
 }
 
+// (a & b) | c as ONE LOP3: ptxas splits the C expression in two for about half of the updates
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// The H packed updates of an iteration (H / 2 even-diagonal registers, then H / 2 odd ones) are numbered f = 0 .. H-1; the
+// two table fetches of update f + D are issued right before the arithmetic of update f, into a ring of D register pairs
+// (they depend on the string windows only), so that a fetch has D updates of arithmetic between issue and use.
+template <int B> __host__ __device__ constexpr int fetch_dist() { return B >= 32 ? 4 : (B >= 8 ? 2 : 1); }
+
+// fetches of update g in the frame of iteration tt (g >= H: update g - H of the next iteration)
+template <int B>
+__device__ __forceinline__ void fetch16(int tt, int g, const uint32_t (&lw)[B / 2], const uint32_t (&sw)[B / 2], const FillConst fc,
+                                        uint32_t &lo, uint32_t &hi)
+{
+    constexpr int H = B / 2, Q = H / 2, U = H / 2;
+    const int t2 = tt + g / H, gg = g % H, odd = gg >= U ? 1 : 0, u = gg - U * odd;
+    lo = lds_u16(imad(lw[(t2 - u + 2 * H) % H], fc.lstride, sw[(t2 + u + odd) % H]));
+    hi = lds_u16(imad(lw[(t2 - u - Q + 2 * H) % H], fc.lstride, sw[(t2 + u + Q + odd) % H]));
+}
+
 template <int B, bool TAIL>
 __device__ __forceinline__ void run_chunk16(uint32_t (&R)[B / 2], const uint32_t (&penc)[B / 2], uint32_t (&dw)[B / 2],
-                                            uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], const FillConst fc,
+                                            uint32_t (&lw)[B / 2], uint32_t (&sw)[B / 2], uint32_t (&p_lo)[fetch_dist<B>()],
+                                            uint32_t (&p_hi)[fetch_dist<B>()], const FillConst fc,
                                             uint32_t tab_lane, const char *&lptr, const char *&sptr, int n_iter,
                                             uint32_t *&out)
 {
-    constexpr int H = B / 2, Q = H / 2, CH = pack16_chunk(B);
+    constexpr int H = B / 2, U = H / 2, CH = pack16_chunk(B), D = fetch_dist<B>();
+    static_assert(D <= U, "fetch distance");
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
-        // ---- even diagonals (registers with even m): anti-diagonal s = 2t
-        const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
-        const uint32_t left0 = __funnelshift_l(prev, R[H - 1], 16);      // (own diag H-1) << 16 | (left lane's diag B-1)
+        const uint32_t s_new = ld_u16(sptr + 2 * r) + tab_lane;
+        const uint32_t l_new = ld_u8(lptr + r);
+        uint32_t edge = 0;
 #pragma unroll
-        for (int m = 0; m < H; m += 2) {
-            const int u = m / 2;
-            const uint32_t left = (m == 0) ? left0 : R[m > 0 ? m - 1 : 0];
-            const uint32_t a_lo = imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u) % H]);
-            const uint32_t a_hi = imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q) % H]);
-            const uint32_t sub2 = imad(lds_u16(a_hi), fc.k64k, lds_u16(a_lo));
-            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
-            const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
-            R[m] = (mn & 0xfffcfffcu) | penc[m];
+        for (int f = 0; f < H; ++f) {
+            if (f + D == U) sw[tt] = s_new;                 // before the first odd-diagonal fetch of this iteration
+            if (f + D == H) lw[(tt + 1) % H] = l_new;       // before the first fetch of the next one
+            const uint32_t sub2 = imad(p_hi[f % D], fc.k64k, p_lo[f % D]);
+            fetch16<B>(tt, f + D, lw, sw, fc, p_lo[(f + D) % D], p_hi[(f + D) % D]);
+            uint32_t mn;
+            int m;
+            if (f < U) {            // even diagonals (registers with even m): anti-diagonal s = 2t
+                m = 2 * f;
+                if (f == 0) {
+                    const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
+                    edge = __funnelshift_l(prev, R[H - 1], 16);      // (own diag H-1) << 16 | (left lane's diag B-1)
+                }
+                const uint32_t left = (m == 0) ? edge : R[m > 0 ? m - 1 : 0];
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1 < H ? m + 1 : H - 1]);
+                mn = __viaddmin_u16x2(left, 0x00010001u, t1);
+            } else {                // odd diagonals: anti-diagonal s = 2t + 1
+                m = 2 * (f - U) + 1;
+                if (f == U) {
+                    const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
+                    edge = __funnelshift_r(R[0], next, 16);          // (right lane's diag 0) << 16 | (own diag H)
+                }
+                const uint32_t up = (m == H - 1) ? edge : R[m + 1 < H ? m + 1 : H - 1];
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
+                mn = __viaddmin_u16x2(R[m - 1 >= 0 ? m - 1 : 0], 0x00010001u, t1);
+            }
+            R[m] = and_or(mn, 0xfffcfffcu, penc[m]);
             const uint32_t c2 = mn & 0x00030003u;
             dw[m] = (r % 8 == 0) ? c2 : imad(dw[m], fc.k4, c2);
         }
-        sw[tt] = ld_u16(sptr + 2 * r) + tab_lane;
-        // ---- odd diagonals: anti-diagonal s = 2t + 1
-        const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
-        const uint32_t upl = __funnelshift_r(R[0], next, 16);            // (right lane's diag 0) << 16 | (own diag H)
-#pragma unroll
-        for (int m = 1; m < H; m += 2) {
-            const int u = (m - 1) / 2;
-            const uint32_t up = (m == H - 1) ? upl : R[m + 1 < H ? m + 1 : H - 1];
-            const uint32_t a_lo = imad(lw[(tt - u + 2 * H) % H], fc.lstride, sw[(tt + u + 1) % H]);
-            const uint32_t a_hi = imad(lw[(tt - u - Q + 2 * H) % H], fc.lstride, sw[(tt + u + Q + 1) % H]);
-            const uint32_t sub2 = imad(lds_u16(a_hi), fc.k64k, lds_u16(a_lo));
-            const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
-            const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
-            R[m] = (mn & 0xfffcfffcu) | penc[m];
-            const uint32_t c2 = mn & 0x00030003u;
-            dw[m] = (r % 8 == 0) ? c2 : imad(dw[m], fc.k4, c2);
-        }
-        lw[(tt + 1) % H] = ld_u8(lptr + r);
         if (r % 8 == 7) {
             store_words16<H>(out, dw, 8);
             out += 32 * H;
@@ -317,17 +343,20 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
     const char *lptr = Lb + (I0 + 1);
     const char *sptr = Sb + 2 * (J0 + H);
     uint32_t *out = slot + lane * H;
+    uint32_t p_lo[fetch_dist<B>()], p_hi[fetch_dist<B>()];
+#pragma unroll
+    for (int g0 = 0; g0 < fetch_dist<B>(); ++g0) fetch16<B>(0, g0, lw, sw, fc, p_lo[g0], p_hi[g0]);
     constexpr int CH = pack16_chunk(B), RB = 32 / CH;        // re-base every 32 iterations
     const int nfull = g.T / CH, rem = g.T % CH;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
         if (c && c % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        run_chunk16<B, false>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, CH, out);
+        run_chunk16<B, false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, lptr, sptr, CH, out);
     }
     if (rem) {
         if (nfull && nfull % RB == 0) ok = rebase16<H>(R, total_shift, spread_limit) && ok;
-        run_chunk16<B, true>(R, penc, dw, lw, sw, fc, tab_lane, lptr, sptr, rem, out);
+        run_chunk16<B, true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, lptr, sptr, rem, out);
     }
     // one last look at the window: everything since the previous check stayed inside it iff that check passed
     ok = rebase16<H>(R, total_shift, spread_limit) && ok;
@@ -407,13 +436,6 @@ __device__ __forceinline__ void quad_fetch(int tt, const uint32_t (&lw)[kQuadH],
     hi = lds_u16(imad(lw[(t2 - u - Q + 2 * H) % H], fc.lstride, sw[(t2 + u + Q + odd) % H]));
 }
 
-// (a & b) | c as ONE LOP3: ptxas splits the C expression in two for about half of the updates
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 // s_entry without the branch: e * c1 - (e & 1) * c2 with (c1, c2) = (64, 62) for the replicated table, (2, 0) otherwise
 __device__ __forceinline__ uint32_t s_entry2(uint32_t e, uint32_t c1, uint32_t c2neg, uint32_t base)
 {

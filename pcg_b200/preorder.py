@@ -129,3 +129,99 @@ def preorder_device(ctx, children: np.ndarray, n_taxa: int, contexts, a: int):
     finally:
         pre.close()
     return ia, single
+
+
+# ------------------------------------------------------------------------------------------------
+# The driver over re-rooted traversal foci (trees)
+# ------------------------------------------------------------------------------------------------
+def rooting_contexts(ctx, tcm, children: np.ndarray, n_taxa: int, leaves):
+    """Directed subtree data WITH their alignment contexts, for one tree and one character — the re-rooting pass of
+    ``assignOptimalDynamicCharacterRootEdges`` (Bio/Graph/PhylogeneticDAG/DynamicCharacterRerooting.hs:230-330,
+    ``contextNodeDatum``) kept with the full (median, left, right) contexts the pre-order needs instead of medians only.
+    Every alignment runs on the device (``foreign_pairwise_do_batch``, one batch per round of ready data).
+
+    Returns (root, adj, ctx_of, total_of, edges):
+      adj[n]           = [c1, c2, unrooted parent] of an internal non-root node (children ascending; the sibling stands in
+                         for the root)
+      ctx_of[(n, q)]   = context of "n entered from q" (for a leaf, or q = n's original parent: the post-order context)
+      total_of[(n, q)] = its total cost
+      edges            = [(u, v, total, context of the rooting on that edge)], edge 0 = the original root edge"""
+    from .pairwise import foreign_pairwise_do_batch
+    from .postorder import postorder_contexts
+    ch = np.asarray(children, np.int32)
+    n_nodes = 2 * n_taxa - 1
+    down, local, total = postorder_contexts(ctx, tcm, ch, n_taxa, leaves)
+    parent = {int(c): n_taxa + x for x in range(n_taxa - 1) for c in ch[x]}
+    root = next(v for v in range(n_taxa, n_nodes) if v not in parent)
+    rc = [int(ch[root - n_taxa][0]), int(ch[root - n_taxa][1])]
+    adj = {}
+    for v in range(n_taxa, n_nodes):
+        if v == root:
+            continue
+        c1, c2 = sorted(int(c) for c in ch[v - n_taxa])
+        p = parent[v]
+        if p == root:
+            p = rc[1] if rc[0] == v else rc[0]
+        adj[v] = [c1, c2, p]
+    ctx_of, total_of = {}, {}
+
+    def known(n, q):
+        return n < n_taxa or (n, q) in ctx_of
+
+    def get(n, q):
+        return (down[n], total[n]) if n < n_taxa else (ctx_of[(n, q)], total_of[(n, q)])
+    for v, (c1, c2, p) in adj.items():                       # base case: entered from the original parent
+        ctx_of[(v, p)], total_of[(v, p)] = down[v], total[v]
+    pending = [(n, s) for n in adj for s in (0, 1)]          # entered from child adj[n][s]: DO(datum j, datum k), rotation
+    while pending:
+        ready = [(n, s) for (n, s) in pending
+                 if known(adj[n][(s + 1) % 3], n) and known(adj[n][(s + 2) % 3], n)]
+        assert ready, "cyclic dependency among directed data"
+        lhs = [get(adj[n][(s + 1) % 3], n) for n, s in ready]
+        rhs = [get(adj[n][(s + 2) % 3], n) for n, s in ready]
+        res = foreign_pairwise_do_batch(ctx, tcm, [x[0] for x in lhs], [x[0] for x in rhs])
+        for (n, s), (cost, c), l, r in zip(ready, res, lhs, rhs):
+            ctx_of[(n, adj[n][s])], total_of[(n, adj[n][s])] = c, cost + l[1] + r[1]
+        done = set(ready)
+        pending = [x for x in pending if x not in done]
+    edges = [(rc[0], rc[1], total[root], down[root])]
+    pairs = [(i, int(j)) for i in adj for j in ch[i - n_taxa]]
+    lhs = [get(i, j) for i, j in pairs]
+    rhs = [get(j, i) for i, j in pairs]
+    res = foreign_pairwise_do_batch(ctx, tcm, [x[0] for x in lhs], [x[0] for x in rhs])
+    for (i, j), (cost, c), l, r in zip(pairs, res, lhs, rhs):
+        edges.append((i, j, cost + l[1] + r[1], c))
+    return root, adj, ctx_of, total_of, edges
+
+
+def preorder_from_rooting(ctx, tcm, children: np.ndarray, n_taxa: int, leaves, a: int, edge: Optional[int] = None):
+    """The pre-order pass driven from the character's traversal focus (``preorderFromRooting``,
+    Bio/Graph/PhylogeneticDAG/Preorder.hs:359-520, trees): the tree is re-rooted on its cheapest edge (``edge``: force
+    one), the rooting's datum is the virtual root (``FociEdgeNode`` / ``RootContext``), every other node is decorated
+    against its parent in the re-rooted orientation with the datum it has when entered from that parent, and the descent
+    itself runs on the device (``pcg_b200.Preorder``).
+
+    Returns (edge index, (u, v), total cost, children of the re-rooted tree, contexts per node, ia, single) in the node
+    numbering of the original tree; the virtual root takes the id of the original root (which is no node of the re-rooted
+    tree).  Parity unpinned upstream, as the rest of the pass."""
+    ch = np.asarray(children, np.int32)
+    root, adj, ctx_of, total_of, edges = rooting_contexts(ctx, tcm, ch, n_taxa, leaves)
+    if edge is None:
+        edge = min(range(len(edges)), key=lambda e: (edges[e][2], e))       # first minimal edge
+    u, v, tot, root_ctx = edges[edge]
+    new_children = np.zeros_like(ch)
+    contexts: Dict[int, Optional[np.ndarray]] = {x: np.stack([np.asarray(leaves[x], np.uint8)] * 3, axis=1) for x in range(n_taxa)}
+    contexts[root] = root_ctx
+    new_children[root - n_taxa] = (u, v)
+    stack = [(u, v), (v, u)]                                                # (node, entered from)
+    while stack:
+        n, frm = stack.pop()
+        if n < n_taxa:
+            continue
+        contexts[n] = ctx_of[(n, frm)]
+        s = adj[n].index(frm)
+        j, k = adj[n][(s + 1) % 3], adj[n][(s + 2) % 3]                     # the operands of that datum, in order
+        new_children[n - n_taxa] = (j, k)
+        stack += [(j, n), (k, n)]
+    ia, single = preorder_device(ctx, new_children, n_taxa, [contexts], a)
+    return edge, (u, v), tot, new_children, contexts, ia[0][0], single[0][0]

@@ -499,3 +499,41 @@ def test_preorder_on_the_device_equals_the_restatement(oracle_mod, gpu_ctx):
     except P.BackendError:
         pass        # (a context that no longer belongs to the tree may legitimately hit "Impossible happened")
     pre.close()
+
+
+def test_preorder_from_the_traversal_focus(oracle_mod, gpu_ctx):
+    """preorder_from_rooting: re-root on the cheapest edge (costs as the re-rooting restatement's), decorate every node
+    against its parent in that orientation on the device; the result equals the Python restatement of the fold run over the
+    same re-rooted tree, every final alignment has the virtual root's length, and ungapping a leaf's gives its sequence."""
+    from pcg_b200.postorder import random_binary_trees
+    from pcg_b200.preorder import preorder_from_rooting, preorder_implied_alignments
+    from tests.helpers import tcm_matrix, random_string
+    rng = np.random.default_rng(99)
+    n_taxa = 14
+    sig = tcm_matrix("discrete")
+    gpu_ctx.configure(pairs_per_warp=8, warps_per_cta=32, max_len=512, max_b=32, arena_words=0)
+    tcm = gpu_ctx.tcm(sig)
+    o = oracle_mod.Oracle(sig)
+    for t in range(3):
+        children = random_binary_trees(1, n_taxa, 50 + t)[0]
+        base = random_string(rng, 100, amb=0.05)
+        leaves = []
+        for _ in range(n_taxa):
+            s = base.copy()
+            mut = rng.random(len(s)) < 0.15
+            s[mut] = random_string(rng, int(mut.sum()), amb=0.0)
+            s = s[rng.random(len(s)) > 0.08]
+            leaves.append(s[s != 16])
+        best, edges, ecost, _ = oracle_mod.reroot(o, children, leaves)
+        e, uv, tot, new_children, contexts, ia, single = preorder_from_rooting(gpu_ctx, tcm, children, n_taxa, leaves, 5)
+        assert tot == best and int(ecost[e]) == best and tuple(edges[e]) == tuple(uv)
+        ia_py, single_py = preorder_implied_alignments(new_children, n_taxa, contexts, 5)
+        n_root = len(contexts[2 * n_taxa - 2]) if 2 * n_taxa - 2 in contexts else None
+        for v in range(2 * n_taxa - 1):
+            assert np.array_equal(ia[v], ia_py[v]), (t, v)
+            assert np.array_equal(single[v], single_py[v][:, 0]), (t, v)
+        lens = {len(x) for x in ia.values()}
+        assert len(lens) == 1
+        for v in range(n_taxa):
+            med = ia[v][:, 0]
+            assert np.array_equal(med[med != 16], leaves[v]), (t, v)
