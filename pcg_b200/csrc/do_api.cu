@@ -17,8 +17,8 @@
 
 namespace pcgdo {
 cudaError_t launch_linear(const LinearParams &p, bool wide, int grid, int block, size_t smem_bytes, cudaStream_t stream);
-cudaError_t launch_linear_quad(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream);
-uint32_t quad_seq_cap_for(int max_len);
+cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+uint32_t multi_seq_cap_for(int max_len, int shape);
 uint32_t seq_cap_for(int max_len, int B);
 uint64_t general_words_for(uint32_t n1, uint32_t n2);
 cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_t *list, const uint64_t *scratch_off,
@@ -134,7 +134,7 @@ extern "C" void pcgdo_destroy(pcgdo_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->singles, &ctx->phase, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_dict, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
+    DevBuf *bufs[] = {&ctx->arena, &ctx->counters, &ctx->overflow, &ctx->big, &ctx->singles, &ctx->singles2, &ctx->phase, &ctx->gen_scratch, &ctx->gen_off, &ctx->tscratch, &ctx->d_dict, &ctx->d_elems, &ctx->d_off1, &ctx->d_off2,
                       &ctx->d_len1, &ctx->d_len2, &ctx->d_out_off, &ctx->d_og, &ctx->d_o1, &ctx->d_o2,
                       &ctx->d_olen, &ctx->d_cost, &ctx->d_cells, &ctx->d_stage, &ctx->d_actual, &ctx->d_total, &ctx->d_strag};
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
@@ -389,19 +389,27 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     // back — the host pipeline, the forest — size these for their largest batch before the first one)
     if ((rc = pcgdo_ensure(ctx, ctx->overflow, (size_t)bd.n_pairs * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4))) return rc;
-    // Four pairs per warp (do_linear_quad_kernel) first, when the TCM qualifies for the packed fill and one pair's
-    // strings fit a quarter of a warp's staging share; what it leaves over goes to the narrow kernel through a list.
-    uint32_t cap_q = 0;
+    // Several pairs per warp (do_linear_multi_kernel, two shapes) first, when the TCM qualifies for the packed fill; what
+    // one launch leaves over goes to the next through a list on the device, and last to the narrow kernel.
+    uint32_t cap_m[2] = {0, 0};
     int warps_q = 0;
     if (tcm->dev.pack_ok && !ctx->knobs.no_pack16 && !ctx->knobs.no_quad && bd.n_pairs >= 4) {
         const size_t dim = (size_t)1 << tcm->a;
         const size_t fixed = tcm->dev.sub4_bytes + 2 * dim * 4;
         warps_q = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
         const size_t room = (227 * 1024 - fixed) / warps_q;
-        const uint32_t want = (quad_seq_cap_for(ctx->max_len) + 15u) & ~15u;
-        if (room >= 640 + 4 * 1024) cap_q = std::min<uint32_t>((uint32_t)((room - 640) / 4) & ~15u, want);
+        for (int shape = 0; shape < 2; ++shape) {
+            const uint32_t np = shape == 0 ? 4u : 8u;
+            const uint32_t want = (multi_seq_cap_for(ctx->max_len, shape) + 15u) & ~15u;
+            if (room >= 640 + np * 256) cap_m[shape] = std::min<uint32_t>((uint32_t)((room - 640) / np) & ~15u, want);
+        }
+        if (ctx->knobs.quad_flags & 4u) cap_m[1] = 0;          // experiment switches: one shape only
+        if (ctx->knobs.quad_flags & 8u) cap_m[0] = 0;
     }
-    if (cap_q && (rc = pcgdo_ensure(ctx, ctx->singles, (size_t)bd.n_pairs * 4))) return rc;
+    const bool multi = cap_m[0] || cap_m[1];
+    if (multi && ((rc = pcgdo_ensure(ctx, ctx->singles, (size_t)bd.n_pairs * 4)) ||
+                  (rc = pcgdo_ensure(ctx, ctx->singles2, (size_t)bd.n_pairs * 4))))
+        return rc;
     CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 32, st));
 
     LinearParams p{};
@@ -424,10 +432,7 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     p.k_64k = 65536u;
     p.grab = 2;
 
-    if (cap_q) {
-        p.single_count = p.counter + 5;
-        p.single_list = (uint32_t *)ctx->singles.p;
-        p.seq_cap = cap_q;
+    if (multi) {
         p.quad_flags = ctx->knobs.quad_flags;
         if (ctx->knobs.quad_flags & 2u) {
             if ((rc = pcgdo_ensure(ctx, ctx->phase, 64))) return rc;
@@ -436,8 +441,26 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
         }
         p.quad_arena_words = (uint32_t)std::min<size_t>((arena_words * warps_max / warps_q) & ~(size_t)3, 0xfffffff0u);
         const size_t dim = (size_t)1 << tcm->a;
-        CK(launch_linear_quad(p, grid, warps_q * 32, tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps_q * (640 + 4 * (size_t)cap_q), st));
-        ctx->last_launches += 1;
+        // the shape most pairs are expected to take goes first (it reads the batch itself): strings of a few hundred
+        // elements have bands of 65 .. 127 diagonals, ~1 kb strings 129 .. 223
+        const int order[2] = {ctx->max_len >= 320 ? 0 : 1, ctx->max_len >= 320 ? 1 : 0};
+        int stage = 0;
+        for (int o = 0; o < 2; ++o) {
+            const int shape = order[o];
+            if (!cap_m[shape]) continue;
+            const uint32_t np = shape == 0 ? 4u : 8u;
+            p.multi_in_list = stage == 0 ? nullptr : (const uint32_t *)ctx->singles.p;
+            p.multi_in_count = stage == 0 ? nullptr : p.counter + 5;
+            p.multi_counter = p.counter + (stage == 0 ? 4 : 7);
+            p.single_list = (uint32_t *)(stage == 0 ? ctx->singles.p : ctx->singles2.p);
+            p.single_count = p.counter + (stage == 0 ? 5 : 6);
+            p.seq_cap = cap_m[shape];
+            CK(launch_linear_multi(p, shape, grid, warps_q * 32,
+                                   tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps_q * (640 + np * (size_t)cap_m[shape]), st));
+            ctx->last_launches += 1;
+            ++stage;
+        }
+        // (the narrow kernel reads p.single_list / p.single_count as set by the last stage)
     }
     p.seq_cap = cap_n;
     CK(launch_linear(p, false, grid, warps_n * 32, smem_for(tcm, warps_n, cap_n), st));
@@ -495,7 +518,7 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
     if (p.phase_cycles) {
         unsigned long long h_ph[6] = {0};
         CK(cudaMemcpy(h_ph, p.phase_cycles, 48, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[pcgdo] quad kernel warp-cycles: stage %llu fill %llu trace %llu emit %llu prep %llu post %llu; singles %u\n", h_ph[0], h_ph[1],
+        fprintf(stderr, "[pcgdo] multi-pair kernels warp-cycles: stage %llu fill %llu trace %llu emit %llu prep %llu post %llu; singles %u\n", h_ph[0], h_ph[1],
                 h_ph[2], h_ph[3], h_ph[4], h_ph[5], h_cnt[5]);
     }
     // pairs the warp kernels could not hold (band wider than 1023 diagonals, strings longer than the

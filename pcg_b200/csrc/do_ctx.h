@@ -43,7 +43,8 @@ struct pcgdo_ctx {
         bool trace_pipeline = false;   // PCGDO_TRACE_PIPELINE     per-chunk completion times to stderr
         bool no_pack16 = false;        // PCGDO_NO_PACK16          32-bit fills only
         bool no_quad = false;          // PCGDO_NO_QUAD            dense path: no four-pairs-per-warp kernel
-        unsigned quad_flags = 0;       // PCGDO_QUAD_FLAGS         bit 0: stagger first batches; bit 1: phase cycle counts to stderr
+        unsigned quad_flags = 0;       // PCGDO_QUAD_FLAGS         bit 0: stagger first batches; bit 1: phase cycle counts to stderr;
+                                       //                          bit 2 / 3: without the 8- / 4-pairs-per-warp shape
         bool affine_rowwise = false;   // PCGDO_AFFINE_ROWWISE     first-generation affine fill
         bool metric_registers = false; // PCGDO_METRIC_REGISTERS   do_metric.cu instead of the table kernel
         bool explicit_multi_pass = false;  // PCGDO_EXPLICIT_MULTI_PASS
@@ -53,7 +54,7 @@ struct pcgdo_ctx {
         int  affine_variant = 0;       // PCGDO_AFFINE_VARIANT     reading of the reference's UB shift in the align2dAffine shim
     } knobs;
     // device scratch
-    DevBuf arena, counters, overflow, big, singles, phase, gen_scratch, gen_off, tscratch, d_dict;
+    DevBuf arena, counters, overflow, big, singles, singles2, phase, gen_scratch, gen_off, tscratch, d_dict;
     // staging for the host-buffer entry point
     DevBuf d_elems, d_off1, d_off2, d_len1, d_len2, d_out_off, d_og, d_o1, d_o2, d_olen, d_cost, d_cells;
     DevBuf d_strag;                  // descriptors of the few pairs a pipelined batch hands to the general-geometry kernel

@@ -98,8 +98,11 @@ struct LinearParams {
     uint32_t      overflow_cap;
     unsigned int *big_count;       // pairs whose band needs more than 8 diagonals per lane:
     uint32_t     *big_list;        //   queued by the narrow kernel, consumed by the wide one
-    unsigned int *single_count;    // four-pairs-per-warp kernel: the pairs it did not take (bit 31: 32-bit fill),
-    uint32_t     *single_list;     //   consumed by the narrow kernel; NULL = the narrow kernel reads the batch itself
+    unsigned int *single_count;    // multi-pair kernels: the pairs the launch did not take (bit 31: 32-bit fill) — input of
+    uint32_t     *single_list;     //   the next kernel; for the narrow kernel NULL = it reads the batch itself
+    const unsigned int *multi_in_count;   // multi-pair kernels: the list to work from (NULL = the batch) and
+    const uint32_t     *multi_in_list;    //   the hand-out counter of this launch
+    unsigned int *multi_counter;
     // run-time "constants" (1, 4, -1, table row stride) kept opaque to ptxas so that the table-address add
     // and the direction accumulation are emitted as IMAD (FMA pipe) instead of IADD3/LEA/SHF (ALU pipe)
     uint32_t  k_four, k_minus1, l_stride, k_64k;

@@ -390,21 +390,22 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
 // Direction words: word[(t >> 3) * 448 + lane * 14 + m] — the diagonals of a pair are consecutive words (two diagonals 14
 // apart share a word), so the trace's next word is usually in the 32-byte sector it already holds.
 // ---------------------------------------------------------------------------------------------
-constexpr int kQuadB = 28, kQuadH = 14, kQuadLanes = 8, kQuadPairs = 4;
-constexpr uint32_t kQuadRow = 32u * kQuadH;        // direction words per 8 iterations of one group
-
-__host__ __device__ inline uint32_t quad_dir_words(int tmax) { return (uint32_t)((tmax + 7) / 8) * kQuadRow; }
+// Two shapes are built: LP = 8 lanes x 28 diagonals (H = 14 registers; 4 pairs per warp; bands of 129 .. 223 diagonals: ~1 kb
+// strings) and LP = 4 lanes x 32 diagonals (H = 16; 8 pairs per warp; bands of 65 .. 127: the ~250-element strings of tree
+// scoring).  Direction words per 8 iterations of one group: 32 * H.
+template <int H> __host__ __device__ inline uint32_t multi_dir_words(int tmax) { return (uint32_t)((tmax + 7) / 8) * 32u * (uint32_t)H; }
 
 // Staging of one pair of a group: both strings as raw bytes (element 0 = padding), zero-padded for `tmax` iterations.
-__host__ __device__ inline SeqLayout seq_layout_quad(const Geom &g, int tmax)
+template <int LP, int H>
+__host__ __device__ inline SeqLayout seq_layout_multi(const Geom &g, int tmax)
 {
     const int tpad = (tmax + 15) & ~15;
     SeqLayout s;
-    s.offL = kQuadLanes * kQuadH;
+    s.offL = LP * H;
     int needL = tpad + g.q0 / 2 + 2;
     s.sizeL = s.offL + (needL > g.lg ? needL : g.lg) + 2;
     s.offS = g.q0 / 2;
-    int needS = tpad - g.q0 / 2 + kQuadLanes * kQuadH + 2;
+    int needS = tpad - g.q0 / 2 + LP * H + 2;
     if (needS < g.sh) needS = g.sh;
     s.sizeS = s.offS + needS + 2;
     s.sizeL = (s.sizeL + 3) & ~3;
@@ -416,25 +417,10 @@ __host__ __device__ inline SeqLayout seq_layout_quad(const Geom &g, int tmax)
 // per lane and iteration)
 __device__ __forceinline__ uint32_t s_entry(uint32_t e, bool repl) { return repl ? (((e >> 1) << 7) | ((e & 1u) << 1)) : (e << 1); }
 
-// The 14 packed updates of an iteration (7 even-diagonal registers, then 7 odd ones) are numbered f = 0 .. 13.  The two
-// table fetches of update f + kQuadDist are issued right before the arithmetic of update f (they depend on the string
-// windows only, not on cell values), into a ring of kQuadDist register pairs: every fetch has kQuadDist updates of
-// arithmetic between issue and use — with 4 warps per scheduler nothing else would cover the shared-memory latency —
-// and each warp's instruction stream alternates between the ALU pipe (min-plus) and the FMA / LSU pipes (addresses,
-// fetches) instead of running them in separate bursts.
-constexpr int kQuadDist = 7;
-
-// issue the fetches of update g (0 .. 13 in the frame of iteration tt; 14 .. 27 = update g - 14 of iteration tt + 1)
-template <int G>
-__device__ __forceinline__ void quad_fetch(int tt, const uint32_t (&lw)[kQuadH], const uint32_t (&sw)[kQuadH], const FillConst fc,
-                                           uint32_t &lo, uint32_t &hi)
-{
-    constexpr int H = kQuadH, Q = H / 2;
-    constexpr int g = G % 14, odd = g >= 7 ? 1 : 0, u = g - 7 * odd;
-    const int t2 = tt + G / 14;
-    lo = lds_u16(imad(lw[(t2 - u + 2 * H) % H], fc.lstride, sw[(t2 + u + odd) % H]));
-    hi = lds_u16(imad(lw[(t2 - u - Q + 2 * H) % H], fc.lstride, sw[(t2 + u + Q + odd) % H]));
-}
+// Fetch distance of the multi-pair fill (see fetch16 / run_chunk16: the fetches of update f + D are issued before the
+// arithmetic of update f).  With 4 warps per scheduler nothing else covers the shared-memory latency; half an iteration
+// ahead measured as good as a whole batch up front.
+template <int H> __host__ __device__ constexpr int multi_dist() { return H >= 16 ? 4 : (H / 2 < 7 ? H / 2 : 7); }   // (H = 16: the register file)
 
 // s_entry without the branch: e * c1 - (e & 1) * c2 with (c1, c2) = (64, 62) for the replicated table, (2, 0) otherwise
 __device__ __forceinline__ uint32_t s_entry2(uint32_t e, uint32_t c1, uint32_t c2neg, uint32_t base)
@@ -442,14 +428,14 @@ __device__ __forceinline__ uint32_t s_entry2(uint32_t e, uint32_t c1, uint32_t c
     return imad(e & 1u, c2neg, imad(e, c1, base));
 }
 
-template <bool TAIL>
-__device__ __forceinline__ void run_chunk16q(uint32_t (&R)[kQuadH], const uint32_t (&penc)[kQuadH], uint32_t (&dw)[kQuadH],
-                                             uint32_t (&lw)[kQuadH], uint32_t (&sw)[kQuadH], uint32_t (&p_lo)[kQuadDist],
-                                             uint32_t (&p_hi)[kQuadDist], const FillConst fc, uint32_t tab_lane, uint32_t sc1, uint32_t sc2,
+template <int LP, int H, bool TAIL>
+__device__ __forceinline__ void run_chunk16q(uint32_t (&R)[H], const uint32_t (&penc)[H], uint32_t (&dw)[H],
+                                             uint32_t (&lw)[H], uint32_t (&sw)[H], uint32_t (&p_lo)[multi_dist<H>()],
+                                             uint32_t (&p_hi)[multi_dist<H>()], const FillConst fc, uint32_t tab_lane, uint32_t sc1, uint32_t sc2,
                                              const char *&lptr, const char *&sptr, int n_iter, uint32_t *&out)
 {
-    constexpr int H = kQuadH, CH = 8, D = kQuadDist;
-    static_assert(D >= 1 && D <= 7, "fetch distance");
+    constexpr int U = H / 2, CH = 8, D = multi_dist<H>();
+    static_assert(D >= 1 && D <= U && H > CH && H % 2 == 0, "shape");
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
@@ -458,55 +444,34 @@ __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[kQuadH], const uint32
         const uint32_t l_new = ld_u8(lptr + r);
         uint32_t edge = 0;
 #pragma unroll
-        for (int f = 0; f < 14; ++f) {
+        for (int f = 0; f < H; ++f) {
             // the window slots are replaced once nothing issued later still wants the old element: the lesser string's
             // before the first odd-diagonal fetch of this iteration, the longer string's before the first fetch of the next
-            if (f + D == 7) sw[tt] = s_new;
-            if (f + D == 14) lw[(tt + 1) % H] = l_new;
+            if (f + D == U) sw[tt] = s_new;
+            if (f + D == H) lw[(tt + 1) % H] = l_new;
             const uint32_t sub2 = imad(p_hi[f % D], fc.k64k, p_lo[f % D]);
-            switch (f + D) {        // (compile-time: the loop is unrolled)
-                case 1: quad_fetch<1>(tt, lw, sw, fc, p_lo[1 % D], p_hi[1 % D]); break;
-                case 2: quad_fetch<2>(tt, lw, sw, fc, p_lo[2 % D], p_hi[2 % D]); break;
-                case 3: quad_fetch<3>(tt, lw, sw, fc, p_lo[3 % D], p_hi[3 % D]); break;
-                case 4: quad_fetch<4>(tt, lw, sw, fc, p_lo[4 % D], p_hi[4 % D]); break;
-                case 5: quad_fetch<5>(tt, lw, sw, fc, p_lo[5 % D], p_hi[5 % D]); break;
-                case 6: quad_fetch<6>(tt, lw, sw, fc, p_lo[6 % D], p_hi[6 % D]); break;
-                case 7: quad_fetch<7>(tt, lw, sw, fc, p_lo[7 % D], p_hi[7 % D]); break;
-                case 8: quad_fetch<8>(tt, lw, sw, fc, p_lo[8 % D], p_hi[8 % D]); break;
-                case 9: quad_fetch<9>(tt, lw, sw, fc, p_lo[9 % D], p_hi[9 % D]); break;
-                case 10: quad_fetch<10>(tt, lw, sw, fc, p_lo[10 % D], p_hi[10 % D]); break;
-                case 11: quad_fetch<11>(tt, lw, sw, fc, p_lo[11 % D], p_hi[11 % D]); break;
-                case 12: quad_fetch<12>(tt, lw, sw, fc, p_lo[12 % D], p_hi[12 % D]); break;
-                case 13: quad_fetch<13>(tt, lw, sw, fc, p_lo[13 % D], p_hi[13 % D]); break;
-                case 14: quad_fetch<14>(tt, lw, sw, fc, p_lo[14 % D], p_hi[14 % D]); break;
-                case 15: quad_fetch<15>(tt, lw, sw, fc, p_lo[15 % D], p_hi[15 % D]); break;
-                case 16: quad_fetch<16>(tt, lw, sw, fc, p_lo[16 % D], p_hi[16 % D]); break;
-                case 17: quad_fetch<17>(tt, lw, sw, fc, p_lo[17 % D], p_hi[17 % D]); break;
-                case 18: quad_fetch<18>(tt, lw, sw, fc, p_lo[18 % D], p_hi[18 % D]); break;
-                case 19: quad_fetch<19>(tt, lw, sw, fc, p_lo[19 % D], p_hi[19 % D]); break;
-                default: quad_fetch<20>(tt, lw, sw, fc, p_lo[20 % D], p_hi[20 % D]); break;
-            }
-            if (f < 7) {            // ---- even diagonals (registers with even m): anti-diagonal s = 2t
+            fetch16<2 * H>(tt, f + D, lw, sw, fc, p_lo[(f + D) % D], p_hi[(f + D) % D]);
+            if (f < U) {            // ---- even diagonals (registers with even m): anti-diagonal s = 2t
                 const int m = 2 * f;
                 if (f == 0) {
                     const uint32_t prev = __shfl_up_sync(kFull, R[H - 1], 1);
                     edge = __funnelshift_l(prev, R[H - 1], 16);      // (own diag H-1) << 16 | (left lane's diag B-1)
                 }
                 const uint32_t left = (m == 0) ? edge : R[m > 0 ? m - 1 : 0];
-                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1]);
+                const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, R[m + 1 < H ? m + 1 : H - 1]);
                 const uint32_t mn = __viaddmin_u16x2(left, 0x00010001u, t1);
                 R[m] = and_or(mn, 0xfffcfffcu, penc[m]);
                 const uint32_t c2 = mn & 0x00030003u;
                 dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
             } else {                // ---- odd diagonals: anti-diagonal s = 2t + 1
-                const int m = 2 * (f - 7) + 1;
-                if (f == 7) {
+                const int m = 2 * (f - U) + 1;
+                if (f == U) {
                     const uint32_t next = __shfl_down_sync(kFull, R[0], 1);
                     edge = __funnelshift_r(R[0], next, 16);          // (right lane's diag 0) << 16 | (own diag H)
                 }
                 const uint32_t up = (m == H - 1) ? edge : R[m + 1 < H ? m + 1 : H - 1];
                 const uint32_t t1 = __viaddmin_u16x2(R[m], sub2, up);
-                const uint32_t mn = __viaddmin_u16x2(R[m - 1], 0x00010001u, t1);
+                const uint32_t mn = __viaddmin_u16x2(R[m - 1 >= 0 ? m - 1 : 0], 0x00010001u, t1);
                 R[m] = and_or(mn, 0xfffcfffcu, penc[m]);
                 const uint32_t c2 = mn & 0x00030003u;
                 dw[m] = (r == 0) ? c2 : imad(dw[m], fc.k4, c2);
@@ -516,7 +481,7 @@ __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[kQuadH], const uint32
             const int sh = 2 * (CH - 1 - r);          // left-align a partial group
 #pragma unroll
             for (int m = 0; m < H; m += 2) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m] << sh, dw[m + 1] << sh);
-            out += kQuadRow;
+            out += 32 * H;
         }
     }
     lptr += CH;
@@ -525,18 +490,19 @@ __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[kQuadH], const uint32
     rot16<H, CH % H>(sw);
 }
 
-// rebase16 over the 8 lanes of one pair
-__device__ __forceinline__ bool rebase16q(uint32_t (&R)[kQuadH], int &total_shift, uint32_t spread_limit)
+// rebase16 over the LP lanes of one pair
+template <int LP, int H>
+__device__ __forceinline__ bool rebase16q(uint32_t (&R)[H], int &total_shift, uint32_t spread_limit)
 {
     uint32_t mx = 0u, mnv = 0xffffffffu;
 #pragma unroll
-    for (int m = 0; m < kQuadH; ++m) {
+    for (int m = 0; m < H; ++m) {
         mx = __vmaxu2(mx, R[m] ^ 0x80008000u);
         mnv = __vminu2(mnv, R[m]);
     }
     uint32_t hi = max(mx & 0xffffu, mx >> 16), lo = min(mnv & 0xffffu, mnv >> 16);
 #pragma unroll
-    for (int d = kQuadLanes / 2; d > 0; d >>= 1) {
+    for (int d = LP / 2; d > 0; d >>= 1) {
         hi = max(hi, __shfl_xor_sync(kFull, hi, d));
         lo = min(lo, __shfl_xor_sync(kFull, lo, d));
     }
@@ -545,7 +511,7 @@ __device__ __forceinline__ bool rebase16q(uint32_t (&R)[kQuadH], int &total_shif
     const int delta = (int)kTop16 - (int)maxf;
     const uint32_t d2 = ((uint32_t)delta & 0xffffu) * 0x00010001u;
 #pragma unroll
-    for (int m = 0; m < kQuadH; ++m) {
+    for (int m = 0; m < H; ++m) {
         const uint32_t unreach = ((R[m] >> 15) & 0x00010001u) * 0xffffu;
         R[m] = __vadd2(R[m], d2 & ~unreach);
     }
@@ -554,13 +520,14 @@ __device__ __forceinline__ bool rebase16q(uint32_t (&R)[kQuadH], int &total_shif
 }
 
 // g, Lb, Sb: of the lane's own pair.  tmax: iterations of the group (warp-uniform).  slot: the group's direction words.
-__device__ __noinline__ uint32_t fill_quad16(const Geom g, int tmax, const FillConst fc, uint32_t tab_lane, bool repl,
+template <int LP, int H>
+__device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const FillConst fc, uint32_t tab_lane, bool repl,
                                              const char *Lb, const char *Sb, uint32_t *slot, int lane, int sub4gg,
                                              uint32_t spread_limit)
 {
-    constexpr int B = kQuadB, H = kQuadH;
+    constexpr int B = 2 * H, D = multi_dist<H>();
     uint32_t R[H], penc[H], dw[H], lw[H], sw[H];
-    const int ln = lane & (kQuadLanes - 1);
+    const int ln = lane & (LP - 1);
     const int qb = ln * B;
 #pragma unroll
     for (int m = 0; m < H; ++m) {
@@ -589,26 +556,21 @@ __device__ __noinline__ uint32_t fill_quad16(const Geom g, int tmax, const FillC
     const char *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
     const uint32_t sc1 = repl ? 64u : 2u, sc2 = repl ? (uint32_t)-62 : 0u;
-    uint32_t p_lo[kQuadDist], p_hi[kQuadDist];
-    quad_fetch<0>(0, lw, sw, fc, p_lo[0], p_hi[0]);
-    if constexpr (kQuadDist > 1) quad_fetch<1 % 14>(0, lw, sw, fc, p_lo[1 % kQuadDist], p_hi[1 % kQuadDist]);
-    if constexpr (kQuadDist > 2) quad_fetch<2 % 14>(0, lw, sw, fc, p_lo[2 % kQuadDist], p_hi[2 % kQuadDist]);
-    if constexpr (kQuadDist > 3) quad_fetch<3 % 14>(0, lw, sw, fc, p_lo[3 % kQuadDist], p_hi[3 % kQuadDist]);
-    if constexpr (kQuadDist > 4) quad_fetch<4 % 14>(0, lw, sw, fc, p_lo[4 % kQuadDist], p_hi[4 % kQuadDist]);
-    if constexpr (kQuadDist > 5) quad_fetch<5 % 14>(0, lw, sw, fc, p_lo[5 % kQuadDist], p_hi[5 % kQuadDist]);
-    if constexpr (kQuadDist > 6) quad_fetch<6 % 14>(0, lw, sw, fc, p_lo[6 % kQuadDist], p_hi[6 % kQuadDist]);
+    uint32_t p_lo[D], p_hi[D];
+#pragma unroll
+    for (int g0 = 0; g0 < D; ++g0) fetch16<B>(0, g0, lw, sw, fc, p_lo[g0], p_hi[g0]);
     const int nfull = tmax / 8, rem = tmax % 8;
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
-        if (c && c % 4 == 0) ok = rebase16q(R, total_shift, spread_limit) && ok;       // every 32 iterations
-        run_chunk16q<false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, 8, out);
+        if (c && c % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit) && ok;       // every 32 iterations
+        run_chunk16q<LP, H, false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, 8, out);
     }
     if (rem) {
-        if (nfull && nfull % 4 == 0) ok = rebase16q(R, total_shift, spread_limit) && ok;
-        run_chunk16q<true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, rem, out);
+        if (nfull && nfull % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit) && ok;
+        run_chunk16q<LP, H, true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, rem, out);
     }
-    ok = rebase16q(R, total_shift, spread_limit) && ok;
+    ok = rebase16q<LP, H>(R, total_shift, spread_limit) && ok;
     const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
     const int m_last = q_last % B;
     uint32_t v = 0;
@@ -617,7 +579,7 @@ __device__ __noinline__ uint32_t fill_quad16(const Geom g, int tmax, const FillC
         if (m == m_last) v = R[m] & 0xffffu;
         if (m + H == m_last) v = R[m] >> 16;
     }
-    v = __shfl_sync(kFull, v, (lane & ~(kQuadLanes - 1)) + q_last / B);
+    v = __shfl_sync(kFull, v, (lane & ~(LP - 1)) + q_last / B);
     if (!ok) return kOverflow16;
     const int x4 = (int)(v & 0x7ffcu) - (int)kTop16 - total_shift;
     return (uint32_t)((int)kBias4 + x4) | 1u;
@@ -651,22 +613,23 @@ __device__ __forceinline__ void qwalk_step(QWalk &x)
         else { x.s -= 1; x.q += (code == 1u) ? 1 : -1; x.sft = 16; }      // 1: consume longer (i--), 2: consume lesser (j--)
     }
 }
+template <int LP, int H>
 __device__ __forceinline__ void trace_two16q(QWalk &a, QWalk &b)
 {
     while (a.s > 0 || b.s > 0) {
         const bool la = a.s > 0 && a.sft == 16, lb = b.s > 0 && b.sft == 16;
-        // diagonal q = 14 * h14 + r: lane h14 >> 1, register r, half h14 & 1 -> word 14 * lane + r of the pair's 112
+        // diagonal q = H * h + r: lane h >> 1, register r, half h & 1 -> word H * lane + r of the pair's LP * H
         const int ta = (a.s - (a.q & 1)) >> 1, tb = (b.s - (b.q & 1)) >> 1;
-        const uint32_t ha = (uint32_t)a.q / (uint32_t)kQuadH, hb = (uint32_t)b.q / (uint32_t)kQuadH;
-        const uint32_t *pa = a.dirw + ((uint32_t)(ta >> 3) * kQuadRow + (uint32_t)a.seg * (kQuadLanes * kQuadH) +
-                                       (uint32_t)a.q - (uint32_t)kQuadH * ((ha + 1u) >> 1));
-        const uint32_t *pb = b.dirw + ((uint32_t)(tb >> 3) * kQuadRow + (uint32_t)b.seg * (kQuadLanes * kQuadH) +
-                                       (uint32_t)b.q - (uint32_t)kQuadH * ((hb + 1u) >> 1));
+        const uint32_t ha = (uint32_t)a.q / (uint32_t)H, hb = (uint32_t)b.q / (uint32_t)H;
+        const uint32_t *pa = a.dirw + ((uint32_t)(ta >> 3) * (32u * H) + (uint32_t)a.seg * (uint32_t)(LP * H) +
+                                       (uint32_t)a.q - (uint32_t)H * ((ha + 1u) >> 1));
+        const uint32_t *pb = b.dirw + ((uint32_t)(tb >> 3) * (32u * H) + (uint32_t)b.seg * (uint32_t)(LP * H) +
+                                       (uint32_t)b.q - (uint32_t)H * ((hb + 1u) >> 1));
         uint32_t wa = 0, wb = 0;
         if (la) wa = __ldcg(pa);
         if (lb) wb = __ldcg(pb);
-        if (la && ta >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa - kQuadRow));
-        if (lb && tb >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb - kQuadRow));
+        if (la && ta >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa - (32u * H)));
+        if (lb && tb >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb - (32u * H)));
         if (la) { a.w = wa >> (16 * (ha & 1u)); a.sft = 2 * (7 - (ta & 7)); }
         if (lb) { b.w = wb >> (16 * (hb & 1u)); b.sft = 2 * (7 - (tb & 7)); }
         qwalk_step(a);
@@ -1138,42 +1101,47 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Four pairs per warp (fill_quad16).  Takes groups of four consecutive pairs straight from the batch; a group all of
-// whose pairs have a band of 129 .. 223 diagonals, fit the staging windows and need about the same number of
-// iterations is swept at once, every other pair goes to single_list for the narrow kernel launched next.
-// Shared memory: [sub4 table | cgap | gapc | per warp: flags, nal, off, pair, ops (5 x 32 words) + 4 string windows].
+// Several pairs per warp (fill_multi16<LP, H>: 32 / LP pairs, LP lanes x 2H diagonals each).  Takes groups of consecutive
+// pairs — straight from the batch, or from the list an earlier kernel of this family left over; a group all of whose pairs
+// have a band this shape is made for, fit the staging windows and need about the same number of iterations is swept at
+// once, every other pair goes to the output list for the next kernel (another shape, then the narrow kernel).
+// Shared memory: [sub4 table | cgap | gapc | per warp: group / pair records (640 bytes) + 32 / LP string windows].
 // ---------------------------------------------------------------------------------------------
+template <int LP>
 __device__ __forceinline__ bool first_is_long_seg(const uint8_t *p1, uint32_t n1, const uint8_t *p2, uint32_t n2, int lane)
 {
-    const int ln = lane & (kQuadLanes - 1), sb = lane & ~(kQuadLanes - 1);
+    const int ln = lane & (LP - 1), sb = lane & ~(LP - 1);
     bool decided = n1 != n2 || n1 == 0, res = n1 >= n2;
-    for (uint32_t base = 0; __any_sync(kFull, !decided); base += kQuadLanes) {
+    for (uint32_t base = 0; __any_sync(kFull, !decided); base += LP) {
         const uint32_t i = base + ln;
         uint32_t a = 0, b = 0;
         if (!decided && i < n1) { a = __ldg(p1 + i); b = __ldg(p2 + i); }
-        const unsigned diff = (__ballot_sync(kFull, a != b) >> sb) & ((1u << kQuadLanes) - 1u);
+        const unsigned diff = (__ballot_sync(kFull, a != b) >> sb) & ((1u << LP) - 1u);
         const int src = diff ? sb + __ffs(diff) - 1 : lane;
         const uint32_t aa = __shfl_sync(kFull, a, src), bb = __shfl_sync(kFull, b, src);
         if (!decided) {
             if (diff) { res = aa > bb; decided = true; }
-            else if (base + kQuadLanes >= n1) { res = true; decided = true; }
+            else if (base + LP >= n1) { res = true; decided = true; }
         }
     }
     return res;
 }
 
 // PROFILE: per-phase cycle counts into p.phase_cycles (an instantiation of its own: the counters cost registers)
-template <bool PROFILE>
-__global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearParams p)
+template <int LP, int H, bool PROFILE>
+__global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearParams p)
 {
-    constexpr int NP = kQuadPairs, LP = kQuadLanes;
+    constexpr int NP = 32 / LP, B = 2 * H;
+    // bands this shape takes: more diagonals than the next smaller shape (or the narrow kernel's B = 2) holds
+    constexpr int kLow = LP == 8 ? 128 : 64;
     const TcmDev &tcm = p.tcm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int seg = lane / LP, ln = lane % LP;
     const int dim = 1 << tcm.a;
     const BatchDev &b = p.b;
-    const uint32_t n_work = b.n_pairs;
+    const uint32_t n_work = p.multi_in_list ? *p.multi_in_count : b.n_pairs;
     if (n_work == 0) return;
+    const uint32_t *in_list = p.multi_in_list;
 
     char *tab = smem;
     uint32_t *s_cgap = reinterpret_cast<uint32_t *>(smem + tcm.sub4_bytes);
@@ -1185,8 +1153,8 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
     uint32_t *g_off = reinterpret_cast<uint32_t *>(warp_base + (size_t)warp * per_warp);
     uint32_t *g_ops = g_off + 16, *g_opw = g_off + 32, *s_pair = g_off + 48;
     uint16_t *s_nal = reinterpret_cast<uint16_t *>(g_off + 112);
-    // (each pair's window starts one bank further than the previous one's: with equal geometries the four segments'
-    // window loads would otherwise hit the same 8 banks)
+    // (each pair's window starts one bank further than the previous one's: with equal geometries the segments' window
+    // loads would otherwise hit the same banks)
     uint8_t *win = reinterpret_cast<uint8_t *>(g_off) + 640 + (size_t)seg * p.seq_cap + 4 * seg;
 
     for (uint32_t i = threadIdx.x; i < tcm.sub4_bytes / 16; i += blockDim.x)
@@ -1208,7 +1176,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
     auto phase = [&](int i) { if constexpr (PROFILE) { const long long t = clock64(); ph[i] += (unsigned long long)(t - ph_t); ph_t = t; } };
     const size_t warp_global = (size_t)blockIdx.x * nwarps + warp;
     uint32_t *arena = p.arena + warp_global * (size_t)p.quad_arena_words;
-    unsigned int *counter = p.counter + 4;
+    unsigned int *counter = p.multi_counter;
     const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len || b.out_ungapped;
     const uint32_t emask = (uint32_t)dim - 1u;
 
@@ -1240,8 +1208,9 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
                 if (base >= n_work) exhausted = true;
                 else {
                     nxt = base;
-                    const uint32_t kn = base + (uint32_t)seg;
-                    if (kn < n_work) {
+                    const uint32_t kx = base + (uint32_t)seg;
+                    if (kx < n_work) {
+                        const uint32_t kn = in_list ? (in_list[kx] & 0x7fffffffu) : kx;
                         const uint8_t *q1 = b.elems + b.off1[kn], *q2 = b.elems + b.off2[kn];
                         const uint32_t m1 = b.len1[kn], m2 = b.len2[kn];
                         for (uint32_t o = 128u * ln; m1 && o < m1 + 127u; o += 128u * LP)
@@ -1252,10 +1221,12 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
                 }
             }
             const bool have = pend + (uint32_t)seg < n_work;
-            const uint32_t k = have ? pend + (uint32_t)seg : pend;
+            const uint32_t kx = have ? pend + (uint32_t)seg : pend;
+            const uint32_t entry = in_list ? in_list[kx] : kx;          // (bit 31: already marked for the 32-bit fill)
+            const uint32_t k = entry & 0x7fffffffu;
             const uint32_t n1 = b.len1[k], n2 = b.len2[k];
             const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
-            const bool fl = first_is_long_seg(p1, n1, p2, n2, lane);
+            const bool fl = first_is_long_seg<LP>(p1, n1, p2, n2, lane);
             const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
             const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
             int tmax = g.T;
@@ -1265,14 +1236,14 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
                 tmax = max(tmax, __shfl_xor_sync(kFull, tmax, d));
                 opw = max(opw, __shfl_xor_sync(kFull, opw, d));
             }
-            const SeqLayout sl = seq_layout_quad(g, tmax);
-            const uint32_t dirw = quad_dir_words(tmax);
+            const SeqLayout sl = seq_layout_multi<LP, H>(g, tmax);
+            const uint32_t dirw = multi_dir_words<H>(tmax);
             const uint32_t need = (dirw + NP * opw + 3u) & ~3u;
-            const bool elig = have && g.wb + 1 <= LP * kQuadB && g.wb + 1 > 128 && g.sh > 8 &&
-                              (uint32_t)(sl.sizeL + sl.sizeS) + 16u <= p.seq_cap && (tmax - g.T) * 8 <= tmax &&
+            const bool elig = have && !(entry >> 31) && g.wb + 1 <= LP * B && g.wb + 1 > kLow && g.sh > 8 &&
+                              (uint32_t)(sl.sizeL + sl.sizeS) + 4u * NP <= p.seq_cap && (tmax - g.T) * 8 <= tmax &&
                               need <= p.quad_arena_words && g.lg + g.sh < 65536 && k < (1u << 30);
             if (!__all_sync(kFull, elig)) {
-                if (ln == 0 && have) p.single_list[atomicAdd(p.single_count, 1u)] = k;
+                if (ln == 0 && have) p.single_list[atomicAdd(p.single_count, 1u)] = entry;
                 pend = kNone;
                 continue;
             }
@@ -1331,7 +1302,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
             __syncwarp();
             phase(0);
 
-            const uint32_t fw = fill_quad16(g, tmax, fc, tab_lane, repl, reinterpret_cast<const char *>(Lr + sl.offL),
+            const uint32_t fw = fill_multi16<LP, H>(g, tmax, fc, tab_lane, repl, reinterpret_cast<const char *>(Lr + sl.offL),
                                             reinterpret_cast<const char *>(Sr + sl.offS), slot, lane, tcm.sub4_gapgap,
                                             tcm.spread16);
             phase(1);
@@ -1374,7 +1345,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_quad_kernel(const LinearPara
                     const int gi = (live ? ix : 0) / NP;
                     qwalk_init(wk[h], arena + g_off[gi], ix % NP, g.q0, g.lg, g.sh, arena + g_ops[gi] + (uint32_t)(ix % NP) * g_opw[gi], live);
                 }
-                trace_two16q(wk[0], wk[1]);
+                trace_two16q<LP, H>(wk[0], wk[1]);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (kk[h] != 0xffffffffu) {
@@ -1563,29 +1534,38 @@ cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_
 }
 
 // Host-side launchers (called from do_api.cu).
-cudaError_t launch_linear_quad(const LinearParams &p, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+// shape 0: 8 lanes x 28 diagonals (4 pairs per warp), shape 1: 4 lanes x 32 diagonals (8 pairs per warp)
+cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
     static DeviceOnce once;
     int dev = 0;
     if (once.pending(&dev)) {
-        cudaError_t e = cudaFuncSetAttribute(do_linear_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(do_linear_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
+        const void *fns[] = {(const void *)do_linear_multi_kernel<8, 14, false>, (const void *)do_linear_multi_kernel<8, 14, true>,
+                             (const void *)do_linear_multi_kernel<4, 16, false>, (const void *)do_linear_multi_kernel<4, 16, true>};
+        for (const void *f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+        }
         once.mark(dev);
     }
-    if (p.phase_cycles) do_linear_quad_kernel<true><<<grid, block, smem_bytes, stream>>>(p);
-    else                do_linear_quad_kernel<false><<<grid, block, smem_bytes, stream>>>(p);
+    if (shape == 0) {
+        if (p.phase_cycles) do_linear_multi_kernel<8, 14, true><<<grid, block, smem_bytes, stream>>>(p);
+        else                do_linear_multi_kernel<8, 14, false><<<grid, block, smem_bytes, stream>>>(p);
+    } else {
+        if (p.phase_cycles) do_linear_multi_kernel<4, 16, true><<<grid, block, smem_bytes, stream>>>(p);
+        else                do_linear_multi_kernel<4, 16, false><<<grid, block, smem_bytes, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
-// staging bytes one pair of a four-pair group may need for strings of up to max_len elements
-uint32_t quad_seq_cap_for(int max_len)
+// staging bytes one pair of a multi-pair group may need for strings of up to max_len elements (shape as above)
+uint32_t multi_seq_cap_for(int max_len, int shape)
 {
+    const int lanes_h = shape == 0 ? 8 * 14 : 4 * 16;
     const int tpad = (max_len + 1 + 15) & ~15;
-    const int q0h = 16 * 8 + 1;                       // q0 / 2 <= wb / 2 <= 112
-    const int sizeL = kQuadLanes * kQuadH + tpad + q0h + 8;
-    const int sizeS = q0h + tpad + kQuadLanes * kQuadH + 8;
+    const int q0h = (shape == 0 ? 224 : 128) / 2 + 1;           // q0 / 2 <= wb / 2
+    const int sizeL = lanes_h + tpad + q0h + 8;
+    const int sizeS = q0h + tpad + lanes_h + 8;
     return (uint32_t)((sizeS + sizeL + 15) & ~15);
 }
 

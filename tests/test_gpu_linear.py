@@ -364,18 +364,18 @@ def test_packed_fill_equals_32bit_fill(oracle_mod, gpu_ctx, monkeypatch):
         _check_batch(o, gpu_ctx, gpu_ctx.tcm(sig), pairs[:60] + pairs[-2:])
 
 
-def _grouped_pairs(rng, n_groups, lo=330, hi=1040):
+def _grouped_pairs(rng, n_groups, lo=330, hi=1040, per_group=4):
     """Groups of four consecutive pairs of about the same size (what the four-pairs-per-warp kernel sweeps at once),
     with ragged members: unequal operands, related strings, ambiguity, the odd group that does not qualify."""
     from tests.helpers import random_string
     pairs = []
     for gi in range(n_groups):
         base = int(rng.integers(lo, hi))
-        for _ in range(4):
+        for _ in range(per_group):
             n1 = max(1, base + int(rng.integers(-25, 25)))
             n2 = max(1, n1 - int(rng.integers(0, 40))) if rng.random() < 0.7 else n1
             if gi % 11 == 10 and rng.random() < 0.3:
-                n2 = int(rng.integers(1, 200))                 # a member that breaks up its group
+                n2 = int(rng.integers(1, max(2, lo // 2)))     # a member that breaks up its group
             s1 = random_string(rng, n1, 5, 0.15)
             if rng.random() < 0.5:
                 s2 = s1[:n2].copy()
@@ -387,17 +387,24 @@ def _grouped_pairs(rng, n_groups, lo=330, hi=1040):
     return pairs
 
 
+@pytest.mark.parametrize("shape", ["4x8x28", "8x4x32", "mixed"])
 @pytest.mark.parametrize("name", ["discrete", "l1", "1:2", "2:1", "weird"])
-def test_four_pairs_per_warp_kernel(oracle_mod, gpu_ctx, monkeypatch, name):
-    """do_linear_quad_kernel (bands of 129..223 diagonals, four pairs per warp) against the CPU side — the compiled
-    reference when present — and against the one-pair-per-warp kernels on the same batch."""
+def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, shape):
+    """do_linear_multi_kernel — four pairs per warp for bands of 129..223 diagonals, eight for 65..127 — against the CPU
+    side (the compiled reference when present) and against the one-pair-per-warp kernels on the same batch."""
     import zlib
     import pcg_b200 as P
     sig = tcm_matrix(name)
     rng = np.random.default_rng(4242)
-    pairs = _grouped_pairs(rng, 150)
+    if shape == "4x8x28":
+        pairs = _grouped_pairs(rng, 150)
+    elif shape == "8x4x32":
+        pairs = _grouped_pairs(rng, 120, lo=30, hi=290, per_group=8)
+    else:
+        pairs = _grouped_pairs(rng, 60) + _grouped_pairs(rng, 60, lo=30, hi=290, per_group=8) + _grouped_pairs(rng, 20, lo=900, hi=1400)
+        rng.shuffle(pairs)
     pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
-    gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=32, max_len=1100, max_b=32, arena_words=0)
+    gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=32, max_len=1500 if shape == "mixed" else 1100, max_b=32, arena_words=0)
     tcm = gpu_ctx.tcm(sig)
     r = P.align2d_batch(gpu_ctx, tcm, pp, want_cells=True)
     n_launch_quad = gpu_ctx.last_kernel_ms()[1]
@@ -409,7 +416,7 @@ def test_four_pairs_per_warp_kernel(oracle_mod, gpu_ctx, monkeypatch, name):
     finally:
         monkeypatch.delenv("PCGDO_NO_QUAD")
         gpu_ctx.reload_env()
-    assert n_launch_quad == n_launch_single + 1                # the extra kernel did run
+    assert n_launch_quad == n_launch_single + 2                # the two extra kernels did run
     assert np.array_equal(r.cost, r1.cost) and np.array_equal(r.out_len, r1.out_len)
     assert np.array_equal(r.cells, r1.cells)
     kind = "reference" if oracle_mod.Reference.available() else "port"
