@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-L = 1000
+L = int(os.environ.get("BENCH_L", "1000"))      # (BENCH_L: experiments on other string lengths; the bench line is L = 1000)
 SEED = 20260101
 ALG_OPS_PER_CELL = 8          # 3 adds + 2 min + 2 compare/select + 1 table fetch
 

@@ -384,33 +384,37 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     if (arena_words > 0xfffffff0u) arena_words = 0xfffffff0u;
     int rc;
     if ((rc = pcgdo_ensure(ctx, ctx->arena, (size_t)grid * warps_max * arena_words * 4))) return rc;
-    if ((rc = pcgdo_ensure(ctx, ctx->counters, 64))) return rc;
+    if ((rc = pcgdo_ensure(ctx, ctx->counters, 128))) return rc;
     // (growing a buffer frees the old one, which synchronises the device: callers that enqueue many batches back to
     // back — the host pipeline, the forest — size these for their largest batch before the first one)
     if ((rc = pcgdo_ensure(ctx, ctx->overflow, (size_t)bd.n_pairs * 4))) return rc;
     if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4))) return rc;
     // Several pairs per warp (do_linear_multi_kernel, two shapes) first, when the TCM qualifies for the packed fill; what
     // one launch leaves over goes to the next through a list on the device, and last to the narrow kernel.
-    uint32_t cap_m[2] = {0, 0};
+    uint32_t cap_m[3] = {0, 0, 0};
     int warps_q = 0;
     if (tcm->dev.pack_ok && !ctx->knobs.no_pack16 && !ctx->knobs.no_quad && bd.n_pairs >= 4) {
         const size_t dim = (size_t)1 << tcm->a;
         const size_t fixed = tcm->dev.sub4_bytes + 2 * dim * 4;
         warps_q = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
         const size_t room = (227 * 1024 - fixed) / warps_q;
-        for (int shape = 0; shape < 2; ++shape) {
-            const uint32_t np = shape == 0 ? 4u : 8u;
+        for (int shape = 0; shape < 3; ++shape) {
+            const uint32_t np = shape == 0 ? 4u : (shape == 1 ? 8u : 6u);
             const uint32_t want = (multi_seq_cap_for(ctx->max_len, shape) + 15u) & ~15u;
             if (room >= 640 + np * 256) cap_m[shape] = std::min<uint32_t>((uint32_t)((room - 640) / np) & ~15u, want);
         }
-        if (ctx->knobs.quad_flags & 4u) cap_m[1] = 0;          // experiment switches: one shape only
-        if (ctx->knobs.quad_flags & 8u) cap_m[0] = 0;
+        // The 8-pairs-per-warp shape (4 lanes x 32 diagonals, bands of 65 .. 127) is built and tested but OFF unless asked
+        // for (PCGDO_QUAD_FLAGS bit 5): on 256-element strings it only equals the narrow kernel's B = 4 fill at 32 warps per
+        // SM (1989 vs 1999 GCUPS) and costs config 5 6 % (1468 vs 1558 tree-evals/s).
+        if (!(ctx->knobs.quad_flags & 32u)) cap_m[1] = 0;
+        if (ctx->knobs.quad_flags & 8u) cap_m[0] = 0;          // experiment switches: without one shape
+        if (ctx->knobs.quad_flags & 16u) cap_m[2] = 0;
     }
-    const bool multi = cap_m[0] || cap_m[1];
+    const bool multi = cap_m[0] || cap_m[1] || cap_m[2];
     if (multi && ((rc = pcgdo_ensure(ctx, ctx->singles, (size_t)bd.n_pairs * 4)) ||
                   (rc = pcgdo_ensure(ctx, ctx->singles2, (size_t)bd.n_pairs * 4))))
         return rc;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 32, st));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, reset_overflow ? 64 : 16, st));
 
     LinearParams p{};
     p.tcm = tcm->dev;
@@ -442,18 +446,22 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
         p.quad_arena_words = (uint32_t)std::min<size_t>((arena_words * warps_max / warps_q) & ~(size_t)3, 0xfffffff0u);
         const size_t dim = (size_t)1 << tcm->a;
         // the shape most pairs are expected to take goes first (it reads the batch itself): strings of a few hundred
-        // elements have bands of 65 .. 127 diagonals, ~1 kb strings 129 .. 223
-        const int order[2] = {ctx->max_len >= 320 ? 0 : 1, ctx->max_len >= 320 ? 1 : 0};
+        // elements have bands of 65 .. 139 diagonals, ~1 kb strings 141 .. 223.  Stage s hands pairs out through
+        // counter[16 + s] and leaves what it does not take in list s % 2, counted in counter[20 + s].
+        CK(cudaMemsetAsync((unsigned int *)ctx->counters.p + 16, 0, 32, st));
+        const bool big_first = ctx->max_len >= 700;
+        const int order[3] = {big_first ? 0 : 2, big_first ? 2 : 1, big_first ? 1 : 0};
         int stage = 0;
-        for (int o = 0; o < 2; ++o) {
+        for (int o = 0; o < 3; ++o) {
             const int shape = order[o];
             if (!cap_m[shape]) continue;
-            const uint32_t np = shape == 0 ? 4u : 8u;
-            p.multi_in_list = stage == 0 ? nullptr : (const uint32_t *)ctx->singles.p;
-            p.multi_in_count = stage == 0 ? nullptr : p.counter + 5;
-            p.multi_counter = p.counter + (stage == 0 ? 4 : 7);
-            p.single_list = (uint32_t *)(stage == 0 ? ctx->singles.p : ctx->singles2.p);
-            p.single_count = p.counter + (stage == 0 ? 5 : 6);
+            const uint32_t np = shape == 0 ? 4u : (shape == 1 ? 8u : 6u);
+            DevBuf &in = (stage & 1) ? ctx->singles : ctx->singles2, &outb = (stage & 1) ? ctx->singles2 : ctx->singles;
+            p.multi_in_list = stage == 0 ? nullptr : (const uint32_t *)in.p;
+            p.multi_in_count = stage == 0 ? nullptr : p.counter + 20 + (stage - 1);
+            p.multi_counter = p.counter + 16 + stage;
+            p.single_list = (uint32_t *)outb.p;
+            p.single_count = p.counter + 20 + stage;
             p.seq_cap = cap_m[shape];
             CK(launch_linear_multi(p, shape, grid, warps_q * 32,
                                    tcm->dev.sub4_bytes + 2 * dim * 4 + (size_t)warps_q * (640 + np * (size_t)cap_m[shape]), st));
@@ -519,7 +527,7 @@ extern "C" int pcgdo_align2d_batch_device(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, 
         unsigned long long h_ph[6] = {0};
         CK(cudaMemcpy(h_ph, p.phase_cycles, 48, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[pcgdo] multi-pair kernels warp-cycles: stage %llu fill %llu trace %llu emit %llu prep %llu post %llu; singles %u\n", h_ph[0], h_ph[1],
-                h_ph[2], h_ph[3], h_ph[4], h_ph[5], h_cnt[5]);
+                h_ph[2], h_ph[3], h_ph[4], h_ph[5], 0u);
     }
     // pairs the warp kernels could not hold (band wider than 1023 diagonals, strings longer than the
     // staging window, scratch larger than the arena; plus the wide queue when that kernel is disabled)

@@ -390,9 +390,9 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
 // Direction words: word[(t >> 3) * 448 + lane * 14 + m] — the diagonals of a pair are consecutive words (two diagonals 14
 // apart share a word), so the trace's next word is usually in the 32-byte sector it already holds.
 // ---------------------------------------------------------------------------------------------
-// Two shapes are built: LP = 8 lanes x 28 diagonals (H = 14 registers; 4 pairs per warp; bands of 129 .. 223 diagonals: ~1 kb
-// strings) and LP = 4 lanes x 32 diagonals (H = 16; 8 pairs per warp; bands of 65 .. 127: the ~250-element strings of tree
-// scoring).  Direction words per 8 iterations of one group: 32 * H.
+// Three shapes are built: LP = 8 lanes x 28 diagonals (H = 14 registers; 4 pairs per warp; bands of 141 .. 223 diagonals:
+// ~1 kb strings), LP = 5 lanes x 28 (6 pairs per warp, two lanes idle; bands of 129 .. 139: the ~300-element medians of tree
+// scoring) and LP = 4 lanes x 32 diagonals (H = 16; 8 pairs per warp; bands of 65 .. 127: its ~250-element leaves).  Direction words per 8 iterations of one group: 32 * H.
 template <int H> __host__ __device__ inline uint32_t multi_dir_words(int tmax) { return (uint32_t)((tmax + 7) / 8) * 32u * (uint32_t)H; }
 
 // Staging of one pair of a group: both strings as raw bytes (element 0 = padding), zero-padded for `tmax` iterations.
@@ -490,9 +490,26 @@ __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[H], const uint32_t (&
     rot16<H, CH % H>(sw);
 }
 
+// Reductions over the LP lanes of one pair (sbase = its first lane).  LP need not be a power of two (5 lanes x 28
+// diagonals serve six pairs per warp, lanes 30 / 31 idle along): then the values are gathered one by one.
+template <int LP, class F>
+__device__ __forceinline__ uint32_t seg_reduce(uint32_t v, int sbase, F f)
+{
+    if constexpr ((LP & (LP - 1)) == 0) {
+#pragma unroll
+        for (int d = LP / 2; d > 0; d >>= 1) v = f(v, __shfl_xor_sync(kFull, v, d));
+        return v;
+    } else {
+        uint32_t r = __shfl_sync(kFull, v, sbase);
+#pragma unroll
+        for (int i = 1; i < LP; ++i) r = f(r, __shfl_sync(kFull, v, sbase + i));
+        return r;
+    }
+}
+
 // rebase16 over the LP lanes of one pair
 template <int LP, int H>
-__device__ __forceinline__ bool rebase16q(uint32_t (&R)[H], int &total_shift, uint32_t spread_limit)
+__device__ __forceinline__ bool rebase16q(uint32_t (&R)[H], int &total_shift, uint32_t spread_limit, int sbase)
 {
     uint32_t mx = 0u, mnv = 0xffffffffu;
 #pragma unroll
@@ -501,11 +518,8 @@ __device__ __forceinline__ bool rebase16q(uint32_t (&R)[H], int &total_shift, ui
         mnv = __vminu2(mnv, R[m]);
     }
     uint32_t hi = max(mx & 0xffffu, mx >> 16), lo = min(mnv & 0xffffu, mnv >> 16);
-#pragma unroll
-    for (int d = LP / 2; d > 0; d >>= 1) {
-        hi = max(hi, __shfl_xor_sync(kFull, hi, d));
-        lo = min(lo, __shfl_xor_sync(kFull, lo, d));
-    }
+    hi = seg_reduce<LP>(hi, sbase, [](uint32_t x, uint32_t y) { return max(x, y); });
+    lo = seg_reduce<LP>(lo, sbase, [](uint32_t x, uint32_t y) { return min(x, y); });
     if (hi < 0x8000u) return true;
     const uint32_t maxf = hi & 0x7ffcu, minf = lo & 0xfffcu;
     const int delta = (int)kTop16 - (int)maxf;
@@ -527,7 +541,7 @@ __device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const Fill
 {
     constexpr int B = 2 * H, D = multi_dist<H>();
     uint32_t R[H], penc[H], dw[H], lw[H], sw[H];
-    const int ln = lane & (LP - 1);
+    const int ln = lane % LP, sbase = lane - ln;      // (idle lanes behind the last pair: a phantom pair, results unused)
     const int qb = ln * B;
 #pragma unroll
     for (int m = 0; m < H; ++m) {
@@ -563,14 +577,14 @@ __device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const Fill
     int total_shift = 0;
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
-        if (c && c % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit) && ok;       // every 32 iterations
+        if (c && c % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit, sbase) && ok;       // every 32 iterations
         run_chunk16q<LP, H, false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, 8, out);
     }
     if (rem) {
-        if (nfull && nfull % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit) && ok;
+        if (nfull && nfull % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit, sbase) && ok;
         run_chunk16q<LP, H, true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, rem, out);
     }
-    ok = rebase16q<LP, H>(R, total_shift, spread_limit) && ok;
+    ok = rebase16q<LP, H>(R, total_shift, spread_limit, sbase) && ok;
     const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
     const int m_last = q_last % B;
     uint32_t v = 0;
@@ -579,7 +593,7 @@ __device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const Fill
         if (m == m_last) v = R[m] & 0xffffu;
         if (m + H == m_last) v = R[m] >> 16;
     }
-    v = __shfl_sync(kFull, v, (lane & ~(LP - 1)) + q_last / B);
+    v = __shfl_sync(kFull, v, min(31, sbase + q_last / B));
     if (!ok) return kOverflow16;
     const int x4 = (int)(v & 0x7ffcu) - (int)kTop16 - total_shift;
     return (uint32_t)((int)kBias4 + x4) | 1u;
@@ -770,9 +784,12 @@ __device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *
 // 16-move word, the number of longer / lesser elements consumed by all LATER words (= earlier columns); a column's
 // element indices are then that count plus a popcount inside its own word, and passes are independent of each other
 // (two are kept in flight).  ops_s / suf: scratch in the warp's string windows, which are idle during this phase.
-__device__ __forceinline__ void emit_pair_q(const TcmDev &tcm, const uint8_t *med, const uint8_t *pL, const uint8_t *pS,
-                                            const uint32_t *ops, uint32_t nal, bool first_long, uint8_t *og, uint8_t *o1,
-                                            uint8_t *o2, int lane, uint32_t *ops_s, uint32_t *suf)
+// ou (post-order mode): the medians with the gap elements dropped; only its write positions run from pass to pass (one
+// warp scan each), no load address does.  Returns their number.
+__device__ __forceinline__ uint32_t emit_pair_q(const TcmDev &tcm, const uint8_t *med, const uint8_t *pL, const uint8_t *pS,
+                                                const uint32_t *ops, uint32_t nal, bool first_long, uint8_t *og, uint8_t *o1,
+                                                uint8_t *o2, int lane, uint32_t *ops_s, uint32_t *suf,
+                                                uint8_t *ou = nullptr, uint32_t ucap = 0)
 {
     const uint32_t gap = tcm.gap;
     const uint32_t nw = (nal + 15u) >> 4, K = (nw + 31u) >> 5;
@@ -804,16 +821,18 @@ __device__ __forceinline__ void emit_pair_q(const TcmDev &tcm, const uint8_t *me
     __syncwarp();
     const uint8_t *oany = og ? og : (o1 ? o1 : o2);
     const int mis = (int)(reinterpret_cast<uintptr_t>(oany) & 124u);
+    uint32_t base_u = 0;
 #pragma unroll 2
     for (int c0 = -mis; c0 < (int)nal; c0 += 128) {
         const int c = c0 + 4 * lane;
-        if (c < 0 || c >= (int)nal) continue;
+        const bool mine = c >= 0 && c < (int)nal;
+        if (!mine && !ou) continue;
         uint32_t xx[4], yy[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             xx[x] = 0; yy[x] = 0;
             const uint32_t r = nal - 1u - (uint32_t)(c + x);              // (wraps for columns past the end: r >= nal)
-            if (r < nal) {
+            if (c + x >= 0 && r < nal) {
                 const uint32_t v = ops_s[r >> 4], sh = 2u * (r & 15u), code = (v >> sh) & 3u;
                 const uint32_t above = (~v >> sh) >> 2, base = suf[r >> 4];
                 const uint32_t il = (base & 0xffffu) + (uint32_t)__popc((above >> 1) & 0x55555555u);
@@ -822,22 +841,42 @@ __device__ __forceinline__ void emit_pair_q(const TcmDev &tcm, const uint8_t *me
                 if (code == 0u || code == 2u) xx[x] = __ldg(pS + js);     // consume lesser
             }
         }
-        uint32_t wg = 0, wx = 0, wy = 0;
+        uint32_t wg = 0, wx = 0, wy = 0, nk = 0, keep = 0;
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             const uint32_t r = nal - 1u - (uint32_t)(c + x);
-            if (r < nal) {
+            if (c + x >= 0 && r < nal) {
                 const uint32_t md = med[((xx[x] ? xx[x] : gap) << tcm.a) | (yy[x] ? yy[x] : gap)];
                 wg |= md << (8 * x);
                 wx |= xx[x] << (8 * x);
                 wy |= yy[x] << (8 * x);
+                if (md != gap) { ++nk; keep |= 1u << x; }
             }
         }
-        if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
-        if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wx : wy;
-        if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? wy : wx;
+        if (mine) {
+            if (og) *reinterpret_cast<uint32_t *>(og + c) = wg;
+            if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wx : wy;
+            if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? wy : wx;
+        }
+        if (ou) {       // deleteGaps of the node's context, medians only
+            uint32_t inc = nk;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += o;
+            }
+            uint32_t pos = base_u + inc - nk;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if ((keep >> x) & 1u) {
+                    if (pos < ucap) ou[pos] = (uint8_t)(wg >> (8 * x));
+                    ++pos;
+                }
+            base_u += __shfl_sync(kFull, inc, 31);
+        }
     }
     __syncwarp();
+    return base_u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1108,9 +1147,9 @@ __global__ void __launch_bounds__(BMAX <= 8 ? 1024 : 512, 1) do_linear_kernel(co
 // Shared memory: [sub4 table | cgap | gapc | per warp: group / pair records (640 bytes) + 32 / LP string windows].
 // ---------------------------------------------------------------------------------------------
 template <int LP>
-__device__ __forceinline__ bool first_is_long_seg(const uint8_t *p1, uint32_t n1, const uint8_t *p2, uint32_t n2, int lane)
+__device__ __forceinline__ bool first_is_long_seg(const uint8_t *p1, uint32_t n1, const uint8_t *p2, uint32_t n2, int lane,
+                                                  int ln, int sb)
 {
-    const int ln = lane & (LP - 1), sb = lane & ~(LP - 1);
     bool decided = n1 != n2 || n1 == 0, res = n1 >= n2;
     for (uint32_t base = 0; __any_sync(kFull, !decided); base += LP) {
         const uint32_t i = base + ln;
@@ -1133,10 +1172,14 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
 {
     constexpr int NP = 32 / LP, B = 2 * H;
     // bands this shape takes: more diagonals than the next smaller shape (or the narrow kernel's B = 2) holds
-    constexpr int kLow = LP == 8 ? 128 : 64;
+    constexpr int kLow = LP == 8 ? 5 * 28 : (LP == 5 ? 128 : 64);
     const TcmDev &tcm = p.tcm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int seg = lane / LP, ln = lane % LP;
+    // lanes behind the last pair (LP = 5: lanes 30, 31) shadow the first lanes of the last pair: same loads, same window
+    // writes, results unused
+    const bool real = lane < NP * LP;
+    const int seg = real ? lane / LP : NP - 1, ln = lane % LP;
+    const bool lead = real && ln == 0;
     const int dim = 1 << tcm.a;
     const BatchDev &b = p.b;
     const uint32_t n_work = p.multi_in_list ? *p.multi_in_count : b.n_pairs;
@@ -1165,7 +1208,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
     const bool repl = tcm.repl != 0;
     const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(tab) + (repl ? 4u * lane : 0u);
     const FillConst fc = {p.k_four, p.k_minus1, p.l_stride, p.k_64k};
-    int G = (2 * p.pairs_per_warp) & ~(NP - 1);        // two walks per lane in the trace
+    int G = (2 * p.pairs_per_warp) / NP * NP;          // two walks per lane in the trace
     if (G < NP) G = NP;
     // The warps of a CTA start together and a uniform batch keeps them in step: all fill (issue-bound) and then all trace
     // (latency-bound) at the same time.  Experiment (quad_flags bit 0): a first batch of a different size per warp spreads
@@ -1226,24 +1269,29 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
             const uint32_t k = entry & 0x7fffffffu;
             const uint32_t n1 = b.len1[k], n2 = b.len2[k];
             const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
-            const bool fl = first_is_long_seg<LP>(p1, n1, p2, n2, lane);
+            const bool fl = first_is_long_seg<LP>(p1, n1, p2, n2, lane, ln, seg * LP);
             const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
             const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
             int tmax = g.T;
             uint32_t opw = ops_words(g);
-#pragma unroll
-            for (int d = LP; d < 32; d <<= 1) {
-                tmax = max(tmax, __shfl_xor_sync(kFull, tmax, d));
-                opw = max(opw, __shfl_xor_sync(kFull, opw, d));
-            }
+            tmax = __reduce_max_sync(kFull, tmax);
+            opw = __reduce_max_sync(kFull, opw);
             const SeqLayout sl = seq_layout_multi<LP, H>(g, tmax);
             const uint32_t dirw = multi_dir_words<H>(tmax);
             const uint32_t need = (dirw + NP * opw + 3u) & ~3u;
-            const bool elig = have && !(entry >> 31) && g.wb + 1 <= LP * B && g.wb + 1 > kLow && g.sh > 8 &&
+            // the group's widest band decides the shape (a narrower member rides along at this shape's width)
+            const int wmax = __reduce_max_sync(kFull, have ? g.wb + 1 : 0);
+            const bool elig = have && !(entry >> 31) && wmax <= LP * B && wmax > kLow && g.sh > 8 &&
                               (uint32_t)(sl.sizeL + sl.sizeS) + 4u * NP <= p.seq_cap && (tmax - g.T) * 8 <= tmax &&
                               need <= p.quad_arena_words && g.lg + g.sh < 65536 && k < (1u << 30);
             if (!__all_sync(kFull, elig)) {
-                if (ln == 0 && have) p.single_list[atomicAdd(p.single_count, 1u)] = entry;
+                // handed on as a block: the next kernel forms its groups from consecutive list entries, and neighbours in
+                // the batch are what is likely to be of one size
+                const uint32_t n_have = min((uint32_t)NP, n_work - pend);
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(p.single_count, n_have);
+                at = __shfl_sync(kFull, at, 0);
+                if (lead && have) p.single_list[at + (uint32_t)seg] = entry;
                 pend = kNone;
                 continue;
             }
@@ -1297,8 +1345,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
                     reinterpret_cast<uint32_t *>(Sr)[w4] = word;
                 }
             }
-#pragma unroll
-            for (int d = LP / 2; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+            csum = seg_reduce<LP>(csum, seg * LP, [](uint32_t x, uint32_t y) { return x + y; });
             __syncwarp();
             phase(0);
 
@@ -1307,17 +1354,17 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
                                             tcm.spread16);
             phase(1);
             const bool over = fw == kOverflow16;           // the sweep's finite spread left the 15-bit window:
-            if (ln == 0) {                                 //   the narrow kernel redoes the pair with the 32-bit fill
+            if (lead) {                                    //   the narrow kernel redoes the pair with the 32-bit fill
                 if (over) p.single_list[atomicAdd(p.single_count, 1u)] = k | 0x80000000u;
                 else b.cost[k] = (int32_t)((fw >> 2) - (kBias4 >> 2) + csum);
                 s_pair[cnt + seg] = k | (fl ? 0x80000000u : 0u) | (over ? 0x40000000u : 0u);
             }
             if (lane == 0) { g_off[cnt / NP] = cur; g_ops[cnt / NP] = cur + dirw; g_opw[cnt / NP] = opw; }
             if (b.cells && !over) {
-                unsigned long long c = band_cells(g, ln, LP);
-#pragma unroll
-                for (int d = LP / 2; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
-                if (ln == 0) b.cells[k] = c;
+                const unsigned long long c = band_cells(g, ln, LP);
+                const uint32_t c_lo = seg_reduce<LP>((uint32_t)(c & 0xffffffu), seg * LP, [](uint32_t x, uint32_t y) { return x + y; });
+                const uint32_t c_hi = seg_reduce<LP>((uint32_t)(c >> 24), seg * LP, [](uint32_t x, uint32_t y) { return x + y; });
+                if (lead) b.cells[k] = ((unsigned long long)c_hi << 24) + c_lo;
             }
             cur += need;
             cnt += NP;
@@ -1365,7 +1412,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
                 const uint32_t nws = p.seq_cap / 16u + 4u;
                 uint32_t *suf = ops_s + nws;
                 const uint8_t *med = tcm.median;
-                if ((uint32_t)(dim * dim) + 8u * nws <= NP * p.seq_cap && !b.out_ungapped) {
+                if ((uint32_t)(dim * dim) + 8u * nws <= NP * p.seq_cap) {
                     uint32_t *ms = suf + nws;
                     for (int i = lane; i < dim * dim / 4; i += 32) ms[i] = __ldg(reinterpret_cast<const uint32_t *>(tcm.median) + i);
                     med = reinterpret_cast<const uint8_t *>(ms);
@@ -1388,20 +1435,15 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
                         const uint32_t o = 128u * (uint32_t)(lane & 15);
                         if (m && o < m + 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + min(o, m - 1u)));
                     }
-                    if (!b.out_ungapped) {
-                        if (wr) emit_pair_q(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
-                                            b.out_gapped ? b.out_gapped + oo : nullptr, b.out_slot1 ? b.out_slot1 + oo : nullptr,
-                                            b.out_slot2 ? b.out_slot2 + oo : nullptr, lane, ops_s, suf);
-                        continue;
-                    }
-                    const uint32_t nu = emit_pair(tcm, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
-                                                  b.out_gapped && wr ? b.out_gapped + oo : nullptr,
-                                                  b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
-                                                  b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane,
-                                                  b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+                    const uint32_t nu = (wr || b.out_ungapped)
+                        ? emit_pair_q(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                                      b.out_gapped && wr ? b.out_gapped + oo : nullptr, b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
+                                      b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane, ops_s, suf,
+                                      b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap)
+                        : 0u;
                     if (b.out_ungapped && lane == 0) {
                         b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
-                        if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);
+                        if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);   // node string does not fit its slot
                     }
                 }
             }
@@ -1534,14 +1576,15 @@ cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_
 }
 
 // Host-side launchers (called from do_api.cu).
-// shape 0: 8 lanes x 28 diagonals (4 pairs per warp), shape 1: 4 lanes x 32 diagonals (8 pairs per warp)
+// shape 0: 8 lanes x 28 diagonals (4 pairs per warp), 1: 4 lanes x 32 (8 pairs), 2: 5 lanes x 28 (6 pairs, 2 lanes idle)
 cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
     static DeviceOnce once;
     int dev = 0;
     if (once.pending(&dev)) {
         const void *fns[] = {(const void *)do_linear_multi_kernel<8, 14, false>, (const void *)do_linear_multi_kernel<8, 14, true>,
-                             (const void *)do_linear_multi_kernel<4, 16, false>, (const void *)do_linear_multi_kernel<4, 16, true>};
+                             (const void *)do_linear_multi_kernel<4, 16, false>, (const void *)do_linear_multi_kernel<4, 16, true>,
+                             (const void *)do_linear_multi_kernel<5, 14, false>, (const void *)do_linear_multi_kernel<5, 14, true>};
         for (const void *f : fns) {
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return e;
@@ -1551,9 +1594,12 @@ cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int 
     if (shape == 0) {
         if (p.phase_cycles) do_linear_multi_kernel<8, 14, true><<<grid, block, smem_bytes, stream>>>(p);
         else                do_linear_multi_kernel<8, 14, false><<<grid, block, smem_bytes, stream>>>(p);
-    } else {
+    } else if (shape == 1) {
         if (p.phase_cycles) do_linear_multi_kernel<4, 16, true><<<grid, block, smem_bytes, stream>>>(p);
         else                do_linear_multi_kernel<4, 16, false><<<grid, block, smem_bytes, stream>>>(p);
+    } else {
+        if (p.phase_cycles) do_linear_multi_kernel<5, 14, true><<<grid, block, smem_bytes, stream>>>(p);
+        else                do_linear_multi_kernel<5, 14, false><<<grid, block, smem_bytes, stream>>>(p);
     }
     return cudaGetLastError();
 }
@@ -1561,9 +1607,9 @@ cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int 
 // staging bytes one pair of a multi-pair group may need for strings of up to max_len elements (shape as above)
 uint32_t multi_seq_cap_for(int max_len, int shape)
 {
-    const int lanes_h = shape == 0 ? 8 * 14 : 4 * 16;
+    const int lanes_h = shape == 0 ? 8 * 14 : (shape == 1 ? 4 * 16 : 5 * 14);
     const int tpad = (max_len + 1 + 15) & ~15;
-    const int q0h = (shape == 0 ? 224 : 128) / 2 + 1;           // q0 / 2 <= wb / 2
+    const int q0h = (shape == 0 ? 224 : (shape == 1 ? 128 : 140)) / 2 + 1;           // q0 / 2 <= wb / 2
     const int sizeL = lanes_h + tpad + q0h + 8;
     const int sizeS = q0h + tpad + lanes_h + 8;
     return (uint32_t)((sizeS + sizeL + 15) & ~15);

@@ -387,10 +387,10 @@ def _grouped_pairs(rng, n_groups, lo=330, hi=1040, per_group=4):
     return pairs
 
 
-@pytest.mark.parametrize("shape", ["4x8x28", "8x4x32", "mixed"])
+@pytest.mark.parametrize("shape", ["4x8x28", "8x4x32", "6x5x28", "mixed"])
 @pytest.mark.parametrize("name", ["discrete", "l1", "1:2", "2:1", "weird"])
 def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, shape):
-    """do_linear_multi_kernel — four pairs per warp for bands of 129..223 diagonals, eight for 65..127 — against the CPU
+    """do_linear_multi_kernel — four pairs per warp for bands of 141..223 diagonals, six for 129..139, eight for 65..127 — against the CPU
     side (the compiled reference when present) and against the one-pair-per-warp kernels on the same batch."""
     import zlib
     import pcg_b200 as P
@@ -400,14 +400,26 @@ def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, 
         pairs = _grouped_pairs(rng, 150)
     elif shape == "8x4x32":
         pairs = _grouped_pairs(rng, 120, lo=30, hi=290, per_group=8)
+    elif shape == "6x5x28":
+        pairs = _grouped_pairs(rng, 150, lo=270, hi=360, per_group=6)
     else:
-        pairs = _grouped_pairs(rng, 60) + _grouped_pairs(rng, 60, lo=30, hi=290, per_group=8) + _grouped_pairs(rng, 20, lo=900, hi=1400)
+        pairs = _grouped_pairs(rng, 60) + _grouped_pairs(rng, 60, lo=30, hi=290, per_group=8) + \
+            _grouped_pairs(rng, 60, lo=270, hi=360, per_group=6) + _grouped_pairs(rng, 20, lo=900, hi=1400)
         rng.shuffle(pairs)
     pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
     gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=32, max_len=1500 if shape == "mixed" else 1100, max_b=32, arena_words=0)
     tcm = gpu_ctx.tcm(sig)
-    r = P.align2d_batch(gpu_ctx, tcm, pp, want_cells=True)
-    n_launch_quad = gpu_ctx.last_kernel_ms()[1]
+    all_shapes = shape in ("8x4x32", "mixed")                  # the 8-pairs shape is off by default (measured: no gain)
+    if all_shapes:
+        monkeypatch.setenv("PCGDO_QUAD_FLAGS", "32")
+        gpu_ctx.reload_env()
+    try:
+        r = P.align2d_batch(gpu_ctx, tcm, pp, want_cells=True)
+        n_launch_quad = gpu_ctx.last_kernel_ms()[1]
+    finally:
+        if all_shapes:
+            monkeypatch.delenv("PCGDO_QUAD_FLAGS")
+        gpu_ctx.reload_env()
     monkeypatch.setenv("PCGDO_NO_QUAD", "1")
     gpu_ctx.reload_env()
     try:
@@ -416,7 +428,7 @@ def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, 
     finally:
         monkeypatch.delenv("PCGDO_NO_QUAD")
         gpu_ctx.reload_env()
-    assert n_launch_quad == n_launch_single + 2                # the two extra kernels did run
+    assert n_launch_quad == n_launch_single + (3 if all_shapes else 2)        # the extra kernels did run
     assert np.array_equal(r.cost, r1.cost) and np.array_equal(r.out_len, r1.out_len)
     assert np.array_equal(r.cells, r1.cells)
     kind = "reference" if oracle_mod.Reference.available() else "port"
