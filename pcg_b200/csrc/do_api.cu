@@ -391,15 +391,15 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
     if ((rc = pcgdo_ensure(ctx, ctx->big, (size_t)bd.n_pairs * 4))) return rc;
     // Several pairs per warp (do_linear_multi_kernel, two shapes) first, when the TCM qualifies for the packed fill; what
     // one launch leaves over goes to the next through a list on the device, and last to the narrow kernel.
-    uint32_t cap_m[3] = {0, 0, 0};
+    uint32_t cap_m[4] = {0, 0, 0, 0};
     int warps_q = 0;
     if (tcm->dev.pack_ok && !ctx->knobs.no_pack16 && !ctx->knobs.no_quad && bd.n_pairs >= 4) {
         const size_t dim = (size_t)1 << tcm->a;
         const size_t fixed = tcm->dev.sub4_bytes + 2 * dim * 4;
         warps_q = ctx->warps_per_cta < 16 ? ctx->warps_per_cta : 16;
         const size_t room = (227 * 1024 - fixed) / warps_q;
-        for (int shape = 0; shape < 3; ++shape) {
-            const uint32_t np = shape == 0 ? 4u : (shape == 1 ? 8u : 6u);
+        for (int shape = 0; shape < 4; ++shape) {
+            const uint32_t np = shape == 0 ? 4u : (shape == 1 ? 8u : (shape == 2 ? 6u : 5u));
             const uint32_t want = (multi_seq_cap_for(ctx->max_len, shape) + 15u) & ~15u;
             if (room >= 640 + np * 256) cap_m[shape] = std::min<uint32_t>((uint32_t)((room - 640) / np) & ~15u, want);
         }
@@ -409,8 +409,9 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
         if (!(ctx->knobs.quad_flags & 32u)) cap_m[1] = 0;
         if (ctx->knobs.quad_flags & 8u) cap_m[0] = 0;          // experiment switches: without one shape
         if (ctx->knobs.quad_flags & 16u) cap_m[2] = 0;
+        if (ctx->knobs.quad_flags & 64u) cap_m[3] = 0;
     }
-    const bool multi = cap_m[0] || cap_m[1] || cap_m[2];
+    const bool multi = cap_m[0] || cap_m[1] || cap_m[2] || cap_m[3];
     if (multi && ((rc = pcgdo_ensure(ctx, ctx->singles, (size_t)bd.n_pairs * 4)) ||
                   (rc = pcgdo_ensure(ctx, ctx->singles2, (size_t)bd.n_pairs * 4))))
         return rc;
@@ -450,12 +451,12 @@ int pcgdo_enqueue_linear(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const BatchDev &b
         // counter[16 + s] and leaves what it does not take in list s % 2, counted in counter[20 + s].
         CK(cudaMemsetAsync((unsigned int *)ctx->counters.p + 16, 0, 32, st));
         const bool big_first = ctx->max_len >= 700;
-        const int order[3] = {big_first ? 0 : 2, big_first ? 2 : 1, big_first ? 1 : 0};
+        const int order[4] = {big_first ? 0 : 2, big_first ? 3 : 3, big_first ? 2 : 0, 1};
         int stage = 0;
-        for (int o = 0; o < 3; ++o) {
+        for (int o = 0; o < 4; ++o) {
             const int shape = order[o];
             if (!cap_m[shape]) continue;
-            const uint32_t np = shape == 0 ? 4u : (shape == 1 ? 8u : 6u);
+            const uint32_t np = shape == 0 ? 4u : (shape == 1 ? 8u : (shape == 2 ? 6u : 5u));
             DevBuf &in = (stage & 1) ? ctx->singles : ctx->singles2, &outb = (stage & 1) ? ctx->singles2 : ctx->singles;
             p.multi_in_list = stage == 0 ? nullptr : (const uint32_t *)in.p;
             p.multi_in_count = stage == 0 ? nullptr : p.counter + 20 + (stage - 1);

@@ -44,7 +44,7 @@ struct pcgdo_ctx {
         bool no_pack16 = false;        // PCGDO_NO_PACK16          32-bit fills only
         bool no_quad = false;          // PCGDO_NO_QUAD            dense path: no four-pairs-per-warp kernel
         unsigned quad_flags = 0;       // PCGDO_QUAD_FLAGS         bit 0: stagger first batches; bit 1: phase cycle counts to stderr;
-                                       //                          bit 3 / 4: without the 4- / 6-pairs-per-warp shape; bit 5: with the 8-pairs one
+                                       //                          bit 3 / 4 / 6: without the 4- / 6- / 5-pairs-per-warp shape; bit 5: with the 8-pairs one
         bool affine_rowwise = false;   // PCGDO_AFFINE_ROWWISE     first-generation affine fill
         bool metric_registers = false; // PCGDO_METRIC_REGISTERS   do_metric.cu instead of the table kernel
         bool explicit_multi_pass = false;  // PCGDO_EXPLICIT_MULTI_PASS

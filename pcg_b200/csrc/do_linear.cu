@@ -390,9 +390,10 @@ __device__ __noinline__ uint32_t fill_pair16(const Geom g, const FillConst fc, u
 // Direction words: word[(t >> 3) * 448 + lane * 14 + m] — the diagonals of a pair are consecutive words (two diagonals 14
 // apart share a word), so the trace's next word is usually in the 32-byte sector it already holds.
 // ---------------------------------------------------------------------------------------------
-// Three shapes are built: LP = 8 lanes x 28 diagonals (H = 14 registers; 4 pairs per warp; bands of 141 .. 223 diagonals:
-// ~1 kb strings), LP = 5 lanes x 28 (6 pairs per warp, two lanes idle; bands of 129 .. 139: the ~300-element medians of tree
-// scoring) and LP = 4 lanes x 32 diagonals (H = 16; 8 pairs per warp; bands of 65 .. 127: its ~250-element leaves).  Direction words per 8 iterations of one group: 32 * H.
+// Shapes built: LP = 8 lanes x 28 diagonals (H = 14 registers; 4 pairs per warp; bands of 169 .. 223 diagonals: ~1 kb
+// strings), LP = 6 x 28 (5 pairs per warp, two lanes idle; 141 .. 167) and LP = 5 x 28 (6 pairs, two lanes idle; 129 .. 139):
+// the 300 .. 500-element medians of tree scoring, and LP = 4 lanes x 32 diagonals (H = 16; 8 pairs per warp; bands of
+// 65 .. 127: its ~250-element leaves; off by default, see do_api.cu).  Direction words per 8 iterations of one group: 32 * H.
 template <int H> __host__ __device__ inline uint32_t multi_dir_words(int tmax) { return (uint32_t)((tmax + 7) / 8) * 32u * (uint32_t)H; }
 
 // Staging of one pair of a group: both strings as raw bytes (element 0 = padding), zero-padded for `tmax` iterations.
@@ -786,6 +787,7 @@ __device__ __forceinline__ uint32_t emit_pair(const TcmDev &tcm, const uint8_t *
 // (two are kept in flight).  ops_s / suf: scratch in the warp's string windows, which are idle during this phase.
 // ou (post-order mode): the medians with the gap elements dropped; only its write positions run from pass to pass (one
 // warp scan each), no load address does.  Returns their number.
+template <bool UNGAPPED>
 __device__ __forceinline__ uint32_t emit_pair_q(const TcmDev &tcm, const uint8_t *med, const uint8_t *pL, const uint8_t *pS,
                                                 const uint32_t *ops, uint32_t nal, bool first_long, uint8_t *og, uint8_t *o1,
                                                 uint8_t *o2, int lane, uint32_t *ops_s, uint32_t *suf,
@@ -826,7 +828,7 @@ __device__ __forceinline__ uint32_t emit_pair_q(const TcmDev &tcm, const uint8_t
     for (int c0 = -mis; c0 < (int)nal; c0 += 128) {
         const int c = c0 + 4 * lane;
         const bool mine = c >= 0 && c < (int)nal;
-        if (!mine && !ou) continue;
+        if (!mine && !UNGAPPED) continue;
         uint32_t xx[4], yy[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
@@ -850,7 +852,7 @@ __device__ __forceinline__ uint32_t emit_pair_q(const TcmDev &tcm, const uint8_t
                 wg |= md << (8 * x);
                 wx |= xx[x] << (8 * x);
                 wy |= yy[x] << (8 * x);
-                if (md != gap) { ++nk; keep |= 1u << x; }
+                if (UNGAPPED && md != gap) { ++nk; keep |= 1u << x; }
             }
         }
         if (mine) {
@@ -858,7 +860,7 @@ __device__ __forceinline__ uint32_t emit_pair_q(const TcmDev &tcm, const uint8_t
             if (o1) *reinterpret_cast<uint32_t *>(o1 + c) = first_long ? wx : wy;
             if (o2) *reinterpret_cast<uint32_t *>(o2 + c) = first_long ? wy : wx;
         }
-        if (ou) {       // deleteGaps of the node's context, medians only
+        if constexpr (UNGAPPED) {       // deleteGaps of the node's context, medians only
             uint32_t inc = nk;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -1172,7 +1174,7 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
 {
     constexpr int NP = 32 / LP, B = 2 * H;
     // bands this shape takes: more diagonals than the next smaller shape (or the narrow kernel's B = 2) holds
-    constexpr int kLow = LP == 8 ? 5 * 28 : (LP == 5 ? 128 : 64);
+    constexpr int kLow = LP == 8 ? 6 * 28 : (LP == 6 ? 5 * 28 : (LP == 5 ? 128 : 64));
     const TcmDev &tcm = p.tcm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     // lanes behind the last pair (LP = 5: lanes 30, 31) shadow the first lanes of the last pair: same loads, same window
@@ -1435,12 +1437,17 @@ __global__ void __launch_bounds__(512, 1) do_linear_multi_kernel(const LinearPar
                         const uint32_t o = 128u * (uint32_t)(lane & 15);
                         if (m && o < m + 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + min(o, m - 1u)));
                     }
-                    const uint32_t nu = (wr || b.out_ungapped)
-                        ? emit_pair_q(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
-                                      b.out_gapped && wr ? b.out_gapped + oo : nullptr, b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
-                                      b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane, ops_s, suf,
-                                      b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap)
-                        : 0u;
+                    uint32_t nu = 0;
+                    if (b.out_ungapped)
+                        nu = emit_pair_q<true>(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                                               b.out_gapped && wr ? b.out_gapped + oo : nullptr,
+                                               b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
+                                               b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane, ops_s, suf,
+                                               b.out_ungapped + b.out_uoff[k], b.ucap);
+                    else if (wr)
+                        emit_pair_q<false>(tcm, med, fl ? p1 : p2, fl ? p2 : p1, ops, s_nal[pe], fl,
+                                           b.out_gapped ? b.out_gapped + oo : nullptr, b.out_slot1 ? b.out_slot1 + oo : nullptr,
+                                           b.out_slot2 ? b.out_slot2 + oo : nullptr, lane, ops_s, suf);
                     if (b.out_ungapped && lane == 0) {
                         b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
                         if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);   // node string does not fit its slot
@@ -1576,7 +1583,8 @@ cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_
 }
 
 // Host-side launchers (called from do_api.cu).
-// shape 0: 8 lanes x 28 diagonals (4 pairs per warp), 1: 4 lanes x 32 (8 pairs), 2: 5 lanes x 28 (6 pairs, 2 lanes idle)
+// shape 0: 8 lanes x 28 diagonals (4 pairs per warp), 1: 4 lanes x 32 (8 pairs), 2: 5 lanes x 28 (6 pairs, 2 lanes idle),
+// 3: 6 lanes x 28 (5 pairs, 2 lanes idle)
 cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
     static DeviceOnce once;
@@ -1584,7 +1592,8 @@ cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int 
     if (once.pending(&dev)) {
         const void *fns[] = {(const void *)do_linear_multi_kernel<8, 14, false>, (const void *)do_linear_multi_kernel<8, 14, true>,
                              (const void *)do_linear_multi_kernel<4, 16, false>, (const void *)do_linear_multi_kernel<4, 16, true>,
-                             (const void *)do_linear_multi_kernel<5, 14, false>, (const void *)do_linear_multi_kernel<5, 14, true>};
+                             (const void *)do_linear_multi_kernel<5, 14, false>, (const void *)do_linear_multi_kernel<5, 14, true>,
+                             (const void *)do_linear_multi_kernel<6, 14, false>, (const void *)do_linear_multi_kernel<6, 14, true>};
         for (const void *f : fns) {
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return e;
@@ -1597,9 +1606,12 @@ cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int 
     } else if (shape == 1) {
         if (p.phase_cycles) do_linear_multi_kernel<4, 16, true><<<grid, block, smem_bytes, stream>>>(p);
         else                do_linear_multi_kernel<4, 16, false><<<grid, block, smem_bytes, stream>>>(p);
-    } else {
+    } else if (shape == 2) {
         if (p.phase_cycles) do_linear_multi_kernel<5, 14, true><<<grid, block, smem_bytes, stream>>>(p);
         else                do_linear_multi_kernel<5, 14, false><<<grid, block, smem_bytes, stream>>>(p);
+    } else {
+        if (p.phase_cycles) do_linear_multi_kernel<6, 14, true><<<grid, block, smem_bytes, stream>>>(p);
+        else                do_linear_multi_kernel<6, 14, false><<<grid, block, smem_bytes, stream>>>(p);
     }
     return cudaGetLastError();
 }
@@ -1607,9 +1619,9 @@ cudaError_t launch_linear_multi(const LinearParams &p, int shape, int grid, int 
 // staging bytes one pair of a multi-pair group may need for strings of up to max_len elements (shape as above)
 uint32_t multi_seq_cap_for(int max_len, int shape)
 {
-    const int lanes_h = shape == 0 ? 8 * 14 : (shape == 1 ? 4 * 16 : 5 * 14);
+    const int lanes_h = shape == 0 ? 8 * 14 : (shape == 1 ? 4 * 16 : (shape == 2 ? 5 * 14 : 6 * 14));
     const int tpad = (max_len + 1 + 15) & ~15;
-    const int q0h = (shape == 0 ? 224 : (shape == 1 ? 128 : 140)) / 2 + 1;           // q0 / 2 <= wb / 2
+    const int q0h = (shape == 0 ? 224 : (shape == 1 ? 128 : (shape == 2 ? 140 : 168))) / 2 + 1;           // q0 / 2 <= wb / 2
     const int sizeL = lanes_h + tpad + q0h + 8;
     const int sizeS = q0h + tpad + lanes_h + 8;
     return (uint32_t)((sizeS + sizeL + 15) & ~15);

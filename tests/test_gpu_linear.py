@@ -387,10 +387,10 @@ def _grouped_pairs(rng, n_groups, lo=330, hi=1040, per_group=4):
     return pairs
 
 
-@pytest.mark.parametrize("shape", ["4x8x28", "8x4x32", "6x5x28", "mixed"])
+@pytest.mark.parametrize("shape", ["4x8x28", "8x4x32", "6x5x28", "5x6x28", "mixed"])
 @pytest.mark.parametrize("name", ["discrete", "l1", "1:2", "2:1", "weird"])
 def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, shape):
-    """do_linear_multi_kernel — four pairs per warp for bands of 141..223 diagonals, six for 129..139, eight for 65..127 — against the CPU
+    """do_linear_multi_kernel — four pairs per warp for bands of 169..223 diagonals, five for 141..167, six for 129..139, eight for 65..127 — against the CPU
     side (the compiled reference when present) and against the one-pair-per-warp kernels on the same batch."""
     import zlib
     import pcg_b200 as P
@@ -402,9 +402,12 @@ def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, 
         pairs = _grouped_pairs(rng, 120, lo=30, hi=290, per_group=8)
     elif shape == "6x5x28":
         pairs = _grouped_pairs(rng, 150, lo=270, hi=360, per_group=6)
+    elif shape == "5x6x28":
+        pairs = _grouped_pairs(rng, 150, lo=400, hi=640, per_group=5)
     else:
         pairs = _grouped_pairs(rng, 60) + _grouped_pairs(rng, 60, lo=30, hi=290, per_group=8) + \
-            _grouped_pairs(rng, 60, lo=270, hi=360, per_group=6) + _grouped_pairs(rng, 20, lo=900, hi=1400)
+            _grouped_pairs(rng, 60, lo=270, hi=360, per_group=6) + _grouped_pairs(rng, 60, lo=400, hi=640, per_group=5) + \
+            _grouped_pairs(rng, 20, lo=900, hi=1400)
         rng.shuffle(pairs)
     pp = P.PackedPairs.from_lists([p[0] for p in pairs], [p[1] for p in pairs])
     gpu_ctx.configure(pairs_per_warp=32, warps_per_cta=32, max_len=1500 if shape == "mixed" else 1100, max_b=32, arena_words=0)
@@ -428,7 +431,7 @@ def test_several_pairs_per_warp_kernels(oracle_mod, gpu_ctx, monkeypatch, name, 
     finally:
         monkeypatch.delenv("PCGDO_NO_QUAD")
         gpu_ctx.reload_env()
-    assert n_launch_quad == n_launch_single + (3 if all_shapes else 2)        # the extra kernels did run
+    assert n_launch_quad == n_launch_single + (4 if all_shapes else 3)        # the extra kernels did run
     assert np.array_equal(r.cost, r1.cost) and np.array_equal(r.out_len, r1.out_len)
     assert np.array_equal(r.cells, r1.cells)
     kind = "reference" if oracle_mod.Reference.available() else "port"
