@@ -433,7 +433,7 @@ template <int LP, int H, bool TAIL>
 __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[H], const uint32_t (&penc)[H], uint32_t (&dw)[H],
                                              uint32_t (&lw)[H], uint32_t (&sw)[H], uint32_t (&p_lo)[multi_dist<H>()],
                                              uint32_t (&p_hi)[multi_dist<H>()], const FillConst fc, uint32_t tab_lane, uint32_t sc1, uint32_t sc2,
-                                             const char *&lptr, const char *&sptr, int n_iter, uint32_t *&out)
+                                             const char *&lptr, const char *&sptr, int n_iter, uint32_t *&out, int n_st)
 {
     constexpr int U = H / 2, CH = 8, D = multi_dist<H>();
     static_assert(D >= 1 && D <= U && H > CH && H % 2 == 0, "shape");
@@ -480,8 +480,10 @@ __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[H], const uint32_t (&
         }
         if (r == CH - 1 || (TAIL && r == n_iter - 1)) {
             const int sh = 2 * (CH - 1 - r);          // left-align a partial group
+            // (only registers that hold a diagonal of the band: the last lanes of a pair are partly or wholly beyond it)
 #pragma unroll
-            for (int m = 0; m < H; m += 2) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m] << sh, dw[m + 1] << sh);
+            for (int m = 0; m < H; m += 2)
+                if (m / 2 < n_st) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m] << sh, dw[m + 1] << sh);
             out += 32 * H;
         }
     }
@@ -570,6 +572,9 @@ __device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const Fill
     const char *lptr = Lb + (I0 + 1);
     const char *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
+    // register m holds diagonals qb + m and qb + m + H: pairs of registers up to the band's last diagonal are stored
+    // (config 2: the 8th lane of a pair owns diagonals 196..223 of 200 — two stores instead of seven)
+    const int n_st = min(H / 2, max(0, (g.wb - qb + 1) / 2));
     const uint32_t sc1 = repl ? 64u : 2u, sc2 = repl ? (uint32_t)-62 : 0u;
     uint32_t p_lo[D], p_hi[D];
 #pragma unroll
@@ -579,11 +584,11 @@ __device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const Fill
     bool ok = true;
     for (int c = 0; c < nfull; ++c) {
         if (c && c % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit, sbase) && ok;       // every 32 iterations
-        run_chunk16q<LP, H, false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, 8, out);
+        run_chunk16q<LP, H, false>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, 8, out, n_st);
     }
     if (rem) {
         if (nfull && nfull % 4 == 0) ok = rebase16q<LP, H>(R, total_shift, spread_limit, sbase) && ok;
-        run_chunk16q<LP, H, true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, rem, out);
+        run_chunk16q<LP, H, true>(R, penc, dw, lw, sw, p_lo, p_hi, fc, tab_lane, sc1, sc2, lptr, sptr, rem, out, n_st);
     }
     ok = rebase16q<LP, H>(R, total_shift, spread_limit, sbase) && ok;
     const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
