@@ -1659,7 +1659,10 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
             while (at < n) { cb.push_back(at); at += sz; if (sz < 4 * chunk) sz *= 2; }
         } else {
             // a short first chunk gets the aligner going early; the copy-out lags by one chunk whatever the sizes
-            // (its rate is within 10 % of the aligner's), so the rest stay equal
+            // (its rate is within 10 % of the aligner's), so the rest stay equal.  (Tried in round 2: chunks of twice the
+            // size in the middle and a ramp down at the end, so that a warp of the multi-pair kernel comes to its trace +
+            // emit phase with a full batch — 82 ms instead of 75: a 131 072-pair chunk aligned in 9 – 10 ms next to the
+            // copies against 7.5 ms alone.)
             size_t at = 0;
             for (size_t sz = std::max<size_t>(chunk / 4, 256); at < n && sz < chunk; sz *= 2) { cb.push_back(at); at += sz; }
             for (; at < n; at += chunk) cb.push_back(at);
@@ -1731,6 +1734,8 @@ static int batch_host_impl(pcgdo_ctx *ctx, const pcgdo_tcm *tcm, const pcgdo_bat
         // buffer (a device-wide synchronisation); the failure list holds batch-wide pair indices of ALL chunks
         if ((rc = pcgdo_ensure(ctx, ctx->overflow, std::max(max_chunk_pairs, std::min(n, 4 * kMaxStragglers)) * 4))) return rc;
         if ((rc = pcgdo_ensure(ctx, ctx->big, max_chunk_pairs * 4 * (affine ? 6 : 1)))) return rc;
+        if (!affine && ((rc = pcgdo_ensure(ctx, ctx->singles, max_chunk_pairs * 4)) || (rc = pcgdo_ensure(ctx, ctx->singles2, max_chunk_pairs * 4))))
+            return rc;
         EventPool events;
         std::vector<cudaEvent_t> ev_in(nch), ev_done(nch), ev_out(nch);
         const bool trace = ctx->knobs.trace_pipeline;             // per-chunk completion times to stderr
