@@ -1485,15 +1485,17 @@ __host__ __device__ inline uint64_t general_words(const Geom &g)
     return (wq + 8) + (uint64_t)((g.T + 15) / 16) * wq + ops_words(g) + 8;
 }
 
-__global__ void __launch_bounds__(256) do_general_kernel(const LinearParams p, const uint32_t *list,
-                                                         const uint64_t *scratch_off, uint32_t *scratch)
+// The diagonal values in global memory, direction words by read-modify-write: for what do_general_kernel cannot hold in
+// shared memory / registers (bands beyond 8192 diagonals).
+__device__ __noinline__ void general_pair_global(const LinearParams &p, const uint32_t *list, const uint64_t *scratch_off,
+                                                 uint32_t *scratch)
 {
     const TcmDev &tcm = p.tcm;
     const BatchDev &b = p.b;
     const uint32_t k = list[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_fl;
-    __shared__ uint32_t s_red[8];
+    __shared__ uint32_t s_red[32];
     __shared__ uint32_t s_n;
     const uint32_t n1 = b.len1[k], n2 = b.len2[k];
     const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
@@ -1574,6 +1576,142 @@ __global__ void __launch_bounds__(256) do_general_kernel(const LinearParams p, c
     }
 }
 
+// Tuned path (round 2): the reference's own CPU benchmark (config 1) is 190 pairs of 8 .. 4608 elements, half of them in
+// full-matrix mode with 1000 .. 6900 diagonals — one CTA each, so a launch lasts as long as its longest pair: 6900
+// anti-diagonal steps.  A step used to be a round of global-memory loads + a read-modify-write of the direction word
+// (2 µs); here the diagonal values, both strings and the cost table live in shared memory, every thread owns up to 8 fixed
+// diagonals (q = tid, tid + 1024, ...) whose direction words it builds in registers and stores once per 16 cells, and a
+// step is a few dozen instructions and one barrier.
+constexpr int kGenThreads = 1024, kGenOwn = 8;
+
+__global__ void __launch_bounds__(kGenThreads) do_general_kernel(const LinearParams p, const uint32_t *list,
+                                                                 const uint64_t *scratch_off, uint32_t *scratch, uint32_t smem_bytes)
+{
+    const TcmDev &tcm = p.tcm;
+    const BatchDev &b = p.b;
+    const uint32_t k = list[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    __shared__ int s_fl;
+    __shared__ uint32_t s_red[32];
+    __shared__ uint32_t s_n;
+    const uint32_t n1 = b.len1[k], n2 = b.len2[k];
+    const uint8_t *p1 = b.elems + b.off1[k], *p2 = b.elems + b.off2[k];
+    if (warp == 0) {
+        const bool f = first_is_long(p1, n1, p2, n2, lane);
+        if (lane == 0) s_fl = f;
+    }
+    __syncthreads();
+    const bool fl = s_fl != 0;
+    const uint8_t *pL = fl ? p1 : p2, *pS = fl ? p2 : p1;
+    const Geom g = make_geom((int)(fl ? n1 : n2) + 1, (int)(fl ? n2 : n1) + 1);
+    const uint32_t wq = general_wq(g);
+    const int dim = 1 << tcm.a;
+    const uint32_t tab_bytes = (uint32_t)(dim * dim * 2);
+    const bool tab_in = tcm.a <= 7;
+    const uint32_t need = (wq + 8u) * 4u + (tab_in ? tab_bytes : 0u) + (((uint32_t)g.lg + 3u) & ~3u) + (((uint32_t)g.sh + 3u) & ~3u);
+    if (need > smem_bytes || (uint32_t)g.wb > (uint32_t)(kGenThreads * kGenOwn)) {      // (uniform over the CTA)
+        general_pair_global(p, list, scratch_off, scratch);
+        return;
+    }
+    uint32_t *w = reinterpret_cast<uint32_t *>(smem);                    // w[1 + q], fences at 0 and wq + 1
+    int16_t *tab = reinterpret_cast<int16_t *>(w + wq + 8);
+    uint8_t *Ls = reinterpret_cast<uint8_t *>(tab) + (tab_in ? tab_bytes : 0u);
+    uint8_t *Ss = Ls + (((uint32_t)g.lg + 3u) & ~3u);
+    uint32_t *gbase = scratch + scratch_off[blockIdx.x];
+    uint32_t *dirw = gbase + wq + 8;                                     // (same scratch layout as the global path)
+    const uint32_t ndir = (uint32_t)((g.T + 15) / 16) * wq;
+    uint32_t *ops = dirw + ndir;
+    const uint32_t emask = (uint32_t)dim - 1u;
+    for (uint32_t i = tid; i < wq + 8; i += kGenThreads) w[i] = kInfW;
+    if (tab_in) for (int i = tid; i < dim * dim; i += kGenThreads) tab[i] = tcm.sub4_nat[i];
+    uint32_t csum = 0;
+    for (int i = tid; i < g.lg; i += kGenThreads) {
+        uint32_t e = tcm.gap;
+        if (i > 0) { e = pL[i - 1] & emask; csum += tcm.cgap[e]; }
+        Ls[i] = (uint8_t)e;
+    }
+    for (int j = tid; j < g.sh; j += kGenThreads) {
+        uint32_t e = tcm.gap;
+        if (j > 0) { e = pS[j - 1] & emask; csum += tcm.gapc[e]; }
+        Ss[j] = (uint8_t)e;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) csum += __shfl_xor_sync(kFull, csum, d);
+    if (lane == 0) s_red[warp] = csum;
+    __syncthreads();
+    csum = 0;
+    for (int x = 0; x < kGenThreads / 32; ++x) csum += s_red[x];
+    if (tid == 0) w[1 + g.q0] = kBias4 - (uint32_t)tcm.sub4_gapgap;
+    __syncthreads();
+
+    // Thread tid owns the diagonals q = 2 * (tid + o * 1024) + c, o < 4, of BOTH parities c: a step only touches the
+    // diagonals of its own parity (q0 is even), so every thread has work in every step and no slot is looked at in vain.
+    uint32_t acc[kGenOwn];
+#pragma unroll
+    for (int o = 0; o < kGenOwn; ++o) acc[o] = 0;
+    const int16_t *tb = tab_in ? tab : tcm.sub4_nat;
+    const int smax = (g.lg - 1) + (g.sh - 1);
+    for (int s = 0; s <= smax; ++s) {
+        const int c = s & 1;
+        // diagonals with a cell on anti-diagonal s: i = (s - d) / 2 in [0, lg), j = (s + d) / 2 in [0, sh), inside the band
+        const int q_lo = max(g.pad, g.q0 + max(s - 2 * (g.lg - 1), -s)), q_hi = min(g.wb - 1, g.q0 + min(s, 2 * (g.sh - 1) - s));
+#pragma unroll
+        for (int oo = 0; oo < kGenOwn / 2; ++oo) {
+            const int o = 2 * oo + c;            // (accumulator slot; resolved by predication below)
+            const int q = 2 * (tid + oo * kGenThreads) + c;
+            if (q < q_lo || q > q_hi) continue;
+            const int d = q - g.q0;
+            const int i = (s - d) >> 1, j = i + d;
+            const uint32_t sub = (uint32_t)(int)tb[((uint32_t)Ls[i] << tcm.a) | Ss[j]];
+            const uint32_t t1 = __viaddmin_u32(w[1 + q], sub, w[2 + q]);
+            const uint32_t mn = __viaddmin_u32(w[q], 1u, t1);
+            const int t = (s - (q & 1)) >> 1;
+            uint32_t a = (c ? acc[2 * oo + 1] : acc[2 * oo]) | ((mn & 3u) << (2 * (15 - (t & 15))));
+            w[1 + q] = (mn & ~3u) | 1u;
+            // the word is complete, or this was the diagonal's last cell
+            if ((t & 15) == 15 || i == g.lg - 1 || j == g.sh - 1) {
+                dirw[(uint32_t)(t >> 4) * wq + (uint32_t)q] = a;
+                if ((t & 15) == 15) a = 0;
+            }
+            if (c) acc[2 * oo + 1] = a; else acc[2 * oo] = a;
+            (void)o;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int q_last = (g.sh - 1) - (g.lg - 1) + g.q0;
+        b.cost[k] = (int32_t)((w[1 + q_last] >> 2) - (kBias4 >> 2) + csum);
+        if (b.cells) b.cells[k] = band_cells(g, 0, 1);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const bool want_out = b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_len || b.out_ungapped;
+        uint32_t n = 0;
+        if (want_out) {
+            n = trace_lane(dirw, wq, g.q0, g.lg, g.sh, ops);
+            if (b.out_len) b.out_len[k] = n;
+            if (b.pack_cursor) pack_claim(b, k, n);
+        }
+        s_n = n;
+        __threadfence_block();
+    }
+    __syncthreads();
+    if (warp == 0 && (b.out_gapped || b.out_slot1 || b.out_slot2 || b.out_ungapped)) {
+        const uint64_t oa = b.pack_cursor ? __ldcg(b.out_off_actual + k) : 0;
+        const bool wr = oa != ~0ull;
+        const uint64_t oo = b.pack_cursor ? oa - b.pack_base : b.out_off ? b.out_off[k] : 0;
+        const uint32_t nu = emit_pair(tcm, pL, pS, ops, s_n, fl, b.out_gapped && wr ? b.out_gapped + oo : nullptr,
+                                      b.out_slot1 && wr ? b.out_slot1 + oo : nullptr,
+                                      b.out_slot2 && wr ? b.out_slot2 + oo : nullptr, lane,
+                                      b.out_ungapped ? b.out_ungapped + b.out_uoff[k] : nullptr, b.ucap);
+        if (b.out_ungapped && lane == 0) {
+            b.out_ulen[k] = nu < b.ucap ? nu : b.ucap;
+            if (nu > b.ucap) atomicAdd(p.overflow_count + 1, 1u);
+        }
+    }
+}
+
 uint64_t general_words_for(uint32_t n1, uint32_t n2)
 {
     const uint32_t lg = (n1 > n2 ? n1 : n2) + 1, sh = (n1 > n2 ? n2 : n1) + 1;
@@ -1583,7 +1721,15 @@ uint64_t general_words_for(uint32_t n1, uint32_t n2)
 cudaError_t launch_general(const LinearParams &p, uint32_t n_list, const uint32_t *list, const uint64_t *scratch_off,
                            uint32_t *scratch, cudaStream_t stream)
 {
-    do_general_kernel<<<n_list, 256, 0, stream>>>(p, list, scratch_off, scratch);
+    constexpr uint32_t kSmem = 200 * 1024;
+    static DeviceOnce once;
+    int dev = 0;
+    if (once.pending(&dev)) {
+        cudaError_t e = cudaFuncSetAttribute(do_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        if (e != cudaSuccess) return e;
+        once.mark(dev);
+    }
+    do_general_kernel<<<n_list, kGenThreads, kSmem, stream>>>(p, list, scratch_off, scratch, kSmem);
     return cudaGetLastError();
 }
 
