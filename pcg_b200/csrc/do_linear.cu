@@ -480,10 +480,12 @@ __device__ __forceinline__ void run_chunk16q(uint32_t (&R)[H], const uint32_t (&
         }
         if (r == CH - 1 || (TAIL && r == n_iter - 1)) {
             const int sh = 2 * (CH - 1 - r);          // left-align a partial group
-            // (only registers that hold a diagonal of the band: the last lanes of a pair are partly or wholly beyond it)
+            // (All registers, also those beyond the band: storing only the band's left partially written 32-byte sectors
+            // behind — lanes are 56 bytes apart — which L2 completes by READING them back: DRAM reads 26.7 -> 33.8 GB per
+            // launch for 2 GB fewer written.  n_st = 0 still skips a lane that is wholly beyond the band and 64-byte aligned.)
 #pragma unroll
             for (int m = 0; m < H; m += 2)
-                if (m / 2 < n_st) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m] << sh, dw[m + 1] << sh);
+                if (n_st) *reinterpret_cast<uint2 *>(out + m) = make_uint2(dw[m] << sh, dw[m + 1] << sh);
             out += 32 * H;
         }
     }
@@ -572,9 +574,8 @@ __device__ __noinline__ uint32_t fill_multi16(const Geom g, int tmax, const Fill
     const char *lptr = Lb + (I0 + 1);
     const char *sptr = Sb + (J0 + H);
     uint32_t *out = slot + lane * H;
-    // register m holds diagonals qb + m and qb + m + H: pairs of registers up to the band's last diagonal are stored
-    // (config 2: the 8th lane of a pair owns diagonals 196..223 of 200 — two stores instead of seven)
-    const int n_st = min(H / 2, max(0, (g.wb - qb + 1) / 2));
+    // a lane wholly beyond the band stores nothing when that leaves no 32-byte sector half written (H = 16: 64 bytes per lane)
+    const int n_st = (H % 8 == 0 && qb >= g.wb) ? 0 : 1;
     const uint32_t sc1 = repl ? 64u : 2u, sc2 = repl ? (uint32_t)-62 : 0u;
     uint32_t p_lo[D], p_hi[D];
 #pragma unroll
