@@ -111,13 +111,13 @@ def int_issue_peak(ctx):
 
 
 def source_hash():
-    """Hash of the kernel sources: ties profiles/traffic.json (an ncu capture) to the build being timed."""
+    """Hash of the sources of the config-2 path (the dense C-linear kernels, their launch code and shared headers): ties
+    profiles/traffic.json (an ncu capture of that kernel) to the build being timed."""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(ROOT, "pcg_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in ("do_linear.cu", "do_pack16.cuh", "do_device.cuh", "do_api.cu", "do_ctx.h", "do_host.h"):
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 

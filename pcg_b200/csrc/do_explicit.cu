@@ -238,6 +238,9 @@ __device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)
                                         int n_iter, uint32_t lane_off, int lane)
 {
     constexpr int H = B / 2;
+    // bytes between the table copies of neighbouring lanes: lane 1's offset (lane 0's is 0 in either mode — testing
+    // `lane_off` itself left lane 0 on lane 1's copy and bank: every fetch took two wavefronts)
+    const uint32_t lane_step = __shfl_sync(kFullM, lane_off, 1);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         if (TAIL && r >= n_iter) break;
@@ -260,7 +263,7 @@ __device__ __forceinline__ void x_chunk(uint32_t (&w)[B], const uint32_t (&penc)
         // lane 31 / lane 0 read the staged strings.  The per-lane loads this replaces were H-way bank conflicts (lanes H
         // words apart): as many shared-memory wavefronts per iteration as all the table lookups together.
         {
-            uint32_t nv = __shfl_down_sync(kFullM, sw[tt], 1) - (lane_off ? 4u : 0u);
+            uint32_t nv = __shfl_down_sync(kFullM, sw[tt], 1) - lane_step;
             if (lane == 31) nv = sptr[r] + lane_off;
             sw[tt] = nv;
         }
@@ -403,13 +406,14 @@ __device__ __forceinline__ void x_chunk16(uint32_t (&R)[B / 2], const uint32_t (
 {
     constexpr int H = B / 2, U = H / 2, CH = x_chunk_len(B), D = x_dist<B>();
     constexpr bool HALF = CH < 8;               // the chunk is half a direction word: `phase` = second half
+    const uint32_t lane_step = __shfl_sync(kFull, lane_off, 1);       // (see x_chunk)
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
         if (TAIL && r >= n_iter) break;
         const int tt = r % H;
         const bool first = HALF ? (r == 0 && !phase) : (r % 8 == 0);       // first iteration of a direction word
         // sliding windows by shuffle (see x_chunk): the new elements, installed below once no pending fetch wants the old
-        uint32_t s_new = __shfl_down_sync(kFull, sw[tt], 1) - (lane_off ? 4u : 0u);
+        uint32_t s_new = __shfl_down_sync(kFull, sw[tt], 1) - lane_step;
         if (lane == 31) s_new = sptr[r] + lane_off;
         uint32_t l_new = __shfl_up_sync(kFull, lw[(tt + 1) % H], 1);
         if (lane == 0) l_new = lptr[r];
